@@ -1,0 +1,104 @@
+"""ctypes loader for libct_b200.so — the thin C-ABI boundary (include/ct_b200.h).
+
+The product path never falls back to CPU or eager PyTorch math: if the shared library is missing
+or the device is not an sm_100 part, importing/using the ops raises.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libct_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_float = ctypes.c_float
+
+
+class GemmArgs(ctypes.Structure):
+    """Mirror of `ct_gemm_args` in include/ct_b200.h (field order and types must match)."""
+
+    _fields_ = [
+        ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
+        ("a_mn_major", ctypes.c_int32), ("b_mn_major", ctypes.c_int32),
+        ("ab_dtype", ctypes.c_int32),
+        ("A", c_void_p), ("lda", c_i64),
+        ("B", c_void_p), ("ldb", c_i64),
+        ("C", c_void_p), ("c_dtype", ctypes.c_int32), ("ldc", c_i64),
+        ("alpha", c_float), ("beta", c_float),
+        ("bias", c_void_p),
+        ("act", ctypes.c_int32),
+        ("preact", c_void_p), ("preact_dtype", ctypes.c_int32), ("ldp", c_i64),
+        ("actgrad_src", c_void_p), ("actgrad_dtype", ctypes.c_int32),
+        ("actgrad_act", ctypes.c_int32), ("ldg", c_i64),
+        ("residual", c_void_p), ("res_dtype", ctypes.c_int32), ("ldr", c_i64),
+        ("impl", ctypes.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/ct_b200.h
+SIGNATURES = {
+    "ct_version": (c_int, []),
+    "ct_last_error": (c_int, [ctypes.c_char_p, ctypes.c_size_t]),
+    "ct_device_check": (c_int, [c_int]),
+    "ct_layernorm_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_int, c_void_p, c_void_p, c_i64, c_i64, c_float, c_void_p]),
+    "ct_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_int, c_i64, c_i64, c_void_p]),
+    "ct_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float,
+                              c_float, c_float, c_float, c_float, c_i64, c_int, c_float, c_void_p]),
+    "ct_adamw_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_float, c_float, c_float, c_float, c_float, c_i64, c_int, c_float,
+                               c_void_p]),
+    "ct_sgd_step": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float,
+                            c_float, c_int, c_void_p]),
+    "ct_cast": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_void_p]),
+    "ct_colsum": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_int, c_i64, c_i64, c_void_p]),
+    "ct_act_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_i64, c_void_p]),
+    "ct_act_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_i64,
+                           c_void_p]),
+    "ct_gemm": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
+    "ct_gemm_bias_act": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_int, c_void_p, c_int, c_i64, c_i64, c_i64, c_int, c_void_p]),
+    "ct_gemm_dgrad": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_i64,
+                              c_i64, c_i64, c_int, c_void_p]),
+    "ct_gemm_wgrad_bias": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_i64,
+                                   c_i64, c_i64, c_int, c_void_p]),
+}
+
+
+def load():
+    """Load the shared library (once) and attach prototypes. Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libct_b200.so not found at %s — run `python -m cleantransformer_b200.build` "
+                "(there is no CPU or eager fallback)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    buf = ctypes.create_string_buffer(512)
+    load().ct_last_error(buf, 512)
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (rc=%d): %s" % (what, rc, last_error()))

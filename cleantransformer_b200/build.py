@@ -1,0 +1,82 @@
+"""Build libct_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m cleantransformer_b200.build [--force] [--verbose]
+
+The shared object lands next to this file (cleantransformer_b200/libct_b200.so) so it travels with
+the repo snapshot to the GPU box; objects go to cleantransformer_b200/_build/.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libct_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest(path):
+    h = hashlib.sha1()
+    for p in [path] + sorted(
+        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))
+    ) + [os.path.join(HERE, "..", "include", "ct_b200.h")]:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile_one(src, force, verbose):
+    obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
+    stamp = obj + ".sha1"
+    dig = _digest(src)
+    if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return obj, False, ""
+    cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log = r.stdout + r.stderr
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s" % (src, log))
+    with open(stamp, "w") as f:
+        f.write(dig)
+    with open(obj + ".log", "w") as f:
+        f.write(log)
+    if verbose:
+        print(log)
+    return obj, True, log
+
+
+def build(force=False, verbose=False):
+    os.makedirs(BUILD, exist_ok=True)
+    srcs = sources()
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(lambda s: _compile_one(s, force, verbose), srcs))
+    objs = [r[0] for r in results]
+    rebuilt = any(r[1] for r in results)
+    if rebuilt or not os.path.exists(LIB):
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                      "-Xcompiler", "-fPIC"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    lib = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(lib)

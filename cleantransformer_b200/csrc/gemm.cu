@@ -1,0 +1,621 @@
+// gemm.cu — the GEMM family behind every nn.Linear / Conv1D on the hot path, forward and backward.
+//
+//   C[M,N] = epilogue(alpha * sum_k A(m,k) * B(n,k))     (see include/ct_b200.h: ct_gemm_args)
+//
+// Main kernel: persistent, warp-specialised tcgen05 GEMM for sm_100a
+//   warp 0      TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B tiles, 4-6 stage mbarrier ring)
+//   warp 1      MMA issuer    (one thread issues tcgen05.mma kind::f16, M=128 x N=BN x K=16,
+//                              fp32 accumulators in TMEM, double-buffered across tiles)
+//   warps 2..5  epilogue      (tcgen05.ld TMEM->registers, fused bias / activation / activation-grad
+//                              / residual / accumulate, 128-bit global stores or red.add for split-K)
+// Operands may be K-major (row = M|N index, K contiguous) or MN-major (row = K index, M|N
+// contiguous): forward uses K-major x K-major, dgrad K-major x MN-major, wgrad MN-major x MN-major,
+// Conv1D ([in,out] weight, modeling_gpt.py:32-46) K-major x MN-major. No transposes are
+// materialised.
+//
+// Reference lines replaced: transformer.py:37,98-102; modeling_bloom.py:79,121-122,256,267-269;
+// modeling_gpt.py:45,71,106,133-135; modeling_bert.py:238-247 and the dgrad/wgrad GEMMs autograd
+// derives from them. Tensor-pipe bound: 2*M*N*K flop per call.
+//
+// Fallback kernel: a plain SIMT tile GEMM with the same epilogue, used for tiny or TMA-unaligned
+// problems (e.g. the 28-way BERT classifier) and as an in-library cross-check (impl = 2).
+#include "ct_common.cuh"
+#include "../../include/ct_b200.h"
+#include <cstring>
+
+namespace ct {
+
+struct EpiParams {
+  int M, N;
+  void* C; int c_dtype; int64_t ldc;
+  float alpha, beta;
+  const float* bias;
+  int act;
+  void* preact; int preact_dtype; int64_t ldp;
+  const void* actgrad_src; int actgrad_dtype; int actgrad_act; int64_t ldg;
+  const void* residual; int res_dtype; int64_t ldr;
+  int vec_ok;     // all pointers 16B aligned and leading dims multiples of 8 elements
+  int atomic_out; // split-K: C += t via red.global.add.f32 (C f32, linear epilogue only)
+};
+
+__device__ __forceinline__ float ld_elem(const void* p, int dt, int64_t i) {
+  if (dt == DT_F32) return reinterpret_cast<const float*>(p)[i];
+  if (dt == DT_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  return __half2float(reinterpret_cast<const __half*>(p)[i]);
+}
+__device__ __forceinline__ void st_elem(void* p, int dt, int64_t i, float v) {
+  if (dt == DT_F32) reinterpret_cast<float*>(p)[i] = v;
+  else if (dt == DT_BF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+}
+
+// Scalar epilogue for one element (SIMT kernel and ragged edges of the tcgen05 kernel).
+__device__ __forceinline__ void epi_scalar(const EpiParams& e, int m, int n, float acc,
+                                           bool add_bias) {
+  float t = e.alpha * acc;
+  if (e.bias && add_bias) t += e.bias[n];
+  if (e.atomic_out) {
+    atomicAdd(reinterpret_cast<float*>(e.C) + (int64_t)m * e.ldc + n, t);
+    return;
+  }
+  if (e.preact) st_elem(e.preact, e.preact_dtype, (int64_t)m * e.ldp + n, t);
+  t = act_apply(t, e.act);
+  if (e.actgrad_src)
+    t *= act_grad(ld_elem(e.actgrad_src, e.actgrad_dtype, (int64_t)m * e.ldg + n), e.actgrad_act);
+  if (e.residual) t += ld_elem(e.residual, e.res_dtype, (int64_t)m * e.ldr + n);
+  if (e.beta != 0.f) t += e.beta * ld_elem(e.C, e.c_dtype, (int64_t)m * e.ldc + n);
+  st_elem(e.C, e.c_dtype, (int64_t)m * e.ldc + n, t);
+}
+
+// 32 consecutive elements of one row, 128-bit accesses.
+__device__ __forceinline__ void ld32(const void* p, int dt, int64_t off, float (&v)[32]) {
+  if (dt == DT_F32) {
+    const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 a = q[i];
+      v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+    }
+  } else if (dt == DT_BF16) {
+    const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 a = q[i];
+      float2 f;
+      f = unpack_bf16x2(a.x); v[8 * i] = f.x; v[8 * i + 1] = f.y;
+      f = unpack_bf16x2(a.y); v[8 * i + 2] = f.x; v[8 * i + 3] = f.y;
+      f = unpack_bf16x2(a.z); v[8 * i + 4] = f.x; v[8 * i + 5] = f.y;
+      f = unpack_bf16x2(a.w); v[8 * i + 6] = f.x; v[8 * i + 7] = f.y;
+    }
+  } else {
+    const __half* q = reinterpret_cast<const __half*>(p) + off;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __half2float(q[i]);
+  }
+}
+__device__ __forceinline__ void st32(void* p, int dt, int64_t off, const float (&v)[32]) {
+  if (dt == DT_F32) {
+    float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else if (dt == DT_BF16) {
+    uint4* q = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p) + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 a;
+      a.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
+      a.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+      a.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+      a.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      q[i] = a;
+    }
+  } else {
+    __half* q = reinterpret_cast<__half*>(p) + off;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) q[i] = __float2half_rn(v[i]);
+  }
+}
+
+// Epilogue for 32 consecutive columns [n0, n0+32) of row m held as fp32 accumulators.
+__device__ __forceinline__ void epi_chunk32(const EpiParams& e, int m, int n0, float (&t)[32],
+                                            bool add_bias) {
+  if (m >= e.M || n0 >= e.N) return;
+  const bool full = (n0 + 32 <= e.N) && e.vec_ok;
+  if (!full) {
+    const int lim = min(32, e.N - n0);
+    for (int j = 0; j < lim; ++j) epi_scalar(e, m, n0 + j, t[j], add_bias);
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) t[j] *= e.alpha;
+  if (e.bias && add_bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 b = __ldg(b4 + i);
+      t[4 * i] += b.x; t[4 * i + 1] += b.y; t[4 * i + 2] += b.z; t[4 * i + 3] += b.w;
+    }
+  }
+  if (e.atomic_out) {
+    float* c = reinterpret_cast<float*>(e.C) + (int64_t)m * e.ldc + n0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + 4 * i), "f"(t[4 * i]),
+                   "f"(t[4 * i + 1]), "f"(t[4 * i + 2]), "f"(t[4 * i + 3])
+                   : "memory");
+    return;
+  }
+  if (e.preact) st32(e.preact, e.preact_dtype, (int64_t)m * e.ldp + n0, t);
+  if (e.act != ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = act_apply(t[j], e.act);
+  }
+  if (e.actgrad_src) {
+    float s[32];
+    ld32(e.actgrad_src, e.actgrad_dtype, (int64_t)m * e.ldg + n0, s);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] *= act_grad(s[j], e.actgrad_act);
+  }
+  if (e.residual) {
+    float s[32];
+    ld32(e.residual, e.res_dtype, (int64_t)m * e.ldr + n0, s);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] += s[j];
+  }
+  if (e.beta != 0.f) {
+    float s[32];
+    ld32(e.C, e.c_dtype, (int64_t)m * e.ldc + n0, s);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = fmaf(e.beta, s[j], t[j]);
+  }
+  st32(e.C, e.c_dtype, (int64_t)m * e.ldc + n0, t);
+}
+
+// =================================================================================================
+// tcgen05 kernel
+// =================================================================================================
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int GEMM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct TcParams {
+  int M, N, K;
+  int a_mn, b_mn;
+  int fmt;       // 0 f16, 1 bf16
+  int split_k;   // number of K splits (>=1)
+  int group_m;   // rasterisation group (m-tiles per group)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const TcParams p, const EpiParams e) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t full_bar = bar_base;                     // STAGES x 8 B
+  const uint32_t empty_bar = bar_base + 8 * STAGES;       // STAGES x 8 B
+  const uint32_t tfull_bar = bar_base + 16 * STAGES;      // 2 x 8 B
+  const uint32_t tempty_bar = tfull_bar + 16;             // 2 x 8 B
+  const uint32_t tmem_slot = tempty_bar + 16;             // 4 B
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int k_blocks_total = (p.K + BK - 1) / BK;
+  const int kb_per_split = (k_blocks_total + p.split_k - 1) / p.split_k;
+  const int num_work = m_tiles * n_tiles * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // work item -> (m_blk, n_blk, split): m fastest inside groups of `group_m` m-tiles so that the
+  // CTAs resident at one time share a handful of A row-panels and B column-panels in L2.
+  auto decode = [&](int w, int& m_blk, int& n_blk, int& split) {
+    split = w % p.split_k;
+    int t = w / p.split_k;
+    const int per_group = p.group_m * n_tiles;
+    const int grp = t / per_group;
+    const int in_grp = t - grp * per_group;
+    const int m_first = grp * p.group_m;
+    const int gm = min(p.group_m, m_tiles - m_first);
+    m_blk = m_first + in_grp % gm;
+    n_blk = in_grp / gm;
+  };
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        int m_blk, n_blk, split;
+        decode(w, m_blk, n_blk, split);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, k_blocks_total);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          mbar_expect_tx(full_bar + 8 * s, Cfg::STAGE_BYTES);
+          const uint32_t a_dst = sA + s * A_STAGE_BYTES;
+          const uint32_t b_dst = sB + s * Cfg::B_STAGE_BYTES;
+          if (!p.a_mn) {
+            tma_load_2d(a_dst, &tmA, full_bar + 8 * s, kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(a_dst + j * (64 * BK * 2), &tmA, full_bar + 8 * s, m_blk * BM + 64 * j,
+                          kb * BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(b_dst, &tmB, full_bar + 8 * s, kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(b_dst + j * (64 * BK * 2), &tmB, full_bar + 8 * s, n_blk * BN + 64 * j,
+                          kb * BK);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(p.fmt, p.a_mn, p.b_mn, BM, BN);
+      // K-major : 8-row x 128 B swizzle atoms stacked along M/N (SBO = 1024 B); a K=16 step moves
+      //           the start address by 32 B inside the atom.
+      // MN-major: atoms are 64 (M/N) x 8 (K); SBO = 1024 B between 8-row K groups, LBO = BK*128 B
+      //           between 64-wide M/N chunks; a K=16 step moves the start address by 2048 B.
+      const uint32_t a_lbo = p.a_mn ? (BK * 128) : 0, b_lbo = p.b_mn ? (BK * 128) : 0;
+      const uint32_t a_kstep = p.a_mn ? 2048 : 32, b_kstep = p.b_mn ? 2048 : 32;
+      uint32_t it = 0;
+      uint32_t local = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++local) {
+        int m_blk, n_blk, split;
+        decode(w, m_blk, n_blk, split);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, k_blocks_total);
+        const uint32_t acc = local & 1;
+        const uint32_t acc_ph = (local >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * acc, acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t a_addr = sA + s * A_STAGE_BYTES;
+          const uint32_t b_addr = sB + s * Cfg::B_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = umma_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+            umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * s);  // smem stage reusable once these MMAs retire
+        }
+        umma_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ======================================= epilogue =======================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t local = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++local) {
+      int m_blk, n_blk, split;
+      decode(w, m_blk, n_blk, split);
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb0 + kb_per_split, k_blocks_total);
+      const uint32_t acc = local & 1;
+      const uint32_t acc_ph = (local >> 1) & 1;
+      mbar_wait(tfull_bar + 8 * acc, acc_ph);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      if (kb1 > kb0) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c * 32, r);
+          tmem_ld_wait();
+          float t[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(r[j]);
+          epi_chunk32(e, row, n_blk * BN + c * 32, t, split == 0);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// =================================================================================================
+// SIMT fallback (64x64 tile, 256 threads, 4x4 outputs per thread)
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+    gemm_simt_kernel(const void* __restrict__ A, int64_t lda, int a_mn, const void* __restrict__ B,
+                     int64_t ldb, int b_mn, int ab_dtype, int K, const EpiParams e) {
+  __shared__ float As[16][65];
+  __shared__ float Bs[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int mm, kk;
+      if (a_mn) { mm = i & 63; kk = i >> 6; } else { kk = i & 15; mm = i >> 4; }
+      float v = 0.f;
+      if (m0 + mm < e.M && k0 + kk < K)
+        v = ld_elem(A, ab_dtype, a_mn ? (int64_t)(k0 + kk) * lda + (m0 + mm)
+                                      : (int64_t)(m0 + mm) * lda + (k0 + kk));
+      As[kk][mm] = v;
+      int nn;
+      if (b_mn) { nn = i & 63; kk = i >> 6; } else { kk = i & 15; nn = i >> 4; }
+      v = 0.f;
+      if (n0 + nn < e.N && k0 + kk < K)
+        v = ld_elem(B, ab_dtype, b_mn ? (int64_t)(k0 + kk) * ldb + (n0 + nn)
+                                      : (int64_t)(n0 + nn) * ldb + (k0 + kk));
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < e.M && n < e.N) epi_scalar(e, m, n, acc[i][j], true);
+    }
+}
+
+static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+template <int BN>
+static int launch_tc(const ct_gemm_args& a, const EpiParams& e, int split_k, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2], strides[2];
+    uint32_t box[2];
+    if (!a.a_mn_major) { dims[0] = a.K; dims[1] = a.M; box[0] = BK; box[1] = BM; }
+    else               { dims[0] = a.M; dims[1] = a.K; box[0] = 64; box[1] = BK; }
+    strides[0] = 2; strides[1] = (uint64_t)a.lda * 2;
+    int r = make_tmap(&tmA, a.A, 2, 2, dims, strides, box, 1);
+    if (r) return r;
+    if (!a.b_mn_major) { dims[0] = a.K; dims[1] = a.N; box[0] = BK; box[1] = BN; }
+    else               { dims[0] = a.N; dims[1] = a.K; box[0] = 64; box[1] = BK; }
+    strides[1] = (uint64_t)a.ldb * 2;
+    r = make_tmap(&tmB, a.B, 2, 2, dims, strides, box, 1);
+    if (r) return r;
+  }
+  TcParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.a_mn = a.a_mn_major; p.b_mn = a.b_mn_major;
+  p.fmt = a.ab_dtype == DT_BF16 ? 1 : 0;
+  p.split_k = split_k;
+  p.group_m = 16;
+  static bool attr_set = false;  // benign race: idempotent
+  if (!attr_set) {
+    CT_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (a.M + BM - 1) / BM, n_tiles = (a.N + BN - 1) / BN;
+  int64_t work = (int64_t)m_tiles * n_tiles * split_k;
+  int grid = sm_count();
+  if (work < grid) grid = (int)work;
+  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p, e);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace ct
+
+using namespace ct;
+
+extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
+  CT_REQUIRE(args != nullptr, CT_ERR_BAD_ARG, "ct_gemm: null args");
+  const ct_gemm_args& a = *args;
+  CT_REQUIRE(a.A && a.B && a.C, CT_ERR_BAD_ARG, "ct_gemm: null operand");
+  CT_REQUIRE(a.M >= 0 && a.N >= 0 && a.K >= 0, CT_ERR_BAD_ARG, "ct_gemm: negative dim");
+  CT_REQUIRE(a.ab_dtype == DT_BF16 || a.ab_dtype == DT_F16, CT_ERR_UNSUPPORTED,
+             "ct_gemm: A/B must be bf16 or f16");
+  CT_REQUIRE(a.c_dtype >= 0 && a.c_dtype <= 2, CT_ERR_UNSUPPORTED, "ct_gemm: bad c_dtype");
+  CT_REQUIRE(a.beta == 0.f || a.beta == 1.f, CT_ERR_BAD_ARG, "ct_gemm: beta must be 0 or 1");
+  CT_REQUIRE(a.beta == 0.f || a.c_dtype == DT_F32, CT_ERR_UNSUPPORTED,
+             "ct_gemm: beta=1 requires f32 C");
+  CT_REQUIRE(a.act >= 0 && a.act <= 3 && a.actgrad_act >= 0 && a.actgrad_act <= 3, CT_ERR_BAD_ARG,
+             "ct_gemm: bad activation enum");
+  CT_REQUIRE(a.lda >= (a.a_mn_major ? a.M : a.K) && a.ldb >= (a.b_mn_major ? a.N : a.K) &&
+                 a.ldc >= a.N,
+             CT_ERR_BAD_ARG, "ct_gemm: leading dimension too small");
+  if (a.M == 0 || a.N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  EpiParams e;
+  e.M = a.M; e.N = a.N;
+  e.C = a.C; e.c_dtype = a.c_dtype; e.ldc = a.ldc;
+  e.alpha = a.alpha; e.beta = a.beta;
+  e.bias = a.bias; e.act = a.act;
+  e.preact = a.preact; e.preact_dtype = a.preact_dtype; e.ldp = a.ldp;
+  e.actgrad_src = a.actgrad_src; e.actgrad_dtype = a.actgrad_dtype; e.actgrad_act = a.actgrad_act;
+  e.ldg = a.ldg;
+  e.residual = a.residual; e.res_dtype = a.res_dtype; e.ldr = a.ldr;
+  e.atomic_out = 0;
+  e.vec_ok = al16(a.C) && (a.ldc % 8 == 0) && (!a.bias || al16(a.bias)) &&
+             (!a.preact || (al16(a.preact) && a.ldp % 8 == 0)) &&
+             (!a.actgrad_src || (al16(a.actgrad_src) && a.ldg % 8 == 0)) &&
+             (!a.residual || (al16(a.residual) && a.ldr % 8 == 0));
+
+  const bool tma_ok = al16(a.A) && al16(a.B) && (a.lda % 8 == 0) && (a.ldb % 8 == 0) && a.K > 0;
+  bool use_tc;
+  if (a.impl == 1) {
+    CT_REQUIRE(tma_ok, CT_ERR_UNSUPPORTED,
+               "ct_gemm: tcgen05 path needs 16-byte aligned A/B and lda/ldb multiples of 8");
+    use_tc = true;
+  } else if (a.impl == 2) {
+    use_tc = false;
+  } else {
+    use_tc = tma_ok && ((int64_t)a.M * a.N * a.K >= (1 << 18));
+  }
+
+  if (!use_tc) {
+    if (a.K == 0) {
+      // degenerate: C = epilogue(0)
+    }
+    dim3 grid((a.N + 63) / 64, (a.M + 63) / 64);
+    gemm_simt_kernel<<<grid, 256, 0, st>>>(a.A, a.lda, a.a_mn_major, a.B, a.ldb, a.b_mn_major,
+                                           a.ab_dtype, a.K, e);
+    CT_LAUNCH_OK();
+    return 0;
+  }
+
+  const int bn = (a.N > 128) ? 256 : 128;
+  const int m_tiles = (a.M + BM - 1) / BM, n_tiles = (a.N + bn - 1) / bn;
+  const int k_blocks = (a.K + BK - 1) / BK;
+  // split-K only for linear f32-accumulate epilogues (wgrad): partial sums go out via red.add
+  int split_k = 1;
+  const bool linear = a.act == ACT_NONE && !a.preact && !a.actgrad_src && !a.residual &&
+                      a.c_dtype == DT_F32;
+  const int tiles = m_tiles * n_tiles;
+  const int sms = sm_count();
+  if (linear && tiles < sms && k_blocks >= 16) {
+    split_k = (2 * sms + tiles - 1) / tiles;
+    const int max_split = k_blocks / 8;  // at least 8 k-blocks (K=512) per split
+    if (split_k > max_split) split_k = max_split;
+    if (split_k < 1) split_k = 1;
+    // make sure no split is empty
+    const int per = (k_blocks + split_k - 1) / split_k;
+    split_k = (k_blocks + per - 1) / per;
+  }
+  if (split_k > 1) {
+    e.atomic_out = 1;
+    if (a.beta == 0.f)
+      CT_CUDA_OK(cudaMemset2DAsync(a.C, (size_t)a.ldc * 4, 0, (size_t)a.N * 4, (size_t)a.M, st));
+  }
+  return bn == 256 ? launch_tc<256>(a, e, split_k, st) : launch_tc<128>(a, e, split_k, st);
+}
+
+static void init_args(ct_gemm_args& g) {
+  memset(&g, 0, sizeof(g));
+  g.alpha = 1.f;
+}
+
+extern "C" int ct_gemm_bias_act(const void* x, const void* w, int w_in_out, const float* bias,
+                                const void* residual, int res_dtype, void* y, int y_dtype,
+                                void* preact, int act, int64_t M, int64_t N, int64_t K,
+                                int ab_dtype, void* stream) {
+  ct_gemm_args g;
+  init_args(g);
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.ab_dtype = ab_dtype;
+  g.A = x; g.lda = K; g.a_mn_major = 0;
+  g.B = w; g.b_mn_major = w_in_out ? 1 : 0; g.ldb = w_in_out ? N : K;
+  g.C = y; g.c_dtype = y_dtype; g.ldc = N;
+  g.bias = bias; g.act = act;
+  g.preact = preact; g.preact_dtype = ab_dtype; g.ldp = N;
+  g.residual = residual; g.res_dtype = res_dtype; g.ldr = N;
+  return ct_gemm(&g, stream);
+}
+
+extern "C" int ct_gemm_dgrad(const void* dy, const void* w, int w_in_out, void* dx, int dx_dtype,
+                             const void* actgrad_src, int actgrad_act, int64_t M, int64_t N,
+                             int64_t K, int ab_dtype, void* stream) {
+  // dx[M,K] = dy[M,N] @ W  -> GEMM with (M, N'=K, K'=N); B(n'=k, k'=n) = W[n,k]
+  ct_gemm_args g;
+  init_args(g);
+  g.M = (int)M; g.N = (int)K; g.K = (int)N;
+  g.ab_dtype = ab_dtype;
+  g.A = dy; g.lda = N; g.a_mn_major = 0;
+  // nn.Linear W [N,K]: row = reduction index n, contiguous = output index k -> MN-major.
+  // Conv1D  W [K,N]: row = output index k, contiguous = reduction n      -> K-major.
+  g.B = w; g.b_mn_major = w_in_out ? 0 : 1; g.ldb = w_in_out ? N : K;
+  g.C = dx; g.c_dtype = dx_dtype; g.ldc = K;
+  g.actgrad_src = actgrad_src; g.actgrad_dtype = ab_dtype; g.actgrad_act = actgrad_act; g.ldg = K;
+  return ct_gemm(&g, stream);
+}
+
+extern "C" int ct_gemm_wgrad_bias(const void* dy, const void* x, int w_in_out, float* dw,
+                                  float* db, int accumulate, int64_t M, int64_t N, int64_t K,
+                                  int ab_dtype, void* stream) {
+  ct_gemm_args g;
+  init_args(g);
+  g.ab_dtype = ab_dtype;
+  g.c_dtype = DT_F32;
+  g.beta = accumulate ? 1.f : 0.f;
+  if (!w_in_out) {
+    // dW[N,K] = dy^T[N,M] @ x[M,K]: A(n,m) = dy[m,n] (MN-major), B(k,m) = x[m,k] (MN-major)
+    g.M = (int)N; g.N = (int)K; g.K = (int)M;
+    g.A = dy; g.lda = N; g.a_mn_major = 1;
+    g.B = x; g.ldb = K; g.b_mn_major = 1;
+    g.C = dw; g.ldc = K;
+  } else {
+    // Conv1D: dW[K,N] = x^T[K,M] @ dy[M,N]
+    g.M = (int)K; g.N = (int)N; g.K = (int)M;
+    g.A = x; g.lda = K; g.a_mn_major = 1;
+    g.B = dy; g.ldb = N; g.b_mn_major = 1;
+    g.C = dw; g.ldc = N;
+  }
+  int r = ct_gemm(&g, stream);
+  if (r) return r;
+  if (db) return ct_colsum(dy, ab_dtype, N, db, accumulate, M, N, stream);
+  return 0;
+}

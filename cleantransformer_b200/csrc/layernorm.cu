@@ -1,0 +1,370 @@
+// layernorm.cu — fused LayerNorm forward/backward (HBM-bound; one warp per row, 128-bit accesses,
+// fp32 statistics via warp shuffles).
+//
+// Replaces the ~9 eager elementwise/reduce kernels of CleanTransformer/transformer.py:71-89
+// (LayerNorm._mean + forward): mean = sum(x)/N; std = sqrt(mean((x-mean)^2 + eps));
+// y = w * (x - mean)/std + b. Note eps sits inside the mean, i.e. std^2 = var + eps (biased var),
+// identical to torch.nn.LayerNorm. The two-pass (mean, then centred squares) order of the
+// reference is kept.
+//
+// Algorithmic bytes per row (cols = H): fwd  H*(sizeof(x) + sizeof(y) [+ sizeof(y2)]) + 8
+//                                       bwd  H*(sizeof(dy) + sizeof(x) + sizeof(dx) [+4 dx_add]) + 8
+#include "ct_common.cuh"
+#include "../../include/ct_b200.h"
+
+namespace ct {
+
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  static __device__ __forceinline__ float4 load(const float* p) {
+    return *reinterpret_cast<const float4*>(p);
+  }
+  static __device__ __forceinline__ void store(float* p, float4 v) {
+    *reinterpret_cast<float4*>(p) = v;
+  }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 load(const __nv_bfloat16* p) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float4 v) {
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+__device__ __forceinline__ float4 load4_dyn(const void* base, int dtype, int64_t idx) {
+  if (dtype == DT_F32) return Vec4<float>::load(reinterpret_cast<const float*>(base) + idx);
+  return Vec4<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+}
+__device__ __forceinline__ void store4_dyn(void* base, int dtype, int64_t idx, float4 v) {
+  if (dtype == DT_F32)
+    Vec4<float>::store(reinterpret_cast<float*>(base) + idx, v);
+  else
+    Vec4<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(base) + idx, v);
+}
+__device__ __forceinline__ float load1_dyn(const void* base, int dtype, int64_t idx) {
+  if (dtype == DT_F32) return reinterpret_cast<const float*>(base)[idx];
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+}
+__device__ __forceinline__ void store1_dyn(void* base, int dtype, int64_t idx, float v) {
+  if (dtype == DT_F32)
+    reinterpret_cast<float*>(base)[idx] = v;
+  else
+    reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+}
+
+constexpr int LN_WARPS = 8;
+
+// ---- forward, cols == 128 * VPL (row held in registers) ------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+    ln_fwd_vec_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, void* __restrict__ y, int y_dtype,
+                      void* __restrict__ y2, int y2_dtype, float* __restrict__ mean_out,
+                      float* __restrict__ rstd_out, int64_t rows, float eps) {
+  constexpr int COLS = VPL * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * LN_WARPS;
+
+  float4 g[VPL], b[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    g[i] = Vec4<float>::load(gamma + i * 128 + lane * 4);
+    b[i] = Vec4<float>::load(beta + i * 128 + lane * 4);
+  }
+  for (int64_t row = warp; row < rows; row += nwarps) {
+    float4 v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      v[i] = load4_dyn(x, x_dtype, row * COLS + i * 128 + lane * 4);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.f / COLS);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float var = warp_sum(q) * (1.f / COLS) + eps;
+    const float rstd = rsqrtf(var);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float4 o;
+      o.x = fmaf(v[i].x * rstd, g[i].x, b[i].x);
+      o.y = fmaf(v[i].y * rstd, g[i].y, b[i].y);
+      o.z = fmaf(v[i].z * rstd, g[i].z, b[i].z);
+      o.w = fmaf(v[i].w * rstd, g[i].w, b[i].w);
+      const int64_t idx = row * COLS + i * 128 + lane * 4;
+      if (y) store4_dyn(y, y_dtype, idx, o);
+      if (y2) store4_dyn(y2, y2_dtype, idx, o);
+    }
+  }
+}
+
+// ---- forward, arbitrary cols (row re-read from L1/L2) -------------------------------------------
+__global__ void __launch_bounds__(LN_WARPS * 32)
+    ln_fwd_generic_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, void* __restrict__ y, int y_dtype,
+                          void* __restrict__ y2, int y2_dtype, float* __restrict__ mean_out,
+                          float* __restrict__ rstd_out, int64_t rows, int64_t cols, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * LN_WARPS;
+  for (int64_t row = warp; row < rows; row += nwarps) {
+    float s = 0.f;
+    for (int64_t c = lane; c < cols; c += 32) s += load1_dyn(x, x_dtype, row * cols + c);
+    const float mean = warp_sum(s) / (float)cols;
+    float q = 0.f;
+    for (int64_t c = lane; c < cols; c += 32) {
+      float d = load1_dyn(x, x_dtype, row * cols + c) - mean;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)cols + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    for (int64_t c = lane; c < cols; c += 32) {
+      float o = fmaf((load1_dyn(x, x_dtype, row * cols + c) - mean) * rstd, gamma[c], beta[c]);
+      if (y) store1_dyn(y, y_dtype, row * cols + c, o);
+      if (y2) store1_dyn(y2, y2_dtype, row * cols + c, o);
+    }
+  }
+}
+
+// ---- backward -----------------------------------------------------------------------------------
+// dx = rstd * (gy - mean(gy) - xhat * mean(gy * xhat)),  gy = gamma * dy,  xhat = (x - mean) * rstd
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (per-warp register partials -> smem ->
+// one atomicAdd per column per CTA)
+template <int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+    ln_bwd_vec_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ dy2,
+                      int dy2_dtype, const void* __restrict__ x, int x_dtype,
+                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                      const float* __restrict__ rstd_in, const void* __restrict__ dx_add,
+                      int dx_add_dtype, void* __restrict__ dx, int dx_dtype,
+                      float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows) {
+  constexpr int COLS = VPL * 128;
+  __shared__ float red[LN_WARPS][128 + 1];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * LN_WARPS + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * LN_WARPS;
+
+  float4 g[VPL], dg[VPL], db[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    g[i] = Vec4<float>::load(gamma + i * 128 + lane * 4);
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t row = warp; row < rows; row += nwarps) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float4 xh[VPL], d[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int64_t idx = row * COLS + i * 128 + lane * 4;
+      float4 xv = load4_dyn(x, x_dtype, idx);
+      if (dy) {
+        d[i] = load4_dyn(dy, dy_dtype, idx);
+        if (dy2) {
+          float4 e = load4_dyn(dy2, dy2_dtype, idx);
+          d[i].x += e.x; d[i].y += e.y; d[i].z += e.z; d[i].w += e.w;
+        }
+      } else {
+        d[i] = load4_dyn(dy2, dy2_dtype, idx);
+      }
+      xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd;
+      xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
+      dg[i].x = fmaf(d[i].x, xh[i].x, dg[i].x); dg[i].y = fmaf(d[i].y, xh[i].y, dg[i].y);
+      dg[i].z = fmaf(d[i].z, xh[i].z, dg[i].z); dg[i].w = fmaf(d[i].w, xh[i].w, dg[i].w);
+      db[i].x += d[i].x; db[i].y += d[i].y; db[i].z += d[i].z; db[i].w += d[i].w;
+      d[i].x *= g[i].x; d[i].y *= g[i].y; d[i].z *= g[i].z; d[i].w *= g[i].w;
+      s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+      s2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
+    }
+    s1 = warp_sum(s1) * (1.f / COLS);
+    s2 = warp_sum(s2) * (1.f / COLS);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int64_t idx = row * COLS + i * 128 + lane * 4;
+      float4 o;
+      o.x = rstd * (d[i].x - s1 - xh[i].x * s2);
+      o.y = rstd * (d[i].y - s1 - xh[i].y * s2);
+      o.z = rstd * (d[i].z - s1 - xh[i].z * s2);
+      o.w = rstd * (d[i].w - s1 - xh[i].w * s2);
+      if (dx_add) {
+        float4 a = load4_dyn(dx_add, dx_add_dtype, idx);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      store4_dyn(dx, dx_dtype, idx, o);
+    }
+  }
+  // cross-warp reduction of dgamma / dbeta partials, 128 columns at a time
+  if (dgamma == nullptr && dbeta == nullptr) return;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    float* dst = pass == 0 ? dgamma : dbeta;
+    if (dst == nullptr) continue;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float4 v = pass == 0 ? dg[i] : db[i];
+      __syncthreads();
+      red[wib][lane * 4 + 0] = v.x; red[wib][lane * 4 + 1] = v.y;
+      red[wib][lane * 4 + 2] = v.z; red[wib][lane * 4 + 3] = v.w;
+      __syncthreads();
+      if (threadIdx.x < 128) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) acc += red[w][threadIdx.x];
+        atomicAdd(dst + i * 128 + threadIdx.x, acc);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LN_WARPS * 32)
+    ln_bwd_generic_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ dy2,
+                          int dy2_dtype, const void* __restrict__ x, int x_dtype,
+                          const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                          const float* __restrict__ rstd_in, const void* __restrict__ dx_add,
+                          int dx_add_dtype, void* __restrict__ dx, int dx_dtype,
+                          float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
+                          int64_t cols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * LN_WARPS;
+  for (int64_t row = warp; row < rows; row += nwarps) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int64_t c = lane; c < cols; c += 32) {
+      const int64_t idx = row * cols + c;
+      float d = (dy ? load1_dyn(dy, dy_dtype, idx) : 0.f) + (dy2 ? load1_dyn(dy2, dy2_dtype, idx) : 0.f);
+      float xh = (load1_dyn(x, x_dtype, idx) - mean) * rstd;
+      if (dgamma) atomicAdd(dgamma + c, d * xh);
+      if (dbeta) atomicAdd(dbeta + c, d);
+      d *= gamma[c];
+      s1 += d;
+      s2 += d * xh;
+    }
+    s1 = warp_sum(s1) / (float)cols;
+    s2 = warp_sum(s2) / (float)cols;
+    for (int64_t c = lane; c < cols; c += 32) {
+      const int64_t idx = row * cols + c;
+      float d = (dy ? load1_dyn(dy, dy_dtype, idx) : 0.f) + (dy2 ? load1_dyn(dy2, dy2_dtype, idx) : 0.f);
+      d *= gamma[c];
+      float xh = (load1_dyn(x, x_dtype, idx) - mean) * rstd;
+      float o = rstd * (d - s1 - xh * s2);
+      if (dx_add) o += load1_dyn(dx_add, dx_add_dtype, idx);
+      store1_dyn(dx, dx_dtype, idx, o);
+    }
+  }
+}
+
+static bool dt_ok(int dt) { return dt == DT_F32 || dt == DT_BF16; }
+static bool aligned16(const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; }
+
+static int ln_grid(int64_t rows) {
+  int64_t need = (rows + LN_WARPS - 1) / LN_WARPS;
+  int64_t cap = (int64_t)sm_count() * 8;  // 8 CTAs x 8 warps per SM = full occupancy
+  if (need > cap) need = cap;
+  if (need < 1) need = 1;
+  return (int)need;
+}
+
+}  // namespace ct
+
+using namespace ct;
+
+extern "C" int ct_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta,
+                                void* y, int y_dtype, void* y2, int y2_dtype, float* mean,
+                                float* rstd, int64_t rows, int64_t cols, float eps, void* stream) {
+  CT_REQUIRE(x && gamma && beta && (y || y2), CT_ERR_BAD_ARG, "ct_layernorm_fwd: null pointer");
+  CT_REQUIRE(rows >= 0 && cols > 0, CT_ERR_BAD_ARG, "ct_layernorm_fwd: bad shape %lld x %lld",
+             (long long)rows, (long long)cols);
+  CT_REQUIRE(dt_ok(x_dtype) && (!y || dt_ok(y_dtype)) && (!y2 || dt_ok(y2_dtype)),
+             CT_ERR_UNSUPPORTED, "ct_layernorm_fwd: dtype must be f32 or bf16");
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(rows);
+  const bool vec = (cols % 128 == 0) && cols <= 1024 && aligned16(x) && aligned16(y) &&
+                   aligned16(y2) && aligned16(gamma) && aligned16(beta);
+#define CT_LN_FWD(V)                                                                           \
+  case V:                                                                                      \
+    ln_fwd_vec_kernel<V><<<grid, LN_WARPS * 32, 0, st>>>(x, x_dtype, gamma, beta, y, y_dtype,  \
+                                                         y2, y2_dtype, mean, rstd, rows, eps); \
+    break;
+  if (vec) {
+    switch ((int)(cols / 128)) {
+      CT_LN_FWD(1) CT_LN_FWD(2) CT_LN_FWD(3) CT_LN_FWD(4) CT_LN_FWD(5) CT_LN_FWD(6) CT_LN_FWD(7)
+      CT_LN_FWD(8)
+    }
+  } else {
+    ln_fwd_generic_kernel<<<grid, LN_WARPS * 32, 0, st>>>(x, x_dtype, gamma, beta, y, y_dtype, y2,
+                                                          y2_dtype, mean, rstd, rows, cols, eps);
+  }
+#undef CT_LN_FWD
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_layernorm_bwd(const void* dy, int dy_dtype, const void* dy2, int dy2_dtype,
+                                const void* x, int x_dtype, const float* gamma, const float* mean,
+                                const float* rstd, const void* dx_add, int dx_add_dtype, void* dx,
+                                int dx_dtype, float* dgamma, float* dbeta, int dgb_accumulate,
+                                int64_t rows, int64_t cols, void* stream) {
+  CT_REQUIRE((dy || dy2) && x && gamma && mean && rstd && dx, CT_ERR_BAD_ARG,
+             "ct_layernorm_bwd: null pointer");
+  CT_REQUIRE(rows >= 0 && cols > 0, CT_ERR_BAD_ARG, "ct_layernorm_bwd: bad shape");
+  CT_REQUIRE(dt_ok(x_dtype) && dt_ok(dx_dtype) && (!dy || dt_ok(dy_dtype)) &&
+                 (!dy2 || dt_ok(dy2_dtype)) && (!dx_add || dt_ok(dx_add_dtype)),
+             CT_ERR_UNSUPPORTED, "ct_layernorm_bwd: dtype must be f32 or bf16");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!dgb_accumulate) {
+    if (dgamma) CT_CUDA_OK(cudaMemsetAsync(dgamma, 0, sizeof(float) * cols, st));
+    if (dbeta) CT_CUDA_OK(cudaMemsetAsync(dbeta, 0, sizeof(float) * cols, st));
+  }
+  if (rows == 0) return 0;
+  // fewer, fatter CTAs than forward: each CTA ends with 2*cols atomics
+  int grid = ln_grid(rows);
+  const int cap = sm_count() * 2;
+  if (grid > cap) grid = cap;
+  const bool vec = (cols % 128 == 0) && cols <= 1024 && aligned16(x) && aligned16(dy) &&
+                   aligned16(dy2) && aligned16(dx) && aligned16(dx_add) && aligned16(gamma);
+#define CT_LN_BWD(V)                                                                             \
+  case V:                                                                                        \
+    ln_bwd_vec_kernel<V><<<grid, LN_WARPS * 32, 0, st>>>(dy, dy_dtype, dy2, dy2_dtype, x,        \
+                                                         x_dtype, gamma, mean, rstd, dx_add,     \
+                                                         dx_add_dtype, dx, dx_dtype, dgamma,     \
+                                                         dbeta, rows);                           \
+    break;
+  if (vec) {
+    switch ((int)(cols / 128)) {
+      CT_LN_BWD(1) CT_LN_BWD(2) CT_LN_BWD(3) CT_LN_BWD(4) CT_LN_BWD(5) CT_LN_BWD(6) CT_LN_BWD(7)
+      CT_LN_BWD(8)
+    }
+  } else {
+    ln_bwd_generic_kernel<<<grid, LN_WARPS * 32, 0, st>>>(dy, dy_dtype, dy2, dy2_dtype, x, x_dtype,
+                                                          gamma, mean, rstd, dx_add, dx_add_dtype,
+                                                          dx, dx_dtype, dgamma, dbeta, rows, cols);
+  }
+#undef CT_LN_BWD
+  CT_LAUNCH_OK();
+  return 0;
+}

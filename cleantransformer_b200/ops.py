@@ -1,0 +1,224 @@
+"""Tensor-level wrappers over the C ABI (include/ct_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every arithmetic step is a
+hand-written sm_100a kernel in libct_b200.so. Wrappers allocate outputs with torch.empty and pass
+raw data_ptr()s + the current stream. Nothing in this module computes with torch ops.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, check
+
+F32, BF16, F16 = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_GELU_ERF, ACT_GELU_TANH = 0, 1, 2, 3
+ACT_BY_NAME = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU_ERF,
+               "gelu_erf": ACT_GELU_ERF, "gelu_new": ACT_GELU_TANH, "gelu_tanh": ACT_GELU_TANH}
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
+
+
+def dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError("unsupported dtype %s" % t.dtype)
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cleantransformer_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def device_check(device=None):
+    dev = torch.cuda.current_device() if device is None else device
+    check(_lib.load().ct_device_check(int(dev)), "ct_device_check")
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, out_dtype=None, out2_dtype=None, save_stats=True):
+    """x [..., cols] -> (y, y2, mean, rstd). transformer.py:79-89."""
+    _req_cuda(x, gamma, beta)
+    cols = gamma.numel()
+    x2 = x.contiguous().view(-1, cols)
+    rows = x2.shape[0]
+    y = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device) if out_dtype is not False else None
+    y2 = torch.empty(x.shape, dtype=out2_dtype, device=x.device) if out2_dtype is not None else None
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    check(_lib.load().ct_layernorm_fwd(
+        ptr(x2), dt(x2), ptr(gamma), ptr(beta), ptr(y), dt(y) if y is not None else 0,
+        ptr(y2), dt(y2) if y2 is not None else 0, ptr(mean), ptr(rstd), rows, cols, float(eps),
+        stream()), "ct_layernorm_fwd")
+    return y, y2, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, accumulate, dy2=None, dx_add=None,
+                  dx_dtype=torch.float32):
+    """Returns dx; dgamma/dbeta (f32 [cols]) are written (accumulate=False) or += (True)."""
+    _req_cuda(x, gamma, mean, rstd)
+    cols = gamma.numel()
+    x2 = x.contiguous().view(-1, cols)
+    rows = x2.shape[0]
+    dy = dy.contiguous() if dy is not None else None
+    dy2 = dy2.contiguous() if dy2 is not None else None
+    dx_add = dx_add.contiguous() if dx_add is not None else None
+    dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
+    check(_lib.load().ct_layernorm_bwd(
+        ptr(dy), dt(dy) if dy is not None else 0, ptr(dy2), dt(dy2) if dy2 is not None else 0,
+        ptr(x2), dt(x2), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx_add),
+        dt(dx_add) if dx_add is not None else 0, ptr(dx), dt(dx), ptr(dgamma), ptr(dbeta),
+        1 if accumulate else 0, rows, cols, stream()), "ct_layernorm_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# Optimizers
+# ------------------------------------------------------------------------------------------------
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, mode=0, grad_scale=1.0,
+               shadow=None):
+    _req_cuda(p, g, m, v)
+    n = p.numel()
+    check(_lib.load().ct_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), n, lr, beta1,
+                                    beta2, eps, weight_decay, int(step), int(mode), grad_scale,
+                                    stream()), "ct_adamw_step")
+
+
+def adamw_multi(ps, gs, ms, vs, lr, beta1, beta2, eps, weight_decay, step, mode=0, grad_scale=1.0,
+                shadows=None):
+    n = len(ps)
+    if n == 0:
+        return
+    _req_cuda(*ps)
+    arr = ctypes.c_void_p * n
+    i64 = ctypes.c_int64 * n
+    P = arr(*[t.data_ptr() for t in ps])
+    G = arr(*[t.data_ptr() for t in gs])
+    M = arr(*[t.data_ptr() for t in ms])
+    V = arr(*[t.data_ptr() for t in vs])
+    S = arr(*[(t.data_ptr() if t is not None else None) for t in shadows]) if shadows else None
+    sizes = i64(*[t.numel() for t in ps])
+    check(_lib.load().ct_adamw_multi(n, P, G, M, V, S, sizes, lr, beta1, beta2, eps, weight_decay,
+                                     int(step), int(mode), grad_scale, stream()), "ct_adamw_multi")
+
+
+def sgd_step(p, g, buf, lr, momentum, dampening, weight_decay, first_step):
+    _req_cuda(p, g)
+    check(_lib.load().ct_sgd_step(ptr(p), ptr(g), ptr(buf), p.numel(), lr, momentum or 0.0,
+                                  dampening or 0.0, weight_decay or 0.0, 1 if first_step else 0,
+                                  stream()), "ct_sgd_step")
+
+
+# ------------------------------------------------------------------------------------------------
+# Elementwise
+# ------------------------------------------------------------------------------------------------
+def cast(src, dtype, out=None):
+    _req_cuda(src)
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, dtype=dtype, device=src.device)
+    check(_lib.load().ct_cast(ptr(src), dt(src), ptr(out), dt(out), src.numel(), stream()), "ct_cast")
+    return out
+
+
+def colsum(x2d, out, accumulate):
+    _req_cuda(x2d, out)
+    rows, cols = x2d.shape
+    check(_lib.load().ct_colsum(ptr(x2d), dt(x2d), x2d.stride(0), ptr(out), 1 if accumulate else 0,
+                                rows, cols, stream()), "ct_colsum")
+
+
+def act_fwd(x, act, out_dtype=None):
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
+    check(_lib.load().ct_act_fwd(ptr(x), dt(x), ptr(y), dt(y), act, x.numel(), stream()), "ct_act_fwd")
+    return y
+
+
+def act_bwd(dy, x, act, out_dtype=None):
+    dy, x = dy.contiguous(), x.contiguous()
+    dx = torch.empty(x.shape, dtype=out_dtype or dy.dtype, device=x.device)
+    check(_lib.load().ct_act_bwd(ptr(dy), dt(dy), ptr(x), dt(x), ptr(dx), dt(dx), act, x.numel(),
+                                 stream()), "ct_act_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, alpha=1.0,
+         beta=0.0, bias=None, act=ACT_NONE, preact=None, actgrad_src=None, actgrad_act=ACT_NONE,
+         residual=None, impl=0):
+    """C[M,N] = epilogue(alpha * A(m,k) B(n,k)); A, B are 2-D row-major storage tensors:
+    K-major operand -> [rows=M|N, K]; MN-major operand -> [rows=K, M|N]."""
+    _req_cuda(A, B)
+    assert A.dim() == 2 and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1
+    assert A.dtype == B.dtype
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+    assert out.dim() == 2 and out.stride(1) == 1
+    g = GemmArgs()
+    g.M, g.N, g.K = M, N, K
+    g.a_mn_major, g.b_mn_major = int(a_mn), int(b_mn)
+    g.ab_dtype = dt(A)
+    g.A, g.lda = A.data_ptr(), A.stride(0)
+    g.B, g.ldb = B.data_ptr(), B.stride(0)
+    g.C, g.c_dtype, g.ldc = out.data_ptr(), dt(out), out.stride(0)
+    g.alpha, g.beta = alpha, beta
+    g.bias = ptr(bias)
+    g.act = act
+    if preact is not None:
+        g.preact, g.preact_dtype, g.ldp = preact.data_ptr(), dt(preact), preact.stride(0)
+    if actgrad_src is not None:
+        g.actgrad_src, g.actgrad_dtype, g.ldg = actgrad_src.data_ptr(), dt(actgrad_src), actgrad_src.stride(0)
+        g.actgrad_act = actgrad_act
+    if residual is not None:
+        g.residual, g.res_dtype, g.ldr = residual.data_ptr(), dt(residual), residual.stride(0)
+    g.impl = impl
+    check(_lib.load().ct_gemm(ctypes.byref(g), stream()), "ct_gemm")
+    return out
+
+
+def linear_fwd(x2d, w, bias=None, act=ACT_NONE, residual=None, out_dtype=torch.bfloat16,
+               save_preact=False, w_in_out=False, impl=0):
+    """y = act(x @ W^T + b) (+ residual). W is [N,K] (nn.Linear) or [K,N] (Conv1D, w_in_out)."""
+    M, K = x2d.shape
+    N = w.shape[1] if w_in_out else w.shape[0]
+    pre = torch.empty((M, N), dtype=x2d.dtype, device=x2d.device) if save_preact else None
+    y = gemm(x2d, w, M, N, K, a_mn=False, b_mn=bool(w_in_out), out_dtype=out_dtype, bias=bias,
+             act=act, preact=pre, residual=residual, impl=impl)
+    return y, pre
+
+
+def linear_dgrad(dy2d, w, out_dtype=torch.bfloat16, actgrad_src=None, actgrad_act=ACT_NONE,
+                 w_in_out=False, impl=0):
+    """dx[M,K] = dy[M,N] @ W (optionally * act'(actgrad_src))."""
+    M, N = dy2d.shape
+    K = w.shape[0] if w_in_out else w.shape[1]
+    return gemm(dy2d, w, M, K, N, a_mn=False, b_mn=not w_in_out, out_dtype=out_dtype,
+                actgrad_src=actgrad_src, actgrad_act=actgrad_act, impl=impl)
+
+
+def linear_wgrad(dy2d, x2d, dw, db=None, accumulate=False, w_in_out=False, impl=0):
+    """dW (+)= dy^T @ x into the f32 tensor dw ([N,K] or [K,N]); db (+)= colsum(dy)."""
+    M, N = dy2d.shape
+    K = x2d.shape[1]
+    if not w_in_out:
+        gemm(dy2d, x2d, N, K, M, a_mn=True, b_mn=True, out=dw, beta=1.0 if accumulate else 0.0, impl=impl)
+    else:
+        gemm(x2d, dy2d, K, N, M, a_mn=True, b_mn=True, out=dw, beta=1.0 if accumulate else 0.0, impl=impl)
+    if db is not None:
+        colsum(dy2d, db, accumulate)

@@ -1,0 +1,152 @@
+/* ct_b200.h — C ABI of libct_b200.so: the B200 (sm_100a) implementation of CleanTransformer's
+ * dense forward/backward + optimizer + gradient all-reduce hot path.
+ *
+ * The reference (firechecking/CleanTransformer) has no FFI layer: the path sits behind Python
+ * classes that call PyTorch ops. Each entry point below replaces the PyTorch-op sequence of the
+ * cited reference lines (paths relative to the reference root) and is what a ctypes binding in the
+ * reference's own modules would call.
+ *
+ * Conventions
+ *   - every tensor argument is a raw DEVICE pointer owned by the caller (PyTorch); the library never
+ *     frees or retains it past the call. Only the ct_comm_* buffers are library-owned.
+ *   - dtype enum: 0 = f32, 1 = bf16, 2 = f16.   activation enum: 0 none, 1 relu, 2 gelu_erf,
+ *     3 gelu_tanh.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises,
+ *     nothing touches the legacy default stream; calls are CUDA-graph capturable unless noted.
+ *   - return 0 on success, >0 = cudaError_t, <0 = library code (-1 bad argument/shape,
+ *     -2 unsupported dtype/arch, -3 workspace too small, -4 comm not initialised). The message is
+ *     available per calling thread through ct_last_error(). Re-entrant: callable concurrently from
+ *     the Python main thread and PyTorch's autograd thread.
+ */
+#ifndef CT_B200_H_
+#define CT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CT_B200_VERSION 100
+
+#define CT_F32 0
+#define CT_BF16 1
+#define CT_F16 2
+
+#define CT_ACT_NONE 0
+#define CT_ACT_RELU 1      /* transformer.py:100 */
+#define CT_ACT_GELU_ERF 2  /* modeling_bert.py:229 (torch.nn.GELU) */
+#define CT_ACT_GELU_TANH 3 /* modeling_bloom.py:335-345, modeling_gpt.py:112-122 */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int ct_version(void);
+int ct_last_error(char* buf, size_t n);
+/* 0 only if `device` is an sm_100 part (B200). */
+int ct_device_check(int device);
+
+/* ---- LayerNorm: CleanTransformer/transformer.py:61-89 (LayerNorm._mean / forward) ----------- *
+ * y = gamma * (x - mean) / sqrt(mean((x-mean)^2 + eps)) + beta over the last `cols` elements.
+ * x: [rows, cols] f32 or bf16. Optional second output y2 (e.g. a bf16 copy that feeds the next
+ * GEMM while y stays f32). mean/rstd ([rows] f32) may be NULL for inference. */
+int ct_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y,
+                     int y_dtype, void* y2, int y2_dtype, float* mean, float* rstd, int64_t rows,
+                     int64_t cols, float eps, void* stream);
+/* Backward of the above (what autograd derives from transformer.py:86-89).
+ * dx = (dx_add ? dx_add : 0) + dLN/dx ; dgamma/dbeta are ACCUMULATED (+=) into f32 buffers when
+ * dgb_accumulate != 0, else overwritten. dy may be NULL only if dy2 is given; when both dy and dy2
+ * are non-NULL the incoming gradient is their sum (two consumers of the LN output). */
+int ct_layernorm_bwd(const void* dy, int dy_dtype, const void* dy2, int dy2_dtype, const void* x,
+                     int x_dtype, const float* gamma, const float* mean, const float* rstd,
+                     const void* dx_add, int dx_add_dtype, void* dx, int dx_dtype, float* dgamma,
+                     float* dbeta, int dgb_accumulate, int64_t rows, int64_t cols, void* stream);
+
+/* ---- optimizers: CleanTransformer/optimizer.py ---------------------------------------------- *
+ * One vectorised kernel over a flat f32 arena (p, g, m, v all [n]).
+ * mode 0 = decoupled weight decay, the arithmetic of torch.optim.AdamW which the examples call
+ *          (examples/ft_bloom.py:19,70,90);
+ * mode 1 = the reference's own class, optimizer.py:71-97: coupled L2 (g += wd*p written back to g),
+ *          m_hat/(sqrt(v_hat)+eps), `step` is the reference's counter which starts at 1.
+ * grad_scale multiplies g on load (1/world for a summed all-reduce; 1.0 otherwise).
+ * p_shadow (nullable): bf16 copy of the updated parameters for the next forward's GEMMs. */
+int ct_adamw_step(float* p, float* g, float* m, float* v, void* p_shadow_bf16, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int64_t step, int mode,
+                  float grad_scale, void* stream);
+/* Same arithmetic over `ntensors` separate tensors (host arrays of device pointers). */
+int ct_adamw_multi(int ntensors, float* const* p, float* const* g, float* const* m, float* const* v,
+                   void* const* p_shadow_bf16, const int64_t* sizes, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int64_t step, int mode,
+                   float grad_scale, void* stream);
+/* optimizer.py:28-50 (SGD.step): g += wd*p; buf = first ? g : momentum*buf + (1-dampening)*g;
+ * g = buf; p -= lr*g. `buf` may be NULL when momentum == 0. g is rewritten like the reference. */
+int ct_sgd_step(float* p, float* g, float* buf, int64_t n, float lr, float momentum,
+                float dampening, float weight_decay, int first_step, void* stream);
+
+/* ---- elementwise helpers --------------------------------------------------------------------- */
+/* dst[i] = (dst_dtype) src[i]  (autocast's parameter/activation casts) */
+int ct_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* out[j] (+)= sum_i x[i, j]  — bias gradients (rows x cols, row stride ld elements) */
+int ct_colsum(const void* x, int x_dtype, int64_t ld, float* out, int accumulate, int64_t rows,
+              int64_t cols, void* stream);
+/* y = act(x) and dx = dy * act'(x): modeling_bloom.py:335-363, modeling_gpt.py:112-122 */
+int ct_act_fwd(const void* x, int x_dtype, void* y, int y_dtype, int act, int64_t n, void* stream);
+int ct_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx, int dx_dtype,
+               int act, int64_t n, void* stream);
+
+/* ---- GEMM family (tcgen05 / TMEM / TMA): every nn.Linear / Conv1D on the path ---------------- *
+ * C[M,N] = epilogue( alpha * sum_k A(m,k) * B(n,k) )
+ *   a_mn_major = 0: A stored [M rows][K] with K contiguous (row stride lda elements)
+ *   a_mn_major = 1: A stored [K rows][M] with M contiguous (row stride lda)      — "A transposed"
+ *   b_mn_major likewise for B over (N, K).
+ * epilogue, in order:  t = alpha*acc + bias[n];  if (preact) preact[m,n] = t;  t = act(t);
+ *   if (actgrad_src) t *= act'(actgrad_src[m,n]);  if (residual) t += residual[m,n];
+ *   C[m,n] = t + beta * C_old[m,n]   (beta in {0,1}; beta=1 needs c_dtype f32).
+ * Covers: nn.Linear fwd (transformer.py:37,98-102; modeling_bloom.py:79,121,256,267;
+ * modeling_bert.py:238-247), Conv1D fwd with its [in,out] weight via b_mn_major=1
+ * (modeling_gpt.py:32-46), and the dgrad / wgrad GEMMs autograd derives from them. */
+typedef struct {
+  int32_t M, N, K;
+  int32_t a_mn_major, b_mn_major;
+  int32_t ab_dtype; /* CT_BF16 or CT_F16 */
+  const void* A;
+  int64_t lda;
+  const void* B;
+  int64_t ldb;
+  void* C;
+  int32_t c_dtype;
+  int64_t ldc;
+  float alpha, beta;
+  const float* bias; /* [N] or NULL */
+  int32_t act;
+  void* preact; /* nullable, [M,N] */
+  int32_t preact_dtype;
+  int64_t ldp;
+  const void* actgrad_src; /* nullable, [M,N]: multiply by act'(src) with `actgrad_act` */
+  int32_t actgrad_dtype;
+  int32_t actgrad_act;
+  int64_t ldg;
+  const void* residual; /* nullable, [M,N] */
+  int32_t res_dtype;
+  int64_t ldr;
+  int32_t impl; /* 0 auto, 1 force tcgen05, 2 force the SIMT kernel (small/unaligned shapes) */
+} ct_gemm_args;
+int ct_gemm(const ct_gemm_args* args, void* stream);
+
+/* Named wrappers matching SURVEY.md §8 b3.
+ * y[M,N] = act(x[M,K] @ w^T + bias) (+ residual); w is [N,K] (nn.Linear) or, with w_in_out = 1,
+ * [K,N] (Conv1D). */
+int ct_gemm_bias_act(const void* x, const void* w, int w_in_out, const float* bias,
+                     const void* residual, int res_dtype, void* y, int y_dtype, void* preact,
+                     int act, int64_t M, int64_t N, int64_t K, int ab_dtype, void* stream);
+/* dx[M,K] = dy[M,N] @ w   (w [N,K], or [K,N] when w_in_out) ; optional dx *= act'(actgrad_src) */
+int ct_gemm_dgrad(const void* dy, const void* w, int w_in_out, void* dx, int dx_dtype,
+                  const void* actgrad_src, int actgrad_act, int64_t M, int64_t N, int64_t K,
+                  int ab_dtype, void* stream);
+/* dw (+)= dy^T @ x  as f32 [N,K] (or [K,N] when w_in_out);  db (+)= colsum(dy) when db != NULL */
+int ct_gemm_wgrad_bias(const void* dy, const void* x, int w_in_out, float* dw, float* db,
+                       int accumulate, int64_t M, int64_t N, int64_t K, int ab_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CT_B200_H_ */
