@@ -1,0 +1,255 @@
+"""Generate tests/golden/*.pt by importing and running the REAL reference (read-only at
+/root/reference) in the build container. The reference is pure Python and cannot travel to the GPU
+box, so its live outputs on small seeded cases are committed as fixtures; tests/test_oracle_golden.py
+pins oracle/ct_oracle.py against them, and the GPU parity tests then compare the CUDA path with the
+oracle.
+
+    PYTHONDONTWRITEBYTECODE=1 python tools/make_golden.py
+
+Cases mirror the reference's own self-checks where it has them (transformer.py:134-156 seed 999,
+optimizer.py:100-132) and SURVEY.md §8 d2 shapes scaled down.
+"""
+import os
+import sys
+import types
+
+sys.dont_write_bytecode = True
+REF = os.environ.get("CT_REFERENCE", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REF)
+
+# modeling_bert imports CleanTransformer.tokenizers which needs `toolz` (not installed):
+# 2-function stand-in, only so the module imports (tokenizers are not on the hot path).
+if "toolz" not in sys.modules:
+    import itertools
+
+    tz = types.ModuleType("toolz")
+    tz.concat = lambda seqs: itertools.chain.from_iterable(seqs)
+
+    def sliding_window(n, seq):
+        seq = list(seq)
+        return [tuple(seq[i:i + n]) for i in range(len(seq) - n + 1)]
+
+    tz.sliding_window = sliding_window
+    sys.modules["toolz"] = tz
+
+import torch  # noqa: E402
+
+from CleanTransformer import transformer as rt  # noqa: E402
+from CleanTransformer import optimizer as ropt  # noqa: E402
+from CleanTransformer.models import modeling_bloom as rbloom  # noqa: E402
+from CleanTransformer.models import modeling_gpt as rgpt  # noqa: E402
+from CleanTransformer.models import modeling_bert as rbert  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def reinit(model, seed=999, std=0.02):
+    """SURVEY.md §8 d2 weight init: matrices ~ N(0, 0.02), biases 0, LayerNorm w=1 b=0."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() >= 2:
+                p.copy_(torch.randn(p.shape, generator=g) * std)
+            elif name.endswith("weight"):
+                p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))  # LN gamma: not all-ones
+            else:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))        # biases / LN beta: non-zero
+    return model
+
+
+def sd_of(model):
+    return {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+
+def save(name, obj):
+    path = os.path.join(OUT, name + ".pt")
+    torch.save(obj, path)
+    print("%-28s %8.1f KB" % (name, os.path.getsize(path) / 1024))
+
+
+def golden_layernorm():
+    torch.manual_seed(999)  # transformer.py:134-141 (layernorm_sample)
+    x = torch.rand((3, 4, 6))
+    ln = rt.LayerNorm([4, 6])
+    y = ln(x)
+    torch.manual_seed(5)
+    x2 = torch.randn(2, 5, 128)
+    ln2 = rt.LayerNorm(128, eps=1e-12)
+    with torch.no_grad():
+        ln2.weight.copy_(torch.randn(128)); ln2.bias.copy_(torch.randn(128))
+    x2r = x2.clone().requires_grad_(True)
+    y2 = ln2(x2r)
+    dy2 = torch.randn_like(y2)
+    y2.backward(dy2)
+    save("layernorm", {"x": x, "y": y.detach(), "x2": x2, "w2": ln2.weight.detach().clone(),
+                       "b2": ln2.bias.detach().clone(), "eps2": 1e-12, "y2": y2.detach(), "dy2": dy2,
+                       "dx2": x2r.grad.clone(), "dw2": ln2.weight.grad.clone(), "db2": ln2.bias.grad.clone()})
+
+
+def golden_generic_block():
+    torch.manual_seed(999)  # transformer.py:144-151 (t_TransformerBlock)
+    cfg = rt.ExampleConfig()
+    blk = rt.TransformerBlock(cfg).eval()
+    q = torch.rand((3, 4, cfg.hidden_size))
+    r = blk(q)
+    # attention with an additive mask (BERT-style (1-m)*-1e4, modeling_bert.py:303-304)
+    att = blk.attention
+    m = torch.tensor([[1, 1, 1, 0], [1, 1, 0, 0], [1, 1, 1, 1]], dtype=torch.float32)
+    add = (1.0 - m[:, None, None, :]) * -10000.0
+    a = att(q, add)
+    save("generic_block", {"x": q, "sd": sd_of(blk), "y": r.detach(), "mask": m, "att_masked": a.detach(),
+                           "n_head": cfg.num_attention_heads, "eps": cfg.layer_norm_epsilong})
+
+
+def golden_gelu():
+    torch.manual_seed(3)
+    x = torch.randn(4, 33) * 2
+    g = torch.randn(4, 33)
+    save("gelu", {"x": x, "g": g, "bloom_fwd": rbloom.bloom_gelu_forward(x),
+                  "bloom_back": rbloom.bloom_gelu_back(g, (x,)),
+                  "gelu_new": rgpt.NewGELUActivation()(x)})
+
+
+def golden_bloom():
+    cfg = rbloom.BloomConfig(vocab_size=97, hidden_size=64, n_layer=2, num_attention_heads=8)
+    torch.manual_seed(999)
+    model = reinit(rbloom.BloomForCausalLM(cfg))
+    model._tie_weight()
+    g = torch.Generator().manual_seed(1000)
+    B, S = 3, 12
+    ids = torch.randint(3, 97, (B, S), generator=g)
+    lens = [12, 7, 9]
+    mask = torch.zeros(B, S, dtype=torch.long)
+    for b, n in enumerate(lens):
+        mask[b, :n] = 1
+        ids[b, n:] = 3  # right padding with pad id 3 (ft_bloom.py:125)
+    labels = ids.clone()  # ft_bloom.py:52: labels include pads
+    model.train()  # GeLUFunction path (modeling_bloom.py:301-302); dropouts are p=0
+    model.zero_grad()
+    (loss, logits, hidden), kv = model(input_ids=ids, attention_mask=mask, labels=labels)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    # eval + cache: prefill on the first 8 tokens then one decode step (left-over rows all valid)
+    model.eval()
+    with torch.no_grad():
+        full_mask = torch.ones(B, 9, dtype=torch.long)
+        (lg_full, _), _ = model(input_ids=ids[:, :9], attention_mask=full_mask)
+        (lg_pre, _), kv = model(input_ids=ids[:, :8], attention_mask=full_mask[:, :8])
+        (lg_dec, _), kv2 = model(input_ids=ids[:, 8:9], attention_mask=full_mask, k_v_pasts=kv)
+    save("bloom_tiny", {
+        "cfg": {"vocab_size": 97, "hidden_size": 64, "n_layer": 2, "num_attention_heads": 8,
+                "layer_norm_epsilon": cfg.layer_norm_epsilon},
+        "sd": sd_of(model), "ids": ids, "mask": mask, "labels": labels,
+        "loss": loss.detach(), "logits": logits.detach(), "hidden": hidden.detach(), "grads": grads,
+        "alibi": rbloom.build_alibi_tensor(mask, 8, torch.float32),
+        "logits_full9": lg_full, "logits_prefill8": lg_pre, "logits_decode": lg_dec,
+        "kv_shape": list(kv2[0][0].shape),
+    })
+
+
+def golden_gpt():
+    out = {}
+    for version in ("gpt2", "gpt"):
+        cfg = rgpt.GPTConfig(vocab_size=101, n_embd=48, n_positions=64, n_layer=2, n_head=4, n_ctx=64,
+                             afn="gelu_new")
+        torch.manual_seed(999)
+        model = reinit(rgpt.GPTLMHeadModel(cfg, version=version)).eval()
+        model._tie_weights()
+        g = torch.Generator().manual_seed(999)
+        B, P = 3, 8
+        ids = torch.randint(1, 101, (B, P), generator=g)
+        lens = [8, 5, 6]
+        mask = torch.zeros(B, P, dtype=torch.long)
+        for b, n in enumerate(lens):  # LEFT padding with 0 (inference_gpt2.py:55,59)
+            mask[b, P - n:] = 1
+            ids[b, :P - n] = 0
+        with torch.no_grad():
+            (logits, hidden), kv = model(ids, attention_mask=mask)
+            gen = model.generate(ids, attention_mask=mask,
+                                 generation_configs={"beam_size": 1, "do_sample": False, "max_gen_len": 6,
+                                                     "end_ids": None, "pad_id": 0, "no_repeat_ngram_size": 0})
+        # block-level fwd/bwd (config 1 shape scaled down): eval because of Dropout(0.5) gpt:136
+        blk = model.gpt.blocks[0]
+        torch.manual_seed(0)
+        x = torch.randn(2, 16, 48, requires_grad=True)
+        y, kvb = blk(x)
+        torch.manual_seed(1)
+        dy = torch.randn_like(y)
+        model.zero_grad()
+        y.backward(dy)
+        bgr = {k: p.grad.detach().clone() for k, p in blk.named_parameters()}
+        out[version] = {"sd": sd_of(model), "ids": ids, "mask": mask, "logits": logits, "hidden": hidden,
+                        "generated": gen, "blk_x": x.detach().clone(), "blk_y": y.detach(), "blk_dy": dy,
+                        "blk_dx": x.grad.clone(), "blk_grads": bgr,
+                        "blk_k": kvb[0].detach(), "blk_v": kvb[1].detach()}
+    out["cfg"] = {"vocab_size": 101, "n_embd": 48, "n_positions": 64, "n_layer": 2, "n_head": 4, "n_ctx": 64,
+                  "layer_norm_epsilon": 1e-5, "afn": "gelu_new"}
+    save("gpt_tiny", out)
+
+
+def golden_bert():
+    cfg = rbert.BertConfig(vocab_size=120, hidden_size=48, num_hidden_layers=2, num_attention_heads=4,
+                           intermediate_size=96, max_position_embeddings=32, num_labels=5)
+    torch.manual_seed(999)
+    model = reinit(rbert.BertForSequenceClassification(cfg)).eval()
+    g = torch.Generator().manual_seed(999)
+    B, S = 3, 10
+    ids = torch.randint(1, 120, (B, S), generator=g)
+    lens = [10, 6, 8]
+    mask = torch.zeros(B, S)
+    for b, n in enumerate(lens):
+        mask[b, :n] = 1.0
+        ids[b, n:] = 0
+    seg = torch.zeros(B, S, dtype=torch.long)
+    pos = torch.arange(S)
+    with torch.no_grad():
+        logits = model(ids, mask, seg, pos)
+        hidden, pooled = model.bert(ids, mask, seg, pos)
+    save("bert_tiny", {"cfg": {"vocab_size": 120, "hidden_size": 48, "num_hidden_layers": 2,
+                               "num_attention_heads": 4, "intermediate_size": 96,
+                               "max_position_embeddings": 32, "num_labels": 5, "layer_norm_eps": cfg.layer_norm_eps},
+                       "sd": sd_of(model), "ids": ids, "mask": mask, "seg": seg, "pos": pos,
+                       "logits": logits, "hidden": hidden, "pooled": pooled})
+
+
+def golden_optim():
+    torch.manual_seed(999)
+    p0 = [torch.rand(3, 4), torch.rand(4), torch.rand(37)]
+    grads = [[torch.randn_like(p) for p in p0] for _ in range(4)]
+
+    def run(make_opt):
+        ps = [p.clone().requires_grad_(True) for p in p0]
+        opt = make_opt(ps)
+        traj = []
+        for step_g in grads:
+            for p, g in zip(ps, step_g):
+                p.grad = g.clone()
+            opt.step()
+            traj.append([p.detach().clone() for p in ps])
+        return traj, opt
+
+    # the reference's own AdamW (optimizer.py:53-97) — must be given a LIST
+    ref_adam, o = run(lambda ps: ropt.AdamW(ps, lr=0.01, weight_decay=0.01))
+    ref_adam_m = [m.clone() for m in o.momentum_buffer]
+    ref_adam_v = [v.clone() for v in o.rmsp_buffer]
+    ref_adam_nowd, _ = run(lambda ps: ropt.AdamW(ps, lr=0.01))
+    ref_sgd, _ = run(lambda ps: ropt.SGD(ps, lr=0.01, weight_decay=0.01, momentum=0.9))
+    ref_sgd_plain, _ = run(lambda ps: ropt.SGD(ps, lr=0.01))
+    torch_adamw, _ = run(lambda ps: torch.optim.AdamW(ps, lr=0.01, weight_decay=0.01))
+    torch_sgd, _ = run(lambda ps: torch.optim.SGD(ps, lr=0.01, weight_decay=0.01, momentum=0.9))
+    save("optim", {"p0": p0, "grads": grads, "ref_adamw": ref_adam, "ref_adamw_m": ref_adam_m,
+                   "ref_adamw_v": ref_adam_v, "ref_adamw_nowd": ref_adam_nowd, "ref_sgd": ref_sgd,
+                   "ref_sgd_plain": ref_sgd_plain, "torch_adamw": torch_adamw, "torch_sgd": torch_sgd})
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    golden_layernorm()
+    golden_generic_block()
+    golden_gelu()
+    golden_bloom()
+    golden_gpt()
+    golden_bert()
+    golden_optim()
