@@ -40,6 +40,37 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
+class AttnArgs(ctypes.Structure):
+    """Mirror of `ct_attn_args`."""
+
+    _fields_ = [
+        ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("Sq", ctypes.c_int32), ("Sk", ctypes.c_int32),
+        ("D", ctypes.c_int32), ("dtype", ctypes.c_int32),
+        ("q", c_void_p), ("q_sb", c_i64), ("q_sh", c_i64), ("q_ss", c_i64),
+        ("k", c_void_p), ("k_sb", c_i64), ("k_sh", c_i64), ("k_ss", c_i64),
+        ("v", c_void_p), ("v_sb", c_i64), ("v_sh", c_i64), ("v_ss", c_i64),
+        ("o", c_void_p), ("o_sb", c_i64), ("o_sh", c_i64), ("o_ss", c_i64),
+        ("lse2", c_void_p),
+        ("scale", c_float), ("causal", ctypes.c_int32), ("causal_fill", c_float),
+        ("kbias2", c_void_p), ("kb_sb", c_i64), ("kb_sh", c_i64),
+        ("first_valid", c_void_p),
+        ("impl", ctypes.c_int32),
+    ]
+
+
+class AttnBwdArgs(ctypes.Structure):
+    """Mirror of `ct_attn_bwd_args`."""
+
+    _fields_ = [
+        ("f", AttnArgs),
+        ("dout", c_void_p),
+        ("dq", c_void_p), ("dq_sb", c_i64), ("dq_sh", c_i64), ("dq_ss", c_i64),
+        ("dk", c_void_p), ("dk_sb", c_i64), ("dk_sh", c_i64), ("dk_ss", c_i64),
+        ("dv", c_void_p), ("dv_sb", c_i64), ("dv_sh", c_i64), ("dv_ss", c_i64),
+        ("delta", c_void_p), ("dq_accum", c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/ct_b200.h
 SIGNATURES = {
     "ct_version": (c_int, []),
@@ -67,6 +98,20 @@ SIGNATURES = {
                                  c_int, c_void_p, c_int, c_i64, c_i64, c_i64, c_int, c_void_p]),
     "ct_gemm_dgrad": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_i64,
                               c_i64, c_i64, c_int, c_void_p]),
+    "ct_attn_fwd": (c_int, [ctypes.POINTER(AttnArgs), c_void_p]),
+    "ct_attn_bwd": (c_int, [ctypes.POINTER(AttnBwdArgs), c_void_p]),
+    "ct_attn_mask_prep": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
+    "ct_embedding_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_void_p]),
+    "ct_embedding_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p]),
+    "ct_cross_entropy_fwd": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p, c_i64, c_void_p,
+                                     c_void_p, c_i64, c_i64, c_i64, c_int, c_i64, c_void_p]),
+    "ct_scale_by_scalar": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p]),
+    "ct_comm_init": (c_int, [c_int, c_int, c_int, ctypes.c_size_t, ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
+    "ct_comm_connect": (c_int, [c_void_p, c_void_p]),
+    "ct_allreduce_bucket": (c_int, [c_i64, c_i64, c_float, c_int, c_int, c_void_p]),
+    "ct_broadcast": (c_int, [c_i64, c_i64, c_int, c_void_p]),
+    "ct_comm_finalize": (c_int, []),
     "ct_gemm_wgrad_bias": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_i64,
                                    c_i64, c_i64, c_int, c_void_p]),
 }

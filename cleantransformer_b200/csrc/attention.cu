@@ -1,0 +1,1064 @@
+// attention.cu — fused QK^T -> (+ALiBi / masks) -> online softmax -> PV, forward and backward.
+//
+// Replaces the materialised [B,H,Sq,Sk] score pipeline of
+//   CleanTransformer/models/modeling_bloom.py:99-116, modeling_gpt.py:83-103, transformer.py:41-57
+// (see include/ct_b200.h for the exact score definition shared by all three variants).
+//
+// tcgen05 forward  (head_dim 64): CTA = 128 query rows of one (b,h); warp 0 TMA producer (Q once, K/V
+//   double-buffered 128-key tiles), warp 1 single-thread MMA issuer (S = Q K^T into one of two TMEM
+//   score buffers; O_tile = P V into the score buffer that was just drained), warps 2..5 softmax: one
+//   thread per query row (no shuffles), two TMEM passes (max, then exp2 + P -> swizzled smem),
+//   running O kept in registers. 2 CTAs/SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax
+//   overlaps the other's MMAs.
+// tcgen05 backward (head_dim 64): CTA = 128 keys of one (b,h), loops over query tiles:
+//   S^T = K Q^T, dP^T = V dO^T (TMEM) -> P^T, dS^T (bf16, swizzled smem) -> dV += P^T dO,
+//   dK += dS^T Q (TMEM accumulators), dQ_tile = dS K -> red.global.add.f32 into an fp32 dQ workspace.
+//   The Q/dO tiles are read through two descriptor views (K-major for the first pair of MMAs,
+//   MN-major for the second), dS^T likewise (K-major for dK, MN-major for dQ): no transposes.
+// SIMT kernels: any head_dim <= 128 and tiny shapes (golden-vector tests, q_len = 1 decode).
+//
+// FLOPs: forward 4*Sq*Sk*D per (b,h) dense (half that under the causal mask); backward 2.5x.
+#include "ct_common.cuh"
+#include "../../include/ct_b200.h"
+#include <cfloat>
+#include <cstring>
+
+namespace ct {
+
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct AttnP {
+  int B, H, Sq, Sk;
+  int fmt;  // 0 f16, 1 bf16
+  float sl2;           // scale * log2e
+  float scale;
+  int causal;
+  float causal_fill2;  // causal_fill * log2e (may be -inf)
+  int off;             // Sk - Sq
+  const float* kbias2; int64_t kb_sb, kb_sh;
+  const int32_t* first_valid;
+  void* o; int64_t o_sb, o_sh, o_ss;
+  float* lse2;
+};
+
+// score in the log2 domain for element (query i, key j) given the raw dot product
+__device__ __forceinline__ float score2(float acc, float sl2, float kb, bool future, float cf2,
+                                        bool oob) {
+  float v = future ? (cf2 + kb) : fmaf(acc, sl2, kb);
+  v = fmaxf(v, -FLT_MAX);
+  return oob ? -INFINITY : v;
+}
+
+// =================================================================================================
+// tcgen05 forward
+// =================================================================================================
+constexpr int FA_THREADS = 192;
+constexpr int FA_TILE = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, SWIZZLE_128B
+constexpr int FA_SMEM = FA_TILE /*Q*/ + 2 * FA_TILE /*K*/ + 2 * FA_TILE /*V*/ + 2 * FA_TILE /*P*/ + 128;
+
+__global__ void __launch_bounds__(FA_THREADS, 2)
+    attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const AttnP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t sQ = base;
+  const uint32_t sK = base + FA_TILE;
+  const uint32_t sV = base + 3 * FA_TILE;
+  const uint32_t sP = base + 5 * FA_TILE;
+  const uint32_t bars = base + 7 * FA_TILE;
+  const uint32_t q_full = bars, k_full = bars + 8, v_full = bars + 24, kv_empty = bars + 40,
+                 s_full = bars + 56, p_ready = bars + 72, o_full = bars + 80, tmem_slot = bars + 88;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + 7 * FA_TILE + 88);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_q_tiles = (p.Sq + 127) / 128;
+  // heavy (late) query tiles first: better tail under the causal mask
+  const int q_tile = n_q_tiles - 1 - (int)(blockIdx.x % n_q_tiles);
+  const int bh = blockIdx.x / n_q_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int q0 = q_tile * 128;
+
+  int n_kv = (p.Sk + 127) / 128;
+  if (p.causal) {
+    const bool full_sweep = p.first_valid && (q0 + p.off < p.first_valid[b]);
+    if (!full_sweep) {
+      const int last_key = min(p.Sk - 1, q0 + 127 + p.off);
+      n_kv = last_key < 0 ? 0 : last_key / 128 + 1;
+    }
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full + 8 * s, 1); mbar_init(v_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1);
+      mbar_init(s_full + 8 * s, 1);
+    }
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0 && n_kv > 0) {
+      mbar_expect_tx(q_full, FA_TILE);
+      tma_load_4d(sQ, &tmQ, q_full, 0, q0, h, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        mbar_wait(kv_empty + 8 * s, ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(k_full + 8 * s, FA_TILE);
+        tma_load_4d(sK + s * FA_TILE, &tmK, k_full + 8 * s, 0, j * 128, h, b);
+        mbar_expect_tx(v_full + 8 * s, FA_TILE);
+        tma_load_4d(sV + s * FA_TILE, &tmV, v_full + 8 * s, 0, j * 128, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_kv > 0) {
+      const uint32_t idesc_s = umma_idesc_f16(p.fmt, 0, 0, 128, 128);
+      const uint32_t idesc_o = umma_idesc_f16(p.fmt, 0, 1, 128, 64);
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(k_full + 8 * s, (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem + (j & 1) * 128, umma_smem_desc_sw128(sQ + k * 32, 0, 1024),
+                   umma_smem_desc_sw128(sK + s * FA_TILE + k * 32, 0, 1024), idesc_s, k > 0);
+        umma_commit(s_full + 8 * (j & 1));
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        mbar_wait(p_ready, j & 1);
+        mbar_wait(v_full + 8 * s, (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16(tmem + (j & 1) * 128,
+                   umma_smem_desc_sw128(sP + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                   umma_smem_desc_sw128(sV + s * FA_TILE + k * 2048, 64 * 128, 1024), idesc_o, k > 0);
+        umma_commit(kv_empty + 8 * s);
+        umma_commit(o_full);
+        if (j + 1 < n_kv) issue_s(j + 1);
+      }
+    }
+  } else {
+    // ------------------------------ softmax: one thread per query row ------------------------------
+    const int qr = (warp & 3) * 32 + lane;  // row inside the tile == TMEM lane
+    const int i = q0 + qr;
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const float* kb_row = p.kbias2 ? p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh : nullptr;
+    float o_acc[64];
+#pragma unroll
+    for (int d = 0; d < 64; ++d) o_acc[d] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    const uint32_t p_row = sP + qr * 128;
+    const int sw = qr & 7;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int kv0 = j * 128;
+      const uint32_t t_s = t_lane + (j & 1) * 128;
+      mbar_wait(s_full + 8 * (j & 1), (j >> 1) & 1);
+      tc_fence_after();
+      // a tile needs per-element masking if it touches the causal diagonal or the ragged key edge
+      const bool slow = (p.causal && (kv0 + 127 > q0 + p.off)) || (kv0 + 128 > p.Sk);
+      const bool vec_kb = kb_row && (kv0 + 128 <= p.Sk) && ((p.Sk & 3) == 0) && ((p.kb_sb & 3) == 0) &&
+                          ((p.kb_sh & 3) == 0);
+      float mt = -INFINITY;
+      // ---- pass 1: row maximum ----
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_s + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t4 = 0; t4 < 8; ++t4) {
+          float kb[4] = {0.f, 0.f, 0.f, 0.f};
+          const int jg = kv0 + c * 32 + t4 * 4;
+          if (vec_kb) {
+            const float4 k4 = __ldg(reinterpret_cast<const float4*>(kb_row + jg));
+            kb[0] = k4.x; kb[1] = k4.y; kb[2] = k4.z; kb[3] = k4.w;
+          } else if (kb_row) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) kb[u] = (jg + u < p.Sk) ? __ldg(kb_row + jg + u) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float a = __uint_as_float(r[t4 * 4 + u]);
+            float v;
+            if (slow)
+              v = score2(a, p.sl2, kb[u], p.causal && (jg + u > i + p.off), p.causal_fill2,
+                         jg + u >= p.Sk);
+            else
+              v = fmaxf(fmaf(a, p.sl2, kb[u]), -FLT_MAX);
+            mt = fmaxf(mt, v);
+          }
+        }
+      }
+      const float m_new = fmaxf(m, mt);
+      const float alpha = ex2(m - m_new);
+      float lt = 0.f;
+      // ---- pass 2: p = 2^(s - m), write bf16 P into the K-major SWIZZLE_128B tile ----
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_s + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int t4 = 0; t4 < 8; ++t4) {
+          float kb[4] = {0.f, 0.f, 0.f, 0.f};
+          const int jg = kv0 + c * 32 + t4 * 4;
+          if (vec_kb) {
+            const float4 k4 = __ldg(reinterpret_cast<const float4*>(kb_row + jg));
+            kb[0] = k4.x; kb[1] = k4.y; kb[2] = k4.z; kb[3] = k4.w;
+          } else if (kb_row) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) kb[u] = (jg + u < p.Sk) ? __ldg(kb_row + jg + u) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float a = __uint_as_float(r[t4 * 4 + u]);
+            float v;
+            if (slow)
+              v = score2(a, p.sl2, kb[u], p.causal && (jg + u > i + p.off), p.causal_fill2,
+                         jg + u >= p.Sk);
+            else
+              v = fmaxf(fmaf(a, p.sl2, kb[u]), -FLT_MAX);
+            const float e = ex2(v - m_new);
+            lt += e;
+            pv[t4 * 4 + u] = e;
+          }
+        }
+        // 32 columns = 4 x 16-byte chunks; panel = c / 2, chunk index within the 128-byte row
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w0, w1, w2, w3;
+          if (p.fmt == 1) {
+            w0 = pack_bf16x2(pv[8 * g], pv[8 * g + 1]); w1 = pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]);
+            w2 = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]); w3 = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
+          } else {
+            __half2 h0 = __floats2half2_rn(pv[8 * g], pv[8 * g + 1]), h1 = __floats2half2_rn(pv[8 * g + 2], pv[8 * g + 3]);
+            __half2 h2 = __floats2half2_rn(pv[8 * g + 4], pv[8 * g + 5]), h3 = __floats2half2_rn(pv[8 * g + 6], pv[8 * g + 7]);
+            w0 = *reinterpret_cast<uint32_t*>(&h0); w1 = *reinterpret_cast<uint32_t*>(&h1);
+            w2 = *reinterpret_cast<uint32_t*>(&h2); w3 = *reinterpret_cast<uint32_t*>(&h3);
+          }
+          const int chunk = (c & 1) * 4 + g;
+          const uint32_t addr = p_row + (c >> 1) * FA_TILE + ((chunk ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1),
+                       "r"(w2), "r"(w3)
+                       : "memory");
+        }
+      }
+      l = l * alpha + lt;
+      m = m_new;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      // ---- O = O * alpha + P V ----
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_s + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) o_acc[c * 32 + t] = fmaf(o_acc[c * 32 + t], alpha, __uint_as_float(r[t]));
+      }
+      tc_fence_before();
+    }
+    // ---- epilogue: normalise, write O (merged-head layout) and lse2 ----
+    if (i < p.Sq) {
+      const float inv = (n_kv > 0) ? 1.f / l : 0.f;
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
+                      2 * ((int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)i * p.o_ss);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 w;
+        if (p.fmt == 1) {
+          w.x = pack_bf16x2(o_acc[8 * g] * inv, o_acc[8 * g + 1] * inv);
+          w.y = pack_bf16x2(o_acc[8 * g + 2] * inv, o_acc[8 * g + 3] * inv);
+          w.z = pack_bf16x2(o_acc[8 * g + 4] * inv, o_acc[8 * g + 5] * inv);
+          w.w = pack_bf16x2(o_acc[8 * g + 6] * inv, o_acc[8 * g + 7] * inv);
+        } else {
+          __half2 h0 = __floats2half2_rn(o_acc[8 * g] * inv, o_acc[8 * g + 1] * inv);
+          __half2 h1 = __floats2half2_rn(o_acc[8 * g + 2] * inv, o_acc[8 * g + 3] * inv);
+          __half2 h2 = __floats2half2_rn(o_acc[8 * g + 4] * inv, o_acc[8 * g + 5] * inv);
+          __half2 h3 = __floats2half2_rn(o_acc[8 * g + 6] * inv, o_acc[8 * g + 7] * inv);
+          w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+          w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+        }
+        *reinterpret_cast<uint4*>(orow + 16 * g) = w;
+      }
+      if (p.lse2) p.lse2[((int64_t)b * p.H + h) * p.Sq + i] = (n_kv > 0) ? m + log2f(l) : -INFINITY;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+// =================================================================================================
+// tcgen05 backward
+// =================================================================================================
+struct AttnBwdP {
+  AttnP f;
+  const float* delta;
+  float* dq_accum;  // [B, Sq, H, 64] f32
+  void* dk; int64_t dk_sb, dk_sh, dk_ss;
+  void* dv; int64_t dv_sb, dv_sh, dv_ss;
+};
+constexpr int FB_SMEM = 2 * FA_TILE /*K,V*/ + 4 * FA_TILE /*2 x (Q,dO)*/ + 2 * FA_TILE /*P^T*/ +
+                        2 * FA_TILE /*dS^T*/ + 128;
+
+__device__ __forceinline__ void st_row64(void* basep, int64_t elem_off, const float (&v)[64], int fmt) {
+  uint8_t* row = reinterpret_cast<uint8_t*>(basep) + 2 * elem_off;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    uint4 w;
+    if (fmt == 1) {
+      w.x = pack_bf16x2(v[8 * g], v[8 * g + 1]); w.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+      w.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]); w.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+    } else {
+      __half2 h0 = __floats2half2_rn(v[8 * g], v[8 * g + 1]), h1 = __floats2half2_rn(v[8 * g + 2], v[8 * g + 3]);
+      __half2 h2 = __floats2half2_rn(v[8 * g + 4], v[8 * g + 5]), h3 = __floats2half2_rn(v[8 * g + 6], v[8 * g + 7]);
+      w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+      w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+    }
+    *reinterpret_cast<uint4*>(row + 16 * g) = w;
+  }
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+    attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                       const AttnBwdP bp) {
+  const AttnP& p = bp.f;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t sK = base, sV = base + FA_TILE;
+  const uint32_t sQ = base + 2 * FA_TILE;   // 2 stages, each Q then dO
+  const uint32_t sPT = base + 6 * FA_TILE;  // 2 panels
+  const uint32_t sDS = base + 8 * FA_TILE;  // 2 panels
+  const uint32_t bars = base + 10 * FA_TILE;
+  const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 24, sdp_full = bars + 40,
+                 pds_ready = bars + 48, dq_full = bars + 56, dkv_full = bars + 64, tmem_slot = bars + 72;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + 10 * FA_TILE + 72);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_kv_tiles = (p.Sk + 127) / 128;
+  const int kv_tile = blockIdx.x % n_kv_tiles;
+  const int bh = blockIdx.x / n_kv_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int kv0 = kv_tile * 128;
+  const int n_q_tiles = (p.Sq + 127) / 128;
+  int i_start = 0;
+  if (p.causal) {
+    const bool full_sweep = p.first_valid && (p.first_valid[b] > p.off);
+    if (!full_sweep) i_start = max(0, (kv0 - p.off) / 128);
+  }
+  const int n_it = max(0, n_q_tiles - i_start);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full + 8 * s, 1); mbar_init(qdo_empty + 8 * s, 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_ready, 128);
+    mbar_init(dq_full, 1);
+    mbar_init(dkv_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t T_ST = tmem, T_DPT = tmem + 128, T_DV = tmem + 256, T_DK = tmem + 320, T_DQ = tmem + 384;
+
+  if (warp == 0) {
+    if (lane == 0 && n_it > 0) {
+      mbar_expect_tx(kv_full, 2 * FA_TILE);
+      tma_load_4d(sK, &tmK, kv_full, 0, kv0, h, b);
+      tma_load_4d(sV, &tmV, kv_full, 0, kv0, h, b);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1, q0 = (i_start + it) * 128;
+        mbar_wait(qdo_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(qdo_full + 8 * s, 2 * FA_TILE);
+        tma_load_4d(sQ + s * 2 * FA_TILE, &tmQ, qdo_full + 8 * s, 0, q0, h, b);
+        tma_load_4d(sQ + s * 2 * FA_TILE + FA_TILE, &tmDO, qdo_full + 8 * s, 0, q0, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_it > 0) {
+      const uint32_t idesc_kk = umma_idesc_f16(p.fmt, 0, 0, 128, 128);  // S^T, dP^T
+      const uint32_t idesc_km = umma_idesc_f16(p.fmt, 0, 1, 128, 64);   // dV, dK
+      const uint32_t idesc_mm = umma_idesc_f16(p.fmt, 1, 1, 128, 64);   // dQ
+      auto issue_sdp = [&](int it) {
+        const int s = it & 1;
+        const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
+        mbar_wait(qdo_full + 8 * s, (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // S^T[kv, q] = K[kv, d] . Q[q, d]
+          umma_f16(T_ST, umma_smem_desc_sw128(sK + k * 32, 0, 1024), umma_smem_desc_sw128(q + k * 32, 0, 1024),
+                   idesc_kk, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dP^T[kv, q] = V[kv, d] . dO[q, d]
+          umma_f16(T_DPT, umma_smem_desc_sw128(sV + k * 32, 0, 1024),
+                   umma_smem_desc_sw128(d_o + k * 32, 0, 1024), idesc_kk, k > 0);
+        umma_commit(sdp_full);
+      };
+      mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
+        mbar_wait(pds_ready, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV[kv, d] += P^T[kv, q] . dO[q, d]   (B MN-major: rows = q)
+          umma_f16(T_DV, umma_smem_desc_sw128(sPT + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                   umma_smem_desc_sw128(d_o + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dK[kv, d] += dS^T[kv, q] . Q[q, d]
+          umma_f16(T_DK, umma_smem_desc_sw128(sDS + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                   umma_smem_desc_sw128(q + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ[q, d] = dS[q, kv] . K[kv, d]  (A MN-major view of dS^T)
+          umma_f16(T_DQ, umma_smem_desc_sw128(sDS + k * 2048, FA_TILE, 1024),
+                   umma_smem_desc_sw128(sK + k * 2048, 64 * 128, 1024), idesc_mm, k > 0);
+        umma_commit(qdo_empty + 8 * s);
+        umma_commit(dq_full);
+        if (it + 1 < n_it) issue_sdp(it + 1);
+      }
+      umma_commit(dkv_full);
+    }
+  } else {
+    const int rr = (warp & 3) * 32 + lane;  // key row inside the tile (S^T) / query row (dQ)
+    const int jg = kv0 + rr;
+    const uint32_t t_lane = (uint32_t)((warp & 3) * 32) << 16;
+    const float kb = (p.kbias2 && jg < p.Sk)
+                         ? __ldg(p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh + jg) : 0.f;
+    const bool key_oob = jg >= p.Sk;
+    const float* lse_bh = p.lse2 + ((int64_t)b * p.H + h) * p.Sq;
+    const float* del_bh = bp.delta + ((int64_t)b * p.H + h) * p.Sq;
+    const int sw = rr & 7;
+    for (int it = 0; it < n_it; ++it) {
+      const int q0 = (i_start + it) * 128;
+      mbar_wait(sdp_full, it & 1);
+      tc_fence_after();
+      const bool vec_q = (q0 + 128 <= p.Sq) && ((p.Sq & 3) == 0);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rd[32];
+        tmem_ld_32x32(T_ST + t_lane + c * 32, rs);
+        tmem_ld_32x32(T_DPT + t_lane + c * 32, rd);
+        tmem_ld_wait();
+        float pt[32], ds[32];
+#pragma unroll
+        for (int t4 = 0; t4 < 8; ++t4) {
+          const int qg = q0 + c * 32 + t4 * 4;
+          float ls[4], dl[4];
+          if (vec_q) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(lse_bh + qg));
+            const float4 d = __ldg(reinterpret_cast<const float4*>(del_bh + qg));
+            ls[0] = a.x; ls[1] = a.y; ls[2] = a.z; ls[3] = a.w;
+            dl[0] = d.x; dl[1] = d.y; dl[2] = d.z; dl[3] = d.w;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const bool ok = qg + u < p.Sq;
+              ls[u] = ok ? __ldg(lse_bh + qg + u) : INFINITY;
+              dl[u] = ok ? __ldg(del_bh + qg + u) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = t4 * 4 + u;
+            const bool fut = p.causal && (jg > qg + u + p.off);
+            const float v = score2(__uint_as_float(rs[e]), p.sl2, kb, fut, p.causal_fill2, false);
+            float pe = ex2(v - ls[u]);
+            if (key_oob) pe = 0.f;
+            pt[e] = pe;
+            // a causally masked score is a constant in the reference (modeling_gpt.py:89 `w*b`,
+            // modeling_bloom.py:108 masked_fill): P still feeds dV, but no gradient reaches q.k
+            ds[e] = fut ? 0.f : pe * (__uint_as_float(rd[e]) - dl[u]) * p.scale;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int chunk = (c & 1) * 4 + g;
+          const uint32_t off = rr * 128 + (c >> 1) * FA_TILE + ((chunk ^ sw) << 4);
+          uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+          if (p.fmt == 1) {
+            a0 = pack_bf16x2(pt[8 * g], pt[8 * g + 1]); a1 = pack_bf16x2(pt[8 * g + 2], pt[8 * g + 3]);
+            a2 = pack_bf16x2(pt[8 * g + 4], pt[8 * g + 5]); a3 = pack_bf16x2(pt[8 * g + 6], pt[8 * g + 7]);
+            b0 = pack_bf16x2(ds[8 * g], ds[8 * g + 1]); b1 = pack_bf16x2(ds[8 * g + 2], ds[8 * g + 3]);
+            b2 = pack_bf16x2(ds[8 * g + 4], ds[8 * g + 5]); b3 = pack_bf16x2(ds[8 * g + 6], ds[8 * g + 7]);
+          } else {
+            __half2 x;
+            x = __floats2half2_rn(pt[8 * g], pt[8 * g + 1]); a0 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(pt[8 * g + 2], pt[8 * g + 3]); a1 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(pt[8 * g + 4], pt[8 * g + 5]); a2 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(pt[8 * g + 6], pt[8 * g + 7]); a3 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(ds[8 * g], ds[8 * g + 1]); b0 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(ds[8 * g + 2], ds[8 * g + 3]); b1 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(ds[8 * g + 4], ds[8 * g + 5]); b2 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(ds[8 * g + 6], ds[8 * g + 7]); b3 = *reinterpret_cast<uint32_t*>(&x);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPT + off), "r"(a0), "r"(a1),
+                       "r"(a2), "r"(a3) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(b0), "r"(b1),
+                       "r"(b2), "r"(b3) : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_ready);
+      // ---- dQ tile: this thread now owns query row (q0 + rr) ----
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+      const int qi = q0 + rr;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(T_DQ + t_lane + c * 32, r);
+        tmem_ld_wait();
+        if (qi < p.Sq) {
+          float* dst = bp.dq_accum + (((int64_t)b * p.Sq + qi) * p.H + h) * 64 + c * 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g),
+                         "f"(__uint_as_float(r[4 * g])), "f"(__uint_as_float(r[4 * g + 1])),
+                         "f"(__uint_as_float(r[4 * g + 2])), "f"(__uint_as_float(r[4 * g + 3]))
+                         : "memory");
+        }
+      }
+      tc_fence_before();
+    }
+    // ---- dK / dV for this key row ----
+    float acc[64];
+    if (n_it > 0) {
+      mbar_wait(dkv_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      if (n_it > 0) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32((which == 0 ? T_DV : T_DK) + t_lane + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) acc[c * 32 + t] = __uint_as_float(r[t]);
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 64; ++t) acc[t] = 0.f;
+      }
+      if (!key_oob) {
+        if (which == 0)
+          st_row64(bp.dv, (int64_t)b * bp.dv_sb + (int64_t)h * bp.dv_sh + (int64_t)jg * bp.dv_ss, acc, p.fmt);
+        else
+          st_row64(bp.dk, (int64_t)b * bp.dk_sb + (int64_t)h * bp.dk_sh + (int64_t)jg * bp.dk_ss, acc, p.fmt);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (one warp per (b,i,h); D <= 128)
+__global__ void __launch_bounds__(256)
+    attn_delta_kernel(const void* __restrict__ dout, const void* __restrict__ o, int fmt, int64_t sb,
+                      int64_t sh, int64_t ss, float* __restrict__ delta, int B, int H, int Sq, int D) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (int64_t)B * H * Sq) return;
+  const int i = (int)(w % Sq);
+  const int h = (int)((w / Sq) % H);
+  const int b = (int)(w / ((int64_t)Sq * H));
+  const int64_t off = (int64_t)b * sb + (int64_t)h * sh + (int64_t)i * ss;
+  float acc = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    float x, y;
+    if (fmt == 1) {
+      x = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dout)[off + d]);
+      y = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(o)[off + d]);
+    } else {
+      x = __half2float(reinterpret_cast<const __half*>(dout)[off + d]);
+      y = __half2float(reinterpret_cast<const __half*>(o)[off + d]);
+    }
+    acc = fmaf(x, y, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) delta[((int64_t)b * H + h) * Sq + i] = acc;
+}
+
+// dq[b,h,i,:] = (bf16) dq_accum[b,i,h,:]
+__global__ void __launch_bounds__(256)
+    attn_dq_convert_kernel(const float* __restrict__ acc, void* __restrict__ dq, int fmt, int64_t sb,
+                           int64_t sh, int64_t ss, int B, int H, int Sq, int D) {
+  const int64_t n = (int64_t)B * Sq * H * D;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(e % D);
+    const int h = (int)((e / D) % H);
+    const int i = (int)((e / ((int64_t)D * H)) % Sq);
+    const int b = (int)(e / ((int64_t)D * H * Sq));
+    const int64_t off = (int64_t)b * sb + (int64_t)h * sh + (int64_t)i * ss + d;
+    if (fmt == 1) reinterpret_cast<__nv_bfloat16*>(dq)[off] = __float2bfloat16_rn(acc[e]);
+    else reinterpret_cast<__half*>(dq)[off] = __float2half_rn(acc[e]);
+  }
+}
+
+// =================================================================================================
+// SIMT kernels (any D <= 128): one warp per (b, h, query row) / per (b, h, key row)
+// =================================================================================================
+__device__ __forceinline__ float ld16(const void* p, int fmt, int64_t idx) {
+  return fmt == 1 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx])
+                  : __half2float(reinterpret_cast<const __half*>(p)[idx]);
+}
+__device__ __forceinline__ void st16(void* p, int fmt, int64_t idx, float v) {
+  if (fmt == 1) reinterpret_cast<__nv_bfloat16*>(p)[idx] = __float2bfloat16_rn(v);
+  else reinterpret_cast<__half*>(p)[idx] = __float2half_rn(v);
+}
+
+struct SimtP {
+  AttnP a;
+  int D;
+  const void *q, *k, *v;
+  int64_t q_sb, q_sh, q_ss, k_sb, k_sh, k_ss, v_sb, v_sh, v_ss;
+};
+
+constexpr int SIMT_WARPS = 4;
+
+__global__ void __launch_bounds__(SIMT_WARPS * 32)
+    attn_fwd_simt_kernel(const SimtP sp) {
+  const AttnP& p = sp.a;
+  __shared__ float qs[SIMT_WARPS][128];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * SIMT_WARPS + wib;
+  if (w >= (int64_t)p.B * p.H * p.Sq) return;
+  const int i = (int)(w % p.Sq);
+  const int h = (int)((w / p.Sq) % p.H);
+  const int b = (int)(w / ((int64_t)p.Sq * p.H));
+  const int D = sp.D;
+  const int64_t qoff = (int64_t)b * sp.q_sb + (int64_t)h * sp.q_sh + (int64_t)i * sp.q_ss;
+  for (int d = lane; d < D; d += 32) qs[wib][d] = ld16(sp.q, p.fmt, qoff + d);
+  __syncwarp();
+  const float* kb_row = p.kbias2 ? p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh : nullptr;
+  float m = -INFINITY, l = 0.f;
+  float o_acc[4] = {0.f, 0.f, 0.f, 0.f};  // lane owns d = lane, lane+32, lane+64, lane+96
+  for (int j0 = 0; j0 < p.Sk; j0 += 32) {
+    const int j = j0 + lane;
+    float v = -INFINITY;
+    if (j < p.Sk) {
+      const int64_t koff = (int64_t)b * sp.k_sb + (int64_t)h * sp.k_sh + (int64_t)j * sp.k_ss;
+      float acc = 0.f;
+      for (int d = 0; d < D; ++d) acc = fmaf(qs[wib][d], ld16(sp.k, p.fmt, koff + d), acc);
+      v = score2(acc, p.sl2, kb_row ? kb_row[j] : 0.f, p.causal && (j > i + p.off), p.causal_fill2, false);
+    }
+    const float m_new = fmaxf(m, warp_max(v));
+    const float alpha = ex2(m - m_new);
+    const float e = ex2(v - m_new);
+    // P is rounded to the activation dtype before the PV product, like the tensor-core path
+    const float er = p.fmt == 1 ? __bfloat162float(__float2bfloat16_rn(e)) : __half2float(__float2half_rn(e));
+    l = l * alpha + warp_sum(e);
+    m = m_new;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) o_acc[u] *= alpha;
+    const int lim = min(32, p.Sk - j0);
+    for (int t = 0; t < lim; ++t) {
+      const float pj = __shfl_sync(0xffffffffu, er, t);
+      const int64_t voff = (int64_t)b * sp.v_sb + (int64_t)h * sp.v_sh + (int64_t)(j0 + t) * sp.v_ss;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int d = lane + 32 * u;
+        if (d < D) o_acc[u] = fmaf(pj, ld16(sp.v, p.fmt, voff + d), o_acc[u]);
+      }
+    }
+  }
+  const float inv = 1.f / l;
+  const int64_t ooff = (int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)i * p.o_ss;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int d = lane + 32 * u;
+    if (d < D) st16(p.o, p.fmt, ooff + d, o_acc[u] * inv);
+  }
+  if (p.lse2 && lane == 0) p.lse2[((int64_t)b * p.H + h) * p.Sq + i] = m + log2f(l);
+}
+
+struct SimtBwdP {
+  SimtP s;
+  const void* dout;
+  const float* delta;
+  void *dq, *dk, *dv;
+  int64_t dq_sb, dq_sh, dq_ss, dk_sb, dk_sh, dk_ss, dv_sb, dv_sh, dv_ss;
+};
+
+// dq row: warp per (b,h,i)
+__global__ void __launch_bounds__(SIMT_WARPS * 32)
+    attn_bwd_dq_simt_kernel(const SimtBwdP bp) {
+  const SimtP& sp = bp.s;
+  const AttnP& p = sp.a;
+  __shared__ float qs[SIMT_WARPS][128];
+  __shared__ float dos[SIMT_WARPS][128];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * SIMT_WARPS + wib;
+  if (w >= (int64_t)p.B * p.H * p.Sq) return;
+  const int i = (int)(w % p.Sq);
+  const int h = (int)((w / p.Sq) % p.H);
+  const int b = (int)(w / ((int64_t)p.Sq * p.H));
+  const int D = sp.D;
+  const int64_t qoff = (int64_t)b * sp.q_sb + (int64_t)h * sp.q_sh + (int64_t)i * sp.q_ss;
+  const int64_t ooff = (int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)i * p.o_ss;
+  for (int d = lane; d < D; d += 32) {
+    qs[wib][d] = ld16(sp.q, p.fmt, qoff + d);
+    dos[wib][d] = ld16(bp.dout, p.fmt, ooff + d);
+  }
+  __syncwarp();
+  const float* kb_row = p.kbias2 ? p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh : nullptr;
+  const float lse = p.lse2[((int64_t)b * p.H + h) * p.Sq + i];
+  const float dl = bp.delta[((int64_t)b * p.H + h) * p.Sq + i];
+  float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j0 = 0; j0 < p.Sk; j0 += 32) {
+    const int j = j0 + lane;
+    float ds = 0.f;
+    if (j < p.Sk) {
+      const int64_t koff = (int64_t)b * sp.k_sb + (int64_t)h * sp.k_sh + (int64_t)j * sp.k_ss;
+      const int64_t voff = (int64_t)b * sp.v_sb + (int64_t)h * sp.v_sh + (int64_t)j * sp.v_ss;
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < D; ++d) {
+        s = fmaf(qs[wib][d], ld16(sp.k, p.fmt, koff + d), s);
+        dp = fmaf(dos[wib][d], ld16(sp.v, p.fmt, voff + d), dp);
+      }
+      const bool fut = p.causal && (j > i + p.off);
+      const float v = score2(s, p.sl2, kb_row ? kb_row[j] : 0.f, fut, p.causal_fill2, false);
+      ds = fut ? 0.f : ex2(v - lse) * (dp - dl) * p.scale;
+    }
+    const int lim = min(32, p.Sk - j0);
+    for (int t = 0; t < lim; ++t) {
+      const float dsj = __shfl_sync(0xffffffffu, ds, t);
+      const int64_t koff = (int64_t)b * sp.k_sb + (int64_t)h * sp.k_sh + (int64_t)(j0 + t) * sp.k_ss;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int d = lane + 32 * u;
+        if (d < D) acc4[u] = fmaf(dsj, ld16(sp.k, p.fmt, koff + d), acc4[u]);
+      }
+    }
+  }
+  const int64_t dqoff = (int64_t)b * bp.dq_sb + (int64_t)h * bp.dq_sh + (int64_t)i * bp.dq_ss;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int d = lane + 32 * u;
+    if (d < D) st16(bp.dq, p.fmt, dqoff + d, acc4[u]);
+  }
+}
+
+// dk, dv rows: warp per (b,h,j)
+__global__ void __launch_bounds__(SIMT_WARPS * 32)
+    attn_bwd_dkv_simt_kernel(const SimtBwdP bp) {
+  const SimtP& sp = bp.s;
+  const AttnP& p = sp.a;
+  __shared__ float ks[SIMT_WARPS][128];
+  __shared__ float vs[SIMT_WARPS][128];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * SIMT_WARPS + wib;
+  if (w >= (int64_t)p.B * p.H * p.Sk) return;
+  const int j = (int)(w % p.Sk);
+  const int h = (int)((w / p.Sk) % p.H);
+  const int b = (int)(w / ((int64_t)p.Sk * p.H));
+  const int D = sp.D;
+  const int64_t koff = (int64_t)b * sp.k_sb + (int64_t)h * sp.k_sh + (int64_t)j * sp.k_ss;
+  const int64_t voff = (int64_t)b * sp.v_sb + (int64_t)h * sp.v_sh + (int64_t)j * sp.v_ss;
+  for (int d = lane; d < D; d += 32) {
+    ks[wib][d] = ld16(sp.k, p.fmt, koff + d);
+    vs[wib][d] = ld16(sp.v, p.fmt, voff + d);
+  }
+  __syncwarp();
+  const float kb = p.kbias2 ? p.kbias2[(int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh + j] : 0.f;
+  float dk4[4] = {0.f, 0.f, 0.f, 0.f}, dv4[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i0 = 0; i0 < p.Sq; i0 += 32) {
+    const int i = i0 + lane;
+    float pe = 0.f, ds = 0.f;
+    if (i < p.Sq) {
+      const int64_t qoff = (int64_t)b * sp.q_sb + (int64_t)h * sp.q_sh + (int64_t)i * sp.q_ss;
+      const int64_t ooff = (int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)i * p.o_ss;
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < D; ++d) {
+        s = fmaf(ld16(sp.q, p.fmt, qoff + d), ks[wib][d], s);
+        dp = fmaf(ld16(bp.dout, p.fmt, ooff + d), vs[wib][d], dp);
+      }
+      const bool fut = p.causal && (j > i + p.off);
+      const float v = score2(s, p.sl2, kb, fut, p.causal_fill2, false);
+      pe = ex2(v - p.lse2[((int64_t)b * p.H + h) * p.Sq + i]);
+      ds = fut ? 0.f : pe * (dp - bp.delta[((int64_t)b * p.H + h) * p.Sq + i]) * p.scale;
+    }
+    const int lim = min(32, p.Sq - i0);
+    for (int t = 0; t < lim; ++t) {
+      const float pi = __shfl_sync(0xffffffffu, pe, t);
+      const float dsi = __shfl_sync(0xffffffffu, ds, t);
+      const int64_t qoff = (int64_t)b * sp.q_sb + (int64_t)h * sp.q_sh + (int64_t)(i0 + t) * sp.q_ss;
+      const int64_t ooff = (int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)(i0 + t) * p.o_ss;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int d = lane + 32 * u;
+        if (d < D) {
+          dv4[u] = fmaf(pi, ld16(bp.dout, p.fmt, ooff + d), dv4[u]);
+          dk4[u] = fmaf(dsi, ld16(sp.q, p.fmt, qoff + d), dk4[u]);
+        }
+      }
+    }
+  }
+  const int64_t dkoff = (int64_t)b * bp.dk_sb + (int64_t)h * bp.dk_sh + (int64_t)j * bp.dk_ss;
+  const int64_t dvoff = (int64_t)b * bp.dv_sb + (int64_t)h * bp.dv_sh + (int64_t)j * bp.dv_ss;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int d = lane + 32 * u;
+    if (d < D) {
+      st16(bp.dk, p.fmt, dkoff + d, dk4[u]);
+      st16(bp.dv, p.fmt, dvoff + d, dv4[u]);
+    }
+  }
+}
+
+// =================================================================================================
+// mask preparation: one block per batch row
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+    attn_mask_prep_kernel(const void* __restrict__ mask, int mask_dtype, int Sk, int H, int mode,
+                          const float* __restrict__ slopes, float* __restrict__ kbias2,
+                          int32_t* __restrict__ first_valid) {
+  extern __shared__ int pos_s[];  // [Sk] inclusive cumsum - 1
+  __shared__ int first_s;
+  const int b = blockIdx.x;
+  auto mval = [&](int j) -> float {
+    if (mask_dtype == 3) return (float)reinterpret_cast<const long long*>(mask)[(int64_t)b * Sk + j];
+    if (mask_dtype == 4) return (float)reinterpret_cast<const int*>(mask)[(int64_t)b * Sk + j];
+    return reinterpret_cast<const float*>(mask)[(int64_t)b * Sk + j];
+  };
+  if (threadIdx.x == 0) {
+    int run = 0, first = Sk;
+    for (int j = 0; j < Sk; ++j) {  // serial scan: Sk <= a few thousand, once per forward
+      const int mv = (int)mval(j);
+      run += mv;
+      pos_s[j] = run - 1;
+      if (mv != 0 && first == Sk) first = j;
+    }
+    first_s = first;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && first_valid) first_valid[b] = first_s;
+  const int heads = (mode == 0) ? H : 1;
+  for (int e = threadIdx.x; e < heads * Sk; e += blockDim.x) {
+    const int h = e / Sk, j = e % Sk;
+    const float mv = mval(j);
+    float add, pos = 0.f;
+    if (mode == 0) {  // modeling_bloom.py:179-185 (fill finfo.min) + :328-331 (alibi)
+      add = (mv != 0.f) ? 0.f : -FLT_MAX;
+      pos = slopes[h] * ((float)pos_s[j] * mv);
+    } else if (mode == 1) {  // modeling_gpt.py:176-179
+      add = (1.0f - mv) * -FLT_MAX;
+    } else {  // modeling_bert.py:303-304
+      add = (1.0f - mv) * -10000.0f;
+    }
+    kbias2[((int64_t)b * heads + h) * Sk + j] = (pos + add) * LOG2E;
+  }
+}
+
+static int make_qkv_tmap(CUtensorMap* tm, const void* base, int64_t sb, int64_t sh, int64_t ss, int B,
+                         int H, int S, int D) {
+  uint64_t dims[4] = {(uint64_t)D, (uint64_t)S, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[4] = {2, (uint64_t)ss * 2, (uint64_t)sh * 2, (uint64_t)sb * 2};
+  uint32_t box[4] = {64, 128, 1, 1};
+  return make_tmap(tm, base, 2, 4, dims, strides, box, 1);
+}
+
+static bool tma_ok4(const void* base, int64_t sb, int64_t sh, int64_t ss) {
+  return (((uintptr_t)base & 15) == 0) && (sb % 8 == 0) && (sh % 8 == 0) && (ss % 8 == 0);
+}
+
+static void fill_common(AttnP& p, const ct_attn_args& a) {
+  p.B = a.B; p.H = a.H; p.Sq = a.Sq; p.Sk = a.Sk;
+  p.fmt = a.dtype == DT_BF16 ? 1 : 0;
+  p.scale = a.scale;
+  p.sl2 = a.scale * LOG2E;
+  p.causal = a.causal;
+  p.causal_fill2 = a.causal_fill * LOG2E;  // -FLT_MAX * log2e -> -inf; clamped in score2
+  p.off = a.Sk - a.Sq;
+  p.kbias2 = a.kbias2; p.kb_sb = a.kb_sb; p.kb_sh = a.kb_sh;
+  p.first_valid = a.first_valid;
+  p.o = a.o; p.o_sb = a.o_sb; p.o_sh = a.o_sh; p.o_ss = a.o_ss;
+  p.lse2 = a.lse2;
+}
+
+static int check_args(const ct_attn_args& a, const char* who) {
+  CT_REQUIRE(a.q && a.k && a.v && a.o, CT_ERR_BAD_ARG, "%s: null tensor", who);
+  CT_REQUIRE(a.B > 0 && a.H > 0 && a.Sq > 0 && a.Sk > 0 && a.D > 0 && a.D <= 128, CT_ERR_BAD_ARG,
+             "%s: bad shape B=%d H=%d Sq=%d Sk=%d D=%d", who, a.B, a.H, a.Sq, a.Sk, a.D);
+  CT_REQUIRE(a.dtype == DT_BF16 || a.dtype == DT_F16, CT_ERR_UNSUPPORTED, "%s: dtype must be bf16/f16", who);
+  return 0;
+}
+
+}  // namespace ct
+
+using namespace ct;
+
+extern "C" int ct_attn_fwd(const ct_attn_args* args, void* stream) {
+  CT_REQUIRE(args != nullptr, CT_ERR_BAD_ARG, "ct_attn_fwd: null args");
+  const ct_attn_args& a = *args;
+  int rc = check_args(a, "ct_attn_fwd");
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_ok = a.D == 64 && tma_ok4(a.q, a.q_sb, a.q_sh, a.q_ss) &&
+                     tma_ok4(a.k, a.k_sb, a.k_sh, a.k_ss) && tma_ok4(a.v, a.v_sb, a.v_sh, a.v_ss) &&
+                     tma_ok4(a.o, a.o_sb, a.o_sh, a.o_ss);
+  bool use_tc;
+  if (a.impl == 1) {
+    CT_REQUIRE(tc_ok, CT_ERR_UNSUPPORTED, "ct_attn_fwd: tcgen05 path needs D=64 and 16-byte aligned strides");
+    use_tc = true;
+  } else if (a.impl == 2) {
+    use_tc = false;
+  } else {
+    use_tc = tc_ok && a.Sq >= 16;
+  }
+  if (use_tc) {
+    AttnP p;
+    fill_common(p, a);
+    CUtensorMap tmQ, tmK, tmV;
+    if ((rc = make_qkv_tmap(&tmQ, a.q, a.q_sb, a.q_sh, a.q_ss, a.B, a.H, a.Sq, 64))) return rc;
+    if ((rc = make_qkv_tmap(&tmK, a.k, a.k_sb, a.k_sh, a.k_ss, a.B, a.H, a.Sk, 64))) return rc;
+    if ((rc = make_qkv_tmap(&tmV, a.v, a.v_sb, a.v_sh, a.v_ss, a.B, a.H, a.Sk, 64))) return rc;
+    static bool attr = false;
+    if (!attr) {
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+      attr = true;
+    }
+    const int64_t grid = (int64_t)a.B * a.H * ((a.Sq + 127) / 128);
+    attn_fwd_tc_kernel<<<(unsigned)grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, p);
+    CT_LAUNCH_OK();
+    return 0;
+  }
+  SimtP sp;
+  fill_common(sp.a, a);
+  sp.D = a.D;
+  sp.q = a.q; sp.k = a.k; sp.v = a.v;
+  sp.q_sb = a.q_sb; sp.q_sh = a.q_sh; sp.q_ss = a.q_ss;
+  sp.k_sb = a.k_sb; sp.k_sh = a.k_sh; sp.k_ss = a.k_ss;
+  sp.v_sb = a.v_sb; sp.v_sh = a.v_sh; sp.v_ss = a.v_ss;
+  const int64_t warps = (int64_t)a.B * a.H * a.Sq;
+  attn_fwd_simt_kernel<<<(unsigned)((warps + SIMT_WARPS - 1) / SIMT_WARPS), SIMT_WARPS * 32, 0, st>>>(sp);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
+  CT_REQUIRE(args != nullptr, CT_ERR_BAD_ARG, "ct_attn_bwd: null args");
+  const ct_attn_args& a = args->f;
+  int rc = check_args(a, "ct_attn_bwd");
+  if (rc) return rc;
+  CT_REQUIRE(args->dout && args->dq && args->dk && args->dv && args->delta && a.lse2, CT_ERR_BAD_ARG,
+             "ct_attn_bwd: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int fmt = a.dtype == DT_BF16 ? 1 : 0;
+  {
+    const int64_t warps = (int64_t)a.B * a.H * a.Sq;
+    attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+        args->dout, a.o, fmt, a.o_sb, a.o_sh, a.o_ss, args->delta, a.B, a.H, a.Sq, a.D);
+    CT_LAUNCH_OK();
+  }
+  const bool tc_ok = a.D == 64 && tma_ok4(a.q, a.q_sb, a.q_sh, a.q_ss) &&
+                     tma_ok4(a.k, a.k_sb, a.k_sh, a.k_ss) && tma_ok4(a.v, a.v_sb, a.v_sh, a.v_ss) &&
+                     tma_ok4(args->dout, a.o_sb, a.o_sh, a.o_ss) &&
+                     tma_ok4(args->dk, args->dk_sb, args->dk_sh, args->dk_ss) &&
+                     tma_ok4(args->dv, args->dv_sb, args->dv_sh, args->dv_ss) && args->dq_accum != nullptr;
+  bool use_tc;
+  if (a.impl == 1) {
+    CT_REQUIRE(tc_ok, CT_ERR_UNSUPPORTED, "ct_attn_bwd: tcgen05 path needs D=64, aligned strides, dq_accum");
+    use_tc = true;
+  } else if (a.impl == 2) {
+    use_tc = false;
+  } else {
+    use_tc = tc_ok && a.Sq >= 16;
+  }
+  if (use_tc) {
+    AttnBwdP bp;
+    fill_common(bp.f, a);
+    bp.delta = args->delta;
+    bp.dq_accum = args->dq_accum;
+    bp.dk = args->dk; bp.dk_sb = args->dk_sb; bp.dk_sh = args->dk_sh; bp.dk_ss = args->dk_ss;
+    bp.dv = args->dv; bp.dv_sb = args->dv_sb; bp.dv_sh = args->dv_sh; bp.dv_ss = args->dv_ss;
+    CUtensorMap tmQ, tmK, tmV, tmDO;
+    if ((rc = make_qkv_tmap(&tmQ, a.q, a.q_sb, a.q_sh, a.q_ss, a.B, a.H, a.Sq, 64))) return rc;
+    if ((rc = make_qkv_tmap(&tmK, a.k, a.k_sb, a.k_sh, a.k_ss, a.B, a.H, a.Sk, 64))) return rc;
+    if ((rc = make_qkv_tmap(&tmV, a.v, a.v_sb, a.v_sh, a.v_ss, a.B, a.H, a.Sk, 64))) return rc;
+    if ((rc = make_qkv_tmap(&tmDO, args->dout, a.o_sb, a.o_sh, a.o_ss, a.B, a.H, a.Sq, 64))) return rc;
+    CT_CUDA_OK(cudaMemsetAsync(args->dq_accum, 0, sizeof(float) * (size_t)a.B * a.Sq * a.H * 64, st));
+    static bool attr = false;
+    if (!attr) {
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      attr = true;
+    }
+    const int64_t grid = (int64_t)a.B * a.H * ((a.Sk + 127) / 128);
+    attn_bwd_tc_kernel<<<(unsigned)grid, FA_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
+    CT_LAUNCH_OK();
+    const int64_t n = (int64_t)a.B * a.Sq * a.H * 64;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+    attn_dq_convert_kernel<<<(unsigned)blocks, 256, 0, st>>>(args->dq_accum, args->dq, fmt, args->dq_sb,
+                                                             args->dq_sh, args->dq_ss, a.B, a.H, a.Sq, 64);
+    CT_LAUNCH_OK();
+    return 0;
+  }
+  SimtBwdP bp;
+  fill_common(bp.s.a, a);
+  bp.s.D = a.D;
+  bp.s.q = a.q; bp.s.k = a.k; bp.s.v = a.v;
+  bp.s.q_sb = a.q_sb; bp.s.q_sh = a.q_sh; bp.s.q_ss = a.q_ss;
+  bp.s.k_sb = a.k_sb; bp.s.k_sh = a.k_sh; bp.s.k_ss = a.k_ss;
+  bp.s.v_sb = a.v_sb; bp.s.v_sh = a.v_sh; bp.s.v_ss = a.v_ss;
+  bp.dout = args->dout; bp.delta = args->delta;
+  bp.dq = args->dq; bp.dk = args->dk; bp.dv = args->dv;
+  bp.dq_sb = args->dq_sb; bp.dq_sh = args->dq_sh; bp.dq_ss = args->dq_ss;
+  bp.dk_sb = args->dk_sb; bp.dk_sh = args->dk_sh; bp.dk_ss = args->dk_ss;
+  bp.dv_sb = args->dv_sb; bp.dv_sh = args->dv_sh; bp.dv_ss = args->dv_ss;
+  const int64_t wq = (int64_t)a.B * a.H * a.Sq, wk = (int64_t)a.B * a.H * a.Sk;
+  attn_bwd_dq_simt_kernel<<<(unsigned)((wq + SIMT_WARPS - 1) / SIMT_WARPS), SIMT_WARPS * 32, 0, st>>>(bp);
+  CT_LAUNCH_OK();
+  attn_bwd_dkv_simt_kernel<<<(unsigned)((wk + SIMT_WARPS - 1) / SIMT_WARPS), SIMT_WARPS * 32, 0, st>>>(bp);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_attn_mask_prep(const void* attention_mask, int mask_dtype, int64_t B, int64_t Sk,
+                                 int64_t H, int mode, const float* slopes, float* kbias2,
+                                 int32_t* first_valid, void* stream) {
+  CT_REQUIRE(attention_mask && kbias2, CT_ERR_BAD_ARG, "ct_attn_mask_prep: null pointer");
+  CT_REQUIRE(mask_dtype == DT_F32 || mask_dtype == 3 || mask_dtype == 4, CT_ERR_UNSUPPORTED,
+             "ct_attn_mask_prep: mask dtype must be f32/int64/int32");
+  CT_REQUIRE(mode >= 0 && mode <= 2 && (mode != 0 || slopes), CT_ERR_BAD_ARG, "ct_attn_mask_prep: bad mode");
+  CT_REQUIRE(B > 0 && Sk > 0 && Sk <= 12000 && H > 0, CT_ERR_BAD_ARG, "ct_attn_mask_prep: bad shape");
+  attn_mask_prep_kernel<<<(unsigned)B, 256, sizeof(int) * Sk, (cudaStream_t)stream>>>(
+      attention_mask, mask_dtype, (int)Sk, (int)H, mode, slopes, kbias2, first_valid);
+  CT_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,304 @@
+// comm.cu — gradient-bucket all-reduce as plain CUDA kernels over NVLink/NVSwitch peer memory.
+//
+// Replaces the ncclAllReduce calls that torch's DDP reducer issues for the reference
+// (examples/ft_bloom_DDP.py:99,126,135 `DDP(model, device_ids=[local_rank])`; README.md:46-52
+// describes the hand-rolled version: param sync, gradient buckets, overlapped reduction).
+//
+// Memory: every rank cudaMalloc()s one symmetric gradient buffer + one small signal buffer and
+// publishes cudaIpcMemHandles; Python (torch.distributed, used only as bootstrap) exchanges the 64-byte
+// handles and each rank maps every peer buffer (cudaIpcOpenMemHandle). The gradient arena
+// (arena.py) lives inside the symmetric buffer, so wgrad kernels write straight into NVLink-visible
+// memory and the reduction is in place.
+//
+// ct_allreduce(offset, count): two-shot, one kernel per rank
+//   phase 0  signal "my data for epoch e is ready" to every peer, wait for all peers
+//   phase 1  rank r owns slice r of the range: 128-bit loads of that slice from all W ranks
+//            (peer reads over NVLink), fp32 sum in rank order (deterministic), * scale, 128-bit
+//            stores of the result to all W ranks (peer writes)
+//   phase 2  last CTA signals "my slice is written everywhere", waits for all peers' signals
+// One-shot variant (each rank reads everything from every peer, writes only locally) for small,
+// latency-bound buckets. Bytes over NVLink per rank: two-shot 2*(W-1)/W * bytes, one-shot
+// (W-1) * bytes inbound.
+#include "ct_common.cuh"
+#include "../../include/ct_b200.h"
+#include <mutex>
+#include <vector>
+
+namespace ct {
+
+constexpr int MAX_WORLD = 16;
+
+struct CommCtx {
+  int rank = -1, world = 0, device = 0;
+  bool ready = false;
+  float* data[MAX_WORLD] = {nullptr};        // symmetric gradient buffers (local at [rank])
+  uint32_t* sig[MAX_WORLD] = {nullptr};      // signal buffers: [0..W) ready flags, [W..2W) done flags,
+                                             // [2W] CTA counter (local use only)
+  size_t data_bytes = 0;
+  uint32_t epoch = 0;
+  std::vector<void*> opened;
+};
+static CommCtx g_comm;
+static std::mutex g_comm_mu;
+
+struct ArParams {
+  float* data[MAX_WORLD];
+  uint32_t* sig[MAX_WORLD];
+  int rank, world;
+  uint32_t epoch;
+  int64_t offset, count;  // elements (count % 4 == 0, offset % 4 == 0)
+  float scale;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_peer_f4(float* p, float4 v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ void wait_flags(const uint32_t* flags, int world, uint32_t epoch) {
+  // threads 0..world-1 poll one peer flag each; bounded so a lost peer traps instead of hanging
+  if ((int)threadIdx.x < world) {
+    long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
+      if (clock64() - t0 > 40000000000LL) {  // ~20 s
+        printf("ct_b200 comm: rank flag wait timeout (peer %d epoch %u)\n", threadIdx.x, epoch);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <bool ONE_SHOT>
+__global__ void __launch_bounds__(512)
+    allreduce_kernel(const ArParams p) {
+  const int W = p.world, r = p.rank;
+  uint32_t* my_sig = p.sig[r];
+  // ---- phase 0: publish readiness, wait for everyone ----
+  if (blockIdx.x == 0 && (int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + r, p.epoch);
+  wait_flags(my_sig, W, p.epoch);
+
+  const int64_t nvec = p.count >> 2;
+  if (ONE_SHOT) {
+    // every rank reduces the whole range into its own buffer
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 mine;
+      for (int q = 0; q < W; ++q) {
+        const float4 v = ld_peer_f4(p.data[q] + p.offset + 4 * i);
+        if (q == r) mine = v;
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      (void)mine;
+      acc.x *= p.scale; acc.y *= p.scale; acc.z *= p.scale; acc.w *= p.scale;
+      // results are staged: nobody may overwrite its input while peers still read it
+      // -> written after phase 2's barrier below (kept in registers is impossible for big ranges),
+      // so one-shot writes to a shadow half of the range instead: see host side (count doubled)
+      st_peer_f4(p.data[r] + p.offset + p.count + 4 * i, acc);
+    }
+  } else {
+    // slice owned by this rank (multiple of 4 elements)
+    const int64_t per = ((nvec + W - 1) / W);
+    const int64_t v0 = min(nvec, per * r), v1 = min(nvec, per * (r + 1));
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = v0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v1; i += stride) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int q = 0; q < W; ++q) {
+        const float4 v = ld_peer_f4(p.data[q] + p.offset + 4 * i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      acc.x *= p.scale; acc.y *= p.scale; acc.z *= p.scale; acc.w *= p.scale;
+#pragma unroll 4
+      for (int q = 0; q < W; ++q) st_peer_f4(p.data[q] + p.offset + 4 * i, acc);
+    }
+  }
+  // ---- phase 2: last CTA publishes completion and waits for the peers' completion ----
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int last;
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(my_sig + 2 * MAX_WORLD, 1u);
+    last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) my_sig[2 * MAX_WORLD] = 0;  // reset for the next call (stream-ordered)
+  if ((int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + MAX_WORLD + r, p.epoch);
+  wait_flags(my_sig + MAX_WORLD, W, p.epoch);
+}
+
+// one-shot epilogue: copy the staged result back over the input (local, after the barrier)
+__global__ void __launch_bounds__(256)
+    copy_f4_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+}
+
+// broadcast: every rank copies [offset, offset+count) from the root's buffer (after a barrier)
+__global__ void __launch_bounds__(512)
+    broadcast_kernel(const ArParams p, int root) {
+  const int W = p.world, r = p.rank;
+  uint32_t* my_sig = p.sig[r];
+  if (blockIdx.x == 0 && (int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + r, p.epoch);
+  wait_flags(my_sig, W, p.epoch);
+  if (r != root) {
+    const int64_t nvec = p.count >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x)
+      st_peer_f4(p.data[r] + p.offset + 4 * i, ld_peer_f4(p.data[root] + p.offset + 4 * i));
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int last;
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(my_sig + 2 * MAX_WORLD, 1u);
+    last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) my_sig[2 * MAX_WORLD] = 0;
+  if ((int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + MAX_WORLD + r, p.epoch);
+  wait_flags(my_sig + MAX_WORLD, W, p.epoch);
+}
+
+static void fill_params(ArParams& p, int64_t offset, int64_t count, float scale) {
+  for (int q = 0; q < g_comm.world; ++q) { p.data[q] = g_comm.data[q]; p.sig[q] = g_comm.sig[q]; }
+  p.rank = g_comm.rank; p.world = g_comm.world;
+  p.epoch = ++g_comm.epoch;
+  p.offset = offset; p.count = count; p.scale = scale;
+}
+
+}  // namespace ct
+
+using namespace ct;
+
+extern "C" int ct_comm_init(int rank, int world, int device, size_t data_bytes, void** local_data,
+                            void* data_handle_out, void* sig_handle_out) {
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  CT_REQUIRE(world >= 1 && world <= MAX_WORLD && rank >= 0 && rank < world, CT_ERR_BAD_ARG,
+             "ct_comm_init: bad rank/world %d/%d", rank, world);
+  CT_REQUIRE(!g_comm.ready && g_comm.rank < 0, CT_ERR_COMM, "ct_comm_init: already initialised");
+  CT_REQUIRE(local_data && data_handle_out && sig_handle_out, CT_ERR_BAD_ARG, "ct_comm_init: null out");
+  CT_CUDA_OK(cudaSetDevice(device));
+  data_bytes = (data_bytes + 255) & ~(size_t)255;
+  float* d = nullptr;
+  uint32_t* s = nullptr;
+  CT_CUDA_OK(cudaMalloc(&d, data_bytes));
+  CT_CUDA_OK(cudaMalloc(&s, sizeof(uint32_t) * (2 * MAX_WORLD + 8)));
+  CT_CUDA_OK(cudaMemset(d, 0, data_bytes));
+  CT_CUDA_OK(cudaMemset(s, 0, sizeof(uint32_t) * (2 * MAX_WORLD + 8)));
+  CT_CUDA_OK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)data_handle_out, d));
+  CT_CUDA_OK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)sig_handle_out, s));
+  g_comm.rank = rank; g_comm.world = world; g_comm.device = device;
+  g_comm.data[rank] = d; g_comm.sig[rank] = s;
+  g_comm.data_bytes = data_bytes;
+  g_comm.epoch = 0;
+  *local_data = d;
+  return 0;
+}
+
+extern "C" int ct_comm_connect(const void* data_handles, const void* sig_handles) {
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  CT_REQUIRE(g_comm.rank >= 0, CT_ERR_COMM, "ct_comm_connect: ct_comm_init first");
+  CT_REQUIRE(data_handles && sig_handles, CT_ERR_BAD_ARG, "ct_comm_connect: null handles");
+  const cudaIpcMemHandle_t* dh = (const cudaIpcMemHandle_t*)data_handles;
+  const cudaIpcMemHandle_t* sh = (const cudaIpcMemHandle_t*)sig_handles;
+  for (int q = 0; q < g_comm.world; ++q) {
+    if (q == g_comm.rank) continue;
+    void* pd = nullptr;
+    void* ps = nullptr;
+    CT_CUDA_OK(cudaIpcOpenMemHandle(&pd, dh[q], cudaIpcMemLazyEnablePeerAccess));
+    CT_CUDA_OK(cudaIpcOpenMemHandle(&ps, sh[q], cudaIpcMemLazyEnablePeerAccess));
+    g_comm.data[q] = (float*)pd;
+    g_comm.sig[q] = (uint32_t*)ps;
+    g_comm.opened.push_back(pd);
+    g_comm.opened.push_back(ps);
+  }
+  g_comm.ready = true;
+  return 0;
+}
+
+extern "C" int ct_allreduce_bucket(int64_t offset, int64_t count, float scale, int mode, int max_ctas,
+                                   void* stream) {
+  CT_REQUIRE(g_comm.ready, CT_ERR_COMM, "ct_allreduce_bucket: comm not initialised");
+  CT_REQUIRE(offset >= 0 && count >= 0 && (offset % 4) == 0 && (count % 4) == 0 &&
+                 (size_t)(offset + count) * 4 <= g_comm.data_bytes,
+             CT_ERR_BAD_ARG, "ct_allreduce_bucket: range [%lld,+%lld) must be 16-byte aligned and inside the buffer",
+             (long long)offset, (long long)count);
+  CT_REQUIRE(mode == 0 || mode == 1, CT_ERR_BAD_ARG, "ct_allreduce_bucket: mode 0 (auto/two-shot) or 1 (one-shot)");
+  if (count == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  ArParams p;
+  {
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    fill_params(p, offset, count, scale);
+  }
+  if (max_ctas <= 0) max_ctas = 32;
+  const int64_t nvec = count >> 2;
+  if (mode == 1) {
+    // one-shot needs a staging area of `count` floats right after the range
+    CT_REQUIRE((size_t)(offset + 2 * count) * 4 <= g_comm.data_bytes, CT_ERR_WORKSPACE,
+               "ct_allreduce_bucket: one-shot needs a staging area after the range");
+    int64_t ctas = (nvec + 511) / 512;
+    if (ctas > max_ctas) ctas = max_ctas;
+    allreduce_kernel<true><<<(unsigned)ctas, 512, 0, st>>>(p);
+    CT_LAUNCH_OK();
+    copy_f4_kernel<<<(unsigned)ctas, 256, 0, st>>>(g_comm.data[g_comm.rank] + offset,
+                                                    g_comm.data[g_comm.rank] + offset + count, nvec);
+    CT_LAUNCH_OK();
+    return 0;
+  }
+  int64_t per = (nvec + g_comm.world - 1) / g_comm.world;
+  int64_t ctas = (per + 511) / 512;
+  if (ctas > max_ctas) ctas = max_ctas;
+  if (ctas < 1) ctas = 1;
+  allreduce_kernel<false><<<(unsigned)ctas, 512, 0, st>>>(p);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_broadcast(int64_t offset, int64_t count, int root, void* stream) {
+  CT_REQUIRE(g_comm.ready, CT_ERR_COMM, "ct_broadcast: comm not initialised");
+  CT_REQUIRE(offset >= 0 && count >= 0 && (offset % 4) == 0 && (count % 4) == 0 &&
+                 (size_t)(offset + count) * 4 <= g_comm.data_bytes && root >= 0 && root < g_comm.world,
+             CT_ERR_BAD_ARG, "ct_broadcast: bad range/root");
+  if (count == 0) return 0;
+  ArParams p;
+  {
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    fill_params(p, offset, count, 1.f);
+  }
+  broadcast_kernel<<<32, 512, 0, (cudaStream_t)stream>>>(p, root);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_comm_finalize(void) {
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  if (g_comm.rank < 0) return 0;
+  cudaDeviceSynchronize();  // teardown only
+  for (void* p : g_comm.opened) cudaIpcCloseMemHandle(p);
+  g_comm.opened.clear();
+  if (g_comm.data[g_comm.rank]) cudaFree(g_comm.data[g_comm.rank]);
+  if (g_comm.sig[g_comm.rank]) cudaFree(g_comm.sig[g_comm.rank]);
+  g_comm = CommCtx();
+  return 0;
+}

@@ -56,7 +56,7 @@ int sm_count();  // cached multiprocessor count of the current device
 // dtype enum shared with include/ct_b200.h
 enum : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 // activation enum shared with include/ct_b200.h
-enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU_ERF = 2, ACT_GELU_TANH = 3 };
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU_ERF = 2, ACT_GELU_TANH = 3, ACT_TANH = 4 };
 
 #ifdef __CUDACC__
 
@@ -104,6 +104,7 @@ __device__ __forceinline__ float act_apply(float x, int act) {
       float hx = 0.5f * x;
       return fmaf(hx, tanh_approx(u), hx);
     }
+    case ACT_TANH: return tanhf(x);  // BERT pooler, modeling_bert.py:283-286
     default: return x;
   }
 }
@@ -118,6 +119,10 @@ __device__ __forceinline__ float act_grad(float x, int act) {
     case ACT_GELU_TANH: {
       float t = tanh_approx(0.79788456f * x * (1.f + 0.044715f * x * x));
       return 0.5f * x * ((1.f - t * t) * (0.79788456f + 0.1070322243f * x * x)) + 0.5f * (1.f + t);
+    }
+    case ACT_TANH: {
+      float t = tanhf(x);
+      return 1.f - t * t;
     }
     default: return 1.f;
   }

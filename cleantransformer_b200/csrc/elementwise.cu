@@ -133,7 +133,7 @@ extern "C" int ct_colsum(const void* x, int x_dtype, int64_t ld, float* out, int
 extern "C" int ct_act_fwd(const void* x, int x_dtype, void* y, int y_dtype, int act, int64_t n,
                           void* stream) {
   CT_REQUIRE(x && y, CT_ERR_BAD_ARG, "ct_act_fwd: null pointer");
-  CT_REQUIRE(dt_any_ok(x_dtype) && dt_any_ok(y_dtype) && act >= 0 && act <= 3, CT_ERR_UNSUPPORTED,
+  CT_REQUIRE(dt_any_ok(x_dtype) && dt_any_ok(y_dtype) && act >= 0 && act <= 4, CT_ERR_UNSUPPORTED,
              "ct_act_fwd: dtype/act");
   if (n <= 0) return 0;
   act_fwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, y, y_dtype, act, n);
@@ -145,7 +145,7 @@ extern "C" int ct_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dty
                           int dx_dtype, int act, int64_t n, void* stream) {
   CT_REQUIRE(dy && x && dx, CT_ERR_BAD_ARG, "ct_act_bwd: null pointer");
   CT_REQUIRE(dt_any_ok(dy_dtype) && dt_any_ok(x_dtype) && dt_any_ok(dx_dtype) && act >= 0 &&
-                 act <= 3,
+                 act <= 4,
              CT_ERR_UNSUPPORTED, "ct_act_bwd: dtype/act");
   if (n <= 0) return 0;
   act_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, x, x_dtype, dx,

@@ -482,7 +482,7 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
   CT_REQUIRE(a.beta == 0.f || a.beta == 1.f, CT_ERR_BAD_ARG, "ct_gemm: beta must be 0 or 1");
   CT_REQUIRE(a.beta == 0.f || a.c_dtype == DT_F32, CT_ERR_UNSUPPORTED,
              "ct_gemm: beta=1 requires f32 C");
-  CT_REQUIRE(a.act >= 0 && a.act <= 3 && a.actgrad_act >= 0 && a.actgrad_act <= 3, CT_ERR_BAD_ARG,
+  CT_REQUIRE(a.act >= 0 && a.act <= 4 && a.actgrad_act >= 0 && a.actgrad_act <= 4, CT_ERR_BAD_ARG,
              "ct_gemm: bad activation enum");
   CT_REQUIRE(a.lda >= (a.a_mn_major ? a.M : a.K) && a.ldb >= (a.b_mn_major ? a.N : a.K) &&
                  a.ldc >= a.N,

@@ -1,0 +1,327 @@
+// loss_embed.cu — the two ends of the model around the block stack:
+//   * embedding gather / scatter-add   (modeling_bloom.py:190, modeling_gpt.py:169,184,
+//     modeling_bert.py:297-300 and the autograd scatter they imply)
+//   * shifted / plain cross-entropy    (modeling_bloom.py:224-230: torch CrossEntropyLoss, mean over
+//     all B*(S-1) shifted positions) producing the loss AND dlogits in one pass over the logits.
+// Both are HBM-bound. CE algorithmic bytes: rows * V * (sizeof(logit) read + sizeof(dlogit) write).
+#include "ct_common.cuh"
+#include "../../include/ct_b200.h"
+#include <cfloat>
+
+namespace ct {
+
+// ---------------------------------------------------------------------------------------------
+// embedding
+// ---------------------------------------------------------------------------------------------
+// out[t, :] (+)= W[ids[t], :]   one warp per token, float4 accesses when H % 4 == 0
+__global__ void __launch_bounds__(256)
+    embedding_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ W,
+                         float* __restrict__ out, int64_t T, int64_t H, int64_t V, int accumulate) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= T) return;
+  long long id = ids[w];
+  if (id < 0 || id >= V) id = 0;  // torch would raise; stay in bounds
+  const float* src = W + id * H;
+  float* dst = out + w * H;
+  if ((H & 3) == 0) {
+    for (int64_t c = lane * 4; c < H; c += 128) {
+      float4 v = *reinterpret_cast<const float4*>(src + c);
+      if (accumulate) {
+        float4 o = *reinterpret_cast<const float4*>(dst + c);
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      *reinterpret_cast<float4*>(dst + c) = v;
+    }
+  } else {
+    for (int64_t c = lane; c < H; c += 32) dst[c] = (accumulate ? dst[c] : 0.f) + src[c];
+  }
+}
+
+// dW[ids[t], :] += dout[t, :]  (red.global.add; rows equal to padding_idx are skipped like
+// torch.nn.Embedding(padding_idx=...) does, modeling_bert.py:273)
+__global__ void __launch_bounds__(256)
+    embedding_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dout,
+                         float* __restrict__ dW, int64_t T, int64_t H, int64_t V,
+                         long long padding_idx) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= T) return;
+  const long long id = ids[w];
+  if (id < 0 || id >= V || id == padding_idx) return;
+  const float* src = dout + w * H;
+  float* dst = dW + id * H;
+  if ((H & 3) == 0) {
+    for (int64_t c = lane * 4; c < H; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(src + c);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(v.x), "f"(v.y),
+                   "f"(v.z), "f"(v.w)
+                   : "memory");
+    }
+  } else {
+    for (int64_t c = lane; c < H; c += 32) atomicAdd(dst + c, src[c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross entropy
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long ce_target(const long long* labels, int64_t r, int64_t S, int shift) {
+  if (!shift) return labels[r];
+  // modeling_bloom.py:224-225: logits[..., :-1, :] vs labels[..., 1:]
+  return ((r % S) < S - 1) ? labels[r + 1] : -100;
+}
+
+// stats[0] = number of rows with a valid target
+__global__ void ce_count_kernel(const long long* __restrict__ labels, int64_t rows, int64_t S, int shift,
+                                long long ignore_index, int64_t V, float* __restrict__ stats) {
+  __shared__ int red[32];
+  int cnt = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const long long t = ce_target(labels, r, S, shift);
+    cnt += (t != ignore_index && t >= 0 && t < V) ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    atomicAdd(stats, (float)s);
+  }
+}
+
+constexpr int CE_THREADS = 512;
+
+template <typename T>
+__device__ __forceinline__ float ce_ld(const T* p, int64_t i);
+template <>
+__device__ __forceinline__ float ce_ld<float>(const float* p, int64_t i) { return p[i]; }
+template <>
+__device__ __forceinline__ float ce_ld<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) {
+  return __bfloat162float(p[i]);
+}
+
+// (max, sum of exp relative to max) pairs; a side that saw no element is (-inf, 0) and must not
+// produce exp(-inf - -inf) = NaN
+__device__ __forceinline__ void ms_merge(float& m, float& s, float m2, float s2) {
+  const float mn = fmaxf(m, m2);
+  const float a = (m == mn) ? 1.f : __expf(m - mn);
+  const float b = (m2 == mn) ? 1.f : __expf(m2 - mn);
+  s = s * a + s2 * b;
+  m = mn;
+}
+
+__device__ __forceinline__ float2 block_max_sum(float m, float s, float* red) {
+  // combine (max, sum of exp relative to max) across the block
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    ms_merge(m, s, m2, s2);
+  }
+  if (lane == 0) { red[2 * w] = m; red[2 * w + 1] = s; }
+  __syncthreads();
+  if (w == 0) {
+    m = lane < (CE_THREADS >> 5) ? red[2 * lane] : -INFINITY;
+    s = lane < (CE_THREADS >> 5) ? red[2 * lane + 1] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      ms_merge(m, s, m2, s2);
+    }
+    if (lane == 0) { red[0] = m; red[1] = s; }
+  }
+  __syncthreads();
+  const float2 r = make_float2(red[0], red[1]);
+  __syncthreads();
+  return r;
+}
+
+// One CTA per row (grid-stride). Pass 1: online max / sum-exp. Pass 2: dlogits = (softmax - onehot)
+// * inv_count (row re-read, normally from L2).
+template <typename T>
+__global__ void __launch_bounds__(CE_THREADS)
+    ce_fwd_kernel(const T* __restrict__ logits, int64_t ld, const long long* __restrict__ labels,
+                  T* __restrict__ dlogits, int64_t ldd, float* __restrict__ row_loss,
+                  const float* __restrict__ stats, int64_t rows, int64_t V, int64_t S, int shift,
+                  long long ignore_index) {
+  __shared__ float red[2 * (CE_THREADS >> 5)];
+  const float inv_count = 1.f / fmaxf(stats[0], 1.f);
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const T* x = logits + r * ld;
+    const long long tgt = ce_target(labels, r, S, shift);
+    const bool valid = (tgt != ignore_index && tgt >= 0 && tgt < V);
+    if (!valid) {
+      if (row_loss && threadIdx.x == 0) row_loss[r] = 0.f;
+      if (dlogits) {
+        T* d = dlogits + r * ldd;
+        for (int64_t c = threadIdx.x; c < V; c += CE_THREADS) d[c] = (T)0.f;
+      }
+      continue;
+    }
+    float m = -INFINITY, s = 0.f;
+    if (sizeof(T) == 2 && (V & 7) == 0 && (ld & 7) == 0) {
+      const uint4* x8 = reinterpret_cast<const uint4*>(x);
+      for (int64_t c = threadIdx.x; c < (V >> 3); c += CE_THREADS) {
+        const uint4 u = x8[c];
+        float v[8];
+        float2 f;
+        f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+        float mx = v[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) mx = fmaxf(mx, v[i]);
+        const float mn = fmaxf(m, mx);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += __expf(v[i] - mn);
+        s = s * ((m == mn) ? 1.f : __expf(m - mn)) + acc;
+        m = mn;
+      }
+    } else {
+      for (int64_t c = threadIdx.x; c < V; c += CE_THREADS) {
+        const float v = ce_ld<T>(x, c);
+        const float mn = fmaxf(m, v);
+        s = s * ((m == mn) ? 1.f : __expf(m - mn)) + __expf(v - mn);
+        m = mn;
+      }
+    }
+    const float2 ms = block_max_sum(m, s, red);
+    const float lse = ms.x + logf(ms.y);
+    if (row_loss && threadIdx.x == 0) row_loss[r] = lse - ce_ld<T>(x, tgt);
+    if (dlogits) {
+      T* d = dlogits + r * ldd;
+      if (sizeof(T) == 2 && (V & 7) == 0 && (ld & 7) == 0 && (ldd & 7) == 0) {
+        const uint4* x8 = reinterpret_cast<const uint4*>(x);
+        uint4* d8 = reinterpret_cast<uint4*>(d);
+        for (int64_t c = threadIdx.x; c < (V >> 3); c += CE_THREADS) {
+          const uint4 u = x8[c];
+          float v[8];
+          float2 f;
+          f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+          f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+          f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+          f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+          const int64_t c0 = c << 3;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float pgrad = __expf(v[i] - lse);
+            if (c0 + i == tgt) pgrad -= 1.f;
+            v[i] = pgrad * inv_count;
+          }
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+          d8[c] = o;
+        }
+      } else {
+        for (int64_t c = threadIdx.x; c < V; c += CE_THREADS) {
+          float pgrad = __expf(ce_ld<T>(x, c) - lse);
+          if (c == tgt) pgrad -= 1.f;
+          d[c] = (T)(pgrad * inv_count);
+        }
+      }
+    }
+  }
+}
+
+// loss = sum(row_loss) / count   (single block, deterministic order)
+__global__ void __launch_bounds__(1024)
+    ce_finalize_kernel(const float* __restrict__ row_loss, int64_t rows, const float* __restrict__ stats,
+                       float* __restrict__ loss) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int64_t r = threadIdx.x; r < rows; r += 1024) acc += row_loss[r];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = red[threadIdx.x];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) loss[0] = v / fmaxf(stats[0], 1.f);
+  }
+}
+
+// x *= *scalar unless *scalar == 1 (upstream dloss, e.g. a GradScaler factor)
+template <typename T>
+__global__ void __launch_bounds__(256)
+    scale_by_device_scalar_kernel(T* __restrict__ x, int64_t n, const float* __restrict__ scalar) {
+  const float s = *scalar;
+  if (s == 1.f) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = (T)((float)x[i] * s);
+}
+
+}  // namespace ct
+
+using namespace ct;
+
+extern "C" int ct_embedding_fwd(const int64_t* ids, const float* weight, float* out, int64_t T,
+                                int64_t H, int64_t V, int accumulate, void* stream) {
+  CT_REQUIRE(ids && weight && out, CT_ERR_BAD_ARG, "ct_embedding_fwd: null pointer");
+  if (T <= 0) return 0;
+  embedding_fwd_kernel<<<(unsigned)((T * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const long long*)ids, weight, out, T, H, V, accumulate);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_embedding_bwd(const int64_t* ids, const float* dout, float* dweight, int64_t T,
+                                int64_t H, int64_t V, int64_t padding_idx, void* stream) {
+  CT_REQUIRE(ids && dout && dweight, CT_ERR_BAD_ARG, "ct_embedding_bwd: null pointer");
+  if (T <= 0) return 0;
+  embedding_bwd_kernel<<<(unsigned)((T * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const long long*)ids, dout, dweight, T, H, V, (long long)padding_idx);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_cross_entropy_fwd(const void* logits, int dtype, int64_t ld, const int64_t* labels,
+                                    void* dlogits, int64_t ldd, float* loss, float* workspace,
+                                    int64_t rows, int64_t V, int64_t S, int shift,
+                                    int64_t ignore_index, void* stream) {
+  CT_REQUIRE(logits && labels && loss && workspace, CT_ERR_BAD_ARG, "ct_cross_entropy_fwd: null pointer");
+  CT_REQUIRE(dtype == DT_F32 || dtype == DT_BF16, CT_ERR_UNSUPPORTED, "ct_cross_entropy_fwd: dtype");
+  CT_REQUIRE(rows > 0 && V > 0 && (!shift || (S > 0 && rows % S == 0)), CT_ERR_BAD_ARG,
+             "ct_cross_entropy_fwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* stats = workspace;        // [0] = valid-row count
+  float* row_loss = workspace + 4; // [rows]
+  CT_CUDA_OK(cudaMemsetAsync(stats, 0, 16, st));
+  ce_count_kernel<<<64, 256, 0, st>>>((const long long*)labels, rows, S, shift, (long long)ignore_index, V, stats);
+  CT_LAUNCH_OK();
+  int64_t grid = rows;
+  const int64_t cap = (int64_t)sm_count() * 4;
+  if (grid > cap) grid = cap;
+  if (dtype == DT_BF16)
+    ce_fwd_kernel<__nv_bfloat16><<<(unsigned)grid, CE_THREADS, 0, st>>>(
+        (const __nv_bfloat16*)logits, ld, (const long long*)labels, (__nv_bfloat16*)dlogits, ldd, row_loss,
+        stats, rows, V, S, shift, (long long)ignore_index);
+  else
+    ce_fwd_kernel<float><<<(unsigned)grid, CE_THREADS, 0, st>>>(
+        (const float*)logits, ld, (const long long*)labels, (float*)dlogits, ldd, row_loss, stats, rows, V, S,
+        shift, (long long)ignore_index);
+  CT_LAUNCH_OK();
+  ce_finalize_kernel<<<1, 1024, 0, st>>>(row_loss, rows, stats, loss);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_scale_by_scalar(void* x, int dtype, int64_t n, const float* device_scalar, void* stream) {
+  CT_REQUIRE(x && device_scalar, CT_ERR_BAD_ARG, "ct_scale_by_scalar: null pointer");
+  CT_REQUIRE(dtype == DT_F32 || dtype == DT_BF16, CT_ERR_UNSUPPORTED, "ct_scale_by_scalar: dtype");
+  if (n <= 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+  if (dtype == DT_BF16)
+    scale_by_device_scalar_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (__nv_bfloat16*)x, n, device_scalar);
+  else
+    scale_by_device_scalar_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((float*)x, n,
+                                                                                           device_scalar);
+  CT_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,224 @@
+"""DistributedDataParallel — the wrapper the reference's DDP example constructs
+(`DDP(model, device_ids=[local_rank])`, examples/ft_bloom_DDP.py:99), built the way README.md:46-52
+describes the hand-rolled version: (1) parameter sync at construction, (2) gradient buckets,
+(3) bucket reduction overlapped with the rest of backward.
+
+Call-compatible surface (what the example uses): ctor `(module, device_ids=[r])`, `.module`,
+`__call__/forward(**kw)`, `parameters()`, `state_dict()` with the `module.` prefix
+(ft_bloom_DDP.py:99,124,150,156), `train()/eval()`.
+
+B200 design
+  * all parameters are flattened into one arena (arena.py); its gradient buffer is the symmetric,
+    peer-mapped buffer of csrc/comm.cu, so every wgrad kernel writes straight into NVLink-visible
+    memory and buckets are plain [lo, hi) ranges of that buffer (no copies in or out);
+  * buckets are laid out in reverse parameter order (~ the order gradients appear in backward),
+    ~25 MiB each like torch's default; a bucket is launched on a side stream the moment all of its
+    gradients have been enqueued (functional.grad_written) — the all-reduce kernel itself waits for
+    the peers with flags in the same symmetric memory;
+  * averaging (1/world) is fused into the all-reduce kernel;
+  * `comm="nccl"` keeps torch.distributed.all_reduce (NCCL on GPUs, gloo in the CPU tests) on the
+    same bucket layout as the baseline/oracle.
+Parameters used more than once per step (tied embedding / lm_head) are reduced when the last of
+their gradients has been written (`_ct_expected_writes`, set by EmbeddingFn / tie helpers), in
+practice at the end of backward.
+"""
+import ctypes
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .arena import ParamArena
+
+BUCKET_CAP_MB = 25
+
+
+class _CudaView:
+    """Non-owning __cuda_array_interface__ view of library-owned device memory."""
+
+    def __init__(self, ptr, numel):
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+def plan_buckets(sizes_offsets, cap_elems):
+    """sizes_offsets: [(offset, numel_padded)] in arena order. Returns [(lo, hi, [param indices])]
+    covering the arena back to front in chunks of about cap_elems."""
+    buckets, cur, cur_lo, cur_hi = [], [], None, None
+    for idx in range(len(sizes_offsets) - 1, -1, -1):
+        off, n = sizes_offsets[idx]
+        if cur and (cur_hi - off) > cap_elems and (cur_hi - cur_lo) > 0:
+            buckets.append((cur_lo, cur_hi, cur))
+            cur, cur_lo, cur_hi = [], None, None
+        if not cur:
+            cur_hi = off + n
+        cur.append(idx)
+        cur_lo = off
+    if cur:
+        buckets.append((cur_lo, cur_hi, cur))
+    return buckets
+
+
+class DistributedDataParallel(torch.nn.Module):
+    def __init__(self, module, device_ids=None, output_device=None, bucket_cap_mb=BUCKET_CAP_MB,
+                 comm=None, process_group=None, max_ctas=32, **unused):
+        super().__init__()
+        if not dist.is_initialized():
+            raise RuntimeError("DistributedDataParallel needs torch.distributed.init_process_group first "
+                               "(it is only the bootstrap channel for the P2P path)")
+        self.module = module
+        self.group = process_group
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        params = [p for p in module.parameters() if p.requires_grad]
+        if not params:
+            raise ValueError("DistributedDataParallel: module has no trainable parameters")
+        self.device = params[0].device
+        on_gpu = self.device.type == "cuda"
+        self.comm = comm or os.environ.get("CT_DDP_COMM") or ("p2p" if on_gpu else "nccl")
+        if self.comm == "p2p" and not on_gpu:
+            raise RuntimeError("comm='p2p' needs CUDA parameters")
+        self.max_ctas = max_ctas
+        grad_buf = None
+        n_total = sum((p.numel() + 63) // 64 * 64 for p in params)
+        if self.comm == "p2p" and self.world > 1:
+            grad_buf = self._init_p2p(n_total)
+        self.arena = ParamArena(params, grad_buffer=grad_buf)
+        # (1) parameter / buffer sync from rank 0 (README.md:47; torch DDP's _sync_module_states)
+        dist.broadcast(self.arena.flat, 0, group=self.group)
+        for b in module.buffers():
+            if b.numel():
+                dist.broadcast(b, 0, group=self.group)
+        for p in self.arena.params:
+            p._ct_shadow_ver = -1
+        # (2) buckets
+        so = []
+        for i, p in enumerate(self.arena.params):
+            end = self.arena.offsets[i + 1] if i + 1 < len(self.arena.params) else self.arena.numel
+            so.append((self.arena.offsets[i], end - self.arena.offsets[i]))
+        self.buckets = plan_buckets(so, int(bucket_cap_mb * 1024 * 1024 // 4))
+        self._bucket_of = {}
+        for bi, (_, _, idxs) in enumerate(self.buckets):
+            for i in idxs:
+                self._bucket_of[id(self.arena.params[i])] = bi
+        self._pending = None
+        self._launched = None
+        self._writes = None
+        self._cb_queued = False
+        self._comm_stream = torch.cuda.Stream(device=self.device) if on_gpu else None
+        self.require_backward_grad_sync = True
+        # (3) hooks: our kernels announce gradients through functional.grad_written; gradients that
+        # come from torch autograd (plain nn modules) through post-accumulate hooks
+        for p in self.arena.params:
+            hooks = getattr(p, "_ct_grad_hooks", None)
+            if hooks is None:
+                p._ct_grad_hooks = hooks = []
+            hooks.append(self._on_grad_written)
+            p.register_post_accumulate_grad_hook(self._on_autograd_grad)
+
+    # ---------------------------------------------------------------- P2P bootstrap
+    def _init_p2p(self, n_total):
+        lib = _lib.load()
+        local = ctypes.c_void_p()
+        dh = ctypes.create_string_buffer(64)
+        sh = ctypes.create_string_buffer(64)
+        nbytes = n_total * 4
+        _lib.check(lib.ct_comm_init(self.rank, self.world, self.device.index, nbytes, ctypes.byref(local), dh, sh),
+                   "ct_comm_init")
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (dh.raw, sh.raw), group=self.group)
+        dhs = b"".join(g[0] for g in gathered)
+        shs = b"".join(g[1] for g in gathered)
+        _lib.check(lib.ct_comm_connect(dhs, shs), "ct_comm_connect")
+        dist.barrier(group=self.group)
+        return torch.as_tensor(_CudaView(local.value, n_total), device=self.device)
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, *args, **kwargs):
+        if torch.is_grad_enabled() and self.require_backward_grad_sync:
+            self._begin_step()
+        return self.module(*args, **kwargs)
+
+    def _begin_step(self):
+        self._pending = [len(idxs) for (_, _, idxs) in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._writes = {}
+        self._cb_queued = False
+
+    # ---------------------------------------------------------------- gradient notifications
+    def _on_autograd_grad(self, p):
+        view = p._ct_grad_view
+        if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+            view.copy_(p.grad)  # gradient produced by torch autograd outside the arena: move it in
+            p.grad = view
+        self._on_grad_written(p)
+
+    def _on_grad_written(self, p):
+        if self._pending is None or not self.require_backward_grad_sync:
+            return
+        if not self._cb_queued:
+            self._cb_queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(self._finish_backward)
+        n = self._writes.get(id(p), 0) + 1
+        self._writes[id(p)] = n
+        if n != getattr(p, "_ct_expected_writes", 1):
+            return
+        bi = self._bucket_of[id(p)]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        if self._launched[bi] or self.world == 1:
+            self._launched[bi] = True
+            return
+        self._launched[bi] = True
+        lo, hi, _ = self.buckets[bi]
+        if self.comm == "p2p":
+            cur = torch.cuda.current_stream(self.device)
+            self._comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self._comm_stream):
+                _lib.check(_lib.load().ct_allreduce_bucket(lo, hi - lo, 1.0 / self.world, 0, self.max_ctas,
+                                                           self._comm_stream.cuda_stream), "ct_allreduce_bucket")
+        else:  # baseline / oracle path: library collective on the same bucket layout
+            seg = self.arena.grad[lo:hi]
+            if self._comm_stream is not None:
+                self._comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(self._comm_stream):
+                    dist.all_reduce(seg, group=self.group)
+                    seg.mul_(1.0 / self.world)
+            else:
+                dist.all_reduce(seg, group=self.group)
+                seg.mul_(1.0 / self.world)
+
+    def _finish_backward(self):
+        # gradients that never arrived (unused parameters) or multi-use parameters still pending:
+        # reduce whatever is left, in bucket order (identical on every rank)
+        for bi in range(len(self.buckets)):
+            if not self._launched[bi]:
+                self._launch(bi)
+        if self._comm_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
+        self._pending = None
+
+    # ---------------------------------------------------------------- misc surface
+    def no_sync(self):
+        ddp = self
+
+        class _NoSync:
+            def __enter__(self_inner):
+                ddp.require_backward_grad_sync = False
+
+            def __exit__(self_inner, *a):
+                ddp.require_backward_grad_sync = True
+
+        return _NoSync()
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            if name == "module":
+                raise
+            return getattr(self.module, name)

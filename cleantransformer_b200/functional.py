@@ -1,0 +1,344 @@
+"""Autograd glue: torch.autograd.Function wrappers around the C-ABI kernels (ops.py).
+
+Numerics contract = the reference under torch.autocast(bfloat16): fp32 master parameters, fp32
+residual stream / LayerNorm / softmax statistics / loss, bf16 (or fp16) tensor-core operands with
+fp32 accumulation. Parameter gradients are fp32 and are written by the wgrad kernels DIRECTLY into
+`param.grad` (or into a flat-arena view of it, see arena.py) instead of being returned to autograd:
+that removes autograd's accumulate copies and lets the DDP wrapper see a gradient the moment the
+kernel that produced it has been enqueued.
+"""
+import math
+
+import torch
+
+from . import ops
+
+COMPUTE_DTYPE = torch.bfloat16
+
+
+def compute_dtype():
+    """bf16 unless the caller is inside torch.autocast(device_type='cuda', dtype=float16)."""
+    if torch.is_autocast_enabled():
+        d = torch.get_autocast_dtype("cuda")
+        if d in (torch.float16, torch.bfloat16):
+            return d
+    return COMPUTE_DTYPE
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter-side bookkeeping
+# ------------------------------------------------------------------------------------------------
+def shadow(param, dtype=None):
+    """Low-precision copy of an fp32 parameter for the tensor cores (autocast's weight cast),
+    cached per parameter version. arena.py points `_ct_shadow_view` into a flat bf16 buffer that the
+    fused AdamW kernel refreshes in the same pass as the fp32 update."""
+    dtype = dtype or compute_dtype()
+    if param.dtype == dtype:
+        return param.detach()
+    sh = getattr(param, "_ct_shadow", None)
+    if sh is not None and sh.dtype == dtype and getattr(param, "_ct_shadow_ver", -1) == param._version \
+            and sh.device == param.device:
+        return sh
+    target = getattr(param, "_ct_shadow_view", None)
+    if target is not None and (target.dtype != dtype or target.device != param.device):
+        target = None
+    sh = ops.cast(param.detach(), dtype, out=target)
+    param._ct_shadow = sh
+    param._ct_shadow_ver = param._version
+    return sh
+
+
+def grad_buffer(param):
+    """(f32 tensor the gradient must be written into, accumulate?)."""
+    g = param.grad
+    if g is not None:
+        return g, True
+    view = getattr(param, "_ct_grad_view", None)
+    if view is None or view.device != param.device:
+        view = torch.empty(param.shape, dtype=torch.float32, device=param.device)
+    param.grad = view
+    return view, False
+
+
+def grad_written(param):
+    """Tell listeners (the DDP wrapper) that a kernel producing this gradient has been enqueued."""
+    hooks = getattr(param, "_ct_grad_hooks", None)
+    if hooks:
+        for h in hooks:
+            h(param)
+
+
+def _as2d(x):
+    return x.reshape(-1, x.shape[-1])
+
+
+def _low(x, dtype):
+    """Activation cast to the compute dtype (autocast's input cast)."""
+    x = x.contiguous()
+    return x if x.dtype == dtype else ops.cast(x, dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    """transformer.py:79-89. Returns y in `out_dtype`, plus an optional second copy in `out2_dtype`
+    (e.g. f32 for the residual stream + bf16 for the next GEMM)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype, out2_dtype):
+        need = x.requires_grad or weight.requires_grad or bias.requires_grad
+        w = weight.detach().reshape(-1)
+        b = bias.detach().reshape(-1)
+        y, y2, mean, rstd = ops.layernorm_fwd(x.detach(), w, b, eps, out_dtype, out2_dtype, save_stats=need)
+        ctx.save_for_backward(x, mean, rstd)
+        ctx.weight, ctx.bias = weight, bias
+        ctx.x_dtype = x.dtype
+        if y2 is None:
+            return y
+        return y, y2
+
+    @staticmethod
+    def backward(ctx, dy, dy2=None):
+        x, mean, rstd = ctx.saved_tensors
+        weight, bias = ctx.weight, ctx.bias
+        gw, acc_w = grad_buffer(weight) if weight.requires_grad else (None, False)
+        gb, acc_b = grad_buffer(bias) if bias.requires_grad else (None, False)
+        if gw is not None and gb is not None and acc_w != acc_b:
+            # keep one accumulate flag for the fused kernel: zero the fresh one
+            (gw if not acc_w else gb).zero_()
+            acc_w = acc_b = True
+        dx = ops.layernorm_bwd(dy, x, weight.detach().reshape(-1), mean, rstd,
+                               gw.view(-1) if gw is not None else None,
+                               gb.view(-1) if gb is not None else None,
+                               acc_w if gw is not None else acc_b, dy2=dy2,
+                               dx_dtype=torch.float32 if ctx.x_dtype == torch.float32 else ctx.x_dtype)
+        if gw is not None:
+            grad_written(weight)
+        if gb is not None:
+            grad_written(bias)
+        return dx, None, None, None, None, None
+
+
+def layer_norm(x, weight, bias, eps, out_dtype=None, out2_dtype=None):
+    return LayerNormFn.apply(x, weight, bias, eps, out_dtype or x.dtype, out2_dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# Linear / Conv1D (+ bias, activation, residual)
+# ------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = act(x @ W^T + b) (+ residual). W: nn.Linear [out,in] or Conv1D [in,out] (w_in_out)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, residual, out_dtype, w_in_out):
+        cd = compute_dtype()
+        x2 = _low(_as2d(x.detach()), cd)
+        w16 = shadow(weight, cd)
+        N = weight.shape[1] if w_in_out else weight.shape[0]
+        need = x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad) or \
+            (residual is not None and residual.requires_grad)
+        res2 = _as2d(residual.detach()).contiguous() if residual is not None else None
+        y, pre = ops.linear_fwd(x2, w16, bias.detach() if bias is not None else None, act, res2, out_dtype,
+                                save_preact=(act != ops.ACT_NONE and need), w_in_out=w_in_out)
+        ctx.save_for_backward(x2, pre)
+        ctx.weight, ctx.bias, ctx.act, ctx.w_in_out = weight, bias, act, w_in_out
+        ctx.x_shape, ctx.x_dtype, ctx.x_req = x.shape, x.dtype, x.requires_grad
+        ctx.has_res = residual is not None
+        ctx.res_dtype = residual.dtype if residual is not None else None
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, pre = ctx.saved_tensors
+        weight, bias = ctx.weight, ctx.bias
+        cd = x2.dtype
+        dres = None
+        if ctx.has_res:
+            dres = dy if dy.dtype == ctx.res_dtype else ops.cast(dy.contiguous(), ctx.res_dtype)
+        d2 = _as2d(dy).contiguous()
+        if ctx.act != ops.ACT_NONE:
+            d2 = ops.act_bwd(d2, pre, ctx.act, out_dtype=cd)
+        else:
+            d2 = _low(d2, cd)
+        if weight.requires_grad:
+            gw, acc = grad_buffer(weight)
+            gbias = None
+            if bias is not None and bias.requires_grad:
+                gbias, accb = grad_buffer(bias)
+                if accb != acc:
+                    (gbias if not accb else gw).zero_()
+                    acc = True
+            ops.linear_wgrad(d2, x2, gw, gbias, accumulate=acc, w_in_out=ctx.w_in_out)
+            grad_written(weight)
+            if gbias is not None:
+                grad_written(bias)
+        elif bias is not None and bias.requires_grad:
+            gbias, accb = grad_buffer(bias)
+            ops.colsum(d2, gbias, accb)
+            grad_written(bias)
+        dx = None
+        if ctx.x_req:
+            dx = ops.linear_dgrad(d2, shadow(weight, cd), out_dtype=ctx.x_dtype, w_in_out=ctx.w_in_out)
+            dx = dx.view(ctx.x_shape)
+        return dx, None, None, None, dres, None, None
+
+
+def linear(x, weight, bias=None, act=ops.ACT_NONE, residual=None, out_dtype=None, w_in_out=False):
+    if out_dtype is None:
+        out_dtype = residual.dtype if residual is not None else compute_dtype()
+    return LinearFn.apply(x, weight, bias, act, residual, out_dtype, w_in_out)
+
+
+# ------------------------------------------------------------------------------------------------
+# Attention core
+# ------------------------------------------------------------------------------------------------
+LAYOUT_BLOOM = "bloom"        # fused [B,S,H,3,D]   (modeling_bloom.py:81-82)
+LAYOUT_GPT = "gpt"            # fused [B,S,3,H,D]   (modeling_gpt.py:72)
+
+
+def split_packed(qkv, n_head, layout):
+    """Strided [B,H,S,D] views of q, k, v inside a packed projection output."""
+    B, S, three_h = qkv.shape
+    D = three_h // (3 * n_head)
+    if layout == LAYOUT_BLOOM:
+        t = qkv.view(B, S, n_head, 3, D)
+        return [t[:, :, :, i, :].permute(0, 2, 1, 3) for i in range(3)]
+    t = qkv.view(B, S, 3, n_head, D)
+    return [t[:, :, i, :, :].permute(0, 2, 1, 3) for i in range(3)]
+
+
+class PackedAttentionFn(torch.autograd.Function):
+    """softmax(QK^T*scale + bias/masks) V on a packed QKV tensor (training / prefill, no cache)."""
+
+    @staticmethod
+    def forward(ctx, qkv, n_head, layout, scale, causal, causal_fill, kbias2, first_valid):
+        qkv_d = qkv.detach().contiguous()
+        q, k, v = split_packed(qkv_d, n_head, layout)
+        o, lse2 = ops.attn_fwd(q, k, v, scale, causal, causal_fill, kbias2, first_valid,
+                               need_lse=qkv.requires_grad)
+        ctx.save_for_backward(qkv_d, o, lse2, kbias2, first_valid)
+        ctx.cfg = (n_head, layout, scale, causal, causal_fill)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse2, kbias2, first_valid = ctx.saved_tensors
+        n_head, layout, scale, causal, causal_fill = ctx.cfg
+        dqkv = torch.empty_like(qkv)
+        q, k, v = split_packed(qkv, n_head, layout)
+        dq, dk, dv = split_packed(dqkv, n_head, layout)
+        do = do.contiguous()
+        if do.dtype != qkv.dtype:
+            do = ops.cast(do, qkv.dtype)
+        ops.attn_bwd(do, q, k, v, o, lse2, dq, dk, dv, scale, causal, causal_fill, kbias2, first_valid)
+        return dqkv, None, None, None, None, None, None, None
+
+
+class SeparateAttentionFn(torch.autograd.Function):
+    """Same, for three separate [B,S,H*D] projections (transformer.py:37-57)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, n_head, scale, causal, causal_fill, kbias2, first_valid):
+        B, Sq, HD = q.shape
+        D = HD // n_head
+        qd, kd, vd = [t.detach().contiguous() for t in (q, k, v)]
+        q4, k4, v4 = [t.view(B, t.shape[1], n_head, D).permute(0, 2, 1, 3) for t in (qd, kd, vd)]
+        need = q.requires_grad or k.requires_grad or v.requires_grad
+        o, lse2 = ops.attn_fwd(q4, k4, v4, scale, causal, causal_fill, kbias2, first_valid, need_lse=need)
+        ctx.save_for_backward(qd, kd, vd, o, lse2, kbias2, first_valid)
+        ctx.cfg = (n_head, scale, causal, causal_fill)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qd, kd, vd, o, lse2, kbias2, first_valid = ctx.saved_tensors
+        n_head, scale, causal, causal_fill = ctx.cfg
+        B, Sq, HD = qd.shape
+        D = HD // n_head
+        v4 = lambda t: t.view(B, t.shape[1], n_head, D).permute(0, 2, 1, 3)
+        dq, dk, dv = torch.empty_like(qd), torch.empty_like(kd), torch.empty_like(vd)
+        do = do.contiguous()
+        if do.dtype != qd.dtype:
+            do = ops.cast(do, qd.dtype)
+        ops.attn_bwd(do, v4(qd), v4(kd), v4(vd), o, lse2, v4(dq), v4(dk), v4(dv), scale, causal,
+                     causal_fill, kbias2, first_valid)
+        return dq, dk, dv, None, None, None, None, None, None
+
+
+def attention_cached(q4, k4, v4, scale, causal, causal_fill, kbias2, first_valid):
+    """Inference with a KV cache: q4 [B,H,Sq,D], k4/v4 [B,H,Sk,D] (any strides). No autograd."""
+    o, _ = ops.attn_fwd(q4, k4, v4, scale, causal, causal_fill, kbias2, first_valid, need_lse=False)
+    return o
+
+
+# ------------------------------------------------------------------------------------------------
+# Embedding and LM loss
+# ------------------------------------------------------------------------------------------------
+class EmbeddingFn(torch.autograd.Function):
+    """sum_k weight_k[ids_k] (token + position + segment tables): modeling_bloom.py:190,
+    modeling_gpt.py:169-188, modeling_bert.py:297-300. Gradients are scattered straight into
+    weight.grad."""
+
+    @staticmethod
+    def forward(ctx, n_tables, padding_idx0, *args):
+        ids = args[:n_tables]
+        weights = args[n_tables:]
+        shape = torch.broadcast_shapes(*[i.shape for i in ids])
+        out = None
+        for i, w in zip(ids, weights):
+            i = i.expand(shape).contiguous()
+            out = ops.embedding_fwd(i, w.detach(), out, accumulate=out is not None)
+        ctx.ids = [i.expand(shape).contiguous() for i in ids]
+        ctx.weights = weights
+        ctx.padding_idx0 = padding_idx0
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        if dout.dtype != torch.float32:
+            dout = ops.cast(dout, torch.float32)
+        for k, (i, w) in enumerate(zip(ctx.ids, ctx.weights)):
+            if not w.requires_grad:
+                continue
+            g, acc = grad_buffer(w)
+            if not acc:
+                g.zero_()
+            ops.embedding_bwd(i, dout, g, ctx.padding_idx0 if k == 0 else -1)
+            grad_written(w)
+        return (None, None) + (None,) * (2 * len(ctx.ids))
+
+
+def embedding_sum(ids_list, weight_list, padding_idx0=-1):
+    return EmbeddingFn.apply(len(ids_list), padding_idx0, *ids_list, *weight_list)
+
+
+class LMLossFn(torch.autograd.Function):
+    """modeling_bloom.py:224-230: shifted cross entropy, mean over B*(S-1) positions. One pass over
+    the logits produces the loss and dlogits."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, shift):
+        B, S, V = logits.shape
+        l2 = logits.detach().reshape(B * S, V)
+        loss, dl = ops.cross_entropy_fwd(l2, labels.reshape(-1), S=S, shift=shift,
+                                         want_dlogits=logits.requires_grad)
+        ctx.dl = dl
+        ctx.shape = logits.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        dl = ctx.dl
+        ctx.dl = None
+        ops.scale_by_scalar(dl, dloss.contiguous().float())
+        return dl.view(ctx.shape), None, None
+
+
+def lm_loss(logits, labels, shift=True):
+    return LMLossFn.apply(logits, labels, shift)
+
+
+def default_scale(head_dim):
+    return 1.0 / math.sqrt(head_dim)

@@ -9,12 +9,13 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, check
+from ._lib import AttnArgs, AttnBwdArgs, GemmArgs, check
 
 F32, BF16, F16 = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_GELU_ERF, ACT_GELU_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_GELU_ERF, ACT_GELU_TANH, ACT_TANH = 0, 1, 2, 3, 4
 ACT_BY_NAME = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU_ERF,
-               "gelu_erf": ACT_GELU_ERF, "gelu_new": ACT_GELU_TANH, "gelu_tanh": ACT_GELU_TANH}
+               "gelu_erf": ACT_GELU_ERF, "gelu_new": ACT_GELU_TANH, "gelu_tanh": ACT_GELU_TANH,
+               "tanh": ACT_TANH}
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
@@ -222,3 +223,135 @@ def linear_wgrad(dy2d, x2d, dw, db=None, accumulate=False, w_in_out=False, impl=
         gemm(x2d, dy2d, K, N, M, a_mn=True, b_mn=True, out=dw, beta=1.0 if accumulate else 0.0, impl=impl)
     if db is not None:
         colsum(dy2d, db, accumulate)
+
+
+# ------------------------------------------------------------------------------------------------
+# Attention
+# ------------------------------------------------------------------------------------------------
+FLT_MAX = 3.4028234663852886e38
+MASK_BLOOM, MASK_GPT, MASK_BERT = 0, 1, 2
+
+
+def attn_mask_prep(attention_mask, n_head, mode, slopes=None):
+    """attention_mask [B,Sk] (1 = attend) -> (kbias2 [B,H|1,Sk] f32, first_valid [B] int32)."""
+    _req_cuda(attention_mask)
+    am = attention_mask.contiguous()
+    if am.dtype == torch.int64:
+        code = 3
+    elif am.dtype == torch.int32:
+        code = 4
+    else:
+        am = am if am.dtype == torch.float32 else cast(am, torch.float32)
+        code = F32
+    B, Sk = am.shape
+    heads = n_head if mode == MASK_BLOOM else 1
+    kb = torch.empty((B, heads, Sk), dtype=torch.float32, device=am.device)
+    fv = torch.empty((B,), dtype=torch.int32, device=am.device)
+    check(_lib.load().ct_attn_mask_prep(ptr(am), code, B, Sk, n_head, mode, ptr(slopes), ptr(kb),
+                                        ptr(fv), stream()), "ct_attn_mask_prep")
+    return kb, fv
+
+
+def _bhsd_strides(t):
+    """t viewed as [B, H, S, D] (any strides, D contiguous) -> (sb, sh, ss)."""
+    assert t.dim() == 4 and t.stride(3) == 1
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+def _fill_attn(a, q, k, v, o, lse2, scale, causal, causal_fill, kbias2, first_valid, impl):
+    B, H, Sq, D = q.shape
+    Sk = k.shape[2]
+    a.B, a.H, a.Sq, a.Sk, a.D = B, H, Sq, Sk, D
+    a.dtype = dt(q)
+    a.q = q.data_ptr(); a.q_sb, a.q_sh, a.q_ss = _bhsd_strides(q)
+    a.k = k.data_ptr(); a.k_sb, a.k_sh, a.k_ss = _bhsd_strides(k)
+    a.v = v.data_ptr(); a.v_sb, a.v_sh, a.v_ss = _bhsd_strides(v)
+    a.o = o.data_ptr(); a.o_sb, a.o_sh, a.o_ss = _bhsd_strides(o)
+    a.lse2 = ptr(lse2)
+    a.scale = scale
+    a.causal = 1 if causal else 0
+    a.causal_fill = causal_fill
+    if kbias2 is not None:
+        assert kbias2.dim() == 3 and kbias2.stride(2) == 1
+        a.kbias2 = kbias2.data_ptr()
+        a.kb_sb = kbias2.stride(0)
+        a.kb_sh = kbias2.stride(1) if kbias2.shape[1] > 1 else 0
+    a.first_valid = ptr(first_valid)
+    a.impl = impl
+
+
+def attn_fwd(q, k, v, scale, causal=False, causal_fill=-FLT_MAX, kbias2=None, first_valid=None,
+             need_lse=True, impl=0):
+    """q [B,H,Sq,D], k/v [B,H,Sk,D] as strided VIEWS (D contiguous). Returns (o [B,Sq,H*D], lse2)."""
+    _req_cuda(q, k, v)
+    B, H, Sq, D = q.shape
+    o = torch.empty((B, Sq, H * D), dtype=q.dtype, device=q.device)
+    o4 = o.view(B, Sq, H, D).permute(0, 2, 1, 3)
+    lse2 = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device) if need_lse else None
+    a = AttnArgs()
+    _fill_attn(a, q, k, v, o4, lse2, scale, causal, causal_fill, kbias2, first_valid, impl)
+    check(_lib.load().ct_attn_fwd(ctypes.byref(a), stream()), "ct_attn_fwd")
+    return o, lse2
+
+
+def attn_bwd(dout, q, k, v, o, lse2, dq, dk, dv, scale, causal=False, causal_fill=-FLT_MAX,
+             kbias2=None, first_valid=None, impl=0):
+    """dout/o [B,Sq,H*D]; q,k,v,dq,dk,dv [B,H,S,D] strided views; dq/dk/dv are written."""
+    B, H, Sq, D = q.shape
+    o4 = o.view(B, Sq, H, D).permute(0, 2, 1, 3)
+    dout = dout.contiguous()
+    a = AttnBwdArgs()
+    _fill_attn(a.f, q, k, v, o4, lse2, scale, causal, causal_fill, kbias2, first_valid, impl)
+    a.dout = dout.data_ptr()
+    a.dq = dq.data_ptr(); a.dq_sb, a.dq_sh, a.dq_ss = _bhsd_strides(dq)
+    a.dk = dk.data_ptr(); a.dk_sb, a.dk_sh, a.dk_ss = _bhsd_strides(dk)
+    a.dv = dv.data_ptr(); a.dv_sb, a.dv_sh, a.dv_ss = _bhsd_strides(dv)
+    delta = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
+    dq_acc = torch.empty((B, Sq, H, D), dtype=torch.float32, device=q.device) if D == 64 else None
+    a.delta = delta.data_ptr()
+    a.dq_accum = ptr(dq_acc)
+    check(_lib.load().ct_attn_bwd(ctypes.byref(a), stream()), "ct_attn_bwd")
+
+
+# ------------------------------------------------------------------------------------------------
+# Embedding / cross entropy
+# ------------------------------------------------------------------------------------------------
+def embedding_fwd(ids, weight, out=None, accumulate=False):
+    """out[..., :] (+)= weight[ids]; ids int64 [...], weight f32 [V,H] -> f32 [..., H]."""
+    _req_cuda(ids, weight)
+    ids = ids.contiguous()
+    V, H = weight.shape
+    if out is None:
+        out = torch.empty(tuple(ids.shape) + (H,), dtype=torch.float32, device=weight.device)
+        accumulate = False
+    check(_lib.load().ct_embedding_fwd(ptr(ids), ptr(weight), ptr(out), ids.numel(), H, V,
+                                       1 if accumulate else 0, stream()), "ct_embedding_fwd")
+    return out
+
+
+def embedding_bwd(ids, dout, dweight, padding_idx=-1):
+    ids = ids.contiguous()
+    dout = dout.contiguous()
+    V, H = dweight.shape
+    check(_lib.load().ct_embedding_bwd(ptr(ids), ptr(dout), ptr(dweight), ids.numel(), H, V,
+                                       int(padding_idx), stream()), "ct_embedding_bwd")
+
+
+def cross_entropy_fwd(logits2d, labels, S=0, shift=False, ignore_index=-100, want_dlogits=True):
+    """Returns (loss scalar f32 tensor, dlogits or None)."""
+    _req_cuda(logits2d, labels)
+    rows, V = logits2d.shape
+    labels = labels.contiguous()
+    dl = torch.empty_like(logits2d) if want_dlogits else None
+    loss = torch.empty((), dtype=torch.float32, device=logits2d.device)
+    ws = torch.empty(rows + 4, dtype=torch.float32, device=logits2d.device)
+    check(_lib.load().ct_cross_entropy_fwd(ptr(logits2d), dt(logits2d), logits2d.stride(0), ptr(labels),
+                                           ptr(dl), dl.stride(0) if dl is not None else 0, ptr(loss),
+                                           ptr(ws), rows, V, S, 1 if shift else 0, ignore_index,
+                                           stream()), "ct_cross_entropy_fwd")
+    return loss, dl
+
+
+def scale_by_scalar(x, scalar_f32):
+    check(_lib.load().ct_scale_by_scalar(ptr(x), dt(x), x.numel(), ptr(scalar_f32), stream()),
+          "ct_scale_by_scalar")

@@ -10,7 +10,7 @@
  *   - every tensor argument is a raw DEVICE pointer owned by the caller (PyTorch); the library never
  *     frees or retains it past the call. Only the ct_comm_* buffers are library-owned.
  *   - dtype enum: 0 = f32, 1 = bf16, 2 = f16.   activation enum: 0 none, 1 relu, 2 gelu_erf,
- *     3 gelu_tanh.
+ *     3 gelu_tanh, 4 tanh.
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises,
  *     nothing touches the legacy default stream; calls are CUDA-graph capturable unless noted.
  *   - return 0 on success, >0 = cudaError_t, <0 = library code (-1 bad argument/shape,
@@ -38,6 +38,7 @@ extern "C" {
 #define CT_ACT_RELU 1      /* transformer.py:100 */
 #define CT_ACT_GELU_ERF 2  /* modeling_bert.py:229 (torch.nn.GELU) */
 #define CT_ACT_GELU_TANH 3 /* modeling_bloom.py:335-345, modeling_gpt.py:112-122 */
+#define CT_ACT_TANH 4      /* modeling_bert.py:283-286 (pooler) */
 
 /* ---- library ------------------------------------------------------------------------------- */
 int ct_version(void);
@@ -145,6 +146,118 @@ int ct_gemm_dgrad(const void* dy, const void* w, int w_in_out, void* dx, int dx_
 /* dw (+)= dy^T @ x  as f32 [N,K] (or [K,N] when w_in_out);  db (+)= colsum(dy) when db != NULL */
 int ct_gemm_wgrad_bias(const void* dy, const void* x, int w_in_out, float* dw, float* db,
                        int accumulate, int64_t M, int64_t N, int64_t K, int ab_dtype, void* stream);
+
+
+/* ---- attention: QK^T -> (+ALiBi / mask) -> softmax -> PV, flash-style -------------------------- *
+ * One kernel replaces the batched GEMM + mask + softmax + batched GEMM + re-layout sequences of
+ *   CleanTransformer/models/modeling_bloom.py:99-116  (alibi.baddbmm, masked_fill(finfo.min), softmax, PV)
+ *   CleanTransformer/models/modeling_gpt.py:83-103    (w*b + -1e4*(1-b), + additive mask, softmax, PV)
+ *   CleanTransformer/transformer.py:41-57             (scores/sqrt(d) + additive mask, softmax, PV)
+ * without materialising the [B,H,Sq,Sk] score tensor.
+ *
+ * q/k/v element (b,h,s,d) lives at base + b*sb + h*sh + s*ss + d  (d contiguous), which covers the
+ * per-head interleaved fused QKV of Bloom (bloom:81-82), the blocked [Q|K|V] of GPT (gpt:72), three
+ * separate projections (transformer.py:37) and [b,h,t,d] KV caches (bloom:88-92, gpt:76-80).
+ * o has the merged-head layout the reference produces after transpose+view ([B,Sq,H*D]).
+ *
+ * score2(i,j) = log2e * ( scale * q_i.k_j )  + kbias2[b,h,j]            (log2 domain)
+ *   if causal and j > i + (Sk - Sq):  score2 = causal_fill*log2e + kbias2[b,h,j]
+ *   score2 = max(score2, -FLT_MAX)   (so a fully masked row is uniform, as masked_fill(finfo.min) is)
+ * kbias2 = log2e * (alibi_slope[h]*pos[b,j] + key_add[b,j]) comes from ct_attn_mask_prep.
+ * lse2[b,h,i] = log2(sum_j 2^score2(i,j)) is kept for the backward pass. */
+typedef struct {
+  int32_t B, H, Sq, Sk, D;
+  int32_t dtype; /* CT_BF16 or CT_F16 */
+  const void* q;
+  int64_t q_sb, q_sh, q_ss;
+  const void* k;
+  int64_t k_sb, k_sh, k_ss;
+  const void* v;
+  int64_t v_sb, v_sh, v_ss;
+  void* o;
+  int64_t o_sb, o_sh, o_ss;
+  float* lse2; /* [B,H,Sq], nullable for inference */
+  float scale;
+  int32_t causal;
+  float causal_fill;          /* -FLT_MAX (Bloom fill) or -1e4 (GPT, modeling_gpt.py:89) */
+  const float* kbias2;        /* nullable; element (b,h,j) at kbias2 + b*kb_sb + h*kb_sh + j */
+  int64_t kb_sb, kb_sh;
+  const int32_t* first_valid; /* [B] nullable: first key that is not hard-masked (left padding) */
+  int32_t impl;               /* 0 auto, 1 force tcgen05 (D == 64), 2 force SIMT */
+} ct_attn_args;
+int ct_attn_fwd(const ct_attn_args* args, void* stream);
+
+/* Backward: recomputes P from q,k,lse2; dq/dk/dv use the same (sb,sh,ss) addressing as q/k/v.
+ * delta ([B,H,Sq] f32) and dq_accum ([B,Sq,H,D] f32) are caller-allocated workspaces. */
+typedef struct {
+  ct_attn_args f; /* forward arguments (o = forward output, lse2 = saved statistics) */
+  const void* dout; /* same layout as o */
+  void* dq;
+  int64_t dq_sb, dq_sh, dq_ss;
+  void* dk;
+  int64_t dk_sb, dk_sh, dk_ss;
+  void* dv;
+  int64_t dv_sb, dv_sh, dv_ss;
+  float* delta;
+  float* dq_accum;
+} ct_attn_bwd_args;
+int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream);
+
+/* Build kbias2 / first_valid from the caller's attention_mask [B,Sk] (1 = attend).
+ * mask_dtype: CT_F32, 3 = int64, 4 = int32.
+ * mode 0 (Bloom, modeling_bloom.py:176-185,309-331): key_add = mask ? 0 : -FLT_MAX and ALiBi
+ *        pos = (cumsum(mask)-1)*mask times slopes[h]  -> kbias2 [B,H,Sk]
+ * mode 1 (GPT, modeling_gpt.py:176-179): key_add = (1-mask)*finfo(f32).min       -> kbias2 [B,1,Sk]
+ * mode 2 (BERT, modeling_bert.py:303-304): key_add = (1-mask)*-10000.0           -> kbias2 [B,1,Sk]
+ * slopes ([H] f32) only for mode 0. */
+int ct_attn_mask_prep(const void* attention_mask, int mask_dtype, int64_t B, int64_t Sk, int64_t H,
+                      int mode, const float* slopes, float* kbias2, int32_t* first_valid,
+                      void* stream);
+
+
+/* ---- embedding: modeling_bloom.py:190, modeling_gpt.py:169,184, modeling_bert.py:297-300 ------- *
+ * out[t,:] (+)= weight[ids[t],:]  (f32 weights, int64 ids); accumulate adds into `out` (position /
+ * segment embeddings). Backward scatters dout rows into dweight with red.add (dweight must hold the
+ * running gradient or zeros); rows equal to padding_idx receive no gradient (modeling_bert.py:273). */
+int ct_embedding_fwd(const int64_t* ids, const float* weight, float* out, int64_t T, int64_t H,
+                     int64_t V, int accumulate, void* stream);
+int ct_embedding_bwd(const int64_t* ids, const float* dout, float* dweight, int64_t T, int64_t H,
+                     int64_t V, int64_t padding_idx, void* stream);
+
+/* ---- cross entropy: modeling_bloom.py:224-230 (shift + torch CrossEntropyLoss, mean) ---------- *
+ * logits [rows, V] (bf16 or f32). shift != 0: row r = (b, s) is scored against labels[r + 1] and the
+ * last position of every length-S sequence is skipped; shift == 0: labels[r]. Rows whose target is
+ * ignore_index do not count. Writes loss (f32 scalar, mean over counted rows) and, when dlogits is
+ * non-NULL, dlogits = (softmax - onehot) / count in the logits dtype (zero on skipped rows).
+ * workspace: f32 [rows + 4]. */
+int ct_cross_entropy_fwd(const void* logits, int dtype, int64_t ld, const int64_t* labels,
+                         void* dlogits, int64_t ldd, float* loss, float* workspace, int64_t rows,
+                         int64_t V, int64_t S, int shift, int64_t ignore_index, void* stream);
+/* x *= *device_scalar (no-op when the scalar is 1.0): applies an upstream dloss to dlogits. */
+int ct_scale_by_scalar(void* x, int dtype, int64_t n, const float* device_scalar, void* stream);
+
+
+/* ---- DDP gradient all-reduce over NVLink/NVSwitch peer memory ---------------------------------- *
+ * Replaces the ncclAllReduce calls of torch's DDP reducer behind `DDP(model, device_ids=[rank])`
+ * (examples/ft_bloom_DDP.py:99,126,135; README.md:46-52). One process per GPU.
+ *   ct_comm_init     cudaMalloc a symmetric f32 buffer of data_bytes (+ a signal buffer) on `device`,
+ *                    return the local pointer and two 64-byte cudaIpcMemHandle blobs to publish
+ *   ct_comm_connect  data_handles / sig_handles: world x 64 bytes, rank-ordered, as gathered by the
+ *                    caller over its bootstrap channel (torch.distributed); maps every peer buffer
+ *   ct_allreduce_bucket  in place over elements [offset, offset+count) of the symmetric buffer on
+ *                    every rank: x = scale * sum_ranks x. mode 0 two-shot (reduce-scatter + all-gather
+ *                    by the slice owner), mode 1 one-shot (needs `count` spare floats after the range).
+ *                    Must be called in the same order by all ranks. max_ctas bounds the SMs used so
+ *                    backward compute keeps running (0 = default 32).
+ *   ct_broadcast     copy [offset, offset+count) from root's buffer to every rank's buffer.
+ * The buffers are library-owned (freed by ct_comm_finalize); PyTorch sees them as non-owning tensors. */
+int ct_comm_init(int rank, int world, int device, size_t data_bytes, void** local_data,
+                 void* data_handle_out, void* sig_handle_out);
+int ct_comm_connect(const void* data_handles, const void* sig_handles);
+int ct_allreduce_bucket(int64_t offset, int64_t count, float scale, int mode, int max_ctas,
+                        void* stream);
+int ct_broadcast(int64_t offset, int64_t count, int root, void* stream);
+int ct_comm_finalize(void);
 
 #ifdef __cplusplus
 }

@@ -126,6 +126,140 @@ def case_gemm_perf():
     return res
 
 
+
+def _attn_ref(q, k, v, scale, causal, causal_fill, kb2):
+    """fp32 torch restatement of the ct_b200.h score definition. q,k,v [B,H,S,D] (any dtype)."""
+    import torch
+    FLT_MAX = 3.4028234663852886e38
+    LOG2E = 1.4426950408889634
+    qf, kf, vf = q.float(), k.float(), v.float()
+    Sq, Sk = q.shape[2], k.shape[2]
+    s2 = (qf @ kf.transpose(2, 3)) * (scale * LOG2E)
+    kb = kb2[:, :, None, :] if kb2 is not None else 0.0
+    s2 = s2 + kb
+    if causal:
+        i = torch.arange(Sq, device=q.device)[:, None]; j = torch.arange(Sk, device=q.device)[None, :]
+        fut = j > i + (Sk - Sq)
+        fill = torch.full_like(s2, causal_fill * LOG2E if causal_fill > -1e30 else float("-inf")) + kb
+        s2 = torch.where(fut, fill, s2)
+    s2 = s2.clamp_min(-FLT_MAX)
+    m = s2.max(-1, keepdim=True).values
+    e = torch.exp2(s2 - m)
+    l = e.sum(-1, keepdim=True)
+    o = (e / l) @ vf
+    return o.transpose(1, 2).reshape(q.shape[0], Sq, -1), (m + torch.log2(l)).squeeze(-1)
+
+
+def _attn_case(B, H, Sq, Sk, D, causal, mode, impl, bwd=False, pad="none", causal_fill=None):
+    import torch
+    from cleantransformer_b200 import ops
+    torch.manual_seed(7)
+    dev = "cuda"
+    qkv = (torch.randn(B, Sk, H, 3, D, device=dev) * 1.0).bfloat16()
+    q = qkv[:, Sk - Sq:, :, 0, :].permute(0, 2, 1, 3); k = qkv[..., 1, :].permute(0, 2, 1, 3); v = qkv[..., 2, :].permute(0, 2, 1, 3)
+    kb2 = fv = None
+    if mode is not None:
+        mask = torch.ones(B, Sk, dtype=torch.long, device=dev)
+        for b in range(B):
+            n = Sk - (b * 37) % (Sk // 2)
+            if pad == "right": mask[b, n:] = 0
+            if pad == "left": mask[b, :Sk - n] = 0
+        slopes = None
+        if mode == 0:
+            from oracle import ct_oracle as O
+            slopes = O.alibi_slopes(H).to(dev)
+        kb2, fv = ops.attn_mask_prep(mask, H, mode, slopes)
+    cf = causal_fill if causal_fill is not None else -ops.FLT_MAX
+    scale = 1.0 / D ** 0.5
+    o, lse2 = ops.attn_fwd(q, k, v, scale, causal, cf, kb2, fv, impl=impl)
+    torch.cuda.synchronize()
+    kbe = kb2.expand(B, H, Sk) if kb2 is not None else None
+    qr, kr, vr = [t.float().detach().requires_grad_(True) for t in (q, k, v)]
+    oref, lref = _attn_ref(qr, kr, vr, scale, causal, cf, kbe)
+    res = {"o": rel(o, oref), "lse": float((lse2 - lref).abs().max())}
+    if bwd:
+        do = (torch.randn_like(o.float()) * 1.0).bfloat16()
+        dqkv = torch.zeros_like(qkv)
+        dq = dqkv[:, Sk - Sq:, :, 0, :].permute(0, 2, 1, 3); dk = dqkv[..., 1, :].permute(0, 2, 1, 3); dv = dqkv[..., 2, :].permute(0, 2, 1, 3)
+        ops.attn_bwd(do, q, k, v, o, lse2, dq, dk, dv, scale, causal, cf, kb2, fv, impl=impl)
+        torch.cuda.synchronize()
+        oref.backward(do.float())
+        res.update({"dq": rel(dq, qr.grad), "dk": rel(dk, kr.grad), "dv": rel(dv, vr.grad)})
+    return res
+
+
+def mk_attn(*a, **kw):
+    def f():
+        return _attn_case(*a, **kw)
+    return f
+
+
+def case_attn_perf():
+    import torch
+    from cleantransformer_b200 import ops
+    B, H, S, D = 8, 16, 1024, 64
+    qkv = torch.randn(B, S, H, 3, D, device="cuda").bfloat16()
+    q, k, v = [qkv[..., i, :].permute(0, 2, 1, 3) for i in range(3)]
+    mask = torch.ones(B, S, dtype=torch.long, device="cuda")
+    from oracle import ct_oracle as O
+    kb2, fv = ops.attn_mask_prep(mask, H, 0, O.alibi_slopes(H).cuda())
+    scale = 0.125
+    res = {}
+    def timeit(fn, n=10):
+        for _ in range(3): fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n): fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    o, lse2 = ops.attn_fwd(q, k, v, scale, True, -ops.FLT_MAX, kb2, fv)
+    ms = timeit(lambda: ops.attn_fwd(q, k, v, scale, True, -ops.FLT_MAX, kb2, fv))
+    fl = 4 * B * H * S * S * D / 2
+    res["fwd_causal_ms"] = ms; res["fwd_causal_tflops"] = fl / ms / 1e9
+    ms = timeit(lambda: ops.attn_fwd(q, k, v, scale, False))
+    res["fwd_dense_ms"] = ms; res["fwd_dense_tflops"] = 2 * fl / ms / 1e9
+    do = torch.randn_like(o); dqkv = torch.empty_like(qkv)
+    dq, dk, dv = [dqkv[..., i, :].permute(0, 2, 1, 3) for i in range(3)]
+    ms = timeit(lambda: ops.attn_bwd(do, q, k, v, o, lse2, dq, dk, dv, scale, True, -ops.FLT_MAX, kb2, fv))
+    res["bwd_causal_ms"] = ms; res["bwd_causal_tflops"] = 2.5 * fl / ms / 1e9
+    import torch.nn.functional as F
+    qs, ks, vs = [t.contiguous() for t in (q, k, v)]
+    ms = timeit(lambda: F.scaled_dot_product_attention(qs, ks, vs, is_causal=True))
+    res["sdpa_fwd_causal_ms"] = ms
+    return res
+
+
+
+def case_ce_embed():
+    import torch
+    from cleantransformer_b200 import ops
+    torch.manual_seed(3)
+    res = {}
+    B, S, V = 3, 17, 1000
+    logits = (torch.randn(B, S, V, device="cuda") * 3).bfloat16()
+    labels = torch.randint(0, V, (B, S), device="cuda")
+    loss, dl = ops.cross_entropy_fwd(logits.view(B * S, V), labels.view(-1), S=S, shift=True)
+    lr = logits.float().clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lr[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1))
+    ref.backward()
+    res["loss_shift"] = abs(float(loss) - float(ref)) / abs(float(ref))
+    res["dlogits_shift"] = rel(dl.view(B, S, V), lr.grad)
+    lab2 = labels.clone().view(-1); lab2[::5] = -100
+    lf = torch.randn(B * S, 777, device="cuda")
+    loss2, dl2 = ops.cross_entropy_fwd(lf, lab2.clamp(max=776), S=0, shift=False)
+    lr2 = lf.clone().requires_grad_(True)
+    ref2 = torch.nn.functional.cross_entropy(lr2, lab2.clamp(max=776)); ref2.backward()
+    res["loss_plain"] = abs(float(loss2) - float(ref2)) / abs(float(ref2)); res["dlogits_plain"] = rel(dl2, lr2.grad)
+    W = torch.randn(500, 64, device="cuda"); ids = torch.randint(0, 500, (4, 9), device="cuda")
+    out = ops.embedding_fwd(ids, W)
+    res["emb_fwd"] = rel(out, W[ids])
+    dout = torch.randn(4, 9, 64, device="cuda"); dW = torch.zeros_like(W)
+    ops.embedding_bwd(ids, dout, dW)
+    Wr = W.clone().requires_grad_(True); torch.nn.functional.embedding(ids, Wr).backward(dout)
+    res["emb_bwd"] = rel(dW, Wr.grad)
+    return res
+
 CASES = {
     "ln": case_ln,
     "adamw": case_adamw,
@@ -142,6 +276,23 @@ CASES = {
     "tc_epi": mk_tc(1024, 1024, 512, 0, 0, True),
     "tc_wgrad_splitk": case_gemm_wgrad_splitk,
     "gemm_perf": case_gemm_perf,
+    "attn_simt_d8_bloom": mk_attn(2, 8, 12, 12, 8, True, 0, 2, bwd=True, pad="right"),
+    "attn_simt_d12_gpt": mk_attn(3, 4, 8, 8, 12, True, 1, 2, bwd=True, pad="left", causal_fill=-1e4),
+    "attn_simt_d64_bert": mk_attn(2, 4, 40, 40, 64, False, 2, 2, bwd=True, pad="right"),
+    "attn_simt_decode": mk_attn(2, 4, 1, 33, 64, True, 1, 2, pad="left", causal_fill=-1e4),
+    "attn_tc_plain": mk_attn(2, 4, 256, 256, 64, False, None, 1),
+    "attn_tc_causal": mk_attn(2, 4, 384, 384, 64, True, None, 1),
+    "attn_tc_bloom_ragged": mk_attn(3, 4, 300, 300, 64, True, 0, 1, pad="right"),
+    "attn_tc_gpt_left": mk_attn(3, 4, 300, 300, 64, True, 1, 1, pad="left", causal_fill=-1e4),
+    "attn_tc_bert": mk_attn(2, 4, 512, 512, 64, False, 2, 1, pad="right"),
+    "attn_tc_prefill_off": mk_attn(2, 4, 128, 384, 64, True, 1, 1, pad="none", causal_fill=-1e4),
+    "attn_tc_bwd_plain": mk_attn(2, 4, 256, 256, 64, False, None, 1, bwd=True),
+    "attn_tc_bwd_causal": mk_attn(2, 4, 384, 384, 64, True, None, 1, bwd=True),
+    "attn_tc_bwd_bloom_ragged": mk_attn(3, 4, 300, 300, 64, True, 0, 1, bwd=True, pad="right"),
+    "attn_tc_bwd_gpt_left": mk_attn(3, 4, 300, 300, 64, True, 1, 1, bwd=True, pad="left", causal_fill=-1e4),
+    "attn_tc_bwd_big": mk_attn(2, 16, 1024, 1024, 64, True, 0, 1, bwd=True, pad="right"),
+    "attn_perf": case_attn_perf,
+    "ce_embed": case_ce_embed,
 }
 
 if __name__ == "__main__":
