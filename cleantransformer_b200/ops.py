@@ -21,6 +21,22 @@ _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
 
 
+# Kernel-launch accounting (bench.py's `gpu_launches`) and optional per-GEMM CUDA-event timing
+# (bench.py's roofline pass). Counts are the number of kernels each C-ABI call enqueues.
+LAUNCHES = [0]
+GEMM_PROFILE = None  # when a list: (M, N, K, start_event, end_event) appended per ct_gemm call
+_KERNELS_PER_CALL = {"ct_layernorm_fwd": 1, "ct_layernorm_bwd": 1, "ct_adamw_step": 1, "ct_adamw_multi": 1,
+                     "ct_sgd_step": 1, "ct_cast": 1, "ct_colsum": 1, "ct_act_fwd": 1, "ct_act_bwd": 1,
+                     "ct_gemm": 1, "ct_attn_fwd": 1, "ct_attn_bwd": 3, "ct_attn_mask_prep": 1,
+                     "ct_embedding_fwd": 1, "ct_embedding_bwd": 1, "ct_cross_entropy_fwd": 3,
+                     "ct_scale_by_scalar": 1}
+
+
+def _ck(rc, what):
+    check(rc, what)
+    LAUNCHES[0] += _KERNELS_PER_CALL.get(what, 1)
+
+
 def dt(t):
     try:
         return _DT[t.dtype]
@@ -44,7 +60,7 @@ def _req_cuda(*ts):
 
 def device_check(device=None):
     dev = torch.cuda.current_device() if device is None else device
-    check(_lib.load().ct_device_check(int(dev)), "ct_device_check")
+    check(_lib.load().ct_device_check(int(dev)), "ct_device_check")  # no launch
 
 
 # ------------------------------------------------------------------------------------------------
@@ -60,7 +76,7 @@ def layernorm_fwd(x, gamma, beta, eps, out_dtype=None, out2_dtype=None, save_sta
     y2 = torch.empty(x.shape, dtype=out2_dtype, device=x.device) if out2_dtype is not None else None
     mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
-    check(_lib.load().ct_layernorm_fwd(
+    _ck(_lib.load().ct_layernorm_fwd(
         ptr(x2), dt(x2), ptr(gamma), ptr(beta), ptr(y), dt(y) if y is not None else 0,
         ptr(y2), dt(y2) if y2 is not None else 0, ptr(mean), ptr(rstd), rows, cols, float(eps),
         stream()), "ct_layernorm_fwd")
@@ -78,7 +94,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, accumulate, dy2=None,
     dy2 = dy2.contiguous() if dy2 is not None else None
     dx_add = dx_add.contiguous() if dx_add is not None else None
     dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
-    check(_lib.load().ct_layernorm_bwd(
+    _ck(_lib.load().ct_layernorm_bwd(
         ptr(dy), dt(dy) if dy is not None else 0, ptr(dy2), dt(dy2) if dy2 is not None else 0,
         ptr(x2), dt(x2), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx_add),
         dt(dx_add) if dx_add is not None else 0, ptr(dx), dt(dx), ptr(dgamma), ptr(dbeta),
@@ -93,7 +109,7 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, mode=0, gr
                shadow=None):
     _req_cuda(p, g, m, v)
     n = p.numel()
-    check(_lib.load().ct_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), n, lr, beta1,
+    _ck(_lib.load().ct_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), n, lr, beta1,
                                     beta2, eps, weight_decay, int(step), int(mode), grad_scale,
                                     stream()), "ct_adamw_step")
 
@@ -112,13 +128,13 @@ def adamw_multi(ps, gs, ms, vs, lr, beta1, beta2, eps, weight_decay, step, mode=
     V = arr(*[t.data_ptr() for t in vs])
     S = arr(*[(t.data_ptr() if t is not None else None) for t in shadows]) if shadows else None
     sizes = i64(*[t.numel() for t in ps])
-    check(_lib.load().ct_adamw_multi(n, P, G, M, V, S, sizes, lr, beta1, beta2, eps, weight_decay,
+    _ck(_lib.load().ct_adamw_multi(n, P, G, M, V, S, sizes, lr, beta1, beta2, eps, weight_decay,
                                      int(step), int(mode), grad_scale, stream()), "ct_adamw_multi")
 
 
 def sgd_step(p, g, buf, lr, momentum, dampening, weight_decay, first_step):
     _req_cuda(p, g)
-    check(_lib.load().ct_sgd_step(ptr(p), ptr(g), ptr(buf), p.numel(), lr, momentum or 0.0,
+    _ck(_lib.load().ct_sgd_step(ptr(p), ptr(g), ptr(buf), p.numel(), lr, momentum or 0.0,
                                   dampening or 0.0, weight_decay or 0.0, 1 if first_step else 0,
                                   stream()), "ct_sgd_step")
 
@@ -131,28 +147,28 @@ def cast(src, dtype, out=None):
     src = src.contiguous()
     if out is None:
         out = torch.empty(src.shape, dtype=dtype, device=src.device)
-    check(_lib.load().ct_cast(ptr(src), dt(src), ptr(out), dt(out), src.numel(), stream()), "ct_cast")
+    _ck(_lib.load().ct_cast(ptr(src), dt(src), ptr(out), dt(out), src.numel(), stream()), "ct_cast")
     return out
 
 
 def colsum(x2d, out, accumulate):
     _req_cuda(x2d, out)
     rows, cols = x2d.shape
-    check(_lib.load().ct_colsum(ptr(x2d), dt(x2d), x2d.stride(0), ptr(out), 1 if accumulate else 0,
+    _ck(_lib.load().ct_colsum(ptr(x2d), dt(x2d), x2d.stride(0), ptr(out), 1 if accumulate else 0,
                                 rows, cols, stream()), "ct_colsum")
 
 
 def act_fwd(x, act, out_dtype=None):
     x = x.contiguous()
     y = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
-    check(_lib.load().ct_act_fwd(ptr(x), dt(x), ptr(y), dt(y), act, x.numel(), stream()), "ct_act_fwd")
+    _ck(_lib.load().ct_act_fwd(ptr(x), dt(x), ptr(y), dt(y), act, x.numel(), stream()), "ct_act_fwd")
     return y
 
 
 def act_bwd(dy, x, act, out_dtype=None):
     dy, x = dy.contiguous(), x.contiguous()
     dx = torch.empty(x.shape, dtype=out_dtype or dy.dtype, device=x.device)
-    check(_lib.load().ct_act_bwd(ptr(dy), dt(dy), ptr(x), dt(x), ptr(dx), dt(dx), act, x.numel(),
+    _ck(_lib.load().ct_act_bwd(ptr(dy), dt(dy), ptr(x), dt(x), ptr(dx), dt(dx), act, x.numel(),
                                  stream()), "ct_act_bwd")
     return dx
 
@@ -189,7 +205,14 @@ def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat
     if residual is not None:
         g.residual, g.res_dtype, g.ldr = residual.data_ptr(), dt(residual), residual.stride(0)
     g.impl = impl
-    check(_lib.load().ct_gemm(ctypes.byref(g), stream()), "ct_gemm")
+    if GEMM_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _ck(_lib.load().ct_gemm(ctypes.byref(g), stream()), "ct_gemm")
+        e1.record()
+        GEMM_PROFILE.append((M, N, K, e0, e1))
+        return out
+    _ck(_lib.load().ct_gemm(ctypes.byref(g), stream()), "ct_gemm")
     return out
 
 
@@ -247,7 +270,7 @@ def attn_mask_prep(attention_mask, n_head, mode, slopes=None):
     heads = n_head if mode == MASK_BLOOM else 1
     kb = torch.empty((B, heads, Sk), dtype=torch.float32, device=am.device)
     fv = torch.empty((B,), dtype=torch.int32, device=am.device)
-    check(_lib.load().ct_attn_mask_prep(ptr(am), code, B, Sk, n_head, mode, ptr(slopes), ptr(kb),
+    _ck(_lib.load().ct_attn_mask_prep(ptr(am), code, B, Sk, n_head, mode, ptr(slopes), ptr(kb),
                                         ptr(fv), stream()), "ct_attn_mask_prep")
     return kb, fv
 
@@ -290,7 +313,7 @@ def attn_fwd(q, k, v, scale, causal=False, causal_fill=-FLT_MAX, kbias2=None, fi
     lse2 = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device) if need_lse else None
     a = AttnArgs()
     _fill_attn(a, q, k, v, o4, lse2, scale, causal, causal_fill, kbias2, first_valid, impl)
-    check(_lib.load().ct_attn_fwd(ctypes.byref(a), stream()), "ct_attn_fwd")
+    _ck(_lib.load().ct_attn_fwd(ctypes.byref(a), stream()), "ct_attn_fwd")
     return o, lse2
 
 
@@ -310,7 +333,7 @@ def attn_bwd(dout, q, k, v, o, lse2, dq, dk, dv, scale, causal=False, causal_fil
     dq_acc = torch.empty((B, Sq, H, D), dtype=torch.float32, device=q.device) if D == 64 else None
     a.delta = delta.data_ptr()
     a.dq_accum = ptr(dq_acc)
-    check(_lib.load().ct_attn_bwd(ctypes.byref(a), stream()), "ct_attn_bwd")
+    _ck(_lib.load().ct_attn_bwd(ctypes.byref(a), stream()), "ct_attn_bwd")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -324,7 +347,7 @@ def embedding_fwd(ids, weight, out=None, accumulate=False):
     if out is None:
         out = torch.empty(tuple(ids.shape) + (H,), dtype=torch.float32, device=weight.device)
         accumulate = False
-    check(_lib.load().ct_embedding_fwd(ptr(ids), ptr(weight), ptr(out), ids.numel(), H, V,
+    _ck(_lib.load().ct_embedding_fwd(ptr(ids), ptr(weight), ptr(out), ids.numel(), H, V,
                                        1 if accumulate else 0, stream()), "ct_embedding_fwd")
     return out
 
@@ -333,7 +356,7 @@ def embedding_bwd(ids, dout, dweight, padding_idx=-1):
     ids = ids.contiguous()
     dout = dout.contiguous()
     V, H = dweight.shape
-    check(_lib.load().ct_embedding_bwd(ptr(ids), ptr(dout), ptr(dweight), ids.numel(), H, V,
+    _ck(_lib.load().ct_embedding_bwd(ptr(ids), ptr(dout), ptr(dweight), ids.numel(), H, V,
                                        int(padding_idx), stream()), "ct_embedding_bwd")
 
 
@@ -345,7 +368,7 @@ def cross_entropy_fwd(logits2d, labels, S=0, shift=False, ignore_index=-100, wan
     dl = torch.empty_like(logits2d) if want_dlogits else None
     loss = torch.empty((), dtype=torch.float32, device=logits2d.device)
     ws = torch.empty(rows + 4, dtype=torch.float32, device=logits2d.device)
-    check(_lib.load().ct_cross_entropy_fwd(ptr(logits2d), dt(logits2d), logits2d.stride(0), ptr(labels),
+    _ck(_lib.load().ct_cross_entropy_fwd(ptr(logits2d), dt(logits2d), logits2d.stride(0), ptr(labels),
                                            ptr(dl), dl.stride(0) if dl is not None else 0, ptr(loss),
                                            ptr(ws), rows, V, S, 1 if shift else 0, ignore_index,
                                            stream()), "ct_cross_entropy_fwd")
@@ -353,5 +376,5 @@ def cross_entropy_fwd(logits2d, labels, S=0, shift=False, ignore_index=-100, wan
 
 
 def scale_by_scalar(x, scalar_f32):
-    check(_lib.load().ct_scale_by_scalar(ptr(x), dt(x), x.numel(), ptr(scalar_f32), stream()),
+    _ck(_lib.load().ct_scale_by_scalar(ptr(x), dt(x), x.numel(), ptr(scalar_f32), stream()),
           "ct_scale_by_scalar")
