@@ -22,6 +22,7 @@
 #include "../../include/ct_b200.h"
 #include <cfloat>
 #include <cstring>
+#include <type_traits>
 
 namespace ct {
 
@@ -63,7 +64,8 @@ __device__ __forceinline__ float score2(float acc, float sl2, float kb, bool fut
 // =================================================================================================
 constexpr int FA_THREADS = 192;
 constexpr int FA_TILE = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, SWIZZLE_128B
-constexpr int FA_SMEM = FA_TILE /*Q*/ + 2 * FA_TILE /*K*/ + 2 * FA_TILE /*V*/ + 2 * FA_TILE /*P*/ + 128;
+constexpr int FA_SMEM = FA_TILE /*Q*/ + 2 * FA_TILE /*K*/ + 2 * FA_TILE /*V*/ + 2 * FA_TILE /*P*/ + 128 /*barriers*/ +
+                        512 /*per-key bias of the current tile*/;
 
 __global__ void __launch_bounds__(FA_THREADS, 2)
     attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -76,7 +78,8 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
   const uint32_t sP = base + 5 * FA_TILE;
   const uint32_t bars = base + 7 * FA_TILE;
   const uint32_t q_full = bars, k_full = bars + 8, v_full = bars + 24, kv_empty = bars + 40,
-                 s_full = bars + 56, p_ready = bars + 72, o_full = bars + 80, tmem_slot = bars + 88;
+                 s_full = bars + 56, p_ready = bars + 72, o_full = bars + 80, tmem_slot = bars + 88,
+                 kb_s = bars + 128;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + 7 * FA_TILE + 88);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -163,12 +166,24 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
     const int i = q0 + qr;
     const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float* kb_row = p.kbias2 ? p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh : nullptr;
+    const bool has_kb = kb_row != nullptr;
     float o_acc[64];
 #pragma unroll
     for (int d = 0; d < 64; ++d) o_acc[d] = 0.f;
     float m = -INFINITY, l = 0.f;
     const uint32_t p_row = sP + qr * 128;
     const int sw = qr & 7;
+    // per-key bias of the current tile, staged through smem: one global load per thread per tile,
+    // prefetched one tile ahead (a global load per element exposed ~L2 latency 64x per tile)
+    float kb_next = (has_kb && qr < p.Sk) ? __ldg(kb_row + qr) : 0.f;
+
+    auto kb4 = [&](int col) -> float4 {  // 4 consecutive staged bias values (broadcast LDS.128)
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                   : "r"(kb_s + 4 * col));
+      return v;
+    };
 
     for (int j = 0; j < n_kv; ++j) {
       const int kv0 = j * 128;
@@ -177,94 +192,96 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
       tc_fence_after();
       // a tile needs per-element masking if it touches the causal diagonal or the ragged key edge
       const bool slow = (p.causal && (kv0 + 127 > q0 + p.off)) || (kv0 + 128 > p.Sk);
-      const bool vec_kb = kb_row && (kv0 + 128 <= p.Sk) && ((p.Sk & 3) == 0) && ((p.kb_sb & 3) == 0) &&
-                          ((p.kb_sh & 3) == 0);
+      if (has_kb) {
+        // every thread is past o_full(j-1), i.e. all 128 have finished reading the previous tile's bias
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(kb_s + 4 * qr), "f"(kb_next) : "memory");
+        bar_sync_named(1, 128);
+        const int nj = kv0 + 128 + qr;
+        kb_next = (j + 1 < n_kv && nj < p.Sk) ? __ldg(kb_row + nj) : 0.f;
+      }
+      // Both passes run as ROLLED loops over the four 32-column chunks (one body each for the
+      // masked and the mask-free tile kinds): the first fully unrolled version was 7k SASS
+      // instructions and spent most of its time stalled on instruction fetch. The TMEM load of the
+      // next chunk is issued before the math of the current one (register copy = 32 MOVs).
+      uint32_t r[32];
+      float cur[32];
       float mt = -INFINITY;
-      // ---- pass 1: row maximum ----
+      auto val = [&](float a, float kb, int jg, auto slow_tag) -> float {
+        if constexpr (decltype(slow_tag)::value)
+          return score2(a, p.sl2, kb, p.causal && (jg > i + p.off), p.causal_fill2, jg >= p.Sk);
+        else
+          return fmaf(a, p.sl2, kb);
+      };
+      auto pass1 = [&](auto slow_tag) {
+        tmem_ld_32x32(t_s, r);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_s + c * 32, r);
-        tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
 #pragma unroll
-        for (int t4 = 0; t4 < 8; ++t4) {
-          float kb[4] = {0.f, 0.f, 0.f, 0.f};
-          const int jg = kv0 + c * 32 + t4 * 4;
-          if (vec_kb) {
-            const float4 k4 = __ldg(reinterpret_cast<const float4*>(kb_row + jg));
-            kb[0] = k4.x; kb[1] = k4.y; kb[2] = k4.z; kb[3] = k4.w;
-          } else if (kb_row) {
+          for (int t = 0; t < 32; ++t) cur[t] = __uint_as_float(r[t]);
+          tmem_ld_32x32(t_s + ((c + 1) & 3) * 32, r);  // c == 3: first chunk of pass 2
 #pragma unroll
-            for (int u = 0; u < 4; ++u) kb[u] = (jg + u < p.Sk) ? __ldg(kb_row + jg + u) : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float a = __uint_as_float(r[t4 * 4 + u]);
-            float v;
-            if (slow)
-              v = score2(a, p.sl2, kb[u], p.causal && (jg + u > i + p.off), p.causal_fill2,
-                         jg + u >= p.Sk);
-            else
-              v = fmaxf(fmaf(a, p.sl2, kb[u]), -FLT_MAX);
-            mt = fmaxf(mt, v);
+          for (int t4 = 0; t4 < 8; ++t4) {
+            float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_kb) k4 = kb4(c * 32 + t4 * 4);
+            const int jg = kv0 + c * 32 + t4 * 4;
+            mt = fmaxf(mt, val(cur[t4 * 4 + 0], k4.x, jg + 0, slow_tag));
+            mt = fmaxf(mt, val(cur[t4 * 4 + 1], k4.y, jg + 1, slow_tag));
+            mt = fmaxf(mt, val(cur[t4 * 4 + 2], k4.z, jg + 2, slow_tag));
+            mt = fmaxf(mt, val(cur[t4 * 4 + 3], k4.w, jg + 3, slow_tag));
           }
         }
-      }
+      };
+      if (slow) pass1(std::true_type{}); else pass1(std::false_type{});
+      mt = fmaxf(mt, -FLT_MAX);  // clamp once: max(clamp(x)) == clamp(max(x))
       const float m_new = fmaxf(m, mt);
       const float alpha = ex2(m - m_new);
       float lt = 0.f;
       // ---- pass 2: p = 2^(s - m), write bf16 P into the K-major SWIZZLE_128B tile ----
+      auto pass2 = [&](auto slow_tag) {
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_s + c * 32, r);
-        tmem_ld_wait();
-        float pv[32];
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
 #pragma unroll
-        for (int t4 = 0; t4 < 8; ++t4) {
-          float kb[4] = {0.f, 0.f, 0.f, 0.f};
-          const int jg = kv0 + c * 32 + t4 * 4;
-          if (vec_kb) {
-            const float4 k4 = __ldg(reinterpret_cast<const float4*>(kb_row + jg));
-            kb[0] = k4.x; kb[1] = k4.y; kb[2] = k4.z; kb[3] = k4.w;
-          } else if (kb_row) {
+          for (int t = 0; t < 32; ++t) cur[t] = __uint_as_float(r[t]);
+          if (c < 3) tmem_ld_32x32(t_s + (c + 1) * 32, r);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) kb[u] = (jg + u < p.Sk) ? __ldg(kb_row + jg + u) : 0.f;
-          }
+          for (int g = 0; g < 4; ++g) {  // 4 x 16-byte chunks (8 values each); panel = c / 2
+            float pv[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float a = __uint_as_float(r[t4 * 4 + u]);
-            float v;
-            if (slow)
-              v = score2(a, p.sl2, kb[u], p.causal && (jg + u > i + p.off), p.causal_fill2,
-                         jg + u >= p.Sk);
-            else
-              v = fmaxf(fmaf(a, p.sl2, kb[u]), -FLT_MAX);
-            const float e = ex2(v - m_new);
-            lt += e;
-            pv[t4 * 4 + u] = e;
+            for (int hh = 0; hh < 2; ++hh) {
+              const int col = c * 32 + g * 8 + hh * 4;
+              float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (has_kb) k4 = kb4(col);
+              const float kb[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                float v = val(cur[g * 8 + hh * 4 + u], kb[u], kv0 + col + u, slow_tag);
+                if constexpr (!decltype(slow_tag)::value) v = fmaxf(v, -FLT_MAX);
+                const float e = ex2(v - m_new);
+                lt += e;
+                pv[hh * 4 + u] = e;
+              }
+            }
+            uint32_t w0, w1, w2, w3;
+            if (p.fmt == 1) {
+              w0 = pack_bf16x2(pv[0], pv[1]); w1 = pack_bf16x2(pv[2], pv[3]);
+              w2 = pack_bf16x2(pv[4], pv[5]); w3 = pack_bf16x2(pv[6], pv[7]);
+            } else {
+              __half2 h0 = __floats2half2_rn(pv[0], pv[1]), h1 = __floats2half2_rn(pv[2], pv[3]);
+              __half2 h2 = __floats2half2_rn(pv[4], pv[5]), h3 = __floats2half2_rn(pv[6], pv[7]);
+              w0 = *reinterpret_cast<uint32_t*>(&h0); w1 = *reinterpret_cast<uint32_t*>(&h1);
+              w2 = *reinterpret_cast<uint32_t*>(&h2); w3 = *reinterpret_cast<uint32_t*>(&h3);
+            }
+            const int chunk = (c & 1) * 4 + g;
+            const uint32_t addr = p_row + (c >> 1) * FA_TILE + ((chunk ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1),
+                         "r"(w2), "r"(w3)
+                         : "memory");
           }
         }
-        // 32 columns = 4 x 16-byte chunks; panel = c / 2, chunk index within the 128-byte row
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t w0, w1, w2, w3;
-          if (p.fmt == 1) {
-            w0 = pack_bf16x2(pv[8 * g], pv[8 * g + 1]); w1 = pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]);
-            w2 = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]); w3 = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
-          } else {
-            __half2 h0 = __floats2half2_rn(pv[8 * g], pv[8 * g + 1]), h1 = __floats2half2_rn(pv[8 * g + 2], pv[8 * g + 3]);
-            __half2 h2 = __floats2half2_rn(pv[8 * g + 4], pv[8 * g + 5]), h3 = __floats2half2_rn(pv[8 * g + 6], pv[8 * g + 7]);
-            w0 = *reinterpret_cast<uint32_t*>(&h0); w1 = *reinterpret_cast<uint32_t*>(&h1);
-            w2 = *reinterpret_cast<uint32_t*>(&h2); w3 = *reinterpret_cast<uint32_t*>(&h3);
-          }
-          const int chunk = (c & 1) * 4 + g;
-          const uint32_t addr = p_row + (c >> 1) * FA_TILE + ((chunk ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1),
-                       "r"(w2), "r"(w3)
-                       : "memory");
-        }
-      }
+      };
+      if (slow) pass2(std::true_type{}); else pass2(std::false_type{});
       l = l * alpha + lt;
       m = m_new;
       fence_proxy_async_smem();
@@ -273,13 +290,16 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
       // ---- O = O * alpha + P V ----
       mbar_wait(o_full, j & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_s + c * 32, r);
+      {
+        uint32_t r2[32];
+        tmem_ld_32x32(t_s, r);
+        tmem_ld_32x32(t_s + 32, r2);
         tmem_ld_wait();
 #pragma unroll
-        for (int t = 0; t < 32; ++t) o_acc[c * 32 + t] = fmaf(o_acc[c * 32 + t], alpha, __uint_as_float(r[t]));
+        for (int t = 0; t < 32; ++t) {
+          o_acc[t] = fmaf(o_acc[t], alpha, __uint_as_float(r[t]));
+          o_acc[32 + t] = fmaf(o_acc[32 + t], alpha, __uint_as_float(r2[t]));
+        }
       }
       tc_fence_before();
     }
@@ -325,7 +345,7 @@ struct AttnBwdP {
   void* dv; int64_t dv_sb, dv_sh, dv_ss;
 };
 constexpr int FB_SMEM = 2 * FA_TILE /*K,V*/ + 4 * FA_TILE /*2 x (Q,dO)*/ + 2 * FA_TILE /*P^T*/ +
-                        2 * FA_TILE /*dS^T*/ + 128;
+                        2 * FA_TILE /*dS^T*/ + 128 /*barriers*/ + 1024 /*lse2, delta of the query tile*/;
 
 __device__ __forceinline__ void st_row64(void* basep, int64_t elem_off, const float (&v)[64], int fmt) {
   uint8_t* row = reinterpret_cast<uint8_t*>(basep) + 2 * elem_off;
@@ -358,7 +378,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   const uint32_t sDS = base + 8 * FA_TILE;  // 2 panels
   const uint32_t bars = base + 10 * FA_TILE;
   const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 24, sdp_full = bars + 40,
-                 pds_ready = bars + 48, dq_full = bars + 56, dkv_full = bars + 64, tmem_slot = bars + 72;
+                 pds_ready = bars + 48, dq_full = bars + 56, dkv_full = bars + 64, tmem_slot = bars + 72,
+                 lse_s = bars + 128, del_s = bars + 640;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + 10 * FA_TILE + 72);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -460,68 +481,86 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     const float* lse_bh = p.lse2 + ((int64_t)b * p.H + h) * p.Sq;
     const float* del_bh = bp.delta + ((int64_t)b * p.H + h) * p.Sq;
     const int sw = rr & 7;
+    // per-query statistics of the current query tile, staged through smem (prefetched one tile ahead)
+    float lse_next = INFINITY, del_next = 0.f;
+    if (n_it > 0 && i_start * 128 + rr < p.Sq) {
+      lse_next = __ldg(lse_bh + i_start * 128 + rr);
+      del_next = __ldg(del_bh + i_start * 128 + rr);
+    }
     for (int it = 0; it < n_it; ++it) {
       const int q0 = (i_start + it) * 128;
       mbar_wait(sdp_full, it & 1);
       tc_fence_after();
-      const bool vec_q = (q0 + 128 <= p.Sq) && ((p.Sq & 3) == 0);
+      // all 128 threads are past dq_full(it-1): nobody still reads the previous tile's statistics
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(lse_s + 4 * rr), "f"(lse_next) : "memory");
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(del_s + 4 * rr), "f"(del_next) : "memory");
+      bar_sync_named(1, 128);
+      {
+        const int nq = q0 + 128 + rr;
+        const bool ok = (it + 1 < n_it) && nq < p.Sq;
+        lse_next = ok ? __ldg(lse_bh + nq) : INFINITY;
+        del_next = ok ? __ldg(del_bh + nq) : 0.f;
+      }
+      // rolled loop over the four 32-column chunks (code size: see the forward kernel); the TMEM
+      // loads of the next chunk are issued before the math of the current one
+      uint32_t rs[32], rd[32];
+      tmem_ld_32x32(T_ST + t_lane, rs);
+      tmem_ld_32x32(T_DPT + t_lane, rd);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        uint32_t rs[32], rd[32];
-        tmem_ld_32x32(T_ST + t_lane + c * 32, rs);
-        tmem_ld_32x32(T_DPT + t_lane + c * 32, rd);
+        float cs[32], cdp[32];
         tmem_ld_wait();
-        float pt[32], ds[32];
 #pragma unroll
-        for (int t4 = 0; t4 < 8; ++t4) {
-          const int qg = q0 + c * 32 + t4 * 4;
-          float ls[4], dl[4];
-          if (vec_q) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(lse_bh + qg));
-            const float4 d = __ldg(reinterpret_cast<const float4*>(del_bh + qg));
-            ls[0] = a.x; ls[1] = a.y; ls[2] = a.z; ls[3] = a.w;
-            dl[0] = d.x; dl[1] = d.y; dl[2] = d.z; dl[3] = d.w;
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const bool ok = qg + u < p.Sq;
-              ls[u] = ok ? __ldg(lse_bh + qg + u) : INFINITY;
-              dl[u] = ok ? __ldg(del_bh + qg + u) : 0.f;
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int e = t4 * 4 + u;
-            const bool fut = p.causal && (jg > qg + u + p.off);
-            const float v = score2(__uint_as_float(rs[e]), p.sl2, kb, fut, p.causal_fill2, false);
-            float pe = ex2(v - ls[u]);
-            if (key_oob) pe = 0.f;
-            pt[e] = pe;
-            // a causally masked score is a constant in the reference (modeling_gpt.py:89 `w*b`,
-            // modeling_bloom.py:108 masked_fill): P still feeds dV, but no gradient reaches q.k
-            ds[e] = fut ? 0.f : pe * (__uint_as_float(rd[e]) - dl[u]) * p.scale;
-          }
+        for (int t = 0; t < 32; ++t) { cs[t] = __uint_as_float(rs[t]); cdp[t] = __uint_as_float(rd[t]); }
+        if (c < 3) {
+          tmem_ld_32x32(T_ST + t_lane + (c + 1) * 32, rs);
+          tmem_ld_32x32(T_DPT + t_lane + (c + 1) * 32, rd);
         }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 4; ++g) {  // 16-byte output chunks of 8 query columns
+          float pt[8], ds[8];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int col = c * 32 + g * 8 + hh * 4;
+            const int qg = q0 + col;
+            float4 a, d;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(lse_s + 4 * col));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w) : "r"(del_s + 4 * col));
+            const float ls[4] = {a.x, a.y, a.z, a.w};
+            const float dl[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = g * 8 + hh * 4 + u;
+              const bool fut = p.causal && (jg > qg + u + p.off);
+              const float v = score2(cs[e], p.sl2, kb, fut, p.causal_fill2, false);
+              float pe = ex2(v - ls[u]);
+              if (key_oob) pe = 0.f;
+              pt[hh * 4 + u] = pe;
+              // a causally masked score is a constant in the reference (modeling_gpt.py:89 `w*b`,
+              // modeling_bloom.py:108 masked_fill): P still feeds dV, but no gradient reaches q.k
+              ds[hh * 4 + u] = fut ? 0.f : pe * (cdp[e] - dl[u]) * p.scale;
+            }
+          }
           const int chunk = (c & 1) * 4 + g;
           const uint32_t off = rr * 128 + (c >> 1) * FA_TILE + ((chunk ^ sw) << 4);
           uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
           if (p.fmt == 1) {
-            a0 = pack_bf16x2(pt[8 * g], pt[8 * g + 1]); a1 = pack_bf16x2(pt[8 * g + 2], pt[8 * g + 3]);
-            a2 = pack_bf16x2(pt[8 * g + 4], pt[8 * g + 5]); a3 = pack_bf16x2(pt[8 * g + 6], pt[8 * g + 7]);
-            b0 = pack_bf16x2(ds[8 * g], ds[8 * g + 1]); b1 = pack_bf16x2(ds[8 * g + 2], ds[8 * g + 3]);
-            b2 = pack_bf16x2(ds[8 * g + 4], ds[8 * g + 5]); b3 = pack_bf16x2(ds[8 * g + 6], ds[8 * g + 7]);
+            a0 = pack_bf16x2(pt[0], pt[1]); a1 = pack_bf16x2(pt[2], pt[3]);
+            a2 = pack_bf16x2(pt[4], pt[5]); a3 = pack_bf16x2(pt[6], pt[7]);
+            b0 = pack_bf16x2(ds[0], ds[1]); b1 = pack_bf16x2(ds[2], ds[3]);
+            b2 = pack_bf16x2(ds[4], ds[5]); b3 = pack_bf16x2(ds[6], ds[7]);
           } else {
             __half2 x;
-            x = __floats2half2_rn(pt[8 * g], pt[8 * g + 1]); a0 = *reinterpret_cast<uint32_t*>(&x);
-            x = __floats2half2_rn(pt[8 * g + 2], pt[8 * g + 3]); a1 = *reinterpret_cast<uint32_t*>(&x);
-            x = __floats2half2_rn(pt[8 * g + 4], pt[8 * g + 5]); a2 = *reinterpret_cast<uint32_t*>(&x);
-            x = __floats2half2_rn(pt[8 * g + 6], pt[8 * g + 7]); a3 = *reinterpret_cast<uint32_t*>(&x);
-            x = __floats2half2_rn(ds[8 * g], ds[8 * g + 1]); b0 = *reinterpret_cast<uint32_t*>(&x);
-            x = __floats2half2_rn(ds[8 * g + 2], ds[8 * g + 3]); b1 = *reinterpret_cast<uint32_t*>(&x);
-            x = __floats2half2_rn(ds[8 * g + 4], ds[8 * g + 5]); b2 = *reinterpret_cast<uint32_t*>(&x);
-            x = __floats2half2_rn(ds[8 * g + 6], ds[8 * g + 7]); b3 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(pt[0], pt[1]); a0 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(pt[2], pt[3]); a1 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(pt[4], pt[5]); a2 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(pt[6], pt[7]); a3 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(ds[0], ds[1]); b0 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(ds[2], ds[3]); b1 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(ds[4], ds[5]); b2 = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(ds[6], ds[7]); b3 = *reinterpret_cast<uint32_t*>(&x);
           }
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPT + off), "r"(a0), "r"(a1),
                        "r"(a2), "r"(a3) : "memory");
@@ -614,19 +653,59 @@ __global__ void __launch_bounds__(256)
   if (lane == 0) delta[((int64_t)b * H + h) * Sq + i] = acc;
 }
 
+// D == 64, bf16, merged-head layout: 8 lanes x 16 bytes cover one (b,i,h) row; a warp handles 4 rows
+__global__ void __launch_bounds__(256)
+    attn_delta64_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ o, int64_t sb,
+                        int64_t sh, int64_t ss, float* __restrict__ delta, int B, int H, int Sq) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = t >> 3;  // (b, i, h) flattened with h fastest: coalesced along the merged head dim
+  const int part = (int)(t & 7);
+  const bool ok = row < (int64_t)B * Sq * H;
+  float acc = 0.f;
+  int h = 0, i = 0, b = 0;
+  if (ok) {
+    h = (int)(row % H); i = (int)((row / H) % Sq); b = (int)(row / ((int64_t)H * Sq));
+    const int64_t off = (int64_t)b * sb + (int64_t)h * sh + (int64_t)i * ss + part * 8;
+    const uint4 x = *reinterpret_cast<const uint4*>(dout + off), y = *reinterpret_cast<const uint4*>(o + off);
+    float2 a, c;
+    a = unpack_bf16x2(x.x); c = unpack_bf16x2(y.x); acc = fmaf(a.x, c.x, fmaf(a.y, c.y, acc));
+    a = unpack_bf16x2(x.y); c = unpack_bf16x2(y.y); acc = fmaf(a.x, c.x, fmaf(a.y, c.y, acc));
+    a = unpack_bf16x2(x.z); c = unpack_bf16x2(y.z); acc = fmaf(a.x, c.x, fmaf(a.y, c.y, acc));
+    a = unpack_bf16x2(x.w); c = unpack_bf16x2(y.w); acc = fmaf(a.x, c.x, fmaf(a.y, c.y, acc));
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (ok && part == 0) delta[((int64_t)b * H + h) * Sq + i] = acc;
+}
+
 // dq[b,h,i,:] = (bf16) dq_accum[b,i,h,:]
 __global__ void __launch_bounds__(256)
     attn_dq_convert_kernel(const float* __restrict__ acc, void* __restrict__ dq, int fmt, int64_t sb,
                            int64_t sh, int64_t ss, int B, int H, int Sq, int D) {
-  const int64_t n = (int64_t)B * Sq * H * D;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    const int d = (int)(e % D);
-    const int h = (int)((e / D) % H);
-    const int i = (int)((e / ((int64_t)D * H)) % Sq);
-    const int b = (int)(e / ((int64_t)D * H * Sq));
+  // 8 elements per thread: two 16-byte loads, one 16-byte store (D % 8 == 0)
+  const int64_t nvec = (int64_t)B * Sq * H * D / 8;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nvec; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t el = e * 8;
+    const int d = (int)(el % D);
+    const int h = (int)((el / D) % H);
+    const int i = (int)((el / ((int64_t)D * H)) % Sq);
+    const int b = (int)(el / ((int64_t)D * H * Sq));
+    const float4 lo = __ldcs(reinterpret_cast<const float4*>(acc + el));
+    const float4 hi = __ldcs(reinterpret_cast<const float4*>(acc + el) + 1);
     const int64_t off = (int64_t)b * sb + (int64_t)h * sh + (int64_t)i * ss + d;
-    if (fmt == 1) reinterpret_cast<__nv_bfloat16*>(dq)[off] = __float2bfloat16_rn(acc[e]);
-    else reinterpret_cast<__half*>(dq)[off] = __float2half_rn(acc[e]);
+    uint4 w;
+    if (fmt == 1) {
+      w.x = pack_bf16x2(lo.x, lo.y); w.y = pack_bf16x2(lo.z, lo.w);
+      w.z = pack_bf16x2(hi.x, hi.y); w.w = pack_bf16x2(hi.z, hi.w);
+    } else {
+      __half2 t;
+      t = __floats2half2_rn(lo.x, lo.y); w.x = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2half2_rn(lo.z, lo.w); w.y = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2half2_rn(hi.x, hi.y); w.z = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2half2_rn(hi.z, hi.w); w.w = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(dq) + off) = w;
   }
 }
 
@@ -982,8 +1061,13 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
   const int fmt = a.dtype == DT_BF16 ? 1 : 0;
   {
     const int64_t warps = (int64_t)a.B * a.H * a.Sq;
-    attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-        args->dout, a.o, fmt, a.o_sb, a.o_sh, a.o_ss, args->delta, a.B, a.H, a.Sq, a.D);
+    if (a.D == 64 && fmt == 1 && tma_ok4(args->dout, a.o_sb, a.o_sh, a.o_ss) && tma_ok4(a.o, a.o_sb, a.o_sh, a.o_ss))
+      attn_delta64_kernel<<<(unsigned)((warps * 8 + 255) / 256), 256, 0, st>>>(
+          (const __nv_bfloat16*)args->dout, (const __nv_bfloat16*)a.o, a.o_sb, a.o_sh, a.o_ss, args->delta, a.B,
+          a.H, a.Sq);
+    else
+      attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+          args->dout, a.o, fmt, a.o_sb, a.o_sh, a.o_ss, args->delta, a.B, a.H, a.Sq, a.D);
     CT_LAUNCH_OK();
   }
   const bool tc_ok = a.D == 64 && tma_ok4(a.q, a.q_sb, a.q_sh, a.q_ss) &&
@@ -1021,7 +1105,7 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     const int64_t grid = (int64_t)a.B * a.H * ((a.Sk + 127) / 128);
     attn_bwd_tc_kernel<<<(unsigned)grid, FA_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
     CT_LAUNCH_OK();
-    const int64_t n = (int64_t)a.B * a.Sq * a.H * 64;
+    const int64_t n = (int64_t)a.B * a.Sq * a.H * 64 / 8;
     int64_t blocks = (n + 255) / 256;
     if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
     attn_dq_convert_kernel<<<(unsigned)blocks, 256, 0, st>>>(args->dq_accum, args->dq, fmt, args->dq_sb,

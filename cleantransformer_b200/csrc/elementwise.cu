@@ -67,6 +67,41 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// bf16 fast path: each thread owns 8 consecutive columns (one 16-byte load per row), a block covers
+// 256 columns x a slab of rows; 8 row-groups reduced through smem.
+__global__ void __launch_bounds__(256)
+    colsum_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, float* __restrict__ out,
+                         int64_t rows, int64_t cols, int64_t rows_per_block) {
+  __shared__ float red[8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c0 = (int64_t)blockIdx.x * 256 + tx * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c0 < cols) {
+#pragma unroll 4
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const uint4 u = __ldcs(reinterpret_cast<const uint4*>(x + r * ld + c0));
+      float2 f;
+      f = unpack_bf16x2(u.x); acc[0] += f.x; acc[1] += f.y;
+      f = unpack_bf16x2(u.y); acc[2] += f.x; acc[3] += f.y;
+      f = unpack_bf16x2(u.z); acc[4] += f.x; acc[5] += f.y;
+      f = unpack_bf16x2(u.w); acc[6] += f.x; acc[7] += f.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[ty][tx * 8 + i] = acc[i];
+  __syncthreads();
+  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+
 __global__ void __launch_bounds__(256)
     act_fwd_kernel(const void* __restrict__ x, int xdt, void* __restrict__ y, int ydt, int act,
                    int64_t n) {
@@ -80,6 +115,37 @@ __global__ void __launch_bounds__(256)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     st_any(dx, ddt, i, ld_any(dy, gdt, i) * act_grad(ld_any(x, xdt, i), act));
+}
+// all-bf16 fast paths: 16-byte accesses
+__global__ void __launch_bounds__(256)
+    act_fwd_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int act, int64_t nvec) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 u = __ldcs(x + i);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    uint4 o;
+    o.x = pack_bf16x2(act_apply(a.x, act), act_apply(a.y, act));
+    o.y = pack_bf16x2(act_apply(b.x, act), act_apply(b.y, act));
+    o.z = pack_bf16x2(act_apply(c.x, act), act_apply(c.y, act));
+    o.w = pack_bf16x2(act_apply(d.x, act), act_apply(d.y, act));
+    y[i] = o;
+  }
+}
+__global__ void __launch_bounds__(256)
+    act_bwd_bf16x8_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, uint4* __restrict__ dx,
+                          int act, int64_t nvec) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 g = __ldcs(dy + i), u = __ldcs(x + i);
+    float2 ga = unpack_bf16x2(g.x), gb = unpack_bf16x2(g.y), gc = unpack_bf16x2(g.z), gd = unpack_bf16x2(g.w);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    uint4 o;
+    o.x = pack_bf16x2(ga.x * act_grad(a.x, act), ga.y * act_grad(a.y, act));
+    o.y = pack_bf16x2(gb.x * act_grad(b.x, act), gb.y * act_grad(b.y, act));
+    o.z = pack_bf16x2(gc.x * act_grad(c.x, act), gc.y * act_grad(c.y, act));
+    o.w = pack_bf16x2(gd.x * act_grad(d.x, act), gd.y * act_grad(d.y, act));
+    dx[i] = o;
+  }
 }
 
 static int ew_blocks(int64_t work) {
@@ -124,6 +190,17 @@ extern "C" int ct_colsum(const void* x, int x_dtype, int64_t ld, float* out, int
   int64_t rpb = (rows + slabs - 1) / slabs;
   if (rpb < 64) rpb = 64;
   slabs = (rows + rpb - 1) / rpb;
+  if (x_dtype == DT_BF16 && (cols % 8) == 0 && (ld % 8) == 0 && (((uintptr_t)x) & 15) == 0) {
+    const int64_t strips8 = (cols + 255) / 256;
+    int64_t slabs8 = ((int64_t)sm_count() * 8 + strips8 - 1) / strips8;
+    int64_t rpb8 = (rows + slabs8 - 1) / slabs8;
+    if (rpb8 < 64) rpb8 = 64;
+    slabs8 = (rows + rpb8 - 1) / rpb8;
+    dim3 grid8((unsigned)strips8, (unsigned)slabs8);
+    colsum_bf16x8_kernel<<<grid8, 256, 0, st>>>((const __nv_bfloat16*)x, ld, out, rows, cols, rpb8);
+    CT_LAUNCH_OK();
+    return 0;
+  }
   dim3 grid((unsigned)strips, (unsigned)slabs);
   colsum_kernel<<<grid, 256, 0, st>>>(x, x_dtype, ld, out, rows, cols, rpb);
   CT_LAUNCH_OK();
@@ -136,7 +213,10 @@ extern "C" int ct_act_fwd(const void* x, int x_dtype, void* y, int y_dtype, int 
   CT_REQUIRE(dt_any_ok(x_dtype) && dt_any_ok(y_dtype) && act >= 0 && act <= 4, CT_ERR_UNSUPPORTED,
              "ct_act_fwd: dtype/act");
   if (n <= 0) return 0;
-  act_fwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, y, y_dtype, act, n);
+  if (x_dtype == DT_BF16 && y_dtype == DT_BF16 && (n % 8) == 0 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0)
+    act_fwd_bf16x8_kernel<<<ew_blocks(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, act, n / 8);
+  else
+    act_fwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, y, y_dtype, act, n);
   CT_LAUNCH_OK();
   return 0;
 }
@@ -148,8 +228,13 @@ extern "C" int ct_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dty
                  act <= 4,
              CT_ERR_UNSUPPORTED, "ct_act_bwd: dtype/act");
   if (n <= 0) return 0;
-  act_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, x, x_dtype, dx,
-                                                                 dx_dtype, act, n);
+  if (dy_dtype == DT_BF16 && x_dtype == DT_BF16 && dx_dtype == DT_BF16 && (n % 8) == 0 &&
+      ((((uintptr_t)dy) | ((uintptr_t)x) | ((uintptr_t)dx)) & 15) == 0)
+    act_bwd_bf16x8_kernel<<<ew_blocks(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)x,
+                                                                              (uint4*)dx, act, n / 8);
+  else
+    act_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, x, x_dtype, dx,
+                                                                   dx_dtype, act, n);
   CT_LAUNCH_OK();
   return 0;
 }

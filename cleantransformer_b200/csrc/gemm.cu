@@ -49,9 +49,49 @@ __device__ __forceinline__ void st_elem(void* p, int dt, int64_t i, float v) {
   else reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
 }
 
+// Code size matters here: the tcgen05 kernel's epilogue is executed by 4 warps while the TMA and MMA
+// warps run other code, and a fully inlined epilogue (32 unrolled elements x every activation x every
+// dtype x scalar fallbacks) reached 47k SASS instructions (750 KB) and stalled on instruction fetch.
+// Rare paths are therefore real function calls.
+__device__ __noinline__ float act_apply_call(float x, int act) { return act_apply(x, act); }
+__device__ __noinline__ float act_grad_call(float x, int act) { return act_grad(x, act); }
+
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float u = 0.79788456f * x * (1.f + 0.044715f * x * x);
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(u), hx);
+}
+__device__ __forceinline__ float gelu_tanh_grad_fast(float x) {
+  const float t = tanh_approx(0.79788456f * x * (1.f + 0.044715f * x * x));
+  return 0.5f * x * ((1.f - t * t) * (0.79788456f + 0.1070322243f * x * x)) + 0.5f * (1.f + t);
+}
+__device__ __forceinline__ void act32(float (&t)[32], int act) {
+  if (act == ACT_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = gelu_tanh_fast(t[j]);
+  } else if (act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = fmaxf(t[j], 0.f);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = act_apply_call(t[j], act);
+  }
+}
+__device__ __forceinline__ void actgrad32(float (&t)[32], const float (&s)[32], int act) {
+  if (act == ACT_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] *= gelu_tanh_grad_fast(s[j]);
+  } else if (act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = s[j] > 0.f ? t[j] : 0.f;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] *= act_grad_call(s[j], act);
+  }
+}
+
 // Scalar epilogue for one element (SIMT kernel and ragged edges of the tcgen05 kernel).
-__device__ __forceinline__ void epi_scalar(const EpiParams& e, int m, int n, float acc,
-                                           bool add_bias) {
+__device__ __noinline__ void epi_scalar(const EpiParams& e, int m, int n, float acc, bool add_bias) {
   float t = e.alpha * acc;
   if (e.bias && add_bias) t += e.bias[n];
   if (e.atomic_out) {
@@ -59,9 +99,9 @@ __device__ __forceinline__ void epi_scalar(const EpiParams& e, int m, int n, flo
     return;
   }
   if (e.preact) st_elem(e.preact, e.preact_dtype, (int64_t)m * e.ldp + n, t);
-  t = act_apply(t, e.act);
+  if (e.act != ACT_NONE) t = act_apply_call(t, e.act);
   if (e.actgrad_src)
-    t *= act_grad(ld_elem(e.actgrad_src, e.actgrad_dtype, (int64_t)m * e.ldg + n), e.actgrad_act);
+    t *= act_grad_call(ld_elem(e.actgrad_src, e.actgrad_dtype, (int64_t)m * e.ldg + n), e.actgrad_act);
   if (e.residual) t += ld_elem(e.residual, e.res_dtype, (int64_t)m * e.ldr + n);
   if (e.beta != 0.f) t += e.beta * ld_elem(e.C, e.c_dtype, (int64_t)m * e.ldc + n);
   st_elem(e.C, e.c_dtype, (int64_t)m * e.ldc + n, t);
@@ -76,56 +116,124 @@ __device__ __forceinline__ void ld32(const void* p, int dt, int64_t off, float (
       float4 a = q[i];
       v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
     }
-  } else if (dt == DT_BF16) {
-    const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + off);
+  } else {
+    const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p) + off);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint4 a = q[i];
-      float2 f;
-      f = unpack_bf16x2(a.x); v[8 * i] = f.x; v[8 * i + 1] = f.y;
-      f = unpack_bf16x2(a.y); v[8 * i + 2] = f.x; v[8 * i + 3] = f.y;
-      f = unpack_bf16x2(a.z); v[8 * i + 4] = f.x; v[8 * i + 5] = f.y;
-      f = unpack_bf16x2(a.w); v[8 * i + 6] = f.x; v[8 * i + 7] = f.y;
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 f;
+        if (dt == DT_BF16) f = unpack_bf16x2(w[k]);
+        else { __half2 h = *reinterpret_cast<const __half2*>(&w[k]); f = __half22float2(h); }
+        v[8 * i + 2 * k] = f.x; v[8 * i + 2 * k + 1] = f.y;
+      }
     }
-  } else {
-    const __half* q = reinterpret_cast<const __half*>(p) + off;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __half2float(q[i]);
-  }
-}
-__device__ __forceinline__ void st32(void* p, int dt, int64_t off, const float (&v)[32]) {
-  if (dt == DT_F32) {
-    float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + off);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  } else if (dt == DT_BF16) {
-    uint4* q = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p) + off);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 a;
-      a.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
-      a.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      a.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-      a.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      q[i] = a;
-    }
-  } else {
-    __half* q = reinterpret_cast<__half*>(p) + off;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) q[i] = __float2half_rn(v[i]);
   }
 }
 
-// Epilogue for 32 consecutive columns [n0, n0+32) of row m held as fp32 accumulators.
+// Direct (row-per-thread) epilogue for 32 consecutive columns [n0, n0+32) of row m: split-K
+// red.add output, or the scalar fallback for ragged / unaligned problems.
 __device__ __forceinline__ void epi_chunk32(const EpiParams& e, int m, int n0, float (&t)[32],
                                             bool add_bias) {
   if (m >= e.M || n0 >= e.N) return;
   const bool full = (n0 + 32 <= e.N) && e.vec_ok;
-  if (!full) {
-    const int lim = min(32, e.N - n0);
-    for (int j = 0; j < lim; ++j) epi_scalar(e, m, n0 + j, t[j], add_bias);
+  if (full && e.atomic_out) {
+    float* c = reinterpret_cast<float*>(e.C) + (int64_t)m * e.ldc + n0;
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
+    const bool bias = e.bias && add_bias;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 b = bias ? __ldg(b4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + 4 * i),
+                   "f"(fmaf(e.alpha, t[4 * i], b.x)), "f"(fmaf(e.alpha, t[4 * i + 1], b.y)),
+                   "f"(fmaf(e.alpha, t[4 * i + 2], b.z)), "f"(fmaf(e.alpha, t[4 * i + 3], b.w))
+                   : "memory");
+    }
     return;
   }
+  // static indices only: a runtime-indexed t[] would be demoted to local memory for EVERY path
+  const int lim = e.N - n0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < lim) epi_scalar(e, m, n0 + j, t[j], add_bias);
+}
+
+// ---- coalesced epilogue stores --------------------------------------------------------------------
+// A thread owns one accumulator ROW, so a direct store instruction of a warp touches 32 different
+// rows (32 half-used sectors per request). Instead each warp transposes its 32x32 result block
+// through a private smem buffer (row stride 144 B: conflict-free 16-byte row writes) and writes it
+// out with lanes running along the row: 64 B (16-bit) or 128 B (fp32) contiguous per row, 8 or 4
+// rows per instruction.
+constexpr int EPI_STAGE_ROW = 144;
+constexpr int EPI_STAGE_BYTES = 32 * EPI_STAGE_ROW;  // per epilogue warp
+
+__device__ __forceinline__ void stage_store32(uint32_t stage, int lane, const float (&v)[32], int dt,
+                                              void* gbase, int64_t ld, int m_base, int M, int n0) {
+  const uint32_t my = stage + lane * EPI_STAGE_ROW;
+  if (dt == DT_F32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my + 16 * i), "f"(v[4 * i]),
+                   "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t w0, w1, w2, w3;
+      if (dt == DT_BF16) {
+        w0 = pack_bf16x2(v[8 * i], v[8 * i + 1]); w1 = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        w2 = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); w3 = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      } else {
+        __half2 h;
+        h = __floats2half2_rn(v[8 * i], v[8 * i + 1]); w0 = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]); w1 = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]); w2 = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]); w3 = *reinterpret_cast<uint32_t*>(&h);
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my + 16 * i), "r"(w0), "r"(w1),
+                   "r"(w2), "r"(w3) : "memory");
+    }
+  }
+  __syncwarp();
+  if (dt == DT_F32) {
+    const int piece = lane & 7;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = (lane >> 3) + 4 * k;
+      uint4 w;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                   : "r"(stage + r * EPI_STAGE_ROW + piece * 16));
+      const int m = m_base + r;
+      if (m < M) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(gbase) + (int64_t)m * ld + n0 + piece * 4) = w;
+    }
+  } else {
+    const int piece = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = (lane >> 2) + 8 * k;
+      uint4 w;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                   : "r"(stage + r * EPI_STAGE_ROW + piece * 16));
+      const int m = m_base + r;
+      if (m < M)
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(gbase) + (int64_t)m * ld + n0 + piece * 8) = w;
+    }
+  }
+  __syncwarp();
+}
+
+// Warp-collective epilogue for a 32-row x 32-column block: lane l owns row m_base + l.
+__device__ __forceinline__ void epi_block32(const EpiParams& e, int m_base, int lane, int n0, float (&t)[32],
+                                            bool add_bias, uint32_t stage) {
+  if (n0 >= e.N) return;  // warp-uniform
+  const int m = m_base + lane;
+  const bool full = (n0 + 32 <= e.N) && e.vec_ok;  // warp-uniform
+  if (!full || e.atomic_out) {
+    epi_chunk32(e, m, n0, t, add_bias);
+    return;
+  }
+  const bool row_ok = m < e.M;
 #pragma unroll
   for (int j = 0; j < 32; ++j) t[j] *= e.alpha;
   if (e.bias && add_bias) {
@@ -136,39 +244,26 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& e, int m, int n0, f
       t[4 * i] += b.x; t[4 * i + 1] += b.y; t[4 * i + 2] += b.z; t[4 * i + 3] += b.w;
     }
   }
-  if (e.atomic_out) {
-    float* c = reinterpret_cast<float*>(e.C) + (int64_t)m * e.ldc + n0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + 4 * i), "f"(t[4 * i]),
-                   "f"(t[4 * i + 1]), "f"(t[4 * i + 2]), "f"(t[4 * i + 3])
-                   : "memory");
-    return;
-  }
-  if (e.preact) st32(e.preact, e.preact_dtype, (int64_t)m * e.ldp + n0, t);
-  if (e.act != ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) t[j] = act_apply(t[j], e.act);
-  }
-  if (e.actgrad_src) {
+  if (e.preact) stage_store32(stage, lane, t, e.preact_dtype, e.preact, e.ldp, m_base, e.M, n0);
+  if (e.act != ACT_NONE) act32(t, e.act);
+  if (e.actgrad_src && row_ok) {
     float s[32];
     ld32(e.actgrad_src, e.actgrad_dtype, (int64_t)m * e.ldg + n0, s);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) t[j] *= act_grad(s[j], e.actgrad_act);
+    actgrad32(t, s, e.actgrad_act);
   }
-  if (e.residual) {
+  if (e.residual && row_ok) {
     float s[32];
     ld32(e.residual, e.res_dtype, (int64_t)m * e.ldr + n0, s);
 #pragma unroll
     for (int j = 0; j < 32; ++j) t[j] += s[j];
   }
-  if (e.beta != 0.f) {
+  if (e.beta != 0.f && row_ok) {
     float s[32];
     ld32(e.C, e.c_dtype, (int64_t)m * e.ldc + n0, s);
 #pragma unroll
     for (int j = 0; j < 32; ++j) t[j] = fmaf(e.beta, s[j], t[j]);
   }
-  st32(e.C, e.c_dtype, (int64_t)m * e.ldc + n0, t);
+  stage_store32(stage, lane, t, e.c_dtype, e.C, e.ldc, m_base, e.M, n0);
 }
 
 // =================================================================================================
@@ -180,12 +275,13 @@ constexpr int GEMM_THREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
 template <int BN>
-struct GemmCfg {
+struct GemmCfg {  // (EPI_STAGE_BYTES is defined above)
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                                    4 * EPI_STAGE_BYTES /*epilogue transposition buffers*/;
 };
 
 struct TcParams {
@@ -213,6 +309,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const uint32_t tfull_bar = bar_base + 16 * STAGES;      // 2 x 8 B
   const uint32_t tempty_bar = tfull_bar + 16;             // 2 x 8 B
   const uint32_t tmem_slot = tempty_bar + 16;             // 4 B
+  const uint32_t epi_stage = bar_base + 256;               // 4 x EPI_STAGE_BYTES
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -349,18 +446,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const uint32_t acc_ph = (local >> 1) & 1;
       mbar_wait(tfull_bar + 8 * acc, acc_ph);
       tc_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
+      const int m_base = m_blk * BM + q * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const uint32_t stage = epi_stage + (uint32_t)q * EPI_STAGE_BYTES;
       if (kb1 > kb0) {
+        // TMEM load of chunk c+1 is in flight while chunk c goes through the (single) epilogue body
+        uint32_t r[32];
+        tmem_ld_32x32(t_row, r);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_row + c * 32, r);
-          tmem_ld_wait();
           float t[32];
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(r[j]);
-          epi_chunk32(e, row, n_blk * BN + c * 32, t, split == 0);
+          if (c + 1 < BN / 32) tmem_ld_32x32(t_row + (c + 1) * 32, r);
+          epi_block32(e, m_base, lane, n_blk * BN + c * 32, t, split == 0, stage);
         }
       }
       tc_fence_before();

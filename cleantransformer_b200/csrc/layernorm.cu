@@ -151,8 +151,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 // dx = rstd * (gy - mean(gy) - xhat * mean(gy * xhat)),  gy = gamma * dy,  xhat = (x - mean) * rstd
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (per-warp register partials -> smem ->
 // one atomicAdd per column per CTA)
+// dgamma/dbeta partials live in shared memory (one private [2][COLS] slice per warp, each lane
+// only ever touches its own columns, so no synchronisation is needed until the final reduction).
+// Keeping them in registers cost 64 registers per thread (194 total) and limited the kernel to 8
+// warps per SM; with ~100 registers two CTAs are resident.
 template <int VPL>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
     ln_bwd_vec_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ dy2,
                       int dy2_dtype, const void* __restrict__ x, int x_dtype,
                       const float* __restrict__ gamma, const float* __restrict__ mean_in,
@@ -160,18 +164,23 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
                       int dx_add_dtype, void* __restrict__ dx, int dx_dtype,
                       float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows) {
   constexpr int COLS = VPL * 128;
-  __shared__ float red[LN_WARPS][128 + 1];
+  extern __shared__ float acc_s[];  // [LN_WARPS][2][COLS]
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int64_t warp = (int64_t)blockIdx.x * LN_WARPS + wib;
   const int64_t nwarps = (int64_t)gridDim.x * LN_WARPS;
+  float* my_dg = acc_s + (size_t)wib * 2 * COLS;
+  float* my_db = my_dg + COLS;
+  const bool need_gb = (dgamma != nullptr) || (dbeta != nullptr);
 
-  float4 g[VPL], dg[VPL], db[VPL];
+  float4 g[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     g[i] = Vec4<float>::load(gamma + i * 128 + lane * 4);
-    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (need_gb) {
+      Vec4<float>::store(my_dg + i * 128 + lane * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+      Vec4<float>::store(my_db + i * 128 + lane * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
   }
   for (int64_t row = warp; row < rows; row += nwarps) {
     const float mean = mean_in[row], rstd = rstd_in[row];
@@ -192,9 +201,21 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
       }
       xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd;
       xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
-      dg[i].x = fmaf(d[i].x, xh[i].x, dg[i].x); dg[i].y = fmaf(d[i].y, xh[i].y, dg[i].y);
-      dg[i].z = fmaf(d[i].z, xh[i].z, dg[i].z); dg[i].w = fmaf(d[i].w, xh[i].w, dg[i].w);
-      db[i].x += d[i].x; db[i].y += d[i].y; db[i].z += d[i].z; db[i].w += d[i].w;
+    }
+    if (need_gb) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float4 a = Vec4<float>::load(my_dg + i * 128 + lane * 4);
+        float4 b = Vec4<float>::load(my_db + i * 128 + lane * 4);
+        a.x = fmaf(d[i].x, xh[i].x, a.x); a.y = fmaf(d[i].y, xh[i].y, a.y);
+        a.z = fmaf(d[i].z, xh[i].z, a.z); a.w = fmaf(d[i].w, xh[i].w, a.w);
+        b.x += d[i].x; b.y += d[i].y; b.z += d[i].z; b.w += d[i].w;
+        Vec4<float>::store(my_dg + i * 128 + lane * 4, a);
+        Vec4<float>::store(my_db + i * 128 + lane * 4, b);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
       d[i].x *= g[i].x; d[i].y *= g[i].y; d[i].z *= g[i].z; d[i].w *= g[i].w;
       s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
       s2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
@@ -216,26 +237,18 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
       store4_dyn(dx, dx_dtype, idx, o);
     }
   }
-  // cross-warp reduction of dgamma / dbeta partials, 128 columns at a time
-  if (dgamma == nullptr && dbeta == nullptr) return;
+  if (!need_gb) return;
+  __syncthreads();
+  // cross-warp reduction: thread t sums column t, t + 256, ... over the LN_WARPS slices
+  for (int c = threadIdx.x; c < COLS; c += LN_WARPS * 32) {
+    float sg = 0.f, sb = 0.f;
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    float* dst = pass == 0 ? dgamma : dbeta;
-    if (dst == nullptr) continue;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      float4 v = pass == 0 ? dg[i] : db[i];
-      __syncthreads();
-      red[wib][lane * 4 + 0] = v.x; red[wib][lane * 4 + 1] = v.y;
-      red[wib][lane * 4 + 2] = v.z; red[wib][lane * 4 + 3] = v.w;
-      __syncthreads();
-      if (threadIdx.x < 128) {
-        float acc = 0.f;
-#pragma unroll
-        for (int w = 0; w < LN_WARPS; ++w) acc += red[w][threadIdx.x];
-        atomicAdd(dst + i * 128 + threadIdx.x, acc);
-      }
+    for (int w = 0; w < LN_WARPS; ++w) {
+      sg += acc_s[(size_t)w * 2 * COLS + c];
+      sb += acc_s[(size_t)w * 2 * COLS + COLS + c];
     }
+    if (dgamma) atomicAdd(dgamma + c, sg);
+    if (dbeta) atomicAdd(dbeta + c, sb);
   }
 }
 
@@ -295,9 +308,10 @@ using namespace ct;
 extern "C" int ct_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta,
                                 void* y, int y_dtype, void* y2, int y2_dtype, float* mean,
                                 float* rstd, int64_t rows, int64_t cols, float eps, void* stream) {
-  CT_REQUIRE(x && gamma && beta && (y || y2), CT_ERR_BAD_ARG, "ct_layernorm_fwd: null pointer");
   CT_REQUIRE(rows >= 0 && cols > 0, CT_ERR_BAD_ARG, "ct_layernorm_fwd: bad shape %lld x %lld",
              (long long)rows, (long long)cols);
+  if (rows == 0) return 0;  // empty input: nothing to do (pointers may legitimately be null)
+  CT_REQUIRE(x && gamma && beta && (y || y2), CT_ERR_BAD_ARG, "ct_layernorm_fwd: null pointer");
   CT_REQUIRE(dt_ok(x_dtype) && (!y || dt_ok(y_dtype)) && (!y2 || dt_ok(y2_dtype)),
              CT_ERR_UNSUPPORTED, "ct_layernorm_fwd: dtype must be f32 or bf16");
   if (rows == 0) return 0;
@@ -343,17 +357,24 @@ extern "C" int ct_layernorm_bwd(const void* dy, int dy_dtype, const void* dy2, i
   if (rows == 0) return 0;
   // fewer, fatter CTAs than forward: each CTA ends with 2*cols atomics
   int grid = ln_grid(rows);
-  const int cap = sm_count() * 2;
+  const int cap = sm_count() * 2;  // 2 resident CTAs per SM, each ends with 2*cols atomics
   if (grid > cap) grid = cap;
   const bool vec = (cols % 128 == 0) && cols <= 1024 && aligned16(x) && aligned16(dy) &&
                    aligned16(dy2) && aligned16(dx) && aligned16(dx_add) && aligned16(gamma);
 #define CT_LN_BWD(V)                                                                             \
-  case V:                                                                                        \
-    ln_bwd_vec_kernel<V><<<grid, LN_WARPS * 32, 0, st>>>(dy, dy_dtype, dy2, dy2_dtype, x,        \
-                                                         x_dtype, gamma, mean, rstd, dx_add,     \
-                                                         dx_add_dtype, dx, dx_dtype, dgamma,     \
-                                                         dbeta, rows);                           \
-    break;
+  case V: {                                                                                      \
+    const int smem = LN_WARPS * 2 * V * 128 * (int)sizeof(float);                                \
+    static bool attr = false;                                                                    \
+    if (!attr) {                                                                                 \
+      CT_CUDA_OK(cudaFuncSetAttribute(ln_bwd_vec_kernel<V>,                                      \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));       \
+      attr = true;                                                                               \
+    }                                                                                            \
+    ln_bwd_vec_kernel<V><<<grid, LN_WARPS * 32, smem, st>>>(dy, dy_dtype, dy2, dy2_dtype, x,     \
+                                                            x_dtype, gamma, mean, rstd, dx_add,  \
+                                                            dx_add_dtype, dx, dx_dtype, dgamma,  \
+                                                            dbeta, rows);                        \
+  } break;
   if (vec) {
     switch ((int)(cols / 128)) {
       CT_LN_BWD(1) CT_LN_BWD(2) CT_LN_BWD(3) CT_LN_BWD(4) CT_LN_BWD(5) CT_LN_BWD(6) CT_LN_BWD(7)

@@ -342,3 +342,108 @@ def lm_loss(logits, labels, shift=True):
 
 def default_scale(head_dim):
     return 1.0 / math.sqrt(head_dim)
+
+
+# ------------------------------------------------------------------------------------------------
+# Fused pre-LN block (Bloom / GPT-2 wiring): one autograd node per block
+# ------------------------------------------------------------------------------------------------
+class PreLNBlockFn(torch.autograd.Function):
+    """x -> x + proj(attn(qkv(LN1 x)))  -> ... + W2 act(W1 LN2(.)):
+    modeling_bloom.py:142-159 (apply_residual_connection_post_layernorm = False) and the 'gpt2' branch
+    of modeling_gpt.py:147-152. Compared with composing the op-level Functions this removes, per layer,
+    the stand-alone activation-gradient kernel (fused into the 4h->h dgrad epilogue), the two residual
+    gradient adds (fused into the LayerNorm backward via dx_add) and ~10 autograd nodes.
+
+    `spec` = dict(ln1, qkv, proj, ln2, fc1, fc2: modules holding .weight/.bias; w_in_out: Conv1D
+    layout flag; n_head, layout, scale, causal, causal_fill, act). Parameter gradients are written in
+    place (functional.grad_buffer), only the hidden-state gradient flows through autograd."""
+
+    @staticmethod
+    def forward(ctx, x, spec, kbias2, first_valid):
+        cd = compute_dtype()
+        io = spec["w_in_out"]
+        B, S, H = x.shape
+        xd = x.detach().contiguous()
+        x2 = xd.view(B * S, H)
+        ln1, _, mean1, rstd1 = ops.layernorm_fwd(x2, spec["ln1"].weight.detach(), spec["ln1"].bias.detach(),
+                                                 spec["ln1"].eps, out_dtype=cd)
+        qkv, _ = ops.linear_fwd(ln1, shadow(spec["qkv"].weight, cd), spec["qkv"].bias.detach(), out_dtype=cd,
+                                w_in_out=io)
+        q, k, v = split_packed(qkv.view(B, S, -1), spec["n_head"], spec["layout"])
+        o, lse2 = ops.attn_fwd(q, k, v, spec["scale"], spec["causal"], spec["causal_fill"], kbias2, first_valid)
+        att, _ = ops.linear_fwd(o.view(B * S, H), shadow(spec["proj"].weight, cd), spec["proj"].bias.detach(),
+                                residual=x2, out_dtype=torch.float32, w_in_out=io)
+        ln2, _, mean2, rstd2 = ops.layernorm_fwd(att, spec["ln2"].weight.detach(), spec["ln2"].bias.detach(),
+                                                 spec["ln2"].eps, out_dtype=cd)
+        h4, pre = ops.linear_fwd(ln2, shadow(spec["fc1"].weight, cd), spec["fc1"].bias.detach(), act=spec["act"],
+                                 out_dtype=cd, save_preact=True, w_in_out=io)
+        out, _ = ops.linear_fwd(h4, shadow(spec["fc2"].weight, cd), spec["fc2"].bias.detach(), residual=att,
+                                out_dtype=torch.float32, w_in_out=io)
+        ctx.save_for_backward(x2, mean1, rstd1, ln1, qkv, o, lse2, att, mean2, rstd2, ln2, pre, h4, kbias2,
+                              first_valid)
+        ctx.spec = spec
+        ctx.shape = (B, S, H)
+        ctx.mark_non_differentiable(k, v)
+        return out.view(B, S, H), k, v
+
+    @staticmethod
+    def _linear_bwd(lin, dy16, x16, io, cd, need_dx=True, actgrad_src=None, actgrad_act=ops.ACT_NONE):
+        w, b = lin.weight, lin.bias
+        if w.requires_grad:
+            gw, acc = grad_buffer(w)
+            gb = None
+            if b is not None and b.requires_grad:
+                gb, accb = grad_buffer(b)
+                if accb != acc:
+                    (gb if not accb else gw).zero_()
+                    acc = True
+            ops.linear_wgrad(dy16, x16, gw, gb, accumulate=acc, w_in_out=io)
+            grad_written(w)
+            if gb is not None:
+                grad_written(b)
+        if not need_dx:
+            return None
+        return ops.linear_dgrad(dy16, shadow(w, cd), out_dtype=cd, actgrad_src=actgrad_src,
+                                actgrad_act=actgrad_act, w_in_out=io)
+
+    @staticmethod
+    def _ln_bwd(ln, dy16, x, mean, rstd, dx_add):
+        gw, acc_w = grad_buffer(ln.weight) if ln.weight.requires_grad else (None, False)
+        gb, acc_b = grad_buffer(ln.bias) if ln.bias.requires_grad else (None, False)
+        if gw is not None and gb is not None and acc_w != acc_b:
+            (gw if not acc_w else gb).zero_()
+            acc_w = acc_b = True
+        dx = ops.layernorm_bwd(dy16, x, ln.weight.detach(), mean, rstd, gw, gb, acc_w if gw is not None else acc_b,
+                               dx_add=dx_add, dx_dtype=torch.float32)
+        if gw is not None:
+            grad_written(ln.weight)
+        if gb is not None:
+            grad_written(ln.bias)
+        return dx
+
+    @staticmethod
+    def backward(ctx, g_out, _gk, _gv):
+        (x2, mean1, rstd1, ln1, qkv, o, lse2, att, mean2, rstd2, ln2, pre, h4, kbias2, first_valid) = ctx.saved_tensors
+        spec = ctx.spec
+        B, S, H = ctx.shape
+        io = spec["w_in_out"]
+        cd = ln1.dtype
+        g_out = g_out.contiguous().view(B * S, H)
+        if g_out.dtype != torch.float32:
+            g_out = ops.cast(g_out, torch.float32)
+        g16 = ops.cast(g_out, cd)
+        # FFN: out = att + fc2(act(fc1(ln2)))
+        d_pre = PreLNBlockFn._linear_bwd(spec["fc2"], g16, h4, io, cd, actgrad_src=pre, actgrad_act=spec["act"])
+        d_ln2 = PreLNBlockFn._linear_bwd(spec["fc1"], d_pre, ln2, io, cd)
+        g_att = PreLNBlockFn._ln_bwd(spec["ln2"], d_ln2, att, mean2, rstd2, g_out)  # + residual path
+        # attention: att = x + proj(attn(qkv(ln1)))
+        g16b = ops.cast(g_att, cd)
+        d_o = PreLNBlockFn._linear_bwd(spec["proj"], g16b, o.view(B * S, H), io, cd)
+        dqkv = torch.empty_like(qkv)
+        q, k, v = split_packed(qkv.view(B, S, -1), spec["n_head"], spec["layout"])
+        dq, dk, dv = split_packed(dqkv.view(B, S, -1), spec["n_head"], spec["layout"])
+        ops.attn_bwd(d_o.view(B, S, H), q, k, v, o, lse2, dq, dk, dv, spec["scale"], spec["causal"],
+                     spec["causal_fill"], kbias2, first_valid)
+        d_ln1 = PreLNBlockFn._linear_bwd(spec["qkv"], dqkv, ln1, io, cd)
+        g_x = PreLNBlockFn._ln_bwd(spec["ln1"], d_ln1, x2, mean1, rstd1, g_att)
+        return g_x.view(B, S, H), None, None, None

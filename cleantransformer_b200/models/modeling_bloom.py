@@ -172,10 +172,24 @@ class BloomBlock(torch.nn.Module):
         self.apply_residual_connection_post_layernorm = config.apply_residual_connection_post_layernorm
         self.hidden_dropout = config.hidden_dropout
 
+    def _fused_spec(self):
+        sa = self.self_attention
+        return dict(ln1=self.input_layernorm, qkv=sa.query_key_value, proj=sa.dense,
+                    ln2=self.post_attention_layernorm, fc1=self.mlp.dense_h_to_4h, fc2=self.mlp.dense_4h_to_h,
+                    w_in_out=False, n_head=sa.num_heads, layout=F.LAYOUT_BLOOM, scale=sa.inv_norm_factor,
+                    causal=True, causal_fill=-ops.FLT_MAX, act=ops.ACT_GELU_TANH)
+
     def forward(self, hidden_states, attention_mask, alibi, head_mask, k_v_past=None):
         cd = F.compute_dtype()
         post = self.apply_residual_connection_post_layernorm
         hidden_states = hidden_states if hidden_states.dtype == torch.float32 else hidden_states.float()
+        if (isinstance(alibi, AttnBias) and k_v_past is None and not post and torch.is_grad_enabled()
+                and hidden_states.requires_grad and alibi.causal and self.hidden_dropout == 0
+                and self.self_attention.attention_dropout.p == 0):
+            # training / full-sequence path: one fused autograd node for the whole block
+            spec = self._fused_spec()
+            out, k, v = F.PreLNBlockFn.apply(hidden_states, spec, alibi.kbias2, alibi.first_valid)
+            return out, (k, v)
         if post:
             res1, ln1 = self.input_layernorm(hidden_states, out_dtype=torch.float32, out2_dtype=cd)
         else:
