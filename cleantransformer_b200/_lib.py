@@ -17,6 +17,7 @@ c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int
 c_i64 = ctypes.c_int64
 c_float = ctypes.c_float
+c_double = ctypes.c_double
 
 
 class GemmArgs(ctypes.Structure):
@@ -81,10 +82,10 @@ SIGNATURES = {
     "ct_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                  c_void_p, c_int, c_i64, c_i64, c_void_p]),
-    "ct_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float,
-                              c_float, c_float, c_float, c_float, c_i64, c_int, c_float, c_void_p]),
+    "ct_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_double,
+                              c_double, c_double, c_double, c_double, c_i64, c_int, c_float, c_void_p]),
     "ct_adamw_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                               c_float, c_float, c_float, c_float, c_float, c_i64, c_int, c_float,
+                               c_double, c_double, c_double, c_double, c_double, c_i64, c_int, c_float,
                                c_void_p]),
     "ct_sgd_step": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float,
                             c_float, c_int, c_void_p]),
@@ -112,6 +113,9 @@ SIGNATURES = {
     "ct_allreduce_bucket": (c_int, [c_i64, c_i64, c_float, c_int, c_int, c_void_p]),
     "ct_broadcast": (c_int, [c_i64, c_i64, c_int, c_void_p]),
     "ct_comm_finalize": (c_int, []),
+    "ct_kv_append": (c_int, [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int,
+                             c_int, c_int, c_int, c_void_p]),
+    "ct_attn_decode": (c_int, [ctypes.POINTER(AttnArgs), c_void_p]),
     "ct_gemm_wgrad_bias": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_i64,
                                    c_i64, c_i64, c_int, c_void_p]),
 }

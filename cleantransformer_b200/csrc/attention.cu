@@ -964,6 +964,24 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+// cache[b,h,pos+s,:] = src[b,h,s,:]  — in-place K/V append into a preallocated [B,H,T_max,D] cache
+// (replaces the O(ctx) torch.concat of modeling_bloom.py:88-92 / modeling_gpt.py:76-80 per layer per step)
+__global__ void __launch_bounds__(256)
+    kv_append_kernel(const uint16_t* __restrict__ src, int64_t s_sb, int64_t s_sh, int64_t s_ss,
+                     uint16_t* __restrict__ cache, int64_t c_sb, int64_t c_sh, int64_t c_ss, int B, int H,
+                     int S, int D, int pos) {
+  const int64_t n = (int64_t)B * H * S * D;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(e % D);
+    const int sidx = (int)((e / D) % S);
+    const int h = (int)((e / ((int64_t)D * S)) % H);
+    const int b = (int)(e / ((int64_t)D * S * H));
+    cache[(int64_t)b * c_sb + (int64_t)h * c_sh + (int64_t)(pos + sidx) * c_ss + d] =
+        src[(int64_t)b * s_sb + (int64_t)h * s_sh + (int64_t)sidx * s_ss + d];
+  }
+}
+
 static int make_qkv_tmap(CUtensorMap* tm, const void* base, int64_t sb, int64_t sh, int64_t ss, int B,
                          int H, int S, int D) {
   uint64_t dims[4] = {(uint64_t)D, (uint64_t)S, (uint64_t)H, (uint64_t)B};
@@ -1145,4 +1163,29 @@ extern "C" int ct_attn_mask_prep(const void* attention_mask, int mask_dtype, int
       attention_mask, mask_dtype, (int)Sk, (int)H, mode, slopes, kbias2, first_valid);
   CT_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int ct_kv_append(const void* src, int64_t s_sb, int64_t s_sh, int64_t s_ss, void* cache,
+                            int64_t c_sb, int64_t c_sh, int64_t c_ss, int B, int H, int S_new, int D,
+                            int pos, int t_max, void* stream) {
+  CT_REQUIRE(src && cache, CT_ERR_BAD_ARG, "ct_kv_append: null pointer");
+  CT_REQUIRE(B > 0 && H > 0 && S_new >= 0 && D > 0 && pos >= 0 && pos + S_new <= t_max, CT_ERR_BAD_ARG,
+             "ct_kv_append: rows [%d,%d) do not fit a cache of %d", pos, pos + S_new, t_max);
+  if (S_new == 0) return 0;
+  const int64_t n = (int64_t)B * H * S_new * D;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  kv_append_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const uint16_t*)src, s_sb, s_sh, s_ss, (uint16_t*)cache, c_sb, c_sh, c_ss, B, H, S_new, D, pos);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+// q_len = 1 (or a few) against a cache: same contract as ct_attn_fwd, warp-per-query-row kernel.
+extern "C" int ct_attn_decode(const ct_attn_args* args, void* stream) {
+  CT_REQUIRE(args != nullptr, CT_ERR_BAD_ARG, "ct_attn_decode: null args");
+  ct_attn_args a = *args;
+  a.impl = 2;
+  a.lse2 = nullptr;
+  return ct_attn_fwd(&a, stream);
 }

@@ -12,6 +12,8 @@ namespace ct {
 
 struct AdamConsts {
   float lr, beta1, beta2, eps, wd;
+  float omb1, omb2;     // 1 - beta, rounded from the double-precision difference (as Python/torch do)
+  float decay;          // 1 - lr*wd
   float bc1, bc2;       // 1 - beta^t
   float rsqrt_bc2;      // 1/sqrt(bc2)   (torch path)
   float step_size;      // lr / bc1       (torch path)
@@ -25,16 +27,16 @@ __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v,
   if (c.mode == 0) {
     // torch.optim.AdamW (decoupled): p *= 1 - lr*wd; m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g^2;
     // denom = sqrt(v)/sqrt(bc2) + eps; p -= (lr/bc1) * m / denom
-    p *= (1.f - c.lr * c.wd);
-    m = m + (g - m) * (1.f - c.beta1);
-    v = c.beta2 * v + (1.f - c.beta2) * g * g;
+    p *= c.decay;
+    m = m + (g - m) * c.omb1;
+    v = c.beta2 * v + c.omb2 * g * g;
     const float denom = sqrtf(v) * c.rsqrt_bc2 + c.eps;
     p -= c.step_size * (m / denom);
   } else {
     // optimizer.py:80-95 — coupled L2, bias-corrected moments, eps outside the sqrt
     if (c.wd != 0.f) g += c.wd * p;
-    m = c.beta1 * m + (1.f - c.beta1) * g;
-    v = c.beta2 * v + (1.f - c.beta2) * g * g;
+    m = c.beta1 * m + c.omb1 * g;
+    v = c.beta2 * v + c.omb2 * g * g;
     const float mh = m / c.bc1;
     const float vh = v / c.bc2;
     p -= c.lr * mh / (sqrtf(vh) + c.eps);
@@ -153,16 +155,20 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-static AdamConsts make_consts(float lr, float b1, float b2, float eps, float wd, int64_t step,
+// Hyper-parameters arrive as doubles (Python floats) and every derived constant is formed in double
+// before rounding to fp32 once, which is what `(1 - beta) * tensor` does in the reference / torch.
+static AdamConsts make_consts(double lr, double b1, double b2, double eps, double wd, int64_t step,
                               int mode, float grad_scale) {
   AdamConsts c;
-  c.lr = lr; c.beta1 = b1; c.beta2 = b2; c.eps = eps; c.wd = wd;
-  const double bc1 = 1.0 - std::pow((double)b1, (double)step);
-  const double bc2 = 1.0 - std::pow((double)b2, (double)step);
+  c.lr = (float)lr; c.beta1 = (float)b1; c.beta2 = (float)b2; c.eps = (float)eps; c.wd = (float)wd;
+  c.omb1 = (float)(1.0 - b1); c.omb2 = (float)(1.0 - b2);
+  c.decay = (float)(1.0 - lr * wd);
+  const double bc1 = 1.0 - std::pow(b1, (double)step);
+  const double bc2 = 1.0 - std::pow(b2, (double)step);
   c.bc1 = (float)bc1;
   c.bc2 = (float)bc2;
   c.rsqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
-  c.step_size = (float)((double)lr / bc1);
+  c.step_size = (float)(lr / bc1);
   c.grad_scale = grad_scale;
   c.mode = mode;
   return c;
@@ -173,8 +179,8 @@ static AdamConsts make_consts(float lr, float b1, float b2, float eps, float wd,
 using namespace ct;
 
 extern "C" int ct_adamw_step(float* p, float* g, float* m, float* v, void* p_shadow_bf16,
-                             int64_t n, float lr, float beta1, float beta2, float eps,
-                             float weight_decay, int64_t step, int mode, float grad_scale,
+                             int64_t n, double lr, double beta1, double beta2, double eps,
+                             double weight_decay, int64_t step, int mode, float grad_scale,
                              void* stream) {
   CT_REQUIRE(p && g && m && v, CT_ERR_BAD_ARG, "ct_adamw_step: null pointer");
   CT_REQUIRE(n >= 0 && step >= 1 && (mode == 0 || mode == 1), CT_ERR_BAD_ARG,
@@ -184,7 +190,7 @@ extern "C" int ct_adamw_step(float* p, float* g, float* m, float* v, void* p_sha
              CT_ERR_BAD_ARG, "ct_adamw_step: arena pointers must be 16-byte aligned");
   if (n == 0) return 0;
   AdamConsts c = make_consts(lr, beta1, beta2, eps, weight_decay, step, mode, grad_scale);
-  const int write_g = (mode == 1 && weight_decay != 0.f) ? 1 : 0;
+  const int write_g = (mode == 1 && weight_decay != 0.0) ? 1 : 0;
   int64_t blocks = ((n >> 2) + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
@@ -197,13 +203,13 @@ extern "C" int ct_adamw_step(float* p, float* g, float* m, float* v, void* p_sha
 
 extern "C" int ct_adamw_multi(int ntensors, float* const* p, float* const* g, float* const* m,
                               float* const* v, void* const* p_shadow_bf16, const int64_t* sizes,
-                              float lr, float beta1, float beta2, float eps, float weight_decay,
+                              double lr, double beta1, double beta2, double eps, double weight_decay,
                               int64_t step, int mode, float grad_scale, void* stream) {
   CT_REQUIRE(ntensors >= 0 && p && g && m && v && sizes, CT_ERR_BAD_ARG,
              "ct_adamw_multi: null pointer");
   CT_REQUIRE(step >= 1 && (mode == 0 || mode == 1), CT_ERR_BAD_ARG, "ct_adamw_multi: bad step/mode");
   AdamConsts c = make_consts(lr, beta1, beta2, eps, weight_decay, step, mode, grad_scale);
-  const int write_g = (mode == 1 && weight_decay != 0.f) ? 1 : 0;
+  const int write_g = (mode == 1 && weight_decay != 0.0) ? 1 : 0;
   int done = 0;
   while (done < ntensors) {
     MultiTable t;

@@ -384,6 +384,7 @@ class PreLNBlockFn(torch.autograd.Function):
         ctx.spec = spec
         ctx.shape = (B, S, H)
         ctx.mark_non_differentiable(k, v)
+        ctx.set_materialize_grads(False)  # no zero-filled [B,H,S,D] gradients for the k/v outputs
         return out.view(B, S, H), k, v
 
     @staticmethod

@@ -129,8 +129,12 @@ class BloomAttentionLayer(torch.nn.Module):
             _, k, v = F.split_packed(qkv.detach(), self.num_heads, F.LAYOUT_BLOOM)
         else:
             q, k, v = F.split_packed(qkv, self.num_heads, F.LAYOUT_BLOOM)
-            if k_v_past is not None:
-                k = torch.cat((k_v_past[0], k), dim=-2)  # cache layout [b,h,t,d], modeling_bloom.py:88-92
+            if not torch.is_grad_enabled():
+                # cache layout [b,h,t,d] (modeling_bloom.py:88-92), grown in place instead of concat
+                k = ops.kv_cache_append(None if k_v_past is None else k_v_past[0], k)
+                v = ops.kv_cache_append(None if k_v_past is None else k_v_past[1], v)
+            elif k_v_past is not None:
+                k = torch.cat((k_v_past[0], k), dim=-2)
                 v = torch.cat((k_v_past[1], v), dim=-2)
             ctx = F.attention_cached(q, k, v, self.inv_norm_factor, bias.causal, -ops.FLT_MAX,
                                      bias.kbias2, bias.first_valid)

@@ -129,7 +129,11 @@ class AttentionLayer(torch.nn.Module):
             _, k, v = F.split_packed(qkv.detach(), self.n_head, F.LAYOUT_GPT)
         else:
             q, k, v = F.split_packed(qkv, self.n_head, F.LAYOUT_GPT)
-            if k_v_past is not None:
+            if not torch.is_grad_enabled():
+                # [b,h,t,d] cache (modeling_gpt.py:76-80) grown in place instead of torch.concat
+                k = ops.kv_cache_append(None if k_v_past is None else k_v_past[0], k)
+                v = ops.kv_cache_append(None if k_v_past is None else k_v_past[1], v)
+            elif k_v_past is not None:
                 k = torch.cat((k_v_past[0], k), dim=-2)
                 v = torch.cat((k_v_past[1], v), dim=-2)
             ctx = F.attention_cached(q, k, v, sm_scale, True, -1e4, kb, fv)

@@ -25,7 +25,8 @@ _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
 # (bench.py's roofline pass). Counts are the number of kernels each C-ABI call enqueues.
 LAUNCHES = [0]
 GEMM_PROFILE = None  # when a list: (M, N, K, start_event, end_event) appended per ct_gemm call
-_KERNELS_PER_CALL = {"ct_layernorm_fwd": 1, "ct_layernorm_bwd": 1, "ct_adamw_step": 1, "ct_adamw_multi": 1,
+_KERNELS_PER_CALL = {"ct_kv_append": 1, "ct_attn_decode": 1,
+                     "ct_layernorm_fwd": 1, "ct_layernorm_bwd": 1, "ct_adamw_step": 1, "ct_adamw_multi": 1,
                      "ct_sgd_step": 1, "ct_cast": 1, "ct_colsum": 1, "ct_act_fwd": 1, "ct_act_bwd": 1,
                      "ct_gemm": 1, "ct_attn_fwd": 1, "ct_attn_bwd": 3, "ct_attn_mask_prep": 1,
                      "ct_embedding_fwd": 1, "ct_embedding_bwd": 1, "ct_cross_entropy_fwd": 3,
@@ -378,3 +379,34 @@ def cross_entropy_fwd(logits2d, labels, S=0, shift=False, ignore_index=-100, wan
 def scale_by_scalar(x, scalar_f32):
     _ck(_lib.load().ct_scale_by_scalar(ptr(x), dt(x), x.numel(), ptr(scalar_f32), stream()),
           "ct_scale_by_scalar")
+
+
+# ------------------------------------------------------------------------------------------------
+# KV cache for generation
+# ------------------------------------------------------------------------------------------------
+KV_CACHE_CHUNK = 256  # capacity grows in steps of this many positions
+
+
+def kv_cache_append(past, new):
+    """past: None or a [B,H,t,D] tensor previously returned by this function; new: [B,H,s,D] (any
+    strides). Returns a [B,H,t+s,D] VIEW of a preallocated buffer: the new rows are written in place
+    (ct_kv_append) instead of re-copying the whole cache like torch.concat does every step."""
+    _req_cuda(new)
+    B, H, s, D = new.shape
+    t = 0 if past is None else past.shape[2]
+    base = getattr(past, "_ct_cache_base", None) if past is not None else None
+    if base is None or base.shape[2] < t + s or base.dtype != new.dtype or past.data_ptr() != base.data_ptr():
+        cap = ((t + s + KV_CACHE_CHUNK - 1) // KV_CACHE_CHUNK + 1) * KV_CACHE_CHUNK
+        nbase = torch.empty((B, H, cap, D), dtype=new.dtype, device=new.device)
+        if t:
+            _ck(_lib.load().ct_kv_append(ptr(past), past.stride(0), past.stride(1), past.stride(2), ptr(nbase),
+                                         nbase.stride(0), nbase.stride(1), nbase.stride(2), B, H, t, D, 0, cap,
+                                         stream()), "ct_kv_append")
+        base = nbase
+    assert new.stride(3) == 1
+    _ck(_lib.load().ct_kv_append(ptr(new), new.stride(0), new.stride(1), new.stride(2), ptr(base), base.stride(0),
+                                 base.stride(1), base.stride(2), B, H, s, D, t, base.shape[2], stream()),
+        "ct_kv_append")
+    view = base[:, :, :t + s]
+    view._ct_cache_base = base
+    return view

@@ -68,15 +68,17 @@ int ct_layernorm_bwd(const void* dy, int dy_dtype, const void* dy2, int dy2_dtyp
  *          (examples/ft_bloom.py:19,70,90);
  * mode 1 = the reference's own class, optimizer.py:71-97: coupled L2 (g += wd*p written back to g),
  *          m_hat/(sqrt(v_hat)+eps), `step` is the reference's counter which starts at 1.
+ * Hyper-parameters are doubles (Python floats); derived constants (1-beta, 1-beta^t, lr/(1-beta1^t))
+ * are formed in double and rounded to fp32 once, like the reference's Python-scalar arithmetic.
  * grad_scale multiplies g on load (1/world for a summed all-reduce; 1.0 otherwise).
  * p_shadow (nullable): bf16 copy of the updated parameters for the next forward's GEMMs. */
-int ct_adamw_step(float* p, float* g, float* m, float* v, void* p_shadow_bf16, int64_t n, float lr,
-                  float beta1, float beta2, float eps, float weight_decay, int64_t step, int mode,
+int ct_adamw_step(float* p, float* g, float* m, float* v, void* p_shadow_bf16, int64_t n, double lr,
+                  double beta1, double beta2, double eps, double weight_decay, int64_t step, int mode,
                   float grad_scale, void* stream);
 /* Same arithmetic over `ntensors` separate tensors (host arrays of device pointers). */
 int ct_adamw_multi(int ntensors, float* const* p, float* const* g, float* const* m, float* const* v,
-                   void* const* p_shadow_bf16, const int64_t* sizes, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, int64_t step, int mode,
+                   void* const* p_shadow_bf16, const int64_t* sizes, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, int64_t step, int mode,
                    float grad_scale, void* stream);
 /* optimizer.py:28-50 (SGD.step): g += wd*p; buf = first ? g : momentum*buf + (1-dampening)*g;
  * g = buf; p -= lr*g. `buf` may be NULL when momentum == 0. g is rewritten like the reference. */
@@ -258,6 +260,18 @@ int ct_allreduce_bucket(int64_t offset, int64_t count, float scale, int mode, in
                         void* stream);
 int ct_broadcast(int64_t offset, int64_t count, int root, void* stream);
 int ct_comm_finalize(void);
+
+
+/* ---- decode with a preallocated KV cache (generation_util.py:57-119 calls the models with
+ * k_v_pasts; modeling_bloom.py:88-92 / modeling_gpt.py:76-80 grow the cache with torch.concat) --- *
+ * ct_kv_append: cache[b,h,pos+s,:] = src[b,h,s,:] for s < S_new (16-bit elements; strides in
+ * elements as in ct_attn_args); fails if pos + S_new > t_max.
+ * ct_attn_decode: ct_attn_fwd's contract specialised for q_len = 1 (or a few) rows against the
+ * cache: warp-per-query-row kernel, any head_dim <= 128, no lse2. */
+int ct_kv_append(const void* src, int64_t s_sb, int64_t s_sh, int64_t s_ss, void* cache, int64_t c_sb,
+                 int64_t c_sh, int64_t c_ss, int B, int H, int S_new, int D, int pos, int t_max,
+                 void* stream);
+int ct_attn_decode(const ct_attn_args* args, void* stream);
 
 #ifdef __cplusplus
 }
