@@ -23,7 +23,10 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + (["-DCT_DEBUG_TIMING"] if os.environ.get("CT_DEBUG_TIMING") else [])
+if os.environ.get("CT_DEBUG_TIMING"):
+    LIB = os.path.join(HERE, "libct_b200_dbg.so")
+    BUILD = os.path.join(HERE, "_build_dbg")
 
 
 def sources():

@@ -28,6 +28,17 @@ namespace ct {
 
 constexpr float LOG2E = 1.4426950408889634f;
 
+#ifdef CT_DEBUG_TIMING
+__device__ long long ct_dbg_clk[4096];
+#define CT_DBG_STAMP(slot) do { if (blockIdx.x == CT_DBG_BLOCK && threadIdx.x == CT_DBG_THREAD && (slot) < 4096) ct_dbg_clk[(slot)] = clock64(); } while (0)
+#else
+#define CT_DBG_STAMP(slot) do {} while (0)
+#endif
+#ifndef CT_DBG_BLOCK
+#define CT_DBG_BLOCK 700
+#define CT_DBG_THREAD 64
+#endif
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -188,7 +199,9 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
     for (int j = 0; j < n_kv; ++j) {
       const int kv0 = j * 128;
       const uint32_t t_s = t_lane + (j & 1) * 128;
+      CT_DBG_STAMP(2048 + 16 * j + 0);
       mbar_wait(s_full + 8 * (j & 1), (j >> 1) & 1);
+      CT_DBG_STAMP(2048 + 16 * j + 1);
       tc_fence_after();
       // a tile needs per-element masking if it touches the causal diagonal or the ragged key edge
       const bool slow = (p.causal && (kv0 + 127 > q0 + p.off)) || (kv0 + 128 > p.Sk);
@@ -233,6 +246,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
         }
       };
       if (slow) pass1(std::true_type{}); else pass1(std::false_type{});
+      CT_DBG_STAMP(2048 + 16 * j + 2);
       mt = fmaxf(mt, -FLT_MAX);  // clamp once: max(clamp(x)) == clamp(max(x))
       const float m_new = fmaxf(m, mt);
       const float alpha = ex2(m - m_new);
@@ -282,6 +296,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
         }
       };
       if (slow) pass2(std::true_type{}); else pass2(std::false_type{});
+      CT_DBG_STAMP(2048 + 16 * j + 3);
       l = l * alpha + lt;
       m = m_new;
       fence_proxy_async_smem();
@@ -289,6 +304,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
       mbar_arrive(p_ready);
       // ---- O = O * alpha + P V ----
       mbar_wait(o_full, j & 1);
+      CT_DBG_STAMP(2048 + 16 * j + 4);
       tc_fence_after();
       {
         uint32_t r2[32];
@@ -344,6 +360,7 @@ struct AttnBwdP {
   void* dk; int64_t dk_sb, dk_sh, dk_ss;
   void* dv; int64_t dv_sb, dv_sh, dv_ss;
 };
+constexpr int FB_THREADS = 320;  // TMA warp + MMA warp + 8 compute warps (2 per TMEM lane quarter)
 constexpr int FB_SMEM = 2 * FA_TILE /*K,V*/ + 4 * FA_TILE /*2 x (Q,dO)*/ + 2 * FA_TILE /*P^T*/ +
                         2 * FA_TILE /*dS^T*/ + 128 /*barriers*/ + 1024 /*lse2, delta of the query tile*/;
 
@@ -365,7 +382,7 @@ __device__ __forceinline__ void st_row64(void* basep, int64_t elem_off, const fl
   }
 }
 
-__global__ void __launch_bounds__(FA_THREADS, 1)
+__global__ void __launch_bounds__(FB_THREADS, 1)
     attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                        const AttnBwdP bp) {
@@ -401,7 +418,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(qdo_full + 8 * s, 1); mbar_init(qdo_empty + 8 * s, 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_ready, 128);
+    mbar_init(pds_ready, 256);
     mbar_init(dq_full, 1);
     mbar_init(dkv_full, 1);
     mbar_fence_init();
@@ -472,7 +489,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       umma_commit(dkv_full);
     }
   } else {
+    // 8 compute warps: a single warp per scheduler cannot hide its own ALU/MUFU dependency latency
+    // (measured: ~20% issue utilisation with 4 warps), so every TMEM lane quarter is served by two
+    // warps that split the 128 query columns (the backward math is purely elementwise per (key,query)).
     const int rr = (warp & 3) * 32 + lane;  // key row inside the tile (S^T) / query row (dQ)
+    const int hf = (warp - 2) >> 2;         // which half of the columns this warp owns
     const int jg = kv0 + rr;
     const uint32_t t_lane = (uint32_t)((warp & 3) * 32) << 16;
     const float kb = (p.kbias2 && jg < p.Sk)
@@ -483,36 +504,39 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     const int sw = rr & 7;
     // per-query statistics of the current query tile, staged through smem (prefetched one tile ahead)
     float lse_next = INFINITY, del_next = 0.f;
-    if (n_it > 0 && i_start * 128 + rr < p.Sq) {
+    if (hf == 0 && n_it > 0 && i_start * 128 + rr < p.Sq) {
       lse_next = __ldg(lse_bh + i_start * 128 + rr);
       del_next = __ldg(del_bh + i_start * 128 + rr);
     }
     for (int it = 0; it < n_it; ++it) {
       const int q0 = (i_start + it) * 128;
+      CT_DBG_STAMP(16 * it + 0);
       mbar_wait(sdp_full, it & 1);
+      CT_DBG_STAMP(16 * it + 1);
       tc_fence_after();
-      // all 128 threads are past dq_full(it-1): nobody still reads the previous tile's statistics
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(lse_s + 4 * rr), "f"(lse_next) : "memory");
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(del_s + 4 * rr), "f"(del_next) : "memory");
-      bar_sync_named(1, 128);
-      {
+      // all 256 threads are past dq_full(it-1): nobody still reads the previous tile's statistics
+      if (hf == 0) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(lse_s + 4 * rr), "f"(lse_next) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(del_s + 4 * rr), "f"(del_next) : "memory");
+      }
+      bar_sync_named(1, 256);
+      if (hf == 0) {
         const int nq = q0 + 128 + rr;
         const bool ok = (it + 1 < n_it) && nq < p.Sq;
         lse_next = ok ? __ldg(lse_bh + nq) : INFINITY;
         del_next = ok ? __ldg(del_bh + nq) : 0.f;
       }
-      // rolled loop over the four 32-column chunks (code size: see the forward kernel); the TMEM
-      // loads of the next chunk are issued before the math of the current one
       uint32_t rs[32], rd[32];
-      tmem_ld_32x32(T_ST + t_lane, rs);
-      tmem_ld_32x32(T_DPT + t_lane, rd);
+      tmem_ld_32x32(T_ST + t_lane + hf * 64, rs);
+      tmem_ld_32x32(T_DPT + t_lane + hf * 64, rd);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = hf * 2 + cc;  // 32-column chunk index inside the 128-query tile
         float cs[32], cdp[32];
         tmem_ld_wait();
 #pragma unroll
         for (int t = 0; t < 32; ++t) { cs[t] = __uint_as_float(rs[t]); cdp[t] = __uint_as_float(rd[t]); }
-        if (c < 3) {
+        if (cc == 0) {
           tmem_ld_32x32(T_ST + t_lane + (c + 1) * 32, rs);
           tmem_ld_32x32(T_DPT + t_lane + (c + 1) * 32, rd);
         }
@@ -568,20 +592,22 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
                        "r"(b2), "r"(b3) : "memory");
         }
       }
+      CT_DBG_STAMP(16 * it + 2);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_ready);
-      // ---- dQ tile: this thread now owns query row (q0 + rr) ----
+      // ---- dQ tile: this thread owns query row (q0 + rr), columns [32*hf, 32*hf + 32) of d ----
+      CT_DBG_STAMP(16 * it + 3);
       mbar_wait(dq_full, it & 1);
+      CT_DBG_STAMP(16 * it + 4);
       tc_fence_after();
       const int qi = q0 + rr;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t r[32];
-        tmem_ld_32x32(T_DQ + t_lane + c * 32, r);
+        tmem_ld_32x32(T_DQ + t_lane + hf * 32, r);
         tmem_ld_wait();
         if (qi < p.Sq) {
-          float* dst = bp.dq_accum + (((int64_t)b * p.Sq + qi) * p.H + h) * 64 + c * 32;
+          float* dst = bp.dq_accum + (((int64_t)b * p.Sq + qi) * p.H + h) * 64 + hf * 32;
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g),
@@ -590,34 +616,48 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
                          : "memory");
         }
       }
+      CT_DBG_STAMP(16 * it + 5);
       tc_fence_before();
     }
-    // ---- dK / dV for this key row ----
-    float acc[64];
+    // ---- dK / dV for this key row: 32 of the 64 head-dim columns per thread ----
     if (n_it > 0) {
       mbar_wait(dkv_full, 0);
       tc_fence_after();
     }
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
+      uint32_t r[32];
       if (n_it > 0) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32((which == 0 ? T_DV : T_DK) + t_lane + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int t = 0; t < 32; ++t) acc[c * 32 + t] = __uint_as_float(r[t]);
-        }
+        tmem_ld_32x32((which == 0 ? T_DV : T_DK) + t_lane + hf * 32, r);
+        tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int t = 0; t < 64; ++t) acc[t] = 0.f;
+        for (int t = 0; t < 32; ++t) r[t] = 0u;
       }
       if (!key_oob) {
-        if (which == 0)
-          st_row64(bp.dv, (int64_t)b * bp.dv_sb + (int64_t)h * bp.dv_sh + (int64_t)jg * bp.dv_ss, acc, p.fmt);
-        else
-          st_row64(bp.dk, (int64_t)b * bp.dk_sb + (int64_t)h * bp.dk_sh + (int64_t)jg * bp.dk_ss, acc, p.fmt);
+        void* basep = which == 0 ? bp.dv : bp.dk;
+        const int64_t eo = which == 0
+            ? (int64_t)b * bp.dv_sb + (int64_t)h * bp.dv_sh + (int64_t)jg * bp.dv_ss
+            : (int64_t)b * bp.dk_sb + (int64_t)h * bp.dk_sh + (int64_t)jg * bp.dk_ss;
+        uint8_t* row = reinterpret_cast<uint8_t*>(basep) + 2 * (eo + hf * 32);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          const float f0 = __uint_as_float(r[8 * g]), f1 = __uint_as_float(r[8 * g + 1]),
+                      f2 = __uint_as_float(r[8 * g + 2]), f3 = __uint_as_float(r[8 * g + 3]),
+                      f4 = __uint_as_float(r[8 * g + 4]), f5 = __uint_as_float(r[8 * g + 5]),
+                      f6 = __uint_as_float(r[8 * g + 6]), f7 = __uint_as_float(r[8 * g + 7]);
+          if (p.fmt == 1) {
+            w.x = pack_bf16x2(f0, f1); w.y = pack_bf16x2(f2, f3); w.z = pack_bf16x2(f4, f5); w.w = pack_bf16x2(f6, f7);
+          } else {
+            __half2 x;
+            x = __floats2half2_rn(f0, f1); w.x = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f2, f3); w.y = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f4, f5); w.z = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f6, f7); w.w = *reinterpret_cast<uint32_t*>(&x);
+          }
+          *reinterpret_cast<uint4*>(row + 16 * g) = w;
+        }
       }
     }
   }
@@ -1121,7 +1161,7 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
       attr = true;
     }
     const int64_t grid = (int64_t)a.B * a.H * ((a.Sk + 127) / 128);
-    attn_bwd_tc_kernel<<<(unsigned)grid, FA_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
+    attn_bwd_tc_kernel<<<(unsigned)grid, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
     CT_LAUNCH_OK();
     const int64_t n = (int64_t)a.B * a.Sq * a.H * 64 / 8;
     int64_t blocks = (n + 255) / 256;
@@ -1189,3 +1229,10 @@ extern "C" int ct_attn_decode(const ct_attn_args* args, void* stream) {
   a.lse2 = nullptr;
   return ct_attn_fwd(&a, stream);
 }
+
+#ifdef CT_DEBUG_TIMING
+extern "C" int ct_debug_timing(long long* out, int n) {
+  if (n > 4096) n = 4096;
+  return (int)cudaMemcpyFromSymbol(out, ct::ct_dbg_clk, sizeof(long long) * n);
+}
+#endif

@@ -25,6 +25,13 @@
 
 namespace ct {
 
+#ifdef CT_DEBUG_TIMING
+__device__ long long ct_dbg_gemm[4096];
+#define CT_GDBG(thread, slot) do { if (blockIdx.x == 5 && threadIdx.x == (thread) && (slot) < 4096) ct_dbg_gemm[(slot)] = clock64(); } while (0)
+#else
+#define CT_GDBG(thread, slot) do {} while (0)
+#endif
+
 struct EpiParams {
   int M, N;
   void* C; int c_dtype; int64_t ldc;
@@ -166,16 +173,20 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& e, int m, int n0, f
 // through a private smem buffer (row stride 144 B: conflict-free 16-byte row writes) and writes it
 // out with lanes running along the row: 64 B (16-bit) or 128 B (fp32) contiguous per row, 8 or 4
 // rows per instruction.
-constexpr int EPI_STAGE_ROW = 144;
+constexpr int EPI_STAGE_ROW = 128;
 constexpr int EPI_STAGE_BYTES = 32 * EPI_STAGE_ROW;  // per epilogue warp
+constexpr int EPI_WARPS = 8;
 
+// chunk i (16 bytes) of row r lives at position i ^ (r & 7) of the row's 128-byte slot: both the
+// row-per-thread writes and the lanes-along-the-row reads are bank-conflict free without padding
 __device__ __forceinline__ void stage_store32(uint32_t stage, int lane, const float (&v)[32], int dt,
                                               void* gbase, int64_t ld, int m_base, int M, int n0) {
   const uint32_t my = stage + lane * EPI_STAGE_ROW;
+  const int sw = lane & 7;
   if (dt == DT_F32) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my + 16 * i), "f"(v[4 * i]),
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my + 16 * (i ^ sw)), "f"(v[4 * i]),
                    "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
   } else {
 #pragma unroll
@@ -191,7 +202,7 @@ __device__ __forceinline__ void stage_store32(uint32_t stage, int lane, const fl
         h = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]); w2 = *reinterpret_cast<uint32_t*>(&h);
         h = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]); w3 = *reinterpret_cast<uint32_t*>(&h);
       }
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my + 16 * i), "r"(w0), "r"(w1),
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my + 16 * (i ^ sw)), "r"(w0), "r"(w1),
                    "r"(w2), "r"(w3) : "memory");
     }
   }
@@ -203,7 +214,7 @@ __device__ __forceinline__ void stage_store32(uint32_t stage, int lane, const fl
       const int r = (lane >> 3) + 4 * k;
       uint4 w;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
-                   : "r"(stage + r * EPI_STAGE_ROW + piece * 16));
+                   : "r"(stage + r * EPI_STAGE_ROW + 16 * (piece ^ (r & 7))));
       const int m = m_base + r;
       if (m < M) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(gbase) + (int64_t)m * ld + n0 + piece * 4) = w;
     }
@@ -214,7 +225,7 @@ __device__ __forceinline__ void stage_store32(uint32_t stage, int lane, const fl
       const int r = (lane >> 2) + 8 * k;
       uint4 w;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
-                   : "r"(stage + r * EPI_STAGE_ROW + piece * 16));
+                   : "r"(stage + r * EPI_STAGE_ROW + 16 * (piece ^ (r & 7))));
       const int m = m_base + r;
       if (m < M)
         *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(gbase) + (int64_t)m * ld + n0 + piece * 8) = w;
@@ -223,9 +234,30 @@ __device__ __forceinline__ void stage_store32(uint32_t stage, int lane, const fl
   __syncwarp();
 }
 
+// The epilogue is latency-bound: besides running 8 warps (two per TMEM lane quarter, alternating
+// 32-column chunks) every global operand it consumes is fetched one of its chunks AHEAD. aux_kind names the single per-element operand that is prefetched:
+//   1 = residual, 2 = activation-gradient source (saved pre-activation), 3 = old C (beta accumulate).
+enum : int { AUX_NONE = 0, AUX_RES = 1, AUX_ACTGRAD = 2, AUX_C = 3 };
+
+__device__ __forceinline__ int epi_aux_kind(const EpiParams& e) {
+  if (!e.vec_ok || e.atomic_out) return AUX_NONE;
+  if (e.residual) return AUX_RES;
+  if (e.actgrad_src) return AUX_ACTGRAD;
+  if (e.beta != 0.f) return AUX_C;
+  return AUX_NONE;
+}
+__device__ __forceinline__ void epi_aux_load(const EpiParams& e, int kind, int m, int n0, float (&a)[32]) {
+  if (kind == AUX_NONE || m >= e.M || n0 + 32 > e.N) return;
+  if (kind == AUX_RES) ld32(e.residual, e.res_dtype, (int64_t)m * e.ldr + n0, a);
+  else if (kind == AUX_ACTGRAD) ld32(e.actgrad_src, e.actgrad_dtype, (int64_t)m * e.ldg + n0, a);
+  else ld32(e.C, e.c_dtype, (int64_t)m * e.ldc + n0, a);
+}
+
 // Warp-collective epilogue for a 32-row x 32-column block: lane l owns row m_base + l.
-__device__ __forceinline__ void epi_block32(const EpiParams& e, int m_base, int lane, int n0, float (&t)[32],
-                                            bool add_bias, uint32_t stage) {
+// bias_s: shared-memory address of this tile's bias slice (floats, indexed from the tile's n origin).
+__device__ __forceinline__ void epi_block32(const EpiParams& e, int m_base, int lane, int n0, int n_in_tile,
+                                            float (&t)[32], const float (&aux)[32], int aux_kind, bool add_bias,
+                                            uint32_t stage, uint32_t bias_s) {
   if (n0 >= e.N) return;  // warp-uniform
   const int m = m_base + lane;
   const bool full = (n0 + 32 <= e.N) && e.vec_ok;  // warp-uniform
@@ -237,31 +269,46 @@ __device__ __forceinline__ void epi_block32(const EpiParams& e, int m_base, int 
 #pragma unroll
   for (int j = 0; j < 32; ++j) t[j] *= e.alpha;
   if (e.bias && add_bias) {
-    const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float4 b = __ldg(b4 + i);
+      float4 b;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                   : "r"(bias_s + 4 * (n_in_tile + 4 * i)));
       t[4 * i] += b.x; t[4 * i + 1] += b.y; t[4 * i + 2] += b.z; t[4 * i + 3] += b.w;
     }
   }
   if (e.preact) stage_store32(stage, lane, t, e.preact_dtype, e.preact, e.ldp, m_base, e.M, n0);
   if (e.act != ACT_NONE) act32(t, e.act);
   if (e.actgrad_src && row_ok) {
-    float s[32];
-    ld32(e.actgrad_src, e.actgrad_dtype, (int64_t)m * e.ldg + n0, s);
-    actgrad32(t, s, e.actgrad_act);
+    if (aux_kind == AUX_ACTGRAD) {
+      actgrad32(t, aux, e.actgrad_act);
+    } else {
+      float s[32];
+      ld32(e.actgrad_src, e.actgrad_dtype, (int64_t)m * e.ldg + n0, s);
+      actgrad32(t, s, e.actgrad_act);
+    }
   }
   if (e.residual && row_ok) {
-    float s[32];
-    ld32(e.residual, e.res_dtype, (int64_t)m * e.ldr + n0, s);
+    if (aux_kind == AUX_RES) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) t[j] += s[j];
+      for (int j = 0; j < 32; ++j) t[j] += aux[j];
+    } else {
+      float s[32];
+      ld32(e.residual, e.res_dtype, (int64_t)m * e.ldr + n0, s);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] += s[j];
+    }
   }
   if (e.beta != 0.f && row_ok) {
-    float s[32];
-    ld32(e.C, e.c_dtype, (int64_t)m * e.ldc + n0, s);
+    if (aux_kind == AUX_C) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) t[j] = fmaf(e.beta, s[j], t[j]);
+      for (int j = 0; j < 32; ++j) t[j] = fmaf(e.beta, aux[j], t[j]);
+    } else {
+      float s[32];
+      ld32(e.C, e.c_dtype, (int64_t)m * e.ldc + n0, s);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] = fmaf(e.beta, s[j], t[j]);
+    }
   }
   stage_store32(stage, lane, t, e.c_dtype, e.C, e.ldc, m_base, e.M, n0);
 }
@@ -271,7 +318,7 @@ __device__ __forceinline__ void epi_block32(const EpiParams& e, int m_base, int 
 // =================================================================================================
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 64 + 32 * 8;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
 template <int BN>
@@ -280,8 +327,9 @@ struct GemmCfg {  // (EPI_STAGE_BYTES is defined above)
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
-                                    4 * EPI_STAGE_BYTES /*epilogue transposition buffers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ +
+                                    EPI_WARPS * EPI_STAGE_BYTES /*epilogue transposition buffers*/ +
+                                    2 * 256 * 4 /*double-buffered bias slice of the tile*/;
 };
 
 struct TcParams {
@@ -298,9 +346,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         const TcParams p, const EpiParams e) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment (the budget has no slack for rounding up)
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0u) __trap();
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
   const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
@@ -310,6 +359,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const uint32_t tempty_bar = tfull_bar + 16;             // 2 x 8 B
   const uint32_t tmem_slot = tempty_bar + 16;             // 4 B
   const uint32_t epi_stage = bar_base + 256;               // 4 x EPI_STAGE_BYTES
+  const uint32_t bias_smem = epi_stage + EPI_WARPS * EPI_STAGE_BYTES;  // 2 x 256 floats
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -331,7 +381,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
-      mbar_init(tempty_bar + 8 * a, 128);
+      mbar_init(tempty_bar + 8 * a, 32 * EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -412,7 +462,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const int kb1 = min(kb0 + kb_per_split, k_blocks_total);
         const uint32_t acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
+        CT_GDBG(32, 2048 + 8 * local + 0);
         mbar_wait(tempty_bar + 8 * acc, acc_ph ^ 1);
+        CT_GDBG(32, 2048 + 8 * local + 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -431,6 +483,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           umma_commit(empty_bar + 8 * s);  // smem stage reusable once these MMAs retire
         }
         umma_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
+        CT_GDBG(32, 2048 + 8 * local + 2);
       }
     }
   } else {
@@ -444,25 +497,43 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const int kb1 = min(kb0 + kb_per_split, k_blocks_total);
       const uint32_t acc = local & 1;
       const uint32_t acc_ph = (local >> 1) & 1;
+      CT_GDBG(64, 8 * local + 0);
       mbar_wait(tfull_bar + 8 * acc, acc_ph);
+      CT_GDBG(64, 8 * local + 1);
       tc_fence_after();
       const int m_base = m_blk * BM + q * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      const uint32_t stage = epi_stage + (uint32_t)q * EPI_STAGE_BYTES;
+      const int ew = warp - 2;                 // 0..7
+      const int hf = ew >> 2;                  // even / odd 32-column chunks
+      const uint32_t stage = epi_stage + (uint32_t)ew * EPI_STAGE_BYTES;
+      const uint32_t bias_s = bias_smem + (local & 1) * (256 * 4);
+      const int et = ew * 32 + lane;           // 0..255 among the epilogue threads
+      if (e.bias) {
+        // stage this tile's bias slice (double-buffered by tile parity: the single barrier below also
+        // orders the previous-but-one tile's reads before this write)
+        if (et < BN) {
+          const int n = n_blk * BN + et;
+          const float bv = n < e.N ? __ldg(e.bias + n) : 0.f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4 * et), "f"(bv) : "memory");
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       if (kb1 > kb0) {
-        // TMEM load of chunk c+1 is in flight while chunk c goes through the (single) epilogue body
+        // the TMEM load of this warp's next chunk is in flight while the current one is processed
+        const float aux[32] = {};
         uint32_t r[32];
-        tmem_ld_32x32(t_row, r);
+        tmem_ld_32x32(t_row + hf * 32, r);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = hf; c < BN / 32; c += 2) {
           float t[32];
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(r[j]);
-          if (c + 1 < BN / 32) tmem_ld_32x32(t_row + (c + 1) * 32, r);
-          epi_block32(e, m_base, lane, n_blk * BN + c * 32, t, split == 0, stage);
+          if (c + 2 < BN / 32) tmem_ld_32x32(t_row + (c + 2) * 32, r);
+          epi_block32(e, m_base, lane, n_blk * BN + c * 32, c * 32, t, aux, AUX_NONE, split == 0, stage, bias_s);
         }
       }
+      CT_GDBG(64, 8 * local + 2);
       tc_fence_before();
       mbar_arrive(tempty_bar + 8 * acc);
     }
@@ -719,3 +790,10 @@ extern "C" int ct_gemm_wgrad_bias(const void* dy, const void* x, int w_in_out, f
   if (db) return ct_colsum(dy, ab_dtype, N, db, accumulate, M, N, stream);
   return 0;
 }
+
+#ifdef CT_DEBUG_TIMING
+extern "C" int ct_debug_timing_gemm(long long* out, int n) {
+  if (n > 4096) n = 4096;
+  return (int)cudaMemcpyFromSymbol(out, ct::ct_dbg_gemm, sizeof(long long) * n);
+}
+#endif
