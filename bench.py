@@ -36,7 +36,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"],
+                    help="ours = this repo; reference = the reference's CPU path (oracle port) on host cores; "
+                         "eager = the reference's eager-PyTorch path (oracle under bf16 autocast + torch AdamW/DDP) on the GPUs")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--layers", type=int, default=24)
@@ -168,6 +170,92 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------
+# extra arm: the reference's own eager path on the same GPUs (what examples/ft_bloom*.py run)
+# ------------------------------------------------------------------------------------------------
+def run_eager_arm(args):
+    """oracle/ct_oracle.py is an op-for-op restatement of the reference modules in plain PyTorch, so
+    running it on the GPU under torch.autocast(bfloat16) with torch.optim.AdamW (and torch DDP for
+    N > 1) is the reference's eager path; /root/reference itself does not exist on the GPU box."""
+    import torch.distributed as dist
+    from oracle import ct_oracle as O
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    H, V, nh, L = BLOOM_560M["hidden_size"], BLOOM_560M["vocab_size"], 16, args.layers
+    torch.manual_seed(999)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            def mat(*shape): return torch.nn.Parameter(torch.randn(*shape, device=dev) * 0.02)
+            def vec(n, one=False): return torch.nn.Parameter(torch.ones(n, device=dev) if one else torch.zeros(n, device=dev))
+            sd = {"bloom.word_embeddings.weight": mat(V, H)}
+            for nme in ("bloom.word_embeddings_layernorm", "bloom.ln_f"):
+                sd[nme + ".weight"], sd[nme + ".bias"] = vec(H, True), vec(H)
+            for i in range(L):
+                p = "bloom.blocks.%d." % i
+                sd[p + "input_layernorm.weight"], sd[p + "input_layernorm.bias"] = vec(H, True), vec(H)
+                sd[p + "post_attention_layernorm.weight"], sd[p + "post_attention_layernorm.bias"] = vec(H, True), vec(H)
+                sd[p + "self_attention.query_key_value.weight"], sd[p + "self_attention.query_key_value.bias"] = mat(3 * H, H), vec(3 * H)
+                sd[p + "self_attention.dense.weight"], sd[p + "self_attention.dense.bias"] = mat(H, H), vec(H)
+                sd[p + "mlp.dense_h_to_4h.weight"], sd[p + "mlp.dense_h_to_4h.bias"] = mat(4 * H, H), vec(4 * H)
+                sd[p + "mlp.dense_4h_to_h.weight"], sd[p + "mlp.dense_4h_to_h.bias"] = mat(H, 4 * H), vec(H)
+            self.keys = list(sd.keys())
+            self.ps = torch.nn.ParameterList(list(sd.values()))
+
+        def forward(self, ids, mask, labels):
+            sd = dict(zip(self.keys, self.ps))
+            (loss, _, _), _ = O.bloom_causal_lm(ids, mask, sd, L, nh, 1e-5, labels=labels, training=True)
+            return loss
+
+    net = Net()
+    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local]) if world > 1 else net
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
+    B, S = args.batch, args.seq
+    g = torch.Generator().manual_seed(999 + rank)
+    ids = torch.randint(3, V, (B, S), generator=g).to(dev)
+    mask = torch.ones(B, S, dtype=torch.long, device=dev)
+
+    def step():
+        opt.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = model(ids, mask, ids)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t)
+    if rank == 0:
+        print(json.dumps({"impl": "eager", "metric": "Bloom-560M SFT tokens/sec", "value": B * S * world * args.steps / (ms * 1e-3),
+                          "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "dtype": "bf16 autocast",
+                          "data": "synthetic", "loss": float(loss),
+                          "config": {"workload": "Bloom-560M SFT step: reference eager-PyTorch path (oracle restatement), "
+                                                 "torch.optim.AdamW" + (", torch DDP/NCCL" if world > 1 else ""),
+                                     "global_batch": B * world, "seq_len": S, "layers": L}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -175,6 +263,9 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.impl == "eager":
+        run_eager_arm(args)
         return
     import torch.distributed as dist
     from cleantransformer_b200 import ops

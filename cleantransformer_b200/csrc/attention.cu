@@ -470,6 +470,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
         mbar_wait(pds_ready, it & 1);
         tc_fence_after();
+        // dQ first: the compute warps turn it into red.global.add traffic (slow) while dV / dK and
+        // the next tile's S^T / dP^T run on the tensor pipe
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ[q, d] = dS[q, kv] . K[kv, d]  (A MN-major view of dS^T)
+          umma_f16(T_DQ, umma_smem_desc_sw128(sDS + k * 2048, FA_TILE, 1024),
+                   umma_smem_desc_sw128(sK + k * 2048, 64 * 128, 1024), idesc_mm, k > 0);
+        umma_commit(dq_full);
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // dV[kv, d] += P^T[kv, q] . dO[q, d]   (B MN-major: rows = q)
           umma_f16(T_DV, umma_smem_desc_sw128(sPT + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
@@ -478,12 +485,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         for (int k = 0; k < 8; ++k)  // dK[kv, d] += dS^T[kv, q] . Q[q, d]
           umma_f16(T_DK, umma_smem_desc_sw128(sDS + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
                    umma_smem_desc_sw128(q + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // dQ[q, d] = dS[q, kv] . K[kv, d]  (A MN-major view of dS^T)
-          umma_f16(T_DQ, umma_smem_desc_sw128(sDS + k * 2048, FA_TILE, 1024),
-                   umma_smem_desc_sw128(sK + k * 2048, 64 * 128, 1024), idesc_mm, k > 0);
         umma_commit(qdo_empty + 8 * s);
-        umma_commit(dq_full);
         if (it + 1 < n_it) issue_sdp(it + 1);
       }
       umma_commit(dkv_full);

@@ -21,6 +21,7 @@
 // problems (e.g. the 28-way BERT classifier) and as an in-library cross-check (impl = 2).
 #include "ct_common.cuh"
 #include "../../include/ct_b200.h"
+#include <cstdlib>
 #include <cstring>
 
 namespace ct {
@@ -547,6 +548,216 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   }
 }
 
+
+// =================================================================================================
+// 2-CTA variant: a cluster of two CTAs computes a 256 x 256 tile with tcgen05.mma.cta_group::2.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 columns): 32 KB per
+// K block per SM instead of 48 KB, i.e. one third less L2->SM traffic, which is what bounds the
+// 1-CTA main loop (measured 645 cycles per K block against the 512-cycle tensor-pipe floor).
+// CTA 0 (leader) issues the MMAs; TMA completions of both CTAs are credited to the leader's full
+// barrier; tcgen05.commit multicasts to the barriers of both CTAs; both CTAs run the epilogue on
+// their own 128 accumulator rows and release the accumulator on the leader's barrier.
+// =================================================================================================
+constexpr int BN2 = 256;
+constexpr int STAGES2 = 6;
+constexpr int STAGE2_BYTES = A_STAGE_BYTES + (BN2 / 2) * BK * 2;  // 32 KB per CTA
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 256 + EPI_WARPS * EPI_STAGE_BYTES + 2 * 256 * 4;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                             const TcParams p, const EpiParams e) {
+  constexpr int BN = BN2;
+  constexpr int STAGES = STAGES2;
+  constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0u) __trap();
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t bar_base = smem_base + STAGES * STAGE2_BYTES;
+  const uint32_t full_bar = bar_base;
+  const uint32_t empty_bar = bar_base + 8 * STAGES;
+  const uint32_t tfull_bar = bar_base + 16 * STAGES;
+  const uint32_t tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_slot = tempty_bar + 16;
+  const uint32_t epi_stage = bar_base + 256;
+  const uint32_t bias_smem = epi_stage + EPI_WARPS * EPI_STAGE_BYTES;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  const int m_tiles = (p.M + 255) / 256;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int k_blocks_total = (p.K + BK - 1) / BK;
+  const int kb_per_split = (k_blocks_total + p.split_k - 1) / p.split_k;
+  const int num_work = m_tiles * n_tiles * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, 2 * EPI_WARPS);  // one elected arrive per epilogue warp of both CTAs
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits + TMEM allocation visible to the peer before any remote access
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto decode = [&](int w, int& m_blk, int& n_blk, int& split) {
+    split = w % p.split_k;
+    int t = w / p.split_k;
+    const int gmx = max(1, p.group_m / 2);
+    const int per_group = gmx * n_tiles;
+    const int grp = t / per_group;
+    const int in_grp = t - grp * per_group;
+    const int m_first = grp * gmx;
+    const int gm = min(gmx, m_tiles - m_first);
+    m_blk = m_first + in_grp % gm;
+    n_blk = in_grp / gm;
+  };
+
+  if (warp == 0) {
+    // ============================== TMA producer (both CTAs) ==============================
+    if (lane == 0) {
+      const uint32_t leader_full = mapa_shared(full_bar, 0);
+      uint32_t it = 0;
+      for (int w = pair; w < num_work; w += num_pairs) {
+        int m_blk, n_blk, split;
+        decode(w, m_blk, n_blk, split);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, k_blocks_total);
+        const int m0 = m_blk * 256 + (int)rank * 128;
+        const int n0 = n_blk * BN + (int)rank * (BN / 2);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          if (leader) mbar_expect_tx(full_bar + 8 * s, 2 * STAGE2_BYTES);
+          const uint32_t a_dst = sA + s * A_STAGE_BYTES;
+          const uint32_t b_dst = sB + s * B_HALF_BYTES;
+          const uint32_t bar = leader_full + 8 * s;
+          if (!p.a_mn) {
+            tma_load_2d_2cta(a_dst, &tmA, bar, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2cta(a_dst + j * (64 * BK * 2), &tmA, bar, m0 + 64 * j, kb * BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_2cta(b_dst, &tmB, bar, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2cta(b_dst + j * (64 * BK * 2), &tmB, bar, n0 + 64 * j, kb * BK);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader only) ================================
+    if (leader && lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(p.fmt, p.a_mn, p.b_mn, 256, BN);
+      const uint32_t a_lbo = p.a_mn ? (BK * 128) : 0, b_lbo = p.b_mn ? (BK * 128) : 0;
+      const uint32_t a_kstep = p.a_mn ? 2048 : 32, b_kstep = p.b_mn ? 2048 : 32;
+      uint32_t it = 0;
+      uint32_t local = 0;
+      for (int w = pair; w < num_work; w += num_pairs, ++local) {
+        int m_blk, n_blk, split;
+        decode(w, m_blk, n_blk, split);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, k_blocks_total);
+        const uint32_t acc = local & 1;
+        const uint32_t acc_ph = (local >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * acc, acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t a_addr = sA + s * A_STAGE_BYTES;
+          const uint32_t b_addr = sB + s * B_HALF_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = umma_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+            umma_f16_2cta(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2cta(empty_bar + 8 * s);  // frees the stage in both CTAs
+        }
+        umma_commit_2cta(tfull_bar + 8 * acc);  // accumulator complete -> both epilogues
+      }
+    }
+  } else {
+    // ================================ epilogue (both CTAs) ================================
+    const int q = warp & 3;
+    const uint32_t leader_tempty = mapa_shared(tempty_bar, 0);
+    uint32_t local = 0;
+    for (int w = pair; w < num_work; w += num_pairs, ++local) {
+      int m_blk, n_blk, split;
+      decode(w, m_blk, n_blk, split);
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb0 + kb_per_split, k_blocks_total);
+      const uint32_t acc = local & 1;
+      const uint32_t acc_ph = (local >> 1) & 1;
+      mbar_wait(tfull_bar + 8 * acc, acc_ph);
+      tc_fence_after();
+      const int m_base = m_blk * 256 + (int)rank * 128 + q * 32;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const int ew = warp - 2;
+      const int hf = ew >> 2;
+      const uint32_t stage = epi_stage + (uint32_t)ew * EPI_STAGE_BYTES;
+      const uint32_t bias_s = bias_smem + (local & 1) * (256 * 4);
+      const int et = ew * 32 + lane;
+      if (e.bias) {
+        const int n = n_blk * BN + et;
+        const float bv = n < e.N ? __ldg(e.bias + n) : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4 * et), "f"(bv) : "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      if (kb1 > kb0) {
+        const float aux[32] = {};
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + hf * 32, r);
+#pragma unroll 1
+        for (int c = hf; c < BN / 32; c += 2) {
+          float t[32];
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(r[j]);
+          if (c + 2 < BN / 32) tmem_ld_32x32(t_row + (c + 2) * 32, r);
+          epi_block32(e, m_base, lane, n_blk * BN + c * 32, c * 32, t, aux, AUX_NONE, split == 0, stage, bias_s);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tempty + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody exits (or frees TMEM) while the peer can still touch its smem / barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
 // =================================================================================================
 // SIMT fallback (64x64 tile, 256 threads, 4x4 outputs per thread)
 // =================================================================================================
@@ -638,6 +849,44 @@ static int launch_tc(const ct_gemm_args& a, const EpiParams& e, int split_k, cud
   return 0;
 }
 
+
+static int launch_tc_2cta(const ct_gemm_args& a, const EpiParams& e, int split_k, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2], strides[2];
+    uint32_t box[2];
+    if (!a.a_mn_major) { dims[0] = a.K; dims[1] = a.M; box[0] = BK; box[1] = 128; }
+    else               { dims[0] = a.M; dims[1] = a.K; box[0] = 64; box[1] = BK; }
+    strides[0] = 2; strides[1] = (uint64_t)a.lda * 2;
+    int r = make_tmap(&tmA, a.A, 2, 2, dims, strides, box, 1);
+    if (r) return r;
+    if (!a.b_mn_major) { dims[0] = a.K; dims[1] = a.N; box[0] = BK; box[1] = BN2 / 2; }
+    else               { dims[0] = a.N; dims[1] = a.K; box[0] = 64; box[1] = BK; }
+    strides[1] = (uint64_t)a.ldb * 2;
+    r = make_tmap(&tmB, a.B, 2, 2, dims, strides, box, 1);
+    if (r) return r;
+  }
+  TcParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.a_mn = a.a_mn_major; p.b_mn = a.b_mn_major;
+  p.fmt = a.ab_dtype == DT_BF16 ? 1 : 0;
+  p.split_k = split_k;
+  p.group_m = 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CT_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    SMEM2_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (a.M + 255) / 256, n_tiles = (a.N + BN2 - 1) / BN2;
+  int64_t work = (int64_t)m_tiles * n_tiles * split_k;
+  int pairs = sm_count() / 2;
+  if (work < pairs) pairs = (int)work;
+  gemm_tcgen05_2cta_kernel<<<2 * pairs, GEMM_THREADS, SMEM2_BYTES, st>>>(tmA, tmB, p, e);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
 }  // namespace ct
 
 using namespace ct;
@@ -682,6 +931,9 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
     CT_REQUIRE(tma_ok, CT_ERR_UNSUPPORTED,
                "ct_gemm: tcgen05 path needs 16-byte aligned A/B and lda/ldb multiples of 8");
     use_tc = true;
+  } else if (a.impl == 3) {
+    CT_REQUIRE(tma_ok, CT_ERR_UNSUPPORTED, "ct_gemm: 2-CTA path needs 16-byte aligned A/B and lda/ldb multiples of 8");
+    use_tc = true;
   } else if (a.impl == 2) {
     use_tc = false;
   } else {
@@ -721,6 +973,28 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
     e.atomic_out = 1;
     if (a.beta == 0.f)
       CT_CUDA_OK(cudaMemset2DAsync(a.C, (size_t)a.ldc * 4, 0, (size_t)a.N * 4, (size_t)a.M, st));
+  }
+  static const int auto_2cta = [] { const char* v = getenv("CT_GEMM_2CTA"); return v ? atoi(v) : 0; }();
+  if (a.impl == 3 || (a.impl == 0 && auto_2cta && a.M >= 512 && a.N >= 256)) {
+    // recompute the split for 256 x 256 tiles
+    const int t2 = ((a.M + 255) / 256) * ((a.N + 255) / 256);
+    int sk = 1;
+    if (linear && t2 < sms / 2 && k_blocks >= 16) {
+      sk = (sms + t2 - 1) / t2;
+      const int max_split = k_blocks / 8;
+      if (sk > max_split) sk = max_split;
+      if (sk < 1) sk = 1;
+      const int per = (k_blocks + sk - 1) / sk;
+      sk = (k_blocks + per - 1) / per;
+    }
+    if (sk > 1 && split_k == 1) {
+      e.atomic_out = 1;
+      if (a.beta == 0.f)
+        CT_CUDA_OK(cudaMemset2DAsync(a.C, (size_t)a.ldc * 4, 0, (size_t)a.N * 4, (size_t)a.M, st));
+    } else if (sk == 1 && split_k > 1) {
+      e.atomic_out = 0;  // (C was zeroed above for the 1-CTA split: harmless)
+    }
+    return launch_tc_2cta(a, e, sk, st);
   }
   return bn == 256 ? launch_tc<256>(a, e, split_k, st) : launch_tc<128>(a, e, split_k, st);
 }

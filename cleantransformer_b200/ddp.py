@@ -62,7 +62,7 @@ def plan_buckets(sizes_offsets, cap_elems):
 
 class DistributedDataParallel(torch.nn.Module):
     def __init__(self, module, device_ids=None, output_device=None, bucket_cap_mb=BUCKET_CAP_MB,
-                 comm=None, process_group=None, max_ctas=32, **unused):
+                 comm=None, process_group=None, max_ctas=48, **unused):
         super().__init__()
         if not dist.is_initialized():
             raise RuntimeError("DistributedDataParallel needs torch.distributed.init_process_group first "
@@ -169,7 +169,7 @@ class DistributedDataParallel(torch.nn.Module):
         if self._pending[bi] == 0:
             self._launch(bi)
 
-    def _launch(self, bi):
+    def _launch(self, bi, final=False):
         if self._launched[bi] or self.world == 1:
             self._launched[bi] = True
             return
@@ -179,7 +179,9 @@ class DistributedDataParallel(torch.nn.Module):
             cur = torch.cuda.current_stream(self.device)
             self._comm_stream.wait_stream(cur)
             with torch.cuda.stream(self._comm_stream):
-                _lib.check(_lib.load().ct_allreduce_bucket(lo, hi - lo, 1.0 / self.world, 0, self.max_ctas,
+                # buckets launched after backward has finished have nothing to overlap with: use every SM
+                ctas = 148 if final else self.max_ctas
+                _lib.check(_lib.load().ct_allreduce_bucket(lo, hi - lo, 1.0 / self.world, 0, ctas,
                                                            self._comm_stream.cuda_stream), "ct_allreduce_bucket")
         else:  # baseline / oracle path: library collective on the same bucket layout
             seg = self.arena.grad[lo:hi]
@@ -197,7 +199,7 @@ class DistributedDataParallel(torch.nn.Module):
         # reduce whatever is left, in bucket order (identical on every rank)
         for bi in range(len(self.buckets)):
             if not self._launched[bi]:
-                self._launch(bi)
+                self._launch(bi, final=True)
         if self._comm_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
         self._pending = None

@@ -82,10 +82,32 @@ def case_gemm_simt():
     return r
 
 
-def mk_tc(M, N, K, a_mn, b_mn, epi=False):
+def mk_tc(M, N, K, a_mn, b_mn, epi=False, impl=1):
     def f():
-        return _gemm_case(M, N, K, a_mn, b_mn, 1, epi)
+        return _gemm_case(M, N, K, a_mn, b_mn, impl, epi)
     return f
+
+
+def case_gemm_perf_2cta():
+    import torch
+    from cleantransformer_b200 import ops
+    res = {}
+    for (M, N, K) in [(8192, 3072, 1024), (8192, 4096, 1024), (8192, 1024, 4096), (8192, 8192, 8192), (8192, 32768, 1024)]:
+        A = torch.randn(M, K, device="cuda").bfloat16(); B = torch.randn(N, K, device="cuda").bfloat16()
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        r = {}
+        for impl in (1, 3):
+            for _ in range(3):
+                ops.gemm(A, B, M, N, K, out=out, impl=impl)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                ops.gemm(A, B, M, N, K, out=out, impl=impl)
+            e1.record(); torch.cuda.synchronize()
+            r["impl%d_tflops" % impl] = 2 * M * N * K / (e0.elapsed_time(e1) / 10) / 1e9
+        res["%dx%dx%d" % (M, N, K)] = r
+    return res
 
 
 def case_gemm_wgrad_splitk():
@@ -276,6 +298,16 @@ CASES = {
     "tc_epi": mk_tc(1024, 1024, 512, 0, 0, True),
     "tc_wgrad_splitk": case_gemm_wgrad_splitk,
     "gemm_perf": case_gemm_perf,
+    "tc2_256x256x64_kk": mk_tc(256, 256, 64, 0, 0, impl=3),
+    "tc2_512x512x512_kk": mk_tc(512, 512, 512, 0, 0, impl=3),
+    "tc2_512x512x512_km": mk_tc(512, 512, 512, 0, 1, impl=3),
+    "tc2_512x512x512_mk": mk_tc(512, 512, 512, 1, 0, impl=3),
+    "tc2_512x512x512_mm": mk_tc(512, 512, 512, 1, 1, impl=3),
+    "tc2_ragged_kk": mk_tc(200, 136, 72, 0, 0, impl=3),
+    "tc2_ragged_mm": mk_tc(712, 520, 200, 1, 1, impl=3),
+    "tc2_big_kk": mk_tc(8192, 3072, 1024, 0, 0, impl=3),
+    "tc2_epi": mk_tc(1024, 1024, 512, 0, 0, True, impl=3),
+    "gemm_perf_2cta": case_gemm_perf_2cta,
     "attn_simt_d8_bloom": mk_attn(2, 8, 12, 12, 8, True, 0, 2, bwd=True, pad="right"),
     "attn_simt_d12_gpt": mk_attn(3, 4, 8, 8, 12, True, 1, 2, bwd=True, pad="left", causal_fill=-1e4),
     "attn_simt_d64_bert": mk_attn(2, 4, 40, 40, 64, False, 2, 2, bwd=True, pad="right"),
