@@ -81,7 +81,7 @@ SIGNATURES = {
                                  c_int, c_void_p, c_void_p, c_i64, c_i64, c_float, c_void_p]),
     "ct_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
-                                 c_void_p, c_int, c_i64, c_i64, c_void_p]),
+                                 c_void_p, c_int, c_void_p, ctypes.c_size_t, c_i64, c_i64, c_void_p]),
     "ct_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_double,
                               c_double, c_double, c_double, c_double, c_i64, c_int, c_float, c_void_p]),
     "ct_adamw_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 2)
                       const float* __restrict__ gamma, const float* __restrict__ mean_in,
                       const float* __restrict__ rstd_in, const void* __restrict__ dx_add,
                       int dx_add_dtype, void* __restrict__ dx, int dx_dtype,
-                      float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows) {
+                      float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
+                      float* __restrict__ partial /* [gridDim.x][2][COLS] or null (-> atomics) */) {
   constexpr int COLS = VPL * 128;
   extern __shared__ float acc_s[];  // [LN_WARPS][2][COLS]
   const int lane = threadIdx.x & 31;
@@ -247,9 +248,27 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 2)
       sg += acc_s[(size_t)w * 2 * COLS + c];
       sb += acc_s[(size_t)w * 2 * COLS + COLS + c];
     }
-    if (dgamma) atomicAdd(dgamma + c, sg);
-    if (dbeta) atomicAdd(dbeta + c, sb);
+    if (partial) {  // deterministic two-stage reduction: no same-address atomics at the tail
+      partial[((size_t)blockIdx.x * 2 + 0) * COLS + c] = sg;
+      partial[((size_t)blockIdx.x * 2 + 1) * COLS + c] = sb;
+    } else {
+      if (dgamma) atomicAdd(dgamma + c, sg);
+      if (dbeta) atomicAdd(dbeta + c, sb);
+    }
   }
+}
+
+// second stage: out[c] (+)= sum_b partial[b][which][c]
+__global__ void __launch_bounds__(256)
+    ln_bwd_reduce_kernel(const float* __restrict__ partial, int nblocks, int cols, float* __restrict__ dgamma,
+                         float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int which = blockIdx.y;
+  float* out = which == 0 ? dgamma : dbeta;
+  if (c >= cols || out == nullptr) return;
+  float acc = 0.f;
+  for (int b = 0; b < nblocks; ++b) acc += partial[((size_t)b * 2 + which) * cols + c];
+  out[c] = accumulate ? out[c] + acc : acc;
 }
 
 __global__ void __launch_bounds__(LN_WARPS * 32)
@@ -342,7 +361,8 @@ extern "C" int ct_layernorm_bwd(const void* dy, int dy_dtype, const void* dy2, i
                                 const void* x, int x_dtype, const float* gamma, const float* mean,
                                 const float* rstd, const void* dx_add, int dx_add_dtype, void* dx,
                                 int dx_dtype, float* dgamma, float* dbeta, int dgb_accumulate,
-                                int64_t rows, int64_t cols, void* stream) {
+                                float* workspace, size_t workspace_bytes, int64_t rows, int64_t cols,
+                                void* stream) {
   CT_REQUIRE((dy || dy2) && x && gamma && mean && rstd && dx, CT_ERR_BAD_ARG,
              "ct_layernorm_bwd: null pointer");
   CT_REQUIRE(rows >= 0 && cols > 0, CT_ERR_BAD_ARG, "ct_layernorm_bwd: bad shape");
@@ -350,7 +370,13 @@ extern "C" int ct_layernorm_bwd(const void* dy, int dy_dtype, const void* dy2, i
                  (!dy2 || dt_ok(dy2_dtype)) && (!dx_add || dt_ok(dx_add_dtype)),
              CT_ERR_UNSUPPORTED, "ct_layernorm_bwd: dtype must be f32 or bf16");
   cudaStream_t st = (cudaStream_t)stream;
-  if (!dgb_accumulate) {
+  const bool vec_shape = (cols % 128 == 0) && cols <= 1024;
+  int grid_probe = ln_grid(rows);
+  if (grid_probe > sm_count() * 2) grid_probe = sm_count() * 2;
+  // two-stage (workspace) reduction of dgamma/dbeta when the caller provides scratch space
+  const bool use_ws = vec_shape && workspace != nullptr && (dgamma || dbeta) &&
+                      workspace_bytes >= (size_t)grid_probe * 2 * cols * sizeof(float) && rows > 0;
+  if (!dgb_accumulate && !use_ws) {
     if (dgamma) CT_CUDA_OK(cudaMemsetAsync(dgamma, 0, sizeof(float) * cols, st));
     if (dbeta) CT_CUDA_OK(cudaMemsetAsync(dbeta, 0, sizeof(float) * cols, st));
   }
@@ -373,7 +399,7 @@ extern "C" int ct_layernorm_bwd(const void* dy, int dy_dtype, const void* dy2, i
     ln_bwd_vec_kernel<V><<<grid, LN_WARPS * 32, smem, st>>>(dy, dy_dtype, dy2, dy2_dtype, x,     \
                                                             x_dtype, gamma, mean, rstd, dx_add,  \
                                                             dx_add_dtype, dx, dx_dtype, dgamma,  \
-                                                            dbeta, rows);                        \
+                                                            dbeta, rows, use_ws ? workspace : nullptr); \
   } break;
   if (vec) {
     switch ((int)(cols / 128)) {
@@ -387,5 +413,10 @@ extern "C" int ct_layernorm_bwd(const void* dy, int dy_dtype, const void* dy2, i
   }
 #undef CT_LN_BWD
   CT_LAUNCH_OK();
+  if (use_ws) {
+    dim3 g2((unsigned)((cols + 255) / 256), 2);
+    ln_bwd_reduce_kernel<<<g2, 256, 0, st>>>(workspace, grid, (int)cols, dgamma, dbeta, dgb_accumulate);
+    CT_LAUNCH_OK();
+  }
   return 0;
 }

@@ -26,7 +26,7 @@ _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
 LAUNCHES = [0]
 GEMM_PROFILE = None  # when a list: (M, N, K, start_event, end_event) appended per ct_gemm call
 _KERNELS_PER_CALL = {"ct_kv_append": 1, "ct_attn_decode": 1,
-                     "ct_layernorm_fwd": 1, "ct_layernorm_bwd": 1, "ct_adamw_step": 1, "ct_adamw_multi": 1,
+                     "ct_layernorm_fwd": 1, "ct_layernorm_bwd": 2, "ct_adamw_step": 1, "ct_adamw_multi": 1,
                      "ct_sgd_step": 1, "ct_cast": 1, "ct_colsum": 1, "ct_act_fwd": 1, "ct_act_bwd": 1,
                      "ct_gemm": 1, "ct_attn_fwd": 1, "ct_attn_bwd": 3, "ct_attn_mask_prep": 1,
                      "ct_embedding_fwd": 1, "ct_embedding_bwd": 1, "ct_cross_entropy_fwd": 3,
@@ -84,6 +84,20 @@ def layernorm_fwd(x, gamma, beta, eps, out_dtype=None, out2_dtype=None, save_sta
     return y, y2, mean, rstd
 
 
+_LN_WS = {}
+
+
+def _ln_workspace(device, cols):
+    """Scratch for the two-stage dgamma/dbeta reduction (stream-ordered reuse on the current stream)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _LN_WS.get(key)
+    need = 2 * 2 * 160 * 1024  # 2 * (2 * #SMs) * cols upper bound for cols <= 1024
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.float32, device=device)
+        _LN_WS[key] = ws
+    return ws
+
+
 def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, accumulate, dy2=None, dx_add=None,
                   dx_dtype=torch.float32):
     """Returns dx; dgamma/dbeta (f32 [cols]) are written (accumulate=False) or += (True)."""
@@ -95,11 +109,15 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, accumulate, dy2=None,
     dy2 = dy2.contiguous() if dy2 is not None else None
     dx_add = dx_add.contiguous() if dx_add is not None else None
     dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
+    ws = None
+    if (dgamma is not None or dbeta is not None) and cols % 128 == 0 and cols <= 1024:
+        ws = _ln_workspace(x.device, cols)
     _ck(_lib.load().ct_layernorm_bwd(
         ptr(dy), dt(dy) if dy is not None else 0, ptr(dy2), dt(dy2) if dy2 is not None else 0,
         ptr(x2), dt(x2), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx_add),
         dt(dx_add) if dx_add is not None else 0, ptr(dx), dt(dx), ptr(dgamma), ptr(dbeta),
-        1 if accumulate else 0, rows, cols, stream()), "ct_layernorm_bwd")
+        1 if accumulate else 0, ptr(ws), ws.numel() * 4 if ws is not None else 0, rows, cols, stream()),
+        "ct_layernorm_bwd")
     return dx
 
 

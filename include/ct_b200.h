@@ -56,11 +56,14 @@ int ct_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float
 /* Backward of the above (what autograd derives from transformer.py:86-89).
  * dx = (dx_add ? dx_add : 0) + dLN/dx ; dgamma/dbeta are ACCUMULATED (+=) into f32 buffers when
  * dgb_accumulate != 0, else overwritten. dy may be NULL only if dy2 is given; when both dy and dy2
- * are non-NULL the incoming gradient is their sum (two consumers of the LN output). */
+ * are non-NULL the incoming gradient is their sum (two consumers of the LN output).
+ * workspace (nullable): f32 scratch of >= 2 * (2 * #SMs) * cols floats enables a deterministic two-stage
+ * dgamma/dbeta reduction; without it the per-CTA partials are combined with atomics. */
 int ct_layernorm_bwd(const void* dy, int dy_dtype, const void* dy2, int dy2_dtype, const void* x,
                      int x_dtype, const float* gamma, const float* mean, const float* rstd,
                      const void* dx_add, int dx_add_dtype, void* dx, int dx_dtype, float* dgamma,
-                     float* dbeta, int dgb_accumulate, int64_t rows, int64_t cols, void* stream);
+                     float* dbeta, int dgb_accumulate, float* workspace, size_t workspace_bytes,
+                     int64_t rows, int64_t cols, void* stream);
 
 /* ---- optimizers: CleanTransformer/optimizer.py ---------------------------------------------- *
  * One vectorised kernel over a flat f32 arena (p, g, m, v all [n]).
@@ -131,7 +134,8 @@ typedef struct {
   const void* residual; /* nullable, [M,N] */
   int32_t res_dtype;
   int64_t ldr;
-  int32_t impl; /* 0 auto, 1 force tcgen05, 2 force the SIMT kernel (small/unaligned shapes) */
+  int32_t impl; /* 0 auto, 1 force 1-CTA tcgen05, 2 force the SIMT kernel (small/unaligned shapes),
+                   3 force the 2-CTA (cta_group::2, 256x256 tile) tcgen05 kernel */
 } ct_gemm_args;
 int ct_gemm(const ct_gemm_args* args, void* stream);
 

@@ -115,12 +115,12 @@ MAJORS = [(0, 0), (0, 1), (1, 0), (1, 1)]
 
 
 @pytest.mark.parametrize("a_mn,b_mn", MAJORS)
-@pytest.mark.parametrize("shape", [(512, 512, 512), (200, 136, 72), (128, 3072, 1024), (8, 64, 48)])
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("shape", [(512, 512, 512), (200, 136, 72), (128, 3072, 1024), (8, 64, 48), (712, 520, 200)])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 def test_gemm_all_operand_majors(a_mn, b_mn, shape, impl):
     ops = _ops()
     M, N, K = shape
-    if impl == 1 and ((a_mn and M % 8) or (b_mn and N % 8) or (not a_mn and K % 8) or (not b_mn and K % 8)):
+    if impl in (1, 3) and ((a_mn and M % 8) or (b_mn and N % 8) or (not a_mn and K % 8) or (not b_mn and K % 8)):
         pytest.skip("TMA needs 16-byte aligned leading dimensions")
     torch.manual_seed(3)
     A = torch.randn((K, M) if a_mn else (M, K), device=DEV).bfloat16()
