@@ -275,6 +275,18 @@ extern "C" int ct_allreduce_bucket(int64_t offset, int64_t count, float scale, i
     fill_params(p, offset, count, scale);
   }
   if (max_ctas <= 0) max_ctas = 64;
+  {
+    // same shared-memory carve-out as the big GEMM / attention kernels so that an all-reduce CTA can
+    // be co-resident with them (an SM cannot host CTAs that want different L1/shared splits)
+    static bool carve = false;
+    if (!carve) {
+      cudaFuncSetAttribute(allreduce_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(allreduce_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      carve = true;
+    }
+  }
   const int64_t nvec = count >> 2;
   if (mode == 1) {
     // one-shot needs a staging area of `count` floats right after the range

@@ -174,21 +174,51 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& e, int m, int n0, f
 // through a private smem buffer (row stride 144 B: conflict-free 16-byte row writes) and writes it
 // out with lanes running along the row: 64 B (16-bit) or 128 B (fp32) contiguous per row, 8 or 4
 // rows per instruction.
-constexpr int EPI_STAGE_ROW = 128;
-constexpr int EPI_STAGE_BYTES = 32 * EPI_STAGE_ROW;  // per epilogue warp
+constexpr int EPI_STAGE_ROW = 64;
+constexpr int EPI_STAGE_BYTES = 32 * EPI_STAGE_ROW;  // 2 KB per epilogue warp
 constexpr int EPI_WARPS = 8;
 
-// chunk i (16 bytes) of row r lives at position i ^ (r & 7) of the row's 128-byte slot: both the
-// row-per-thread writes and the lanes-along-the-row reads are bank-conflict free without padding
+// Staging rows are 64 bytes (32 x 16-bit, or HALF of a 32 x fp32 chunk: fp32 goes out in two
+// rounds). 16-byte chunk i of row r lives at position i ^ ((r >> 1) & 3): with rows 2k / 2k+1 in the
+// two halves of a 128-byte line, both the row-per-thread writes and the lanes-along-the-row reads
+// are bank-conflict free without padding. (Keeping the buffers at 16 KB total leaves enough shared
+// memory for an all-reduce CTA to be co-resident with a GEMM CTA during the DDP backward.)
+__device__ __forceinline__ void stage_round(uint32_t stage, int lane, uint32_t w0, uint32_t w1, uint32_t w2,
+                                            uint32_t w3, int i) {
+  const uint32_t my = stage + lane * EPI_STAGE_ROW;
+  const int key = (lane >> 1) & 3;
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my + 16 * (i ^ key)), "r"(w0), "r"(w1), "r"(w2),
+               "r"(w3) : "memory");
+}
+// write out the staged 32 rows x 64 bytes: 8 rows x 64 B per instruction
+__device__ __forceinline__ void stage_flush(uint32_t stage, int lane, uint8_t* gbase_bytes, int64_t ld_bytes,
+                                            int m_base, int M) {
+  const int piece = lane & 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = (lane >> 2) + 8 * k;
+    uint4 w;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                 : "r"(stage + r * EPI_STAGE_ROW + 16 * (piece ^ ((r >> 1) & 3))));
+    const int m = m_base + r;
+    if (m < M) *reinterpret_cast<uint4*>(gbase_bytes + (int64_t)m * ld_bytes + piece * 16) = w;
+  }
+}
+
 __device__ __forceinline__ void stage_store32(uint32_t stage, int lane, const float (&v)[32], int dt,
                                               void* gbase, int64_t ld, int m_base, int M, int n0) {
-  const uint32_t my = stage + lane * EPI_STAGE_ROW;
-  const int sw = lane & 7;
   if (dt == DT_F32) {
+    uint8_t* g = reinterpret_cast<uint8_t*>(gbase) + (int64_t)n0 * 4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my + 16 * (i ^ sw)), "f"(v[4 * i]),
-                   "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        stage_round(stage, lane, __float_as_uint(v[16 * h + 4 * i]), __float_as_uint(v[16 * h + 4 * i + 1]),
+                    __float_as_uint(v[16 * h + 4 * i + 2]), __float_as_uint(v[16 * h + 4 * i + 3]), i);
+      __syncwarp();
+      stage_flush(stage, lane, g + 64 * h, ld * 4, m_base, M);
+      __syncwarp();
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -203,36 +233,12 @@ __device__ __forceinline__ void stage_store32(uint32_t stage, int lane, const fl
         h = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]); w2 = *reinterpret_cast<uint32_t*>(&h);
         h = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]); w3 = *reinterpret_cast<uint32_t*>(&h);
       }
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my + 16 * (i ^ sw)), "r"(w0), "r"(w1),
-                   "r"(w2), "r"(w3) : "memory");
+      stage_round(stage, lane, w0, w1, w2, w3, i);
     }
+    __syncwarp();
+    stage_flush(stage, lane, reinterpret_cast<uint8_t*>(gbase) + (int64_t)n0 * 2, ld * 2, m_base, M);
+    __syncwarp();
   }
-  __syncwarp();
-  if (dt == DT_F32) {
-    const int piece = lane & 7;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int r = (lane >> 3) + 4 * k;
-      uint4 w;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
-                   : "r"(stage + r * EPI_STAGE_ROW + 16 * (piece ^ (r & 7))));
-      const int m = m_base + r;
-      if (m < M) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(gbase) + (int64_t)m * ld + n0 + piece * 4) = w;
-    }
-  } else {
-    const int piece = lane & 3;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int r = (lane >> 2) + 8 * k;
-      uint4 w;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
-                   : "r"(stage + r * EPI_STAGE_ROW + 16 * (piece ^ (r & 7))));
-      const int m = m_base + r;
-      if (m < M)
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(gbase) + (int64_t)m * ld + n0 + piece * 8) = w;
-    }
-  }
-  __syncwarp();
 }
 
 // The epilogue is latency-bound: besides running 8 warps (two per TMEM lane quarter, alternating

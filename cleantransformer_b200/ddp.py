@@ -62,7 +62,7 @@ def plan_buckets(sizes_offsets, cap_elems):
 
 class DistributedDataParallel(torch.nn.Module):
     def __init__(self, module, device_ids=None, output_device=None, bucket_cap_mb=BUCKET_CAP_MB,
-                 comm=None, process_group=None, max_ctas=48, **unused):
+                 comm=None, process_group=None, max_ctas=24, **unused):
         super().__init__()
         if not dist.is_initialized():
             raise RuntimeError("DistributedDataParallel needs torch.distributed.init_process_group first "
@@ -79,7 +79,8 @@ class DistributedDataParallel(torch.nn.Module):
         self.comm = comm or os.environ.get("CT_DDP_COMM") or ("p2p" if on_gpu else "nccl")
         if self.comm == "p2p" and not on_gpu:
             raise RuntimeError("comm='p2p' needs CUDA parameters")
-        self.max_ctas = max_ctas
+        self.max_ctas = int(os.environ.get("CT_DDP_CTAS", max_ctas))
+        self.final_ctas = int(os.environ.get("CT_DDP_FINAL_CTAS", 148))
         grad_buf = None
         n_total = sum((p.numel() + 63) // 64 * 64 for p in params)
         if self.comm == "p2p" and self.world > 1:
@@ -106,7 +107,7 @@ class DistributedDataParallel(torch.nn.Module):
         self._launched = None
         self._writes = None
         self._cb_queued = False
-        self._comm_stream = torch.cuda.Stream(device=self.device) if on_gpu else None
+        self._comm_stream = torch.cuda.Stream(device=self.device, priority=-1) if on_gpu else None
         self.require_backward_grad_sync = True
         # (3) hooks: our kernels announce gradients through functional.grad_written; gradients that
         # come from torch autograd (plain nn modules) through post-accumulate hooks
@@ -170,6 +171,9 @@ class DistributedDataParallel(torch.nn.Module):
             self._launch(bi)
 
     def _launch(self, bi, final=False):
+        if os.environ.get("CT_DDP_DEBUG"):
+            self._dbg = getattr(self, "_dbg", [])
+            self._dbg.append((bi, final, sum(self._writes.values())))
         if self._launched[bi] or self.world == 1:
             self._launched[bi] = True
             return
@@ -180,7 +184,7 @@ class DistributedDataParallel(torch.nn.Module):
             self._comm_stream.wait_stream(cur)
             with torch.cuda.stream(self._comm_stream):
                 # buckets launched after backward has finished have nothing to overlap with: use every SM
-                ctas = 148 if final else self.max_ctas
+                ctas = self.final_ctas if final else self.max_ctas
                 _lib.check(_lib.load().ct_allreduce_bucket(lo, hi - lo, 1.0 / self.world, 0, ctas,
                                                            self._comm_stream.cuda_stream), "ct_allreduce_bucket")
         else:  # baseline / oracle path: library collective on the same bucket layout
@@ -202,6 +206,10 @@ class DistributedDataParallel(torch.nn.Module):
                 self._launch(bi, final=True)
         if self._comm_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
+        if os.environ.get("CT_DDP_DEBUG") and self.rank == 0:
+            print("DDP launch order (bucket, final?, grads written so far):", getattr(self, "_dbg", [])[:60],
+                  "pending", self._pending, flush=True)
+            self._dbg = []
         self._pending = None
 
     # ---------------------------------------------------------------- misc surface

@@ -334,3 +334,20 @@ def test_cast_colsum_activations():
     g = torch.randn_like(x)
     assert rel_err(ops.act_bwd(g, x, ops.ACT_GELU_TANH), O.gelu_tanh_bloom_back(g, x)) < 2e-3
     assert rel_err(ops.act_fwd(x, ops.ACT_GELU_ERF), O.gelu_erf(x)) < 1e-5
+
+
+def test_kv_cache_append_matches_concat():
+    """In-place cache growth (ct_kv_append) == the reference's torch.concat along the time axis
+    (modeling_bloom.py:88-92, modeling_gpt.py:76-80), across a capacity re-allocation."""
+    ops = _ops()
+    torch.manual_seed(12)
+    B, H, D = 2, 3, 64
+    ref = None
+    cache = None
+    for step, s in enumerate([5, 1, 1, 300, 1]):
+        new = torch.randn(B, s, H, 3, D, device=DEV).bfloat16()[..., 1, :].permute(0, 2, 1, 3)  # strided view
+        ref = new.contiguous() if ref is None else torch.cat((ref, new), dim=2)
+        cache = ops.kv_cache_append(cache, new)
+        assert cache.shape == ref.shape
+        assert torch.equal(cache, ref)
+    assert cache._ct_cache_base.shape[2] >= cache.shape[2]
