@@ -384,10 +384,15 @@ def main():
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": 3 * B * S * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "loss": float(loss), "loss_e2e": float(loss_e2e),
+            "loss": float(loss.detach()), "loss_e2e": float(loss_e2e),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of the LM-head forward GEMM
+                         # (the largest launch of this kernel: M=8192, N=250880, K=1024), ncu --set full,
+                         # profiles/r01c_ncu_full_2layer_step_summary.csv row 20 (3.06 GB read + 4.08 GB written;
+                         # algorithmic: 0.53 GB operands + 4.11 GB bf16 logits)
+                         "traffic": 7.14e9 if args.layers == 24 else None,
                          "peak_source": peak_kind + " (bf16_tflops_sustained: kernel timed inside a long step)",
                          "launches_timed": len(prof), "gemm_ms_per_step": gms / 2.0,
                          "gemm_share_of_step": (gms / 2.0) / ms_step if ms_step else None},
