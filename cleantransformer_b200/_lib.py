@@ -72,16 +72,37 @@ class AttnBwdArgs(ctypes.Structure):
     ]
 
 
+class LnBwdArgs(ctypes.Structure):
+    """Mirror of `ct_ln_bwd_args`."""
+
+    _fields_ = [
+        ("rows", c_i64), ("cols", c_i64),
+        ("dy", c_void_p), ("dy_dtype", ctypes.c_int32),
+        ("dy2", c_void_p), ("dy2_dtype", ctypes.c_int32),
+        ("x", c_void_p), ("x_dtype", ctypes.c_int32),
+        ("gamma", c_void_p), ("mean", c_void_p), ("rstd", c_void_p),
+        ("dx_add", c_void_p), ("dx_add_dtype", ctypes.c_int32),
+        ("dx", c_void_p), ("dx_dtype", ctypes.c_int32),
+        ("dx2", c_void_p), ("dx2_dtype", ctypes.c_int32),
+        ("dgamma", c_void_p), ("dbeta", c_void_p), ("dgb_accumulate", ctypes.c_int32),
+        ("dxsum", c_void_p), ("dxsum_accumulate", ctypes.c_int32),
+        ("workspace", c_void_p), ("workspace_bytes", ctypes.c_size_t),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/ct_b200.h
 SIGNATURES = {
     "ct_version": (c_int, []),
     "ct_last_error": (c_int, [ctypes.c_char_p, ctypes.c_size_t]),
     "ct_device_check": (c_int, [c_int]),
+    "ct_set_option": (c_int, [ctypes.c_char_p, c_int]),
+    "ct_get_option": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int)]),
     "ct_layernorm_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                  c_int, c_void_p, c_void_p, c_i64, c_i64, c_float, c_void_p]),
     "ct_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                  c_void_p, c_int, c_void_p, ctypes.c_size_t, c_i64, c_i64, c_void_p]),
+    "ct_layernorm_bwd_ex": (c_int, [ctypes.POINTER(LnBwdArgs), c_void_p]),
     "ct_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_double,
                               c_double, c_double, c_double, c_double, c_i64, c_int, c_float, c_void_p]),
     "ct_adamw_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

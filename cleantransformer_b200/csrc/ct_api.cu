@@ -4,6 +4,7 @@
 #include "../../include/ct_b200.h"
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -83,9 +84,55 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
   return 0;
 }
 
+// ---- tuning knobs (kernel-variant selection for A/B runs and tests) ------------------------------
+// Initial values come from the environment (CT_<NAME>), ct_set_option overrides at run time.
+static int g_opt[OPT_COUNT];
+static std::once_flag g_opt_once;
+static const char* const kOptNames[OPT_COUNT] = {"LN_BWD_IMPL", "ATTN_FWD_IMPL", "ATTN_BWD_IMPL", "GEMM_EPI_IMPL",
+                                                 "GEMM_2CTA", "CE_IMPL"};
+static const int kOptDefaults[OPT_COUNT] = {0, 0, 0, 0, 1, 0};
+static void opt_init() {
+  std::call_once(g_opt_once, [] {
+    for (int i = 0; i < OPT_COUNT; ++i) {
+      char name[64];
+      snprintf(name, sizeof(name), "CT_%s", kOptNames[i]);
+      const char* e = getenv(name);
+      g_opt[i] = e ? atoi(e) : kOptDefaults[i];
+    }
+  });
+}
+int option(int which) {
+  opt_init();
+  return (which >= 0 && which < OPT_COUNT) ? __atomic_load_n(&g_opt[which], __ATOMIC_RELAXED) : 0;
+}
+
 }  // namespace ct
 
 extern "C" {
+
+int ct_set_option(const char* name, int value) {
+  ct::opt_init();
+  CT_REQUIRE(name != nullptr, CT_ERR_BAD_ARG, "ct_set_option: null name");
+  for (int i = 0; i < ct::OPT_COUNT; ++i)
+    if (strcmp(name, ct::kOptNames[i]) == 0) {
+      __atomic_store_n(&ct::g_opt[i], value, __ATOMIC_RELAXED);
+      return 0;
+    }
+  ct::set_error("ct_set_option: unknown option '%s'", name);
+  return CT_ERR_BAD_ARG;
+}
+
+int ct_get_option(const char* name, int* value) {
+  ct::opt_init();
+  CT_REQUIRE(name != nullptr && value != nullptr, CT_ERR_BAD_ARG, "ct_get_option: null argument");
+  for (int i = 0; i < ct::OPT_COUNT; ++i)
+    if (strcmp(name, ct::kOptNames[i]) == 0) {
+      *value = ct::option(i);
+      return 0;
+    }
+  ct::set_error("ct_get_option: unknown option '%s'", name);
+  return CT_ERR_BAD_ARG;
+}
 
 int ct_version(void) { return CT_B200_VERSION; }
 

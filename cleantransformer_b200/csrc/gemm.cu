@@ -980,7 +980,7 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
     if (a.beta == 0.f)
       CT_CUDA_OK(cudaMemset2DAsync(a.C, (size_t)a.ldc * 4, 0, (size_t)a.N * 4, (size_t)a.M, st));
   }
-  static const int auto_2cta = [] { const char* v = getenv("CT_GEMM_2CTA"); return v ? atoi(v) : 1; }();
+  const int auto_2cta = option(OPT_GEMM_2CTA);
   if (a.impl == 3 || (a.impl == 0 && auto_2cta && a.M >= 512 && a.N >= 256)) {
     // recompute the split for 256 x 256 tiles
     const int t2 = ((a.M + 255) / 256) * ((a.N + 255) / 256);

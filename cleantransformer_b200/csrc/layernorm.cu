@@ -11,6 +11,8 @@
 //                                       bwd  H*(sizeof(dy) + sizeof(x) + sizeof(dx) [+4 dx_add]) + 8
 #include "ct_common.cuh"
 #include "../../include/ct_b200.h"
+#include <cstdlib>
+#include <cstring>
 
 namespace ct {
 
@@ -271,6 +273,176 @@ __global__ void __launch_bounds__(256)
   out[c] = accumulate ? out[c] + acc : acc;
 }
 
+// ---- backward v2: a row is spread over cols/4 threads (one float4 per thread and tensor) -----------
+// The warp-per-row kernel above keeps 3 x 32 values per lane in registers (128 registers, 16 warps per
+// SM) and measured 54 us at [8192,1024] against a 21 us HBM floor: too few loads in flight. Here a
+// CTA is two independent halves of cols/4 threads; each half handles LNB_R rows per iteration, so a
+// thread holds LNB_R float4 per tensor (<= 64 registers, 32 warps per SM) and OWNS four fixed
+// columns: the dgamma / dbeta / column-sum(dx) partials stay in registers for the whole kernel. The
+// two row reductions go warp-shuffle -> smem -> one named barrier per iteration (slots double-buffered
+// by iteration parity). Per-CTA partials are combined by ln_bwd_reduce3_kernel (deterministic).
+constexpr int LNB_R = 2;
+
+struct LnBwdP {
+  const void* dy; int dy_dtype;
+  const void* dy2; int dy2_dtype;
+  const void* x; int x_dtype;
+  const float* gamma; const float* mean; const float* rstd;
+  const void* dx_add; int dx_add_dtype;
+  void* dx; int dx_dtype;
+  void* dx2; int dx2_dtype;
+  float* dgamma; float* dbeta; float* dxsum;
+  float* partial;  // [gridDim.x][3][cols] or null (-> atomics into dgamma / dbeta / dxsum)
+  int64_t rows;
+  int cols;
+};
+
+__global__ void __launch_bounds__(512, 2) ln_bwd_cta_kernel(const LnBwdP p) {
+  __shared__ float red[2][2][2 * LNB_R][8];
+  __shared__ __align__(16) float comb[3 * 1024];
+  const int tpr = blockDim.x >> 1;  // threads per row = cols / 4
+  const int half = threadIdx.x >= tpr ? 1 : 0;
+  const int t = threadIdx.x - half * tpr;
+  const int lane = t & 31, wih = t >> 5, nwh = tpr >> 5;
+  const int col0 = 4 * t;
+  const float inv_cols = 1.f / (float)p.cols;
+  const bool need_part = p.dgamma || p.dbeta || p.dxsum;
+
+  const float4 g4 = Vec4<float>::load(p.gamma + col0);
+  float4 adg = make_float4(0.f, 0.f, 0.f, 0.f), adb = adg, adc = adg;
+  int it = 0;
+  for (int64_t grp = (int64_t)blockIdx.x * 2 + half; grp * LNB_R < p.rows; grp += (int64_t)gridDim.x * 2, ++it) {
+    float4 xh[LNB_R], d[LNB_R], av[LNB_R];
+    float rs[LNB_R];
+    float part[2 * LNB_R];
+#pragma unroll
+    for (int r = 0; r < LNB_R; ++r) {
+      const int64_t row = grp * LNB_R + r;
+      const bool ok = row < p.rows;
+      const int64_t idx = row * p.cols + col0;
+      float mean = 0.f;
+      rs[r] = 0.f;
+      xh[r] = make_float4(0.f, 0.f, 0.f, 0.f); d[r] = xh[r]; av[r] = xh[r];
+      if (ok) {
+        xh[r] = load4_dyn(p.x, p.x_dtype, idx);
+        if (p.dy) {
+          d[r] = load4_dyn(p.dy, p.dy_dtype, idx);
+          if (p.dy2) {
+            const float4 e = load4_dyn(p.dy2, p.dy2_dtype, idx);
+            d[r].x += e.x; d[r].y += e.y; d[r].z += e.z; d[r].w += e.w;
+          }
+        } else {
+          d[r] = load4_dyn(p.dy2, p.dy2_dtype, idx);
+        }
+        if (p.dx_add) av[r] = load4_dyn(p.dx_add, p.dx_add_dtype, idx);
+        mean = __ldg(p.mean + row);
+        rs[r] = __ldg(p.rstd + row);
+      }
+      xh[r].x = (xh[r].x - mean) * rs[r]; xh[r].y = (xh[r].y - mean) * rs[r];
+      xh[r].z = (xh[r].z - mean) * rs[r]; xh[r].w = (xh[r].w - mean) * rs[r];
+    }
+#pragma unroll
+    for (int r = 0; r < LNB_R; ++r) {
+      adg.x = fmaf(d[r].x, xh[r].x, adg.x); adg.y = fmaf(d[r].y, xh[r].y, adg.y);
+      adg.z = fmaf(d[r].z, xh[r].z, adg.z); adg.w = fmaf(d[r].w, xh[r].w, adg.w);
+      adb.x += d[r].x; adb.y += d[r].y; adb.z += d[r].z; adb.w += d[r].w;
+      d[r].x *= g4.x; d[r].y *= g4.y; d[r].z *= g4.z; d[r].w *= g4.w;
+      part[2 * r] = (d[r].x + d[r].y) + (d[r].z + d[r].w);
+      part[2 * r + 1] = (d[r].x * xh[r].x + d[r].y * xh[r].y) + (d[r].z * xh[r].z + d[r].w * xh[r].w);
+    }
+#pragma unroll
+    for (int q = 0; q < 2 * LNB_R; ++q) part[q] = warp_sum(part[q]);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < 2 * LNB_R; ++q) red[half][it & 1][q][wih] = part[q];
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(tpr) : "memory");
+#pragma unroll
+    for (int q = 0; q < 2 * LNB_R; ++q) {
+      float s = 0.f;
+      for (int w = 0; w < nwh; ++w) s += red[half][it & 1][q][w];
+      part[q] = s * inv_cols;
+    }
+#pragma unroll
+    for (int r = 0; r < LNB_R; ++r) {
+      const int64_t row = grp * LNB_R + r;
+      if (row >= p.rows) continue;
+      const int64_t idx = row * p.cols + col0;
+      const float s1 = part[2 * r], s2 = part[2 * r + 1];
+      float4 o;
+      o.x = fmaf(rs[r], d[r].x - s1 - xh[r].x * s2, av[r].x);
+      o.y = fmaf(rs[r], d[r].y - s1 - xh[r].y * s2, av[r].y);
+      o.z = fmaf(rs[r], d[r].z - s1 - xh[r].z * s2, av[r].z);
+      o.w = fmaf(rs[r], d[r].w - s1 - xh[r].w * s2, av[r].w);
+      store4_dyn(p.dx, p.dx_dtype, idx, o);
+      if (p.dx2) store4_dyn(p.dx2, p.dx2_dtype, idx, o);
+      adc.x += o.x; adc.y += o.y; adc.z += o.z; adc.w += o.w;
+    }
+  }
+  if (!need_part) return;
+  // combine the two halves, then one partial row set per CTA
+  if (half == 1) {
+    Vec4<float>::store(comb + col0, adg);
+    Vec4<float>::store(comb + p.cols + col0, adb);
+    Vec4<float>::store(comb + 2 * p.cols + col0, adc);
+  }
+  __syncthreads();
+  if (half == 0) {
+    const float4 a = Vec4<float>::load(comb + col0), b = Vec4<float>::load(comb + p.cols + col0),
+                 c = Vec4<float>::load(comb + 2 * p.cols + col0);
+    adg.x += a.x; adg.y += a.y; adg.z += a.z; adg.w += a.w;
+    adb.x += b.x; adb.y += b.y; adb.z += b.z; adb.w += b.w;
+    adc.x += c.x; adc.y += c.y; adc.z += c.z; adc.w += c.w;
+    if (p.partial) {
+      float* dst = p.partial + (size_t)blockIdx.x * 3 * p.cols + col0;
+      if (p.dgamma) Vec4<float>::store(dst, adg);
+      if (p.dbeta) Vec4<float>::store(dst + p.cols, adb);
+      if (p.dxsum) Vec4<float>::store(dst + 2 * p.cols, adc);
+    } else {
+      const float vg[4] = {adg.x, adg.y, adg.z, adg.w}, vb[4] = {adb.x, adb.y, adb.z, adb.w},
+                  vc[4] = {adc.x, adc.y, adc.z, adc.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (p.dgamma) atomicAdd(p.dgamma + col0 + k, vg[k]);
+        if (p.dbeta) atomicAdd(p.dbeta + col0 + k, vb[k]);
+        if (p.dxsum) atomicAdd(p.dxsum + col0 + k, vc[k]);
+      }
+    }
+  }
+}
+
+// second stage of v2: out_which[c] (+)= sum_b partial[b][which][c]; CTA = 32 columns x 8 row groups
+__global__ void __launch_bounds__(256)
+    ln_bwd_reduce3_kernel(const float* __restrict__ partial, int nblocks, int cols, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, float* __restrict__ dxsum, int acc_gb, int acc_sum) {
+  __shared__ float sm[8][33];
+  const int which = blockIdx.y;
+  float* out = which == 0 ? dgamma : (which == 1 ? dbeta : dxsum);
+  if (out == nullptr) return;  // CTA-uniform
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < cols) {
+    const float* src = partial + (size_t)which * cols + c;
+    const size_t stride = (size_t)3 * cols;
+    int b = ty;
+    for (; b + 24 < nblocks; b += 32) {
+      a0 += src[(size_t)b * stride]; a1 += src[(size_t)(b + 8) * stride];
+      a2 += src[(size_t)(b + 16) * stride]; a3 += src[(size_t)(b + 24) * stride];
+    }
+    for (; b < nblocks; b += 8) a0 += src[(size_t)b * stride];
+  }
+  sm[ty][tx] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sm[k][tx];
+    const int acc = which == 2 ? acc_sum : acc_gb;
+    out[c] = acc ? out[c] + s : s;
+  }
+}
+
 __global__ void __launch_bounds__(LN_WARPS * 32)
     ln_bwd_generic_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ dy2,
                           int dy2_dtype, const void* __restrict__ x, int x_dtype,
@@ -357,7 +529,7 @@ extern "C" int ct_layernorm_fwd(const void* x, int x_dtype, const float* gamma, 
   return 0;
 }
 
-extern "C" int ct_layernorm_bwd(const void* dy, int dy_dtype, const void* dy2, int dy2_dtype,
+static int ln_bwd_v1(const void* dy, int dy_dtype, const void* dy2, int dy2_dtype,
                                 const void* x, int x_dtype, const float* gamma, const float* mean,
                                 const float* rstd, const void* dx_add, int dx_add_dtype, void* dx,
                                 int dx_dtype, float* dgamma, float* dbeta, int dgb_accumulate,
@@ -419,4 +591,84 @@ extern "C" int ct_layernorm_bwd(const void* dy, int dy_dtype, const void* dy2, i
     CT_LAUNCH_OK();
   }
   return 0;
+}
+
+extern "C" int ct_layernorm_bwd_ex(const ct_ln_bwd_args* args, void* stream) {
+  CT_REQUIRE(args != nullptr, CT_ERR_BAD_ARG, "ct_layernorm_bwd_ex: null args");
+  const ct_ln_bwd_args& a = *args;
+  CT_REQUIRE((a.dy || a.dy2) && a.x && a.gamma && a.mean && a.rstd && a.dx, CT_ERR_BAD_ARG,
+             "ct_layernorm_bwd: null pointer");
+  CT_REQUIRE(a.rows >= 0 && a.cols > 0, CT_ERR_BAD_ARG, "ct_layernorm_bwd: bad shape");
+  CT_REQUIRE(dt_ok(a.x_dtype) && dt_ok(a.dx_dtype) && (!a.dy || dt_ok(a.dy_dtype)) &&
+                 (!a.dy2 || dt_ok(a.dy2_dtype)) && (!a.dx_add || dt_ok(a.dx_add_dtype)) &&
+                 (!a.dx2 || dt_ok(a.dx2_dtype)),
+             CT_ERR_UNSUPPORTED, "ct_layernorm_bwd: dtype must be f32 or bf16");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = a.rows, cols = a.cols;
+  const bool vec_shape = (cols % 128 == 0) && cols <= 1024;
+  const bool vec = vec_shape && aligned16(a.x) && aligned16(a.dy) && aligned16(a.dy2) && aligned16(a.dx) &&
+                   aligned16(a.dx2) && aligned16(a.dx_add) && aligned16(a.gamma);
+  const bool want_red = a.dgamma || a.dbeta || a.dxsum;
+
+  if (vec && option(OPT_LN_BWD_IMPL) != 1) {  // LN_BWD_IMPL: 0 = auto (v2), 1 = warp-per-row kernel
+    // ---- v2: cols/4 threads per row, two halves per CTA ----
+    int64_t groups = (rows + 2 * LNB_R - 1) / (2 * LNB_R);
+    int grid = (int)(groups < (int64_t)sm_count() * 2 ? groups : (int64_t)sm_count() * 2);
+    if (grid < 1) grid = 1;
+    const bool use_ws = want_red && a.workspace != nullptr &&
+                        a.workspace_bytes >= (size_t)grid * 3 * cols * sizeof(float) && rows > 0;
+    if (want_red && !use_ws) {
+      if (a.dgamma && !a.dgb_accumulate) CT_CUDA_OK(cudaMemsetAsync(a.dgamma, 0, sizeof(float) * cols, st));
+      if (a.dbeta && !a.dgb_accumulate) CT_CUDA_OK(cudaMemsetAsync(a.dbeta, 0, sizeof(float) * cols, st));
+      if (a.dxsum && !a.dxsum_accumulate) CT_CUDA_OK(cudaMemsetAsync(a.dxsum, 0, sizeof(float) * cols, st));
+    }
+    if (rows == 0) return 0;
+    LnBwdP p;
+    p.dy = a.dy; p.dy_dtype = a.dy_dtype; p.dy2 = a.dy2; p.dy2_dtype = a.dy2_dtype;
+    p.x = a.x; p.x_dtype = a.x_dtype; p.gamma = a.gamma; p.mean = a.mean; p.rstd = a.rstd;
+    p.dx_add = a.dx_add; p.dx_add_dtype = a.dx_add_dtype; p.dx = a.dx; p.dx_dtype = a.dx_dtype;
+    p.dx2 = a.dx2; p.dx2_dtype = a.dx2_dtype;
+    p.dgamma = a.dgamma; p.dbeta = a.dbeta; p.dxsum = a.dxsum;
+    p.partial = use_ws ? a.workspace : nullptr;
+    p.rows = rows; p.cols = (int)cols;
+    ln_bwd_cta_kernel<<<grid, (int)(cols / 2), 0, st>>>(p);
+    CT_LAUNCH_OK();
+    if (use_ws) {
+      dim3 g2((unsigned)((cols + 31) / 32), 3);
+      ln_bwd_reduce3_kernel<<<g2, 256, 0, st>>>(a.workspace, grid, (int)cols, a.dgamma, a.dbeta, a.dxsum,
+                                                a.dgb_accumulate, a.dxsum_accumulate);
+      CT_LAUNCH_OK();
+    }
+    return 0;
+  }
+
+  // ---- v1 (warp per row) / generic: no fused second output or column sum -> separate passes ----
+  int r = ln_bwd_v1(a.dy, a.dy_dtype, a.dy2, a.dy2_dtype, a.x, a.x_dtype, a.gamma, a.mean, a.rstd,
+                           a.dx_add, a.dx_add_dtype, a.dx, a.dx_dtype, a.dgamma, a.dbeta, a.dgb_accumulate,
+                           a.workspace, a.workspace_bytes, rows, cols, stream);
+  if (r) return r;
+  if (a.dx2) {
+    r = ct_cast(a.dx, a.dx_dtype, a.dx2, a.dx2_dtype, rows * cols, stream);
+    if (r) return r;
+  }
+  if (a.dxsum) return ct_colsum(a.dx, a.dx_dtype, cols, a.dxsum, a.dxsum_accumulate, rows, cols, stream);
+  return 0;
+}
+
+
+extern "C" int ct_layernorm_bwd(const void* dy, int dy_dtype, const void* dy2, int dy2_dtype,
+                                const void* x, int x_dtype, const float* gamma, const float* mean,
+                                const float* rstd, const void* dx_add, int dx_add_dtype, void* dx,
+                                int dx_dtype, float* dgamma, float* dbeta, int dgb_accumulate,
+                                float* workspace, size_t workspace_bytes, int64_t rows, int64_t cols,
+                                void* stream) {
+  ct_ln_bwd_args a;
+  memset(&a, 0, sizeof(a));
+  a.rows = rows; a.cols = cols;
+  a.dy = dy; a.dy_dtype = dy_dtype; a.dy2 = dy2; a.dy2_dtype = dy2_dtype;
+  a.x = x; a.x_dtype = x_dtype; a.gamma = gamma; a.mean = mean; a.rstd = rstd;
+  a.dx_add = dx_add; a.dx_add_dtype = dx_add_dtype; a.dx = dx; a.dx_dtype = dx_dtype;
+  a.dgamma = dgamma; a.dbeta = dbeta; a.dgb_accumulate = dgb_accumulate;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  return ct_layernorm_bwd_ex(&a, stream);
 }

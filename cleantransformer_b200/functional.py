@@ -8,6 +8,7 @@ that removes autograd's accumulate copies and lets the DDP wrapper see a gradien
 kernel that produced it has been enqueued.
 """
 import math
+import threading
 
 import torch
 
@@ -388,12 +389,15 @@ class PreLNBlockFn(torch.autograd.Function):
         return out.view(B, S, H), k, v
 
     @staticmethod
-    def _linear_bwd(lin, dy16, x16, io, cd, need_dx=True, actgrad_src=None, actgrad_act=ops.ACT_NONE):
+    def _linear_bwd(lin, dy16, x16, io, cd, need_dx=True, actgrad_src=None, actgrad_act=ops.ACT_NONE,
+                    bias_done=False):
+        """wgrad (+ bias gradient unless `bias_done`: the LayerNorm backward that produced dy already
+        wrote its column sums into bias.grad) and dgrad of one Linear / Conv1D."""
         w, b = lin.weight, lin.bias
         if w.requires_grad:
             gw, acc = grad_buffer(w)
             gb = None
-            if b is not None and b.requires_grad:
+            if b is not None and b.requires_grad and not bias_done:
                 gb, accb = grad_buffer(b)
                 if accb != acc:
                     (gb if not accb else gw).zero_()
@@ -408,19 +412,28 @@ class PreLNBlockFn(torch.autograd.Function):
                                 actgrad_act=actgrad_act, w_in_out=io)
 
     @staticmethod
-    def _ln_bwd(ln, dy16, x, mean, rstd, dx_add):
+    def _ln_bwd(ln, dy16, x, mean, rstd, dx_add, low_dtype=None, bias_of=None):
+        """LayerNorm backward + residual-path add. Returns (dx f32, dx in `low_dtype` or None). With
+        `bias_of` (the Linear whose `residual + Linear(.)` output is this LayerNorm's input) the same
+        pass also writes that Linear's bias gradient = column sums of dx."""
         gw, acc_w = grad_buffer(ln.weight) if ln.weight.requires_grad else (None, False)
         gb, acc_b = grad_buffer(ln.bias) if ln.bias.requires_grad else (None, False)
         if gw is not None and gb is not None and acc_w != acc_b:
             (gw if not acc_w else gb).zero_()
             acc_w = acc_b = True
-        dx = ops.layernorm_bwd(dy16, x, ln.weight.detach(), mean, rstd, gw, gb, acc_w if gw is not None else acc_b,
-                               dx_add=dx_add, dx_dtype=torch.float32)
+        dxsum, acc_s = None, False
+        if bias_of is not None and bias_of.bias is not None and bias_of.bias.requires_grad:
+            dxsum, acc_s = grad_buffer(bias_of.bias)
+        out = ops.layernorm_bwd(dy16, x, ln.weight.detach(), mean, rstd, gw, gb, acc_w if gw is not None else acc_b,
+                                dx_add=dx_add, dx_dtype=torch.float32, dx2_dtype=low_dtype,
+                                dxsum=dxsum, dxsum_accumulate=acc_s)
         if gw is not None:
             grad_written(ln.weight)
         if gb is not None:
             grad_written(ln.bias)
-        return dx
+        if dxsum is not None:
+            grad_written(bias_of.bias)
+        return out if low_dtype is not None else (out, None)
 
     @staticmethod
     def backward(ctx, g_out, _gk, _gv):
@@ -429,22 +442,53 @@ class PreLNBlockFn(torch.autograd.Function):
         B, S, H = ctx.shape
         io = spec["w_in_out"]
         cd = ln1.dtype
+        # the block above (later in forward order) hands over the low-precision copy of the very tensor
+        # autograd passes us, written by its LayerNorm backward in the same pass as the f32 gradient
+        g16 = _take_handoff(g_out, cd)
         g_out = g_out.contiguous().view(B * S, H)
         if g_out.dtype != torch.float32:
             g_out = ops.cast(g_out, torch.float32)
-        g16 = ops.cast(g_out, cd)
+        if g16 is None:
+            g16 = ops.cast(g_out, cd)
+        else:
+            g16 = g16.view(B * S, H)
         # FFN: out = att + fc2(act(fc1(ln2)))
         d_pre = PreLNBlockFn._linear_bwd(spec["fc2"], g16, h4, io, cd, actgrad_src=pre, actgrad_act=spec["act"])
         d_ln2 = PreLNBlockFn._linear_bwd(spec["fc1"], d_pre, ln2, io, cd)
-        g_att = PreLNBlockFn._ln_bwd(spec["ln2"], d_ln2, att, mean2, rstd2, g_out)  # + residual path
+        # LN2 backward + residual path; also emits bf16(g_att) and proj.bias.grad = colsum(g_att)
+        g_att, g16b = PreLNBlockFn._ln_bwd(spec["ln2"], d_ln2, att, mean2, rstd2, g_out, low_dtype=cd,
+                                           bias_of=spec["proj"])
         # attention: att = x + proj(attn(qkv(ln1)))
-        g16b = ops.cast(g_att, cd)
-        d_o = PreLNBlockFn._linear_bwd(spec["proj"], g16b, o.view(B * S, H), io, cd)
+        d_o = PreLNBlockFn._linear_bwd(spec["proj"], g16b, o.view(B * S, H), io, cd, bias_done=True)
         dqkv = torch.empty_like(qkv)
         q, k, v = split_packed(qkv.view(B, S, -1), spec["n_head"], spec["layout"])
         dq, dk, dv = split_packed(dqkv.view(B, S, -1), spec["n_head"], spec["layout"])
         ops.attn_bwd(d_o.view(B, S, H), q, k, v, o, lse2, dq, dk, dv, spec["scale"], spec["causal"],
                      spec["causal_fill"], kbias2, first_valid)
         d_ln1 = PreLNBlockFn._linear_bwd(spec["qkv"], dqkv, ln1, io, cd)
-        g_x = PreLNBlockFn._ln_bwd(spec["ln1"], d_ln1, x2, mean1, rstd1, g_att)
-        return g_x.view(B, S, H), None, None, None
+        g_x, g_x16 = PreLNBlockFn._ln_bwd(spec["ln1"], d_ln1, x2, mean1, rstd1, g_att, low_dtype=cd)
+        g_x = g_x.view(B, S, H)
+        _put_handoff(g_x, g_x16)
+        return g_x, None, None, None
+
+
+# One-slot hand-over of a gradient's low-precision copy between consecutive PreLNBlockFn backward
+# nodes. The consumer only uses it when autograd passes the IDENTICAL tensor object on (no
+# accumulation with another consumer's gradient, no hook rewrote it); holding the f32 tensor here
+# keeps its storage alive, so the identity test cannot be fooled by a recycled allocation.
+_HANDOFF = threading.local()
+
+
+def _put_handoff(g32, g16):
+    _HANDOFF.slot = (g32, g32._version, g16)
+
+
+def _take_handoff(g, dtype):
+    slot = getattr(_HANDOFF, "slot", None)
+    _HANDOFF.slot = None
+    if slot is None:
+        return None
+    g32, ver, g16 = slot
+    if g32 is g and g._version == ver and g16 is not None and g16.dtype == dtype:
+        return g16
+    return None

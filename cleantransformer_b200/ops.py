@@ -26,7 +26,7 @@ _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
 LAUNCHES = [0]
 GEMM_PROFILE = None  # when a list: (M, N, K, start_event, end_event) appended per ct_gemm call
 _KERNELS_PER_CALL = {"ct_kv_append": 1, "ct_attn_decode": 1,
-                     "ct_layernorm_fwd": 1, "ct_layernorm_bwd": 2, "ct_adamw_step": 1, "ct_adamw_multi": 1,
+                     "ct_layernorm_fwd": 1, "ct_layernorm_bwd": 2, "ct_layernorm_bwd_ex": 2, "ct_adamw_step": 1, "ct_adamw_multi": 1,
                      "ct_sgd_step": 1, "ct_cast": 1, "ct_colsum": 1, "ct_act_fwd": 1, "ct_act_bwd": 1,
                      "ct_gemm": 1, "ct_attn_fwd": 1, "ct_attn_bwd": 3, "ct_attn_mask_prep": 1,
                      "ct_embedding_fwd": 1, "ct_embedding_bwd": 1, "ct_cross_entropy_fwd": 3,
@@ -57,6 +57,15 @@ def _req_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
             raise RuntimeError("cleantransformer_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def set_option(name, value):
+    """Kernel-variant knob (include/ct_b200.h: ct_set_option); returns the previous value."""
+    lib = _lib.load()
+    old = ctypes.c_int(0)
+    check(lib.ct_get_option(name.encode(), ctypes.byref(old)), "ct_get_option")
+    check(lib.ct_set_option(name.encode(), int(value)), "ct_set_option")
+    return old.value
 
 
 def device_check(device=None):
@@ -91,7 +100,7 @@ def _ln_workspace(device, cols):
     """Scratch for the two-stage dgamma/dbeta reduction (stream-ordered reuse on the current stream)."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _LN_WS.get(key)
-    need = 2 * 2 * 160 * 1024  # 2 * (2 * #SMs) * cols upper bound for cols <= 1024
+    need = 3 * 2 * 160 * 1024  # 3 * (2 * #SMs) * cols upper bound for cols <= 1024
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.float32, device=device)
         _LN_WS[key] = ws
@@ -99,8 +108,9 @@ def _ln_workspace(device, cols):
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, accumulate, dy2=None, dx_add=None,
-                  dx_dtype=torch.float32):
-    """Returns dx; dgamma/dbeta (f32 [cols]) are written (accumulate=False) or += (True)."""
+                  dx_dtype=torch.float32, dx2_dtype=None, dxsum=None, dxsum_accumulate=False):
+    """Returns dx (or (dx, dx2) when dx2_dtype is given); dgamma/dbeta (f32 [cols]) are written
+    (accumulate=False) or += (True); dxsum (f32 [cols], optional) receives the column sums of dx."""
     _req_cuda(x, gamma, mean, rstd)
     cols = gamma.numel()
     x2 = x.contiguous().view(-1, cols)
@@ -109,16 +119,24 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, accumulate, dy2=None,
     dy2 = dy2.contiguous() if dy2 is not None else None
     dx_add = dx_add.contiguous() if dx_add is not None else None
     dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
+    dx2 = torch.empty(x.shape, dtype=dx2_dtype, device=x.device) if dx2_dtype is not None else None
     ws = None
-    if (dgamma is not None or dbeta is not None) and cols % 128 == 0 and cols <= 1024:
+    if (dgamma is not None or dbeta is not None or dxsum is not None) and cols % 128 == 0 and cols <= 1024:
         ws = _ln_workspace(x.device, cols)
-    _ck(_lib.load().ct_layernorm_bwd(
-        ptr(dy), dt(dy) if dy is not None else 0, ptr(dy2), dt(dy2) if dy2 is not None else 0,
-        ptr(x2), dt(x2), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx_add),
-        dt(dx_add) if dx_add is not None else 0, ptr(dx), dt(dx), ptr(dgamma), ptr(dbeta),
-        1 if accumulate else 0, ptr(ws), ws.numel() * 4 if ws is not None else 0, rows, cols, stream()),
-        "ct_layernorm_bwd")
-    return dx
+    a = _lib.LnBwdArgs()
+    a.rows, a.cols = rows, cols
+    a.dy, a.dy_dtype = ptr(dy), dt(dy) if dy is not None else 0
+    a.dy2, a.dy2_dtype = ptr(dy2), dt(dy2) if dy2 is not None else 0
+    a.x, a.x_dtype = ptr(x2), dt(x2)
+    a.gamma, a.mean, a.rstd = ptr(gamma), ptr(mean), ptr(rstd)
+    a.dx_add, a.dx_add_dtype = ptr(dx_add), dt(dx_add) if dx_add is not None else 0
+    a.dx, a.dx_dtype = ptr(dx), dt(dx)
+    a.dx2, a.dx2_dtype = ptr(dx2), dt(dx2) if dx2 is not None else 0
+    a.dgamma, a.dbeta, a.dgb_accumulate = ptr(dgamma), ptr(dbeta), 1 if accumulate else 0
+    a.dxsum, a.dxsum_accumulate = ptr(dxsum), 1 if dxsum_accumulate else 0
+    a.workspace, a.workspace_bytes = ptr(ws), ws.numel() * 4 if ws is not None else 0
+    _ck(_lib.load().ct_layernorm_bwd_ex(ctypes.byref(a), stream()), "ct_layernorm_bwd_ex")
+    return dx if dx2_dtype is None else (dx, dx2)
 
 
 # ------------------------------------------------------------------------------------------------

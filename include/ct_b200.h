@@ -45,6 +45,11 @@ int ct_version(void);
 int ct_last_error(char* buf, size_t n);
 /* 0 only if `device` is an sm_100 part (B200). */
 int ct_device_check(int device);
+/* Kernel-variant knobs for A/B measurements and tests (not needed for normal use). Names:
+ * "LN_BWD_IMPL", "ATTN_FWD_IMPL", "ATTN_BWD_IMPL", "GEMM_EPI_IMPL", "GEMM_2CTA", "CE_IMPL"; 0 = default.
+ * Initial values are read from the environment variables CT_<NAME>. */
+int ct_set_option(const char* name, int value);
+int ct_get_option(const char* name, int* value);
 
 /* ---- LayerNorm: CleanTransformer/transformer.py:61-89 (LayerNorm._mean / forward) ----------- *
  * y = gamma * (x - mean) / sqrt(mean((x-mean)^2 + eps)) + beta over the last `cols` elements.
@@ -64,6 +69,27 @@ int ct_layernorm_bwd(const void* dy, int dy_dtype, const void* dy2, int dy2_dtyp
                      const void* dx_add, int dx_add_dtype, void* dx, int dx_dtype, float* dgamma,
                      float* dbeta, int dgb_accumulate, float* workspace, size_t workspace_bytes,
                      int64_t rows, int64_t cols, void* stream);
+
+/* Extended backward: same arithmetic, plus two fused by-products of the dx pass that the pre-LN block
+ * backward (modeling_bloom.py:142-159 as differentiated by autograd) otherwise pays separate kernels for:
+ *   dx2   - a second copy of dx in another dtype (the bf16 operand of the next dgrad/wgrad GEMM);
+ *   dxsum - column sums of dx ([cols] f32): when x was produced by `residual + Linear(...)`
+ *           (modeling_bloom.py:121-122, 267-269) this is that Linear's bias gradient.
+ * workspace: >= 3 * (2 * #SMs) * cols floats for the deterministic two-stage reductions. */
+typedef struct ct_ln_bwd_args {
+  int64_t rows, cols;
+  const void* dy;  int32_t dy_dtype;      /* nullable when dy2 is given */
+  const void* dy2; int32_t dy2_dtype;     /* nullable; gradient = dy + dy2 */
+  const void* x;   int32_t x_dtype;
+  const float* gamma; const float* mean; const float* rstd;
+  const void* dx_add; int32_t dx_add_dtype; /* nullable: dx += dx_add (residual-path gradient) */
+  void* dx;  int32_t dx_dtype;
+  void* dx2; int32_t dx2_dtype;           /* nullable */
+  float* dgamma; float* dbeta; int32_t dgb_accumulate;
+  float* dxsum; int32_t dxsum_accumulate; /* nullable */
+  float* workspace; size_t workspace_bytes;
+} ct_ln_bwd_args;
+int ct_layernorm_bwd_ex(const ct_ln_bwd_args* args, void* stream);
 
 /* ---- optimizers: CleanTransformer/optimizer.py ---------------------------------------------- *
  * One vectorised kernel over a flat f32 arena (p, g, m, v all [n]).

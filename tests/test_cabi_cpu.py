@@ -37,14 +37,15 @@ def test_struct_mirrors_match_header_sizes(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "ct_b200.h"\n'
-        'int main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(ct_gemm_args), sizeof(ct_attn_args), '
+        'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ct_gemm_args), sizeof(ct_attn_args), '
         'sizeof(ct_attn_bwd_args), offsetof(ct_gemm_args, residual), offsetof(ct_attn_args, kbias2), '
-        'offsetof(ct_attn_bwd_args, delta));return 0;}\n')
+        'offsetof(ct_attn_bwd_args, delta), sizeof(ct_ln_bwd_args), offsetof(ct_ln_bwd_args, dxsum));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(_lib.GemmArgs), ctypes.sizeof(_lib.AttnArgs), ctypes.sizeof(_lib.AttnBwdArgs),
-            _lib.GemmArgs.residual.offset, _lib.AttnArgs.kbias2.offset, _lib.AttnBwdArgs.delta.offset]
+            _lib.GemmArgs.residual.offset, _lib.AttnArgs.kbias2.offset, _lib.AttnBwdArgs.delta.offset,
+            ctypes.sizeof(_lib.LnBwdArgs), _lib.LnBwdArgs.dxsum.offset]
     assert got == want
 
 

@@ -26,33 +26,52 @@ def _ops():
     return ops
 
 
-@pytest.mark.parametrize("cols", [1024, 768, 128, 24])
-def test_layernorm_fwd_bwd_vs_oracle(cols):
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("cols,rows", [(1024, 1000), (768, 1000), (128, 1000), (24, 1000), (1024, 8192), (256, 3)])
+def test_layernorm_fwd_bwd_vs_oracle(cols, rows, impl):
+    """impl 0 = default backward (row spread over cols/4 threads), 1 = warp-per-row backward."""
     from oracle import ct_oracle as O
     ops = _ops()
-    torch.manual_seed(0)
-    x = torch.randn(1000, cols, device=DEV)
-    w = torch.randn(cols, device=DEV); b = torch.randn(cols, device=DEV)
-    y, y2, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-5, out_dtype=torch.float32, out2_dtype=torch.bfloat16)
-    xr, wr, br = [t.clone().requires_grad_(True) for t in (x, w, b)]
-    ref = O.layernorm(xr, wr, br, 1e-5)
-    assert rel_err(y, ref) < 1e-5
-    assert rel_err(y2, ref) < 4e-3
-    dy = torch.randn_like(x)
-    ref.backward(dy)
-    dg = torch.empty(cols, device=DEV); db = torch.empty(cols, device=DEV)
-    extra = torch.randn_like(x)
-    dx = ops.layernorm_bwd(dy, x, w, mean, rstd, dg, db, False, dx_add=extra)
-    assert rel_err(dx - extra, xr.grad) < 1e-4
-    assert rel_err(dg, wr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
-    ops.layernorm_bwd(dy, x, w, mean, rstd, dg, db, True)  # accumulate
-    assert rel_err(dg, 2 * wr.grad) < 1e-4
-    # two incoming gradients (fp32 residual consumer + bf16 GEMM consumer)
-    dy2 = torch.randn_like(x).bfloat16()
-    dx2 = ops.layernorm_bwd(dy, x, w, mean, rstd, None, None, False, dy2=dy2)
-    xr.grad = None
-    O.layernorm(xr, w, b, 1e-5).backward(dy + dy2.float())
-    assert rel_err(dx2, xr.grad) < 1e-4
+    prev = ops.set_option("LN_BWD_IMPL", impl)
+    try:
+        torch.manual_seed(0)
+        x = torch.randn(rows, cols, device=DEV)
+        w = torch.randn(cols, device=DEV); b = torch.randn(cols, device=DEV)
+        y, y2, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-5, out_dtype=torch.float32, out2_dtype=torch.bfloat16)
+        xr, wr, br = [t.clone().requires_grad_(True) for t in (x, w, b)]
+        ref = O.layernorm(xr, wr, br, 1e-5)
+        assert rel_err(y, ref) < 1e-5
+        assert rel_err(y2, ref) < 4e-3
+        dy = torch.randn_like(x)
+        ref.backward(dy)
+        dg = torch.empty(cols, device=DEV); db = torch.empty(cols, device=DEV)
+        extra = torch.randn_like(x)
+        dx = ops.layernorm_bwd(dy, x, w, mean, rstd, dg, db, False, dx_add=extra)
+        assert rel_err(dx - extra, xr.grad) < 1e-4
+        assert rel_err(dg, wr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+        ops.layernorm_bwd(dy, x, w, mean, rstd, dg, db, True)  # accumulate
+        assert rel_err(dg, 2 * wr.grad) < 1e-4
+        # two incoming gradients (fp32 residual consumer + bf16 GEMM consumer)
+        dy2 = torch.randn_like(x).bfloat16()
+        dx2 = ops.layernorm_bwd(dy, x, w, mean, rstd, None, None, False, dy2=dy2)
+        xr.grad = None
+        O.layernorm(xr, w, b, 1e-5).backward(dy + dy2.float())
+        assert rel_err(dx2, xr.grad) < 1e-4
+        # fused by-products: low-precision copy of dx and its column sums (a bias gradient), bf16 dy
+        dyl = dy.bfloat16()
+        xr.grad = None
+        O.layernorm(xr, w, b, 1e-5).backward(dyl.float())
+        want = xr.grad + extra
+        cs = torch.full((cols,), 7.0, device=DEV)
+        dxf, dxl = ops.layernorm_bwd(dyl, x, w, mean, rstd, dg, db, False, dx_add=extra,
+                                     dx2_dtype=torch.bfloat16, dxsum=cs, dxsum_accumulate=False)
+        assert rel_err(dxf, want) < 1e-4 and dxl.dtype == torch.bfloat16 and rel_err(dxl, want) < 4e-3
+        assert torch.equal(dxl, dxf.bfloat16())
+        assert rel_err(cs, want.sum(0)) < 1e-4
+        ops.layernorm_bwd(dyl, x, w, mean, rstd, None, None, False, dx_add=extra, dxsum=cs, dxsum_accumulate=True)
+        assert rel_err(cs, 2 * want.sum(0)) < 1e-4
+    finally:
+        ops.set_option("LN_BWD_IMPL", prev)
 
 
 def test_layernorm_bert_eps_and_empty():
