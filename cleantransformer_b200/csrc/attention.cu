@@ -351,6 +351,430 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
 }
 
 // =================================================================================================
+// tcgen05 forward, v2
+// =================================================================================================
+// Same CTA shape as above (128 query rows of one (b,h), TMA warp + MMA warp + 4 softmax warps, two CTAs
+// per SM) but the softmax side was rebuilt around what the ncu capture of v1 showed (19.6 warp
+// instructions per score element, issue-bound, S read twice from TMEM):
+//   * interior tiles (no causal diagonal, no ragged edge, no masked key) take ONE pass: the whole
+//     128-wide score row is loaded into registers, the score buffer is released to the MMA warp at
+//     once (so S(j+1) = Q K(j+1)^T runs under the softmax of tile j: one TMEM score buffer is enough),
+//     and scale / bias / max / exp2 / sum run on register pairs (fma.f32x2 / add.f32x2);
+//   * the running output O lives in TMEM: P(j) V(j) accumulates into it on the tensor core and the
+//     softmax threads rescale it in place (tcgen05.ld -> mul -> tcgen05.st) only when a row maximum
+//     moved, instead of reading every P V product back into 64 registers per thread;
+//   * tiles on the causal diagonal keep the generic two-pass code but skip the 32-column chunks that
+//     lie entirely in the future of the warp's 32 rows (they are exactly -FLT_MAX for the Bloom fill).
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+// CTA-subset barrier that also ORs a predicate over the participating threads
+__device__ __forceinline__ bool bar_red_or(int id, int nthreads, bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.u32 q, %3, 0;\n"
+      "bar.red.or.pred p, %1, %2, q;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(out)
+      : "r"(id), "r"(nthreads), "r"((uint32_t)pred)
+      : "memory");
+  return out != 0;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// r <- r * sl2 + kb (only with a bias; otherwise r stays raw) ; returns max(mt, chunk max)
+template <bool HAS_KB>
+__device__ __forceinline__ float fa2_scale_max(uint32_t (&r)[32], int col0, float sl2, uint32_t kb_s, float mt) {
+  const float2 s2 = make_float2(sl2, sl2);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float2 a = make_float2(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]));
+    float2 b = make_float2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+    if constexpr (HAS_KB) {
+      const float4 k4 = lds128f(kb_s + 4 * (col0 + 4 * g));
+      a = __ffma2_rn(a, s2, make_float2(k4.x, k4.y));
+      b = __ffma2_rn(b, s2, make_float2(k4.z, k4.w));
+      r[4 * g] = __float_as_uint(a.x); r[4 * g + 1] = __float_as_uint(a.y);
+      r[4 * g + 2] = __float_as_uint(b.x); r[4 * g + 3] = __float_as_uint(b.y);
+    }
+    mt = fmaxf(mt, fmaxf(a.x, a.y));
+    mt = fmaxf(mt, fmaxf(b.x, b.y));
+  }
+  return mt;
+}
+
+// p = 2^(t - m_new) for one 32-column chunk held in registers, bf16/f16 P into the swizzled K-major tile
+template <bool HAS_KB, bool BF16>
+__device__ __forceinline__ void fa2_exp_store(const uint32_t (&r)[32], int c, float m_new, float sl2, uint32_t p_row,
+                                              int sw, float2& acc0, float2& acc1) {
+  const float2 nm = make_float2(-m_new, -m_new);
+  const float2 s2 = make_float2(sl2, sl2);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float2 a = make_float2(__uint_as_float(r[8 * g + 2 * u]), __uint_as_float(r[8 * g + 2 * u + 1]));
+      if constexpr (HAS_KB) a = __fadd2_rn(a, nm);
+      else a = __ffma2_rn(a, s2, nm);
+      v[u] = make_float2(ex2(a.x), ex2(a.y));
+    }
+    acc0 = __fadd2_rn(acc0, v[0]); acc1 = __fadd2_rn(acc1, v[1]);
+    acc0 = __fadd2_rn(acc0, v[2]); acc1 = __fadd2_rn(acc1, v[3]);
+    uint32_t w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if constexpr (BF16) {
+        w[u] = pack_bf16x2(v[u].x, v[u].y);
+      } else {
+        __half2 h = __floats2half2_rn(v[u].x, v[u].y);
+        w[u] = *reinterpret_cast<uint32_t*>(&h);
+      }
+    }
+    const int chunk = (c & 1) * 4 + g;
+    const uint32_t addr = p_row + (c >> 1) * FA_TILE + ((chunk ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                 : "memory");
+  }
+}
+
+template <bool HAS_KB, bool BF16>
+__global__ void __launch_bounds__(FA_THREADS, 2)
+    attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const AttnP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t sQ = base;
+  const uint32_t sK = base + FA_TILE;
+  const uint32_t sV = base + 3 * FA_TILE;
+  const uint32_t sP = base + 5 * FA_TILE;
+  const uint32_t bars = base + 7 * FA_TILE;
+  const uint32_t q_full = bars, k_full = bars + 8, v_full = bars + 24, kv_empty = bars + 40, s_full = bars + 56,
+                 s_free = bars + 64, p_ready = bars + 72, o_full = bars + 80, tmem_slot = bars + 88,
+                 kb_s = bars + 128;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + 7 * FA_TILE + 88);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_q_tiles = (p.Sq + 127) / 128;
+  const int q_tile = n_q_tiles - 1 - (int)(blockIdx.x % n_q_tiles);  // heavy (late) query tiles first
+  const int bh = blockIdx.x / n_q_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int q0 = q_tile * 128;
+
+  int n_kv = (p.Sk + 127) / 128;
+  if (p.causal) {
+    const bool full_sweep = p.first_valid && (q0 + p.off < p.first_valid[b]);
+    if (!full_sweep) {
+      const int last_key = min(p.Sk - 1, q0 + 127 + p.off);
+      n_kv = last_key < 0 ? 0 : last_key / 128 + 1;
+    }
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full + 8 * s, 1); mbar_init(v_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;  // columns [0,128): scores S ; [128,192): running output O
+
+  if (warp == 0) {
+    if (lane == 0 && n_kv > 0) {
+      mbar_expect_tx(q_full, FA_TILE);
+      tma_load_4d(sQ, &tmQ, q_full, 0, q0, h, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        mbar_wait(kv_empty + 8 * s, ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(k_full + 8 * s, FA_TILE);
+        tma_load_4d(sK + s * FA_TILE, &tmK, k_full + 8 * s, 0, j * 128, h, b);
+        mbar_expect_tx(v_full + 8 * s, FA_TILE);
+        tma_load_4d(sV + s * FA_TILE, &tmV, v_full + 8 * s, 0, j * 128, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_kv > 0) {
+      const uint32_t idesc_s = umma_idesc_f16(BF16 ? 1 : 0, 0, 0, 128, 128);
+      const uint32_t idesc_o = umma_idesc_f16(BF16 ? 1 : 0, 0, 1, 128, 64);
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(k_full + 8 * s, (j >> 1) & 1);
+        if (j > 0) mbar_wait(s_free, (j - 1) & 1);  // every softmax thread holds S(j-1) in registers
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem, umma_smem_desc_sw128(sQ + k * 32, 0, 1024),
+                   umma_smem_desc_sw128(sK + s * FA_TILE + k * 32, 0, 1024), idesc_s, k > 0);
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        if (j + 1 < n_kv) issue_s(j + 1);  // runs under the softmax of tile j
+        mbar_wait(p_ready, j & 1);
+        mbar_wait(v_full + 8 * s, (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16(tmem + 128, umma_smem_desc_sw128(sP + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                   umma_smem_desc_sw128(sV + s * FA_TILE + k * 2048, 64 * 128, 1024), idesc_o, (j > 0 || k > 0));
+        umma_commit(kv_empty + 8 * s);
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    // ------------------------------ softmax: one thread per query row ------------------------------
+    const int wq = warp & 3;
+    const int qr = wq * 32 + lane;  // row inside the tile == TMEM lane
+    const int i = q0 + qr;
+    const uint32_t t_s = tmem + ((uint32_t)(wq * 32) << 16);
+    const uint32_t t_o = t_s + 128;
+    const float* kb_row = HAS_KB ? p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh : nullptr;
+    float m = -INFINITY, l = 0.f;
+    const uint32_t p_row = sP + qr * 128;
+    const int sw = qr & 7;
+    const bool fill_is_ninf = p.causal_fill2 == -INFINITY;
+    float kb_next = 0.f;
+    if constexpr (HAS_KB) kb_next = (qr < p.Sk) ? __ldg(kb_row + qr) : 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int kv0 = j * 128;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // CTA-uniform tile kind
+      bool slow = (p.causal && (kv0 + 127 > q0 + p.off)) || (kv0 + 128 > p.Sk);
+      if constexpr (HAS_KB) {
+        // every thread is past o_full(j-1): all 128 finished reading the previous tile's bias
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(kb_s + 4 * qr), "f"(kb_next) : "memory");
+        slow |= bar_red_or(1, 128, kb_next < -1e30f);  // a masked key in this tile -> generic path
+        const int nj = kv0 + 128 + qr;
+        kb_next = (j + 1 < n_kv && nj < p.Sk) ? __ldg(kb_row + nj) : 0.f;
+      }
+      float m_new, alpha, lt;
+      if (!slow) {
+        // ---------------- interior tile: one pass over a register-resident score row ----------------
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        tmem_ld_32x32(t_s, r0);
+        tmem_ld_32x32(t_s + 32, r1);
+        tmem_ld_32x32(t_s + 64, r2);
+        tmem_ld_32x32(t_s + 96, r3);
+        tmem_ld_wait();
+        float mt = -INFINITY;
+        mt = fa2_scale_max<HAS_KB>(r0, 0, p.sl2, kb_s, mt);
+        mt = fa2_scale_max<HAS_KB>(r1, 32, p.sl2, kb_s, mt);
+        mt = fa2_scale_max<HAS_KB>(r2, 64, p.sl2, kb_s, mt);
+        mt = fa2_scale_max<HAS_KB>(r3, 96, p.sl2, kb_s, mt);
+        // Release the score buffer only after the last read of this tile's staged bias: S(j+1) and with it
+        // the next tile's bias staging (single smem buffer) cannot start before every thread got here.
+        tc_fence_before();
+        mbar_arrive(s_free);
+        if constexpr (!HAS_KB) mt *= p.sl2;  // sl2 > 0 (checked on the host)
+        mt = fmaxf(mt, -FLT_MAX);
+        m_new = fmaxf(m, mt);
+        alpha = ex2(m - m_new);
+        if (j > 0) {  // P(j-1) V(j-1) retired: the P tile may be overwritten, O may be rescaled
+          mbar_wait(o_full, (j - 1) & 1);
+          tc_fence_after();
+        }
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
+        fa2_exp_store<HAS_KB, BF16>(r0, 0, m_new, p.sl2, p_row, sw, acc0, acc1);
+        fa2_exp_store<HAS_KB, BF16>(r1, 1, m_new, p.sl2, p_row, sw, acc0, acc1);
+        fa2_exp_store<HAS_KB, BF16>(r2, 2, m_new, p.sl2, p_row, sw, acc0, acc1);
+        fa2_exp_store<HAS_KB, BF16>(r3, 3, m_new, p.sl2, p_row, sw, acc0, acc1);
+        lt = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+      } else {
+        // ---------------- masked tile: two passes over TMEM, per-element masking ----------------
+        int c_hi = 3;  // last 32-column chunk with a visible element for this warp's rows
+        if (p.causal && fill_is_ninf && kv0 == q0 + p.off && kv0 + 128 <= p.Sk) c_hi = wq;
+        uint32_t r[32];
+        float cur[32];
+        float mt = -INFINITY;
+        auto val = [&](float a, float kb, int jg) -> float {
+          return score2(a, p.sl2, kb, p.causal && (jg > i + p.off), p.causal_fill2, jg >= p.Sk);
+        };
+        tmem_ld_32x32(t_s, r);
+#pragma unroll 1
+        for (int c = 0; c <= c_hi; ++c) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) cur[t] = __uint_as_float(r[t]);
+          tmem_ld_32x32(t_s + (c == c_hi ? 0 : c + 1) * 32, r);  // last: first chunk of pass 2
+#pragma unroll
+          for (int t4 = 0; t4 < 8; ++t4) {
+            float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (HAS_KB) k4 = lds128f(kb_s + 4 * (c * 32 + t4 * 4));
+            const int jg = kv0 + c * 32 + t4 * 4;
+            mt = fmaxf(mt, val(cur[t4 * 4 + 0], k4.x, jg + 0));
+            mt = fmaxf(mt, val(cur[t4 * 4 + 1], k4.y, jg + 1));
+            mt = fmaxf(mt, val(cur[t4 * 4 + 2], k4.z, jg + 2));
+            mt = fmaxf(mt, val(cur[t4 * 4 + 3], k4.w, jg + 3));
+          }
+        }
+        mt = fmaxf(mt, -FLT_MAX);  // (skipped future chunks are exactly -FLT_MAX)
+        m_new = fmaxf(m, mt);
+        alpha = ex2(m - m_new);
+        if (j > 0) {
+          mbar_wait(o_full, (j - 1) & 1);
+          tc_fence_after();
+        }
+        lt = 0.f;
+#pragma unroll 1
+        for (int c = 0; c <= c_hi; ++c) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) cur[t] = __uint_as_float(r[t]);
+          if (c < c_hi) tmem_ld_32x32(t_s + (c + 1) * 32, r);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float pv[8];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int col = c * 32 + g * 8 + hh * 4;
+              float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if constexpr (HAS_KB) k4 = lds128f(kb_s + 4 * col);
+              const float kb[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float e = ex2(val(cur[g * 8 + hh * 4 + u], kb[u], kv0 + col + u) - m_new);
+                lt += e;
+                pv[hh * 4 + u] = e;
+              }
+            }
+            uint32_t w0, w1, w2, w3;
+            if constexpr (BF16) {
+              w0 = pack_bf16x2(pv[0], pv[1]); w1 = pack_bf16x2(pv[2], pv[3]);
+              w2 = pack_bf16x2(pv[4], pv[5]); w3 = pack_bf16x2(pv[6], pv[7]);
+            } else {
+              __half2 h0 = __floats2half2_rn(pv[0], pv[1]), h1 = __floats2half2_rn(pv[2], pv[3]);
+              __half2 h2 = __floats2half2_rn(pv[4], pv[5]), h3 = __floats2half2_rn(pv[6], pv[7]);
+              w0 = *reinterpret_cast<uint32_t*>(&h0); w1 = *reinterpret_cast<uint32_t*>(&h1);
+              w2 = *reinterpret_cast<uint32_t*>(&h2); w3 = *reinterpret_cast<uint32_t*>(&h3);
+            }
+            const int chunk = (c & 1) * 4 + g;
+            const uint32_t addr = p_row + (c >> 1) * FA_TILE + ((chunk ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                         : "memory");
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(s_free);  // every TMEM load of this tile has completed
+        if (c_hi < 3) {
+          // chunks entirely in the future of this warp's rows: every score is exactly -FLT_MAX, so
+          // p = 2^(-FLT_MAX - m) is 0 unless the row has seen nothing but masked keys so far (then 1)
+          const float em = ex2(-FLT_MAX - m_new);
+          uint32_t w;
+          if constexpr (BF16) {
+            w = pack_bf16x2(em, em);
+          } else {
+            __half2 hx = __floats2half2_rn(em, em);
+            w = *reinterpret_cast<uint32_t*>(&hx);
+          }
+          for (int c = c_hi + 1; c < 4; ++c) {
+            lt += 32.f * em;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int chunk = (c & 1) * 4 + g;
+              const uint32_t addr = p_row + (c >> 1) * FA_TILE + ((chunk ^ sw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(w) : "memory");
+            }
+          }
+        }
+      }
+      l = l * alpha + lt;
+      m = m_new;
+      fence_proxy_async_smem();
+      // ---- O *= alpha (in TMEM), skipped when no row maximum of this warp moved ----
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(t_o, o0);
+        tmem_ld_32x32(t_o + 32, o1);
+        tmem_ld_wait();
+        const float2 a2 = make_float2(alpha, alpha);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          float2 x = __fmul2_rn(make_float2(__uint_as_float(o0[2 * t]), __uint_as_float(o0[2 * t + 1])), a2);
+          float2 y = __fmul2_rn(make_float2(__uint_as_float(o1[2 * t]), __uint_as_float(o1[2 * t + 1])), a2);
+          o0[2 * t] = __float_as_uint(x.x); o0[2 * t + 1] = __float_as_uint(x.y);
+          o1[2 * t] = __float_as_uint(y.x); o1[2 * t + 1] = __float_as_uint(y.y);
+        }
+        tmem_st_32x32(t_o, o0);
+        tmem_st_32x32(t_o + 32, o1);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    // ---- epilogue: O / l -> merged-head layout, lse2 ----
+    float o_acc[64];
+    if (n_kv > 0) {
+      mbar_wait(o_full, (n_kv - 1) & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(t_o, o0);
+      tmem_ld_32x32(t_o + 32, o1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int t = 0; t < 32; ++t) { o_acc[t] = __uint_as_float(o0[t]); o_acc[32 + t] = __uint_as_float(o1[t]); }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 64; ++t) o_acc[t] = 0.f;
+    }
+    if (i < p.Sq) {
+      const float inv = (n_kv > 0) ? 1.f / l : 0.f;
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
+                      2 * ((int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)i * p.o_ss);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 w;
+        if constexpr (BF16) {
+          w.x = pack_bf16x2(o_acc[8 * g] * inv, o_acc[8 * g + 1] * inv);
+          w.y = pack_bf16x2(o_acc[8 * g + 2] * inv, o_acc[8 * g + 3] * inv);
+          w.z = pack_bf16x2(o_acc[8 * g + 4] * inv, o_acc[8 * g + 5] * inv);
+          w.w = pack_bf16x2(o_acc[8 * g + 6] * inv, o_acc[8 * g + 7] * inv);
+        } else {
+          __half2 h0 = __floats2half2_rn(o_acc[8 * g] * inv, o_acc[8 * g + 1] * inv);
+          __half2 h1 = __floats2half2_rn(o_acc[8 * g + 2] * inv, o_acc[8 * g + 3] * inv);
+          __half2 h2 = __floats2half2_rn(o_acc[8 * g + 4] * inv, o_acc[8 * g + 5] * inv);
+          __half2 h3 = __floats2half2_rn(o_acc[8 * g + 6] * inv, o_acc[8 * g + 7] * inv);
+          w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+          w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+        }
+        *reinterpret_cast<uint4*>(orow + 16 * g) = w;
+      }
+      if (p.lse2) p.lse2[((int64_t)b * p.H + h) * p.Sq + i] = (n_kv > 0) ? m + log2f(l) : -INFINITY;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+// =================================================================================================
 // tcgen05 backward
 // =================================================================================================
 struct AttnBwdP {
@@ -650,6 +1074,328 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
                       f4 = __uint_as_float(r[8 * g + 4]), f5 = __uint_as_float(r[8 * g + 5]),
                       f6 = __uint_as_float(r[8 * g + 6]), f7 = __uint_as_float(r[8 * g + 7]);
           if (p.fmt == 1) {
+            w.x = pack_bf16x2(f0, f1); w.y = pack_bf16x2(f2, f3); w.z = pack_bf16x2(f4, f5); w.w = pack_bf16x2(f6, f7);
+          } else {
+            __half2 x;
+            x = __floats2half2_rn(f0, f1); w.x = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f2, f3); w.y = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f4, f5); w.z = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f6, f7); w.w = *reinterpret_cast<uint32_t*>(&x);
+          }
+          *reinterpret_cast<uint4*>(row + 16 * g) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// =================================================================================================
+// tcgen05 backward, v2: same pipeline as attn_bwd_tc_kernel, leaner compute warps
+// =================================================================================================
+// The ncu capture of v1 showed 23 warp instructions per score element in the 8 compute warps (the tensor
+// pipe idles while they run). v2 keeps barriers, TMEM map and MMA schedule and rewrites the element
+// math: each warp loads its two 32-query chunks of S^T and dP^T up front (no register copies), the
+// per-query statistics are staged as -lse2 and -delta*scale so that P^T = 2^(s*sl2 + (kb - lse2)) and
+// dS^T = P^T * (dP*scale - delta*scale) are two packed fma.f32x2 + one mul.f32x2 per element pair, and
+// 32-query chunks are classified per warp: visible (no masking code), entirely in the future of the
+// warp's 32 keys on an aligned causal diagonal (no TMEM read, dS = 0), or generic (v1 arithmetic).
+template <bool BF16>
+__device__ __forceinline__ void fb2_store_pair(uint32_t sPT, uint32_t sDS, uint32_t off, const float (&pt)[8],
+                                               const float (&ds)[8]) {
+  uint32_t a[4], d[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if constexpr (BF16) {
+      a[u] = pack_bf16x2(pt[2 * u], pt[2 * u + 1]);
+      d[u] = pack_bf16x2(ds[2 * u], ds[2 * u + 1]);
+    } else {
+      __half2 x = __floats2half2_rn(pt[2 * u], pt[2 * u + 1]);
+      a[u] = *reinterpret_cast<uint32_t*>(&x);
+      x = __floats2half2_rn(ds[2 * u], ds[2 * u + 1]);
+      d[u] = *reinterpret_cast<uint32_t*>(&x);
+    }
+  }
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPT + off), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3])
+               : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3])
+               : "memory");
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(FB_THREADS, 1)
+    attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                        const AttnBwdP bp) {
+  const AttnP& p = bp.f;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t sK = base, sV = base + FA_TILE;
+  const uint32_t sQ = base + 2 * FA_TILE;   // 2 stages, each Q then dO
+  const uint32_t sPT = base + 6 * FA_TILE;  // 2 panels
+  const uint32_t sDS = base + 8 * FA_TILE;  // 2 panels
+  const uint32_t bars = base + 10 * FA_TILE;
+  const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 24, sdp_full = bars + 40,
+                 pds_ready = bars + 48, dq_full = bars + 56, dkv_full = bars + 64, tmem_slot = bars + 72,
+                 lse_s = bars + 128, del_s = bars + 640;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + 10 * FA_TILE + 72);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_kv_tiles = (p.Sk + 127) / 128;
+  const int kv_tile = blockIdx.x % n_kv_tiles;
+  const int bh = blockIdx.x / n_kv_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int kv0 = kv_tile * 128;
+  const int n_q_tiles = (p.Sq + 127) / 128;
+  int i_start = 0;
+  if (p.causal) {
+    const bool full_sweep = p.first_valid && (p.first_valid[b] > p.off);
+    if (!full_sweep) i_start = max(0, (kv0 - p.off) / 128);
+  }
+  const int n_it = max(0, n_q_tiles - i_start);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full + 8 * s, 1); mbar_init(qdo_empty + 8 * s, 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_ready, 256);
+    mbar_init(dq_full, 1);
+    mbar_init(dkv_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t T_ST = tmem, T_DPT = tmem + 128, T_DV = tmem + 256, T_DK = tmem + 320, T_DQ = tmem + 384;
+
+  if (warp == 0) {
+    if (lane == 0 && n_it > 0) {
+      mbar_expect_tx(kv_full, 2 * FA_TILE);
+      tma_load_4d(sK, &tmK, kv_full, 0, kv0, h, b);
+      tma_load_4d(sV, &tmV, kv_full, 0, kv0, h, b);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1, q0 = (i_start + it) * 128;
+        mbar_wait(qdo_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(qdo_full + 8 * s, 2 * FA_TILE);
+        tma_load_4d(sQ + s * 2 * FA_TILE, &tmQ, qdo_full + 8 * s, 0, q0, h, b);
+        tma_load_4d(sQ + s * 2 * FA_TILE + FA_TILE, &tmDO, qdo_full + 8 * s, 0, q0, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_it > 0) {
+      const uint32_t idesc_kk = umma_idesc_f16(BF16 ? 1 : 0, 0, 0, 128, 128);  // S^T, dP^T
+      const uint32_t idesc_km = umma_idesc_f16(BF16 ? 1 : 0, 0, 1, 128, 64);   // dV, dK
+      const uint32_t idesc_mm = umma_idesc_f16(BF16 ? 1 : 0, 1, 1, 128, 64);   // dQ
+      auto issue_sdp = [&](int it) {
+        const int s = it & 1;
+        const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
+        mbar_wait(qdo_full + 8 * s, (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // S^T[kv, q] = K[kv, d] . Q[q, d]
+          umma_f16(T_ST, umma_smem_desc_sw128(sK + k * 32, 0, 1024), umma_smem_desc_sw128(q + k * 32, 0, 1024),
+                   idesc_kk, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dP^T[kv, q] = V[kv, d] . dO[q, d]
+          umma_f16(T_DPT, umma_smem_desc_sw128(sV + k * 32, 0, 1024),
+                   umma_smem_desc_sw128(d_o + k * 32, 0, 1024), idesc_kk, k > 0);
+        umma_commit(sdp_full);
+      };
+      mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
+        mbar_wait(pds_ready, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ[q, d] = dS[q, kv] . K[kv, d]  (A MN-major view of dS^T)
+          umma_f16(T_DQ, umma_smem_desc_sw128(sDS + k * 2048, FA_TILE, 1024),
+                   umma_smem_desc_sw128(sK + k * 2048, 64 * 128, 1024), idesc_mm, k > 0);
+        umma_commit(dq_full);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV[kv, d] += P^T[kv, q] . dO[q, d]   (B MN-major: rows = q)
+          umma_f16(T_DV, umma_smem_desc_sw128(sPT + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                   umma_smem_desc_sw128(d_o + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dK[kv, d] += dS^T[kv, q] . Q[q, d]
+          umma_f16(T_DK, umma_smem_desc_sw128(sDS + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                   umma_smem_desc_sw128(q + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
+        umma_commit(qdo_empty + 8 * s);
+        if (it + 1 < n_it) issue_sdp(it + 1);
+      }
+      umma_commit(dkv_full);
+    }
+  } else {
+    const int wq = warp & 3;
+    const int rr = wq * 32 + lane;   // key row inside the tile (S^T) / query row (dQ)
+    const int hf = (warp - 2) >> 2;  // which pair of 32-query chunks this warp owns
+    const int jg = kv0 + rr;
+    const uint32_t t_lane = (uint32_t)(wq * 32) << 16;
+    const float kb = (p.kbias2 && jg < p.Sk)
+                         ? __ldg(p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh + jg) : 0.f;
+    const bool key_oob = jg >= p.Sk;
+    // generic arithmetic for the whole warp when a key is masked (the reference's finite fill matters on
+    // fully masked query rows) or the key tile is ragged
+    const bool warp_generic = __any_sync(0xffffffffu, kb < -1e30f) || (kv0 + 128 > p.Sk);
+    const bool fill_is_ninf = p.causal_fill2 == -INFINITY;
+    const float* lse_bh = p.lse2 + ((int64_t)b * p.H + h) * p.Sq;
+    const float* del_bh = bp.delta + ((int64_t)b * p.H + h) * p.Sq;
+    const int sw = rr & 7;
+    // per-query statistics of the current query tile, staged as -lse2 and -delta*scale
+    float nlse_next = -INFINITY, ndel_next = 0.f;
+    if (hf == 0 && n_it > 0 && i_start * 128 + rr < p.Sq) {
+      nlse_next = -__ldg(lse_bh + i_start * 128 + rr);
+      ndel_next = -__ldg(del_bh + i_start * 128 + rr) * p.scale;
+    }
+    const float2 sl2v = make_float2(p.sl2, p.sl2), scv = make_float2(p.scale, p.scale), kbv = make_float2(kb, kb);
+
+    // one 32-query chunk c of this thread's key row; kind 0 = visible, 1 = future, 2 = generic
+    auto chunk = [&](const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c, int kind, int q0) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float pt[8], ds[8];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int col = c * 32 + g * 8 + hh * 4;
+          const float4 nl = lds128f(lse_s + 4 * col);
+          const float4 nd = lds128f(del_s + 4 * col);
+          const float nls[4] = {nl.x, nl.y, nl.z, nl.w};
+          const float nds[4] = {nd.x, nd.y, nd.z, nd.w};
+          if (kind == 0) {
+#pragma unroll
+            for (int u2 = 0; u2 < 2; ++u2) {
+              const int e = g * 8 + hh * 4 + 2 * u2;
+              const float2 add = __fadd2_rn(kbv, make_float2(nls[2 * u2], nls[2 * u2 + 1]));
+              const float2 t = __ffma2_rn(make_float2(__uint_as_float(rs[e]), __uint_as_float(rs[e + 1])), sl2v, add);
+              const float2 pe = make_float2(ex2(t.x), ex2(t.y));
+              const float2 w = __ffma2_rn(make_float2(__uint_as_float(rd[e]), __uint_as_float(rd[e + 1])), scv,
+                                          make_float2(nds[2 * u2], nds[2 * u2 + 1]));
+              const float2 d2 = __fmul2_rn(pe, w);
+              pt[hh * 4 + 2 * u2] = pe.x; pt[hh * 4 + 2 * u2 + 1] = pe.y;
+              ds[hh * 4 + 2 * u2] = d2.x; ds[hh * 4 + 2 * u2 + 1] = d2.y;
+            }
+          } else if (kind == 1) {
+            // causally masked for every key of this warp: the score is the (clamped) fill, a constant
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              pt[hh * 4 + u] = ex2(-FLT_MAX + nls[u]);
+              ds[hh * 4 + u] = 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = g * 8 + hh * 4 + u;
+              const int qg = q0 + col + u;
+              const bool fut = p.causal && (jg > qg + p.off);
+              const float v = score2(__uint_as_float(rs[e]), p.sl2, kb, fut, p.causal_fill2, false);
+              float pe = ex2(v + nls[u]);
+              if (key_oob) pe = 0.f;
+              pt[hh * 4 + u] = pe;
+              // a causally masked score is a constant in the reference (modeling_gpt.py:89 `w*b`,
+              // modeling_bloom.py:108 masked_fill): P still feeds dV, but no gradient reaches q.k
+              ds[hh * 4 + u] = fut ? 0.f : pe * fmaf(__uint_as_float(rd[e]), p.scale, nds[u]);
+            }
+          }
+        }
+        const int ch = (c & 1) * 4 + g;
+        fb2_store_pair<BF16>(sPT, sDS, rr * 128 + (c >> 1) * FA_TILE + ((ch ^ sw) << 4), pt, ds);
+      }
+    };
+
+    for (int it = 0; it < n_it; ++it) {
+      const int q0 = (i_start + it) * 128;
+      mbar_wait(sdp_full, it & 1);
+      tc_fence_after();
+      // all 256 threads are past pds_ready(it-1): nobody still reads the previous tile's statistics
+      if (hf == 0) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(lse_s + 4 * rr), "f"(nlse_next) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(del_s + 4 * rr), "f"(ndel_next) : "memory");
+      }
+      bar_sync_named(1, 256);
+      if (hf == 0) {
+        const int nq = q0 + 128 + rr;
+        const bool ok = (it + 1 < n_it) && nq < p.Sq;
+        nlse_next = ok ? -__ldg(lse_bh + nq) : -INFINITY;
+        ndel_next = ok ? -__ldg(del_bh + nq) * p.scale : 0.f;
+      }
+      // chunk kinds (warp-uniform)
+      const bool touches_diag = p.causal && (kv0 + 127 > q0 + p.off);
+      const bool aligned_diag = touches_diag && fill_is_ninf && (kv0 == q0 + p.off) && !warp_generic;
+      int kind0, kind1;
+      const int c0 = 2 * hf, c1 = 2 * hf + 1;
+      if (warp_generic || (touches_diag && !aligned_diag)) {
+        kind0 = kind1 = 2;
+      } else if (aligned_diag) {
+        // key row 32*wq+l vs queries 32*c..32*c+31: c < wq entirely future, c > wq entirely visible
+        kind0 = c0 < wq ? 1 : (c0 > wq ? 0 : 2);
+        kind1 = c1 < wq ? 1 : (c1 > wq ? 0 : 2);
+      } else {
+        kind0 = kind1 = 0;
+      }
+      uint32_t rs0[32], rd0[32], rs1[32], rd1[32];
+      if (kind0 != 1) { tmem_ld_32x32(T_ST + t_lane + c0 * 32, rs0); tmem_ld_32x32(T_DPT + t_lane + c0 * 32, rd0); }
+      if (kind1 != 1) { tmem_ld_32x32(T_ST + t_lane + c1 * 32, rs1); tmem_ld_32x32(T_DPT + t_lane + c1 * 32, rd1); }
+      tmem_ld_wait();
+      chunk(rs0, rd0, c0, kind0, q0);
+      chunk(rs1, rd1, c1, kind1, q0);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_ready);
+      // ---- dQ tile: this thread owns query row (q0 + rr), columns [32*hf, 32*hf + 32) of d ----
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+      const int qi = q0 + rr;
+      {
+        uint32_t r[32];
+        tmem_ld_32x32(T_DQ + t_lane + hf * 32, r);
+        tmem_ld_wait();
+        if (qi < p.Sq) {
+          float* dst = bp.dq_accum + (((int64_t)b * p.Sq + qi) * p.H + h) * 64 + hf * 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g),
+                         "f"(__uint_as_float(r[4 * g])), "f"(__uint_as_float(r[4 * g + 1])),
+                         "f"(__uint_as_float(r[4 * g + 2])), "f"(__uint_as_float(r[4 * g + 3]))
+                         : "memory");
+        }
+      }
+      tc_fence_before();
+    }
+    // ---- dK / dV for this key row: 32 of the 64 head-dim columns per thread ----
+    if (n_it > 0) {
+      mbar_wait(dkv_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint32_t r[32];
+      if (n_it > 0) {
+        tmem_ld_32x32((which == 0 ? T_DV : T_DK) + t_lane + hf * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) r[t] = 0u;
+      }
+      if (!key_oob) {
+        void* basep = which == 0 ? bp.dv : bp.dk;
+        const int64_t eo = which == 0
+            ? (int64_t)b * bp.dv_sb + (int64_t)h * bp.dv_sh + (int64_t)jg * bp.dv_ss
+            : (int64_t)b * bp.dk_sb + (int64_t)h * bp.dk_sh + (int64_t)jg * bp.dk_ss;
+        uint8_t* row = reinterpret_cast<uint8_t*>(basep) + 2 * (eo + hf * 32);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          const float f0 = __uint_as_float(r[8 * g]), f1 = __uint_as_float(r[8 * g + 1]),
+                      f2 = __uint_as_float(r[8 * g + 2]), f3 = __uint_as_float(r[8 * g + 3]),
+                      f4 = __uint_as_float(r[8 * g + 4]), f5 = __uint_as_float(r[8 * g + 5]),
+                      f6 = __uint_as_float(r[8 * g + 6]), f7 = __uint_as_float(r[8 * g + 7]);
+          if constexpr (BF16) {
             w.x = pack_bf16x2(f0, f1); w.y = pack_bf16x2(f2, f3); w.z = pack_bf16x2(f4, f5); w.w = pack_bf16x2(f6, f7);
           } else {
             __half2 x;
@@ -977,15 +1723,38 @@ __global__ void __launch_bounds__(256)
     if (mask_dtype == 4) return (float)reinterpret_cast<const int*>(mask)[(int64_t)b * Sk + j];
     return reinterpret_cast<const float*>(mask)[(int64_t)b * Sk + j];
   };
-  if (threadIdx.x == 0) {
-    int run = 0, first = Sk;
-    for (int j = 0; j < Sk; ++j) {  // serial scan: Sk <= a few thousand, once per forward
+  {
+    // inclusive scan of the mask row: each thread owns a contiguous segment, segment totals are scanned
+    // with warp shuffles (256 threads = 8 warps), first valid key = block-wide min
+    __shared__ int wsum_s[8];
+    const int seg = (Sk + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int j0 = min(Sk, (int)threadIdx.x * seg), j1 = min(Sk, j0 + seg);
+    int tot = 0, first = Sk;
+    for (int j = j0; j < j1; ++j) {
       const int mv = (int)mval(j);
-      run += mv;
-      pos_s[j] = run - 1;
+      tot += mv;
       if (mv != 0 && first == Sk) first = j;
     }
-    first_s = first;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    if (threadIdx.x == 0) first_s = Sk;
+    __syncthreads();
+    if (lane == 31) wsum_s[wid] = inc;
+    if (lane == 0) atomicMin(&first_s, first);
+    __syncthreads();
+    int run = inc - tot;  // exclusive prefix inside the warp
+    for (int w = 0; w < wid; ++w) run += wsum_s[w];
+    for (int j = j0; j < j1; ++j) {
+      run += (int)mval(j);
+      pos_s[j] = run - 1;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0 && first_valid) first_valid[b] = first_s;
@@ -1090,10 +1859,24 @@ extern "C" int ct_attn_fwd(const ct_attn_args* args, void* stream) {
     static bool attr = false;
     if (!attr) {
       CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
       attr = true;
     }
     const int64_t grid = (int64_t)a.B * a.H * ((a.Sq + 127) / 128);
-    attn_fwd_tc_kernel<<<(unsigned)grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, p);
+    // ATTN_FWD_IMPL: 0 = auto (v2: register-resident score rows, O in TMEM), 1 = v1 (two TMEM passes)
+    const bool v2 = option(OPT_ATTN_FWD_IMPL) != 1 && a.scale > 0.f;
+    if (v2) {
+      const bool kb = a.kbias2 != nullptr, bf = p.fmt == 1;
+      if (kb && bf) attn_fwd_tc2_kernel<true, true><<<(unsigned)grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, p);
+      else if (kb) attn_fwd_tc2_kernel<true, false><<<(unsigned)grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, p);
+      else if (bf) attn_fwd_tc2_kernel<false, true><<<(unsigned)grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, p);
+      else attn_fwd_tc2_kernel<false, false><<<(unsigned)grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, p);
+    } else {
+      attn_fwd_tc_kernel<<<(unsigned)grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, p);
+    }
     CT_LAUNCH_OK();
     return 0;
   }
@@ -1160,10 +1943,18 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     static bool attr = false;
     if (!attr) {
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
       attr = true;
     }
     const int64_t grid = (int64_t)a.B * a.H * ((a.Sk + 127) / 128);
-    attn_bwd_tc_kernel<<<(unsigned)grid, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
+    // ATTN_BWD_IMPL: 0 = auto (v2 compute warps), 1 = v1
+    if (option(OPT_ATTN_BWD_IMPL) != 1) {
+      if (fmt == 1) attn_bwd_tc2_kernel<true><<<(unsigned)grid, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
+      else attn_bwd_tc2_kernel<false><<<(unsigned)grid, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
+    } else {
+      attn_bwd_tc_kernel<<<(unsigned)grid, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
+    }
     CT_LAUNCH_OK();
     const int64_t n = (int64_t)a.B * a.Sq * a.H * 64 / 8;
     int64_t blocks = (n + 255) / 256;

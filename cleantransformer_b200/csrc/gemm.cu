@@ -320,6 +320,111 @@ __device__ __forceinline__ void epi_block32(const EpiParams& e, int m_base, int 
   stage_store32(stage, lane, t, e.c_dtype, e.C, e.ldc, m_base, e.M, n0);
 }
 
+// ---- specialised epilogues -------------------------------------------------------------------------
+// The generic epilogue above decides dtype / activation / operand set per chunk at run time and
+// measured ~23 warp instructions per output element on the two epilogue-bound layer GEMMs (FFN1 forward:
+// bias + GELU + saved pre-activation; FFN2 dgrad: x GELU'(pre)). The hot Bloom / GPT-2 combinations get
+// compile-time variants: packed f32x2 math, no register copies (the TMEM loads ping-pong between two
+// register sets), the per-element operand (residual / saved pre-activation) prefetched one chunk ahead.
+enum : int { EPIK_GENERIC = 0, EPIK_BF16 = 1, EPIK_GELU_PRE = 2, EPIK_RES_F32 = 3, EPIK_ACTGRAD = 4 };
+
+__device__ __forceinline__ float2 gelu_tanh2(float2 x) {
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 pp = __ffma2_rn(x2, make_float2(0.79788456f * 0.044715f, 0.79788456f * 0.044715f),
+                               make_float2(0.79788456f, 0.79788456f));
+  const float2 u = __fmul2_rn(x, pp);
+  const float2 th = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, th, hx);
+}
+// d gelu_tanh / dx at x (modeling_bloom.py:348-363)
+__device__ __forceinline__ float2 gelu_tanh_grad2(float2 x) {
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 pp = __ffma2_rn(x2, make_float2(0.79788456f * 0.044715f, 0.79788456f * 0.044715f),
+                               make_float2(0.79788456f, 0.79788456f));
+  const float2 u = __fmul2_rn(x, pp);
+  const float2 th = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+  const float2 om = __ffma2_rn(make_float2(-th.x, -th.y), th, make_float2(1.f, 1.f));            // 1 - t^2
+  const float2 q = __ffma2_rn(x2, make_float2(0.1070322243f, 0.1070322243f), make_float2(0.79788456f, 0.79788456f));
+  const float2 w = __fmul2_rn(__fmul2_rn(x, make_float2(0.5f, 0.5f)), om);                        // 0.5 x (1 - t^2)
+  const float2 hh = __ffma2_rn(th, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));            // 0.5 (1 + t)
+  return __ffma2_rn(w, q, hh);
+}
+
+// per-element operand of one chunk (row m, columns [n0, n0+32)): f32 residual = 8 x 16 B, bf16 saved
+// pre-activation = 4 x 16 B
+template <int EPIK>
+__device__ __forceinline__ void epi_fast_aux_load(const EpiParams& e, int m, int n0, uint4 (&x)[8]) {
+  if constexpr (EPIK == EPIK_RES_F32) {
+    if (m < e.M) {
+      const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(e.residual) + (int64_t)m * e.ldr + n0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = q[i];
+    }
+  } else if constexpr (EPIK == EPIK_ACTGRAD) {
+    if (m < e.M) {
+      const uint4* q =
+          reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.actgrad_src) + (int64_t)m * e.ldg + n0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = q[i];
+    }
+  }
+}
+
+template <int EPIK>
+__device__ __forceinline__ void epi_fast_chunk(const EpiParams& e, int m_base, int lane, int n0, int n_in_tile,
+                                               const uint32_t (&r)[32], const uint4 (&x)[8], uint32_t stage,
+                                               uint32_t bias_s) {
+  float t[32];
+  if (e.bias) {  // CTA-uniform
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 bv;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bv.x), "=f"(bv.y), "=f"(bv.z), "=f"(bv.w)
+                   : "r"(bias_s + 4 * (n_in_tile + 4 * i)));
+      const float2 a = __fadd2_rn(make_float2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
+                                  make_float2(bv.x, bv.y));
+      const float2 c = __fadd2_rn(make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])),
+                                  make_float2(bv.z, bv.w));
+      t[4 * i] = a.x; t[4 * i + 1] = a.y; t[4 * i + 2] = c.x; t[4 * i + 3] = c.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(r[j]);
+  }
+  if constexpr (EPIK == EPIK_GELU_PRE) {
+    stage_store32(stage, lane, t, DT_BF16, e.preact, e.ldp, m_base, e.M, n0);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float2 y = gelu_tanh2(make_float2(t[2 * j], t[2 * j + 1]));
+      t[2 * j] = y.x; t[2 * j + 1] = y.y;
+    }
+  }
+  if constexpr (EPIK == EPIK_ACTGRAD) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t w[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 g = gelu_tanh_grad2(unpack_bf16x2(w[k]));
+        const float2 y = __fmul2_rn(make_float2(t[8 * i + 2 * k], t[8 * i + 2 * k + 1]), g);
+        t[8 * i + 2 * k] = y.x; t[8 * i + 2 * k + 1] = y.y;
+      }
+    }
+  }
+  if constexpr (EPIK == EPIK_RES_F32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 a = __fadd2_rn(make_float2(t[4 * i], t[4 * i + 1]),
+                                  make_float2(__uint_as_float(x[i].x), __uint_as_float(x[i].y)));
+      const float2 c = __fadd2_rn(make_float2(t[4 * i + 2], t[4 * i + 3]),
+                                  make_float2(__uint_as_float(x[i].z), __uint_as_float(x[i].w)));
+      t[4 * i] = a.x; t[4 * i + 1] = a.y; t[4 * i + 2] = c.x; t[4 * i + 3] = c.y;
+    }
+  }
+  stage_store32(stage, lane, t, EPIK == EPIK_RES_F32 ? DT_F32 : DT_BF16, e.C, e.ldc, m_base, e.M, n0);
+}
+
 // =================================================================================================
 // tcgen05 kernel
 // =================================================================================================
@@ -569,6 +674,7 @@ constexpr int STAGES2 = 6;
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + (BN2 / 2) * BK * 2;  // 32 KB per CTA
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 256 + EPI_WARPS * EPI_STAGE_BYTES + 2 * 256 * 4;
 
+template <int EPIK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                              const TcParams p, const EpiParams e) {
@@ -736,18 +842,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4 * et), "f"(bv) : "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      if (kb1 > kb0) {
-        const float aux[32] = {};
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + hf * 32, r);
+      if constexpr (EPIK == EPIK_GENERIC) {
+        if (kb1 > kb0) {
+          const float aux[32] = {};
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + hf * 32, r);
 #pragma unroll 1
-        for (int c = hf; c < BN / 32; c += 2) {
-          float t[32];
-          tmem_ld_wait();
+          for (int c = hf; c < BN / 32; c += 2) {
+            float t[32];
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(r[j]);
-          if (c + 2 < BN / 32) tmem_ld_32x32(t_row + (c + 2) * 32, r);
-          epi_block32(e, m_base, lane, n_blk * BN + c * 32, c * 32, t, aux, AUX_NONE, split == 0, stage, bias_s);
+            for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(r[j]);
+            if (c + 2 < BN / 32) tmem_ld_32x32(t_row + (c + 2) * 32, r);
+            epi_block32(e, m_base, lane, n_blk * BN + c * 32, c * 32, t, aux, AUX_NONE, split == 0, stage, bias_s);
+          }
+        }
+      } else {
+        // specialised: 4 chunks per warp, TMEM loads and per-element operand loads one chunk ahead,
+        // alternating between two register sets (fully unrolled: no copies)
+        constexpr int NCH = BN / 64;
+        uint32_t ra[32], rb[32];
+        uint4 xa[8], xb[8];
+        const int m = m_base + lane;
+        const int nt0 = n_blk * BN;
+        tmem_ld_32x32(t_row + hf * 32, ra);
+        if (nt0 + hf * 32 < e.N) epi_fast_aux_load<EPIK>(e, m, nt0 + hf * 32, xa);
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const int c = hf + 2 * k;
+          tmem_ld_wait();
+          if (k + 1 < NCH) {
+            tmem_ld_32x32(t_row + (c + 2) * 32, (k & 1) ? ra : rb);
+            if (nt0 + (c + 2) * 32 < e.N) epi_fast_aux_load<EPIK>(e, m, nt0 + (c + 2) * 32, (k & 1) ? xa : xb);
+          }
+          if (nt0 + c * 32 < e.N)  // warp-uniform (N % 32 == 0 on this path)
+            epi_fast_chunk<EPIK>(e, m_base, lane, nt0 + c * 32, c * 32, (k & 1) ? rb : ra, (k & 1) ? xb : xa, stage,
+                                 bias_s);
         }
       }
       tc_fence_before();
@@ -856,6 +986,37 @@ static int launch_tc(const ct_gemm_args& a, const EpiParams& e, int split_k, cud
 }
 
 
+template <int EPIK>
+static int launch_2cta_kind(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, const EpiParams& e,
+                            int pairs, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CT_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<EPIK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    SMEM2_BYTES));
+    attr_set = true;
+  }
+  gemm_tcgen05_2cta_kernel<EPIK><<<2 * pairs, GEMM_THREADS, SMEM2_BYTES, st>>>(tmA, tmB, p, e);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+// which compile-time epilogue covers this call (EPIK_GENERIC when none does)
+static int pick_epi_kind(const ct_gemm_args& a, const EpiParams& e) {
+  if (option(OPT_GEMM_EPI_IMPL) == 1) return EPIK_GENERIC;
+  if (!e.vec_ok || e.atomic_out || a.alpha != 1.f || a.beta != 0.f || (a.N % 32) != 0) return EPIK_GENERIC;
+  const bool plain = a.act == ACT_NONE && !a.preact && !a.actgrad_src && !a.residual;
+  if (plain && a.c_dtype == DT_BF16 && a.ab_dtype == DT_BF16) return EPIK_BF16;
+  if (a.act == ACT_GELU_TANH && a.preact && a.preact_dtype == DT_BF16 && a.c_dtype == DT_BF16 && !a.actgrad_src &&
+      !a.residual)
+    return EPIK_GELU_PRE;
+  if (a.act == ACT_NONE && !a.preact && !a.actgrad_src && a.residual && a.res_dtype == DT_F32 && a.c_dtype == DT_F32)
+    return EPIK_RES_F32;
+  if (a.act == ACT_NONE && !a.preact && a.actgrad_src && a.actgrad_dtype == DT_BF16 && a.actgrad_act == ACT_GELU_TANH &&
+      !a.residual && a.c_dtype == DT_BF16)
+    return EPIK_ACTGRAD;
+  return EPIK_GENERIC;
+}
+
 static int launch_tc_2cta(const ct_gemm_args& a, const EpiParams& e, int split_k, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   {
@@ -878,19 +1039,17 @@ static int launch_tc_2cta(const ct_gemm_args& a, const EpiParams& e, int split_k
   p.fmt = a.ab_dtype == DT_BF16 ? 1 : 0;
   p.split_k = split_k;
   p.group_m = 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CT_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    SMEM2_BYTES));
-    attr_set = true;
-  }
   const int m_tiles = (a.M + 255) / 256, n_tiles = (a.N + BN2 - 1) / BN2;
   int64_t work = (int64_t)m_tiles * n_tiles * split_k;
   int pairs = sm_count() / 2;
   if (work < pairs) pairs = (int)work;
-  gemm_tcgen05_2cta_kernel<<<2 * pairs, GEMM_THREADS, SMEM2_BYTES, st>>>(tmA, tmB, p, e);
-  CT_LAUNCH_OK();
-  return 0;
+  switch (split_k == 1 ? pick_epi_kind(a, e) : EPIK_GENERIC) {
+    case EPIK_BF16: return launch_2cta_kind<EPIK_BF16>(tmA, tmB, p, e, pairs, st);
+    case EPIK_GELU_PRE: return launch_2cta_kind<EPIK_GELU_PRE>(tmA, tmB, p, e, pairs, st);
+    case EPIK_RES_F32: return launch_2cta_kind<EPIK_RES_F32>(tmA, tmB, p, e, pairs, st);
+    case EPIK_ACTGRAD: return launch_2cta_kind<EPIK_ACTGRAD>(tmA, tmB, p, e, pairs, st);
+    default: return launch_2cta_kind<EPIK_GENERIC>(tmA, tmB, p, e, pairs, st);
+  }
 }
 
 }  // namespace ct

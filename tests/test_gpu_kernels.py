@@ -26,7 +26,7 @@ def _ops():
     return ops
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1], ids=["v2", "v1"])
 @pytest.mark.parametrize("cols,rows", [(1024, 1000), (768, 1000), (128, 1000), (24, 1000), (1024, 8192), (256, 3)])
 def test_layernorm_fwd_bwd_vs_oracle(cols, rows, impl):
     """impl 0 = default backward (row spread over cols/4 threads), 1 = warp-per-row backward."""
@@ -177,6 +177,40 @@ def test_linear_epilogues_vs_oracle(act, name):
     assert rel_err(yc, O.conv1d(x.float(), wc.float(), b)) < 1e-5
 
 
+@pytest.mark.parametrize("variant", ["v1", "v2"])
+@pytest.mark.parametrize("M,N,K", [(1024, 512, 256), (520, 1056, 320), (2048, 1024, 1024)])
+def test_gemm_specialised_epilogues_vs_oracle(M, N, K, variant):
+    """The compile-time epilogue kinds of the 2-CTA kernel (v2; GEMM_EPI_IMPL=0) and the generic run-time
+    epilogue (v1) on the four hot combinations: bias->bf16, bias+GELU+saved pre-activation, bias+f32
+    residual -> f32, dgrad x GELU'(pre). M=520 exercises ragged row tiles, N=1056 a ragged 256-column tile."""
+    from oracle import ct_oracle as O
+    ops = _ops()
+    prev = ops.set_option("GEMM_EPI_IMPL", 1 if variant == "v1" else 0)
+    try:
+        torch.manual_seed(11)
+        x = torch.randn(M, K, device=DEV).bfloat16(); w = (torch.randn(N, K, device=DEV) * 0.1).bfloat16()
+        b = torch.randn(N, device=DEV); res = torch.randn(M, N, device=DEV)
+        t = O.linear(x.float(), w.float(), b)
+        y, _ = ops.linear_fwd(x, w, b)                                            # bias -> bf16
+        assert rel_err(y, t) < 4e-3
+        y0, _ = ops.linear_fwd(x, w, None)                                        # no bias -> bf16
+        assert rel_err(y0, x.float() @ w.float().t()) < 4e-3
+        g, pre = ops.linear_fwd(x, w, b, act=ops.ACT_GELU_TANH, save_preact=True)  # bias + GELU + pre-activation
+        assert rel_err(pre, t) < 4e-3 and rel_err(g, O.activation(t, "gelu_new")) < 4e-3
+        r, _ = ops.linear_fwd(x, w, b, residual=res, out_dtype=torch.float32)      # bias + residual -> f32
+        assert rel_err(r, t + res) < 1e-5
+        r0, _ = ops.linear_fwd(x, w, None, residual=res, out_dtype=torch.float32)
+        assert rel_err(r0, x.float() @ w.float().t() + res) < 1e-5
+        dy = torch.randn(M, K, device=DEV).bfloat16()                              # dgrad [M,K]x[K->N] * GELU'(pre)
+        w2 = (torch.randn(K, N, device=DEV) * 0.1).bfloat16()                      # Linear N -> K: weight [K, N]
+        dx = ops.linear_dgrad(dy, w2, actgrad_src=pre, actgrad_act=ops.ACT_GELU_TANH)
+        pr = pre.float().clone().requires_grad_(True)
+        O.activation(pr, "gelu_new").backward(dy.float() @ w2.float())
+        assert rel_err(dx, pr.grad) < 5e-3
+    finally:
+        ops.set_option("GEMM_EPI_IMPL", prev)
+
+
 def test_wgrad_splitk_accumulate_and_bias():
     ops = _ops()
     torch.manual_seed(5)
@@ -234,15 +268,46 @@ ATT_CASES = [
     (3, 4, 300, 300, 64, True, 1, "left", -1e4, 1),         # GPT: -1e4 replace + finfo.min, left padding
     (2, 4, 512, 512, 64, False, 2, "right", -FLT_MAX, 1),   # BERT additive mask
     (2, 4, 128, 384, 64, True, 1, "none", -1e4, 1),         # prefill chunk against a longer cache
+    (2, 4, 640, 640, 64, True, 0, "none", -FLT_MAX, 1),     # Bloom, no padding: interior + aligned-diagonal tiles
+    (2, 4, 512, 512, 64, True, None, "none", -FLT_MAX, 1),  # causal, no per-key bias at all
+    (2, 4, 384, 384, 64, True, None, "none", -1e4, 1),      # causal with the finite GPT fill, no bias
+    (2, 2, 256, 640, 64, True, 0, "none", -FLT_MAX, 1),     # Sq < Sk: diagonal offset by 384 (aligned)
+    (2, 2, 200, 440, 64, True, 0, "right", -FLT_MAX, 1),    # diagonal offset (240) not a multiple of 128
 ]
+# kernel variants of the tcgen05 path: "v2" = defaults, "v1" = first-generation softmax / backward math
+ATT_PARAMS = [c + ("-",) for c in ATT_CASES if c[-1] == 2] + \
+             [c + (v,) for c in ATT_CASES if c[-1] == 1 for v in ("v1", "v2")]
 
 
-@pytest.mark.parametrize("B,H,Sq,Sk,D,causal,mode,pad,cfill,impl", ATT_CASES)
-def test_attention_fwd_bwd_vs_oracle(B, H, Sq, Sk, D, causal, mode, pad, cfill, impl):
+class _AttnVariant:
+    def __init__(self, variant):
+        self.v = {"v1": 1, "v2": 0}.get(variant)
+
+    def __enter__(self):
+        if self.v is not None:
+            ops = _ops()
+            self.prev = (ops.set_option("ATTN_FWD_IMPL", self.v), ops.set_option("ATTN_BWD_IMPL", self.v))
+
+    def __exit__(self, *exc):
+        if self.v is not None:
+            ops = _ops()
+            ops.set_option("ATTN_FWD_IMPL", self.prev[0]); ops.set_option("ATTN_BWD_IMPL", self.prev[1])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("B,H,Sq,Sk,D,causal,mode,pad,cfill,impl,variant", ATT_PARAMS)
+def test_attention_fwd_bwd_vs_oracle(B, H, Sq, Sk, D, causal, mode, pad, cfill, impl, variant, dtype):
+    if dtype == torch.float16 and (impl == 2 or Sq == 300):
+        pytest.skip("f16 operands: tcgen05 path only, one shape per mask family")
+    with _AttnVariant(variant):
+        _attention_case(B, H, Sq, Sk, D, causal, mode, pad, cfill, impl, dtype)
+
+
+def _attention_case(B, H, Sq, Sk, D, causal, mode, pad, cfill, impl, dtype):
     from oracle import ct_oracle as O
     ops = _ops()
     torch.manual_seed(7)
-    qkv = torch.randn(B, Sk, H, 3, D, device=DEV).bfloat16()
+    qkv = torch.randn(B, Sk, H, 3, D, device=DEV).to(dtype)
     q = qkv[:, Sk - Sq:, :, 0, :].permute(0, 2, 1, 3); k = qkv[..., 1, :].permute(0, 2, 1, 3); v = qkv[..., 2, :].permute(0, 2, 1, 3)
     kb2 = fv = None
     if mode is not None:
@@ -265,7 +330,7 @@ def test_attention_fwd_bwd_vs_oracle(B, H, Sq, Sk, D, causal, mode, pad, cfill, 
     assert rel_err(o, ref) < 5e-3
     if Sq == 1:
         return
-    do = torch.randn_like(ref).bfloat16()
+    do = torch.randn_like(ref).to(dtype)
     dqkv = torch.zeros_like(qkv)
     dq = dqkv[:, Sk - Sq:, :, 0, :].permute(0, 2, 1, 3); dk = dqkv[..., 1, :].permute(0, 2, 1, 3); dv = dqkv[..., 2, :].permute(0, 2, 1, 3)
     ops.attn_bwd(do, q, k, v, o, lse2, dq, dk, dv, scale, causal, cfill, kb2, fv, impl=impl)
@@ -296,7 +361,13 @@ def test_attention_matches_reference_bloom_layer(golden):
     assert rel_err(o, ref) < 8e-3
 
 
-def test_attention_rows_sum_to_one_at_full_size():
+@pytest.mark.parametrize("variant", ["v1", "v2"])
+def test_attention_rows_sum_to_one_at_full_size(variant):
+    with _AttnVariant(variant):
+        _rows_sum_to_one()
+
+
+def _rows_sum_to_one():
     """Property at BASELINE.json's size (B=8,H=16,S=1024,d=64): with V = 1 every output element is
     the softmax row sum, i.e. exactly 1 up to bf16 rounding of P; checks every tile incl. the diagonal."""
     ops = _ops()
