@@ -397,18 +397,25 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   return v;
 }
 
-// r <- r * sl2 + kb (only with a bias; otherwise r stays raw) ; returns max(mt, chunk max)
-template <bool HAS_KB>
+// Running max over one 32-column chunk held in registers. SCALE: r <- r * sl2 (+ kb) in place (always with a
+// per-key bias; without one the raw scores are kept and scaled inside the exp2 instead).
+template <bool HAS_KB, bool SCALE>
 __device__ __forceinline__ float fa2_scale_max(uint32_t (&r)[32], int col0, float sl2, uint32_t kb_s, float mt) {
+  static_assert(SCALE || !HAS_KB, "a per-key bias is folded in by scaling in place");
   const float2 s2 = make_float2(sl2, sl2);
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     float2 a = make_float2(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]));
     float2 b = make_float2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
-    if constexpr (HAS_KB) {
-      const float4 k4 = lds128f(kb_s + 4 * (col0 + 4 * g));
-      a = __ffma2_rn(a, s2, make_float2(k4.x, k4.y));
-      b = __ffma2_rn(b, s2, make_float2(k4.z, k4.w));
+    if constexpr (SCALE) {
+      if constexpr (HAS_KB) {
+        const float4 k4 = lds128f(kb_s + 4 * (col0 + 4 * g));
+        a = __ffma2_rn(a, s2, make_float2(k4.x, k4.y));
+        b = __ffma2_rn(b, s2, make_float2(k4.z, k4.w));
+      } else {
+        a = __fmul2_rn(a, s2);
+        b = __fmul2_rn(b, s2);
+      }
       r[4 * g] = __float_as_uint(a.x); r[4 * g + 1] = __float_as_uint(a.y);
       r[4 * g + 2] = __float_as_uint(b.x); r[4 * g + 3] = __float_as_uint(b.y);
     }
@@ -418,8 +425,9 @@ __device__ __forceinline__ float fa2_scale_max(uint32_t (&r)[32], int col0, floa
   return mt;
 }
 
-// p = 2^(t - m_new) for one 32-column chunk held in registers, bf16/f16 P into the swizzled K-major tile
-template <bool HAS_KB, bool BF16>
+// p = 2^(t - m_new) for one 32-column chunk held in registers (SCALED: t = r, else t = r * sl2), bf16/f16 P
+// into the swizzled K-major tile
+template <bool SCALED, bool BF16>
 __device__ __forceinline__ void fa2_exp_store(const uint32_t (&r)[32], int c, float m_new, float sl2, uint32_t p_row,
                                               int sw, float2& acc0, float2& acc1) {
   const float2 nm = make_float2(-m_new, -m_new);
@@ -430,7 +438,7 @@ __device__ __forceinline__ void fa2_exp_store(const uint32_t (&r)[32], int c, fl
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       float2 a = make_float2(__uint_as_float(r[8 * g + 2 * u]), __uint_as_float(r[8 * g + 2 * u + 1]));
-      if constexpr (HAS_KB) a = __fadd2_rn(a, nm);
+      if constexpr (SCALED) a = __fadd2_rn(a, nm);
       else a = __ffma2_rn(a, s2, nm);
       v[u] = make_float2(ex2(a.x), ex2(a.y));
     }
@@ -450,6 +458,64 @@ __device__ __forceinline__ void fa2_exp_store(const uint32_t (&r)[32], int c, fl
     const uint32_t addr = p_row + (c >> 1) * FA_TILE + ((chunk ^ sw) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
                  : "memory");
+  }
+}
+
+// Tile on an ALIGNED causal diagonal (key tile origin == first visible key of query row 0 of the tile, fill
+// -FLT_MAX, no masked / out-of-range key) for the warp owning rows 32*WQ..32*WQ+31: chunks < WQ are fully
+// visible, chunk WQ is lower-triangular (column t visible iff t <= lane), chunks > WQ lie entirely in the
+// future: every score there is exactly -FLT_MAX, no TMEM read, P = 2^(-FLT_MAX - m) (0 unless the row has
+// seen nothing but masked keys). One pass over register-resident rows like the interior tiles.
+template <bool HAS_KB, bool BF16, int WQ>
+__device__ __forceinline__ void fa2_diag_tile(uint32_t t_s, float sl2, uint32_t kb_s, uint32_t p_row, int sw, int lane,
+                                              float m, int j, uint32_t s_free, uint32_t o_full, float& m_new,
+                                              float& alpha, float& lt) {
+  uint32_t r[WQ + 1][32];
+#pragma unroll
+  for (int c = 0; c <= WQ; ++c) tmem_ld_32x32(t_s + c * 32, r[c]);
+  tmem_ld_wait();
+  float mt = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < WQ; ++c) mt = fa2_scale_max<HAS_KB, true>(r[c], c * 32, sl2, kb_s, mt);
+  (void)fa2_scale_max<HAS_KB, true>(r[WQ], WQ * 32, sl2, kb_s, mt);  // scale in place; max taken after masking
+  tc_fence_before();
+  mbar_arrive(s_free);  // after the last read of the staged bias (see the interior-tile path)
+#pragma unroll
+  for (int t = 1; t < 32; ++t)
+    if (t > lane) r[WQ][t] = __float_as_uint(-FLT_MAX);  // future keys of the diagonal chunk
+#pragma unroll
+  for (int t = 0; t < 32; t += 2)
+    mt = fmaxf(mt, fmaxf(__uint_as_float(r[WQ][t]), __uint_as_float(r[WQ][t + 1])));
+  mt = fmaxf(mt, -FLT_MAX);
+  m_new = fmaxf(m, mt);
+  alpha = ex2(m - m_new);
+  if (j > 0) {
+    mbar_wait(o_full, (j - 1) & 1);
+    tc_fence_after();
+  }
+  float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
+#pragma unroll
+  for (int c = 0; c <= WQ; ++c) fa2_exp_store<true, BF16>(r[c], c, m_new, sl2, p_row, sw, acc0, acc1);
+  lt = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+  if constexpr (WQ < 3) {
+    const float em = ex2(-FLT_MAX - m_new);
+    uint32_t w;
+    if constexpr (BF16) {
+      w = pack_bf16x2(em, em);
+    } else {
+      __half2 hx = __floats2half2_rn(em, em);
+      w = *reinterpret_cast<uint32_t*>(&hx);
+    }
+#pragma unroll
+    for (int c = WQ + 1; c < 4; ++c) {
+      lt += 32.f * em;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int chunk = (c & 1) * 4 + g;
+        const uint32_t addr = p_row + (c >> 1) * FA_TILE + ((chunk ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(w) : "memory");
+      }
+    }
   }
 }
 
@@ -567,16 +633,26 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       // CTA-uniform tile kind
-      bool slow = (p.causal && (kv0 + 127 > q0 + p.off)) || (kv0 + 128 > p.Sk);
+      const bool touches_diag = p.causal && (kv0 + 127 > q0 + p.off);
+      bool irregular = kv0 + 128 > p.Sk;  // ragged key edge, or (below) a masked key: generic path
       if constexpr (HAS_KB) {
-        // every thread is past o_full(j-1): all 128 finished reading the previous tile's bias
+        // S(j) needs s_free(j-1), which every thread arrives on after its last read of the previous tile's bias
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(kb_s + 4 * qr), "f"(kb_next) : "memory");
-        slow |= bar_red_or(1, 128, kb_next < -1e30f);  // a masked key in this tile -> generic path
+        irregular |= bar_red_or(1, 128, kb_next < -1e30f);
         const int nj = kv0 + 128 + qr;
         kb_next = (j + 1 < n_kv && nj < p.Sk) ? __ldg(kb_row + nj) : 0.f;
       }
+      const bool slow = touches_diag || irregular;
+      const bool diag_fast = touches_diag && !irregular && fill_is_ninf && kv0 == q0 + p.off;
       float m_new, alpha, lt;
-      if (!slow) {
+      if (diag_fast) {
+        switch (wq) {
+          case 0: fa2_diag_tile<HAS_KB, BF16, 0>(t_s, p.sl2, kb_s, p_row, sw, lane, m, j, s_free, o_full, m_new, alpha, lt); break;
+          case 1: fa2_diag_tile<HAS_KB, BF16, 1>(t_s, p.sl2, kb_s, p_row, sw, lane, m, j, s_free, o_full, m_new, alpha, lt); break;
+          case 2: fa2_diag_tile<HAS_KB, BF16, 2>(t_s, p.sl2, kb_s, p_row, sw, lane, m, j, s_free, o_full, m_new, alpha, lt); break;
+          default: fa2_diag_tile<HAS_KB, BF16, 3>(t_s, p.sl2, kb_s, p_row, sw, lane, m, j, s_free, o_full, m_new, alpha, lt); break;
+        }
+      } else if (!slow) {
         // ---------------- interior tile: one pass over a register-resident score row ----------------
         uint32_t r0[32], r1[32], r2[32], r3[32];
         tmem_ld_32x32(t_s, r0);
@@ -585,10 +661,10 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
         tmem_ld_32x32(t_s + 96, r3);
         tmem_ld_wait();
         float mt = -INFINITY;
-        mt = fa2_scale_max<HAS_KB>(r0, 0, p.sl2, kb_s, mt);
-        mt = fa2_scale_max<HAS_KB>(r1, 32, p.sl2, kb_s, mt);
-        mt = fa2_scale_max<HAS_KB>(r2, 64, p.sl2, kb_s, mt);
-        mt = fa2_scale_max<HAS_KB>(r3, 96, p.sl2, kb_s, mt);
+        mt = fa2_scale_max<HAS_KB, HAS_KB>(r0, 0, p.sl2, kb_s, mt);
+        mt = fa2_scale_max<HAS_KB, HAS_KB>(r1, 32, p.sl2, kb_s, mt);
+        mt = fa2_scale_max<HAS_KB, HAS_KB>(r2, 64, p.sl2, kb_s, mt);
+        mt = fa2_scale_max<HAS_KB, HAS_KB>(r3, 96, p.sl2, kb_s, mt);
         // Release the score buffer only after the last read of this tile's staged bias: S(j+1) and with it
         // the next tile's bias staging (single smem buffer) cannot start before every thread got here.
         tc_fence_before();
@@ -1093,18 +1169,29 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
 }
 
 // =================================================================================================
-// tcgen05 backward, v2: same pipeline as attn_bwd_tc_kernel, leaner compute warps
+// tcgen05 backward, v2
 // =================================================================================================
-// The ncu capture of v1 showed 23 warp instructions per score element in the 8 compute warps (the tensor
-// pipe idles while they run). v2 keeps barriers, TMEM map and MMA schedule and rewrites the element
-// math: each warp loads its two 32-query chunks of S^T and dP^T up front (no register copies), the
-// per-query statistics are staged as -lse2 and -delta*scale so that P^T = 2^(s*sl2 + (kb - lse2)) and
-// dS^T = P^T * (dP*scale - delta*scale) are two packed fma.f32x2 + one mul.f32x2 per element pair, and
-// 32-query chunks are classified per warp: visible (no masking code), entirely in the future of the
-// warp's 32 keys on an aligned causal diagonal (no TMEM read, dS = 0), or generic (v1 arithmetic).
+// ncu on v1 (same pipeline, 8 compute warps): 23 warp instructions per score element, and every query
+// tile serialises  [S^T, dP^T MMAs] -> [element math] -> [dQ, dV, dK MMAs] -> [dQ red.add]. v2:
+//   * each compute warp loads its two 32-query chunks of S^T and dP^T into registers up front and
+//     immediately releases the two TMEM buffers (sdp_free): the MMA warp issues S^T / dP^T of the NEXT
+//     query tile before the dQ / dV / dK MMAs of the current one, so they run under the element math;
+//   * dQ of tile it-1 is drained (TMEM -> red.global.add) at the start of tile it, while the S^T / dP^T
+//     loads are in flight, instead of stalling on the dQ MMA right after issuing its operands;
+//   * element math on register pairs: statistics staged as -lse2 and -delta*scale, so
+//     P^T = 2^(s*sl2 + (kb - lse2)), dS^T = P^T * (dP*scale - delta*scale): 2 fma.f32x2 + 1 mul.f32x2
+//     + 1 add.f32x2 per element pair; 32-query chunks are classified per warp (visible / entirely in the
+//     future of the warp's 32 keys on an aligned causal diagonal: no TMEM read, dS = 0 / generic = v1
+//     arithmetic) with the classification hoisted out of the element loops.
+struct FbCtx {
+  float kb, sl2, scale, cf2;
+  int jg, off, causal, key_oob;
+  uint32_t lse_s, del_s, sPT, sDS;
+  int rr, sw;
+};
+
 template <bool BF16>
-__device__ __forceinline__ void fb2_store_pair(uint32_t sPT, uint32_t sDS, uint32_t off, const float (&pt)[8],
-                                               const float (&ds)[8]) {
+__device__ __forceinline__ void fb2_store_pair(const FbCtx& cx, int c, int g, const float (&pt)[8], const float (&ds)[8]) {
   uint32_t a[4], d[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
@@ -1118,10 +1205,69 @@ __device__ __forceinline__ void fb2_store_pair(uint32_t sPT, uint32_t sDS, uint3
       d[u] = *reinterpret_cast<uint32_t*>(&x);
     }
   }
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPT + off), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3])
+  const int ch = (c & 1) * 4 + g;
+  const uint32_t off = cx.rr * 128 + (c >> 1) * FA_TILE + ((ch ^ cx.sw) << 4);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cx.sPT + off), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3])
                : "memory");
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3])
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cx.sDS + off), "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3])
                : "memory");
+}
+
+// one 32-query chunk c of this thread's key row. KIND 0 = visible, 1 = entirely future, 2 = generic
+template <int KIND, bool BF16>
+__device__ __forceinline__ void fb2_chunk(const FbCtx& cx, const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c,
+                                          int q0) {
+  const float2 sl2v = make_float2(cx.sl2, cx.sl2), scv = make_float2(cx.scale, cx.scale), kbv = make_float2(cx.kb, cx.kb);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float pt[8], ds[8];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int col = c * 32 + g * 8 + hh * 4;
+      const float4 nl = lds128f(cx.lse_s + 4 * col);
+      const float nls[4] = {nl.x, nl.y, nl.z, nl.w};
+      if constexpr (KIND == 0) {
+        const float4 nd = lds128f(cx.del_s + 4 * col);
+        const float nds[4] = {nd.x, nd.y, nd.z, nd.w};
+#pragma unroll
+        for (int u2 = 0; u2 < 2; ++u2) {
+          const int e = g * 8 + hh * 4 + 2 * u2;
+          const float2 add = __fadd2_rn(kbv, make_float2(nls[2 * u2], nls[2 * u2 + 1]));
+          const float2 t = __ffma2_rn(make_float2(__uint_as_float(rs[e]), __uint_as_float(rs[e + 1])), sl2v, add);
+          const float2 pe = make_float2(ex2(t.x), ex2(t.y));
+          const float2 w = __ffma2_rn(make_float2(__uint_as_float(rd[e]), __uint_as_float(rd[e + 1])), scv,
+                                      make_float2(nds[2 * u2], nds[2 * u2 + 1]));
+          const float2 d2 = __fmul2_rn(pe, w);
+          pt[hh * 4 + 2 * u2] = pe.x; pt[hh * 4 + 2 * u2 + 1] = pe.y;
+          ds[hh * 4 + 2 * u2] = d2.x; ds[hh * 4 + 2 * u2 + 1] = d2.y;
+        }
+      } else if constexpr (KIND == 1) {
+        // causally masked for every key of this warp: the score is the (clamped) fill, a constant
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          pt[hh * 4 + u] = ex2(-FLT_MAX + nls[u]);
+          ds[hh * 4 + u] = 0.f;
+        }
+      } else {
+        const float4 nd = lds128f(cx.del_s + 4 * col);
+        const float nds[4] = {nd.x, nd.y, nd.z, nd.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = g * 8 + hh * 4 + u;
+          const int qg = q0 + col + u;
+          const bool fut = cx.causal && (cx.jg > qg + cx.off);
+          const float v = score2(__uint_as_float(rs[e]), cx.sl2, cx.kb, fut, cx.cf2, false);
+          float pe = ex2(v + nls[u]);
+          if (cx.key_oob) pe = 0.f;
+          pt[hh * 4 + u] = pe;
+          // a causally masked score is a constant in the reference (modeling_gpt.py:89 `w*b`,
+          // modeling_bloom.py:108 masked_fill): P still feeds dV, but no gradient reaches q.k
+          ds[hh * 4 + u] = fut ? 0.f : pe * fmaf(__uint_as_float(rd[e]), cx.scale, nds[u]);
+        }
+      }
+    }
+    fb2_store_pair<BF16>(cx, c, g, pt, ds);
+  }
 }
 
 template <bool BF16>
@@ -1138,8 +1284,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   const uint32_t sDS = base + 8 * FA_TILE;  // 2 panels
   const uint32_t bars = base + 10 * FA_TILE;
   const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 24, sdp_full = bars + 40,
-                 pds_ready = bars + 48, dq_full = bars + 56, dkv_full = bars + 64, tmem_slot = bars + 72,
-                 lse_s = bars + 128, del_s = bars + 640;
+                 pds_ready = bars + 48, mma_done = bars + 56, dkv_full = bars + 64, tmem_slot = bars + 72,
+                 sdp_free = bars + 80, lse_s = bars + 128, del_s = bars + 640;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + 10 * FA_TILE + 72);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1161,8 +1307,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(qdo_full + 8 * s, 1); mbar_init(qdo_empty + 8 * s, 1); }
     mbar_init(sdp_full, 1);
+    mbar_init(sdp_free, 256);
     mbar_init(pds_ready, 256);
-    mbar_init(dq_full, 1);
+    mbar_init(mma_done, 1);
     mbar_init(dkv_full, 1);
     mbar_fence_init();
   }
@@ -1195,6 +1342,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         const int s = it & 1;
         const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
         mbar_wait(qdo_full + 8 * s, (it >> 1) & 1);
+        if (it > 0) mbar_wait(sdp_free, (it - 1) & 1);  // every compute thread holds S^T/dP^T(it-1) in registers
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // S^T[kv, q] = K[kv, d] . Q[q, d]
@@ -1211,13 +1359,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       for (int it = 0; it < n_it; ++it) {
         const int s = it & 1;
         const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
+        if (it + 1 < n_it) issue_sdp(it + 1);  // runs under the element math of tile it
         mbar_wait(pds_ready, it & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // dQ[q, d] = dS[q, kv] . K[kv, d]  (A MN-major view of dS^T)
           umma_f16(T_DQ, umma_smem_desc_sw128(sDS + k * 2048, FA_TILE, 1024),
                    umma_smem_desc_sw128(sK + k * 2048, 64 * 128, 1024), idesc_mm, k > 0);
-        umma_commit(dq_full);
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // dV[kv, d] += P^T[kv, q] . dO[q, d]   (B MN-major: rows = q)
           umma_f16(T_DV, umma_smem_desc_sw128(sPT + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
@@ -1227,7 +1375,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
           umma_f16(T_DK, umma_smem_desc_sw128(sDS + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
                    umma_smem_desc_sw128(q + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
         umma_commit(qdo_empty + 8 * s);
-        if (it + 1 < n_it) issue_sdp(it + 1);
+        umma_commit(mma_done);  // dQ(it) readable; P^T / dS^T tiles free for tile it+1
       }
       umma_commit(dkv_full);
     }
@@ -1237,74 +1385,36 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
     const int hf = (warp - 2) >> 2;  // which pair of 32-query chunks this warp owns
     const int jg = kv0 + rr;
     const uint32_t t_lane = (uint32_t)(wq * 32) << 16;
-    const float kb = (p.kbias2 && jg < p.Sk)
-                         ? __ldg(p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh + jg) : 0.f;
-    const bool key_oob = jg >= p.Sk;
+    FbCtx cx;
+    cx.kb = (p.kbias2 && jg < p.Sk) ? __ldg(p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh + jg) : 0.f;
+    cx.sl2 = p.sl2; cx.scale = p.scale; cx.cf2 = p.causal_fill2;
+    cx.jg = jg; cx.off = p.off; cx.causal = p.causal; cx.key_oob = jg >= p.Sk;
+    cx.lse_s = lse_s; cx.del_s = del_s; cx.sPT = sPT; cx.sDS = sDS; cx.rr = rr; cx.sw = rr & 7;
     // generic arithmetic for the whole warp when a key is masked (the reference's finite fill matters on
     // fully masked query rows) or the key tile is ragged
-    const bool warp_generic = __any_sync(0xffffffffu, kb < -1e30f) || (kv0 + 128 > p.Sk);
+    const bool warp_generic = __any_sync(0xffffffffu, cx.kb < -1e30f) || (kv0 + 128 > p.Sk);
     const bool fill_is_ninf = p.causal_fill2 == -INFINITY;
     const float* lse_bh = p.lse2 + ((int64_t)b * p.H + h) * p.Sq;
     const float* del_bh = bp.delta + ((int64_t)b * p.H + h) * p.Sq;
-    const int sw = rr & 7;
     // per-query statistics of the current query tile, staged as -lse2 and -delta*scale
     float nlse_next = -INFINITY, ndel_next = 0.f;
     if (hf == 0 && n_it > 0 && i_start * 128 + rr < p.Sq) {
       nlse_next = -__ldg(lse_bh + i_start * 128 + rr);
       ndel_next = -__ldg(del_bh + i_start * 128 + rr) * p.scale;
     }
-    const float2 sl2v = make_float2(p.sl2, p.sl2), scv = make_float2(p.scale, p.scale), kbv = make_float2(kb, kb);
+    const int c0 = 2 * hf, c1 = 2 * hf + 1;
 
-    // one 32-query chunk c of this thread's key row; kind 0 = visible, 1 = future, 2 = generic
-    auto chunk = [&](const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c, int kind, int q0) {
+    // dQ rows of query tile `itp`: this thread owns query row (q0 + rr), columns [32*hf, 32*hf + 32) of d
+    auto red_dq = [&](const uint32_t (&r)[32], int itp) {
+      const int qi = (i_start + itp) * 128 + rr;
+      if (qi < p.Sq) {
+        float* dst = bp.dq_accum + (((int64_t)b * p.Sq + qi) * p.H + h) * 64 + hf * 32;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float pt[8], ds[8];
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int col = c * 32 + g * 8 + hh * 4;
-          const float4 nl = lds128f(lse_s + 4 * col);
-          const float4 nd = lds128f(del_s + 4 * col);
-          const float nls[4] = {nl.x, nl.y, nl.z, nl.w};
-          const float nds[4] = {nd.x, nd.y, nd.z, nd.w};
-          if (kind == 0) {
-#pragma unroll
-            for (int u2 = 0; u2 < 2; ++u2) {
-              const int e = g * 8 + hh * 4 + 2 * u2;
-              const float2 add = __fadd2_rn(kbv, make_float2(nls[2 * u2], nls[2 * u2 + 1]));
-              const float2 t = __ffma2_rn(make_float2(__uint_as_float(rs[e]), __uint_as_float(rs[e + 1])), sl2v, add);
-              const float2 pe = make_float2(ex2(t.x), ex2(t.y));
-              const float2 w = __ffma2_rn(make_float2(__uint_as_float(rd[e]), __uint_as_float(rd[e + 1])), scv,
-                                          make_float2(nds[2 * u2], nds[2 * u2 + 1]));
-              const float2 d2 = __fmul2_rn(pe, w);
-              pt[hh * 4 + 2 * u2] = pe.x; pt[hh * 4 + 2 * u2 + 1] = pe.y;
-              ds[hh * 4 + 2 * u2] = d2.x; ds[hh * 4 + 2 * u2 + 1] = d2.y;
-            }
-          } else if (kind == 1) {
-            // causally masked for every key of this warp: the score is the (clamped) fill, a constant
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              pt[hh * 4 + u] = ex2(-FLT_MAX + nls[u]);
-              ds[hh * 4 + u] = 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int e = g * 8 + hh * 4 + u;
-              const int qg = q0 + col + u;
-              const bool fut = p.causal && (jg > qg + p.off);
-              const float v = score2(__uint_as_float(rs[e]), p.sl2, kb, fut, p.causal_fill2, false);
-              float pe = ex2(v + nls[u]);
-              if (key_oob) pe = 0.f;
-              pt[hh * 4 + u] = pe;
-              // a causally masked score is a constant in the reference (modeling_gpt.py:89 `w*b`,
-              // modeling_bloom.py:108 masked_fill): P still feeds dV, but no gradient reaches q.k
-              ds[hh * 4 + u] = fut ? 0.f : pe * fmaf(__uint_as_float(rd[e]), p.scale, nds[u]);
-            }
-          }
-        }
-        const int ch = (c & 1) * 4 + g;
-        fb2_store_pair<BF16>(sPT, sDS, rr * 128 + (c >> 1) * FA_TILE + ((ch ^ sw) << 4), pt, ds);
+        for (int g = 0; g < 8; ++g)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g),
+                       "f"(__uint_as_float(r[4 * g])), "f"(__uint_as_float(r[4 * g + 1])),
+                       "f"(__uint_as_float(r[4 * g + 2])), "f"(__uint_as_float(r[4 * g + 3]))
+                       : "memory");
       }
     };
 
@@ -1312,23 +1422,10 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       const int q0 = (i_start + it) * 128;
       mbar_wait(sdp_full, it & 1);
       tc_fence_after();
-      // all 256 threads are past pds_ready(it-1): nobody still reads the previous tile's statistics
-      if (hf == 0) {
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(lse_s + 4 * rr), "f"(nlse_next) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(del_s + 4 * rr), "f"(ndel_next) : "memory");
-      }
-      bar_sync_named(1, 256);
-      if (hf == 0) {
-        const int nq = q0 + 128 + rr;
-        const bool ok = (it + 1 < n_it) && nq < p.Sq;
-        nlse_next = ok ? -__ldg(lse_bh + nq) : -INFINITY;
-        ndel_next = ok ? -__ldg(del_bh + nq) * p.scale : 0.f;
-      }
       // chunk kinds (warp-uniform)
       const bool touches_diag = p.causal && (kv0 + 127 > q0 + p.off);
       const bool aligned_diag = touches_diag && fill_is_ninf && (kv0 == q0 + p.off) && !warp_generic;
       int kind0, kind1;
-      const int c0 = 2 * hf, c1 = 2 * hf + 1;
       if (warp_generic || (touches_diag && !aligned_diag)) {
         kind0 = kind1 = 2;
       } else if (aligned_diag) {
@@ -1341,34 +1438,53 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       uint32_t rs0[32], rd0[32], rs1[32], rd1[32];
       if (kind0 != 1) { tmem_ld_32x32(T_ST + t_lane + c0 * 32, rs0); tmem_ld_32x32(T_DPT + t_lane + c0 * 32, rd0); }
       if (kind1 != 1) { tmem_ld_32x32(T_ST + t_lane + c1 * 32, rs1); tmem_ld_32x32(T_DPT + t_lane + c1 * 32, rd1); }
+      if (it > 0) {
+        // all MMAs of tile it-1 retired: dQ(it-1) is complete and the P^T / dS^T tiles may be overwritten
+        mbar_wait(mma_done, (it - 1) & 1);
+        tc_fence_after();
+      }
+      // mma_done(it-1) implies pds_ready(it-1): every thread has finished the element math of tile it-1,
+      // nobody still reads its statistics
+      if (hf == 0) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(lse_s + 4 * rr), "f"(nlse_next) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(del_s + 4 * rr), "f"(ndel_next) : "memory");
+      }
       tmem_ld_wait();
-      chunk(rs0, rd0, c0, kind0, q0);
-      chunk(rs1, rd1, c1, kind1, q0);
+      tc_fence_before();
+      mbar_arrive(sdp_free);        // S^T / dP^T are in registers: the next tile's MMAs may overwrite them
+      bar_sync_named(1, 256);       // statistics staged by the hf == 0 warps are visible
+      if (hf == 0) {
+        const int nq = q0 + 128 + rr;
+        const bool ok = (it + 1 < n_it) && nq < p.Sq;
+        nlse_next = ok ? -__ldg(lse_bh + nq) : -INFINITY;
+        ndel_next = ok ? -__ldg(del_bh + nq) * p.scale : 0.f;
+      }
+      if (kind0 == 0) fb2_chunk<0, BF16>(cx, rs0, rd0, c0, q0);
+      else if (kind0 == 1) fb2_chunk<1, BF16>(cx, rs0, rd0, c0, q0);
+      else fb2_chunk<2, BF16>(cx, rs0, rd0, c0, q0);
+      if (it > 0) {
+        // drain dQ(it-1) between the two chunks (T_DQ is only rewritten after pds_ready(it)): the
+        // red.global.add traffic overlaps the second chunk's math
+        uint32_t rq[32];
+        tmem_ld_32x32(T_DQ + t_lane + hf * 32, rq);
+        tmem_ld_wait();
+        red_dq(rq, it - 1);
+      }
+      if (kind1 == 0) fb2_chunk<0, BF16>(cx, rs1, rd1, c1, q0);
+      else if (kind1 == 1) fb2_chunk<1, BF16>(cx, rs1, rd1, c1, q0);
+      else fb2_chunk<2, BF16>(cx, rs1, rd1, c1, q0);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_ready);
-      // ---- dQ tile: this thread owns query row (q0 + rr), columns [32*hf, 32*hf + 32) of d ----
-      mbar_wait(dq_full, it & 1);
-      tc_fence_after();
-      const int qi = q0 + rr;
-      {
-        uint32_t r[32];
-        tmem_ld_32x32(T_DQ + t_lane + hf * 32, r);
-        tmem_ld_wait();
-        if (qi < p.Sq) {
-          float* dst = bp.dq_accum + (((int64_t)b * p.Sq + qi) * p.H + h) * 64 + hf * 32;
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g),
-                         "f"(__uint_as_float(r[4 * g])), "f"(__uint_as_float(r[4 * g + 1])),
-                         "f"(__uint_as_float(r[4 * g + 2])), "f"(__uint_as_float(r[4 * g + 3]))
-                         : "memory");
-        }
-      }
-      tc_fence_before();
     }
-    // ---- dK / dV for this key row: 32 of the 64 head-dim columns per thread ----
+    // ---- last dQ tile, then dK / dV for this key row: 32 of the 64 head-dim columns per thread ----
     if (n_it > 0) {
+      mbar_wait(mma_done, (n_it - 1) & 1);
+      tc_fence_after();
+      uint32_t rq[32];
+      tmem_ld_32x32(T_DQ + t_lane + hf * 32, rq);
+      tmem_ld_wait();
+      red_dq(rq, n_it - 1);
       mbar_wait(dkv_full, 0);
       tc_fence_after();
     }
@@ -1382,7 +1498,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
 #pragma unroll
         for (int t = 0; t < 32; ++t) r[t] = 0u;
       }
-      if (!key_oob) {
+      if (!cx.key_oob) {
         void* basep = which == 0 ? bp.dv : bp.dk;
         const int64_t eo = which == 0
             ? (int64_t)b * bp.dv_sb + (int64_t)h * bp.dv_sh + (int64_t)jg * bp.dv_ss

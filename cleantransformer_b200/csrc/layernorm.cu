@@ -411,6 +411,126 @@ __global__ void __launch_bounds__(512, 2) ln_bwd_cta_kernel(const LnBwdP p) {
   }
 }
 
+// Compile-time variant of ln_bwd_cta_kernel for the training hot path (x f32, dy bf16, optional f32 dx_add,
+// f32 dx, optional bf16 dx2): ncu on the run-time-typed kernel above showed it ISSUE-bound (60 % issue
+// utilisation, ~1100 instructions per two-row iteration, mostly dtype dispatch and 64-bit address math).
+template <int NW, bool HAS_ADD, bool HAS_DX2>
+__global__ void __launch_bounds__(NW * 64, 2)
+    ln_bwd_fast_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                       const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                       const float* __restrict__ rstd_in, const float* __restrict__ dx_add, float* __restrict__ dx,
+                       __nv_bfloat16* __restrict__ dx2, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                       float* __restrict__ dxsum, float* __restrict__ partial, int64_t rows) {
+  constexpr int COLS = NW * 128, TPR = NW * 32;
+  __shared__ __align__(16) float red[2][2][4][8];  // [half][iteration parity][quantity][warp (zero padded)]
+  __shared__ __align__(16) float comb[3 * COLS];
+  const int half = threadIdx.x >= TPR ? 1 : 0;
+  const int t = threadIdx.x - half * TPR;
+  const int lane = t & 31, wih = t >> 5;
+  const int col0 = 4 * t;
+  constexpr float inv_cols = 1.f / (float)COLS;
+  if (threadIdx.x < 2 * 2 * 4 * 8) (&red[0][0][0][0])[threadIdx.x] = 0.f;
+  __syncthreads();
+
+  const float4 g4 = Vec4<float>::load(gamma + col0);
+  float4 adg = make_float4(0.f, 0.f, 0.f, 0.f), adb = adg, adc = adg;
+  const int64_t n_grp = (rows + 1) / 2;
+  int par = 0;
+  for (int64_t grp = (int64_t)blockIdx.x * 2 + half; grp < n_grp; grp += (int64_t)gridDim.x * 2, par ^= 1) {
+    const int64_t row0 = grp * 2;
+    const bool ok1 = row0 + 1 < rows;
+    const int64_t i0 = row0 * COLS + col0, i1 = i0 + COLS;
+    float4 xh0 = Vec4<float>::load(x + i0);
+    float4 d0 = Vec4<__nv_bfloat16>::load(dy + i0);
+    float4 xh1 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = xh1, a0 = xh1, a1 = xh1;
+    if (ok1) { xh1 = Vec4<float>::load(x + i1); d1 = Vec4<__nv_bfloat16>::load(dy + i1); }
+    if constexpr (HAS_ADD) {
+      a0 = Vec4<float>::load(dx_add + i0);
+      if (ok1) a1 = Vec4<float>::load(dx_add + i1);
+    }
+    const float m0 = __ldg(mean_in + row0), r0 = __ldg(rstd_in + row0);
+    const float m1 = ok1 ? __ldg(mean_in + row0 + 1) : 0.f, r1 = ok1 ? __ldg(rstd_in + row0 + 1) : 0.f;
+    xh0.x = (xh0.x - m0) * r0; xh0.y = (xh0.y - m0) * r0; xh0.z = (xh0.z - m0) * r0; xh0.w = (xh0.w - m0) * r0;
+    xh1.x = (xh1.x - m1) * r1; xh1.y = (xh1.y - m1) * r1; xh1.z = (xh1.z - m1) * r1; xh1.w = (xh1.w - m1) * r1;
+    adg.x = fmaf(d0.x, xh0.x, adg.x); adg.y = fmaf(d0.y, xh0.y, adg.y);
+    adg.z = fmaf(d0.z, xh0.z, adg.z); adg.w = fmaf(d0.w, xh0.w, adg.w);
+    adg.x = fmaf(d1.x, xh1.x, adg.x); adg.y = fmaf(d1.y, xh1.y, adg.y);
+    adg.z = fmaf(d1.z, xh1.z, adg.z); adg.w = fmaf(d1.w, xh1.w, adg.w);
+    adb.x += d0.x + d1.x; adb.y += d0.y + d1.y; adb.z += d0.z + d1.z; adb.w += d0.w + d1.w;
+    d0.x *= g4.x; d0.y *= g4.y; d0.z *= g4.z; d0.w *= g4.w;
+    d1.x *= g4.x; d1.y *= g4.y; d1.z *= g4.z; d1.w *= g4.w;
+    float p0 = (d0.x + d0.y) + (d0.z + d0.w);
+    float p1 = (d0.x * xh0.x + d0.y * xh0.y) + (d0.z * xh0.z + d0.w * xh0.w);
+    float p2 = (d1.x + d1.y) + (d1.z + d1.w);
+    float p3 = (d1.x * xh1.x + d1.y * xh1.y) + (d1.z * xh1.z + d1.w * xh1.w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+      p2 += __shfl_xor_sync(0xffffffffu, p2, o); p3 += __shfl_xor_sync(0xffffffffu, p3, o);
+    }
+    if (lane == 0) {
+      red[half][par][0][wih] = p0; red[half][par][1][wih] = p1;
+      red[half][par][2][wih] = p2; red[half][par][3][wih] = p3;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(TPR) : "memory");
+    float tot[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 u = *reinterpret_cast<const float4*>(&red[half][par][q][0]);
+      const float4 v = *reinterpret_cast<const float4*>(&red[half][par][q][4]);
+      tot[q] = ((u.x + u.y) + (u.z + u.w) + (v.x + v.y) + (v.z + v.w)) * inv_cols;
+    }
+    float4 o0, o1;
+    o0.x = fmaf(r0, d0.x - tot[0] - xh0.x * tot[1], a0.x); o0.y = fmaf(r0, d0.y - tot[0] - xh0.y * tot[1], a0.y);
+    o0.z = fmaf(r0, d0.z - tot[0] - xh0.z * tot[1], a0.z); o0.w = fmaf(r0, d0.w - tot[0] - xh0.w * tot[1], a0.w);
+    o1.x = fmaf(r1, d1.x - tot[2] - xh1.x * tot[3], a1.x); o1.y = fmaf(r1, d1.y - tot[2] - xh1.y * tot[3], a1.y);
+    o1.z = fmaf(r1, d1.z - tot[2] - xh1.z * tot[3], a1.z); o1.w = fmaf(r1, d1.w - tot[2] - xh1.w * tot[3], a1.w);
+    Vec4<float>::store(dx + i0, o0);
+    if constexpr (HAS_DX2) Vec4<__nv_bfloat16>::store(dx2 + i0, o0);
+    adc.x += o0.x; adc.y += o0.y; adc.z += o0.z; adc.w += o0.w;
+    if (ok1) {
+      Vec4<float>::store(dx + i1, o1);
+      if constexpr (HAS_DX2) Vec4<__nv_bfloat16>::store(dx2 + i1, o1);
+      adc.x += o1.x; adc.y += o1.y; adc.z += o1.z; adc.w += o1.w;
+    }
+  }
+  if (!(dgamma || dbeta || dxsum)) return;
+  if (half == 1) {
+    Vec4<float>::store(comb + col0, adg);
+    Vec4<float>::store(comb + COLS + col0, adb);
+    Vec4<float>::store(comb + 2 * COLS + col0, adc);
+  }
+  __syncthreads();
+  if (half == 0) {
+    const float4 a = Vec4<float>::load(comb + col0), b = Vec4<float>::load(comb + COLS + col0),
+                 c = Vec4<float>::load(comb + 2 * COLS + col0);
+    adg.x += a.x; adg.y += a.y; adg.z += a.z; adg.w += a.w;
+    adb.x += b.x; adb.y += b.y; adb.z += b.z; adb.w += b.w;
+    adc.x += c.x; adc.y += c.y; adc.z += c.z; adc.w += c.w;
+    float* dst = partial + (size_t)blockIdx.x * 3 * COLS + col0;
+    if (dgamma) Vec4<float>::store(dst, adg);
+    if (dbeta) Vec4<float>::store(dst + COLS, adb);
+    if (dxsum) Vec4<float>::store(dst + 2 * COLS, adc);
+  }
+}
+
+template <int NW>
+static void launch_ln_bwd_fast(const ct_ln_bwd_args& a, int grid, cudaStream_t st) {
+  const float* x = reinterpret_cast<const float*>(a.x);
+  const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(a.dy);
+  const float* add = reinterpret_cast<const float*>(a.dx_add);
+  float* dx = reinterpret_cast<float*>(a.dx);
+  __nv_bfloat16* dx2 = reinterpret_cast<__nv_bfloat16*>(a.dx2);
+#define CT_LNF(A, D)                                                                                         \
+  ln_bwd_fast_kernel<NW, A, D><<<grid, NW * 64, 0, st>>>(x, dy, a.gamma, a.mean, a.rstd, add, dx, dx2, a.dgamma, \
+                                                          a.dbeta, a.dxsum, a.workspace, a.rows)
+  if (add && dx2) CT_LNF(true, true);
+  else if (add) CT_LNF(true, false);
+  else if (dx2) CT_LNF(false, true);
+  else CT_LNF(false, false);
+#undef CT_LNF
+}
+
 // second stage of v2: out_which[c] (+)= sum_b partial[b][which][c]; CTA = 32 columns x 8 row groups
 __global__ void __launch_bounds__(256)
     ln_bwd_reduce3_kernel(const float* __restrict__ partial, int nblocks, int cols, float* __restrict__ dgamma,
@@ -623,6 +743,22 @@ extern "C" int ct_layernorm_bwd_ex(const ct_ln_bwd_args* args, void* stream) {
       if (a.dxsum && !a.dxsum_accumulate) CT_CUDA_OK(cudaMemsetAsync(a.dxsum, 0, sizeof(float) * cols, st));
     }
     if (rows == 0) return 0;
+    // compile-time hot variant (LN_BWD_IMPL 2 forces the run-time-typed kernel of the same design)
+    const bool fast = option(OPT_LN_BWD_IMPL) != 2 && (cols == 1024 || cols == 768) && a.x_dtype == DT_F32 && a.dy &&
+                      a.dy_dtype == DT_BF16 && !a.dy2 && (!a.dx_add || a.dx_add_dtype == DT_F32) &&
+                      a.dx_dtype == DT_F32 && (!a.dx2 || a.dx2_dtype == DT_BF16) && (!want_red || use_ws);
+    if (fast) {
+      if (cols == 1024) launch_ln_bwd_fast<8>(a, grid, st);
+      else launch_ln_bwd_fast<6>(a, grid, st);
+      CT_LAUNCH_OK();
+      if (use_ws) {
+        dim3 g2((unsigned)((cols + 31) / 32), 3);
+        ln_bwd_reduce3_kernel<<<g2, 256, 0, st>>>(a.workspace, grid, (int)cols, a.dgamma, a.dbeta, a.dxsum,
+                                                  a.dgb_accumulate, a.dxsum_accumulate);
+        CT_LAUNCH_OK();
+      }
+      return 0;
+    }
     LnBwdP p;
     p.dy = a.dy; p.dy_dtype = a.dy_dtype; p.dy2 = a.dy2; p.dy2_dtype = a.dy2_dtype;
     p.x = a.x; p.x_dtype = a.x_dtype; p.gamma = a.gamma; p.mean = a.mean; p.rstd = a.rstd;

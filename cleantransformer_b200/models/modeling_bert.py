@@ -156,3 +156,26 @@ class BertForSequenceClassification(torch.nn.Module):
         hidden_states, pooled_output = self.bert(input_ids, attention_mask, segment_ids, position_ids)
         pooled_output = self.drop(pooled_output)
         return F.linear(pooled_output, self.classifier.weight, self.classifier.bias, out_dtype=torch.float32)
+
+
+class BertTokenizer:
+    """examples/inference_bert.py:12,65-67 constructs `BertTokenizer(vocab_file=...)` from this module and
+    reads `input_ids / attention_mask / segment_ids` from `encode_plus`. The reference's own WordPiece
+    implementation (modeling_bert.py:50-226) is CPU string processing and out of scope; this adapter
+    delegates to `transformers.BertTokenizer` (which the reference asserts equality with,
+    modeling_bert.py:336-372) and renames `token_type_ids`."""
+
+    def __init__(self, vocab_file, do_lower_case=True, **kwargs):
+        import transformers
+        self._tok = transformers.BertTokenizer(vocab_file=vocab_file, do_lower_case=do_lower_case, **kwargs)
+
+    def tokenize(self, text):
+        return self._tok.tokenize(text)
+
+    def convert_tokens_to_ids(self, tokens):
+        return self._tok.convert_tokens_to_ids(tokens)
+
+    def encode_plus(self, text, text_pair=None, padding=False, truncation=False, max_length=None, **kwargs):
+        enc = self._tok(text, text_pair, padding=padding, truncation=truncation, max_length=max_length, **kwargs)
+        return {"input_ids": enc["input_ids"], "attention_mask": enc["attention_mask"],
+                "segment_ids": enc["token_type_ids"]}

@@ -26,10 +26,11 @@ def _ops():
     return ops
 
 
-@pytest.mark.parametrize("impl", [0, 1], ids=["v2", "v1"])
+@pytest.mark.parametrize("impl", [0, 2, 1], ids=["v2", "v2generic", "v1"])
 @pytest.mark.parametrize("cols,rows", [(1024, 1000), (768, 1000), (128, 1000), (24, 1000), (1024, 8192), (256, 3)])
 def test_layernorm_fwd_bwd_vs_oracle(cols, rows, impl):
-    """impl 0 = default backward (row spread over cols/4 threads), 1 = warp-per-row backward."""
+    """impl 0 = default backward (row spread over cols/4 threads; compile-time variant on the training dtypes),
+    2 = the same design with run-time dtypes, 1 = warp-per-row backward."""
     from oracle import ct_oracle as O
     ops = _ops()
     prev = ops.set_option("LN_BWD_IMPL", impl)

@@ -1,0 +1,99 @@
+"""The launcher (cleantransformer_b200/run.py) that lets the reference's example scripts run unmodified:
+alias installation, torch.optim / DDP swaps, and — when the reference checkout is present (build
+container only, never on the GPU box) — the reference's own examples/inference_bloom.py loader executed
+UNCHANGED against this package's classes."""
+import json
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+def _run(args, cwd=None, env_extra=None):
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), PYTHONDONTWRITEBYTECODE="1")
+    env.update(env_extra or {})
+    r = subprocess.run([sys.executable] + args, cwd=cwd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + "\n" + r.stderr[-4000:]
+    return r.stdout
+
+
+def test_install_aliases_and_swaps(tmp_path):
+    script = tmp_path / "probe.py"
+    script.write_text(textwrap.dedent('''
+        import sys
+        from CleanTransformer.models.modeling_bloom import BloomForCausalLM, BloomConfig, BloomAttentionLayer
+        from CleanTransformer.models.modeling_gpt import GPTLMHeadModel, GPTConfig, Conv1D
+        from CleanTransformer.models.modeling_bert import BertForSequenceClassification, BertTokenizer, BertConfig
+        from CleanTransformer.transformer import MultiHeadAttention, AttentionLayer, LayerNorm, TransformerBlock
+        from CleanTransformer.generation.generation_util import GenerationMixin
+        from CleanTransformer.trainer.trainer import Trainer
+        from CleanTransformer.optimizer import AdamW as RefAdamW, SGD
+        from torch.optim import AdamW
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        from transformers import BloomTokenizerFast
+        assert MultiHeadAttention is AttentionLayer
+        for c in (BloomForCausalLM, GPTLMHeadModel, BertForSequenceClassification, LayerNorm, GenerationMixin, Trainer,
+                  RefAdamW, SGD, AdamW, DDP):
+            assert c.__module__.startswith("cleantransformer_b200"), (c, c.__module__)
+        assert sys.argv[1:] == ["--flag", "7"], sys.argv
+        print("PROBE-OK")
+    '''))
+    out = _run(["-m", "cleantransformer_b200.run", "--ct-keep-default-device", str(script), "--flag", "7"])
+    assert "PROBE-OK" in out
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "examples")), reason="reference checkout not present")
+def test_reference_inference_bloom_loader_runs_unchanged(tmp_path):
+    """examples/inference_bloom.py (unmodified, imported from the read-only reference tree) builds OUR
+    BloomForCausalLM through its own load_config / load_model: HF-style config synonyms, HF key remap,
+    strict state_dict load, eval(), _tie_weight()."""
+    cfg = dict(vocab_size=97, n_embed=32, n_layer=2, num_attention_heads=4, layer_norm_epsilon=1e-5,
+               hidden_dropout=0.0, attention_dropout=0.0)
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    torch.manual_seed(0)
+    H, L, V = 32, 2, 97
+    sd = {"transformer.word_embeddings.weight": torch.randn(V, H),
+          "transformer.word_embeddings_layernorm.weight": torch.ones(H), "transformer.word_embeddings_layernorm.bias": torch.zeros(H),
+          "transformer.ln_f.weight": torch.ones(H), "transformer.ln_f.bias": torch.zeros(H)}
+    shapes = {"input_layernorm": (H,), "self_attention.query_key_value": (3 * H, H), "self_attention.dense": (H, H),
+              "post_attention_layernorm": (H,), "mlp.dense_h_to_4h": (4 * H, H), "mlp.dense_4h_to_h": (H, 4 * H)}
+    for i in range(L):
+        for name, shp in shapes.items():
+            sd["transformer.h.%d.%s.weight" % (i, name)] = torch.randn(*shp)
+            sd["transformer.h.%d.%s.bias" % (i, name)] = torch.randn(shp[0])
+    torch.save(sd, tmp_path / "pytorch_model.bin")
+    script = tmp_path / "use_ref_loader.py"
+    script.write_text(textwrap.dedent('''
+        import sys, torch
+        sys.path.insert(0, %r)
+        from examples.inference_bloom import load_model, load_config      # the reference's own file
+        config = load_config(%r)
+        model = load_model(config, %r)
+        assert type(model).__module__ == "cleantransformer_b200.models.modeling_bloom", type(model).__module__
+        assert model.lm_head.weight is model.bloom.word_embeddings.weight and not model.training
+        assert len(model.bloom.blocks) == 2 and model.bloom.blocks[0].self_attention.num_heads == 4
+        sd = torch.load(%r)
+        assert torch.equal(model.bloom.blocks[1].mlp.dense_4h_to_h.weight, sd["transformer.h.1.mlp.dense_4h_to_h.weight"])
+        print("REF-LOADER-OK")
+    ''' % (REF, str(tmp_path / "config.json"), str(tmp_path / "pytorch_model.bin"), str(tmp_path / "pytorch_model.bin"))))
+    out = _run(["-m", "cleantransformer_b200.run", "--ct-keep-default-device", str(script)], cwd=str(tmp_path))
+    assert "REF-LOADER-OK" in out
+
+
+def test_trainer_surface_cpu_side():
+    """Constructor signature / helper behaviour that does not need a GPU."""
+    from cleantransformer_b200.trainer import Trainer
+    with pytest.raises(RuntimeError):
+        Trainer()
+    t = Trainer(model=torch.nn.Linear(2, 2), args=None, train_dataset=[{"x": torch.zeros(2)}] * 5)
+    assert t._arg("learning_rate") == 5e-5 and len(t.get_train_dataloader()) == 1
+    assert float(Trainer._loss_of(((torch.tensor(3.0), None, None), None))) == 3.0
+    assert float(Trainer._loss_of({"loss": torch.tensor(2.0)})) == 2.0
+    for name in ("train", "evaluate", "save_model", "compute_loss", "training_step"):
+        assert callable(getattr(t, name))

@@ -7,7 +7,7 @@ TAG=${1:-run}
 OUT=gpurun_out
 mkdir -p $OUT
 echo "== safe-config tests"; date
-CT_LN_BWD_IMPL=1 CT_ATTN_FWD_IMPL=1 CT_ATTN_BWD_IMPL=1 CT_GEMM_EPI_IMPL=1 timeout 600 \
+[ -n "$SKIP_SAFE" ] || CT_LN_BWD_IMPL=1 CT_ATTN_FWD_IMPL=1 CT_ATTN_BWD_IMPL=1 CT_GEMM_EPI_IMPL=1 timeout 600 \
   python -m pytest tests -m gpu -q -k "not v2" > $OUT/${TAG}_tests_safe.log 2>&1; echo "safe rc=$?"
 tail -3 $OUT/${TAG}_tests_safe.log
 echo "== kernel A/B"; date
@@ -28,7 +28,7 @@ echo "== launches"; date
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $OUT/${TAG}_launches.csv python tools/step_prof.py > $OUT/${TAG}_launches.log 2>&1; echo "launches rc=$?"
 echo "== bench, first-generation kernels"; date
-CT_LN_BWD_IMPL=1 CT_ATTN_FWD_IMPL=1 CT_ATTN_BWD_IMPL=1 CT_GEMM_EPI_IMPL=1 timeout 300 \
+[ -n "$SKIP_SAFE" ] || CT_LN_BWD_IMPL=1 CT_ATTN_FWD_IMPL=1 CT_ATTN_BWD_IMPL=1 CT_GEMM_EPI_IMPL=1 timeout 300 \
   python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_v1.json 2> $OUT/${TAG}_bench_v1.err; echo "bench v1 rc=$?"
 grep -o '"value": [0-9.]*' $OUT/${TAG}_bench_v1.json | head -1
 date

@@ -58,7 +58,7 @@ def ln_ab():
     O.layernorm(xr, wr, br, 1e-5).backward(dy.float())
     want = xr.grad + extra
     stats = [ops.layernorm_fwd(s[0], w, b, 1e-5, out_dtype=torch.bfloat16)[2:] for s in sets]
-    for impl in (1, 0):
+    for impl in (1, 2, 0):
         prev = ops.set_option("LN_BWD_IMPL", impl)
         try:
             dg = torch.empty(H, device=DEV); db = torch.empty(H, device=DEV); cs = torch.empty(H, device=DEV)
