@@ -630,7 +630,9 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
 
     for (int j = 0; j < n_kv; ++j) {
       const int kv0 = j * 128;
+      CT_DBG_STAMP(2048 + 16 * j + 0);
       mbar_wait(s_full, j & 1);
+      CT_DBG_STAMP(2048 + 16 * j + 1);
       tc_fence_after();
       // CTA-uniform tile kind
       const bool touches_diag = p.causal && (kv0 + 127 > q0 + p.off);
@@ -642,6 +644,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
         const int nj = kv0 + 128 + qr;
         kb_next = (j + 1 < n_kv && nj < p.Sk) ? __ldg(kb_row + nj) : 0.f;
       }
+      CT_DBG_STAMP(2048 + 16 * j + 2);
       const bool slow = touches_diag || irregular;
       const bool diag_fast = touches_diag && !irregular && fill_is_ninf && kv0 == q0 + p.off;
       float m_new, alpha, lt;
@@ -660,6 +663,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
         tmem_ld_32x32(t_s + 64, r2);
         tmem_ld_32x32(t_s + 96, r3);
         tmem_ld_wait();
+        CT_DBG_STAMP(2048 + 16 * j + 3);
         float mt = -INFINITY;
         mt = fa2_scale_max<HAS_KB, HAS_KB>(r0, 0, p.sl2, kb_s, mt);
         mt = fa2_scale_max<HAS_KB, HAS_KB>(r1, 32, p.sl2, kb_s, mt);
@@ -669,6 +673,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
         // the next tile's bias staging (single smem buffer) cannot start before every thread got here.
         tc_fence_before();
         mbar_arrive(s_free);
+        CT_DBG_STAMP(2048 + 16 * j + 4);
         if constexpr (!HAS_KB) mt *= p.sl2;  // sl2 > 0 (checked on the host)
         mt = fmaxf(mt, -FLT_MAX);
         m_new = fmaxf(m, mt);
@@ -677,6 +682,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
           mbar_wait(o_full, (j - 1) & 1);
           tc_fence_after();
         }
+        CT_DBG_STAMP(2048 + 16 * j + 5);
         float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
         fa2_exp_store<HAS_KB, BF16>(r0, 0, m_new, p.sl2, p_row, sw, acc0, acc1);
         fa2_exp_store<HAS_KB, BF16>(r1, 1, m_new, p.sl2, p_row, sw, acc0, acc1);
@@ -781,6 +787,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
           }
         }
       }
+      CT_DBG_STAMP(2048 + 16 * j + 6);
       l = l * alpha + lt;
       m = m_new;
       fence_proxy_async_smem();
@@ -802,8 +809,10 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
         tmem_st_32x32(t_o + 32, o1);
         tmem_st_wait();
       }
+      CT_DBG_STAMP(2048 + 16 * j + 7);
       tc_fence_before();
       mbar_arrive(p_ready);
+      CT_DBG_STAMP(2048 + 16 * j + 8);
     }
     // ---- epilogue: O / l -> merged-head layout, lse2 ----
     float o_acc[64];
@@ -1420,7 +1429,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
 
     for (int it = 0; it < n_it; ++it) {
       const int q0 = (i_start + it) * 128;
+      CT_DBG_STAMP(16 * it + 0);
       mbar_wait(sdp_full, it & 1);
+      CT_DBG_STAMP(16 * it + 1);
       tc_fence_after();
       // chunk kinds (warp-uniform)
       const bool touches_diag = p.causal && (kv0 + 127 > q0 + p.off);
@@ -1443,6 +1454,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         mbar_wait(mma_done, (it - 1) & 1);
         tc_fence_after();
       }
+      CT_DBG_STAMP(16 * it + 2);
       // mma_done(it-1) implies pds_ready(it-1): every thread has finished the element math of tile it-1,
       // nobody still reads its statistics
       if (hf == 0) {
@@ -1450,9 +1462,11 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(del_s + 4 * rr), "f"(ndel_next) : "memory");
       }
       tmem_ld_wait();
+      CT_DBG_STAMP(16 * it + 3);
       tc_fence_before();
       mbar_arrive(sdp_free);        // S^T / dP^T are in registers: the next tile's MMAs may overwrite them
       bar_sync_named(1, 256);       // statistics staged by the hf == 0 warps are visible
+      CT_DBG_STAMP(16 * it + 4);
       if (hf == 0) {
         const int nq = q0 + 128 + rr;
         const bool ok = (it + 1 < n_it) && nq < p.Sq;
@@ -1462,6 +1476,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       if (kind0 == 0) fb2_chunk<0, BF16>(cx, rs0, rd0, c0, q0);
       else if (kind0 == 1) fb2_chunk<1, BF16>(cx, rs0, rd0, c0, q0);
       else fb2_chunk<2, BF16>(cx, rs0, rd0, c0, q0);
+      CT_DBG_STAMP(16 * it + 5);
       if (it > 0) {
         // drain dQ(it-1) between the two chunks (T_DQ is only rewritten after pds_ready(it)): the
         // red.global.add traffic overlaps the second chunk's math
@@ -1470,12 +1485,15 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         tmem_ld_wait();
         red_dq(rq, it - 1);
       }
+      CT_DBG_STAMP(16 * it + 6);
       if (kind1 == 0) fb2_chunk<0, BF16>(cx, rs1, rd1, c1, q0);
       else if (kind1 == 1) fb2_chunk<1, BF16>(cx, rs1, rd1, c1, q0);
       else fb2_chunk<2, BF16>(cx, rs1, rd1, c1, q0);
+      CT_DBG_STAMP(16 * it + 7);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_ready);
+      CT_DBG_STAMP(16 * it + 8);
     }
     // ---- last dQ tile, then dK / dV for this key row: 32 of the 64 head-dim columns per thread ----
     if (n_it > 0) {
