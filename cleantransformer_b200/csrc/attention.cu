@@ -872,6 +872,11 @@ struct AttnBwdP {
 constexpr int FB_THREADS = 320;  // TMA warp + MMA warp + 8 compute warps (2 per TMEM lane quarter)
 constexpr int FB_SMEM = 2 * FA_TILE /*K,V*/ + 4 * FA_TILE /*2 x (Q,dO)*/ + 2 * FA_TILE /*P^T*/ +
                         2 * FA_TILE /*dS^T*/ + 128 /*barriers*/ + 1024 /*lse2, delta of the query tile*/;
+// v3 (pipelined): second P^T / dS^T buffer pair and a second statistics buffer
+constexpr int FB_SMEM_PIPE = FB_SMEM + 4 * FA_TILE + 1024;
+// dQ workspace, tiled layout: [b][h][query tile][d/4 (16)][row (128)][4] f32 — a warp's red.global.add.v4 then covers
+// 512 contiguous bytes (32 rows x 16 B) instead of 32 different 128-byte lines
+constexpr int FB_DQ_TILE = 128 * 64;
 
 __device__ __forceinline__ void st_row64(void* basep, int64_t elem_off, const float (&v)[64], int fmt) {
   uint8_t* row = reinterpret_cast<uint8_t*>(basep) + 2 * elem_off;
@@ -1279,7 +1284,9 @@ __device__ __forceinline__ void fb2_chunk(const FbCtx& cx, const uint32_t (&rs)[
   }
 }
 
-template <bool BF16>
+// MODE bit 0: tiled dQ workspace; bit 1: P^T / dS^T (and the statistics) double-buffered, so the element math of
+// query tile it+1 runs under the dQ / dV / dK MMAs of tile it (v2 waits for them before touching the tiles).
+template <bool BF16, int MODE>
 __global__ void __launch_bounds__(FB_THREADS, 1)
     attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -1289,13 +1296,17 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   const uint32_t base = smem_u32(smem);
   const uint32_t sK = base, sV = base + FA_TILE;
   const uint32_t sQ = base + 2 * FA_TILE;   // 2 stages, each Q then dO
+  constexpr bool DQT = (MODE & 1) != 0, PIPE = (MODE & 2) != 0;
+  constexpr int N_TILES = PIPE ? 14 : 10;
+  constexpr uint32_t PDS_STRIDE = PIPE ? 4 * FA_TILE : 0;  // buffer (it & 1) of the P^T / dS^T pair
+  constexpr uint32_t STAT_STRIDE = PIPE ? 1024 : 0;
   const uint32_t sPT = base + 6 * FA_TILE;  // 2 panels
   const uint32_t sDS = base + 8 * FA_TILE;  // 2 panels
-  const uint32_t bars = base + 10 * FA_TILE;
+  const uint32_t bars = base + N_TILES * FA_TILE;
   const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 24, sdp_full = bars + 40,
                  pds_ready = bars + 48, mma_done = bars + 56, dkv_full = bars + 64, tmem_slot = bars + 72,
                  sdp_free = bars + 80, lse_s = bars + 128, del_s = bars + 640;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + 10 * FA_TILE + 72);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + N_TILES * FA_TILE + 72);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kv_tiles = (p.Sk + 127) / 128;
@@ -1371,17 +1382,18 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         if (it + 1 < n_it) issue_sdp(it + 1);  // runs under the element math of tile it
         mbar_wait(pds_ready, it & 1);
         tc_fence_after();
+        const uint32_t pt = sPT + (it & 1) * PDS_STRIDE, dst = sDS + (it & 1) * PDS_STRIDE;
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // dQ[q, d] = dS[q, kv] . K[kv, d]  (A MN-major view of dS^T)
-          umma_f16(T_DQ, umma_smem_desc_sw128(sDS + k * 2048, FA_TILE, 1024),
+          umma_f16(T_DQ, umma_smem_desc_sw128(dst + k * 2048, FA_TILE, 1024),
                    umma_smem_desc_sw128(sK + k * 2048, 64 * 128, 1024), idesc_mm, k > 0);
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // dV[kv, d] += P^T[kv, q] . dO[q, d]   (B MN-major: rows = q)
-          umma_f16(T_DV, umma_smem_desc_sw128(sPT + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+          umma_f16(T_DV, umma_smem_desc_sw128(pt + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
                    umma_smem_desc_sw128(d_o + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // dK[kv, d] += dS^T[kv, q] . Q[q, d]
-          umma_f16(T_DK, umma_smem_desc_sw128(sDS + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+          umma_f16(T_DK, umma_smem_desc_sw128(dst + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
                    umma_smem_desc_sw128(q + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
         umma_commit(qdo_empty + 8 * s);
         umma_commit(mma_done);  // dQ(it) readable; P^T / dS^T tiles free for tile it+1
@@ -1417,10 +1429,19 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
     auto red_dq = [&](const uint32_t (&r)[32], int itp) {
       const int qi = (i_start + itp) * 128 + rr;
       if (qi < p.Sq) {
-        float* dst = bp.dq_accum + (((int64_t)b * p.Sq + qi) * p.H + h) * 64 + hf * 32;
+        float* dst;
+        int gs;  // distance between consecutive 4-float groups of this row
+        if constexpr (DQT) {
+          dst = bp.dq_accum + (((int64_t)b * p.H + h) * n_q_tiles + (i_start + itp)) * FB_DQ_TILE +
+                (hf * 8 * 128 + rr) * 4;
+          gs = 128 * 4;
+        } else {
+          dst = bp.dq_accum + (((int64_t)b * p.Sq + qi) * p.H + h) * 64 + hf * 32;
+          gs = 4;
+        }
 #pragma unroll
         for (int g = 0; g < 8; ++g)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g),
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + gs * g),
                        "f"(__uint_as_float(r[4 * g])), "f"(__uint_as_float(r[4 * g + 1])),
                        "f"(__uint_as_float(r[4 * g + 2])), "f"(__uint_as_float(r[4 * g + 3]))
                        : "memory");
@@ -1429,6 +1450,10 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
 
     for (int it = 0; it < n_it; ++it) {
       const int q0 = (i_start + it) * 128;
+      if constexpr (PIPE) {
+        cx.sPT = sPT + (it & 1) * PDS_STRIDE; cx.sDS = sDS + (it & 1) * PDS_STRIDE;
+        cx.lse_s = lse_s + (it & 1) * STAT_STRIDE; cx.del_s = del_s + (it & 1) * STAT_STRIDE;
+      }
       CT_DBG_STAMP(16 * it + 0);
       mbar_wait(sdp_full, it & 1);
       CT_DBG_STAMP(16 * it + 1);
@@ -1449,17 +1474,20 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       uint32_t rs0[32], rd0[32], rs1[32], rd1[32];
       if (kind0 != 1) { tmem_ld_32x32(T_ST + t_lane + c0 * 32, rs0); tmem_ld_32x32(T_DPT + t_lane + c0 * 32, rd0); }
       if (kind1 != 1) { tmem_ld_32x32(T_ST + t_lane + c1 * 32, rs1); tmem_ld_32x32(T_DPT + t_lane + c1 * 32, rd1); }
-      if (it > 0) {
-        // all MMAs of tile it-1 retired: dQ(it-1) is complete and the P^T / dS^T tiles may be overwritten
-        mbar_wait(mma_done, (it - 1) & 1);
-        tc_fence_after();
+      if constexpr (!PIPE) {
+        if (it > 0) {
+          // all MMAs of tile it-1 retired: dQ(it-1) is complete and the P^T / dS^T tiles may be overwritten
+          mbar_wait(mma_done, (it - 1) & 1);
+          tc_fence_after();
+        }
       }
       CT_DBG_STAMP(16 * it + 2);
-      // mma_done(it-1) implies pds_ready(it-1): every thread has finished the element math of tile it-1,
-      // nobody still reads its statistics
+      // v2: mma_done(it-1) implies pds_ready(it-1): every thread has finished the element math of tile it-1,
+      // nobody still reads its statistics. PIPE: buffer (it & 1) was last read by tile it-2, and every thread
+      // finished tile it-2 before it arrived at the named barrier of tile it-1, which this thread has passed.
       if (hf == 0) {
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(lse_s + 4 * rr), "f"(nlse_next) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(del_s + 4 * rr), "f"(ndel_next) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.lse_s + 4 * rr), "f"(nlse_next) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.del_s + 4 * rr), "f"(ndel_next) : "memory");
       }
       tmem_ld_wait();
       CT_DBG_STAMP(16 * it + 3);
@@ -1480,6 +1508,12 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       if (it > 0) {
         // drain dQ(it-1) between the two chunks (T_DQ is only rewritten after pds_ready(it)): the
         // red.global.add traffic overlaps the second chunk's math
+        if constexpr (PIPE) {
+          // MMAs of tile it-1 ran under chunk 0. Waiting for every phase in order also proves that buffer
+          // ((it+1) & 1) of P^T / dS^T — read by the MMAs of tile it-1 — is free when tile it+1 writes it.
+          mbar_wait(mma_done, (it - 1) & 1);
+          tc_fence_after();
+        }
         uint32_t rq[32];
         tmem_ld_32x32(T_DQ + t_lane + hf * 32, rq);
         tmem_ld_wait();
@@ -1616,6 +1650,40 @@ __global__ void __launch_bounds__(256)
     const float4 lo = __ldcs(reinterpret_cast<const float4*>(acc + el));
     const float4 hi = __ldcs(reinterpret_cast<const float4*>(acc + el) + 1);
     const int64_t off = (int64_t)b * sb + (int64_t)h * sh + (int64_t)i * ss + d;
+    uint4 w;
+    if (fmt == 1) {
+      w.x = pack_bf16x2(lo.x, lo.y); w.y = pack_bf16x2(lo.z, lo.w);
+      w.z = pack_bf16x2(hi.x, hi.y); w.w = pack_bf16x2(hi.z, hi.w);
+    } else {
+      __half2 t;
+      t = __floats2half2_rn(lo.x, lo.y); w.x = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2half2_rn(lo.z, lo.w); w.y = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2half2_rn(hi.x, hi.y); w.z = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2half2_rn(hi.z, hi.w); w.w = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(dq) + off) = w;
+  }
+}
+
+// dq[b,h,i,:] = (bf16) of the TILED workspace [b][h][query tile][d/4][row][4] (D == 64). Eight threads cover one
+// query row (coalesced 128-byte stores); their 16-byte loads pair up with the next row's in full 32-byte sectors.
+__global__ void __launch_bounds__(256)
+    attn_dq_convert_tiled_kernel(const float* __restrict__ acc, void* __restrict__ dq, int fmt, int64_t sb,
+                                 int64_t sh, int64_t ss, int B, int H, int Sq) {
+  const int nqt = (Sq + 127) / 128;
+  const int64_t n = (int64_t)B * H * nqt * 1024;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int d8 = (int)(e & 7), row = (int)((e >> 3) & 127);
+    const int64_t tile = e >> 10;
+    const int qt = (int)(tile % nqt);
+    const int64_t bh = tile / nqt;
+    const int h = (int)(bh % H), b = (int)(bh / H);
+    const int i = qt * 128 + row;
+    if (i >= Sq) continue;
+    const float* src = acc + tile * FB_DQ_TILE + ((2 * d8) * 128 + row) * 4;
+    const float4 lo = __ldcs(reinterpret_cast<const float4*>(src));
+    const float4 hi = __ldcs(reinterpret_cast<const float4*>(src + 128 * 4));
+    const int64_t off = (int64_t)b * sb + (int64_t)h * sh + (int64_t)i * ss + d8 * 8;
     uint4 w;
     if (fmt == 1) {
       w.x = pack_bf16x2(lo.x, lo.y); w.y = pack_bf16x2(lo.z, lo.w);
@@ -2073,28 +2141,54 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     if ((rc = make_qkv_tmap(&tmK, a.k, a.k_sb, a.k_sh, a.k_ss, a.B, a.H, a.Sk, 64))) return rc;
     if ((rc = make_qkv_tmap(&tmV, a.v, a.v_sb, a.v_sh, a.v_ss, a.B, a.H, a.Sk, 64))) return rc;
     if ((rc = make_qkv_tmap(&tmDO, args->dout, a.o_sb, a.o_sh, a.o_ss, a.B, a.H, a.Sq, 64))) return rc;
-    CT_CUDA_OK(cudaMemsetAsync(args->dq_accum, 0, sizeof(float) * (size_t)a.B * a.Sq * a.H * 64, st));
+    // ATTN_BWD_IMPL: 0 = auto, 1 = v1, 2 = v2 (row-major dQ workspace), 3 = v2 + tiled dQ workspace,
+    //                4 = v3 (tiled dQ workspace, P^T / dS^T double-buffered)
+    int variant = option(OPT_ATTN_BWD_IMPL);
+    if (variant < 1 || variant > 4) variant = 2;
+    const bool dq_tiled = variant >= 3;
+    const int nqt = (a.Sq + 127) / 128;
+    // the workspace is sized for whole query tiles (include/ct_b200.h): B*H*ceil(Sq/128)*128*64 floats
+    const size_t dq_elems = (size_t)a.B * a.H * nqt * FB_DQ_TILE;
+    CT_CUDA_OK(cudaMemsetAsync(args->dq_accum, 0,
+                               sizeof(float) * (dq_tiled ? dq_elems : (size_t)a.B * a.Sq * a.H * 64), st));
     static bool attr = false;
     if (!attr) {
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
-      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
-      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       attr = true;
     }
     const int64_t grid = (int64_t)a.B * a.H * ((a.Sk + 127) / 128);
-    // ATTN_BWD_IMPL: 0 = auto (v2 compute warps), 1 = v1
-    if (option(OPT_ATTN_BWD_IMPL) != 1) {
-      if (fmt == 1) attn_bwd_tc2_kernel<true><<<(unsigned)grid, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
-      else attn_bwd_tc2_kernel<false><<<(unsigned)grid, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
-    } else {
-      attn_bwd_tc_kernel<<<(unsigned)grid, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
+    const unsigned g = (unsigned)grid;
+    switch (variant) {
+      case 1: attn_bwd_tc_kernel<<<g, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp); break;
+      case 2:
+        if (fmt == 1) attn_bwd_tc2_kernel<true, 0><<<g, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
+        else attn_bwd_tc2_kernel<false, 0><<<g, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
+        break;
+      case 3:
+        if (fmt == 1) attn_bwd_tc2_kernel<true, 1><<<g, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
+        else attn_bwd_tc2_kernel<false, 1><<<g, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
+        break;
+      default:
+        if (fmt == 1) attn_bwd_tc2_kernel<true, 3><<<g, FB_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
+        else attn_bwd_tc2_kernel<false, 3><<<g, FB_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
+        break;
     }
     CT_LAUNCH_OK();
-    const int64_t n = (int64_t)a.B * a.Sq * a.H * 64 / 8;
+    const int64_t n = dq_tiled ? (int64_t)(dq_elems / 8) : (int64_t)a.B * a.Sq * a.H * 64 / 8;
     int64_t blocks = (n + 255) / 256;
     if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
-    attn_dq_convert_kernel<<<(unsigned)blocks, 256, 0, st>>>(args->dq_accum, args->dq, fmt, args->dq_sb,
-                                                             args->dq_sh, args->dq_ss, a.B, a.H, a.Sq, 64);
+    if (dq_tiled)
+      attn_dq_convert_tiled_kernel<<<(unsigned)blocks, 256, 0, st>>>(args->dq_accum, args->dq, fmt, args->dq_sb,
+                                                                     args->dq_sh, args->dq_ss, a.B, a.H, a.Sq);
+    else
+      attn_dq_convert_kernel<<<(unsigned)blocks, 256, 0, st>>>(args->dq_accum, args->dq, fmt, args->dq_sb,
+                                                               args->dq_sh, args->dq_ss, a.B, a.H, a.Sq, 64);
     CT_LAUNCH_OK();
     return 0;
   }

@@ -202,6 +202,78 @@ __global__ void __launch_bounds__(512)
   wait_flags(my_sig + MAX_WORLD, W, p.epoch);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Tied-embedding gradient, sparse half. The LM-head wgrad of a tied table is dense and ready at the START of
+// backward; the embedding scatter-add arrives at the very END. Reducing the table once both are there
+// (what a bucketed reducer does) leaves a ~1 GB all-reduce with nothing to hide behind. Instead the dense
+// half is all-reduced as soon as the LM-head wgrad is enqueued, and the sparse half is exchanged as what it
+// is: every rank publishes its T x H token gradients + token ids in the symmetric buffer, and every rank
+// scatter-adds ALL ranks' rows (scaled by 1/W) into its own, already averaged, table gradient:
+// (W-1) * T * H * 4 bytes inbound per rank (235 MB at W = 8) instead of 2 (W-1)/W x 1 GB.
+struct EsParams {
+  float* data[MAX_WORLD];
+  uint32_t* sig[MAX_WORLD];
+  int rank, world;
+  uint32_t epoch;
+  int64_t hdr_off;    // float offset of the staging header: int64 T (tokens this rank staged)
+  int64_t rows_off;   // float offset of the staged rows [cap, H] f32
+  int64_t ids_off;    // float offset of the staged ids [cap] int64
+  int64_t grad_off;   // float offset of the table gradient [V, H] in the LOCAL buffer
+  int64_t H, V;
+  long long padding_idx;
+  float scale;
+};
+
+__device__ __forceinline__ long long ld_peer_s64(const long long* p) {
+  long long v;
+  asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+    embed_scatter_allranks_kernel(const EsParams p) {
+  const int W = p.world, r = p.rank;
+  uint32_t* my_sig = p.sig[r];
+  if (blockIdx.x == 0 && (int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + r, p.epoch);
+  wait_flags(my_sig, W, p.epoch);
+
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float* grad = p.data[r] + p.grad_off;
+  for (int k = 0; k < W; ++k) {
+    const int q = (r + k) % W;  // own rows first, then the peers round-robin (spreads the NVLink load)
+    const long long Tq = ld_peer_s64(reinterpret_cast<const long long*>(p.data[q] + p.hdr_off));
+    const long long* ids = reinterpret_cast<const long long*>(p.data[q] + p.ids_off);
+    const float* rows = p.data[q] + p.rows_off;
+    for (int64_t t = warp0; t < Tq; t += nwarps) {
+      const long long id = ld_peer_s64(ids + t);
+      if (id < 0 || id >= p.V || id == p.padding_idx) continue;
+      const float* src = rows + t * p.H;
+      float* dst = grad + id * p.H;
+      for (int64_t c = lane * 4; c < p.H; c += 128) {
+        const float4 v = ld_peer_f4(src + c);
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(v.x * p.scale),
+                     "f"(v.y * p.scale), "f"(v.z * p.scale), "f"(v.w * p.scale)
+                     : "memory");
+      }
+    }
+  }
+  // completion barrier: nobody restages while a peer still reads
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int last;
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(my_sig + 2 * MAX_WORLD, 1u);
+    last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) my_sig[2 * MAX_WORLD] = 0;
+  if ((int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + MAX_WORLD + r, p.epoch);
+  wait_flags(my_sig + MAX_WORLD, W, p.epoch);
+}
+
 static void fill_params(ArParams& p, int64_t offset, int64_t count, float scale) {
   for (int q = 0; q < g_comm.world; ++q) { p.data[q] = g_comm.data[q]; p.sig[q] = g_comm.sig[q]; }
   p.rank = g_comm.rank; p.world = g_comm.world;
@@ -306,6 +378,31 @@ extern "C" int ct_allreduce_bucket(int64_t offset, int64_t count, float scale, i
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
   allreduce_kernel<false><<<(unsigned)ctas, AR_THREADS, 0, st>>>(p);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_embedding_bwd_allranks(int64_t hdr_offset, int64_t rows_offset, int64_t ids_offset,
+                                         int64_t grad_offset, int64_t H, int64_t V, int64_t padding_idx,
+                                         float scale, int max_ctas, void* stream) {
+  CT_REQUIRE(g_comm.ready, CT_ERR_COMM, "ct_embedding_bwd_allranks: comm not initialised");
+  const size_t nfl = g_comm.data_bytes / 4;
+  CT_REQUIRE(H > 0 && (H % 4) == 0 && V > 0 && hdr_offset >= 0 && rows_offset >= 0 && ids_offset >= 0 &&
+                 grad_offset >= 0 && (hdr_offset % 2) == 0 && (rows_offset % 4) == 0 && (ids_offset % 2) == 0 &&
+                 (grad_offset % 4) == 0 && (size_t)hdr_offset + 2 <= nfl && (size_t)rows_offset <= nfl &&
+                 (size_t)ids_offset <= nfl && (size_t)(grad_offset + V * H) <= nfl,
+             CT_ERR_BAD_ARG, "ct_embedding_bwd_allranks: offsets must be aligned and inside the symmetric buffer");
+  EsParams p;
+  {
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    for (int q = 0; q < g_comm.world; ++q) { p.data[q] = g_comm.data[q]; p.sig[q] = g_comm.sig[q]; }
+    p.rank = g_comm.rank; p.world = g_comm.world;
+    p.epoch = ++g_comm.epoch;
+  }
+  p.hdr_off = hdr_offset; p.rows_off = rows_offset; p.ids_off = ids_offset; p.grad_off = grad_offset;
+  p.H = H; p.V = V; p.padding_idx = (long long)padding_idx; p.scale = scale;
+  if (max_ctas <= 0) max_ctas = sm_count() * 2;
+  embed_scatter_allranks_kernel<<<(unsigned)max_ctas, 256, 0, (cudaStream_t)stream>>>(p);
   CT_LAUNCH_OK();
   return 0;
 }

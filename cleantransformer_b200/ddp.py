@@ -19,8 +19,11 @@ B200 design
   * `comm="nccl"` keeps torch.distributed.all_reduce (NCCL on GPUs, gloo in the CPU tests) on the
     same bucket layout as the baseline/oracle.
 Parameters used more than once per step (tied embedding / lm_head) are reduced when the last of
-their gradients has been written (`_ct_expected_writes`, set by EmbeddingFn / tie helpers), in
-practice at the end of backward.
+their gradients has been written (`_ct_expected_writes`, set by the tie helpers), in practice at the
+end of backward — except on the P2P path when the second write is an embedding scatter
+(`_ct_sparse_second_write`): the dense LM-head wgrad is all-reduced the moment it is enqueued (first
+kernel of backward, fully hidden), and the token-row gradients are exchanged sparsely at the end
+(`ct_embedding_bwd_allranks`: (W-1)*T*H*4 bytes per rank instead of an exposed 1 GB all-reduce).
 """
 import ctypes
 import os
@@ -42,13 +45,14 @@ class _CudaView:
                                          "version": 2, "strides": None}
 
 
-def plan_buckets(sizes_offsets, cap_elems):
+def plan_buckets(sizes_offsets, cap_elems, solo=()):
     """sizes_offsets: [(offset, numel_padded)] in arena order. Returns [(lo, hi, [param indices])]
-    covering the arena back to front in chunks of about cap_elems."""
+    covering the arena back to front in chunks of about cap_elems. Indices in `solo` get a bucket of
+    their own (parameters that are reduced on their own schedule)."""
     buckets, cur, cur_lo, cur_hi = [], [], None, None
     for idx in range(len(sizes_offsets) - 1, -1, -1):
         off, n = sizes_offsets[idx]
-        if cur and (cur_hi - off) > cap_elems and (cur_hi - cur_lo) > 0:
+        if cur and (((cur_hi - off) > cap_elems and (cur_hi - cur_lo) > 0) or idx in solo or cur[-1] in solo):
             buckets.append((cur_lo, cur_hi, cur))
             cur, cur_lo, cur_hi = [], None, None
         if not cur:
@@ -83,8 +87,27 @@ class DistributedDataParallel(torch.nn.Module):
         self.final_ctas = int(os.environ.get("CT_DDP_FINAL_CTAS", 148))
         grad_buf = None
         n_total = sum((p.numel() + 63) // 64 * 64 for p in params)
+        # tied tables whose second gradient is an embedding scatter: dense half reduced early, sparse half
+        # exchanged at the end of backward (P2P path only)
+        self._sparse = [p for p in params if getattr(p, "_ct_expected_writes", 1) == 2 and
+                        getattr(p, "_ct_sparse_second_write", False) and p.dim() == 2 and p.shape[1] % 4 == 0]
+        if not (self.comm == "p2p" and self.world > 1) or os.environ.get("CT_DDP_SPARSE_TIED", "1") == "0":
+            self._sparse = []
+        self._stage_cap = int(os.environ.get("CT_DDP_STAGE_TOKENS", 16384))
         if self.comm == "p2p" and self.world > 1:
-            grad_buf = self._init_p2p(n_total)
+            n_stage = 0
+            if self._sparse:
+                hmax = max(p.shape[1] for p in self._sparse)
+                n_stage = 64 + self._stage_cap * hmax + 2 * self._stage_cap  # header | rows f32 | ids int64
+            full = self._init_p2p(n_total + n_stage)
+            grad_buf = full[:n_total]
+            if self._sparse:
+                self._stage_hdr_off = n_total
+                self._stage_rows_off = n_total + 64
+                self._stage_ids_off = n_total + 64 + self._stage_cap * hmax
+                self._stage_hdr = full[n_total:n_total + 2].view(torch.int64)
+                self._stage_rows = full[self._stage_rows_off:self._stage_ids_off]
+                self._stage_ids = full[self._stage_ids_off:self._stage_ids_off + 2 * self._stage_cap].view(torch.int64)
         self.arena = ParamArena(params, grad_buffer=grad_buf)
         # (1) parameter / buffer sync from rank 0 (README.md:47; torch DDP's _sync_module_states)
         dist.broadcast(self.arena.flat, 0, group=self.group)
@@ -98,7 +121,11 @@ class DistributedDataParallel(torch.nn.Module):
         for i, p in enumerate(self.arena.params):
             end = self.arena.offsets[i + 1] if i + 1 < len(self.arena.params) else self.arena.numel
             so.append((self.arena.offsets[i], end - self.arena.offsets[i]))
-        self.buckets = plan_buckets(so, int(bucket_cap_mb * 1024 * 1024 // 4))
+        sparse_ids = {id(p) for p in self._sparse}
+        solo = {i for i, p in enumerate(self.arena.params) if id(p) in sparse_ids}
+        self.buckets = plan_buckets(so, int(bucket_cap_mb * 1024 * 1024 // 4), solo)
+        self._grad_off = {id(p): self.arena.offsets[i] for i, p in enumerate(self.arena.params) if id(p) in sparse_ids}
+        self._early = {}
         self._bucket_of = {}
         for bi, (_, _, idxs) in enumerate(self.buckets):
             for i in idxs:
@@ -117,6 +144,8 @@ class DistributedDataParallel(torch.nn.Module):
                 p._ct_grad_hooks = hooks = []
             hooks.append(self._on_grad_written)
             p.register_post_accumulate_grad_hook(self._on_autograd_grad)
+        for p in self._sparse:
+            p._ct_embedding_bwd_override = self._sparse_embedding_bwd
 
     # ---------------------------------------------------------------- P2P bootstrap
     def _init_p2p(self, n_total):
@@ -146,6 +175,7 @@ class DistributedDataParallel(torch.nn.Module):
         self._launched = [False] * len(self.buckets)
         self._writes = {}
         self._cb_queued = False
+        self._early = {}
 
     # ---------------------------------------------------------------- gradient notifications
     def _on_autograd_grad(self, p):
@@ -163,6 +193,17 @@ class DistributedDataParallel(torch.nn.Module):
             torch.autograd.Variable._execution_engine.queue_callback(self._finish_backward)
         n = self._writes.get(id(p), 0) + 1
         self._writes[id(p)] = n
+        if id(p) in self._grad_off:
+            # tied table on the P2P path: write 1 = dense LM-head wgrad -> reduce now; write 2 must have gone
+            # through _sparse_embedding_bwd (which exchanged it), anything else would be lost
+            if n == 1:
+                self._early[id(p)] = "dense"
+                self._pending[self._bucket_of[id(p)]] -= 1
+                self._launch(self._bucket_of[id(p)])
+            elif self._early.get(id(p)) != "sparse":
+                raise RuntimeError("DistributedDataParallel: second gradient of a tied embedding table did not "
+                                   "come from EmbeddingFn (set CT_DDP_SPARSE_TIED=0 to reduce it densely)")
+            return
         if n != getattr(p, "_ct_expected_writes", 1):
             return
         bi = self._bucket_of[id(p)]
@@ -197,6 +238,36 @@ class DistributedDataParallel(torch.nn.Module):
             else:
                 dist.all_reduce(seg, group=self.group)
                 seg.mul_(1.0 / self.world)
+
+    def _sparse_embedding_bwd(self, param, ids, dout, grad, padding_idx):
+        """EmbeddingFn's scatter for a tied table (functional.EmbeddingFn.backward). `grad` already holds the
+        rank-averaged dense half when the early all-reduce has been launched for this step."""
+        from . import ops
+        if self._pending is None or not self.require_backward_grad_sync or self._early.get(id(param)) != "dense":
+            # not inside a synchronised backward (no_sync / plain use), or the table saw no dense gradient
+            # first: local scatter; with a pending dense reduction of this bucket it is picked up there
+            ops.embedding_bwd(ids, dout, grad, padding_idx)
+            return
+        T, H = ids.numel(), dout.shape[-1]
+        if grad.data_ptr() != param._ct_grad_view.data_ptr():
+            raise RuntimeError("DistributedDataParallel: the tied table's .grad is not its arena view")
+        if T > self._stage_cap:
+            raise RuntimeError("DistributedDataParallel: %d tokens per step exceed the sparse-exchange staging "
+                               "area (%d); raise CT_DDP_STAGE_TOKENS" % (T, self._stage_cap))
+        V = param.shape[0]
+        cur = torch.cuda.current_stream(self.device)
+        self._comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self._comm_stream):
+            self._stage_hdr.fill_(T)
+            self._stage_rows[:T * H].copy_(dout.reshape(-1))
+            self._stage_ids[:T].copy_(ids.reshape(-1))
+            _lib.check(_lib.load().ct_embedding_bwd_allranks(
+                self._stage_hdr_off, self._stage_rows_off, self._stage_ids_off, self._grad_off[id(param)], H, V,
+                int(padding_idx), 1.0 / self.world, self.final_ctas * 2, self._comm_stream.cuda_stream),
+                "ct_embedding_bwd_allranks")
+        dout.record_stream(self._comm_stream)
+        ids.record_stream(self._comm_stream)
+        self._early[id(param)] = "sparse"
 
     def _finish_backward(self):
         # gradients that never arrived (unused parameters) or multi-use parameters still pending:

@@ -306,7 +306,12 @@ class EmbeddingFn(torch.autograd.Function):
             g, acc = grad_buffer(w)
             if not acc:
                 g.zero_()
-            ops.embedding_bwd(i, dout, g, ctx.padding_idx0 if k == 0 else -1)
+            pad = ctx.padding_idx0 if k == 0 else -1
+            override = getattr(w, "_ct_embedding_bwd_override", None)  # ddp.py: sparse exchange of a tied table
+            if override is not None:
+                override(w, i, dout, g, pad)
+            else:
+                ops.embedding_bwd(i, dout, g, pad)
             grad_written(w)
         return (None, None) + (None,) * (2 * len(ctx.ids))
 

@@ -248,6 +248,7 @@ class BloomForCausalLM(torch.nn.Module, GenerationMixin):
         # two gradient contributions per step (lm_head wgrad first, embedding scatter last): the DDP
         # wrapper reduces this bucket only after both have been written
         self.lm_head.weight._ct_expected_writes = 2
+        self.lm_head.weight._ct_sparse_second_write = True  # ... the second one being the token scatter
 
     def forward(self, input_ids, attention_mask=None, head_mask=None, k_v_pasts=None, labels=None, **kwargs):
         hidden_states, k_v_pasts = self.bloom(input_ids, attention_mask, head_mask, k_v_pasts)

@@ -240,6 +240,7 @@ class GPTLMHeadModel(torch.nn.Module, GenerationMixin):
     def _tie_weights(self):
         self.lm_head.weight = self.gpt.tokens_embed.weight
         self.lm_head.weight._ct_expected_writes = 2  # lm_head wgrad + embedding scatter (see ddp.py)
+        self.lm_head.weight._ct_sparse_second_write = True  # ... the second one being the token scatter
 
     def forward(self, input_ids, attention_mask=None, segment_ids=None, position_ids=None, k_v_pasts=None):
         hidden_states, k_v_pasts = self.gpt(input_ids, attention_mask, position_ids, segment_ids, k_v_pasts)

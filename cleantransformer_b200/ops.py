@@ -367,7 +367,8 @@ def attn_bwd(dout, q, k, v, o, lse2, dq, dk, dv, scale, causal=False, causal_fil
     a.dk = dk.data_ptr(); a.dk_sb, a.dk_sh, a.dk_ss = _bhsd_strides(dk)
     a.dv = dv.data_ptr(); a.dv_sb, a.dv_sh, a.dv_ss = _bhsd_strides(dv)
     delta = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
-    dq_acc = torch.empty((B, Sq, H, D), dtype=torch.float32, device=q.device) if D == 64 else None
+    # whole query tiles: the tcgen05 kernels may lay the workspace out per 128-row tile (include/ct_b200.h)
+    dq_acc = torch.empty((B, H, (Sq + 127) // 128 * 128, D), dtype=torch.float32, device=q.device) if D == 64 else None
     a.delta = delta.data_ptr()
     a.dq_accum = ptr(dq_acc)
     _ck(_lib.load().ct_attn_bwd(ctypes.byref(a), stream()), "ct_attn_bwd")

@@ -220,7 +220,8 @@ typedef struct {
 int ct_attn_fwd(const ct_attn_args* args, void* stream);
 
 /* Backward: recomputes P from q,k,lse2; dq/dk/dv use the same (sb,sh,ss) addressing as q/k/v.
- * delta ([B,H,Sq] f32) and dq_accum ([B,Sq,H,D] f32) are caller-allocated workspaces. */
+ * delta ([B,H,Sq] f32) and dq_accum (B*H*ceil(Sq/128)*128*D f32, layout private to the library) are
+ * caller-allocated workspaces. */
 typedef struct {
   ct_attn_args f; /* forward arguments (o = forward output, lse2 = saved statistics) */
   const void* dout; /* same layout as o */
@@ -282,6 +283,14 @@ int ct_scale_by_scalar(void* x, int dtype, int64_t n, const float* device_scalar
  *                    Must be called in the same order by all ranks. max_ctas bounds the SMs used so
  *                    backward compute keeps running (0 = default 32).
  *   ct_broadcast     copy [offset, offset+count) from root's buffer to every rank's buffer.
+ *   ct_embedding_bwd_allranks  sparse half of a TIED embedding gradient (modeling_bloom.py:215-216,
+ *                    modeling_gpt.py:205: lm_head.weight is the token table). Every rank has staged, inside
+ *                    its symmetric buffer, an int64 token count T at hdr_offset, T x H f32 token gradients
+ *                    at rows_offset and T int64 ids at ids_offset (offsets in floats, same on all ranks);
+ *                    every rank then adds scale * rows of ALL ranks into its own table gradient [V,H] at
+ *                    grad_offset (rows with id == padding_idx or out of range are skipped). Replaces
+ *                    "scatter locally, then all-reduce the whole V x H table" — see csrc/comm.cu.
+ *                    Collective: same order on all ranks, same stream discipline as ct_allreduce_bucket.
  * The buffers are library-owned (freed by ct_comm_finalize); PyTorch sees them as non-owning tensors. */
 int ct_comm_init(int rank, int world, int device, size_t data_bytes, void** local_data,
                  void* data_handle_out, void* sig_handle_out);
@@ -289,6 +298,9 @@ int ct_comm_connect(const void* data_handles, const void* sig_handles);
 int ct_allreduce_bucket(int64_t offset, int64_t count, float scale, int mode, int max_ctas,
                         void* stream);
 int ct_broadcast(int64_t offset, int64_t count, int root, void* stream);
+int ct_embedding_bwd_allranks(int64_t hdr_offset, int64_t rows_offset, int64_t ids_offset, int64_t grad_offset,
+                              int64_t H, int64_t V, int64_t padding_idx, float scale, int max_ctas,
+                              void* stream);
 int ct_comm_finalize(void);
 
 

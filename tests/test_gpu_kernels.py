@@ -275,19 +275,22 @@ ATT_CASES = [
     (2, 2, 256, 640, 64, True, 0, "none", -FLT_MAX, 1),     # Sq < Sk: diagonal offset by 384 (aligned)
     (2, 2, 200, 440, 64, True, 0, "right", -FLT_MAX, 1),    # diagonal offset (240) not a multiple of 128
 ]
-# kernel variants of the tcgen05 path: "v2" = defaults, "v1" = first-generation softmax / backward math
+# kernel variants of the tcgen05 path (ATTN_FWD_IMPL, ATTN_BWD_IMPL): "v1" = first-generation softmax / backward
+# math, "v2" = register-resident rows, "v2t" = v2 backward with the tiled dQ workspace, "v3" = backward with
+# double-buffered P^T / dS^T (element math of tile it+1 under the MMAs of tile it)
+ATT_VARIANTS = {"v1": (1, 1), "v2": (0, 2), "v2t": (0, 3), "v3": (0, 4)}
 ATT_PARAMS = [c + ("-",) for c in ATT_CASES if c[-1] == 2] + \
-             [c + (v,) for c in ATT_CASES if c[-1] == 1 for v in ("v1", "v2")]
+             [c + (v,) for c in ATT_CASES if c[-1] == 1 for v in ATT_VARIANTS]
 
 
 class _AttnVariant:
     def __init__(self, variant):
-        self.v = {"v1": 1, "v2": 0}.get(variant)
+        self.v = ATT_VARIANTS.get(variant)
 
     def __enter__(self):
         if self.v is not None:
             ops = _ops()
-            self.prev = (ops.set_option("ATTN_FWD_IMPL", self.v), ops.set_option("ATTN_BWD_IMPL", self.v))
+            self.prev = (ops.set_option("ATTN_FWD_IMPL", self.v[0]), ops.set_option("ATTN_BWD_IMPL", self.v[1]))
 
     def __exit__(self, *exc):
         if self.v is not None:

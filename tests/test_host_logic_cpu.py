@@ -43,6 +43,13 @@ def test_bucket_plan_covers_arena_back_to_front():
         assert lo == so[min(idxs)][0] and hi == so[max(idxs)][0] + so[max(idxs)][1]
     his = [b[1] for b in buckets]
     assert his == sorted(his, reverse=True)
+    # parameters on their own reduction schedule (tied tables: ddp.py) never share a bucket
+    for solo in ({0}, {3}, {5}, {1, 2}):
+        bs = plan_buckets(so, cap_elems=700, solo=solo)
+        assert sorted(i for _, _, idxs in bs for i in idxs) == list(range(len(so)))
+        for lo, hi, idxs in bs:
+            assert lo == so[min(idxs)][0] and hi == so[max(idxs)][0] + so[max(idxs)][1]
+            assert len(idxs) == 1 or not (set(idxs) & solo)
 
 
 def test_greedy_loop_matches_reference_semantics(golden):

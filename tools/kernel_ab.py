@@ -2,7 +2,7 @@
 and CUDA-event time per launch (inputs > L2 are rotated between launches), for
   LayerNorm backward  (LN_BWD_IMPL 1 = warp-per-row, 0 = row spread over cols/4 threads)
   attention forward   (ATTN_FWD_IMPL 1 = v1, 0 = v2)
-  attention backward  (ATTN_BWD_IMPL 1 = v1, 0 = v2)
+  attention backward  (ATTN_BWD_IMPL 1 = v1, 2 = v2, 3 = v2 + tiled dQ workspace, 4 = v3 pipelined)
   GEMM epilogues      (GEMM_EPI_IMPL 1 = generic, 0 = specialised)
 Prints one JSON line per measurement; never asserts (a failing variant shows up as a large error or an
 `error` field), so one GPU visit tells everything.   python tools/kernel_ab.py [ln] [attn] [gemm]
@@ -124,8 +124,8 @@ def attn_ab():
         ref = _attn_oracle(qr, kr, vr, scale, True, fill, kb2[:nb].expand(nb, H, S) if kb2 is not None else None)
         do = torch.randn(B, S, H * D, device=DEV).bfloat16()
         ref.backward(do[:nb].float())
-        for impl in (1, 0):
-            pf, pb = ops.set_option("ATTN_FWD_IMPL", impl), ops.set_option("ATTN_BWD_IMPL", impl)
+        for impl, (fi, bi) in (("v1", (1, 1)), ("v2", (0, 2)), ("v2t", (0, 3)), ("v3", (0, 4))):
+            pf, pb = ops.set_option("ATTN_FWD_IMPL", fi), ops.set_option("ATTN_BWD_IMPL", bi)
             try:
                 o, lse2 = ops.attn_fwd(q, k, v, scale, True, fill, kb2, fv)
                 dqkv = torch.zeros_like(qkv)
