@@ -1513,6 +1513,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
           // ((it+1) & 1) of P^T / dS^T — read by the MMAs of tile it-1 — is free when tile it+1 writes it.
           mbar_wait(mma_done, (it - 1) & 1);
           tc_fence_after();
+          CT_DBG_STAMP(16 * it + 9);
         }
         uint32_t rq[32];
         tmem_ld_32x32(T_DQ + t_lane + hf * 32, rq);
@@ -2141,10 +2142,10 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     if ((rc = make_qkv_tmap(&tmK, a.k, a.k_sb, a.k_sh, a.k_ss, a.B, a.H, a.Sk, 64))) return rc;
     if ((rc = make_qkv_tmap(&tmV, a.v, a.v_sb, a.v_sh, a.v_ss, a.B, a.H, a.Sk, 64))) return rc;
     if ((rc = make_qkv_tmap(&tmDO, args->dout, a.o_sb, a.o_sh, a.o_ss, a.B, a.H, a.Sq, 64))) return rc;
-    // ATTN_BWD_IMPL: 0 = auto, 1 = v1, 2 = v2 (row-major dQ workspace), 3 = v2 + tiled dQ workspace,
+    // ATTN_BWD_IMPL: 0 = auto (v3), 1 = v1, 2 = v2 (row-major dQ workspace), 3 = v2 + tiled dQ workspace,
     //                4 = v3 (tiled dQ workspace, P^T / dS^T double-buffered)
     int variant = option(OPT_ATTN_BWD_IMPL);
-    if (variant < 1 || variant > 4) variant = 2;
+    if (variant < 1 || variant > 4) variant = 4;
     const bool dq_tiled = variant >= 3;
     const int nqt = (a.Sq + 127) / 128;
     // the workspace is sized for whole query tiles (include/ct_b200.h): B*H*ceil(Sq/128)*128*64 floats

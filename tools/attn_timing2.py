@@ -36,5 +36,7 @@ print("BWD v2, block 700: cycles per phase per q tile")
 for it in range(8):
     t = b[16 * it: 16 * it + 9]
     if t[1] == 0: break
+    if b[16 * it + 9] and t[5]:
+        print("   v3: wait for mma_done(it-1) inside dq_drain:", b[16 * it + 9] - t[5])
     print(it, {n: t[i + 1] - t[i] for i, n in enumerate(names_b) if t[i + 1] and t[i]}, "tile_total", t[8] - t[0],
           "next_start_gap", (b[16 * (it + 1)] - t[8]) if b[16 * (it + 1)] else None)
