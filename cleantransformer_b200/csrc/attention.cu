@@ -31,8 +31,20 @@ constexpr float LOG2E = 1.4426950408889634f;
 #ifdef CT_DEBUG_TIMING
 __device__ long long ct_dbg_clk[4096];
 #define CT_DBG_STAMP(slot) do { if (blockIdx.x == CT_DBG_BLOCK && threadIdx.x == CT_DBG_THREAD && (slot) < 4096) ct_dbg_clk[(slot)] = clock64(); } while (0)
+// whole-CTA timeline of every 64th block (slots 1024 + 8 * (block / 64) + k): clock64 for k < 6, globaltimer (ns) at
+// entry / exit in slots 6 / 7
+__device__ __forceinline__ long long ct_dbg_gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define CT_DBG_CTA(k) do { if ((blockIdx.x & 63) == 60 && threadIdx.x == CT_DBG_THREAD && blockIdx.x < 64 * 128) { \
+    ct_dbg_clk[1024 + 8 * (blockIdx.x >> 6) + (k)] = clock64(); \
+    if ((k) == 0) ct_dbg_clk[1024 + 8 * (blockIdx.x >> 6) + 6] = ct_dbg_gtime(); \
+    if ((k) == 5) ct_dbg_clk[1024 + 8 * (blockIdx.x >> 6) + 7] = ct_dbg_gtime(); } } while (0)
 #else
 #define CT_DBG_STAMP(slot) do {} while (0)
+#define CT_DBG_CTA(k) do {} while (0)
 #endif
 #ifndef CT_DBG_BLOCK
 #define CT_DBG_BLOCK 700
@@ -1321,6 +1333,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
     if (!full_sweep) i_start = max(0, (kv0 - p.off) / 128);
   }
   const int n_it = max(0, n_q_tiles - i_start);
+  CT_DBG_CTA(0);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
@@ -1424,6 +1437,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       ndel_next = -__ldg(del_bh + i_start * 128 + rr) * p.scale;
     }
     const int c0 = 2 * hf, c1 = 2 * hf + 1;
+    CT_DBG_CTA(1);
 
     // dQ rows of query tile `itp`: this thread owns query row (q0 + rr), columns [32*hf, 32*hf + 32) of d
     auto red_dq = [&](const uint32_t (&r)[32], int itp) {
@@ -1530,6 +1544,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       mbar_arrive(pds_ready);
       CT_DBG_STAMP(16 * it + 8);
     }
+    CT_DBG_CTA(2);
     // ---- last dQ tile, then dK / dV for this key row: 32 of the 64 head-dim columns per thread ----
     if (n_it > 0) {
       mbar_wait(mma_done, (n_it - 1) & 1);
@@ -1538,6 +1553,313 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       tmem_ld_32x32(T_DQ + t_lane + hf * 32, rq);
       tmem_ld_wait();
       red_dq(rq, n_it - 1);
+      mbar_wait(dkv_full, 0);
+      tc_fence_after();
+    }
+    CT_DBG_CTA(3);
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint32_t r[32];
+      if (n_it > 0) {
+        tmem_ld_32x32((which == 0 ? T_DV : T_DK) + t_lane + hf * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) r[t] = 0u;
+      }
+      if (!cx.key_oob) {
+        void* basep = which == 0 ? bp.dv : bp.dk;
+        const int64_t eo = which == 0
+            ? (int64_t)b * bp.dv_sb + (int64_t)h * bp.dv_sh + (int64_t)jg * bp.dv_ss
+            : (int64_t)b * bp.dk_sb + (int64_t)h * bp.dk_sh + (int64_t)jg * bp.dk_ss;
+        uint8_t* row = reinterpret_cast<uint8_t*>(basep) + 2 * (eo + hf * 32);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          const float f0 = __uint_as_float(r[8 * g]), f1 = __uint_as_float(r[8 * g + 1]),
+                      f2 = __uint_as_float(r[8 * g + 2]), f3 = __uint_as_float(r[8 * g + 3]),
+                      f4 = __uint_as_float(r[8 * g + 4]), f5 = __uint_as_float(r[8 * g + 5]),
+                      f6 = __uint_as_float(r[8 * g + 6]), f7 = __uint_as_float(r[8 * g + 7]);
+          if constexpr (BF16) {
+            w.x = pack_bf16x2(f0, f1); w.y = pack_bf16x2(f2, f3); w.z = pack_bf16x2(f4, f5); w.w = pack_bf16x2(f6, f7);
+          } else {
+            __half2 x;
+            x = __floats2half2_rn(f0, f1); w.x = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f2, f3); w.y = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f4, f5); w.z = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f6, f7); w.w = *reinterpret_cast<uint32_t*>(&x);
+          }
+          *reinterpret_cast<uint4*>(row + 16 * g) = w;
+        }
+      }
+    }
+  }
+  CT_DBG_CTA(4);
+  tc_fence_before();
+  __syncthreads();
+  CT_DBG_CTA(5);
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// v4: v3 (tiled dQ workspace, P^T / dS^T double-buffered) with the dQ drain moved off the compute warps. The
+// r01f stamps put 900-1900 of v3's ~4700 cycles per query tile into the eight red.global.add.v4 per compute
+// thread (LSU-bound: the warp sits in the issue queue while its MUFU / FMA work waits). Here a fourth warpgroup
+// owns the drain: T_DQ is double-buffered in TMEM (the last 64 free columns), the drain warps pull tile it out
+// as soon as its MMAs retire and release the buffer before issuing their reds, and the compute warps never touch
+// dQ. 512 threads = 4 warpgroups; setmaxnreg moves registers from the TMA/MMA and drain groups to the compute
+// groups (launch bound 128/thread -> 40 / 72 / 200).
+constexpr int FB3_THREADS = 512;
+template <uint32_t N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <uint32_t N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+template <bool BF16>
+__global__ void __launch_bounds__(FB3_THREADS, 1)
+    attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                        const AttnBwdP bp) {
+  const AttnP& p = bp.f;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t sK = base, sV = base + FA_TILE;
+  const uint32_t sQ = base + 2 * FA_TILE;   // 2 stages, each Q then dO
+  constexpr int N_TILES = 14;
+  constexpr uint32_t PDS_STRIDE = 4 * FA_TILE;  // buffer (it & 1) of the P^T / dS^T pair
+  constexpr uint32_t STAT_STRIDE = 1024;
+  const uint32_t sPT = base + 6 * FA_TILE;  // 2 panels
+  const uint32_t sDS = base + 8 * FA_TILE;  // 2 panels
+  const uint32_t bars = base + N_TILES * FA_TILE;
+  const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 24, sdp_full = bars + 40,
+                 pds_ready = bars + 48, dkv_full = bars + 64, tmem_slot = bars + 72, sdp_free = bars + 80,
+                 tile_done = bars + 88 /* 2: all MMAs of tile it retired (buffer it & 1) */,
+                 dq_free = bars + 104 /* 2: T_DQ[it & 1] is in the drain warps' registers */,
+                 lse_s = bars + 128, del_s = bars + 640;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + N_TILES * FA_TILE + 72);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_kv_tiles = (p.Sk + 127) / 128;
+  const int kv_tile = blockIdx.x % n_kv_tiles;
+  const int bh = blockIdx.x / n_kv_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int kv0 = kv_tile * 128;
+  const int n_q_tiles = (p.Sq + 127) / 128;
+  int i_start = 0;
+  if (p.causal) {
+    const bool full_sweep = p.first_valid && (p.first_valid[b] > p.off);
+    if (!full_sweep) i_start = max(0, (kv0 - p.off) / 128);
+  }
+  const int n_it = max(0, n_q_tiles - i_start);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full + 8 * s, 1); mbar_init(qdo_empty + 8 * s, 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_free, 256);
+    mbar_init(pds_ready, 256);
+    for (int s = 0; s < 2; ++s) { mbar_init(tile_done + 8 * s, 1); mbar_init(dq_free + 8 * s, 128); }
+    mbar_init(dkv_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t T_ST = tmem, T_DPT = tmem + 128, T_DV = tmem + 256, T_DK = tmem + 320, T_DQ = tmem + 384;  // 2 x 64
+
+  // setmaxnreg inside each role branch: ptxas sizes a region's registers by the setmaxnreg that dominates it
+  const int wg = warp >> 2;
+  if (wg == 3) {
+    setmaxnreg_dec<72>();
+    // ------------------------------ dQ drain: one thread per query row, all 64 columns ------------------------------
+    const int wq = warp & 3;
+    const int rr = wq * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(wq * 32) << 16;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1;
+      mbar_wait(tile_done + 8 * s, (it >> 1) & 1);
+      tc_fence_after();
+      const int qi = (i_start + it) * 128 + rr;
+      float* dst = bp.dq_accum + (((int64_t)b * p.H + h) * n_q_tiles + (i_start + it)) * FB_DQ_TILE + rr * 4;
+      uint32_t r[32];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        tmem_ld_32x32(T_DQ + s * 64 + t_lane + half * 32, r);
+        tmem_ld_wait();
+        if (half == 1) {
+          tc_fence_before();
+          mbar_arrive(dq_free + 8 * s);  // dQ(it+2) may overwrite the buffer; the reds below run under later tiles
+        }
+        if (qi < p.Sq) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 512 * (8 * half + g)),
+                         "f"(__uint_as_float(r[4 * g])), "f"(__uint_as_float(r[4 * g + 1])),
+                         "f"(__uint_as_float(r[4 * g + 2])), "f"(__uint_as_float(r[4 * g + 3]))
+                         : "memory");
+        }
+      }
+    }
+  } else if (wg == 0) {
+   setmaxnreg_dec<56>();
+   if (warp == 0) {
+    if (lane == 0 && n_it > 0) {
+      mbar_expect_tx(kv_full, 2 * FA_TILE);
+      tma_load_4d(sK, &tmK, kv_full, 0, kv0, h, b);
+      tma_load_4d(sV, &tmV, kv_full, 0, kv0, h, b);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1, q0 = (i_start + it) * 128;
+        mbar_wait(qdo_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(qdo_full + 8 * s, 2 * FA_TILE);
+        tma_load_4d(sQ + s * 2 * FA_TILE, &tmQ, qdo_full + 8 * s, 0, q0, h, b);
+        tma_load_4d(sQ + s * 2 * FA_TILE + FA_TILE, &tmDO, qdo_full + 8 * s, 0, q0, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_it > 0) {
+      const uint32_t idesc_kk = umma_idesc_f16(BF16 ? 1 : 0, 0, 0, 128, 128);  // S^T, dP^T
+      const uint32_t idesc_km = umma_idesc_f16(BF16 ? 1 : 0, 0, 1, 128, 64);   // dV, dK
+      const uint32_t idesc_mm = umma_idesc_f16(BF16 ? 1 : 0, 1, 1, 128, 64);   // dQ
+      auto issue_sdp = [&](int it) {
+        const int s = it & 1;
+        const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
+        mbar_wait(qdo_full + 8 * s, (it >> 1) & 1);
+        if (it > 0) mbar_wait(sdp_free, (it - 1) & 1);  // every compute thread holds S^T/dP^T(it-1) in registers
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // S^T[kv, q] = K[kv, d] . Q[q, d]
+          umma_f16(T_ST, umma_smem_desc_sw128(sK + k * 32, 0, 1024), umma_smem_desc_sw128(q + k * 32, 0, 1024),
+                   idesc_kk, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dP^T[kv, q] = V[kv, d] . dO[q, d]
+          umma_f16(T_DPT, umma_smem_desc_sw128(sV + k * 32, 0, 1024),
+                   umma_smem_desc_sw128(d_o + k * 32, 0, 1024), idesc_kk, k > 0);
+        umma_commit(sdp_full);
+      };
+      mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
+        if (it + 1 < n_it) issue_sdp(it + 1);  // runs under the element math of tile it
+        mbar_wait(pds_ready, it & 1);
+        tc_fence_after();
+        const uint32_t pt = sPT + (it & 1) * PDS_STRIDE, dst = sDS + (it & 1) * PDS_STRIDE;
+        if (it >= 2) {  // dQ(it-2) has left T_DQ[it & 1]
+          mbar_wait(dq_free + 8 * s, ((it >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ[q, d] = dS[q, kv] . K[kv, d]  (A MN-major view of dS^T)
+          umma_f16(T_DQ + s * 64, umma_smem_desc_sw128(dst + k * 2048, FA_TILE, 1024),
+                   umma_smem_desc_sw128(sK + k * 2048, 64 * 128, 1024), idesc_mm, k > 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV[kv, d] += P^T[kv, q] . dO[q, d]   (B MN-major: rows = q)
+          umma_f16(T_DV, umma_smem_desc_sw128(pt + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                   umma_smem_desc_sw128(d_o + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dK[kv, d] += dS^T[kv, q] . Q[q, d]
+          umma_f16(T_DK, umma_smem_desc_sw128(dst + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                   umma_smem_desc_sw128(q + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
+        umma_commit(qdo_empty + 8 * s);
+        umma_commit(tile_done + 8 * s);  // dQ(it) readable; P^T / dS^T buffer (it & 1) free for tile it+2
+      }
+      umma_commit(dkv_full);
+    }
+   }
+  } else {
+    setmaxnreg_inc<184>();
+    const int wq = warp & 3;
+    const int rr = wq * 32 + lane;   // key row inside the tile (S^T)
+    const int hf = wg - 1;           // which pair of 32-query chunks this warp owns
+    const int jg = kv0 + rr;
+    const uint32_t t_lane = (uint32_t)(wq * 32) << 16;
+    FbCtx cx;
+    cx.kb = (p.kbias2 && jg < p.Sk) ? __ldg(p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh + jg) : 0.f;
+    cx.sl2 = p.sl2; cx.scale = p.scale; cx.cf2 = p.causal_fill2;
+    cx.jg = jg; cx.off = p.off; cx.causal = p.causal; cx.key_oob = jg >= p.Sk;
+    cx.lse_s = lse_s; cx.del_s = del_s; cx.sPT = sPT; cx.sDS = sDS; cx.rr = rr; cx.sw = rr & 7;
+    // generic arithmetic for the whole warp when a key is masked (the reference's finite fill matters on
+    // fully masked query rows) or the key tile is ragged
+    const bool warp_generic = __any_sync(0xffffffffu, cx.kb < -1e30f) || (kv0 + 128 > p.Sk);
+    const bool fill_is_ninf = p.causal_fill2 == -INFINITY;
+    const float* lse_bh = p.lse2 + ((int64_t)b * p.H + h) * p.Sq;
+    const float* del_bh = bp.delta + ((int64_t)b * p.H + h) * p.Sq;
+    // per-query statistics of the current query tile, staged as -lse2 and -delta*scale
+    float nlse_next = -INFINITY, ndel_next = 0.f;
+    if (hf == 0 && n_it > 0 && i_start * 128 + rr < p.Sq) {
+      nlse_next = -__ldg(lse_bh + i_start * 128 + rr);
+      ndel_next = -__ldg(del_bh + i_start * 128 + rr) * p.scale;
+    }
+    const int c0 = 2 * hf, c1 = 2 * hf + 1;
+
+    for (int it = 0; it < n_it; ++it) {
+      const int q0 = (i_start + it) * 128;
+      cx.sPT = sPT + (it & 1) * PDS_STRIDE; cx.sDS = sDS + (it & 1) * PDS_STRIDE;
+      cx.lse_s = lse_s + (it & 1) * STAT_STRIDE; cx.del_s = del_s + (it & 1) * STAT_STRIDE;
+      CT_DBG_STAMP(16 * it + 0);
+      mbar_wait(sdp_full, it & 1);
+      CT_DBG_STAMP(16 * it + 1);
+      tc_fence_after();
+      // chunk kinds (warp-uniform)
+      const bool touches_diag = p.causal && (kv0 + 127 > q0 + p.off);
+      const bool aligned_diag = touches_diag && fill_is_ninf && (kv0 == q0 + p.off) && !warp_generic;
+      int kind0, kind1;
+      if (warp_generic || (touches_diag && !aligned_diag)) {
+        kind0 = kind1 = 2;
+      } else if (aligned_diag) {
+        // key row 32*wq+l vs queries 32*c..32*c+31: c < wq entirely future, c > wq entirely visible
+        kind0 = c0 < wq ? 1 : (c0 > wq ? 0 : 2);
+        kind1 = c1 < wq ? 1 : (c1 > wq ? 0 : 2);
+      } else {
+        kind0 = kind1 = 0;
+      }
+      uint32_t rs0[32], rd0[32], rs1[32], rd1[32];
+      if (kind0 != 1) { tmem_ld_32x32(T_ST + t_lane + c0 * 32, rs0); tmem_ld_32x32(T_DPT + t_lane + c0 * 32, rd0); }
+      if (kind1 != 1) { tmem_ld_32x32(T_ST + t_lane + c1 * 32, rs1); tmem_ld_32x32(T_DPT + t_lane + c1 * 32, rd1); }
+      CT_DBG_STAMP(16 * it + 2);
+      // statistics buffer (it & 1) was last read by tile it-2, and every thread
+      // finished tile it-2 before it arrived at the named barrier of tile it-1, which this thread has passed.
+      if (hf == 0) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.lse_s + 4 * rr), "f"(nlse_next) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.del_s + 4 * rr), "f"(ndel_next) : "memory");
+      }
+      tmem_ld_wait();
+      CT_DBG_STAMP(16 * it + 3);
+      tc_fence_before();
+      mbar_arrive(sdp_free);        // S^T / dP^T are in registers: the next tile's MMAs may overwrite them
+      bar_sync_named(1, 256);       // statistics staged by the hf == 0 warps are visible
+      CT_DBG_STAMP(16 * it + 4);
+      if (hf == 0) {
+        const int nq = q0 + 128 + rr;
+        const bool ok = (it + 1 < n_it) && nq < p.Sq;
+        nlse_next = ok ? -__ldg(lse_bh + nq) : -INFINITY;
+        ndel_next = ok ? -__ldg(del_bh + nq) * p.scale : 0.f;
+      }
+      if (kind0 == 0) fb2_chunk<0, BF16>(cx, rs0, rd0, c0, q0);
+      else if (kind0 == 1) fb2_chunk<1, BF16>(cx, rs0, rd0, c0, q0);
+      else fb2_chunk<2, BF16>(cx, rs0, rd0, c0, q0);
+      CT_DBG_STAMP(16 * it + 5);
+      if (it > 0) {
+        // MMAs of tile it-1 ran under chunk 0; buffer ((it+1) & 1) of P^T / dS^T, which they read, is written
+        // by tile it+1. (The barrier cannot run a phase ahead: its next completion needs pds_ready(it+1).)
+        mbar_wait(tile_done + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);
+        tc_fence_after();
+      }
+      CT_DBG_STAMP(16 * it + 6);
+      if (kind1 == 0) fb2_chunk<0, BF16>(cx, rs1, rd1, c1, q0);
+      else if (kind1 == 1) fb2_chunk<1, BF16>(cx, rs1, rd1, c1, q0);
+      else fb2_chunk<2, BF16>(cx, rs1, rd1, c1, q0);
+      CT_DBG_STAMP(16 * it + 7);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_ready);
+      CT_DBG_STAMP(16 * it + 8);
+    }
+    // ---- dK / dV for this key row: 32 of the 64 head-dim columns per thread ----
+    if (n_it > 0) {
       mbar_wait(dkv_full, 0);
       tc_fence_after();
     }
@@ -2143,9 +2465,9 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     if ((rc = make_qkv_tmap(&tmV, a.v, a.v_sb, a.v_sh, a.v_ss, a.B, a.H, a.Sk, 64))) return rc;
     if ((rc = make_qkv_tmap(&tmDO, args->dout, a.o_sb, a.o_sh, a.o_ss, a.B, a.H, a.Sq, 64))) return rc;
     // ATTN_BWD_IMPL: 0 = auto (v3), 1 = v1, 2 = v2 (row-major dQ workspace), 3 = v2 + tiled dQ workspace,
-    //                4 = v3 (tiled dQ workspace, P^T / dS^T double-buffered)
+    //                4 = v3 (tiled dQ workspace, P^T / dS^T double-buffered), 5 = v4 (v3 + dedicated dQ drain warpgroup)
     int variant = option(OPT_ATTN_BWD_IMPL);
-    if (variant < 1 || variant > 4) variant = 4;
+    if (variant < 1 || variant > 5) variant = 4;
     const bool dq_tiled = variant >= 3;
     const int nqt = (a.Sq + 127) / 128;
     // the workspace is sized for whole query tiles (include/ct_b200.h): B*H*ceil(Sq/128)*128*64 floats
@@ -2161,6 +2483,8 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       attr = true;
     }
     const int64_t grid = (int64_t)a.B * a.H * ((a.Sk + 127) / 128);
@@ -2174,6 +2498,10 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
       case 3:
         if (fmt == 1) attn_bwd_tc2_kernel<true, 1><<<g, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
         else attn_bwd_tc2_kernel<false, 1><<<g, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
+        break;
+      case 5:
+        if (fmt == 1) attn_bwd_tc3_kernel<true><<<g, FB3_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
+        else attn_bwd_tc3_kernel<false><<<g, FB3_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
         break;
       default:
         if (fmt == 1) attn_bwd_tc2_kernel<true, 3><<<g, FB_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);

@@ -228,6 +228,174 @@ __global__ void __launch_bounds__(CE_THREADS)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// cross entropy, one HBM pass: the row lives in the shared memory of a 4-CTA cluster
+// ---------------------------------------------------------------------------------------------
+// ce_fwd_kernel reads every logit twice (statistics, then gradients); at V = 250 880 the 592 rows in flight are
+// 297 MB — more than L2 — so the second read comes from HBM again: 12.3 GB per Bloom-560M step for 8.2 GB of
+// algorithmic traffic (profiles/r01e: 1.98 ms at 6.2 TB/s, i.e. already at the HBM roof for what it moves).
+// Here a cluster of CEC_C CTAs owns one row at a time, each CTA keeping a quarter of it (125 KB of bf16) in
+// shared memory: the slice arrives through cp.async.bulk in 16 KB chunks (one mbarrier per chunk), the
+// statistics pass reads it from shared memory as the chunks land, the CTAs exchange their (max, sum) pairs
+// through distributed shared memory, and the gradient pass re-reads the slice from shared memory. As soon as a
+// chunk has been consumed by the gradient pass the same chunk of the NEXT row is requested, so the loads of row
+// r+1 run under the gradient stores of row r. Exponentials in the log2 domain (ex2.approx), fp32 sums.
+constexpr int CEC_C = 4;
+constexpr int CEC_THREADS = 1024;
+constexpr int CEC_MAX_CHUNKS = 13;  // 13 x 16 KB = 208 KB of shared memory for the slice
+
+__device__ __forceinline__ float ce_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// (max, sum of 2^(t - max)); a side that saw nothing is (-inf, 0)
+__device__ __forceinline__ void ms_merge2(float& m, float& s, float m2, float s2) {
+  const float mn = fmaxf(m, m2);
+  const float a = (m == mn) ? 1.f : ce_ex2(m - mn);
+  const float b = (m2 == mn) ? 1.f : ce_ex2(m2 - mn);
+  s = s * a + s2 * b;
+  m = mn;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_shared_cluster_f2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+
+__global__ void __cluster_dims__(CEC_C, 1, 1) __launch_bounds__(CEC_THREADS, 1)
+    ce_fwd_cluster_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, const long long* __restrict__ labels,
+                          __nv_bfloat16* __restrict__ dlogits, int64_t ldd, float* __restrict__ row_loss,
+                          const float* __restrict__ stats, int64_t rows, int64_t V, int64_t S, int shift,
+                          long long ignore_index, int slice_vec) {
+  extern __shared__ __align__(128) uint8_t ce_smem[];
+  __shared__ __align__(8) unsigned long long full_bar[CEC_MAX_CHUNKS];
+  __shared__ __align__(8) float xchg[2][CEC_C][2];  // [row parity][cluster rank] = (max2, sum2)
+  __shared__ float red[2 * (CEC_THREADS >> 5)];
+  const uint32_t buf = smem_u32(ce_smem);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t crank = cluster_ctarank();
+  const int64_t cid = blockIdx.x / CEC_C, n_clusters = gridDim.x / CEC_C;
+  const int64_t nvec = V >> 3;
+  const int64_t v0 = min(nvec, (int64_t)crank * slice_vec);
+  const int my_len = (int)(min(nvec, v0 + slice_vec) - v0);  // uint4 (8 logits) in this CTA's slice
+  const int n_chunks = (my_len + CEC_THREADS - 1) / CEC_THREADS;
+  const float inv_count = 1.f / fmaxf(stats[0], 1.f);
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+
+  if (tid == 0) {
+    for (int k = 0; k < CEC_MAX_CHUNKS; ++k) mbar_init(smem_u32(&full_bar[k]), 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto request = [&](int64_t r, int k) {  // thread 0: chunk k of row r -> shared memory
+    const int len = min(CEC_THREADS, my_len - k * CEC_THREADS);
+    const uint32_t bar = smem_u32(&full_bar[k]);
+    mbar_expect_tx(bar, 16u * len);
+    bulk_g2s(buf + 16u * CEC_THREADS * k, logits + r * ld + 8 * (v0 + (int64_t)k * CEC_THREADS), 16u * len, bar);
+  };
+  if (tid == 0 && cid < rows)
+    for (int k = 0; k < n_chunks; ++k) request(cid, k);
+  cluster_sync_all();  // peers' barriers and exchange slots exist before anyone writes to them
+
+  uint32_t ph = 0;
+  for (int64_t r = cid; r < rows; r += n_clusters, ph ^= 1) {
+    const long long tgt = ce_target(labels, r, S, shift);
+    const bool valid = (tgt != ignore_index && tgt >= 0 && tgt < V);
+    // ---- pass 1: (max, sum) of this thread's elements as the chunks land ----
+    float m = -INFINITY, s = 0.f;
+    for (int k = 0; k < n_chunks; ++k) {
+      mbar_wait(smem_u32(&full_bar[k]), ph);
+      const int idx = k * CEC_THREADS + tid;
+      if (idx < my_len) {
+        const uint4 u = *reinterpret_cast<const uint4*>(ce_smem + 16 * idx);
+        float v[8];
+        float2 f;
+        f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+        float mx = v[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) mx = fmaxf(mx, v[i]);
+        mx *= LOG2E;
+        if (mx > m) {  // rare once the running maximum has settled
+          s *= ce_ex2(m - mx);
+          m = mx;
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += ce_ex2(fmaf(v[i], LOG2E, -m));
+        s += acc;
+      }
+    }
+    // ---- block, then cluster reduction ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      ms_merge2(m, s, m2, s2);
+    }
+    if (lane == 0) { red[2 * w] = m; red[2 * w + 1] = s; }
+    __syncthreads();
+    if (w == 0) {
+      m = red[2 * lane]; s = red[2 * lane + 1];  // CEC_THREADS / 32 == 32 warps
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        ms_merge2(m, s, m2, s2);
+      }
+      if (lane < CEC_C) st_shared_cluster_f2(mapa_shared(smem_u32(&xchg[ph][crank][0]), lane), m, s);
+    }
+    cluster_sync_all();  // release/acquire: every CTA's pair is visible in every CTA's slots
+    m = xchg[ph][0][0]; s = xchg[ph][0][1];
+#pragma unroll
+    for (int q = 1; q < CEC_C; ++q) ms_merge2(m, s, xchg[ph][q][0], xchg[ph][q][1]);
+    const float lse2 = m + log2f(s);
+    if (row_loss) {
+      if (!valid) {
+        if (crank == 0 && tid == 0) row_loss[r] = 0.f;
+      } else if (tid == 0 && (tgt >> 3) >= v0 && (tgt >> 3) < v0 + my_len) {
+        const __nv_bfloat16 xt = reinterpret_cast<const __nv_bfloat16*>(ce_smem)[tgt - 8 * v0];
+        row_loss[r] = lse2 * LN2 - __bfloat162float(xt);
+      }
+    }
+    // ---- pass 2: gradients from shared memory; refill each chunk with the next row as soon as it is consumed ----
+    const int64_t r_next = r + n_clusters;
+    uint4* d8 = dlogits ? reinterpret_cast<uint4*>(dlogits + r * ldd) + v0 : nullptr;
+    for (int k = 0; k < n_chunks; ++k) {
+      const int idx = k * CEC_THREADS + tid;
+      if (idx < my_len && d8) {
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) {
+          const uint4 u = *reinterpret_cast<const uint4*>(ce_smem + 16 * idx);
+          float v[8];
+          float2 f;
+          f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+          f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+          f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+          f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+          const int64_t c0 = (v0 + idx) << 3;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float pg = ce_ex2(fmaf(v[i], LOG2E, -lse2));
+            if (c0 + i == tgt) pg -= 1.f;
+            v[i] = pg * inv_count;
+          }
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        }
+        d8[idx] = o;
+      }
+      __syncthreads();  // every thread is done with chunk k of row r
+      if (tid == 0 && r_next < rows) request(r_next, k);
+    }
+  }
+  cluster_sync_all();  // no CTA leaves while a peer could still address its shared memory
+}
+
 // loss = sum(row_loss) / count   (single block, deterministic order)
 __global__ void __launch_bounds__(1024)
     ce_finalize_kernel(const float* __restrict__ row_loss, int64_t rows, const float* __restrict__ stats,
@@ -293,6 +461,29 @@ extern "C" int ct_cross_entropy_fwd(const void* logits, int dtype, int64_t ld, c
   CT_CUDA_OK(cudaMemsetAsync(stats, 0, 16, st));
   ce_count_kernel<<<64, 256, 0, st>>>((const long long*)labels, rows, S, shift, (long long)ignore_index, V, stats);
   CT_LAUNCH_OK();
+  // CE_IMPL: 0 = auto, 1 = two-pass kernel (row re-read through L2 / HBM), 2 = row resident in cluster shared memory
+  const int64_t nvec = V >> 3;
+  const int slice_vec = (int)((nvec + CEC_C - 1) / CEC_C);
+  const bool cluster_ok = dtype == DT_BF16 && (V & 7) == 0 && (ld & 7) == 0 && (!dlogits || (ldd & 7) == 0) &&
+                          ((uintptr_t)logits & 15) == 0 && ((uintptr_t)dlogits & 15) == 0 &&
+                          slice_vec <= CEC_MAX_CHUNKS * CEC_THREADS;
+  const int ce_impl = option(OPT_CE_IMPL);
+  if (cluster_ok && (ce_impl == 2 || (ce_impl == 0 && false))) {
+    const size_t smem = (size_t)16 * ((slice_vec + CEC_THREADS - 1) / CEC_THREADS) * CEC_THREADS;
+    static bool attr = false;
+    if (!attr) {
+      CT_CUDA_OK(cudaFuncSetAttribute(ce_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      16 * CEC_MAX_CHUNKS * CEC_THREADS));
+      attr = true;
+    }
+    int64_t clusters = sm_count() / CEC_C;
+    if (clusters > rows) clusters = rows;
+    if (clusters < 1) clusters = 1;
+    ce_fwd_cluster_kernel<<<(unsigned)(clusters * CEC_C), CEC_THREADS, smem, st>>>(
+        (const __nv_bfloat16*)logits, ld, (const long long*)labels, (__nv_bfloat16*)dlogits, ldd, row_loss, stats,
+        rows, V, S, shift, (long long)ignore_index, slice_vec);
+    CT_LAUNCH_OK();
+  } else {
   int64_t grid = rows;
   const int64_t cap = (int64_t)sm_count() * 4;
   if (grid > cap) grid = cap;
@@ -305,6 +496,7 @@ extern "C" int ct_cross_entropy_fwd(const void* logits, int dtype, int64_t ld, c
         (const float*)logits, ld, (const long long*)labels, (float*)dlogits, ldd, row_loss, stats, rows, V, S,
         shift, (long long)ignore_index);
   CT_LAUNCH_OK();
+  }
   ce_finalize_kernel<<<1, 1024, 0, st>>>(row_loss, rows, stats, loss);
   CT_LAUNCH_OK();
   return 0;

@@ -277,8 +277,9 @@ ATT_CASES = [
 ]
 # kernel variants of the tcgen05 path (ATTN_FWD_IMPL, ATTN_BWD_IMPL): "v1" = first-generation softmax / backward
 # math, "v2" = register-resident rows, "v2t" = v2 backward with the tiled dQ workspace, "v3" = backward with
-# double-buffered P^T / dS^T (element math of tile it+1 under the MMAs of tile it)
-ATT_VARIANTS = {"v1": (1, 1), "v2": (0, 2), "v2t": (0, 3), "v3": (0, 4)}
+# double-buffered P^T / dS^T (element math of tile it+1 under the MMAs of tile it), "v4" = v3 with the dQ drain on its
+# own warpgroup
+ATT_VARIANTS = {"v1": (1, 1), "v2": (0, 2), "v2t": (0, 3), "v3": (0, 4), "v4": (0, 5)}
 ATT_PARAMS = [c + ("-",) for c in ATT_CASES if c[-1] == 2] + \
              [c + (v,) for c in ATT_CASES if c[-1] == 1 for v in ATT_VARIANTS]
 
@@ -413,6 +414,36 @@ def test_cross_entropy_and_embedding_vs_oracle():
     Wr = W.clone().requires_grad_(True)
     torch.nn.functional.embedding(ids, Wr, padding_idx=0).backward(dout)
     assert rel_err(dW, Wr.grad) < 1e-6
+
+
+@pytest.mark.parametrize("impl", [1, 2], ids=["twopass", "cluster"])
+@pytest.mark.parametrize("rows,S,V,shift", [(51, 17, 1000, True), (40, 0, 8 * 4099, False), (24, 8, 250880, True),
+                                            (9, 3, 16, True)])
+def test_cross_entropy_variants_vs_torch(impl, rows, S, V, shift):
+    """CE_IMPL 1 = two-pass kernel, 2 = row resident in the shared memory of a 4-CTA cluster (one HBM pass); bf16
+    logits: ragged slices (V/8 not a multiple of the cluster size or of the chunk), a full Bloom vocabulary row,
+    slices shorter than one chunk and CTAs without any element, ignored targets."""
+    ops = _ops()
+    torch.manual_seed(12)
+    logits = (torch.randn(rows, V, device=DEV) * 4).bfloat16()
+    labels = torch.randint(0, V, (rows,), device=DEV)
+    labels[::7] = -100
+    prev = ops.set_option("CE_IMPL", impl)
+    try:
+        loss, dl = ops.cross_entropy_fwd(logits, labels, S=S, shift=shift)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option("CE_IMPL", prev)
+    lr = logits.float().clone().requires_grad_(True)
+    if shift:
+        x = lr.view(rows // S, S, V)[:, :-1].reshape(-1, V); t = labels.view(rows // S, S)[:, 1:].reshape(-1)
+    else:
+        x, t = lr, labels
+    ref = torch.nn.functional.cross_entropy(x, t)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) / abs(float(ref)) < 1e-5
+    assert rel_err(dl, lr.grad) < 4e-3
+    assert torch.isfinite(dl.float()).all()
 
 
 def test_cast_colsum_activations():

@@ -40,3 +40,12 @@ for it in range(8):
         print("   v3: wait for mma_done(it-1) inside dq_drain:", b[16 * it + 9] - t[5])
     print(it, {n: t[i + 1] - t[i] for i, n in enumerate(names_b) if t[i + 1] and t[i]}, "tile_total", t[8] - t[0],
           "next_start_gap", (b[16 * (it + 1)] - t[8]) if b[16 * (it + 1)] else None)
+
+print("BWD whole-CTA timeline of every 64th block (cycles): setup, loop, wait_dkv, epilogue, exit_sync | total; globaltimer ns: start offset, duration")
+g0 = min(b[1024 + 8 * k + 6] for k in range(16) if b[1024 + 8 * k + 6])
+for blk in range(16):
+    t = b[1024 + 8 * blk: 1024 + 8 * blk + 8]
+    if not t[0]:
+        continue
+    bid = blk * 64 + 60
+    print(bid, "tiles", 8 - bid % 8, [t[i + 1] - t[i] for i in range(5)], "total", t[5] - t[0], "| start_ns", t[6] - g0, "dur_ns", t[7] - t[6])

@@ -124,7 +124,7 @@ def attn_ab():
         ref = _attn_oracle(qr, kr, vr, scale, True, fill, kb2[:nb].expand(nb, H, S) if kb2 is not None else None)
         do = torch.randn(B, S, H * D, device=DEV).bfloat16()
         ref.backward(do[:nb].float())
-        for impl, (fi, bi) in (("v1", (1, 1)), ("v2", (0, 2)), ("v2t", (0, 3)), ("v3", (0, 4))):
+        for impl, (fi, bi) in (("v2", (0, 2)), ("v3", (0, 4)), ("v4", (0, 5))):
             pf, pb = ops.set_option("ATTN_FWD_IMPL", fi), ops.set_option("ATTN_BWD_IMPL", bi)
             try:
                 o, lse2 = ops.attn_fwd(q, k, v, scale, True, fill, kb2, fv)
@@ -198,8 +198,39 @@ def gemm_ab():
         del ref
 
 
+def ce_ab():
+    rows, V = 8192, 250880
+    torch.manual_seed(3)
+    logits = torch.empty(rows, V, device=DEV, dtype=torch.bfloat16).normal_(0, 2)
+    labels = torch.randint(0, V, (rows,), device=DEV)
+    ref_rows = 64
+    lr = logits[:ref_rows].float()
+    ref_lse = torch.logsumexp(lr, -1)
+    ref_loss_rows = ref_lse - lr.gather(1, labels[:ref_rows, None]).squeeze(1)
+    for impl in (1, 2):
+        prev = ops.set_option("CE_IMPL", impl)
+        try:
+            loss, dl = ops.cross_entropy_fwd(logits, labels, S=1024, shift=True)
+            torch.cuda.synchronize()
+            p = torch.softmax(lr, -1)
+            tg = labels.view(8, 1024)[:, 1:]
+            cnt = tg.numel()
+            exp = p.clone()
+            for r in range(ref_rows - 1):
+                exp[r, labels[r + 1]] -= 1.0
+            err = rel(dl[:ref_rows - 1].float() * cnt, exp[:ref_rows - 1])
+            us = timeit(lambda: ops.cross_entropy_fwd(logits, labels, S=1024, shift=True))
+            out(kernel="ce", impl=impl, loss=float(loss), err_dlogits=err, us=us,
+                algorithmic_GBs=2.0 * rows * V * 2 / us / 1e3)
+            del dl
+        except Exception as ex:  # noqa: BLE001
+            out(kernel="ce", impl=impl, error=repr(ex)[:300])
+        finally:
+            ops.set_option("CE_IMPL", prev)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ln", "attn", "gemm"]
     ops.device_check(0)
     for wname in which:
-        {"ln": ln_ab, "attn": attn_ab, "gemm": gemm_ab}[wname]()
+        {"ln": ln_ab, "attn": attn_ab, "gemm": gemm_ab, "ce": ce_ab}[wname]()
