@@ -1134,32 +1134,48 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
     const int per = (k_blocks + split_k - 1) / split_k;
     split_k = (k_blocks + per - 1) / per;
   }
-  if (split_k > 1) {
-    e.atomic_out = 1;
-    if (a.beta == 0.f)
-      CT_CUDA_OK(cudaMemset2DAsync(a.C, (size_t)a.ldc * 4, 0, (size_t)a.N * 4, (size_t)a.M, st));
-  }
   const int auto_2cta = option(OPT_GEMM_2CTA);
-  if (a.impl == 3 || (a.impl == 0 && auto_2cta && a.M >= 512 && a.N >= 256)) {
+  const bool use_2cta = a.impl == 3 || (a.impl == 0 && auto_2cta && a.M >= 512 && a.N >= 256);
+  if (use_2cta) {
     // recompute the split for 256 x 256 tiles
     const int t2 = ((a.M + 255) / 256) * ((a.N + 255) / 256);
     int sk = 1;
     if (linear && t2 < sms / 2 && k_blocks >= 16) {
-      sk = (sms + t2 - 1) / t2;
-      const int max_split = k_blocks / 8;
-      if (sk > max_split) sk = max_split;
-      if (sk < 1) sk = 1;
-      const int per = (k_blocks + sk - 1) / sk;
-      sk = (k_blocks + per - 1) / per;
+      if (option(OPT_GEMM_SPLITK) == 1) {  // first-generation rule: about two work units per CTA pair
+        sk = (sms + t2 - 1) / t2;
+        const int max_split = k_blocks / 8;
+        if (sk > max_split) sk = max_split;
+        if (sk < 1) sk = 1;
+        const int per = (k_blocks + sk - 1) / sk;
+        sk = (k_blocks + per - 1) / per;
+      } else {
+        // Wave quantisation decides: t2 * sk work units run in ceil(units / pairs) rounds of ceil(k_blocks / sk)
+        // K blocks each, plus an epilogue per round (~2 K-block times for plain stores, ~4 when the partial sums
+        // leave through red.global.add, which also costs the memset of C). Bloom-560M wgrads on 74 pairs:
+        // 4h<->h (64 tiles) 3 -> 1 split (no atomics at all), QKV (48 tiles) 4 -> 3, h->h (16 tiles) 10 -> 4.
+        const int pairs = sms / 2;
+        const int max_split = k_blocks / 8 < 32 ? k_blocks / 8 : 32;
+        long best_cost = -1;
+        for (int c = 1; c <= (max_split < 1 ? 1 : max_split); ++c) {
+          const int per = (k_blocks + c - 1) / c;
+          if ((k_blocks + per - 1) / per != c) continue;  // same partition as a smaller candidate
+          const long rounds = ((long)t2 * c + pairs - 1) / pairs;
+          const long cost = rounds * (per + (c > 1 ? 4 : 2));
+          if (best_cost < 0 || cost < best_cost) { best_cost = cost; sk = c; }
+        }
+      }
     }
-    if (sk > 1 && split_k == 1) {
+    if (sk > 1) {
       e.atomic_out = 1;
       if (a.beta == 0.f)
         CT_CUDA_OK(cudaMemset2DAsync(a.C, (size_t)a.ldc * 4, 0, (size_t)a.N * 4, (size_t)a.M, st));
-    } else if (sk == 1 && split_k > 1) {
-      e.atomic_out = 0;  // (C was zeroed above for the 1-CTA split: harmless)
     }
     return launch_tc_2cta(a, e, sk, st);
+  }
+  if (split_k > 1) {
+    e.atomic_out = 1;
+    if (a.beta == 0.f)
+      CT_CUDA_OK(cudaMemset2DAsync(a.C, (size_t)a.ldc * 4, 0, (size_t)a.N * 4, (size_t)a.M, st));
   }
   return bn == 256 ? launch_tc<256>(a, e, split_k, st) : launch_tc<128>(a, e, split_k, st);
 }

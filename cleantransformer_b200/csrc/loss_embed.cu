@@ -396,6 +396,124 @@ __global__ void __cluster_dims__(CEC_C, 1, 1) __launch_bounds__(CEC_THREADS, 1)
   cluster_sync_all();  // no CTA leaves while a peer could still address its shared memory
 }
 
+// ---------------------------------------------------------------------------------------------
+// cross entropy, two passes with the row kept in L2
+// ---------------------------------------------------------------------------------------------
+// Same arithmetic as ce_fwd_kernel, different residency: ONE 1024-thread CTA per SM, so only sm_count rows
+// (148 x 0.5 MB = 74 MB at V = 250 880) are between their two passes at any time and the second read hits the
+// 126 MB L2 instead of HBM (ce_fwd_kernel keeps 592 rows = 297 MB in flight: 12.3 GB of DRAM traffic per step for
+// 8.2 GB of algorithmic bytes). Four independent 16-byte loads per thread per iteration keep ~64 KB in flight
+// per SM; the gradient stores and the second read are streaming (.cs) so they do not push the next rows out.
+constexpr int CE2_THREADS = 1024;
+constexpr int CE2_UNROLL = 4;
+
+__device__ __forceinline__ void ce_unpack8(const uint4& u, float (&v)[8]) {
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+}
+
+__global__ void __launch_bounds__(CE2_THREADS, 1)
+    ce_fwd_l2_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, const long long* __restrict__ labels,
+                     __nv_bfloat16* __restrict__ dlogits, int64_t ldd, float* __restrict__ row_loss,
+                     const float* __restrict__ stats, int64_t rows, int64_t V, int64_t S, int shift,
+                     long long ignore_index) {
+  __shared__ float red[2 * (CE2_THREADS >> 5)];
+  const float inv_count = 1.f / fmaxf(stats[0], 1.f);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t nvec = V >> 3;
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const long long tgt = ce_target(labels, r, S, shift);
+    const bool valid = (tgt != ignore_index && tgt >= 0 && tgt < V);
+    const uint4* x8 = reinterpret_cast<const uint4*>(logits + r * ld);
+    uint4* d8 = dlogits ? reinterpret_cast<uint4*>(dlogits + r * ldd) : nullptr;
+    if (!valid) {
+      if (row_loss && tid == 0) row_loss[r] = 0.f;
+      if (d8)
+        for (int64_t c = tid; c < nvec; c += CE2_THREADS) __stcs(d8 + c, make_uint4(0u, 0u, 0u, 0u));
+      continue;
+    }
+    // ---- pass 1: (max, sum 2^(t - max)) in the log2 domain ----
+    float m = -INFINITY, s = 0.f;
+    for (int64_t c0 = tid; c0 < nvec; c0 += CE2_THREADS * CE2_UNROLL) {
+      uint4 u[CE2_UNROLL];
+#pragma unroll
+      for (int k = 0; k < CE2_UNROLL; ++k) {
+        const int64_t c = c0 + (int64_t)k * CE2_THREADS;
+        u[k] = c < nvec ? x8[c] : make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);  // -inf pairs
+      }
+#pragma unroll
+      for (int k = 0; k < CE2_UNROLL; ++k) {
+        float v[8];
+        ce_unpack8(u[k], v);
+        float mx = v[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) mx = fmaxf(mx, v[i]);
+        mx *= LOG2E;
+        if (mx > m) {
+          s *= ce_ex2(m - mx);
+          m = mx;
+        }
+        if (m > -INFINITY) {
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc += ce_ex2(fmaf(v[i], LOG2E, -m));
+          s += acc;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      ms_merge2(m, s, m2, s2);
+    }
+    if (lane == 0) { red[2 * w] = m; red[2 * w + 1] = s; }
+    __syncthreads();
+    m = red[2 * lane]; s = red[2 * lane + 1];  // 32 warps: every warp reduces the same 32 pairs
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      ms_merge2(m, s, m2, s2);
+    }
+    __syncthreads();  // red is rewritten by the next row
+    const float lse2 = m + log2f(s);
+    if (row_loss && tid == 0) row_loss[r] = lse2 * LN2 - __bfloat162float(logits[r * ld + tgt]);
+    // ---- pass 2: gradients; the row comes back from L2 ----
+    if (d8) {
+      for (int64_t c0 = tid; c0 < nvec; c0 += CE2_THREADS * CE2_UNROLL) {
+        uint4 u[CE2_UNROLL];
+#pragma unroll
+        for (int k = 0; k < CE2_UNROLL; ++k) {
+          const int64_t c = c0 + (int64_t)k * CE2_THREADS;
+          if (c < nvec) u[k] = __ldcs(x8 + c);
+        }
+#pragma unroll
+        for (int k = 0; k < CE2_UNROLL; ++k) {
+          const int64_t c = c0 + (int64_t)k * CE2_THREADS;
+          if (c < nvec) {
+            float v[8];
+            ce_unpack8(u[k], v);
+            const int64_t e0 = c << 3;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float pg = ce_ex2(fmaf(v[i], LOG2E, -lse2));
+              if (e0 + i == tgt) pg -= 1.f;
+              v[i] = pg * inv_count;
+            }
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+            __stcs(d8 + c, o);
+          }
+        }
+      }
+    }
+  }
+}
+
 // loss = sum(row_loss) / count   (single block, deterministic order)
 __global__ void __launch_bounds__(1024)
     ce_finalize_kernel(const float* __restrict__ row_loss, int64_t rows, const float* __restrict__ stats,
@@ -461,14 +579,25 @@ extern "C" int ct_cross_entropy_fwd(const void* logits, int dtype, int64_t ld, c
   CT_CUDA_OK(cudaMemsetAsync(stats, 0, 16, st));
   ce_count_kernel<<<64, 256, 0, st>>>((const long long*)labels, rows, S, shift, (long long)ignore_index, V, stats);
   CT_LAUNCH_OK();
-  // CE_IMPL: 0 = auto, 1 = two-pass kernel (row re-read through L2 / HBM), 2 = row resident in cluster shared memory
+  // CE_IMPL: 0 = auto, 1 = two-pass kernel, 592 rows in flight (second read from HBM at Bloom's vocabulary),
+  //          2 = row resident in cluster shared memory (measured slower, r01g), 3 = two passes, one row per SM
+  //          in flight so that the second read hits L2
   const int64_t nvec = V >> 3;
   const int slice_vec = (int)((nvec + CEC_C - 1) / CEC_C);
   const bool cluster_ok = dtype == DT_BF16 && (V & 7) == 0 && (ld & 7) == 0 && (!dlogits || (ldd & 7) == 0) &&
                           ((uintptr_t)logits & 15) == 0 && ((uintptr_t)dlogits & 15) == 0 &&
                           slice_vec <= CEC_MAX_CHUNKS * CEC_THREADS;
   const int ce_impl = option(OPT_CE_IMPL);
-  if (cluster_ok && (ce_impl == 2 || (ce_impl == 0 && false))) {
+  const bool vec_ok = dtype == DT_BF16 && (V & 7) == 0 && (ld & 7) == 0 && (!dlogits || (ldd & 7) == 0) &&
+                      ((uintptr_t)logits & 15) == 0 && ((uintptr_t)dlogits & 15) == 0;
+  if (vec_ok && ce_impl == 3) {
+    int64_t grid = sm_count();
+    if (grid > rows) grid = rows;
+    ce_fwd_l2_kernel<<<(unsigned)grid, CE2_THREADS, 0, st>>>(
+        (const __nv_bfloat16*)logits, ld, (const long long*)labels, (__nv_bfloat16*)dlogits, ldd, row_loss, stats,
+        rows, V, S, shift, (long long)ignore_index);
+    CT_LAUNCH_OK();
+  } else if (cluster_ok && ce_impl == 2) {
     const size_t smem = (size_t)16 * ((slice_vec + CEC_THREADS - 1) / CEC_THREADS) * CEC_THREADS;
     static bool attr = false;
     if (!attr) {

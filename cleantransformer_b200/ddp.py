@@ -66,7 +66,7 @@ def plan_buckets(sizes_offsets, cap_elems, solo=()):
 
 class DistributedDataParallel(torch.nn.Module):
     def __init__(self, module, device_ids=None, output_device=None, bucket_cap_mb=BUCKET_CAP_MB,
-                 comm=None, process_group=None, max_ctas=24, **unused):
+                 comm=None, process_group=None, max_ctas=48, **unused):
         super().__init__()
         if not dist.is_initialized():
             raise RuntimeError("DistributedDataParallel needs torch.distributed.init_process_group first "
@@ -220,6 +220,8 @@ class DistributedDataParallel(torch.nn.Module):
             return
         self._launched[bi] = True
         lo, hi, _ = self.buckets[bi]
+        if os.environ.get("CT_DDP_SKIP_COMM"):  # timing experiments only: gradients stay local (WRONG results)
+            return
         if self.comm == "p2p":
             cur = torch.cuda.current_stream(self.device)
             self._comm_stream.wait_stream(cur)

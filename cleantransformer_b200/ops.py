@@ -5,6 +5,7 @@ hand-written sm_100a kernel in libct_b200.so. Wrappers allocate outputs with tor
 raw data_ptr()s + the current stream. Nothing in this module computes with torch ops.
 """
 import ctypes
+import os
 
 import torch
 
@@ -274,7 +275,9 @@ def linear_dgrad(dy2d, w, out_dtype=torch.bfloat16, actgrad_src=None, actgrad_ac
 
 
 def linear_wgrad(dy2d, x2d, dw, db=None, accumulate=False, w_in_out=False, impl=0):
-    """dW (+)= dy^T @ x into the f32 tensor dw ([N,K] or [K,N]); db (+)= colsum(dy)."""
+    """dW (+)= dy^T @ x into the f32 tensor dw ([N,K] or [K,N]); db (+)= colsum(dy).
+    (Running the column sums on a side stream under the GEMM was measured and is slower — profiles/r01j: the
+    persistent GEMM leaves room for one 256-thread CTA per SM, which stretches the colsum past the GEMM.)"""
     M, N = dy2d.shape
     K = x2d.shape[1]
     if not w_in_out:

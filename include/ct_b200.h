@@ -46,7 +46,7 @@ int ct_last_error(char* buf, size_t n);
 /* 0 only if `device` is an sm_100 part (B200). */
 int ct_device_check(int device);
 /* Kernel-variant knobs for A/B measurements and tests (not needed for normal use). Names:
- * "LN_BWD_IMPL", "ATTN_FWD_IMPL", "ATTN_BWD_IMPL", "GEMM_EPI_IMPL", "GEMM_2CTA", "CE_IMPL"; 0 = default.
+ * "LN_BWD_IMPL", "ATTN_FWD_IMPL", "ATTN_BWD_IMPL", "GEMM_EPI_IMPL", "GEMM_2CTA", "CE_IMPL", "GEMM_SPLITK"; 0 = default.
  * Initial values are read from the environment variables CT_<NAME>. */
 int ct_set_option(const char* name, int value);
 int ct_get_option(const char* name, int* value);

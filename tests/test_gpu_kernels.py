@@ -416,11 +416,12 @@ def test_cross_entropy_and_embedding_vs_oracle():
     assert rel_err(dW, Wr.grad) < 1e-6
 
 
-@pytest.mark.parametrize("impl", [1, 2], ids=["twopass", "cluster"])
+@pytest.mark.parametrize("impl", [1, 2, 3], ids=["twopass", "cluster", "l2resident"])
 @pytest.mark.parametrize("rows,S,V,shift", [(51, 17, 1000, True), (40, 0, 8 * 4099, False), (24, 8, 250880, True),
                                             (9, 3, 16, True)])
 def test_cross_entropy_variants_vs_torch(impl, rows, S, V, shift):
-    """CE_IMPL 1 = two-pass kernel, 2 = row resident in the shared memory of a 4-CTA cluster (one HBM pass); bf16
+    """CE_IMPL 1 = two-pass kernel, 2 = row resident in the shared memory of a 4-CTA cluster (one HBM pass), 3 = two
+    passes with one row per SM in flight (second read from L2); bf16
     logits: ragged slices (V/8 not a multiple of the cluster size or of the chunk), a full Bloom vocabulary row,
     slices shorter than one chunk and CTAs without any element, ignored targets."""
     ops = _ops()

@@ -198,6 +198,37 @@ def gemm_ab():
         del ref
 
 
+def wgrad_ab():
+    """split-K rule of the 2-CTA wgrad GEMMs (GEMM_SPLITK 1 = first-generation rule, 0 = wave-quantisation rule)."""
+    T, H = 8192, 1024
+    torch.manual_seed(4)
+    for name, N, K in (("ffn2_wgrad", H, 4 * H), ("ffn1_wgrad", 4 * H, H), ("qkv_wgrad", 3 * H, H), ("proj_wgrad", H, H)):
+        dy = torch.randn(T, N, device=DEV).bfloat16()
+        x = torch.randn(T, K, device=DEV).bfloat16()
+        ref = dy.float().t() @ x.float()
+        refb = dy.float().sum(0)
+        for rule in (1, 0):
+            for overlap in (False,):
+                prev = ops.set_option("GEMM_SPLITK", rule)
+                try:
+                    dw = torch.empty(N, K, device=DEV); db = torch.empty(N, device=DEV)
+                    ops.linear_wgrad(dy, x, dw, db, accumulate=False)
+                    torch.cuda.synchronize()
+                    err, errb = rel(dw, ref), rel(db, refb)
+                    dw.fill_(1.0); db.fill_(1.0)
+                    ops.linear_wgrad(dy, x, dw, db, accumulate=True)
+                    torch.cuda.synchronize()
+                    err_acc = max(rel(dw - 1.0, ref), rel(db - 1.0, refb))
+                    us = timeit(lambda: ops.linear_wgrad(dy, x, dw, db, accumulate=False))
+                    out(kernel="wgrad", case=name, splitk_rule=rule, overlap_colsum=overlap, err=err, err_bias=errb,
+                        err_accumulate=err_acc, us_gemm_plus_colsum=us, tflops=2.0 * T * N * K / us / 1e6)
+                except Exception as ex:  # noqa: BLE001
+                    out(kernel="wgrad", case=name, splitk_rule=rule, overlap_colsum=overlap, error=repr(ex)[:300])
+                finally:
+                    ops.set_option("GEMM_SPLITK", prev)
+        del dy, x, ref
+
+
 def ce_ab():
     rows, V = 8192, 250880
     torch.manual_seed(3)
@@ -207,7 +238,7 @@ def ce_ab():
     lr = logits[:ref_rows].float()
     ref_lse = torch.logsumexp(lr, -1)
     ref_loss_rows = ref_lse - lr.gather(1, labels[:ref_rows, None]).squeeze(1)
-    for impl in (1, 2):
+    for impl in (1, 3):
         prev = ops.set_option("CE_IMPL", impl)
         try:
             loss, dl = ops.cross_entropy_fwd(logits, labels, S=1024, shift=True)
@@ -233,4 +264,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["ln", "attn", "gemm"]
     ops.device_check(0)
     for wname in which:
-        {"ln": ln_ab, "attn": attn_ab, "gemm": gemm_ab, "ce": ce_ab}[wname]()
+        {"ln": ln_ab, "attn": attn_ab, "gemm": gemm_ab, "ce": ce_ab, "wgrad": wgrad_ab}[wname]()
