@@ -579,7 +579,7 @@ extern "C" int ct_cross_entropy_fwd(const void* logits, int dtype, int64_t ld, c
   CT_CUDA_OK(cudaMemsetAsync(stats, 0, 16, st));
   ce_count_kernel<<<64, 256, 0, st>>>((const long long*)labels, rows, S, shift, (long long)ignore_index, V, stats);
   CT_LAUNCH_OK();
-  // CE_IMPL: 0 = auto, 1 = two-pass kernel, 592 rows in flight (second read from HBM at Bloom's vocabulary),
+  // CE_IMPL: 0 = auto (3 when the row is 16-byte addressable bf16), 1 = two-pass kernel, 592 rows in flight (second read from HBM at Bloom's vocabulary),
   //          2 = row resident in cluster shared memory (measured slower, r01g), 3 = two passes, one row per SM
   //          in flight so that the second read hits L2
   const int64_t nvec = V >> 3;
@@ -590,7 +590,7 @@ extern "C" int ct_cross_entropy_fwd(const void* logits, int dtype, int64_t ld, c
   const int ce_impl = option(OPT_CE_IMPL);
   const bool vec_ok = dtype == DT_BF16 && (V & 7) == 0 && (ld & 7) == 0 && (!dlogits || (ldd & 7) == 0) &&
                       ((uintptr_t)logits & 15) == 0 && ((uintptr_t)dlogits & 15) == 0;
-  if (vec_ok && ce_impl == 3) {
+  if (vec_ok && (ce_impl == 3 || ce_impl == 0)) {
     int64_t grid = sm_count();
     if (grid > rows) grid = rows;
     ce_fwd_l2_kernel<<<(unsigned)grid, CE2_THREADS, 0, st>>>(
