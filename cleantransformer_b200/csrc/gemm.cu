@@ -44,6 +44,7 @@ struct EpiParams {
   const void* residual; int res_dtype; int64_t ldr;
   int vec_ok;     // all pointers 16B aligned and leading dims multiples of 8 elements
   int atomic_out; // split-K: C += t via red.global.add.f32 (C f32, linear epilogue only)
+  int res_coalesced;  // EPIK_RES_F32: residual fetched (and added) in the coalesced write-out pattern
 };
 
 __device__ __forceinline__ float ld_elem(const void* p, int dt, int64_t i) {
@@ -205,6 +206,34 @@ __device__ __forceinline__ void stage_flush(uint32_t stage, int lane, uint8_t* g
   }
 }
 
+// fp32 chunk + fp32 residual: the residual pieces were fetched in the SAME lane -> (row, 16-byte piece) pattern as the
+// write-out (epi_fast_aux_load, coalesced form), so the add happens here, after the transpose through the stage
+__device__ __forceinline__ void stage_store32_f32_res(uint32_t stage, int lane, const float (&v)[32], void* gbase,
+                                                      int64_t ld, int m_base, int M, int n0, const uint4 (&x)[8]) {
+  uint8_t* g = reinterpret_cast<uint8_t*>(gbase) + (int64_t)n0 * 4;
+  const int piece = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      stage_round(stage, lane, __float_as_uint(v[16 * h + 4 * i]), __float_as_uint(v[16 * h + 4 * i + 1]),
+                  __float_as_uint(v[16 * h + 4 * i + 2]), __float_as_uint(v[16 * h + 4 * i + 3]), i);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = (lane >> 2) + 8 * k;
+      float4 w;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
+                   : "r"(stage + r * EPI_STAGE_ROW + 16 * (piece ^ ((r >> 1) & 3))));
+      const uint4 q = x[4 * h + k];
+      w.x += __uint_as_float(q.x); w.y += __uint_as_float(q.y); w.z += __uint_as_float(q.z); w.w += __uint_as_float(q.w);
+      const int m = m_base + r;
+      if (m < M) *reinterpret_cast<float4*>(g + 64 * h + (int64_t)m * ld * 4 + piece * 16) = w;
+    }
+    __syncwarp();
+  }
+}
+
 __device__ __forceinline__ void stage_store32(uint32_t stage, int lane, const float (&v)[32], int dt,
                                               void* gbase, int64_t ld, int m_base, int M, int n0) {
   if (dt == DT_F32) {
@@ -356,7 +385,20 @@ __device__ __forceinline__ float2 gelu_tanh_grad2(float2 x) {
 template <int EPIK>
 __device__ __forceinline__ void epi_fast_aux_load(const EpiParams& e, int m, int n0, uint4 (&x)[8]) {
   if constexpr (EPIK == EPIK_RES_F32) {
-    if (m < e.M) {
+    if (e.res_coalesced) {
+      // lane -> (row (lane >> 2) + 8k, 16-byte piece lane & 3) of each 64-byte half h: 8 rows x 64 B per
+      // instruction (8 L1 wavefronts) instead of 32 rows x 16 B (32 wavefronts) for the row-per-thread form
+      const int lane = threadIdx.x & 31, m_base = m - lane, piece = lane & 3;
+      const float* base = reinterpret_cast<const float*>(e.residual) + n0 + 4 * piece;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int mm = m_base + (lane >> 2) + 8 * k;
+          x[4 * h + k] = mm < e.M ? *reinterpret_cast<const uint4*>(base + (int64_t)mm * e.ldr + 16 * h)
+                                  : make_uint4(0u, 0u, 0u, 0u);
+        }
+    } else if (m < e.M) {
       const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(e.residual) + (int64_t)m * e.ldr + n0);
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] = q[i];
@@ -413,6 +455,10 @@ __device__ __forceinline__ void epi_fast_chunk(const EpiParams& e, int m_base, i
     }
   }
   if constexpr (EPIK == EPIK_RES_F32) {
+    if (e.res_coalesced) {  // CTA-uniform
+      stage_store32_f32_res(stage, lane, t, e.C, e.ldc, m_base, e.M, n0, x);
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float2 a = __fadd2_rn(make_float2(t[4 * i], t[4 * i + 1]),
@@ -1085,6 +1131,7 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
   e.ldg = a.ldg;
   e.residual = a.residual; e.res_dtype = a.res_dtype; e.ldr = a.ldr;
   e.atomic_out = 0;
+  e.res_coalesced = option(OPT_GEMM_EPI_IMPL) != 2;  // GEMM_EPI_IMPL 2 = row-per-thread residual loads (first form)
   e.vec_ok = al16(a.C) && (a.ldc % 8 == 0) && (!a.bias || al16(a.bias)) &&
              (!a.preact || (al16(a.preact) && a.ldp % 8 == 0)) &&
              (!a.actgrad_src || (al16(a.actgrad_src) && a.ldg % 8 == 0)) &&

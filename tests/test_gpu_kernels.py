@@ -178,7 +178,7 @@ def test_linear_epilogues_vs_oracle(act, name):
     assert rel_err(yc, O.conv1d(x.float(), wc.float(), b)) < 1e-5
 
 
-@pytest.mark.parametrize("variant", ["v1", "v2"])
+@pytest.mark.parametrize("variant", ["v1", "v2", "v2row"])
 @pytest.mark.parametrize("M,N,K", [(1024, 512, 256), (520, 1056, 320), (2048, 1024, 1024)])
 def test_gemm_specialised_epilogues_vs_oracle(M, N, K, variant):
     """The compile-time epilogue kinds of the 2-CTA kernel (v2; GEMM_EPI_IMPL=0) and the generic run-time
@@ -186,7 +186,9 @@ def test_gemm_specialised_epilogues_vs_oracle(M, N, K, variant):
     residual -> f32, dgrad x GELU'(pre). M=520 exercises ragged row tiles, N=1056 a ragged 256-column tile."""
     from oracle import ct_oracle as O
     ops = _ops()
-    prev = ops.set_option("GEMM_EPI_IMPL", 1 if variant == "v1" else 0)
+    # "v2row": compile-time epilogues with the first form of the f32 residual fetch (row per thread); "v2" fetches it
+    # in the coalesced write-out pattern and adds it after the transpose through the staging tile
+    prev = ops.set_option("GEMM_EPI_IMPL", {"v1": 1, "v2": 0, "v2row": 2}[variant])
     try:
         torch.manual_seed(11)
         x = torch.randn(M, K, device=DEV).bfloat16(); w = (torch.randn(N, K, device=DEV) * 0.1).bfloat16()

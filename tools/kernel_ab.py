@@ -3,7 +3,7 @@ and CUDA-event time per launch (inputs > L2 are rotated between launches), for
   LayerNorm backward  (LN_BWD_IMPL 1 = warp-per-row, 0 = row spread over cols/4 threads)
   attention forward   (ATTN_FWD_IMPL 1 = v1, 0 = v2)
   attention backward  (ATTN_BWD_IMPL 1 = v1, 2 = v2, 3 = v2 + tiled dQ workspace, 4 = v3 pipelined)
-  GEMM epilogues      (GEMM_EPI_IMPL 1 = generic, 0 = specialised)
+  GEMM epilogues      (GEMM_EPI_IMPL 1 = generic, 2 = specialised with row-per-thread residual loads, 0 = specialised)
 Prints one JSON line per measurement; never asserts (a failing variant shows up as a large error or an
 `error` field), so one GPU visit tells everything.   python tools/kernel_ab.py [ln] [attn] [gemm]
 """
@@ -184,7 +184,7 @@ def gemm_ab():
     ]
     for name, flop, fn, ref_fn, tol in jobs:
         ref = ref_fn()
-        for impl in (1, 0):
+        for impl in (1, 2, 0):
             prev = ops.set_option("GEMM_EPI_IMPL", impl)
             try:
                 got = fn()
