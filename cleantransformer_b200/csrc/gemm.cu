@@ -404,7 +404,17 @@ __device__ __forceinline__ void epi_fast_aux_load(const EpiParams& e, int m, int
       for (int i = 0; i < 8; ++i) x[i] = q[i];
     }
   } else if constexpr (EPIK == EPIK_ACTGRAD) {
-    if (m < e.M) {
+    if (e.res_coalesced) {
+      // same lane -> (row, piece) pattern for the 64-byte bf16 rows of the saved pre-activation; epi_fast_chunk
+      // brings each row back to its owner thread through the staging tile
+      const int lane = threadIdx.x & 31, m_base = m - lane, piece = lane & 3;
+      const uint16_t* base = reinterpret_cast<const uint16_t*>(e.actgrad_src) + n0 + 8 * piece;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int mm = m_base + (lane >> 2) + 8 * k;
+        x[k] = mm < e.M ? *reinterpret_cast<const uint4*>(base + (int64_t)mm * e.ldg) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    } else if (m < e.M) {
       const uint4* q =
           reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.actgrad_src) + (int64_t)m * e.ldg + n0);
 #pragma unroll
@@ -443,9 +453,29 @@ __device__ __forceinline__ void epi_fast_chunk(const EpiParams& e, int m_base, i
     }
   }
   if constexpr (EPIK == EPIK_ACTGRAD) {
+    uint4 xr[4];
+    if (e.res_coalesced) {  // CTA-uniform: (row, piece) pieces -> staging tile -> this thread's own row
+      const int piece = lane & 3;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = (lane >> 2) + 8 * k;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + r * EPI_STAGE_ROW + 16 * (piece ^ ((r >> 1) & 3))),
+                     "r"(x[k].x), "r"(x[k].y), "r"(x[k].z), "r"(x[k].w) : "memory");
+      }
+      __syncwarp();
+      const int key = (lane >> 1) & 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xr[i].x), "=r"(xr[i].y), "=r"(xr[i].z), "=r"(xr[i].w)
+                     : "r"(stage + lane * EPI_STAGE_ROW + 16 * (i ^ key)));
+      __syncwarp();  // the output staging below reuses the tile
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xr[i] = x[i];
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint32_t w[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+      const uint32_t w[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 g = gelu_tanh_grad2(unpack_bf16x2(w[k]));
