@@ -61,7 +61,10 @@ int option(int which);
 // dtype enum shared with include/ct_b200.h
 enum : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 // activation enum shared with include/ct_b200.h
-enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU_ERF = 2, ACT_GELU_TANH = 3, ACT_TANH = 4 };
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU_ERF = 2, ACT_GELU_TANH = 3, ACT_TANH = 4,
+              // GEMM epilogues only: y = gelu_tanh(t) with gelu_tanh'(t) (not t) written to `preact`; and, as an
+              // activation-gradient kind, "the source already holds act'(pre)": multiply by it as is
+              ACT_GELU_TANH_SAVE_GRAD = 5, ACT_GRAD_PRECOMPUTED = 6 };
 
 #ifdef __CUDACC__
 
@@ -104,7 +107,8 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   switch (act) {
     case ACT_RELU: return fmaxf(x, 0.f);
     case ACT_GELU_ERF: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
-    case ACT_GELU_TANH: {
+    case ACT_GELU_TANH:
+    case ACT_GELU_TANH_SAVE_GRAD: {
       float u = 0.79788456f * x * (1.f + 0.044715f * x * x);
       float hx = 0.5f * x;
       return fmaf(hx, tanh_approx(u), hx);
@@ -121,7 +125,8 @@ __device__ __forceinline__ float act_grad(float x, int act) {
     case ACT_GELU_ERF:
       return 0.5f * (1.f + erff(x * 0.70710678118654752f)) +
              x * 0.3989422804014327f * __expf(-0.5f * x * x);
-    case ACT_GELU_TANH: {
+    case ACT_GELU_TANH:
+    case ACT_GELU_TANH_SAVE_GRAD: {
       float t = tanh_approx(0.79788456f * x * (1.f + 0.044715f * x * x));
       return 0.5f * x * ((1.f - t * t) * (0.79788456f + 0.1070322243f * x * x)) + 0.5f * (1.f + t);
     }
@@ -129,6 +134,7 @@ __device__ __forceinline__ float act_grad(float x, int act) {
       float t = tanhf(x);
       return 1.f - t * t;
     }
+    case ACT_GRAD_PRECOMPUTED: return x;  // x IS the saved derivative
     default: return 1.f;
   }
 }

@@ -75,7 +75,7 @@ __device__ __forceinline__ float gelu_tanh_grad_fast(float x) {
   return 0.5f * x * ((1.f - t * t) * (0.79788456f + 0.1070322243f * x * x)) + 0.5f * (1.f + t);
 }
 __device__ __forceinline__ void act32(float (&t)[32], int act) {
-  if (act == ACT_GELU_TANH) {
+  if (act == ACT_GELU_TANH || act == ACT_GELU_TANH_SAVE_GRAD) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) t[j] = gelu_tanh_fast(t[j]);
   } else if (act == ACT_RELU) {
@@ -107,7 +107,9 @@ __device__ __noinline__ void epi_scalar(const EpiParams& e, int m, int n, float 
     atomicAdd(reinterpret_cast<float*>(e.C) + (int64_t)m * e.ldc + n, t);
     return;
   }
-  if (e.preact) st_elem(e.preact, e.preact_dtype, (int64_t)m * e.ldp + n, t);
+  if (e.preact)
+    st_elem(e.preact, e.preact_dtype, (int64_t)m * e.ldp + n,
+            e.act == ACT_GELU_TANH_SAVE_GRAD ? act_grad_call(t, ACT_GELU_TANH) : t);
   if (e.act != ACT_NONE) t = act_apply_call(t, e.act);
   if (e.actgrad_src)
     t *= act_grad_call(ld_elem(e.actgrad_src, e.actgrad_dtype, (int64_t)m * e.ldg + n), e.actgrad_act);
@@ -313,7 +315,16 @@ __device__ __forceinline__ void epi_block32(const EpiParams& e, int m_base, int 
       t[4 * i] += b.x; t[4 * i + 1] += b.y; t[4 * i + 2] += b.z; t[4 * i + 3] += b.w;
     }
   }
-  if (e.preact) stage_store32(stage, lane, t, e.preact_dtype, e.preact, e.ldp, m_base, e.M, n0);
+  if (e.preact) {
+    if (e.act == ACT_GELU_TANH_SAVE_GRAD) {
+      float g[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) g[j] = gelu_tanh_grad_fast(t[j]);
+      stage_store32(stage, lane, g, e.preact_dtype, e.preact, e.ldp, m_base, e.M, n0);
+    } else {
+      stage_store32(stage, lane, t, e.preact_dtype, e.preact, e.ldp, m_base, e.M, n0);
+    }
+  }
   if (e.act != ACT_NONE) act32(t, e.act);
   if (e.actgrad_src && row_ok) {
     if (aux_kind == AUX_ACTGRAD) {
@@ -378,6 +389,21 @@ __device__ __forceinline__ float2 gelu_tanh_grad2(float2 x) {
   const float2 w = __fmul2_rn(__fmul2_rn(x, make_float2(0.5f, 0.5f)), om);                        // 0.5 x (1 - t^2)
   const float2 hh = __ffma2_rn(th, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));            // 0.5 (1 + t)
   return __ffma2_rn(w, q, hh);
+}
+
+// gelu_tanh(x) and its derivative from one tanh (forward epilogue that saves the derivative for the backward)
+__device__ __forceinline__ void gelu_tanh_both2(float2 x, float2& y, float2& g) {
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 pp = __ffma2_rn(x2, make_float2(0.79788456f * 0.044715f, 0.79788456f * 0.044715f),
+                               make_float2(0.79788456f, 0.79788456f));
+  const float2 u = __fmul2_rn(x, pp);
+  const float2 th = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  y = __ffma2_rn(hx, th, hx);
+  const float2 om = __ffma2_rn(make_float2(-th.x, -th.y), th, make_float2(1.f, 1.f));
+  const float2 q = __ffma2_rn(x2, make_float2(0.1070322243f, 0.1070322243f), make_float2(0.79788456f, 0.79788456f));
+  const float2 hh = __ffma2_rn(th, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  g = __ffma2_rn(__fmul2_rn(hx, om), q, hh);
 }
 
 // per-element operand of one chunk (row m, columns [n0, n0+32)): f32 residual = 8 x 16 B, bf16 saved
@@ -445,11 +471,23 @@ __device__ __forceinline__ void epi_fast_chunk(const EpiParams& e, int m_base, i
     for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(r[j]);
   }
   if constexpr (EPIK == EPIK_GELU_PRE) {
-    stage_store32(stage, lane, t, DT_BF16, e.preact, e.ldp, m_base, e.M, n0);
+    if (e.act == ACT_GELU_TANH_SAVE_GRAD) {  // CTA-uniform: the backward wants gelu'(t), one tanh serves both
+      float g[32];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float2 y = gelu_tanh2(make_float2(t[2 * j], t[2 * j + 1]));
-      t[2 * j] = y.x; t[2 * j + 1] = y.y;
+      for (int j = 0; j < 16; ++j) {
+        float2 y, d;
+        gelu_tanh_both2(make_float2(t[2 * j], t[2 * j + 1]), y, d);
+        t[2 * j] = y.x; t[2 * j + 1] = y.y;
+        g[2 * j] = d.x; g[2 * j + 1] = d.y;
+      }
+      stage_store32(stage, lane, g, DT_BF16, e.preact, e.ldp, m_base, e.M, n0);
+    } else {
+      stage_store32(stage, lane, t, DT_BF16, e.preact, e.ldp, m_base, e.M, n0);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 y = gelu_tanh2(make_float2(t[2 * j], t[2 * j + 1]));
+        t[2 * j] = y.x; t[2 * j + 1] = y.y;
+      }
     }
   }
   if constexpr (EPIK == EPIK_ACTGRAD) {
@@ -478,7 +516,8 @@ __device__ __forceinline__ void epi_fast_chunk(const EpiParams& e, int m_base, i
       const uint32_t w[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 g = gelu_tanh_grad2(unpack_bf16x2(w[k]));
+        const float2 s2 = unpack_bf16x2(w[k]);
+        const float2 g = e.actgrad_act == ACT_GRAD_PRECOMPUTED ? s2 : gelu_tanh_grad2(s2);  // CTA-uniform
         const float2 y = __fmul2_rn(make_float2(t[8 * i + 2 * k], t[8 * i + 2 * k + 1]), g);
         t[8 * i + 2 * k] = y.x; t[8 * i + 2 * k + 1] = y.y;
       }
@@ -1082,12 +1121,14 @@ static int pick_epi_kind(const ct_gemm_args& a, const EpiParams& e) {
   if (!e.vec_ok || e.atomic_out || a.alpha != 1.f || a.beta != 0.f || (a.N % 32) != 0) return EPIK_GENERIC;
   const bool plain = a.act == ACT_NONE && !a.preact && !a.actgrad_src && !a.residual;
   if (plain && a.c_dtype == DT_BF16 && a.ab_dtype == DT_BF16) return EPIK_BF16;
-  if (a.act == ACT_GELU_TANH && a.preact && a.preact_dtype == DT_BF16 && a.c_dtype == DT_BF16 && !a.actgrad_src &&
+  if ((a.act == ACT_GELU_TANH || a.act == ACT_GELU_TANH_SAVE_GRAD) && a.preact && a.preact_dtype == DT_BF16 &&
+      a.c_dtype == DT_BF16 && !a.actgrad_src &&
       !a.residual)
     return EPIK_GELU_PRE;
   if (a.act == ACT_NONE && !a.preact && !a.actgrad_src && a.residual && a.res_dtype == DT_F32 && a.c_dtype == DT_F32)
     return EPIK_RES_F32;
-  if (a.act == ACT_NONE && !a.preact && a.actgrad_src && a.actgrad_dtype == DT_BF16 && a.actgrad_act == ACT_GELU_TANH &&
+  if (a.act == ACT_NONE && !a.preact && a.actgrad_src && a.actgrad_dtype == DT_BF16 &&
+      (a.actgrad_act == ACT_GELU_TANH || a.actgrad_act == ACT_GRAD_PRECOMPUTED) &&
       !a.residual && a.c_dtype == DT_BF16)
     return EPIK_ACTGRAD;
   return EPIK_GENERIC;
@@ -1143,7 +1184,10 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
   CT_REQUIRE(a.beta == 0.f || a.beta == 1.f, CT_ERR_BAD_ARG, "ct_gemm: beta must be 0 or 1");
   CT_REQUIRE(a.beta == 0.f || a.c_dtype == DT_F32, CT_ERR_UNSUPPORTED,
              "ct_gemm: beta=1 requires f32 C");
-  CT_REQUIRE(a.act >= 0 && a.act <= 4 && a.actgrad_act >= 0 && a.actgrad_act <= 4, CT_ERR_BAD_ARG,
+  CT_REQUIRE(a.act >= 0 && a.act <= ACT_GELU_TANH_SAVE_GRAD && a.actgrad_act >= 0 &&
+                 a.actgrad_act <= ACT_GRAD_PRECOMPUTED && a.actgrad_act != ACT_GELU_TANH_SAVE_GRAD &&
+                 (a.act != ACT_GELU_TANH_SAVE_GRAD || a.preact != nullptr),
+             CT_ERR_BAD_ARG,
              "ct_gemm: bad activation enum");
   CT_REQUIRE(a.lda >= (a.a_mn_major ? a.M : a.K) && a.ldb >= (a.b_mn_major ? a.N : a.K) &&
                  a.ldc >= a.N,

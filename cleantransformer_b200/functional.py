@@ -8,6 +8,7 @@ that removes autograd's accumulate copies and lets the DDP wrapper see a gradien
 kernel that produced it has been enqueued.
 """
 import math
+import os
 import threading
 
 import torch
@@ -353,6 +354,9 @@ def default_scale(head_dim):
 # ------------------------------------------------------------------------------------------------
 # Fused pre-LN block (Bloom / GPT-2 wiring): one autograd node per block
 # ------------------------------------------------------------------------------------------------
+SAVE_ACT_GRAD = os.environ.get("CT_SAVE_ACT_GRAD", "0") != "0"
+
+
 class PreLNBlockFn(torch.autograd.Function):
     """x -> x + proj(attn(qkv(LN1 x)))  -> ... + W2 act(W1 LN2(.)):
     modeling_bloom.py:142-159 (apply_residual_connection_post_layernorm = False) and the 'gpt2' branch
@@ -381,8 +385,12 @@ class PreLNBlockFn(torch.autograd.Function):
                                 residual=x2, out_dtype=torch.float32, w_in_out=io)
         ln2, _, mean2, rstd2 = ops.layernorm_fwd(att, spec["ln2"].weight.detach(), spec["ln2"].bias.detach(),
                                                  spec["ln2"].eps, out_dtype=cd)
-        h4, pre = ops.linear_fwd(ln2, shadow(spec["fc1"].weight, cd), spec["fc1"].bias.detach(), act=spec["act"],
+        # tanh-GELU: the forward epilogue saves gelu'(h) (same tanh as gelu(h)) in place of h, so the 4h->h dgrad
+        # epilogue only multiplies (SAVE_ACT_GRAD; `pre` then holds the derivative, see backward)
+        act_f = ops.ACT_GELU_TANH_SAVE_GRAD if (SAVE_ACT_GRAD and spec["act"] == ops.ACT_GELU_TANH) else spec["act"]
+        h4, pre = ops.linear_fwd(ln2, shadow(spec["fc1"].weight, cd), spec["fc1"].bias.detach(), act=act_f,
                                  out_dtype=cd, save_preact=True, w_in_out=io)
+        ctx.pre_is_grad = act_f == ops.ACT_GELU_TANH_SAVE_GRAD
         out, _ = ops.linear_fwd(h4, shadow(spec["fc2"].weight, cd), spec["fc2"].bias.detach(), residual=att,
                                 out_dtype=torch.float32, w_in_out=io)
         ctx.save_for_backward(x2, mean1, rstd1, ln1, qkv, o, lse2, att, mean2, rstd2, ln2, pre, h4, kbias2,
@@ -458,7 +466,8 @@ class PreLNBlockFn(torch.autograd.Function):
         else:
             g16 = g16.view(B * S, H)
         # FFN: out = att + fc2(act(fc1(ln2)))
-        d_pre = PreLNBlockFn._linear_bwd(spec["fc2"], g16, h4, io, cd, actgrad_src=pre, actgrad_act=spec["act"])
+        d_pre = PreLNBlockFn._linear_bwd(spec["fc2"], g16, h4, io, cd, actgrad_src=pre,
+                                         actgrad_act=ops.ACT_GRAD_PRECOMPUTED if ctx.pre_is_grad else spec["act"])
         d_ln2 = PreLNBlockFn._linear_bwd(spec["fc1"], d_pre, ln2, io, cd)
         # LN2 backward + residual path; also emits bf16(g_att) and proj.bias.grad = colsum(g_att)
         g_att, g16b = PreLNBlockFn._ln_bwd(spec["ln2"], d_ln2, att, mean2, rstd2, g_out, low_dtype=cd,

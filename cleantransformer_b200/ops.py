@@ -14,6 +14,8 @@ from ._lib import AttnArgs, AttnBwdArgs, GemmArgs, check
 
 F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU_ERF, ACT_GELU_TANH, ACT_TANH = 0, 1, 2, 3, 4
+# GEMM epilogues only (include/ct_b200.h): forward saves gelu_tanh'(t) instead of t / backward multiplies by the saved value
+ACT_GELU_TANH_SAVE_GRAD, ACT_GRAD_PRECOMPUTED = 5, 6
 ACT_BY_NAME = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU_ERF,
                "gelu_erf": ACT_GELU_ERF, "gelu_new": ACT_GELU_TANH, "gelu_tanh": ACT_GELU_TANH,
                "tanh": ACT_TANH}

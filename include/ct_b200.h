@@ -39,6 +39,11 @@ extern "C" {
 #define CT_ACT_GELU_ERF 2  /* modeling_bert.py:229 (torch.nn.GELU) */
 #define CT_ACT_GELU_TANH 3 /* modeling_bloom.py:335-345, modeling_gpt.py:112-122 */
 #define CT_ACT_TANH 4      /* modeling_bert.py:283-286 (pooler) */
+/* GEMM epilogues only. CT_ACT_GELU_TANH_SAVE_GRAD as `act`: y = gelu_tanh(t) and the `preact` output receives
+ * gelu_tanh'(t) — what GeLUFunction.backward (modeling_bloom.py:288-306) derives from the saved input — so that
+ * the backward epilogue only multiplies. CT_ACT_GRAD_PRECOMPUTED as `actgrad_act`: `actgrad_src` holds act'(pre). */
+#define CT_ACT_GELU_TANH_SAVE_GRAD 5
+#define CT_ACT_GRAD_PRECOMPUTED 6
 
 /* ---- library ------------------------------------------------------------------------------- */
 int ct_version(void);

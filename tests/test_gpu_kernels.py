@@ -210,6 +210,16 @@ def test_gemm_specialised_epilogues_vs_oracle(M, N, K, variant):
         pr = pre.float().clone().requires_grad_(True)
         O.activation(pr, "gelu_new").backward(dy.float() @ w2.float())
         assert rel_err(dx, pr.grad) < 5e-3
+        # forward that saves gelu'(t) instead of t (one tanh for both) + backward that only multiplies
+        g2, dpre = ops.linear_fwd(x, w, b, act=ops.ACT_GELU_TANH_SAVE_GRAD, save_preact=True)
+        assert torch.equal(g2, g)
+        tt = t.clone().requires_grad_(True)
+        O.activation(tt, "gelu_new").sum().backward()
+        assert rel_err(dpre, tt.grad) < 4e-3
+        dx2 = ops.linear_dgrad(dy, w2, actgrad_src=dpre, actgrad_act=ops.ACT_GRAD_PRECOMPUTED)
+        pr2 = t.clone().requires_grad_(True)  # reference at the unrounded pre-activation
+        O.activation(pr2, "gelu_new").backward(dy.float() @ w2.float())
+        assert rel_err(dx2, pr2.grad) < 8e-3
     finally:
         ops.set_option("GEMM_EPI_IMPL", prev)
 
