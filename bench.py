@@ -386,7 +386,7 @@ def main():
             "gpu_launches": launches,
             "loss": float(loss.detach()), "loss_e2e": float(loss_e2e),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_2cta_kernel", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch of the LM-head forward GEMM
                          # (the largest launch of this kernel: M=8192, N=250880, K=1024), ncu --set full,

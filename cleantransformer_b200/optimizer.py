@@ -162,6 +162,34 @@ class TorchAdamW(torch.optim.Optimizer):
                 else:
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        self._adopt_state()
+
+    def _adopt_state(self):
+        """Moments that did not come from the arena (torch's load_state_dict hands every parameter freshly
+        cloned tensors: trainer resume, examples/ft_bloom_DDP.py:155-156 checkpoints) are copied INTO the arena
+        and the state is re-pointed at the arena views, so the flat kernel keeps seeing what state_dict() shows."""
+        a = self._arena
+        if a is None:
+            return
+        for p in self._all_params():
+            st = self.state.get(p)
+            if not st:
+                continue
+            for key, buf in (("exp_avg", a.exp_avg), ("exp_avg_sq", a.exp_avg_sq)):
+                view = a.param_view(p, buf)
+                cur = st.get(key)
+                if cur is None:
+                    st[key] = view
+                elif cur.data_ptr() != view.data_ptr():
+                    view.copy_(cur.to(device=view.device, dtype=view.dtype).reshape(view.shape))
+                    st[key] = view
+            if not torch.is_tensor(st.get("step")):
+                st["step"] = torch.tensor(float(st.get("step", 0)), dtype=torch.float32)
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        if self._arena_checked:
+            self._adopt_state()  # before the first step _setup() does it
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale=1.0):

@@ -162,3 +162,40 @@ def test_ddp_wrapper_world2_gloo():
     for a, b, x, y in zip(g0, g1, l0, l1):
         assert torch.allclose(a, b)  # every rank holds the same reduced gradient
         assert rel_err(a, (x + y) / 2) < 1e-6  # and it is the mean of the per-rank gradients
+
+
+def test_adamw_load_state_dict_lands_in_the_arena(monkeypatch):
+    """Resume (trainer / examples/ft_bloom_DDP.py:155-156 checkpoints): torch's load_state_dict hands the
+    optimizer cloned moment tensors; the flat AdamW kernel reads the arena buffers, so the loaded moments must be
+    copied into the arena and the state re-pointed at the arena views — both when the state is loaded before the
+    first step and after it. (Host logic only: no kernel runs.)"""
+    from cleantransformer_b200 import optimizer as opt_mod
+    monkeypatch.setattr(opt_mod, "_require_cuda", lambda ps: None)
+
+    def make():
+        torch.manual_seed(0)
+        return [torch.nn.Parameter(torch.randn(5, 7)), torch.nn.Parameter(torch.randn(9))]
+
+    src = opt_mod.TorchAdamW(make(), lr=1e-3)
+    src._setup()
+    for i, p in enumerate(src._all_params()):
+        src.state[p]["exp_avg"].fill_(0.25 * (i + 1))
+        src.state[p]["exp_avg_sq"].fill_(0.5 * (i + 1))
+        src.state[p]["step"] += 3
+    sd = src.state_dict()
+    assert float(src._arena.exp_avg.abs().sum()) > 0  # state tensors ARE arena views
+
+    for setup_first in (False, True):
+        dst = opt_mod.TorchAdamW(make(), lr=1e-3)
+        if setup_first:
+            dst._setup()
+        dst.load_state_dict(sd)
+        dst._setup()
+        a = dst._arena
+        for i, p in enumerate(dst._all_params()):
+            st = dst.state[p]
+            assert st["exp_avg"].data_ptr() == a.param_view(p, a.exp_avg).data_ptr()
+            assert st["exp_avg_sq"].data_ptr() == a.param_view(p, a.exp_avg_sq).data_ptr()
+            assert torch.all(a.param_view(p, a.exp_avg) == 0.25 * (i + 1))
+            assert torch.all(a.param_view(p, a.exp_avg_sq) == 0.5 * (i + 1))
+            assert int(st["step"]) == 3
