@@ -1905,6 +1905,311 @@ __global__ void __launch_bounds__(FB3_THREADS, 1)
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// v5: persistent v3. r01g's per-CTA timeline puts ~9 k of the 31 k cycles of a 4-tile CTA into work nothing
+// overlaps at one CTA per SM: set-up and first loads (2.7 k), the wait for the last dQ / dV / dK MMAs (2.2 k)
+// and the dQ drain + dK / dV epilogue (4 k). Here a CTA loops over work items (kv tile, b, h) — kv tiles in
+// ascending order = heaviest first under the causal mask — with every barrier phase derived from RUNNING tile /
+// item counters that all roles advance identically, so that
+//   * the TMA warp requests the next item's K / V the moment the last MMAs of the current item retire, and its
+//     Q / dO tiles through the same two-stage ring,
+//   * the MMA warp issues the next item's first S^T / dP^T right behind them (the score buffers were released
+//     when the compute warps took the last tile into registers),
+//   * the compute warps' epilogue (last dQ drain, dV / dK out of TMEM) runs under both; the first dV / dK MMA of
+//     the next item waits until the accumulators have been read (dkv_free).
+template <bool BF16>
+__global__ void __launch_bounds__(FB_THREADS, 1)
+    attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                        const AttnBwdP bp, const int n_items) {
+  const AttnP& p = bp.f;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t sK = base, sV = base + FA_TILE;
+  const uint32_t sQ = base + 2 * FA_TILE;   // 2 stages, each Q then dO
+  constexpr int N_TILES = 14;
+  constexpr uint32_t PDS_STRIDE = 4 * FA_TILE;  // buffer (g & 1) of the P^T / dS^T pair
+  constexpr uint32_t STAT_STRIDE = 1024;
+  const uint32_t sPT = base + 6 * FA_TILE;  // 2 panels
+  const uint32_t sDS = base + 8 * FA_TILE;  // 2 panels
+  const uint32_t bars = base + N_TILES * FA_TILE;
+  const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 24, sdp_full = bars + 40,
+                 pds_ready = bars + 48, mma_done = bars + 56, dkv_full = bars + 64, tmem_slot = bars + 72,
+                 sdp_free = bars + 80, dkv_free = bars + 88, lse_s = bars + 128, del_s = bars + 640;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + N_TILES * FA_TILE + 72);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_q_tiles = (p.Sq + 127) / 128;
+  const int BH = p.B * p.H;
+  // work item -> coordinates; identical in every role
+  auto coords = [&](int item, int& kv0, int& b, int& h, int& i_start, int& n_it) {
+    const int kv_tile = item / BH, bh = item - kv_tile * BH;
+    h = bh % p.H; b = bh / p.H;
+    kv0 = kv_tile * 128;
+    i_start = 0;
+    if (p.causal) {
+      const bool full_sweep = p.first_valid && (p.first_valid[b] > p.off);
+      if (!full_sweep) i_start = max(0, (kv0 - p.off) / 128);
+    }
+    n_it = max(0, n_q_tiles - i_start);
+  };
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full + 8 * s, 1); mbar_init(qdo_empty + 8 * s, 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_free, 256);
+    mbar_init(pds_ready, 256);
+    mbar_init(mma_done, 1);
+    mbar_init(dkv_full, 1);
+    mbar_init(dkv_free, 256);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t T_ST = tmem, T_DPT = tmem + 128, T_DV = tmem + 256, T_DK = tmem + 320, T_DQ = tmem + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0, I = 0;  // query tiles / items (with work) requested so far
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int kv0, b, h, i_start, n_it;
+        coords(item, kv0, b, h, i_start, n_it);
+        if (n_it == 0) continue;
+        if (I > 0) mbar_wait(dkv_full, (I - 1) & 1);  // the previous item's last MMAs retired: K / V are free
+        mbar_expect_tx(kv_full, 2 * FA_TILE);
+        tma_load_4d(sK, &tmK, kv_full, 0, kv0, h, b);
+        tma_load_4d(sV, &tmV, kv_full, 0, kv0, h, b);
+        for (int it = 0; it < n_it; ++it, ++g) {
+          const uint32_t s = g & 1;
+          const int q0 = (i_start + it) * 128;
+          mbar_wait(qdo_empty + 8 * s, ((g >> 1) & 1) ^ 1);
+          mbar_expect_tx(qdo_full + 8 * s, 2 * FA_TILE);
+          tma_load_4d(sQ + s * 2 * FA_TILE, &tmQ, qdo_full + 8 * s, 0, q0, h, b);
+          tma_load_4d(sQ + s * 2 * FA_TILE + FA_TILE, &tmDO, qdo_full + 8 * s, 0, q0, h, b);
+        }
+        ++I;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_kk = umma_idesc_f16(BF16 ? 1 : 0, 0, 0, 128, 128);  // S^T, dP^T
+      const uint32_t idesc_km = umma_idesc_f16(BF16 ? 1 : 0, 0, 1, 128, 64);   // dV, dK
+      const uint32_t idesc_mm = umma_idesc_f16(BF16 ? 1 : 0, 1, 1, 128, 64);   // dQ
+      auto issue_sdp = [&](uint32_t gq) {
+        const uint32_t s = gq & 1;
+        const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
+        mbar_wait(qdo_full + 8 * s, (gq >> 1) & 1);
+        if (gq > 0) mbar_wait(sdp_free, (gq - 1) & 1);  // every compute thread holds S^T/dP^T(gq-1) in registers
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // S^T[kv, q] = K[kv, d] . Q[q, d]
+          umma_f16(T_ST, umma_smem_desc_sw128(sK + k * 32, 0, 1024), umma_smem_desc_sw128(q + k * 32, 0, 1024),
+                   idesc_kk, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dP^T[kv, q] = V[kv, d] . dO[q, d]
+          umma_f16(T_DPT, umma_smem_desc_sw128(sV + k * 32, 0, 1024),
+                   umma_smem_desc_sw128(d_o + k * 32, 0, 1024), idesc_kk, k > 0);
+        umma_commit(sdp_full);
+      };
+      uint32_t g = 0, I = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int kv0, b, h, i_start, n_it;
+        coords(item, kv0, b, h, i_start, n_it);
+        if (n_it == 0) continue;
+        mbar_wait(kv_full, I & 1);
+        issue_sdp(g);
+        for (int it = 0; it < n_it; ++it) {
+          const uint32_t gq = g + it, s = gq & 1;
+          const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
+          if (it + 1 < n_it) issue_sdp(gq + 1);  // runs under the element math of tile gq
+          mbar_wait(pds_ready, gq & 1);
+          if (it == 0 && I > 0) mbar_wait(dkv_free, (I - 1) & 1);  // the previous item's dV / dK have left TMEM
+          tc_fence_after();
+          const uint32_t pt = sPT + s * PDS_STRIDE, dst = sDS + s * PDS_STRIDE;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // dQ[q, d] = dS[q, kv] . K[kv, d]  (A MN-major view of dS^T)
+            umma_f16(T_DQ, umma_smem_desc_sw128(dst + k * 2048, FA_TILE, 1024),
+                     umma_smem_desc_sw128(sK + k * 2048, 64 * 128, 1024), idesc_mm, k > 0);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // dV[kv, d] += P^T[kv, q] . dO[q, d]   (B MN-major: rows = q)
+            umma_f16(T_DV, umma_smem_desc_sw128(pt + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                     umma_smem_desc_sw128(d_o + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // dK[kv, d] += dS^T[kv, q] . Q[q, d]
+            umma_f16(T_DK, umma_smem_desc_sw128(dst + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                     umma_smem_desc_sw128(q + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
+          umma_commit(qdo_empty + 8 * s);
+          umma_commit(mma_done);  // dQ(gq) readable; P^T / dS^T buffer (gq & 1) free for tile gq+2
+        }
+        umma_commit(dkv_full);
+        g += n_it;
+        ++I;
+      }
+    }
+  } else {
+    const int wq = warp & 3;
+    const int rr = wq * 32 + lane;   // key row inside the tile (S^T) / query row (dQ)
+    const int hf = (warp - 2) >> 2;  // which pair of 32-query chunks this warp owns
+    const uint32_t t_lane = (uint32_t)(wq * 32) << 16;
+    const bool fill_is_ninf = p.causal_fill2 == -INFINITY;
+    const int c0 = 2 * hf, c1 = 2 * hf + 1;
+    uint32_t g = 0, I = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int kv0, b, h, i_start, n_it;
+      coords(item, kv0, b, h, i_start, n_it);
+      const int jg = kv0 + rr;
+      FbCtx cx;
+      cx.kb = (p.kbias2 && jg < p.Sk) ? __ldg(p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh + jg) : 0.f;
+      cx.sl2 = p.sl2; cx.scale = p.scale; cx.cf2 = p.causal_fill2;
+      cx.jg = jg; cx.off = p.off; cx.causal = p.causal; cx.key_oob = jg >= p.Sk;
+      cx.lse_s = lse_s; cx.del_s = del_s; cx.sPT = sPT; cx.sDS = sDS; cx.rr = rr; cx.sw = rr & 7;
+      // generic arithmetic for the whole warp when a key is masked (the reference's finite fill matters on
+      // fully masked query rows) or the key tile is ragged
+      const bool warp_generic = __any_sync(0xffffffffu, cx.kb < -1e30f) || (kv0 + 128 > p.Sk);
+      const float* lse_bh = p.lse2 + ((int64_t)b * p.H + h) * p.Sq;
+      const float* del_bh = bp.delta + ((int64_t)b * p.H + h) * p.Sq;
+      // per-query statistics of the first query tile, staged as -lse2 and -delta*scale
+      float nlse_next = -INFINITY, ndel_next = 0.f;
+      if (hf == 0 && n_it > 0 && i_start * 128 + rr < p.Sq) {
+        nlse_next = -__ldg(lse_bh + i_start * 128 + rr);
+        ndel_next = -__ldg(del_bh + i_start * 128 + rr) * p.scale;
+      }
+      // dQ rows of query tile `itp`: this thread owns query row (q0 + rr), columns [32*hf, 32*hf + 32) of d
+      auto red_dq = [&](const uint32_t (&r)[32], int itp) {
+        const int qi = (i_start + itp) * 128 + rr;
+        if (qi < p.Sq) {
+          float* dst = bp.dq_accum + (((int64_t)b * p.H + h) * n_q_tiles + (i_start + itp)) * FB_DQ_TILE +
+                       (hf * 8 * 128 + rr) * 4;
+#pragma unroll
+          for (int gg = 0; gg < 8; ++gg)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 512 * gg),
+                         "f"(__uint_as_float(r[4 * gg])), "f"(__uint_as_float(r[4 * gg + 1])),
+                         "f"(__uint_as_float(r[4 * gg + 2])), "f"(__uint_as_float(r[4 * gg + 3]))
+                         : "memory");
+        }
+      };
+
+      for (int it = 0; it < n_it; ++it) {
+        const uint32_t gq = g + it;
+        const int q0 = (i_start + it) * 128;
+        cx.sPT = sPT + (gq & 1) * PDS_STRIDE; cx.sDS = sDS + (gq & 1) * PDS_STRIDE;
+        cx.lse_s = lse_s + (gq & 1) * STAT_STRIDE; cx.del_s = del_s + (gq & 1) * STAT_STRIDE;
+        mbar_wait(sdp_full, gq & 1);
+        tc_fence_after();
+        // chunk kinds (warp-uniform)
+        const bool touches_diag = p.causal && (kv0 + 127 > q0 + p.off);
+        const bool aligned_diag = touches_diag && fill_is_ninf && (kv0 == q0 + p.off) && !warp_generic;
+        int kind0, kind1;
+        if (warp_generic || (touches_diag && !aligned_diag)) {
+          kind0 = kind1 = 2;
+        } else if (aligned_diag) {
+          // key row 32*wq+l vs queries 32*c..32*c+31: c < wq entirely future, c > wq entirely visible
+          kind0 = c0 < wq ? 1 : (c0 > wq ? 0 : 2);
+          kind1 = c1 < wq ? 1 : (c1 > wq ? 0 : 2);
+        } else {
+          kind0 = kind1 = 0;
+        }
+        uint32_t rs0[32], rd0[32], rs1[32], rd1[32];
+        if (kind0 != 1) { tmem_ld_32x32(T_ST + t_lane + c0 * 32, rs0); tmem_ld_32x32(T_DPT + t_lane + c0 * 32, rd0); }
+        if (kind1 != 1) { tmem_ld_32x32(T_ST + t_lane + c1 * 32, rs1); tmem_ld_32x32(T_DPT + t_lane + c1 * 32, rd1); }
+        // statistics buffer (gq & 1) was last read by tile gq-2, and every thread finished tile gq-2 before it
+        // arrived at the named barrier of tile gq-1, which this thread has passed (also across items)
+        if (hf == 0) {
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.lse_s + 4 * rr), "f"(nlse_next) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.del_s + 4 * rr), "f"(ndel_next) : "memory");
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(sdp_free);        // S^T / dP^T are in registers: the next tile's MMAs may overwrite them
+        bar_sync_named(1, 256);       // statistics staged by the hf == 0 warps are visible
+        if (hf == 0) {
+          const int nq = q0 + 128 + rr;
+          const bool ok = (it + 1 < n_it) && nq < p.Sq;
+          nlse_next = ok ? -__ldg(lse_bh + nq) : -INFINITY;
+          ndel_next = ok ? -__ldg(del_bh + nq) * p.scale : 0.f;
+        }
+        if (kind0 == 0) fb2_chunk<0, BF16>(cx, rs0, rd0, c0, q0);
+        else if (kind0 == 1) fb2_chunk<1, BF16>(cx, rs0, rd0, c0, q0);
+        else fb2_chunk<2, BF16>(cx, rs0, rd0, c0, q0);
+        if (it > 0) {
+          // MMAs of tile gq-1 ran under chunk 0; waiting for every phase in order (the last tile of an item is
+          // waited for in its epilogue) also proves that buffer ((gq+1) & 1) of P^T / dS^T is free for tile gq+1
+          mbar_wait(mma_done, (gq - 1) & 1);
+          tc_fence_after();
+          uint32_t rq[32];
+          tmem_ld_32x32(T_DQ + t_lane + hf * 32, rq);
+          tmem_ld_wait();
+          red_dq(rq, it - 1);
+        }
+        if (kind1 == 0) fb2_chunk<0, BF16>(cx, rs1, rd1, c1, q0);
+        else if (kind1 == 1) fb2_chunk<1, BF16>(cx, rs1, rd1, c1, q0);
+        else fb2_chunk<2, BF16>(cx, rs1, rd1, c1, q0);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(pds_ready);
+      }
+      // ---- epilogue of this item, under the next item's loads and first S^T / dP^T ----
+      uint32_t rv[32], rk[32];
+      if (n_it > 0) {
+        mbar_wait(mma_done, (g + n_it - 1) & 1);
+        tc_fence_after();
+        {
+          uint32_t rq[32];
+          tmem_ld_32x32(T_DQ + t_lane + hf * 32, rq);
+          tmem_ld_wait();
+          red_dq(rq, n_it - 1);
+        }
+        mbar_wait(dkv_full, I & 1);
+        tc_fence_after();
+        tmem_ld_32x32(T_DV + t_lane + hf * 32, rv);
+        tmem_ld_32x32(T_DK + t_lane + hf * 32, rk);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(dkv_free);  // the next item's first dV / dK MMAs may overwrite the accumulators
+      } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) { rv[t] = 0u; rk[t] = 0u; }
+      }
+      if (!cx.key_oob) {
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          void* basep = which == 0 ? bp.dv : bp.dk;
+          const int64_t eo = which == 0
+              ? (int64_t)b * bp.dv_sb + (int64_t)h * bp.dv_sh + (int64_t)jg * bp.dv_ss
+              : (int64_t)b * bp.dk_sb + (int64_t)h * bp.dk_sh + (int64_t)jg * bp.dk_ss;
+          uint8_t* row = reinterpret_cast<uint8_t*>(basep) + 2 * (eo + hf * 32);
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            uint4 w;
+            float f[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[u] = __uint_as_float(which == 0 ? rv[8 * gg + u] : rk[8 * gg + u]);
+            if constexpr (BF16) {
+              w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]);
+              w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
+            } else {
+              __half2 x;
+              x = __floats2half2_rn(f[0], f[1]); w.x = *reinterpret_cast<uint32_t*>(&x);
+              x = __floats2half2_rn(f[2], f[3]); w.y = *reinterpret_cast<uint32_t*>(&x);
+              x = __floats2half2_rn(f[4], f[5]); w.z = *reinterpret_cast<uint32_t*>(&x);
+              x = __floats2half2_rn(f[6], f[7]); w.w = *reinterpret_cast<uint32_t*>(&x);
+            }
+            *reinterpret_cast<uint4*>(row + 16 * gg) = w;
+          }
+        }
+      }
+      if (n_it > 0) { g += n_it; ++I; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (one warp per (b,i,h); D <= 128)
 __global__ void __launch_bounds__(256)
     attn_delta_kernel(const void* __restrict__ dout, const void* __restrict__ o, int fmt, int64_t sb,
@@ -2465,9 +2770,11 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     if ((rc = make_qkv_tmap(&tmV, a.v, a.v_sb, a.v_sh, a.v_ss, a.B, a.H, a.Sk, 64))) return rc;
     if ((rc = make_qkv_tmap(&tmDO, args->dout, a.o_sb, a.o_sh, a.o_ss, a.B, a.H, a.Sq, 64))) return rc;
     // ATTN_BWD_IMPL: 0 = auto (v3), 1 = v1, 2 = v2 (row-major dQ workspace), 3 = v2 + tiled dQ workspace,
-    //                4 = v3 (tiled dQ workspace, P^T / dS^T double-buffered), 5 = v4 (v3 + dedicated dQ drain warpgroup)
+    //                4 = v3 (tiled dQ workspace, P^T / dS^T double-buffered), 5 = v4 (v3 + dedicated dQ drain warpgroup),
+    //                6 = v5 (persistent v3: the next work item's loads and first MMAs run under the epilogue; NOT yet
+    //                    run on a GPU — written after the round's GPU budget was spent)
     int variant = option(OPT_ATTN_BWD_IMPL);
-    if (variant < 1 || variant > 5) variant = 4;
+    if (variant < 1 || variant > 6) variant = 4;
     const bool dq_tiled = variant >= 3;
     const int nqt = (a.Sq + 127) / 128;
     // the workspace is sized for whole query tiles (include/ct_b200.h): B*H*ceil(Sq/128)*128*64 floats
@@ -2485,6 +2792,8 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       attr = true;
     }
     const int64_t grid = (int64_t)a.B * a.H * ((a.Sk + 127) / 128);
@@ -2499,6 +2808,13 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
         if (fmt == 1) attn_bwd_tc2_kernel<true, 1><<<g, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
         else attn_bwd_tc2_kernel<false, 1><<<g, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
         break;
+      case 6: {
+        const int n_items = (int)grid;
+        const unsigned pg = (unsigned)(n_items < sm_count() ? n_items : sm_count());
+        if (fmt == 1) attn_bwd_tc5_kernel<true><<<pg, FB_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp, n_items);
+        else attn_bwd_tc5_kernel<false><<<pg, FB_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp, n_items);
+        break;
+      }
       case 5:
         if (fmt == 1) attn_bwd_tc3_kernel<true><<<g, FB3_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
         else attn_bwd_tc3_kernel<false><<<g, FB3_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);

@@ -9,6 +9,7 @@ Tolerances: err = ||x - ref||_inf / ||ref||_inf.
   attention (P rounded to bf16 before P.V, like the reference's autocast matmul): <= 5e-3
 """
 import math
+import os
 
 import pytest
 import torch
@@ -292,6 +293,10 @@ ATT_CASES = [
 # double-buffered P^T / dS^T (element math of tile it+1 under the MMAs of tile it), "v4" = v3 with the dQ drain on its
 # own warpgroup
 ATT_VARIANTS = {"v1": (1, 1), "v2": (0, 2), "v2t": (0, 3), "v3": (0, 4), "v4": (0, 5)}
+if os.environ.get("CT_TEST_EXPERIMENTAL"):
+    # variants written after the round's GPU budget was spent: compiled, never run — opt-in until a GPU visit
+    # has shown them green (run them under `timeout`: a protocol bug in a persistent kernel traps after 2 s)
+    ATT_VARIANTS["v5"] = (0, 6)  # persistent backward
 ATT_PARAMS = [c + ("-",) for c in ATT_CASES if c[-1] == 2] + \
              [c + (v,) for c in ATT_CASES if c[-1] == 1 for v in ATT_VARIANTS]
 
