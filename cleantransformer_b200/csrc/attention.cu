@@ -531,7 +531,15 @@ __device__ __forceinline__ void fa2_diag_tile(uint32_t t_s, float sl2, uint32_t 
   }
 }
 
-template <bool HAS_KB, bool BF16>
+// LAZY (forward v3, ATTN_FWD_IMPL=2; written after the round's GPU budget was spent — compiled, not yet run):
+// the r01f stamps show the slowest softmax warp of every tile waiting ~1.2 k cycles for P(j-1).V(j-1) before it
+// may overwrite the single P tile and rescale O. Here (interior tiles)
+//   * the running maximum is a REFERENCE that only moves when the tile maximum exceeds it by more than 8 (2^8:
+//     P stays within bf16 range, sums stay fp32), so O is rescaled — and P.V waited for — only in those tiles;
+//   * P is handed over in its two 64-key panels: panel 0 is rewritten as soon as the first four MMAs of the previous
+//     P.V have retired (p0_free) and its MMAs start while the softmax warps still work on panel 1.
+// Masked / diagonal tiles keep the exact per-tile maximum and arrive on both panel barriers at the end.
+template <bool HAS_KB, bool BF16, bool LAZY = false>
 __global__ void __launch_bounds__(FA_THREADS, 2)
     attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const AttnP p) {
@@ -544,6 +552,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
   const uint32_t bars = base + 7 * FA_TILE;
   const uint32_t q_full = bars, k_full = bars + 8, v_full = bars + 24, kv_empty = bars + 40, s_full = bars + 56,
                  s_free = bars + 64, p_ready = bars + 72, o_full = bars + 80, tmem_slot = bars + 88,
+                 p_half1 = bars + 96 /* LAZY: second P panel written */, p0_free = bars + 104 /* LAZY: first P panel read */,
                  kb_s = bars + 128;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + 7 * FA_TILE + 88);
 
@@ -573,6 +582,8 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
     mbar_init(s_free, 128);
     mbar_init(p_ready, 128);
     mbar_init(o_full, 1);
+    mbar_init(p_half1, 128);
+    mbar_init(p0_free, 1);
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
@@ -614,13 +625,21 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         if (j + 1 < n_kv) issue_s(j + 1);  // runs under the softmax of tile j
-        mbar_wait(p_ready, j & 1);
+        mbar_wait(p_ready, j & 1);  // LAZY: first panel (keys 0..63 of the tile) only
         mbar_wait(v_full + 8 * s, (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < 8; ++k) {
+          if constexpr (LAZY) {
+            if (k == 4) {
+              umma_commit(p0_free);
+              mbar_wait(p_half1, j & 1);
+              tc_fence_after();
+            }
+          }
           umma_f16(tmem + 128, umma_smem_desc_sw128(sP + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
                    umma_smem_desc_sw128(sV + s * FA_TILE + k * 2048, 64 * 128, 1024), idesc_o, (j > 0 || k > 0));
+        }
         umma_commit(kv_empty + 8 * s);
         umma_commit(o_full);
       }
@@ -688,6 +707,59 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
         CT_DBG_STAMP(2048 + 16 * j + 4);
         if constexpr (!HAS_KB) mt *= p.sl2;  // sl2 > 0 (checked on the host)
         mt = fmaxf(mt, -FLT_MAX);
+        if constexpr (LAZY) {
+          // reference maximum: moves (and O is rescaled, which needs P(j-1) V(j-1)) only when this tile exceeds it by
+          // more than 2^8; warp-uniform branch because the TMEM accesses are warp-collective
+          const bool need = mt > m + 8.f;
+          if (j == 0) {
+            m = mt;
+          } else if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(o_full, (j - 1) & 1);
+            tc_fence_after();
+            const float m_up = need ? mt : m;
+            const float a_up = ex2(m - m_up);
+            const float2 a2 = make_float2(a_up, a_up);
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {  // 32 columns at a time: the score row stays in registers beside it
+              uint32_t o0[32];
+              tmem_ld_32x32(t_o + 32 * hh, o0);
+              tmem_ld_wait();
+#pragma unroll
+              for (int t = 0; t < 16; ++t) {
+                float2 x = __fmul2_rn(make_float2(__uint_as_float(o0[2 * t]), __uint_as_float(o0[2 * t + 1])), a2);
+                o0[2 * t] = __float_as_uint(x.x); o0[2 * t + 1] = __float_as_uint(x.y);
+              }
+              tmem_st_32x32(t_o + 32 * hh, o0);
+            }
+            tmem_st_wait();
+            l *= a_up;
+            m = m_up;
+          }
+          m_new = m;
+          alpha = 1.f;  // the common tail below: l = l * alpha + lt, no second rescale
+          if (j > 0) {  // first four MMAs of P(j-1) V(j-1) retired: panel 0 of the P tile may be overwritten
+            mbar_wait(p0_free, (j - 1) & 1);
+            tc_fence_after();
+          }
+          float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
+          fa2_exp_store<HAS_KB, BF16>(r0, 0, m_new, p.sl2, p_row, sw, acc0, acc1);
+          fa2_exp_store<HAS_KB, BF16>(r1, 1, m_new, p.sl2, p_row, sw, acc0, acc1);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(p_ready);  // panel 0: its MMAs run under the rest of this tile
+          if (j > 0) {  // all of P(j-1) V(j-1) retired: panel 1 may be overwritten
+            mbar_wait(o_full, (j - 1) & 1);
+            tc_fence_after();
+          }
+          fa2_exp_store<HAS_KB, BF16>(r2, 2, m_new, p.sl2, p_row, sw, acc0, acc1);
+          fa2_exp_store<HAS_KB, BF16>(r3, 3, m_new, p.sl2, p_row, sw, acc0, acc1);
+          lt = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+          l += lt;
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(p_half1);
+          continue;  // (the tail below belongs to the exact-maximum paths)
+        }
         m_new = fmaxf(m, mt);
         alpha = ex2(m - m_new);
         if (j > 0) {  // P(j-1) V(j-1) retired: the P tile may be overwritten, O may be rescaled
@@ -824,6 +896,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
       CT_DBG_STAMP(2048 + 16 * j + 7);
       tc_fence_before();
       mbar_arrive(p_ready);
+      if constexpr (LAZY) mbar_arrive(p_half1);  // exact-maximum paths hand both panels over together
       CT_DBG_STAMP(2048 + 16 * j + 8);
     }
     // ---- epilogue: O / l -> merged-head layout, lse2 ----
@@ -2693,12 +2766,19 @@ extern "C" int ct_attn_fwd(const ct_attn_args* args, void* stream) {
       CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
       CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
       CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
       attr = true;
     }
     const int64_t grid = (int64_t)a.B * a.H * ((a.Sq + 127) / 128);
-    // ATTN_FWD_IMPL: 0 = auto (v2: register-resident score rows, O in TMEM), 1 = v1 (two TMEM passes)
+    // ATTN_FWD_IMPL: 0 = auto (v2: register-resident score rows, O in TMEM), 1 = v1 (two TMEM passes),
+    //                2 = v3 (v2 + lazy reference maximum + P handed over per 64-key panel; bf16 only; compiled,
+    //                    not yet run on a GPU)
     const bool v2 = option(OPT_ATTN_FWD_IMPL) != 1 && a.scale > 0.f;
-    if (v2) {
+    if (v2 && option(OPT_ATTN_FWD_IMPL) == 2 && p.fmt == 1) {
+      if (a.kbias2 != nullptr) attn_fwd_tc2_kernel<true, true, true><<<(unsigned)grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, p);
+      else attn_fwd_tc2_kernel<false, true, true><<<(unsigned)grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, p);
+    } else if (v2) {
       const bool kb = a.kbias2 != nullptr, bf = p.fmt == 1;
       if (kb && bf) attn_fwd_tc2_kernel<true, true><<<(unsigned)grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, p);
       else if (kb) attn_fwd_tc2_kernel<true, false><<<(unsigned)grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, p);
