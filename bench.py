@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--comm", default=None, help="p2p (default) or nccl (baseline collective)")
+    ap.add_argument("--comm", default=None, help="p2p (default), nccl (baseline collective) or ce (copy-engine transport, experimental)")
     return ap.parse_args()
 
 

@@ -133,6 +133,10 @@ SIGNATURES = {
     "ct_comm_connect": (c_int, [c_void_p, c_void_p]),
     "ct_allreduce_bucket": (c_int, [c_i64, c_i64, c_float, c_int, c_int, c_void_p]),
     "ct_broadcast": (c_int, [c_i64, c_i64, c_int, c_void_p]),
+    "ct_comm_barrier": (c_int, [c_void_p]),
+    "ct_comm_pull": (c_int, [c_int, c_i64, c_void_p, c_i64, c_void_p]),
+    "ct_comm_push": (c_int, [c_int, c_i64, c_i64, c_i64, c_void_p]),
+    "ct_comm_reduce_slices": (c_int, [c_i64, c_void_p, c_i64, c_i64, c_float, c_int, c_void_p]),
     "ct_embedding_bwd_allranks": (c_int, [c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_float, c_int,
                                           c_void_p]),
     "ct_comm_finalize": (c_int, []),

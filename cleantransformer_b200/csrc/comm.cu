@@ -274,6 +274,39 @@ __global__ void __launch_bounds__(256)
   wait_flags(my_sig + MAX_WORLD, W, p.epoch);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Copy-engine transport (comm mode "ce"). r01i showed what the register-staged kernel above costs when it shares
+// SMs with the persistent GEMMs of the backward pass: 48 CTAs hide the exchange but slow the GEMMs by 3.3 ms per
+// step, fewer CTAs leave it exposed. The alternative keeps the SMs out of the transport altogether: the two
+// NVLink legs of the two-shot all-reduce are cudaMemcpyAsync peer copies (DMA engines), and the only kernels are a
+// one-CTA flag barrier and an HBM-bound local reduction of the W staged slices:
+//   barrier | pull slice r of every peer into local staging | reduce (rank order) | push the result into every
+//   peer's slice r | barrier
+// Every slice is reduced by exactly one rank and then copied, so all ranks end up bit-identical.
+__global__ void __launch_bounds__(32) comm_barrier_kernel(const ArParams p) {
+  const int W = p.world, r = p.rank;
+  if ((int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + r, p.epoch);
+  wait_flags(p.sig[r], W, p.epoch);
+}
+
+// dst[i] = scale * sum over ranks q in rank order of (q == rank ? dst[i] : staged[slot(q)][i]); slots are the peers
+// in ascending rank order, `stride` floats apart
+__global__ void __launch_bounds__(256)
+    reduce_slices_kernel(float* __restrict__ dst, const float* __restrict__ staged, int64_t stride, int world,
+                         int rank, int64_t nvec, float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int slot = 0;
+    for (int q = 0; q < world; ++q) {
+      const float4 v = q == rank ? reinterpret_cast<const float4*>(dst)[i]
+                                 : __ldcs(reinterpret_cast<const float4*>(staged + (int64_t)(slot++) * stride) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+    reinterpret_cast<float4*>(dst)[i] = acc;
+  }
+}
+
 static void fill_params(ArParams& p, int64_t offset, int64_t count, float scale) {
   for (int q = 0; q < g_comm.world; ++q) { p.data[q] = g_comm.data[q]; p.sig[q] = g_comm.sig[q]; }
   p.rank = g_comm.rank; p.world = g_comm.world;
@@ -403,6 +436,62 @@ extern "C" int ct_embedding_bwd_allranks(int64_t hdr_offset, int64_t rows_offset
   p.H = H; p.V = V; p.padding_idx = (long long)padding_idx; p.scale = scale;
   if (max_ctas <= 0) max_ctas = sm_count() * 2;
   embed_scatter_allranks_kernel<<<(unsigned)max_ctas, 256, 0, (cudaStream_t)stream>>>(p);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_comm_barrier(void* stream) {
+  CT_REQUIRE(g_comm.ready, CT_ERR_COMM, "ct_comm_barrier: comm not initialised");
+  ArParams p;
+  {
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    fill_params(p, 0, 0, 1.f);
+  }
+  comm_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+// copy-engine legs: `count` floats between the symmetric buffer of `peer` (offset in floats) and local memory
+extern "C" int ct_comm_pull(int peer, int64_t peer_offset, void* dst_local, int64_t count, void* stream) {
+  CT_REQUIRE(g_comm.ready, CT_ERR_COMM, "ct_comm_pull: comm not initialised");
+  CT_REQUIRE(peer >= 0 && peer < g_comm.world && dst_local && peer_offset >= 0 && count >= 0 &&
+                 (size_t)(peer_offset + count) * 4 <= g_comm.data_bytes,
+             CT_ERR_BAD_ARG, "ct_comm_pull: bad peer / range");
+  if (count == 0) return 0;
+  CT_CUDA_OK(cudaMemcpyAsync(dst_local, g_comm.data[peer] + peer_offset, (size_t)count * 4, cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int ct_comm_push(int peer, int64_t peer_offset, int64_t local_offset, int64_t count, void* stream) {
+  CT_REQUIRE(g_comm.ready, CT_ERR_COMM, "ct_comm_push: comm not initialised");
+  CT_REQUIRE(peer >= 0 && peer < g_comm.world && peer_offset >= 0 && local_offset >= 0 && count >= 0 &&
+                 (size_t)(peer_offset + count) * 4 <= g_comm.data_bytes &&
+                 (size_t)(local_offset + count) * 4 <= g_comm.data_bytes,
+             CT_ERR_BAD_ARG, "ct_comm_push: bad peer / range");
+  if (count == 0) return 0;
+  CT_CUDA_OK(cudaMemcpyAsync(g_comm.data[peer] + peer_offset, g_comm.data[g_comm.rank] + local_offset, (size_t)count * 4,
+                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+// local_offset: the slice this rank owns (inside its symmetric buffer); staged: (world-1) slices, `stride` floats
+// apart, peers in ascending rank order. count % 4 == 0, everything 16-byte aligned.
+extern "C" int ct_comm_reduce_slices(int64_t local_offset, const float* staged, int64_t stride, int64_t count,
+                                     float scale, int max_ctas, void* stream) {
+  CT_REQUIRE(g_comm.ready, CT_ERR_COMM, "ct_comm_reduce_slices: comm not initialised");
+  CT_REQUIRE(staged && local_offset >= 0 && count >= 0 && (count % 4) == 0 && (local_offset % 4) == 0 &&
+                 (stride % 4) == 0 && stride >= count && ((uintptr_t)staged & 15) == 0 &&
+                 (size_t)(local_offset + count) * 4 <= g_comm.data_bytes,
+             CT_ERR_BAD_ARG, "ct_comm_reduce_slices: bad range / alignment");
+  if (count == 0) return 0;
+  const int64_t nvec = count >> 2;
+  int64_t ctas = (nvec + 255) / 256;
+  if (max_ctas <= 0) max_ctas = sm_count() * 4;
+  if (ctas > max_ctas) ctas = max_ctas;
+  reduce_slices_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(
+      g_comm.data[g_comm.rank] + local_offset, staged, stride, g_comm.world, g_comm.rank, nvec, scale);
   CT_LAUNCH_OK();
   return 0;
 }

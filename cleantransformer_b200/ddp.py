@@ -16,6 +16,10 @@ B200 design
     gradients have been enqueued (functional.grad_written) — the all-reduce kernel itself waits for
     the peers with flags in the same symmetric memory;
   * averaging (1/world) is fused into the all-reduce kernel;
+  * `comm="ce"` (not yet run on GPUs — written after the round's GPU budget was spent): same buckets, same
+    symmetric buffer, but the two NVLink legs of the two-shot all-reduce are peer copies on the DMA engines and the
+    only kernels are a one-CTA flag barrier and a local reduction (csrc/comm.cu), so the persistent GEMMs of the
+    backward pass keep every SM;
   * `comm="nccl"` keeps torch.distributed.all_reduce (NCCL on GPUs, gloo in the CPU tests) on the
     same bucket layout as the baseline/oracle.
 Parameters used more than once per step (tied embedding / lm_head) are reduced when the last of
@@ -81,8 +85,9 @@ class DistributedDataParallel(torch.nn.Module):
         self.device = params[0].device
         on_gpu = self.device.type == "cuda"
         self.comm = comm or os.environ.get("CT_DDP_COMM") or ("p2p" if on_gpu else "nccl")
-        if self.comm == "p2p" and not on_gpu:
-            raise RuntimeError("comm='p2p' needs CUDA parameters")
+        if self.comm in ("p2p", "ce") and not on_gpu:
+            raise RuntimeError("comm='%s' needs CUDA parameters" % self.comm)
+        self._peer_mem = self.comm in ("p2p", "ce")
         self.max_ctas = int(os.environ.get("CT_DDP_CTAS", max_ctas))
         self.final_ctas = int(os.environ.get("CT_DDP_FINAL_CTAS", 148))
         grad_buf = None
@@ -91,10 +96,10 @@ class DistributedDataParallel(torch.nn.Module):
         # exchanged at the end of backward (P2P path only)
         self._sparse = [p for p in params if getattr(p, "_ct_expected_writes", 1) == 2 and
                         getattr(p, "_ct_sparse_second_write", False) and p.dim() == 2 and p.shape[1] % 4 == 0]
-        if not (self.comm == "p2p" and self.world > 1) or os.environ.get("CT_DDP_SPARSE_TIED", "1") == "0":
+        if not (self._peer_mem and self.world > 1) or os.environ.get("CT_DDP_SPARSE_TIED", "1") == "0":
             self._sparse = []
         self._stage_cap = int(os.environ.get("CT_DDP_STAGE_TOKENS", 16384))
-        if self.comm == "p2p" and self.world > 1:
+        if self._peer_mem and self.world > 1:
             n_stage = 0
             if self._sparse:
                 hmax = max(p.shape[1] for p in self._sparse)
@@ -222,7 +227,12 @@ class DistributedDataParallel(torch.nn.Module):
         lo, hi, _ = self.buckets[bi]
         if os.environ.get("CT_DDP_SKIP_COMM"):  # timing experiments only: gradients stay local (WRONG results)
             return
-        if self.comm == "p2p":
+        if self.comm == "ce":
+            cur = torch.cuda.current_stream(self.device)
+            self._comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self._comm_stream):
+                self._allreduce_ce(lo, hi - lo)
+        elif self.comm == "p2p":
             cur = torch.cuda.current_stream(self.device)
             self._comm_stream.wait_stream(cur)
             with torch.cuda.stream(self._comm_stream):
@@ -240,6 +250,51 @@ class DistributedDataParallel(torch.nn.Module):
             else:
                 dist.all_reduce(seg, group=self.group)
                 seg.mul_(1.0 / self.world)
+
+    CE_PIECE = 1 << 24  # floats per piece (64 MiB): bounds the staging area for the 980 MiB tied-table bucket
+
+    @staticmethod
+    def ce_plan(count, world, rank, piece=None):
+        """[(piece offset, slice start in the piece, slice length, slice stride)] for the copy-engine all-reduce of
+        `count` floats: every piece is cut into `world` slices of `stride` floats (a multiple of 4), rank r owns
+        slice r (possibly short or empty at the ragged end)."""
+        piece = piece or DistributedDataParallel.CE_PIECE
+        plan = []
+        for p0 in range(0, count, piece):
+            n = min(piece, count - p0)
+            stride = ((n + 4 * world - 1) // (4 * world)) * 4
+            a = min(n, stride * rank)
+            b = min(n, stride * (rank + 1))
+            plan.append((p0, a, b - a, stride))
+        return plan
+
+    def _allreduce_ce(self, off, count):
+        """Two-shot all-reduce of floats [off, off+count) of the symmetric buffer with the NVLink legs on the DMA
+        engines. Runs on the communication stream (the caller set it current)."""
+        lib = _lib.load()
+        st = self._comm_stream.cuda_stream
+        W, r = self.world, self.rank
+        plan = self.ce_plan(count, W, r)
+        need = (W - 1) * max(p[3] for p in plan)
+        stage = getattr(self, "_ce_stage", None)
+        if stage is None or stage.numel() < need:
+            stage = self._ce_stage = torch.empty(need, dtype=torch.float32, device=self.device)
+        _lib.check(lib.ct_comm_barrier(st), "ct_comm_barrier")  # every rank's gradients of this bucket are final
+        for p0, a, n, stride in plan:
+            if n == 0:
+                continue
+            base = off + p0 + a
+            slot = 0
+            for q in range(W):
+                if q != r:
+                    _lib.check(lib.ct_comm_pull(q, base, stage.data_ptr() + 4 * slot * stride, n, st), "ct_comm_pull")
+                    slot += 1
+            _lib.check(lib.ct_comm_reduce_slices(base, stage.data_ptr(), stride, n, 1.0 / W, 0, st),
+                       "ct_comm_reduce_slices")
+            for q in range(W):
+                if q != r:
+                    _lib.check(lib.ct_comm_push(q, base, base, n, st), "ct_comm_push")
+        _lib.check(lib.ct_comm_barrier(st), "ct_comm_barrier")  # every slice has landed everywhere
 
     def _sparse_embedding_bwd(self, param, ids, dout, grad, padding_idx):
         """EmbeddingFn's scatter for a tied table (functional.EmbeddingFn.backward). `grad` already holds the

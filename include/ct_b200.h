@@ -296,6 +296,11 @@ int ct_scale_by_scalar(void* x, int dtype, int64_t n, const float* device_scalar
  *                    grad_offset (rows with id == padding_idx or out of range are skipped). Replaces
  *                    "scatter locally, then all-reduce the whole V x H table" — see csrc/comm.cu.
  *                    Collective: same order on all ranks, same stream discipline as ct_allreduce_bucket.
+ *   ct_comm_barrier / ct_comm_pull / ct_comm_push / ct_comm_reduce_slices  the same two-shot all-reduce with the
+ *                    NVLink legs on the DMA engines (cudaMemcpyAsync peer copies) instead of SMs: barrier, pull
+ *                    slice `rank` of every peer into caller-provided local staging, reduce the world slices in
+ *                    rank order (scale * sum) into the local buffer, push the result into every peer, barrier.
+ *                    Offsets / counts in floats; peers' staging slots in ascending rank order, `stride` apart.
  * The buffers are library-owned (freed by ct_comm_finalize); PyTorch sees them as non-owning tensors. */
 int ct_comm_init(int rank, int world, int device, size_t data_bytes, void** local_data,
                  void* data_handle_out, void* sig_handle_out);
@@ -303,6 +308,11 @@ int ct_comm_connect(const void* data_handles, const void* sig_handles);
 int ct_allreduce_bucket(int64_t offset, int64_t count, float scale, int mode, int max_ctas,
                         void* stream);
 int ct_broadcast(int64_t offset, int64_t count, int root, void* stream);
+int ct_comm_barrier(void* stream);
+int ct_comm_pull(int peer, int64_t peer_offset, void* dst_local, int64_t count, void* stream);
+int ct_comm_push(int peer, int64_t peer_offset, int64_t local_offset, int64_t count, void* stream);
+int ct_comm_reduce_slices(int64_t local_offset, const float* staged, int64_t stride, int64_t count, float scale,
+                          int max_ctas, void* stream);
 int ct_embedding_bwd_allranks(int64_t hdr_offset, int64_t rows_offset, int64_t ids_offset, int64_t grad_offset,
                               int64_t H, int64_t V, int64_t padding_idx, float scale, int max_ctas,
                               void* stream);

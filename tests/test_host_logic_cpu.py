@@ -199,3 +199,28 @@ def test_adamw_load_state_dict_lands_in_the_arena(monkeypatch):
             assert torch.all(a.param_view(p, a.exp_avg) == 0.25 * (i + 1))
             assert torch.all(a.param_view(p, a.exp_avg_sq) == 0.5 * (i + 1))
             assert int(st["step"]) == 3
+
+
+def test_copy_engine_allreduce_plan_tiles_every_piece():
+    """ddp.DistributedDataParallel.ce_plan: every piece of a bucket is cut into `world` 16-byte aligned slices that
+    tile it exactly (ragged ends short or empty), all ranks agree on the stride, staging fits (world-1) strides."""
+    from cleantransformer_b200.ddp import DistributedDataParallel as D
+    for count, world, piece in [(64, 2, None), (6400, 8, 1024), (1 << 20, 4, 1 << 18), (64 * 7, 3, 128), (192, 8, 64)]:
+        plans = [D.ce_plan(count, world, r, piece) for r in range(world)]
+        assert len({len(p) for p in plans}) == 1
+        covered = 0
+        for k in range(len(plans[0])):
+            p0 = plans[0][k][0]
+            stride = plans[0][k][3]
+            assert stride % 4 == 0 and all(pl[k][0] == p0 and pl[k][3] == stride for pl in plans)
+            n = min(piece or D.CE_PIECE, count - p0)
+            pos = 0
+            for r in range(world):
+                _, a, ln, _ = plans[r][k]
+                assert ln >= 0 and ln <= stride and a % 4 == 0 and ln % 4 == 0
+                if ln:
+                    assert a == pos
+                    pos += ln
+            assert pos == n
+            covered += n
+        assert covered == count
