@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay forward+backward from one CUDA graph (cleantransformer_b200.graphs; single GPU, "
+                         "experimental: not yet run on a GPU)")
     ap.add_argument("--comm", default=None, help="p2p (default), nccl (baseline collective) or ce (copy-engine transport, experimental)")
     return ap.parse_args()
 
@@ -342,6 +345,26 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         loss = step_resident()
+    if args.graph:
+        if world > 1:
+            raise SystemExit("--graph: single GPU only (peer-memory collectives cannot be replayed)")
+        from cleantransformer_b200.graphs import GraphedTrainStep
+        optimizer.zero_grad()
+        gstep = GraphedTrainStep(net, dict(input_ids=ids, attention_mask=mask, labels=labels))
+
+        def step_resident():  # noqa: F811
+            out = gstep(input_ids=ids, attention_mask=mask, labels=labels)
+            optimizer.step()
+            return out
+
+        def step_e2e():  # noqa: F811
+            a = ids_h.to(dev, non_blocking=True); m = mask_h.to(dev, non_blocking=True); l = lab_h.to(dev, non_blocking=True)
+            out = gstep(input_ids=a, attention_mask=m, labels=l)
+            optimizer.step()
+            return out.item()
+
+        for _ in range(3):
+            loss = step_resident()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ops.LAUNCHES[0]
