@@ -344,7 +344,10 @@ def main():
         return ms, out
 
     for _ in range(max(args.warmup, 3)):
+        l_before = ops.LAUNCHES[0]
         loss = step_resident()
+        launches_per_eager_step = ops.LAUNCHES[0] - l_before
+    step_eager = step_resident
     if args.graph:
         if world > 1:
             raise SystemExit("--graph: single GPU only (peer-memory collectives cannot be replayed)")
@@ -370,6 +373,8 @@ def main():
     l0 = ops.LAUNCHES[0]
     ms, loss = timed(step_resident, args.steps)
     launches = ops.LAUNCHES[0] - l0
+    if args.graph:  # the replayed graph launches the same kernels as the eager step it was captured from
+        launches = launches_per_eager_step * args.steps
     for _ in range(2):
         step_e2e()
     ms_e2e, loss_e2e = timed(step_e2e, args.steps)
@@ -380,7 +385,7 @@ def main():
     ops.GEMM_PROFILE = []
     barrier()
     for _ in range(2):
-        step_resident()
+        step_eager()  # (kernel by kernel also under --graph: the per-launch events need individual launches)
     torch.cuda.synchronize()
     prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
     flop = sum(2.0 * m * n * k for (m, n, k, _, _) in prof)
@@ -403,7 +408,8 @@ def main():
                        "model": "bloom-560m", "global_batch": B * world, "seq_len": S, "layers": args.layers,
                        "parallelism": "dp%d" % world, "precision": "fp32 master params/residual/LN/softmax/loss, bf16 tensor-core operands",
                        "l2": "inputs larger than L2 (1.1 GB bf16 weights + >3 GB activations per step vs 126 MB L2); no flush",
-                       "ddp_comm": (args.comm or "p2p") if world > 1 else None},
+                       "ddp_comm": (args.comm or "p2p") if world > 1 else None,
+                       "cuda_graph": bool(args.graph)},
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": 3 * B * S * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
