@@ -38,6 +38,7 @@ class GemmArgs(ctypes.Structure):
         ("actgrad_act", ctypes.c_int32), ("ldg", c_i64),
         ("residual", c_void_p), ("res_dtype", ctypes.c_int32), ("ldr", c_i64),
         ("impl", ctypes.c_int32),
+        ("row_stats", c_void_p),
     ]
 
 
@@ -128,6 +129,8 @@ SIGNATURES = {
     "ct_embedding_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p]),
     "ct_cross_entropy_fwd": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p, c_i64, c_void_p,
                                      c_void_p, c_i64, c_i64, c_i64, c_int, c_i64, c_void_p]),
+    "ct_cross_entropy_fwd_stats": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
+                                           c_i64, c_i64, c_i64, c_i64, c_int, c_i64, c_void_p]),
     "ct_scale_by_scalar": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p]),
     "ct_comm_init": (c_int, [c_int, c_int, c_int, ctypes.c_size_t, ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
     "ct_comm_connect": (c_int, [c_void_p, c_void_p]),

@@ -45,6 +45,7 @@ struct EpiParams {
   int vec_ok;     // all pointers 16B aligned and leading dims multiples of 8 elements
   int atomic_out; // split-K: C += t via red.global.add.f32 (C f32, linear epilogue only)
   int res_coalesced;  // EPIK_RES_F32: residual fetched (and added) in the coalesced write-out pattern
+  float* row_stats;   // EPIK_BF16_STATS: [2 * ceil(N/256)][M] float2 (max2, sum2) softmax statistics of the stored row
 };
 
 __device__ __forceinline__ float ld_elem(const void* p, int dt, int64_t i) {
@@ -366,7 +367,8 @@ __device__ __forceinline__ void epi_block32(const EpiParams& e, int m_base, int 
 // bias + GELU + saved pre-activation; FFN2 dgrad: x GELU'(pre)). The hot Bloom / GPT-2 combinations get
 // compile-time variants: packed f32x2 math, no register copies (the TMEM loads ping-pong between two
 // register sets), the per-element operand (residual / saved pre-activation) prefetched one chunk ahead.
-enum : int { EPIK_GENERIC = 0, EPIK_BF16 = 1, EPIK_GELU_PRE = 2, EPIK_RES_F32 = 3, EPIK_ACTGRAD = 4 };
+enum : int { EPIK_GENERIC = 0, EPIK_BF16 = 1, EPIK_GELU_PRE = 2, EPIK_RES_F32 = 3, EPIK_ACTGRAD = 4,
+              EPIK_BF16_STATS = 5 /* LM head: bf16 logits + per (row, 128-column half tile) softmax statistics */ };
 
 __device__ __forceinline__ float2 gelu_tanh2(float2 x) {
   const float2 x2 = __fmul2_rn(x, x);
@@ -449,10 +451,40 @@ __device__ __forceinline__ void epi_fast_aux_load(const EpiParams& e, int m, int
   }
 }
 
+// Running softmax statistics (log2 domain: max2 = max * log2e, sum2 = sum 2^(v * log2e - max2)) of the bf16-ROUNDED
+// values of one row chunk — exactly the numbers the cross-entropy kernel would read back from the stored logits.
+__device__ __forceinline__ void row_stats_update(const float (&t)[32], float2& ms) {
+  constexpr float L2E = 1.4426950408889634f;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float2 f = unpack_bf16x2(pack_bf16x2(t[2 * j], t[2 * j + 1]));
+    v[2 * j] = f.x; v[2 * j + 1] = f.y;
+  }
+  float mx = v[0];
+#pragma unroll
+  for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+  mx *= L2E;
+  if (mx > ms.x) {
+    float sc;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sc) : "f"(ms.x - mx));
+    ms.y *= sc;  // (-inf - mx) -> 0 on the first chunk
+    ms.x = mx;
+  }
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float ex;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(v[j], L2E, -ms.x)));
+    acc += ex;
+  }
+  ms.y += acc;
+}
+
 template <int EPIK>
 __device__ __forceinline__ void epi_fast_chunk(const EpiParams& e, int m_base, int lane, int n0, int n_in_tile,
                                                const uint32_t (&r)[32], const uint4 (&x)[8], uint32_t stage,
-                                               uint32_t bias_s) {
+                                               uint32_t bias_s, float2* ms = nullptr) {
   float t[32];
   if (e.bias) {  // CTA-uniform
 #pragma unroll
@@ -470,6 +502,7 @@ __device__ __forceinline__ void epi_fast_chunk(const EpiParams& e, int m_base, i
 #pragma unroll
     for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(r[j]);
   }
+  if constexpr (EPIK == EPIK_BF16_STATS) row_stats_update(t, *ms);
   if constexpr (EPIK == EPIK_GELU_PRE) {
     if (e.act == ACT_GELU_TANH_SAVE_GRAD) {  // CTA-uniform: the backward wants gelu'(t), one tanh serves both
       float g[32];
@@ -980,6 +1013,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
         uint4 xa[8], xb[8];
         const int m = m_base + lane;
         const int nt0 = n_blk * BN;
+        float2 ms = make_float2(-INFINITY, 0.f);  // EPIK_BF16_STATS: this thread's row over its four chunks
         tmem_ld_32x32(t_row + hf * 32, ra);
         if (nt0 + hf * 32 < e.N) epi_fast_aux_load<EPIK>(e, m, nt0 + hf * 32, xa);
 #pragma unroll
@@ -992,7 +1026,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
           }
           if (nt0 + c * 32 < e.N)  // warp-uniform (N % 32 == 0 on this path)
             epi_fast_chunk<EPIK>(e, m_base, lane, nt0 + c * 32, c * 32, (k & 1) ? rb : ra, (k & 1) ? xb : xa, stage,
-                                 bias_s);
+                                 bias_s, &ms);
+        }
+        if constexpr (EPIK == EPIK_BF16_STATS) {
+          // slot (2 * tile + hf) of row m; [slot][row] layout: a warp writes 32 consecutive rows (256 contiguous bytes).
+          // A half tile entirely beyond N keeps (-inf, 0), which the merge in the loss kernel ignores.
+          if (m < e.M)
+            reinterpret_cast<float2*>(e.row_stats)[(int64_t)(2 * n_blk + hf) * e.M + m] = ms;
         }
       }
       tc_fence_before();
@@ -1120,7 +1160,7 @@ static int pick_epi_kind(const ct_gemm_args& a, const EpiParams& e) {
   if (option(OPT_GEMM_EPI_IMPL) == 1) return EPIK_GENERIC;
   if (!e.vec_ok || e.atomic_out || a.alpha != 1.f || a.beta != 0.f || (a.N % 32) != 0) return EPIK_GENERIC;
   const bool plain = a.act == ACT_NONE && !a.preact && !a.actgrad_src && !a.residual;
-  if (plain && a.c_dtype == DT_BF16 && a.ab_dtype == DT_BF16) return EPIK_BF16;
+  if (plain && a.c_dtype == DT_BF16 && a.ab_dtype == DT_BF16) return e.row_stats ? EPIK_BF16_STATS : EPIK_BF16;
   if ((a.act == ACT_GELU_TANH || a.act == ACT_GELU_TANH_SAVE_GRAD) && a.preact && a.preact_dtype == DT_BF16 &&
       a.c_dtype == DT_BF16 && !a.actgrad_src &&
       !a.residual)
@@ -1162,6 +1202,7 @@ static int launch_tc_2cta(const ct_gemm_args& a, const EpiParams& e, int split_k
   if (work < pairs) pairs = (int)work;
   switch (split_k == 1 ? pick_epi_kind(a, e) : EPIK_GENERIC) {
     case EPIK_BF16: return launch_2cta_kind<EPIK_BF16>(tmA, tmB, p, e, pairs, st);
+    case EPIK_BF16_STATS: return launch_2cta_kind<EPIK_BF16_STATS>(tmA, tmB, p, e, pairs, st);
     case EPIK_GELU_PRE: return launch_2cta_kind<EPIK_GELU_PRE>(tmA, tmB, p, e, pairs, st);
     case EPIK_RES_F32: return launch_2cta_kind<EPIK_RES_F32>(tmA, tmB, p, e, pairs, st);
     case EPIK_ACTGRAD: return launch_2cta_kind<EPIK_ACTGRAD>(tmA, tmB, p, e, pairs, st);
@@ -1206,6 +1247,7 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
   e.residual = a.residual; e.res_dtype = a.res_dtype; e.ldr = a.ldr;
   e.atomic_out = 0;
   e.res_coalesced = option(OPT_GEMM_EPI_IMPL) != 2;  // GEMM_EPI_IMPL 2 = row-per-thread residual loads (first form)
+  e.row_stats = a.row_stats;
   e.vec_ok = al16(a.C) && (a.ldc % 8 == 0) && (!a.bias || al16(a.bias)) &&
              (!a.preact || (al16(a.preact) && a.ldp % 8 == 0)) &&
              (!a.actgrad_src || (al16(a.actgrad_src) && a.ldg % 8 == 0)) &&
@@ -1226,6 +1268,7 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
     use_tc = tma_ok && ((int64_t)a.M * a.N * a.K >= (1 << 18));
   }
 
+  CT_REQUIRE(use_tc || !a.row_stats, CT_ERR_UNSUPPORTED, "ct_gemm: row_stats needs the tcgen05 2-CTA kernel");
   if (!use_tc) {
     if (a.K == 0) {
       // degenerate: C = epilogue(0)
@@ -1257,6 +1300,10 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
   }
   const int auto_2cta = option(OPT_GEMM_2CTA);
   const bool use_2cta = a.impl == 3 || (a.impl == 0 && auto_2cta && a.M >= 512 && a.N >= 256);
+  // row statistics exist only in one compile-time epilogue of the 2-CTA kernel: refuse rather than skip them silently
+  CT_REQUIRE(!a.row_stats || (use_2cta && pick_epi_kind(a, e) == EPIK_BF16_STATS), CT_ERR_UNSUPPORTED,
+             "ct_gemm: row_stats needs the 2-CTA kernel's plain bf16 epilogue (M >= 512, N >= 256, N %% 32 == 0, "
+             "16-byte aligned, no bias-free restriction, alpha 1, beta 0)");
   if (use_2cta) {
     // recompute the split for 256 x 256 tiles
     const int t2 = ((a.M + 255) / 256) * ((a.N + 255) / 256);

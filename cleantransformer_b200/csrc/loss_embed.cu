@@ -514,6 +514,90 @@ __global__ void __launch_bounds__(CE2_THREADS, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// cross entropy from statistics the LM-head GEMM already produced (ct_gemm_args.row_stats): ONE streaming pass
+// ---------------------------------------------------------------------------------------------
+// The epilogue of the logits GEMM sees every logit in registers; it leaves, per row, 2*ceil(V/256) partial
+// (max2, sum2) pairs of the bf16-rounded values (128 MB for Bloom-560M's 8192 x 250 880 logits, 3 % of the logits
+// themselves). Merging them gives the row's log-sum-exp without reading the row, so this kernel is a single pass:
+// read logit, write (softmax - onehot) / count. SURVEY §8 (f) N1, first half.
+constexpr int CES_THREADS = 512;
+
+__global__ void __launch_bounds__(CES_THREADS)
+    ce_fwd_stats_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, const long long* __restrict__ labels,
+                        __nv_bfloat16* __restrict__ dlogits, int64_t ldd, float* __restrict__ row_loss,
+                        const float* __restrict__ stats, const float2* __restrict__ row_stats, int n_slots,
+                        int64_t rows, int64_t V, int64_t S, int shift, long long ignore_index) {
+  __shared__ float red[2 * (CES_THREADS >> 5)];
+  const float inv_count = 1.f / fmaxf(stats[0], 1.f);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t nvec = V >> 3;
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const long long tgt = ce_target(labels, r, S, shift);
+    const bool valid = (tgt != ignore_index && tgt >= 0 && tgt < V);
+    const uint4* x8 = reinterpret_cast<const uint4*>(logits + r * ld);
+    uint4* d8 = dlogits ? reinterpret_cast<uint4*>(dlogits + r * ldd) : nullptr;
+    if (!valid) {
+      if (row_loss && tid == 0) row_loss[r] = 0.f;
+      if (d8)
+        for (int64_t c = tid; c < nvec; c += CES_THREADS) __stcs(d8 + c, make_uint4(0u, 0u, 0u, 0u));
+      continue;
+    }
+    float m = -INFINITY, s = 0.f;
+    for (int k = tid; k < n_slots; k += CES_THREADS) {
+      const float2 q = __ldg(row_stats + (int64_t)k * rows + r);
+      ms_merge2(m, s, q.x, q.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      ms_merge2(m, s, m2, s2);
+    }
+    if (lane == 0) { red[2 * w] = m; red[2 * w + 1] = s; }
+    __syncthreads();
+    m = lane < (CES_THREADS >> 5) ? red[2 * lane] : -INFINITY;
+    s = lane < (CES_THREADS >> 5) ? red[2 * lane + 1] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      ms_merge2(m, s, m2, s2);
+    }
+    __syncthreads();  // red is rewritten by the next row
+    const float lse2 = m + log2f(s);
+    if (row_loss && tid == 0) row_loss[r] = lse2 * LN2 - __bfloat162float(logits[r * ld + tgt]);
+    if (d8) {
+      for (int64_t c0 = tid; c0 < nvec; c0 += CES_THREADS * CE2_UNROLL) {
+        uint4 u[CE2_UNROLL];
+#pragma unroll
+        for (int k = 0; k < CE2_UNROLL; ++k) {
+          const int64_t c = c0 + (int64_t)k * CES_THREADS;
+          if (c < nvec) u[k] = __ldcs(x8 + c);
+        }
+#pragma unroll
+        for (int k = 0; k < CE2_UNROLL; ++k) {
+          const int64_t c = c0 + (int64_t)k * CES_THREADS;
+          if (c < nvec) {
+            float v[8];
+            ce_unpack8(u[k], v);
+            const int64_t e0 = c << 3;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float pg = ce_ex2(fmaf(v[i], LOG2E, -lse2));
+              if (e0 + i == tgt) pg -= 1.f;
+              v[i] = pg * inv_count;
+            }
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+            __stcs(d8 + c, o);
+          }
+        }
+      }
+    }
+  }
+}
+
 // loss = sum(row_loss) / count   (single block, deterministic order)
 __global__ void __launch_bounds__(1024)
     ce_finalize_kernel(const float* __restrict__ row_loss, int64_t rows, const float* __restrict__ stats,
@@ -626,6 +710,35 @@ extern "C" int ct_cross_entropy_fwd(const void* logits, int dtype, int64_t ld, c
         shift, (long long)ignore_index);
   CT_LAUNCH_OK();
   }
+  ce_finalize_kernel<<<1, 1024, 0, st>>>(row_loss, rows, stats, loss);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+// bf16 logits whose per-row softmax statistics came out of the producing GEMM (ct_gemm_args.row_stats): same contract
+// as ct_cross_entropy_fwd otherwise. n_slots = 2 * ceil(V / 256).
+extern "C" int ct_cross_entropy_fwd_stats(const void* logits, int64_t ld, const int64_t* labels, void* dlogits,
+                                          int64_t ldd, float* loss, float* workspace, const float* row_stats,
+                                          int64_t n_slots, int64_t rows, int64_t V, int64_t S, int shift,
+                                          int64_t ignore_index, void* stream) {
+  CT_REQUIRE(logits && labels && loss && workspace && row_stats, CT_ERR_BAD_ARG,
+             "ct_cross_entropy_fwd_stats: null pointer");
+  CT_REQUIRE(rows > 0 && V > 0 && (V & 7) == 0 && (ld & 7) == 0 && (!dlogits || (ldd & 7) == 0) &&
+                 ((uintptr_t)logits & 15) == 0 && ((uintptr_t)dlogits & 15) == 0 && ((uintptr_t)row_stats & 7) == 0 &&
+                 n_slots == 2 * ((V + 255) / 256) && (!shift || (S > 0 && rows % S == 0)),
+             CT_ERR_BAD_ARG, "ct_cross_entropy_fwd_stats: bad shape / alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* stats = workspace;
+  float* row_loss = workspace + 4;
+  CT_CUDA_OK(cudaMemsetAsync(stats, 0, 16, st));
+  ce_count_kernel<<<64, 256, 0, st>>>((const long long*)labels, rows, S, shift, (long long)ignore_index, V, stats);
+  CT_LAUNCH_OK();
+  int64_t grid = (int64_t)sm_count() * 4;
+  if (grid > rows) grid = rows;
+  ce_fwd_stats_kernel<<<(unsigned)grid, CES_THREADS, 0, st>>>(
+      (const __nv_bfloat16*)logits, ld, (const long long*)labels, (__nv_bfloat16*)dlogits, ldd, row_loss, stats,
+      (const float2*)row_stats, (int)n_slots, rows, V, S, shift, (long long)ignore_index);
+  CT_LAUNCH_OK();
   ce_finalize_kernel<<<1, 1024, 0, st>>>(row_loss, rows, stats, loss);
   CT_LAUNCH_OK();
   return 0;

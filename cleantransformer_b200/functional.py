@@ -347,6 +347,55 @@ def lm_loss(logits, labels, shift=True):
     return LMLossFn.apply(logits, labels, shift)
 
 
+FUSED_LM_STATS = os.environ.get("CT_FUSED_LM_STATS", "0") != "0"
+
+
+class LMHeadLossFn(torch.autograd.Function):
+    """lm_head + shifted cross entropy as one node (modeling_bloom.py:220-230): the logits GEMM leaves the softmax
+    statistics of every row next to the logits, so the loss kernel is a single streaming pass (SURVEY §8 f, N1, first
+    half). Returns (loss, logits); the logits are an output for the caller's tuple only (non-differentiable here —
+    the node back-propagates the loss). Opt-in (CT_FUSED_LM_STATS=1): not yet run on a GPU."""
+
+    @staticmethod
+    def forward(ctx, hidden, weight, labels, shift):
+        cd = compute_dtype()
+        B, S, H = hidden.shape
+        x2 = _low(_as2d(hidden.detach()), cd)
+        w16 = shadow(weight, cd)
+        logits, stats = ops.lm_head_logits_with_stats(x2, w16)
+        need = hidden.requires_grad or weight.requires_grad
+        loss, dl = ops.cross_entropy_fwd_stats(logits, labels.reshape(-1), stats, S=S, shift=shift, want_dlogits=need)
+        ctx.save_for_backward(x2, dl)
+        ctx.weight = weight
+        ctx.x_shape, ctx.x_dtype, ctx.x_req = hidden.shape, hidden.dtype, hidden.requires_grad
+        logits = logits.view(B, S, -1)
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits):
+        x2, dl = ctx.saved_tensors
+        weight = ctx.weight
+        ops.scale_by_scalar(dl, dloss.contiguous().float())
+        if weight.requires_grad:
+            gw, acc = grad_buffer(weight)
+            ops.linear_wgrad(dl, x2, gw, None, accumulate=acc)
+            grad_written(weight)
+        dx = None
+        if ctx.x_req:
+            dx = ops.linear_dgrad(dl, shadow(weight, x2.dtype), out_dtype=ctx.x_dtype).view(ctx.x_shape)
+        return dx, None, None, None
+
+
+def lm_head_loss(hidden, weight, labels, shift=True):
+    """(loss, logits) of the tied LM head; the fused-statistics node when it is enabled and the shape allows it."""
+    B, S, H = hidden.shape
+    if FUSED_LM_STATS and compute_dtype() == torch.bfloat16 and ops.lm_head_stats_ok(B * S, weight.shape[0]):
+        return LMHeadLossFn.apply(hidden, weight, labels, shift)
+    logits = linear(hidden, weight)
+    return lm_loss(logits, labels, shift=shift), logits
+
+
 def default_scale(head_dim):
     return 1.0 / math.sqrt(head_dim)
 

@@ -252,11 +252,11 @@ class BloomForCausalLM(torch.nn.Module, GenerationMixin):
 
     def forward(self, input_ids, attention_mask=None, head_mask=None, k_v_pasts=None, labels=None, **kwargs):
         hidden_states, k_v_pasts = self.bloom(input_ids, attention_mask, head_mask, k_v_pasts)
-        lm_logits = F.linear(hidden_states, self.lm_head.weight)
-        outputs = (lm_logits, hidden_states)
         if labels is not None:
-            outputs = (F.lm_loss(lm_logits, labels, shift=True),) + outputs
-        return outputs, k_v_pasts
+            loss, lm_logits = F.lm_head_loss(hidden_states, self.lm_head.weight, labels, shift=True)
+            return (loss, lm_logits, hidden_states), k_v_pasts
+        lm_logits = F.linear(hidden_states, self.lm_head.weight)
+        return (lm_logits, hidden_states), k_v_pasts
 
 
 class GeLUFunction(torch.autograd.Function):

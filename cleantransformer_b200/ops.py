@@ -218,7 +218,7 @@ def act_bwd(dy, x, act, out_dtype=None):
 # ------------------------------------------------------------------------------------------------
 def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, alpha=1.0,
          beta=0.0, bias=None, act=ACT_NONE, preact=None, actgrad_src=None, actgrad_act=ACT_NONE,
-         residual=None, impl=0):
+         residual=None, impl=0, row_stats=None):
     """C[M,N] = epilogue(alpha * A(m,k) B(n,k)); A, B are 2-D row-major storage tensors:
     K-major operand -> [rows=M|N, K]; MN-major operand -> [rows=K, M|N]."""
     _req_cuda(A, B)
@@ -245,6 +245,7 @@ def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat
     if residual is not None:
         g.residual, g.res_dtype, g.ldr = residual.data_ptr(), dt(residual), residual.stride(0)
     g.impl = impl
+    g.row_stats = ptr(row_stats)
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -265,6 +266,21 @@ def linear_fwd(x2d, w, bias=None, act=ACT_NONE, residual=None, out_dtype=torch.b
     y = gemm(x2d, w, M, N, K, a_mn=False, b_mn=bool(w_in_out), out_dtype=out_dtype, bias=bias,
              act=act, preact=pre, residual=residual, impl=impl)
     return y, pre
+
+
+def lm_head_stats_ok(M, V):
+    """Shapes for which the logits GEMM can emit per-row softmax statistics (include/ct_b200.h: row_stats)."""
+    return M >= 512 and V >= 256 and V % 32 == 0
+
+
+def lm_head_logits_with_stats(x2d, w):
+    """logits[M,V] = x @ W^T in x's dtype (bf16) plus the per-row softmax statistics [2*ceil(V/256), M, 2] f32 that
+    cross_entropy_fwd_stats consumes (modeling_bloom.py:220-230 without re-reading the logits for the log-sum-exp)."""
+    M, K = x2d.shape
+    V = w.shape[0]
+    stats = torch.empty((2 * ((V + 255) // 256), M, 2), dtype=torch.float32, device=x2d.device)
+    y = gemm(x2d, w, M, V, K, out_dtype=x2d.dtype, row_stats=stats)
+    return y, stats
 
 
 def linear_dgrad(dy2d, w, out_dtype=torch.bfloat16, actgrad_src=None, actgrad_act=ACT_NONE,
@@ -415,6 +431,21 @@ def cross_entropy_fwd(logits2d, labels, S=0, shift=False, ignore_index=-100, wan
                                            ptr(dl), dl.stride(0) if dl is not None else 0, ptr(loss),
                                            ptr(ws), rows, V, S, 1 if shift else 0, ignore_index,
                                            stream()), "ct_cross_entropy_fwd")
+    return loss, dl
+
+
+def cross_entropy_fwd_stats(logits2d, labels, row_stats, S=0, shift=False, ignore_index=-100, want_dlogits=True):
+    """cross_entropy_fwd for bf16 logits that came with their row statistics (lm_head_logits_with_stats)."""
+    _req_cuda(logits2d, labels, row_stats)
+    rows, V = logits2d.shape
+    labels = labels.contiguous()
+    dl = torch.empty_like(logits2d) if want_dlogits else None
+    loss = torch.empty((), dtype=torch.float32, device=logits2d.device)
+    ws = torch.empty(rows + 4, dtype=torch.float32, device=logits2d.device)
+    _ck(_lib.load().ct_cross_entropy_fwd_stats(ptr(logits2d), logits2d.stride(0), ptr(labels), ptr(dl),
+                                                 dl.stride(0) if dl is not None else 0, ptr(loss), ptr(ws),
+                                                 ptr(row_stats), row_stats.shape[0], rows, V, S, 1 if shift else 0,
+                                                 ignore_index, stream()), "ct_cross_entropy_fwd_stats")
     return loss, dl
 
 

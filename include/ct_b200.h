@@ -167,6 +167,11 @@ typedef struct {
   int64_t ldr;
   int32_t impl; /* 0 auto, 1 force 1-CTA tcgen05, 2 force the SIMT kernel (small/unaligned shapes),
                    3 force the 2-CTA (cta_group::2, 256x256 tile) tcgen05 kernel */
+  float* row_stats; /* nullable. LM head (modeling_bloom.py:220-230): softmax statistics of every stored bf16 row,
+                       [2*ceil(N/256)][M] float2 = (max * log2e, sum of 2^(v*log2e - max*log2e)) per (slot, row), a
+                       slot being the four 32-column chunks of one parity of a 256-column tile; a slot without any
+                       column holds (-inf, 0). Consumed by ct_cross_entropy_fwd_stats. Plain bf16 epilogue of the
+                       2-CTA kernel only (CT_ERR_UNSUPPORTED otherwise). */
 } ct_gemm_args;
 int ct_gemm(const ct_gemm_args* args, void* stream);
 
@@ -271,6 +276,11 @@ int ct_embedding_bwd(const int64_t* ids, const float* dout, float* dweight, int6
 int ct_cross_entropy_fwd(const void* logits, int dtype, int64_t ld, const int64_t* labels,
                          void* dlogits, int64_t ldd, float* loss, float* workspace, int64_t rows,
                          int64_t V, int64_t S, int shift, int64_t ignore_index, void* stream);
+/* Same contract for bf16 logits whose per-row softmax statistics were produced by the logits GEMM itself
+ * (ct_gemm_args.row_stats, n_slots = 2*ceil(V/256)): one streaming pass, the rows are not read for the log-sum-exp. */
+int ct_cross_entropy_fwd_stats(const void* logits, int64_t ld, const int64_t* labels, void* dlogits, int64_t ldd,
+                               float* loss, float* workspace, const float* row_stats, int64_t n_slots,
+                               int64_t rows, int64_t V, int64_t S, int shift, int64_t ignore_index, void* stream);
 /* x *= *device_scalar (no-op when the scalar is 1.0): applies an upstream dloss to dlogits. */
 int ct_scale_by_scalar(void* x, int dtype, int64_t n, const float* device_scalar, void* stream);
 
