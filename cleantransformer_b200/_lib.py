@@ -111,6 +111,8 @@ SIGNATURES = {
                                c_void_p]),
     "ct_sgd_step": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float,
                             c_float, c_int, c_void_p]),
+    "ct_sgd_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,
+                             c_int, c_void_p]),
     "ct_cast": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_void_p]),
     "ct_colsum": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_int, c_i64, c_i64, c_void_p]),
     "ct_act_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_i64, c_void_p]),

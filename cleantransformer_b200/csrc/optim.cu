@@ -251,3 +251,17 @@ extern "C" int ct_sgd_step(float* p, float* g, float* buf, int64_t n, float lr, 
   CT_LAUNCH_OK();
   return 0;
 }
+
+// Same arithmetic over `ntensors` separate tensors (host arrays of device pointers; `buf` entries may be NULL when
+// momentum == 0): one launch of the flat kernel per tensor.
+extern "C" int ct_sgd_multi(int ntensors, float* const* p, float* const* g, float* const* buf, const int64_t* sizes,
+                            float lr, float momentum, float dampening, float weight_decay, int first_step,
+                            void* stream) {
+  CT_REQUIRE(ntensors >= 0 && (ntensors == 0 || (p && g && sizes)), CT_ERR_BAD_ARG, "ct_sgd_multi: null table");
+  for (int i = 0; i < ntensors; ++i) {
+    const int rc = ct_sgd_step(p[i], g[i], buf ? buf[i] : nullptr, sizes[i], lr, momentum, dampening, weight_decay,
+                               first_step, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}

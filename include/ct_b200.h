@@ -118,6 +118,9 @@ int ct_adamw_multi(int ntensors, float* const* p, float* const* g, float* const*
  * g = buf; p -= lr*g. `buf` may be NULL when momentum == 0. g is rewritten like the reference. */
 int ct_sgd_step(float* p, float* g, float* buf, int64_t n, float lr, float momentum,
                 float dampening, float weight_decay, int first_step, void* stream);
+/* Same arithmetic over `ntensors` separate tensors (host arrays of device pointers; buf may be NULL). */
+int ct_sgd_multi(int ntensors, float* const* p, float* const* g, float* const* buf, const int64_t* sizes,
+                 float lr, float momentum, float dampening, float weight_decay, int first_step, void* stream);
 
 /* ---- elementwise helpers --------------------------------------------------------------------- */
 /* dst[i] = (dst_dtype) src[i]  (autocast's parameter/activation casts) */
