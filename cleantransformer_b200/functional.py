@@ -390,7 +390,7 @@ class LMHeadLossFn(torch.autograd.Function):
 def lm_head_loss(hidden, weight, labels, shift=True):
     """(loss, logits) of the tied LM head; the fused-statistics node when it is enabled and the shape allows it."""
     B, S, H = hidden.shape
-    if FUSED_LM_STATS and compute_dtype() == torch.bfloat16 and ops.lm_head_stats_ok(B * S, weight.shape[0]):
+    if FUSED_LM_STATS and ops.lm_head_stats_ok(B * S, weight.shape[0], compute_dtype()):
         return LMHeadLossFn.apply(hidden, weight, labels, shift)
     logits = linear(hidden, weight)
     return lm_loss(logits, labels, shift=shift), logits

@@ -268,9 +268,10 @@ def linear_fwd(x2d, w, bias=None, act=ACT_NONE, residual=None, out_dtype=torch.b
     return y, pre
 
 
-def lm_head_stats_ok(M, V):
-    """Shapes for which the logits GEMM can emit per-row softmax statistics (include/ct_b200.h: row_stats)."""
-    return M >= 512 and V >= 256 and V % 32 == 0
+def lm_head_stats_ok(M, V, dtype=torch.bfloat16):
+    """Shapes / operand type for which the logits GEMM can emit per-row softmax statistics (include/ct_b200.h:
+    row_stats)."""
+    return dtype == torch.bfloat16 and M >= 512 and V >= 256 and V % 32 == 0
 
 
 def lm_head_logits_with_stats(x2d, w):
