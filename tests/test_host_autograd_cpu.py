@@ -129,3 +129,59 @@ def test_bloom_ddp_world2_gloo_reduces_every_gradient_once():
     for n in r0:
         assert torch.allclose(r0[n], r1[n]), n                  # same reduced gradient on both ranks
         assert rel_err(r0[n], (l0[n] + l1[n]) / 2) < 1e-5, n      # = the mean of the local ones (tied table included)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The other mirrors, same idea: GPT (Conv1D weights [in,out], blocked QKV split, post-LN 'gpt' and pre-LN 'gpt2'
+# wiring, greedy generation with the KV cache), BERT (separate q/k/v Linears, additive -1e4 mask, pooler), the
+# generic TransformerBlock of transformer.py.
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("version", ["gpt", "gpt2"])
+def test_gpt_host_logic_vs_reference_golden(golden, version, monkeypatch):
+    from cleantransformer_b200 import ops
+    from cleantransformer_b200.models import modeling_gpt as mg
+    g = golden("gpt_tiny")
+    c, cfg = g[version], g["cfg"]
+    with mock_ops.patched():
+        # generation grows the cache through ops.kv_cache_append (in-place CUDA append): concat stands in for it
+        monkeypatch.setattr(ops, "kv_cache_append", lambda past, new: new if past is None else torch.cat([past, new], 2))
+        model = mg.GPTLMHeadModel(mg.GPTConfig(**cfg), version=version)
+        model.load_state_dict(c["sd"], strict=True)
+        model._tie_weights()
+        model.eval()
+        with torch.no_grad():
+            (logits, hidden), _ = model(c["ids"], attention_mask=c["mask"])
+        assert rel_err(logits, c["logits"]) < 2e-4 and rel_err(hidden, c["hidden"]) < 2e-4
+        gen = model.generate(c["ids"], attention_mask=c["mask"],
+                             generation_configs={"beam_size": 1, "do_sample": False, "max_gen_len": 6,
+                                                 "end_ids": None, "pad_id": 0, "no_repeat_ngram_size": 0})
+        assert torch.equal(gen, c["generated"])
+        blk = model.gpt.blocks[0]
+        x = c["blk_x"].clone().requires_grad_(True)
+        model.zero_grad()
+        y, _ = blk(x)
+        y.backward(c["blk_dy"])
+    assert rel_err(y, c["blk_y"]) < 2e-4 and rel_err(x.grad, c["blk_dx"]) < 1e-3
+    for name, p in blk.named_parameters():
+        assert rel_err(p.grad, c["blk_grads"][name]) < 1e-3, name
+
+
+def test_bert_and_generic_block_host_logic_vs_reference_golden(golden):
+    from cleantransformer_b200 import transformer as T
+    from cleantransformer_b200.models import modeling_bert as mbert
+    g = golden("bert_tiny")
+    with mock_ops.patched():
+        model = mbert.BertForSequenceClassification(mbert.BertConfig(**dict(g["cfg"]))).eval()
+        model.load_state_dict(g["sd"], strict=True)
+        with torch.no_grad():
+            logits = model(g["ids"], g["mask"], g["seg"], g["pos"])
+            hidden, pooled = model.bert(g["ids"], g["mask"], g["seg"], g["pos"])
+        assert rel_err(hidden, g["hidden"]) < 2e-4 and rel_err(pooled, g["pooled"]) < 2e-4
+        assert rel_err(logits, g["logits"]) < 2e-4
+        gb = golden("generic_block")
+        blk = T.TransformerBlock(T.ExampleConfig()).eval()
+        blk.load_state_dict(gb["sd"], strict=True)
+        with torch.no_grad():
+            y = blk(gb["x"])
+            a = blk.attention(gb["x"], (1.0 - gb["mask"][:, None, None, :]) * -10000.0)
+    assert rel_err(y, gb["y"]) < 2e-4 and rel_err(a, gb["att_masked"]) < 2e-4
