@@ -741,16 +741,19 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
             mbar_wait(p0_free, (j - 1) & 1);
             tc_fence_after();
           }
+          CT_DBG_STAMP(2048 + 16 * j + 5);  // (debug build) 4 -> 5: lazy rescale + wait for panel 0
           float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
           fa2_exp_store<HAS_KB, BF16>(r0, 0, m_new, p.sl2, p_row, sw, acc0, acc1);
           fa2_exp_store<HAS_KB, BF16>(r1, 1, m_new, p.sl2, p_row, sw, acc0, acc1);
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(p_ready);  // panel 0: its MMAs run under the rest of this tile
+          CT_DBG_STAMP(2048 + 16 * j + 6);  // 5 -> 6: exp + store of panel 0
           if (j > 0) {  // all of P(j-1) V(j-1) retired: panel 1 may be overwritten
             mbar_wait(o_full, (j - 1) & 1);
             tc_fence_after();
           }
+          CT_DBG_STAMP(2048 + 16 * j + 7);  // 6 -> 7: wait for panel 1
           fa2_exp_store<HAS_KB, BF16>(r2, 2, m_new, p.sl2, p_row, sw, acc0, acc1);
           fa2_exp_store<HAS_KB, BF16>(r3, 3, m_new, p.sl2, p_row, sw, acc0, acc1);
           lt = (acc0.x + acc0.y) + (acc1.x + acc1.y);
@@ -758,6 +761,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(p_half1);
+          CT_DBG_STAMP(2048 + 16 * j + 8);  // 7 -> 8: exp + store of panel 1
           continue;  // (the tail below belongs to the exact-maximum paths)
         }
         m_new = fmaxf(m, mt);
