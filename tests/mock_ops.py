@@ -237,6 +237,45 @@ def scale_by_scalar(x, scalar_f32):
     x.mul_(float(scalar_f32))
 
 
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, mode=0, grad_scale=1.0, shadow=None):
+    """mode 0 = torch.optim.AdamW (decoupled decay), mode 1 = the reference's class (optimizer.py:78-95: coupled L2,
+    g rewritten, m_hat / (sqrt(v_hat) + eps)); include/ct_b200.h: ct_adamw_step."""
+    gg = g * grad_scale
+    if mode == 1:
+        gg = gg + weight_decay * p
+        g.copy_(gg)
+    else:
+        p.mul_(1 - lr * weight_decay)
+    m.mul_(beta1).add_(gg, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(gg, gg, value=1 - beta2)
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    if mode == 1:
+        p.sub_(lr * (m / bc1) / (torch.sqrt(v / bc2) + eps))
+    else:
+        p.sub_((lr / bc1) * m / (torch.sqrt(v) / math.sqrt(bc2) + eps))
+    if shadow is not None:
+        shadow.copy_(p)
+
+
+def adamw_multi(ps, gs, ms, vs, lr, beta1, beta2, eps, weight_decay, step, mode=0, grad_scale=1.0, shadows=None):
+    for i in range(len(ps)):
+        adamw_step(ps[i], gs[i], ms[i], vs[i], lr, beta1, beta2, eps, weight_decay, step, mode, grad_scale,
+                   shadows[i] if shadows else None)
+
+
+def sgd_step(p, g, buf, lr, momentum, dampening, weight_decay, first_step):
+    """optimizer.py:28-50: g += wd*p; buf = first ? g : momentum*buf + (1-dampening)*g; g = buf; p -= lr*g."""
+    if weight_decay:
+        g.add_(p, alpha=weight_decay)
+    if momentum:
+        if first_step:
+            buf.copy_(g)
+        else:
+            buf.mul_(momentum).add_(g, alpha=1 - dampening)
+        g.copy_(buf)
+    p.sub_(g, alpha=lr)
+
+
 def lm_head_stats_ok(M, V, dtype=None):
     return True
 
@@ -254,17 +293,20 @@ def patched(compute_dtype=torch.float32):
     from cleantransformer_b200 import functional, ops
     names = ["layernorm_fwd", "layernorm_bwd", "cast", "colsum", "act_fwd", "act_bwd", "gemm", "attn_mask_prep",
              "attn_fwd", "attn_bwd", "embedding_fwd", "embedding_bwd", "cross_entropy_fwd", "cross_entropy_fwd_stats",
-             "scale_by_scalar", "lm_head_stats_ok", "lm_head_logits_with_stats"]
+             "scale_by_scalar", "lm_head_stats_ok", "lm_head_logits_with_stats", "adamw_step", "adamw_multi", "sgd_step"]
     saved = {n: getattr(ops, n) for n in names}
-    saved_req, saved_cd = ops._req_cuda, functional.COMPUTE_DTYPE
+    from cleantransformer_b200 import optimizer
+    saved_req, saved_cd, saved_oreq = ops._req_cuda, functional.COMPUTE_DTYPE, optimizer._require_cuda
     try:
         for n in names:
             setattr(ops, n, globals()[n])
         ops._req_cuda = lambda *ts: None
+        optimizer._require_cuda = lambda ps: None
         functional.COMPUTE_DTYPE = compute_dtype
         yield
     finally:
         for n, f in saved.items():
             setattr(ops, n, f)
         ops._req_cuda = saved_req
+        optimizer._require_cuda = saved_oreq
         functional.COMPUTE_DTYPE = saved_cd
