@@ -13,6 +13,7 @@ One `ct_adamw_step` launch then covers the whole model: 28 B/param of HBM traffi
 import torch
 
 ALIGN = 64  # elements: 256 B for f32, 128 B for bf16 -> every view is TMA-legal
+SHADOW_ON_ANY_DEVICE = False  # tests/mock_ops.py sets it so that the shadow bookkeeping can be exercised on CPU
 
 
 class ParamArena:
@@ -44,7 +45,8 @@ class ParamArena:
             self.grad.zero_()
         else:
             self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.shadow = torch.empty(off, dtype=shadow_dtype, device=dev) if dev.type == "cuda" else None
+        self.shadow = torch.empty(off, dtype=shadow_dtype, device=dev) \
+            if (dev.type == "cuda" or SHADOW_ON_ANY_DEVICE) else None
         self.exp_avg = None
         self.exp_avg_sq = None
         with torch.no_grad():

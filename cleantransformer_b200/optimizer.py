@@ -109,6 +109,9 @@ class AdamW:
             ops.adamw_step(a.flat, a.grad, a.exp_avg, a.exp_avg_sq, self.lr, self.beta1, self.beta2,
                            self.eps, wd, self.steps[0], mode=1, shadow=a.shadow)
             a.mark_shadow_fresh()
+            if a.shadow is None:
+                for p in self.params:
+                    p._ct_shadow_ver = -1
             self.steps = [s + 1 for s in self.steps]
             return
         by_step = {}
@@ -213,6 +216,8 @@ class TorchAdamW(torch.optim.Optimizer):
             a.mark_shadow_fresh()
             for p in ps:
                 self.state[p]["step"] += 1
+                if a.shadow is None:
+                    p._ct_shadow_ver = -1  # no shadow buffer (not a CUDA arena): the cached casts are stale
             return loss
         for g in groups:
             by_step = {}

@@ -295,9 +295,11 @@ def patched(compute_dtype=torch.float32):
              "attn_fwd", "attn_bwd", "embedding_fwd", "embedding_bwd", "cross_entropy_fwd", "cross_entropy_fwd_stats",
              "scale_by_scalar", "lm_head_stats_ok", "lm_head_logits_with_stats", "adamw_step", "adamw_multi", "sgd_step"]
     saved = {n: getattr(ops, n) for n in names}
-    from cleantransformer_b200 import optimizer
+    from cleantransformer_b200 import arena, optimizer
     saved_req, saved_cd, saved_oreq = ops._req_cuda, functional.COMPUTE_DTYPE, optimizer._require_cuda
+    saved_sh = arena.SHADOW_ON_ANY_DEVICE
     try:
+        arena.SHADOW_ON_ANY_DEVICE = True
         for n in names:
             setattr(ops, n, globals()[n])
         ops._req_cuda = lambda *ts: None
@@ -310,3 +312,4 @@ def patched(compute_dtype=torch.float32):
         ops._req_cuda = saved_req
         optimizer._require_cuda = saved_oreq
         functional.COMPUTE_DTYPE = saved_cd
+        arena.SHADOW_ON_ANY_DEVICE = saved_sh

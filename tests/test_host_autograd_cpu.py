@@ -236,3 +236,36 @@ def test_optimizer_host_logic_matches_reference_trajectories(golden):
             o.step()
             for p, ref in zip(ps, g["torch_adamw"][k]):
                 assert rel_err(p.detach(), ref) < 1e-5
+
+
+def test_bf16_shadow_weights_stay_coherent_across_optimizer_steps(golden):
+    """The tensor-core operands are bf16 shadows of the fp32 parameters, cached per parameter and refreshed by the
+    fused AdamW pass (arena.shadow, functional.shadow). Four training steps with the cache must equal, bit for bit,
+    four steps where every shadow is thrown away after each optimizer step (a stale shadow would show up as a
+    different trajectory). Also: from the second step on the gradients are arena views and the flat kernel path runs."""
+    from cleantransformer_b200.optimizer import TorchAdamW
+    g = golden("bloom_tiny")
+
+    def run(invalidate):
+        with mock_ops.patched(compute_dtype=torch.bfloat16):
+            m = _bloom(g)
+            o = TorchAdamW(m.parameters(), lr=1e-2)
+            flat_steps = 0
+            for _ in range(4):
+                o.zero_grad()
+                (loss, _, _), _ = m(input_ids=g["ids"], attention_mask=g["mask"], labels=g["labels"])
+                loss.backward()
+                flat_steps += int(o._arena is not None and o._arena.grads_complete())
+                o.step()
+                if invalidate:
+                    for p in m.parameters():
+                        p._ct_shadow_ver = -1
+                        p._ct_shadow = None
+            return [p.detach().clone() for p in m.parameters()], float(loss), flat_steps
+
+    a, la, flat_a = run(False)
+    b, lb, _ = run(True)
+    assert flat_a >= 3
+    assert la == lb
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
