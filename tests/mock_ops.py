@@ -276,6 +276,11 @@ def sgd_step(p, g, buf, lr, momentum, dampening, weight_decay, first_step):
     p.sub_(g, alpha=lr)
 
 
+def kv_cache_append(past, new):
+    """ops.kv_cache_append grows a preallocated cache in place; the observable result is the concatenation."""
+    return new if past is None else torch.cat([past, new], 2)
+
+
 def lm_head_stats_ok(M, V, dtype=None):
     return True
 
@@ -293,7 +298,7 @@ def patched(compute_dtype=torch.float32):
     from cleantransformer_b200 import functional, ops
     names = ["layernorm_fwd", "layernorm_bwd", "cast", "colsum", "act_fwd", "act_bwd", "gemm", "attn_mask_prep",
              "attn_fwd", "attn_bwd", "embedding_fwd", "embedding_bwd", "cross_entropy_fwd", "cross_entropy_fwd_stats",
-             "scale_by_scalar", "lm_head_stats_ok", "lm_head_logits_with_stats", "adamw_step", "adamw_multi", "sgd_step"]
+             "scale_by_scalar", "lm_head_stats_ok", "lm_head_logits_with_stats", "adamw_step", "adamw_multi", "sgd_step", "kv_cache_append"]
     saved = {n: getattr(ops, n) for n in names}
     from cleantransformer_b200 import arena, optimizer
     saved_req, saved_cd, saved_oreq = ops._req_cuda, functional.COMPUTE_DTYPE, optimizer._require_cuda
