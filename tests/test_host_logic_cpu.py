@@ -224,3 +224,42 @@ def test_copy_engine_allreduce_plan_tiles_every_piece():
             assert pos == n
             covered += n
         assert covered == count
+
+
+def test_ddp_tied_table_state_machine():
+    """ddp._on_grad_written for a tied token table on the peer-memory path: the first gradient (dense LM-head wgrad)
+    launches the table's own bucket at once, the second must have gone through the sparse exchange — anything else
+    (a gradient that would silently stay local) is an error; ordinary parameters count down their bucket."""
+    from cleantransformer_b200.ddp import DistributedDataParallel as D
+    d = object.__new__(D)
+    torch.nn.Module.__init__(d)
+    tied, plain_a, plain_b = [torch.nn.Parameter(torch.zeros(4, 4)) for _ in range(3)]
+    tied._ct_expected_writes = 2
+    launched = []
+    d._launch = lambda bi, final=False: launched.append(bi)
+    d._bucket_of = {id(tied): 0, id(plain_a): 1, id(plain_b): 1}
+    d._grad_off = {id(tied): 0}
+    d.require_backward_grad_sync = True
+
+    def begin():
+        d._pending, d._launched, d._writes, d._cb_queued, d._early = [1, 2], [False, False], {}, True, {}
+        launched.clear()
+
+    begin()
+    d._on_grad_written(tied)                       # LM-head wgrad
+    assert launched == [0] and d._early[id(tied)] == "dense" and d._pending[0] == 0
+    d._on_grad_written(plain_a)
+    assert launched == [0] and d._pending[1] == 1
+    d._on_grad_written(plain_b)
+    assert launched == [0, 1]
+    d._early[id(tied)] = "sparse"                  # what _sparse_embedding_bwd records after the exchange
+    d._on_grad_written(tied)                       # embedding scatter: nothing left to launch
+    assert launched == [0, 1]
+    begin()
+    d._on_grad_written(tied)
+    with pytest.raises(RuntimeError):              # second contribution did not come through the sparse exchange
+        d._on_grad_written(tied)
+    begin()
+    d.require_backward_grad_sync = False           # no_sync(): gradients stay local, nothing is launched
+    d._on_grad_written(tied); d._on_grad_written(plain_a)
+    assert launched == []
