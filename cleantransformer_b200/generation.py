@@ -12,18 +12,26 @@ of scope for this tier.
 import torch
 
 
+def _temperature(scores, temperature):
+    """logits_processor.py:35-41 (TemperatureLogitsWrapper): the temperature is clamped at 1e-2."""
+    return scores / max(temperature, 1e-2)
+
+
 def _filter_top_k(scores, k, min_keep=1):
-    k = max(min(k, scores.size(-1)), min_keep)
+    """logits_processor.py:44-56 (TopKLogitsWrapper)."""
+    k = min(int(max(k, min_keep, 1)), scores.size(-1))
     kth = torch.topk(scores, k)[0][..., -1, None]
     return scores.masked_fill(scores < kth, float("-inf"))
 
 
 def _filter_top_p(scores, top_p, min_keep=1):
+    """logits_processor.py:59-79 (TopPLogitsWrapper): top_p clamped to [0, 1]; the `min_keep` (>= 1) most probable
+    tokens always survive — with top_p = 0 that is exactly the arg-max."""
+    top_p = max(min(top_p, 1.0), 0)
     sorted_scores, sorted_idx = torch.sort(scores, descending=False)
     cum = sorted_scores.softmax(dim=-1).cumsum(dim=-1)
     remove = cum <= (1 - top_p)
-    if min_keep > 1:
-        remove[..., -min_keep:] = False
+    remove[..., -max(1, min_keep):] = False
     remove = remove.scatter(1, sorted_idx, remove)
     return scores.masked_fill(remove, float("-inf"))
 
@@ -66,7 +74,7 @@ class GenerationMixin:
             if do_sample:
                 scores = scores.float()
                 if temperature != 1.0:
-                    scores = scores / temperature
+                    scores = _temperature(scores, temperature)
                 if top_k > 0:
                     scores = _filter_top_k(scores, top_k)
                 if top_p < 1.0:

@@ -158,3 +158,22 @@ def test_optimizers_match_reference(golden):
     for a, b in zip(g["ref_sgd"], g["torch_sgd"]):
         for x, y in zip(a, b):
             assert rel_err(x, y) < 1e-5
+
+
+def test_sampling_wrappers_match_reference(golden):
+    """generation/logits_processor.py:35-79 — oracle restatement AND the product's host-side filters
+    (cleantransformer_b200/generation.py) against the real reference's wrappers, clamped corners included."""
+    from cleantransformer_b200 import generation as G
+    from oracle import ct_oracle as O
+    g = golden("sampling")
+    s = g["scores"]
+    for t, ref in g["temperature"].items():
+        assert torch.equal(O.temperature_wrapper(s.clone(), t), ref)
+        assert torch.equal(G._temperature(s.clone(), t), ref)
+    for k, ref in g["top_k"].items():
+        assert torch.equal(O.top_k_wrapper(s.clone(), k), ref)
+        assert torch.equal(G._filter_top_k(s.clone(), k), ref)
+    for p, ref in g["top_p"].items():
+        assert torch.equal(O.top_p_wrapper(s.clone(), p), ref)
+        assert torch.equal(G._filter_top_p(s.clone(), p), ref)
+    assert int(torch.isfinite(g["top_p"][0.0]).sum()) == s.shape[0]  # top_p = 0 keeps exactly the arg-max

@@ -244,8 +244,29 @@ def golden_optim():
                    "ref_sgd_plain": ref_sgd_plain, "torch_adamw": torch_adamw, "torch_sgd": torch_sgd})
 
 
+def golden_sampling():
+    """The reference's logits wrappers (generation/logits_processor.py:35-79) on seeded scores, including the
+    clamped corners: temperature below 1e-2, top_k beyond the vocabulary, top_p at 0 and above 1."""
+    from CleanTransformer.generation import logits_processor as lp
+    torch.manual_seed(999)
+    scores = torch.randn(4, 50) * 3
+    scores[1, 7] = scores[1, 9]  # a tie
+    out = {"scores": scores, "temperature": {}, "top_k": {}, "top_p": {}}
+    for t in (0.7, 1.5, 0.001):
+        out["temperature"][t] = lp.TemperatureLogitsWrapper(t)(None, scores.clone())
+    for k in (1, 5, 1000):
+        out["top_k"][k] = lp.TopKLogitsWrapper(k, min_tokens_to_keep=1)(None, scores.clone())
+    for p_ in (0.8, 0.3, 0.0, 1.5):
+        out["top_p"][p_] = lp.TopPLogitsWrapper(p_, min_tokens_to_keep=1)(None, scores.clone())
+    save("sampling", out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if len(sys.argv) > 1:  # regenerate only the named fixtures: python tools/make_golden.py sampling
+        for name in sys.argv[1:]:
+            globals()["golden_" + name]()
+        sys.exit(0)
     golden_layernorm()
     golden_generic_block()
     golden_gelu()
@@ -253,3 +274,4 @@ if __name__ == "__main__":
     golden_gpt()
     golden_bert()
     golden_optim()
+    golden_sampling()
