@@ -305,3 +305,46 @@ def test_trainer_loop_trains_the_bloom_mirror(golden, tmp_path):
             (lg1, _), _ = m(input_ids=data[0]["input_ids"][None], attention_mask=data[0]["attention_mask"][None])
             (lg2, _), _ = m2(input_ids=data[0]["input_ids"][None], attention_mask=data[0]["attention_mask"][None])
         assert torch.equal(lg1, lg2)
+
+
+@pytest.mark.parametrize("pad", ["left", "right"])
+def test_bloom_padding_semantics_and_greedy_generation_vs_oracle(golden, pad):
+    """Left / right padded batches through the Bloom mirror (ALiBi positions from the mask's cumulative sum,
+    masked_fill(finfo.min) on padded keys, fully masked query rows on left padding) against the oracle restatement
+    of modeling_bloom.py, plus greedy decoding with the KV cache against the oracle's loop (token ids bit-exact)."""
+    from oracle import ct_oracle as O
+    g = golden("bloom_tiny")
+    cfg = g["cfg"]
+    torch.manual_seed(31)
+    B, S = 3, 9
+    ids = torch.randint(3, cfg["vocab_size"], (B, S))
+    mask = torch.ones(B, S, dtype=torch.long)
+    for b, n in enumerate((0, 3, 5)):
+        if n:
+            if pad == "left":
+                mask[b, :n] = 0
+            else:
+                mask[b, S - n:] = 0
+    sd = {k: v for k, v in g["sd"].items() if k != "lm_head.weight"}
+    with torch.no_grad():
+        (lg_ref, h_ref), _ = O.bloom_causal_lm(ids, mask, sd, cfg["n_layer"], cfg["num_attention_heads"],
+                                               cfg["layer_norm_epsilon"])
+    with mock_ops.patched():
+        m = _bloom(g).eval()
+        with torch.no_grad():
+            (lg, h), _ = m(input_ids=ids, attention_mask=mask)
+        valid = mask.bool()
+        assert rel_err(lg[valid], lg_ref[valid]) < 2e-4
+        assert rel_err(lg, lg_ref) < 2e-4  # padded positions too: the reference's finite-fill arithmetic
+        if pad == "left":  # generation recipe of the reference (inference_bloom.py: left padding)
+            gen = m.generate(ids, attention_mask=mask,
+                             generation_configs={"beam_size": 1, "do_sample": False, "max_gen_len": 5,
+                                                 "end_ids": None, "pad_id": 3, "no_repeat_ngram_size": 0})
+
+            def step(x, am, caches):
+                return O.bloom_causal_lm(x, am, sd, cfg["n_layer"], cfg["num_attention_heads"],
+                                         cfg["layer_norm_epsilon"], k_v_pasts=caches)
+
+            with torch.no_grad():
+                ref = O.greedy_generate(step, ids, mask, cfg["n_layer"], max_gen_len=5, pad_id=3)
+            assert torch.equal(gen.view(ref.shape), ref)
