@@ -348,3 +348,30 @@ def test_bloom_padding_semantics_and_greedy_generation_vs_oracle(golden, pad):
             with torch.no_grad():
                 ref = O.greedy_generate(step, ids, mask, cfg["n_layer"], max_gen_len=5, pad_id=3)
             assert torch.equal(gen.view(ref.shape), ref)
+
+
+def test_bloom_post_layernorm_residual_switch_vs_oracle(golden):
+    """BloomBlock's `apply_residual_connection_post_layernorm` switch (modeling_bloom.py:142-159): the residual is
+    the LayerNorm OUTPUT instead of its input — the un-fused block path (the fused pre-LN node does not apply).
+    Training step (loss, every gradient) against the oracle's autograd on the same weights."""
+    from cleantransformer_b200.models import modeling_bloom as mb
+    from oracle import ct_oracle as O
+    g = golden("bloom_tiny")
+    cfg = dict(g["cfg"]); cfg["apply_residual_connection_post_layernorm"] = True
+    ids, mask, labels = g["ids"], g["mask"], g["labels"]
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["sd"].items() if k != "lm_head.weight"}
+    (l_ref, lg_ref, _), _ = O.bloom_causal_lm(ids, mask, sd, cfg["n_layer"], cfg["num_attention_heads"],
+                                              cfg["layer_norm_epsilon"], labels=labels, training=True,
+                                              post_ln_residual=True)
+    l_ref.backward()
+    with mock_ops.patched():
+        m = mb.BloomForCausalLM(mb.BloomConfig(**cfg))
+        m.load_state_dict(g["sd"], strict=True)
+        m._tie_weight(); m.train()
+        (loss, logits, _), _ = m(input_ids=ids, attention_mask=mask, labels=labels)
+        loss.backward()
+    assert abs(float(loss) - float(l_ref)) <= 2e-4 * abs(float(l_ref))
+    assert rel_err(logits, lg_ref) < 2e-4
+    for name, p in m.named_parameters():
+        key = "bloom.word_embeddings.weight" if name == "lm_head.weight" else name
+        assert rel_err(p.grad, sd[key].grad) < 1e-3, name
