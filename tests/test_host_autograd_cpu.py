@@ -375,3 +375,36 @@ def test_bloom_post_layernorm_residual_switch_vs_oracle(golden):
     for name, p in m.named_parameters():
         key = "bloom.word_embeddings.weight" if name == "lm_head.weight" else name
         assert rel_err(p.grad, sd[key].grad) < 1e-3, name
+
+
+def test_bert_classifier_gradients_vs_oracle(golden):
+    """BERT fine-tuning direction (BASELINE config 5): external cross entropy on the classifier logits, backward
+    through the pooler (tanh), erf-GELU FFNs, post-LN blocks, separate q/k/v Linears with the additive -1e4 mask and
+    the three embedding tables — every gradient against the oracle's autograd (dropout off: eval())."""
+    from cleantransformer_b200.models import modeling_bert as mbert
+    from oracle import ct_oracle as O
+    g = golden("bert_tiny")
+    cfg = dict(g["cfg"])
+    ids, mask, seg, pos = g["ids"], g["mask"], g["seg"], g["pos"]
+    torch.manual_seed(5)
+    labels = torch.randint(0, cfg["num_labels"], (ids.shape[0],))
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["sd"].items()}
+    lg_ref, _, _ = O.bert_classifier(ids, mask, seg, pos, sd, cfg["num_hidden_layers"], cfg["num_attention_heads"],
+                                     cfg["layer_norm_eps"])
+    torch.nn.functional.cross_entropy(lg_ref, labels).backward()
+    with mock_ops.patched():
+        model = mbert.BertForSequenceClassification(mbert.BertConfig(**cfg)).eval()
+        model.load_state_dict(g["sd"], strict=True)
+        logits = model(ids, mask, seg, pos)
+        torch.nn.functional.cross_entropy(logits.float(), labels).backward()
+    assert rel_err(logits, lg_ref) < 2e-4
+    checked = 0
+    for name, p in model.named_parameters():
+        ref = sd[name].grad
+        if ref is None:
+            continue
+        assert p.grad is not None, name
+        # (the key bias gradient is analytically zero — softmax is shift invariant — hence the absolute floor)
+        assert float((p.grad - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-9, name
+        checked += 1
+    assert checked >= 20
