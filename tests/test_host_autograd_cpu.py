@@ -408,3 +408,41 @@ def test_bert_classifier_gradients_vs_oracle(golden):
         assert float((p.grad - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-9, name
         checked += 1
     assert checked >= 20
+
+
+@pytest.mark.parametrize("version", ["gpt", "gpt2"])
+def test_gpt_lm_gradients_vs_oracle(golden, version):
+    """GPT training direction: external shifted cross entropy on the LM logits, backward through the tied head, all
+    blocks (post-LN 'gpt' / pre-LN 'gpt2'), Conv1D weights and BOTH embedding tables, left-padded batch — every
+    gradient against the oracle's autograd. eval(): the reference's Dropout(0.5) (modeling_gpt.py:136) is off."""
+    from cleantransformer_b200.models import modeling_gpt as mg
+    from oracle import ct_oracle as O
+    g = golden("gpt_tiny")
+    c, cfg = g[version], g["cfg"]
+    ids, mask = c["ids"], c["mask"]
+
+    def lm_loss(logits):
+        return torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]).float(), ids[:, 1:].reshape(-1))
+
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "attn.bias" not in k) for k, v in c["sd"].items()}
+    (lg_ref, _), _ = O.gpt_lm_head_model(ids, mask, sd, cfg["n_layer"], cfg["n_head"], cfg["n_ctx"],
+                                         cfg["layer_norm_epsilon"], version=version)
+    lm_loss(lg_ref).backward()
+    with mock_ops.patched():
+        model = mg.GPTLMHeadModel(mg.GPTConfig(**cfg), version=version)
+        model.load_state_dict(c["sd"], strict=True)
+        model._tie_weights()
+        model.eval()
+        (logits, _), _ = model(ids, attention_mask=mask)
+        lm_loss(logits).backward()
+    assert rel_err(logits, lg_ref) < 2e-4
+    checked = 0
+    for name, p in model.named_parameters():
+        key = "gpt.tokens_embed.weight" if name == "lm_head.weight" else name
+        ref = sd[key].grad if key in sd else None
+        if ref is None:
+            continue
+        assert p.grad is not None, name
+        assert float((p.grad - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-9, name
+        checked += 1
+    assert checked >= 20
