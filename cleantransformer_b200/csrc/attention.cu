@@ -2287,6 +2287,275 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// v6: v3 with SIXTEEN compute warps. The r01f / r01g stamps put ~3 k of v3's ~4.7 k cycles per query tile into the
+// element math of its eight compute warps (two per scheduler, each working through two 32-query chunks one after
+// the other: MUFU and FMA latencies are barely hidden) and ~1 k into the dQ red.add burst. Here every compute warp
+// owns ONE 32-query chunk (64 score / dP registers instead of 128), so four warps per scheduler interleave, and the
+// dQ drain is spread over sixteen warps (16 head-dim columns each). 640 threads = 5 warpgroups: the TMA / MMA group
+// gives its registers to the four compute groups with setmaxnreg (launch bound 96 -> 40 / 104).
+// Written after round 1's GPU budget was spent: compiled, NOT yet run (ATTN_BWD_IMPL=7, opt-in tests only).
+constexpr int FB6_THREADS = 640;
+
+template <bool BF16>
+__global__ void __launch_bounds__(FB6_THREADS, 1)
+    attn_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                        const AttnBwdP bp) {
+  const AttnP& p = bp.f;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t sK = base, sV = base + FA_TILE;
+  const uint32_t sQ = base + 2 * FA_TILE;   // 2 stages, each Q then dO
+  constexpr int N_TILES = 14;
+  constexpr uint32_t PDS_STRIDE = 4 * FA_TILE;  // buffer (it & 1) of the P^T / dS^T pair
+  constexpr uint32_t STAT_STRIDE = 1024;
+  constexpr int NCOMP = 512;                    // compute threads
+  const uint32_t sPT = base + 6 * FA_TILE;  // 2 panels
+  const uint32_t sDS = base + 8 * FA_TILE;  // 2 panels
+  const uint32_t bars = base + N_TILES * FA_TILE;
+  const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 24, sdp_full = bars + 40,
+                 pds_ready = bars + 48, mma_done = bars + 56, dkv_full = bars + 64, tmem_slot = bars + 72,
+                 sdp_free = bars + 80, lse_s = bars + 128, del_s = bars + 640;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + N_TILES * FA_TILE + 72);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_kv_tiles = (p.Sk + 127) / 128;
+  const int kv_tile = blockIdx.x % n_kv_tiles;
+  const int bh = blockIdx.x / n_kv_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int kv0 = kv_tile * 128;
+  const int n_q_tiles = (p.Sq + 127) / 128;
+  int i_start = 0;
+  if (p.causal) {
+    const bool full_sweep = p.first_valid && (p.first_valid[b] > p.off);
+    if (!full_sweep) i_start = max(0, (kv0 - p.off) / 128);
+  }
+  const int n_it = max(0, n_q_tiles - i_start);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full + 8 * s, 1); mbar_init(qdo_empty + 8 * s, 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_free, NCOMP);
+    mbar_init(pds_ready, NCOMP);
+    mbar_init(mma_done, 1);
+    mbar_init(dkv_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t T_ST = tmem, T_DPT = tmem + 128, T_DV = tmem + 256, T_DK = tmem + 320, T_DQ = tmem + 384;
+
+  // setmaxnreg inside each role branch: ptxas sizes a region's registers by the setmaxnreg that dominates it
+  const int wg = warp >> 2;
+  if (wg == 0) {
+   setmaxnreg_dec<40>();
+   if (warp == 0) {
+    if (lane == 0 && n_it > 0) {
+      mbar_expect_tx(kv_full, 2 * FA_TILE);
+      tma_load_4d(sK, &tmK, kv_full, 0, kv0, h, b);
+      tma_load_4d(sV, &tmV, kv_full, 0, kv0, h, b);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1, q0 = (i_start + it) * 128;
+        mbar_wait(qdo_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(qdo_full + 8 * s, 2 * FA_TILE);
+        tma_load_4d(sQ + s * 2 * FA_TILE, &tmQ, qdo_full + 8 * s, 0, q0, h, b);
+        tma_load_4d(sQ + s * 2 * FA_TILE + FA_TILE, &tmDO, qdo_full + 8 * s, 0, q0, h, b);
+      }
+    }
+   } else if (warp == 1) {
+    if (lane == 0 && n_it > 0) {
+      const uint32_t idesc_kk = umma_idesc_f16(BF16 ? 1 : 0, 0, 0, 128, 128);  // S^T, dP^T
+      const uint32_t idesc_km = umma_idesc_f16(BF16 ? 1 : 0, 0, 1, 128, 64);   // dV, dK
+      const uint32_t idesc_mm = umma_idesc_f16(BF16 ? 1 : 0, 1, 1, 128, 64);   // dQ
+      auto issue_sdp = [&](int it) {
+        const int s = it & 1;
+        const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
+        mbar_wait(qdo_full + 8 * s, (it >> 1) & 1);
+        if (it > 0) mbar_wait(sdp_free, (it - 1) & 1);  // every compute thread holds S^T/dP^T(it-1) in registers
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // S^T[kv, q] = K[kv, d] . Q[q, d]
+          umma_f16(T_ST, umma_smem_desc_sw128(sK + k * 32, 0, 1024), umma_smem_desc_sw128(q + k * 32, 0, 1024),
+                   idesc_kk, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dP^T[kv, q] = V[kv, d] . dO[q, d]
+          umma_f16(T_DPT, umma_smem_desc_sw128(sV + k * 32, 0, 1024),
+                   umma_smem_desc_sw128(d_o + k * 32, 0, 1024), idesc_kk, k > 0);
+        umma_commit(sdp_full);
+      };
+      mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
+        if (it + 1 < n_it) issue_sdp(it + 1);  // runs under the element math of tile it
+        mbar_wait(pds_ready, it & 1);
+        tc_fence_after();
+        const uint32_t pt = sPT + (it & 1) * PDS_STRIDE, dst = sDS + (it & 1) * PDS_STRIDE;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ[q, d] = dS[q, kv] . K[kv, d]  (A MN-major view of dS^T)
+          umma_f16(T_DQ, umma_smem_desc_sw128(dst + k * 2048, FA_TILE, 1024),
+                   umma_smem_desc_sw128(sK + k * 2048, 64 * 128, 1024), idesc_mm, k > 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV[kv, d] += P^T[kv, q] . dO[q, d]   (B MN-major: rows = q)
+          umma_f16(T_DV, umma_smem_desc_sw128(pt + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                   umma_smem_desc_sw128(d_o + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dK[kv, d] += dS^T[kv, q] . Q[q, d]
+          umma_f16(T_DK, umma_smem_desc_sw128(dst + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                   umma_smem_desc_sw128(q + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
+        umma_commit(qdo_empty + 8 * s);
+        umma_commit(mma_done);  // dQ(it) readable; P^T / dS^T buffer (it & 1) free for tile it+2
+      }
+      umma_commit(dkv_full);
+    }
+   }
+  } else {
+    setmaxnreg_inc<104>();  // 128 x 40 + 512 x 104 = 58 368 <= 640 x 96 (the CTA's pool at launch)
+    const int wq = warp & 3;
+    const int rr = wq * 32 + lane;   // key row inside the tile (S^T) / query row (dQ)
+    const int c = wg - 1;            // the 32-query chunk this warp owns; also its 16 head-dim columns of dQ / dK / dV
+    const int jg = kv0 + rr;
+    const uint32_t t_lane = (uint32_t)(wq * 32) << 16;
+    FbCtx cx;
+    cx.kb = (p.kbias2 && jg < p.Sk) ? __ldg(p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh + jg) : 0.f;
+    cx.sl2 = p.sl2; cx.scale = p.scale; cx.cf2 = p.causal_fill2;
+    cx.jg = jg; cx.off = p.off; cx.causal = p.causal; cx.key_oob = jg >= p.Sk;
+    cx.lse_s = lse_s; cx.del_s = del_s; cx.sPT = sPT; cx.sDS = sDS; cx.rr = rr; cx.sw = rr & 7;
+    // generic arithmetic for the whole warp when a key is masked (the reference's finite fill matters on
+    // fully masked query rows) or the key tile is ragged
+    const bool warp_generic = __any_sync(0xffffffffu, cx.kb < -1e30f) || (kv0 + 128 > p.Sk);
+    const bool fill_is_ninf = p.causal_fill2 == -INFINITY;
+    const float* lse_bh = p.lse2 + ((int64_t)b * p.H + h) * p.Sq;
+    const float* del_bh = bp.delta + ((int64_t)b * p.H + h) * p.Sq;
+    // per-query statistics of the current query tile, staged as -lse2 and -delta*scale by the chunk-0 warps
+    float nlse_next = -INFINITY, ndel_next = 0.f;
+    if (c == 0 && n_it > 0 && i_start * 128 + rr < p.Sq) {
+      nlse_next = -__ldg(lse_bh + i_start * 128 + rr);
+      ndel_next = -__ldg(del_bh + i_start * 128 + rr) * p.scale;
+    }
+    // dQ of query tile `itp`: this thread owns query row rr, head-dim columns [16c, 16c + 16) = d/4 planes 4c..4c+3
+    auto red_dq = [&](const uint32_t (&r)[16], int itp) {
+      const int qi = (i_start + itp) * 128 + rr;
+      if (qi < p.Sq) {
+        float* dst = bp.dq_accum + (((int64_t)b * p.H + h) * n_q_tiles + (i_start + itp)) * FB_DQ_TILE +
+                     (4 * c * 128 + rr) * 4;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 512 * g),
+                       "f"(__uint_as_float(r[4 * g])), "f"(__uint_as_float(r[4 * g + 1])),
+                       "f"(__uint_as_float(r[4 * g + 2])), "f"(__uint_as_float(r[4 * g + 3]))
+                       : "memory");
+      }
+    };
+
+    for (int it = 0; it < n_it; ++it) {
+      const int q0 = (i_start + it) * 128;
+      cx.sPT = sPT + (it & 1) * PDS_STRIDE; cx.sDS = sDS + (it & 1) * PDS_STRIDE;
+      cx.lse_s = lse_s + (it & 1) * STAT_STRIDE; cx.del_s = del_s + (it & 1) * STAT_STRIDE;
+      mbar_wait(sdp_full, it & 1);
+      tc_fence_after();
+      // chunk kind (warp-uniform)
+      const bool touches_diag = p.causal && (kv0 + 127 > q0 + p.off);
+      const bool aligned_diag = touches_diag && fill_is_ninf && (kv0 == q0 + p.off) && !warp_generic;
+      int kind;
+      if (warp_generic || (touches_diag && !aligned_diag)) kind = 2;
+      else if (aligned_diag) kind = c < wq ? 1 : (c > wq ? 0 : 2);  // key row 32*wq+l vs queries 32*c..32*c+31
+      else kind = 0;
+      uint32_t rs[32], rd[32];
+      if (kind != 1) { tmem_ld_32x32(T_ST + t_lane + c * 32, rs); tmem_ld_32x32(T_DPT + t_lane + c * 32, rd); }
+      // statistics buffer (it & 1) was last read by tile it-2, and every thread finished tile it-2 before it
+      // arrived at the named barrier of tile it-1, which this thread has passed
+      if (c == 0) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.lse_s + 4 * rr), "f"(nlse_next) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.del_s + 4 * rr), "f"(ndel_next) : "memory");
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(sdp_free);        // S^T / dP^T are in registers: the next tile's MMAs may overwrite them
+      bar_sync_named(1, NCOMP);     // statistics staged by the chunk-0 warps are visible
+      if (c == 0) {
+        const int nq = q0 + 128 + rr;
+        const bool ok = (it + 1 < n_it) && nq < p.Sq;
+        nlse_next = ok ? -__ldg(lse_bh + nq) : -INFINITY;
+        ndel_next = ok ? -__ldg(del_bh + nq) * p.scale : 0.f;
+      }
+      if (kind == 0) fb2_chunk<0, BF16>(cx, rs, rd, c, q0);
+      else if (kind == 1) fb2_chunk<1, BF16>(cx, rs, rd, c, q0);
+      else fb2_chunk<2, BF16>(cx, rs, rd, c, q0);
+      if (it > 0) {
+        // The MMAs of tile it-1 ran under the chunk above: dQ(it-1) is complete (T_DQ is only rewritten after
+        // pds_ready(it)). Waiting for every phase in order also proves that buffer ((it+1) & 1) of P^T / dS^T,
+        // read by the MMAs of tile it-1, is free when tile it+1 writes it.
+        mbar_wait(mma_done, (it - 1) & 1);
+        tc_fence_after();
+        uint32_t rq[16];
+        tmem_ld_32x16(T_DQ + t_lane + c * 16, rq);
+        tmem_ld_wait();
+        red_dq(rq, it - 1);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_ready);
+    }
+    // ---- last dQ tile, then dK / dV for this key row: 16 of the 64 head-dim columns per thread ----
+    if (n_it > 0) {
+      mbar_wait(mma_done, (n_it - 1) & 1);
+      tc_fence_after();
+      uint32_t rq[16];
+      tmem_ld_32x16(T_DQ + t_lane + c * 16, rq);
+      tmem_ld_wait();
+      red_dq(rq, n_it - 1);
+      mbar_wait(dkv_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint32_t r[16];
+      if (n_it > 0) {
+        tmem_ld_32x16((which == 0 ? T_DV : T_DK) + t_lane + c * 16, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) r[t] = 0u;
+      }
+      if (!cx.key_oob) {
+        void* basep = which == 0 ? bp.dv : bp.dk;
+        const int64_t eo = which == 0
+            ? (int64_t)b * bp.dv_sb + (int64_t)h * bp.dv_sh + (int64_t)jg * bp.dv_ss
+            : (int64_t)b * bp.dk_sb + (int64_t)h * bp.dk_sh + (int64_t)jg * bp.dk_ss;
+        uint8_t* row = reinterpret_cast<uint8_t*>(basep) + 2 * (eo + c * 16);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 w;
+          float f[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) f[u] = __uint_as_float(r[8 * g + u]);
+          if constexpr (BF16) {
+            w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]);
+            w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
+          } else {
+            __half2 x;
+            x = __floats2half2_rn(f[0], f[1]); w.x = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f[2], f[3]); w.y = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f[4], f[5]); w.z = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f[6], f[7]); w.w = *reinterpret_cast<uint32_t*>(&x);
+          }
+          *reinterpret_cast<uint4*>(row + 16 * g) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (one warp per (b,i,h); D <= 128)
 __global__ void __launch_bounds__(256)
     attn_delta_kernel(const void* __restrict__ dout, const void* __restrict__ o, int fmt, int64_t sb,
@@ -2856,9 +3125,10 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     // ATTN_BWD_IMPL: 0 = auto (v3), 1 = v1, 2 = v2 (row-major dQ workspace), 3 = v2 + tiled dQ workspace,
     //                4 = v3 (tiled dQ workspace, P^T / dS^T double-buffered), 5 = v4 (v3 + dedicated dQ drain warpgroup),
     //                6 = v5 (persistent v3: the next work item's loads and first MMAs run under the epilogue; NOT yet
-    //                    run on a GPU — written after the round's GPU budget was spent)
+    //                    run on a GPU — written after the round's GPU budget was spent), 7 = v6 (v3 with sixteen
+    //                    compute warps, one 32-query chunk each; same status)
     int variant = option(OPT_ATTN_BWD_IMPL);
-    if (variant < 1 || variant > 6) variant = 4;
+    if (variant < 1 || variant > 7) variant = 4;
     const bool dq_tiled = variant >= 3;
     const int nqt = (a.Sq + 127) / 128;
     // the workspace is sized for whole query tiles (include/ct_b200.h): B*H*ceil(Sq/128)*128*64 floats
@@ -2878,6 +3148,8 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc6_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       attr = true;
     }
     const int64_t grid = (int64_t)a.B * a.H * ((a.Sk + 127) / 128);
@@ -2891,6 +3163,10 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
       case 3:
         if (fmt == 1) attn_bwd_tc2_kernel<true, 1><<<g, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
         else attn_bwd_tc2_kernel<false, 1><<<g, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
+        break;
+      case 7:
+        if (fmt == 1) attn_bwd_tc6_kernel<true><<<g, FB6_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
+        else attn_bwd_tc6_kernel<false><<<g, FB6_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
         break;
       case 6: {
         const int n_items = (int)grid;

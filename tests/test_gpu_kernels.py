@@ -297,6 +297,7 @@ if os.environ.get("CT_TEST_EXPERIMENTAL"):
     # variants written after the round's GPU budget was spent: compiled, never run — opt-in until a GPU visit
     # has shown them green (run them under `timeout`: a protocol bug in a persistent kernel traps after 2 s)
     ATT_VARIANTS["v5"] = (0, 6)  # persistent backward
+    ATT_VARIANTS["v6"] = (0, 7)  # backward with sixteen compute warps
     ATT_VARIANTS["f3"] = (2, 4)  # forward with the lazy reference maximum and per-panel P hand-over
 ATT_PARAMS = [c + ("-",) for c in ATT_CASES if c[-1] == 2] + \
              [c + (v,) for c in ATT_CASES if c[-1] == 1 for v in ATT_VARIANTS]
