@@ -263,3 +263,29 @@ def test_ddp_tied_table_state_machine():
     d.require_backward_grad_sync = False           # no_sync(): gradients stay local, nothing is launched
     d._on_grad_written(tied); d._on_grad_written(plain_a)
     assert launched == []
+
+
+def test_generation_loop_matches_the_real_reference(golden):
+    """cleantransformer_b200.generation.GenerationMixin against outputs of the REFERENCE's GenerationMixin
+    (tests/golden/generation_loop.pt, tools/make_golden.py): greedy and seeded sampling through the temperature /
+    top-k / top-p wrappers, one and several end ids, pad ids for finished rows, left-padded prompts — token ids
+    bit-exact, shapes included (the reference emits max_gen_len + 2 tokens)."""
+    from cleantransformer_b200.generation import GenerationMixin
+    g = golden("generation_loop")
+    emb = g["emb"]
+
+    class Cfg:
+        n_layer = 2
+
+    class Toy(GenerationMixin):
+        config = Cfg()
+
+        def __call__(self, ids, attention_mask=None, k_v_pasts=None, **kw):
+            n = attention_mask.sum(-1, keepdim=True).float()
+            logits = emb[ids] + 0.01 * n[:, :, None]
+            return (logits, logits), k_v_pasts
+
+    for cfg, ref in zip(g["cases"], g["outputs"]):
+        torch.manual_seed(g["seed"])
+        out = Toy().generate(g["ids"].clone(), attention_mask=g["mask"].clone(), generation_configs=dict(cfg))
+        assert out.shape == ref.shape and torch.equal(out, ref), cfg

@@ -261,6 +261,41 @@ def golden_sampling():
     save("sampling", out)
 
 
+def golden_generation_loop():
+    """The reference's own GenerationMixin (generation_util.py:13-119) around a deterministic toy model: greedy and
+    sampled decoding (temperature / top-k / top-p wrappers, seeded torch.multinomial), EOS bookkeeping with one and
+    several end ids, pad ids for finished rows, left-padded prompts."""
+    from CleanTransformer.generation.generation_util import GenerationMixin
+
+    class Cfg:
+        n_layer = 2
+
+    torch.manual_seed(0)
+    emb = torch.randn(50, 50)
+
+    class Toy(GenerationMixin):
+        config = Cfg()
+
+        def __call__(self, ids, attention_mask=None, k_v_pasts=None, **kw):
+            n = attention_mask.sum(-1, keepdim=True).float()
+            logits = emb[ids] + 0.01 * n[:, :, None]
+            return (logits, logits), k_v_pasts
+
+    ids = torch.tensor([[0, 0, 5, 7], [0, 3, 4, 9], [1, 2, 3, 4]])
+    mask = torch.tensor([[0, 0, 1, 1], [0, 1, 1, 1], [1, 1, 1, 1]])
+    cases = [dict(beam_size=1, do_sample=False, max_gen_len=6, end_ids=None, pad_id=0),
+             dict(beam_size=1, do_sample=False, max_gen_len=6, end_ids=[13, 22], pad_id=0),
+             dict(beam_size=1, do_sample=False, max_gen_len=3, end_ids=41, pad_id=2),
+             dict(beam_size=1, do_sample=True, max_gen_len=5, end_ids=None, pad_id=0, temperature=0.7, top_k=5, top_p=0.9),
+             dict(beam_size=1, do_sample=True, max_gen_len=5, end_ids=None, pad_id=0, temperature=1.0, top_k=0, top_p=0.5),
+             dict(beam_size=1, do_sample=True, max_gen_len=5, end_ids=[7], pad_id=0)]
+    outs = []
+    for cfg in cases:
+        torch.manual_seed(123)
+        outs.append(Toy().generate(ids.clone(), attention_mask=mask.clone(), generation_configs=dict(cfg)))
+    save("generation_loop", {"emb": emb, "ids": ids, "mask": mask, "cases": cases, "outputs": outs, "seed": 123})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     if len(sys.argv) > 1:  # regenerate only the named fixtures: python tools/make_golden.py sampling
@@ -275,3 +310,4 @@ if __name__ == "__main__":
     golden_bert()
     golden_optim()
     golden_sampling()
+    golden_generation_loop()
