@@ -50,16 +50,27 @@ class BloomConfig():
         self.slow_but_exact = slow_but_exact
 
 
+_SLOPES = {}
+
+
 def alibi_slopes(num_heads, device=None):
-    """Per-head ALiBi slopes, modeling_bloom.py:313-326."""
+    """Per-head ALiBi slopes, modeling_bloom.py:313-326 — the reference's own sequence of fp32 tensor operations
+    (torch.pow of an fp32 base by int32 powers, on the mask's device), so the values are the ones the reference
+    multiplies with, not a higher-precision restatement that differs in the last bit for 12, 16, 20 … heads.
+    Cached per (heads, device)."""
+    key = (num_heads, str(device))
+    hit = _SLOPES.get(key)
+    if hit is not None:
+        return hit
     closest = 2 ** math.floor(math.log2(num_heads))
-    base = 2 ** (-(2 ** -(math.log2(closest) - 3)))
-    vals = [base ** i for i in range(1, closest + 1)]
+    base = torch.tensor(2 ** (-(2 ** -(math.log2(closest) - 3))), device=device, dtype=torch.float32)
+    slopes = torch.pow(base, torch.arange(1, 1 + closest, device=device, dtype=torch.int32))
     if closest != num_heads:
-        extra = 2 ** (-(2 ** -(math.log2(2 * closest) - 3)))
+        extra = torch.tensor(2 ** (-(2 ** -(math.log2(2 * closest) - 3))), device=device, dtype=torch.float32)
         n_rem = min(closest, num_heads - closest)
-        vals += [extra ** i for i in range(1, 2 * n_rem, 2)]
-    return torch.tensor(vals, dtype=torch.float32, device=device)
+        slopes = torch.cat([slopes, torch.pow(extra, torch.arange(1, 1 + 2 * n_rem, 2, device=device, dtype=torch.int32))], dim=0)
+    _SLOPES[key] = slopes
+    return slopes
 
 
 def build_alibi_tensor(attention_mask, num_heads, dtype):

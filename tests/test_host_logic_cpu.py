@@ -289,3 +289,20 @@ def test_generation_loop_matches_the_real_reference(golden):
         torch.manual_seed(g["seed"])
         out = Toy().generate(g["ids"].clone(), attention_mask=g["mask"].clone(), generation_configs=dict(cfg))
         assert out.shape == ref.shape and torch.equal(out, ref), cfg
+
+
+def test_alibi_tensor_is_bit_identical_to_the_reference_construction():
+    """modeling_bloom.build_alibi_tensor / alibi_slopes follow the reference's fp32 tensor arithmetic
+    (modeling_bloom.py:309-331) — also for head counts that are not powers of two and for the 12 / 16 / 20-head
+    cases where a higher-precision formula differs in the last bit. The oracle's restatement is pinned to the
+    reference by tests/test_oracle_golden.py."""
+    from cleantransformer_b200.models import modeling_bloom as mb
+    from oracle import ct_oracle as O
+    torch.manual_seed(0)
+    for heads in (1, 2, 4, 6, 8, 12, 16, 20, 25, 32, 40):
+        mask = (torch.rand(3, 11) > 0.3).long()
+        mask[0] = 1
+        mask[1, :4] = 0
+        for dtype in (torch.float32, torch.bfloat16):
+            assert torch.equal(mb.build_alibi_tensor(mask, heads, dtype), O.build_alibi_tensor(mask, heads, dtype)), heads
+        assert torch.equal(mb.alibi_slopes(heads), O.alibi_slopes(heads))
