@@ -446,3 +446,33 @@ def test_gpt_lm_gradients_vs_oracle(golden, version):
         assert float((p.grad - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-9, name
         checked += 1
     assert checked >= 20
+
+
+@pytest.mark.parametrize("pad", ["none", "right"])
+def test_bloom_block_accepts_the_reference_argument_tensors(golden, pad):
+    """BloomBlock.forward(hidden, attention_mask=bool [b,1,q,k], alibi=[b*h,1,k]) — the reference's own calling
+    convention (modeling_bloom.py:142-159, tensors built by BloomModel._attn_mask / build_alibi_tensor) — goes
+    through AttnBias.from_reference_args; output and both cache tensors against the oracle's block."""
+    from cleantransformer_b200.models import modeling_bloom as mb
+    from oracle import ct_oracle as O
+    g = golden("bloom_tiny")
+    cfg = g["cfg"]
+    nh = cfg["num_attention_heads"]
+    torch.manual_seed(41)
+    B, S, H = 2, 10, cfg["hidden_size"]
+    x = torch.randn(B, S, H)
+    mask = torch.ones(B, S, dtype=torch.long)
+    if pad == "right":
+        mask[1, 7:] = 0
+    alibi = O.build_alibi_tensor(mask, nh, torch.float32)
+    mask_bool = O.bloom_attn_mask(mask, (B, S))
+    sd = g["sd"]
+    with torch.no_grad():
+        ref, (k_ref, v_ref) = O.bloom_block(x, mask_bool, alibi, sd, "bloom.blocks.0.", nh, cfg["layer_norm_epsilon"])
+    with mock_ops.patched():
+        m = _bloom(g).eval()
+        with torch.no_grad():
+            out, (k, v) = m.bloom.blocks[0](x, attention_mask=mask_bool, alibi=alibi, head_mask=None)
+    valid = mask.bool()
+    assert rel_err(out[valid], ref[valid]) < 2e-4
+    assert rel_err(k, k_ref) < 2e-4 and rel_err(v, v_ref) < 2e-4
