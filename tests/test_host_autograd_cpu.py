@@ -476,3 +476,54 @@ def test_bloom_block_accepts_the_reference_argument_tensors(golden, pad):
     valid = mask.bool()
     assert rel_err(out[valid], ref[valid]) < 2e-4
     assert rel_err(k, k_ref) < 2e-4 and rel_err(v, v_ref) < 2e-4
+
+
+def _bloom_ddp_nosync_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cleantransformer_b200.ddp import DistributedDataParallel
+    from cleantransformer_b200.models import modeling_bloom as mb
+    cfg = dict(vocab_size=96, hidden_size=32, n_layer=1, num_attention_heads=4)
+    with mock_ops.patched():
+        torch.manual_seed(60)
+        m = mb.BloomForCausalLM(mb.BloomConfig(**cfg))
+        m._tie_weight(); m.train()
+        ddp = DistributedDataParallel(m, bucket_cap_mb=0.01)
+        torch.manual_seed(80 + rank)
+        batches = [torch.randint(3, 96, (2, 8)) for _ in range(2)]
+        local = []
+        for ids in batches:  # per-micro-batch local gradients of the same weights
+            for p in m.parameters():
+                p.grad = None
+            with ddp.no_sync():
+                (l, _, _), _ = ddp(input_ids=ids, attention_mask=torch.ones_like(ids), labels=ids)
+                l.backward()
+            local.append({n: p.grad.detach().clone() for n, p in m.named_parameters()})
+        for p in m.parameters():
+            p.grad = None
+        with ddp.no_sync():  # micro-batch 1: accumulate locally, nothing is exchanged
+            (l, _, _), _ = ddp(input_ids=batches[0], attention_mask=torch.ones_like(batches[0]), labels=batches[0])
+            l.backward()
+        (l, _, _), _ = ddp(input_ids=batches[1], attention_mask=torch.ones_like(batches[1]), labels=batches[1])
+        l.backward()               # micro-batch 2: accumulated gradients are averaged over the ranks
+        got = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    out[rank] = (got, {n: local[0][n] + local[1][n] for n in local[0]})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bloom_ddp_gradient_accumulation_with_no_sync():
+    """ft_bloom_DDP-style gradient accumulation: micro-batches under `no_sync()` stay local, the synchronising
+    backward reduces the ACCUMULATED gradients — mean over ranks of each rank's sum, tied table included."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_bloom_ddp_nosync_worker, args=(2, port, out), nprocs=2, join=True)
+    (g0, s0), (g1, s1) = out[0], out[1]
+    for n in g0:
+        assert torch.allclose(g0[n], g1[n]), n
+        assert rel_err(g0[n], (s0[n] + s1[n]) / 2) < 1e-5, n
