@@ -396,6 +396,15 @@ def lm_head_loss(hidden, weight, labels, shift=True):
     return lm_loss(logits, labels, shift=shift), logits
 
 
+def reject_head_mask(head_mask):
+    """The reference multiplies the softmax weights by `head_mask` when one is passed (transformer.py:48-50,
+    modeling_bloom.py:112-113, modeling_gpt.py:95-96); the fused kernels never materialise those weights. Refuse
+    instead of silently computing something else (same policy as dropout with p > 0)."""
+    if head_mask is not None:
+        raise NotImplementedError("head_mask is not supported by the fused attention kernels (the softmax weights are "
+                                  "never materialised); pass head_mask=None")
+
+
 def default_scale(head_dim):
     return 1.0 / math.sqrt(head_dim)
 

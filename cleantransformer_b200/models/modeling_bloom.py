@@ -130,6 +130,7 @@ class BloomAttentionLayer(torch.nn.Module):
             raise Exception("pretraining_tp and slow_but_exact not supported yet")
         if self.training and (self.attention_dropout.p > 0 or self.hidden_dropout > 0):
             raise NotImplementedError("Bloom dropout > 0 in training mode is not supported by the fused path")
+        F.reject_head_mask(head_mask)
         bsz, q_len, _ = hidden_states.shape
         bias = alibi if isinstance(alibi, AttnBias) else \
             AttnBias.from_reference_args(alibi, attention_mask, bsz, self.num_heads)
@@ -234,6 +235,7 @@ class BloomModel(torch.nn.Module):
         self.ln_f = LayerNorm(self.embed_dim, eps=config.layer_norm_epsilon)
 
     def forward(self, input_ids, attention_mask, head_mask, k_v_pasts=None):
+        F.reject_head_mask(head_mask)
         if k_v_pasts is None:
             k_v_pasts = [None] * self.config.n_layer
         emb = F.embedding_sum([input_ids], [self.word_embeddings.weight])

@@ -117,6 +117,7 @@ class AttentionLayer(torch.nn.Module):
         if self.training and (self.attn_dropout.p > 0 or self.resid_dropout.p > 0):
             raise NotImplementedError("GPT dropout > 0 in training mode is not supported by the fused "
                                       "path; call .eval() (the reference's own tests do, SURVEY §8 d2)")
+        F.reject_head_mask(head_mask)
         bsz, q_len, _ = hidden_states.shape
         head_dim = self.n_state // self.n_head
         sm_scale = 1.0 / math.sqrt(head_dim) if self.scale else 1.0

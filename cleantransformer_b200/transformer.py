@@ -75,6 +75,7 @@ class AttentionLayer(torch.nn.Module):
         if _dropout_active(self.dropout):
             raise NotImplementedError("attention-probability dropout with p>0 in training mode is not "
                                       "supported by the fused kernel; use eval() or p=0")
+        F.reject_head_mask(head_mask)
         b, s, _ = hidden_states.shape
         q = F.linear(hidden_states, self.q_linear.weight, self.q_linear.bias)
         k = F.linear(hidden_states, self.k_linear.weight, self.k_linear.bias)

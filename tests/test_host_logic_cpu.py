@@ -306,3 +306,22 @@ def test_alibi_tensor_is_bit_identical_to_the_reference_construction():
         for dtype in (torch.float32, torch.bfloat16):
             assert torch.equal(mb.build_alibi_tensor(mask, heads, dtype), O.build_alibi_tensor(mask, heads, dtype)), heads
         assert torch.equal(mb.alibi_slopes(heads), O.alibi_slopes(heads))
+
+
+def test_head_mask_is_refused_not_ignored():
+    """The reference scales the softmax weights by head_mask (transformer.py:48-50, modeling_bloom.py:112-113,
+    modeling_gpt.py:95-96); the fused kernels cannot, so a non-None head_mask must raise instead of being dropped."""
+    from cleantransformer_b200 import transformer as T
+    from cleantransformer_b200.models import modeling_bloom as mb, modeling_gpt as mg
+    hm = torch.ones(1)
+    x = torch.zeros(1, 4, 32)
+    with pytest.raises(NotImplementedError):
+        T.AttentionLayer(T.ExampleConfig()).eval()(torch.zeros(1, 4, T.ExampleConfig().hidden_size), None, hm)
+    bloom = mb.BloomForCausalLM(mb.BloomConfig(vocab_size=32, hidden_size=32, n_layer=1, num_attention_heads=2)).eval()
+    with pytest.raises(NotImplementedError):
+        bloom(input_ids=torch.zeros(1, 4, dtype=torch.long), attention_mask=torch.ones(1, 4, dtype=torch.long), head_mask=hm)
+    with pytest.raises(NotImplementedError):
+        bloom.bloom.blocks[0].self_attention(x, x, alibi=torch.zeros(2, 1, 4), head_mask=hm)
+    gpt = mg.AttentionLayer(mg.GPTConfig(vocab_size=32, n_embd=32, n_positions=8, n_layer=1, n_head=2, n_ctx=8)).eval()
+    with pytest.raises(NotImplementedError):
+        gpt(x, head_mask=hm)
