@@ -85,6 +85,7 @@ class ParamArena:
             if getattr(p, "_ct_shadow_view", None) is not None:
                 p._ct_shadow = p._ct_shadow_view
                 p._ct_shadow_ver = p._version
+                p._ct_shadow_ptr = p.data_ptr()
 
     def param_view(self, p, buf):
         o = p._ct_off

@@ -21,6 +21,7 @@
 // (W-1) * bytes inbound.
 #include "ct_common.cuh"
 #include "../../include/ct_b200.h"
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -72,15 +73,22 @@ __device__ __forceinline__ void st_peer_f4(float* p, float4 v) {
                : "memory");
 }
 
+// Upper bound on one peer-flag wait, in SM clock cycles; 0 = wait for ever (what NCCL does). Set once by
+// ct_comm_init from CT_COMM_TIMEOUT_S (default 1800 s: rank skew from a slow checkpoint write, a stalled data
+// loader or a debugger must not kill the job; a peer that is really gone still ends in a trap, not a hung node).
+__device__ long long g_wait_timeout_cycles = 0;
+
 __device__ __forceinline__ void wait_flags(const uint32_t* flags, int world, uint32_t epoch) {
-  // threads 0..world-1 poll one peer flag each; bounded so a lost peer traps instead of hanging
+  // threads 0..world-1 poll one peer flag each
   if ((int)threadIdx.x < world) {
+    const long long limit = g_wait_timeout_cycles;
     long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
-      if (clock64() - t0 > 40000000000LL) {  // ~20 s
-        printf("ct_b200 comm: rank flag wait timeout (peer %d epoch %u)\n", threadIdx.x, epoch);
+      if (limit > 0 && clock64() - t0 > limit) {
+        printf("ct_b200 comm: peer %d did not reach epoch %u within CT_COMM_TIMEOUT_S\n", threadIdx.x, epoch);
         __trap();
       }
+      __nanosleep(64);
     }
   }
   __syncthreads();
@@ -335,6 +343,14 @@ extern "C" int ct_comm_init(int rank, int world, int device, size_t data_bytes, 
   CT_CUDA_OK(cudaMemset(s, 0, sizeof(uint32_t) * (2 * MAX_WORLD + 8)));
   CT_CUDA_OK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)data_handle_out, d));
   CT_CUDA_OK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)sig_handle_out, s));
+  {
+    const char* e = getenv("CT_COMM_TIMEOUT_S");
+    const double secs = e ? atof(e) : 1800.0;
+    int khz = 2000000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    const long long cycles = secs > 0 ? (long long)(secs * 1e3 * (double)khz) : 0;
+    CT_CUDA_OK(cudaMemcpyToSymbol(g_wait_timeout_cycles, &cycles, sizeof(cycles)));
+  }
   g_comm.rank = rank; g_comm.world = world; g_comm.device = device;
   g_comm.data[rank] = d; g_comm.sig[rank] = s;
   g_comm.data_bytes = data_bytes;

@@ -21,9 +21,14 @@ __global__ void __launch_bounds__(256)
   const int lane = threadIdx.x & 31;
   if (w >= T) return;
   long long id = ids[w];
-  if (id < 0 || id >= V) id = 0;  // torch would raise; stay in bounds
-  const float* src = W + id * H;
   float* dst = out + w * H;
+  if (id < 0 || id >= V) {
+    // torch raises (device-side assert); no host sync here, so the row is poisoned instead: a tokenizer / vocab_size
+    // mismatch shows up as a NaN loss on the first step, not as silent training on row 0
+    for (int64_t c = lane; c < H; c += 32) dst[c] = __int_as_float(0x7fc00000);
+    return;
+  }
+  const float* src = W + id * H;
   if ((H & 3) == 0) {
     for (int64_t c = lane * 4; c < H; c += 128) {
       float4 v = *reinterpret_cast<const float4*>(src + c);
@@ -611,7 +616,8 @@ __global__ void __launch_bounds__(1024)
   if (threadIdx.x < 32) {
     float v = red[threadIdx.x];
     v = warp_sum(v);
-    if (threadIdx.x == 0) loss[0] = v / fmaxf(stats[0], 1.f);
+    // no valid target at all: 0/0 = NaN like torch.nn.CrossEntropyLoss (an all-masked batch must not look like loss 0)
+    if (threadIdx.x == 0) loss[0] = v / stats[0];
   }
 }
 

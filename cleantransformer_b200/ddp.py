@@ -131,6 +131,7 @@ class DistributedDataParallel(torch.nn.Module):
         self.buckets = plan_buckets(so, int(bucket_cap_mb * 1024 * 1024 // 4), solo)
         self._grad_off = {id(p): self.arena.offsets[i] for i, p in enumerate(self.arena.params) if id(p) in sparse_ids}
         self._early = {}
+        self._scatter_how = {}
         self._bucket_of = {}
         for bi, (_, _, idxs) in enumerate(self.buckets):
             for i in idxs:
@@ -176,11 +177,15 @@ class DistributedDataParallel(torch.nn.Module):
         return self.module(*args, **kwargs)
 
     def _begin_step(self):
+        if self._pending is None:  # the previous synchronised backward has finished (or this is the first step)
+            for p in self.arena.params:
+                p._ct_uses = 0     # functional.note_use counts this forward's uses = the writes to expect
         self._pending = [len(idxs) for (_, _, idxs) in self.buckets]
         self._launched = [False] * len(self.buckets)
         self._writes = {}
         self._cb_queued = False
         self._early = {}
+        self._scatter_how = {}
 
     # ---------------------------------------------------------------- gradient notifications
     def _on_autograd_grad(self, p):
@@ -198,20 +203,33 @@ class DistributedDataParallel(torch.nn.Module):
             torch.autograd.Variable._execution_engine.queue_callback(self._finish_backward)
         n = self._writes.get(id(p), 0) + 1
         self._writes[id(p)] = n
-        if id(p) in self._grad_off:
-            # tied table on the P2P path: write 1 = dense LM-head wgrad -> reduce now; write 2 must have gone
-            # through _sparse_embedding_bwd (which exchanged it), anything else would be lost
-            if n == 1:
-                self._early[id(p)] = "dense"
-                self._pending[self._bucket_of[id(p)]] -= 1
-                self._launch(self._bucket_of[id(p)])
-            elif self._early.get(id(p)) != "sparse":
-                raise RuntimeError("DistributedDataParallel: second gradient of a tied embedding table did not "
-                                   "come from EmbeddingFn (set CT_DDP_SPARSE_TIED=0 to reduce it densely)")
-            return
-        if n != getattr(p, "_ct_expected_writes", 1):
-            return
         bi = self._bucket_of[id(p)]
+        if id(p) in self._grad_off:
+            # tied table on the P2P path. A dense first write (the LM-head wgrad, first kernel of backward) is
+            # all-reduced at once; every later write must be a token scatter that _sparse_embedding_bwd exchanged
+            # across ranks itself (any number of them: GPT looks tokens_embed up twice with segment_ids,
+            # modeling_gpt.py:186-188). A scatter that arrives BEFORE any dense write stays local and the table takes
+            # the generic route below (dense all-reduce once every expected write is in).
+            how = self._scatter_how.pop(id(p), None)  # set by _sparse_embedding_bwd right before this notification
+            state = self._early.get(id(p))
+            if how == "exchanged":
+                return
+            if how is None and state is None and n == 1:
+                self._early[id(p)] = "dense"
+                self._pending[bi] -= 1
+                self._launch(bi)
+                return
+            if state == "dense":
+                raise RuntimeError("DistributedDataParallel: a dense gradient of a tied embedding table arrived "
+                                   "after its early all-reduce was launched (set CT_DDP_SPARSE_TIED=0 to reduce the "
+                                   "table once, densely, at the end of backward)")
+            self._early[id(p)] = "local"
+        if self._launched[bi]:
+            raise RuntimeError("DistributedDataParallel: a gradient was written after its bucket had been "
+                               "all-reduced (parameter used more often in backward than its forward announced)")
+        expected = getattr(p, "_ct_uses", 0) or getattr(p, "_ct_expected_writes", 1)
+        if n != expected:
+            return
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
             self._launch(bi)
@@ -304,6 +322,8 @@ class DistributedDataParallel(torch.nn.Module):
             # not inside a synchronised backward (no_sync / plain use), or the table saw no dense gradient
             # first: local scatter; with a pending dense reduction of this bucket it is picked up there
             ops.embedding_bwd(ids, dout, grad, padding_idx)
+            if self._pending is not None:
+                self._scatter_how[id(param)] = "local"
             return
         T, H = ids.numel(), dout.shape[-1]
         if grad.data_ptr() != param._ct_grad_view.data_ptr():
@@ -324,7 +344,7 @@ class DistributedDataParallel(torch.nn.Module):
                 "ct_embedding_bwd_allranks")
         dout.record_stream(self._comm_stream)
         ids.record_stream(self._comm_stream)
-        self._early[id(param)] = "sparse"
+        self._scatter_how[id(param)] = "exchanged"
 
     def _finish_backward(self):
         # gradients that never arrived (unused parameters) or multi-use parameters still pending:

@@ -39,7 +39,7 @@ def shadow(param, dtype=None):
         return param.detach()
     sh = getattr(param, "_ct_shadow", None)
     if sh is not None and sh.dtype == dtype and getattr(param, "_ct_shadow_ver", -1) == param._version \
-            and sh.device == param.device:
+            and getattr(param, "_ct_shadow_ptr", 0) == param.data_ptr() and sh.device == param.device:
         return sh
     target = getattr(param, "_ct_shadow_view", None)
     if target is not None and (target.dtype != dtype or target.device != param.device):
@@ -47,7 +47,18 @@ def shadow(param, dtype=None):
     sh = ops.cast(param.detach(), dtype, out=target)
     param._ct_shadow = sh
     param._ct_shadow_ver = param._version
+    param._ct_shadow_ptr = param.data_ptr()
     return sh
+
+
+def invalidate_shadows(module_or_params):
+    """Forget the cached low-precision copies. The cache is keyed on (`param._version`, `param.data_ptr()`): in-place
+    updates through the parameter itself and `p.data = ...` re-pointing are noticed, but a write through `p.data`
+    (`p.data.copy_()`, `p.data.mul_()`: weight surgery, EMA, a foreign optimizer) bumps neither — call this after one.
+    The optimizers and the DDP wrapper of this package do it themselves."""
+    params = module_or_params.parameters() if hasattr(module_or_params, "parameters") else module_or_params
+    for p in params:
+        p._ct_shadow_ver = -1
 
 
 def grad_buffer(param):
@@ -62,6 +73,17 @@ def grad_buffer(param):
     return view, False
 
 
+def note_use(*params):
+    """Forward-side count of how many gradient writes a parameter will receive in the coming backward (one per
+    use in a Function of this module). The DDP wrapper compares it with the writes it has seen to decide when a
+    bucket is complete: a table looked up twice (GPT `segment_ids`, modeling_gpt.py:186-188), a shared module or a
+    tied head all work without a declared count. (Called from inside Function.forward, where grad mode is always
+    off — so no grad-mode test here; the wrapper resets the counters at the start of each synchronised forward.)"""
+    for p in params:
+        if p is not None and p.requires_grad:
+            p._ct_uses = getattr(p, "_ct_uses", 0) + 1
+
+
 def grad_written(param):
     """Tell listeners (the DDP wrapper) that a kernel producing this gradient has been enqueued."""
     hooks = getattr(param, "_ct_grad_hooks", None)
@@ -72,6 +94,22 @@ def grad_written(param):
 
 def _as2d(x):
     return x.reshape(-1, x.shape[-1])
+
+
+def _anchor(params, *tensors):
+    """Parameters never enter autograd as inputs of these Functions: their gradients are written in place
+    (grad_buffer), so an edge to the parameter's AccumulateGrad node would carry nothing — but the engine still visits
+    that node and, at the end of backward, synchronises the caller's stream with the stream the node was CREATED on.
+    A node kept alive by an older graph (any loss tensor still referenced) then ties a CUDA-graph capture to
+    uncaptured work on another stream (cudaErrorStreamCaptureIsolation). So parameters travel in a tuple, and when no
+    tensor input requires grad (embedding of integer ids, first Linear on raw features) a fresh zero-size leaf —
+    created on the current stream — makes autograd build the node."""
+    if not torch.is_grad_enabled() or any(t is not None and t.requires_grad for t in tensors):
+        return None
+    for p in params:
+        if p is not None and p.requires_grad:
+            return torch.empty(0, device=p.device, requires_grad=True)
+    return None
 
 
 def _low(x, dtype):
@@ -88,8 +126,10 @@ class LayerNormFn(torch.autograd.Function):
     (e.g. f32 for the residual stream + bf16 for the next GEMM)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, out_dtype, out2_dtype):
+    def forward(ctx, x, wb, eps, out_dtype, out2_dtype, anchor):
+        weight, bias = wb
         need = x.requires_grad or weight.requires_grad or bias.requires_grad
+        note_use(weight, bias)
         w = weight.detach().reshape(-1)
         b = bias.detach().reshape(-1)
         y, y2, mean, rstd = ops.layernorm_fwd(x.detach(), w, b, eps, out_dtype, out2_dtype, save_stats=need)
@@ -123,7 +163,7 @@ class LayerNormFn(torch.autograd.Function):
 
 
 def layer_norm(x, weight, bias, eps, out_dtype=None, out2_dtype=None):
-    return LayerNormFn.apply(x, weight, bias, eps, out_dtype or x.dtype, out2_dtype)
+    return LayerNormFn.apply(x, (weight, bias), eps, out_dtype or x.dtype, out2_dtype, _anchor((weight, bias), x))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -133,7 +173,8 @@ class LinearFn(torch.autograd.Function):
     """y = act(x @ W^T + b) (+ residual). W: nn.Linear [out,in] or Conv1D [in,out] (w_in_out)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, residual, out_dtype, w_in_out):
+    def forward(ctx, x, wb, act, residual, out_dtype, w_in_out, anchor):
+        weight, bias = wb
         cd = compute_dtype()
         x2 = _low(_as2d(x.detach()), cd)
         w16 = shadow(weight, cd)
@@ -141,6 +182,7 @@ class LinearFn(torch.autograd.Function):
         need = x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad) or \
             (residual is not None and residual.requires_grad)
         res2 = _as2d(residual.detach()).contiguous() if residual is not None else None
+        note_use(weight, bias)
         y, pre = ops.linear_fwd(x2, w16, bias.detach() if bias is not None else None, act, res2, out_dtype,
                                 save_preact=(act != ops.ACT_NONE and need), w_in_out=w_in_out)
         ctx.save_for_backward(x2, pre)
@@ -183,13 +225,13 @@ class LinearFn(torch.autograd.Function):
         if ctx.x_req:
             dx = ops.linear_dgrad(d2, shadow(weight, cd), out_dtype=ctx.x_dtype, w_in_out=ctx.w_in_out)
             dx = dx.view(ctx.x_shape)
-        return dx, None, None, None, dres, None, None
+        return dx, None, None, dres, None, None, None
 
 
 def linear(x, weight, bias=None, act=ops.ACT_NONE, residual=None, out_dtype=None, w_in_out=False):
     if out_dtype is None:
         out_dtype = residual.dtype if residual is not None else compute_dtype()
-    return LinearFn.apply(x, weight, bias, act, residual, out_dtype, w_in_out)
+    return LinearFn.apply(x, (weight, bias), act, residual, out_dtype, w_in_out, _anchor((weight, bias), x, residual))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -283,9 +325,7 @@ class EmbeddingFn(torch.autograd.Function):
     weight.grad."""
 
     @staticmethod
-    def forward(ctx, n_tables, padding_idx0, *args):
-        ids = args[:n_tables]
-        weights = args[n_tables:]
+    def forward(ctx, ids, weights, padding_idx0, anchor):
         shape = torch.broadcast_shapes(*[i.shape for i in ids])
         out = None
         for i, w in zip(ids, weights):
@@ -293,6 +333,7 @@ class EmbeddingFn(torch.autograd.Function):
             out = ops.embedding_fwd(i, w.detach(), out, accumulate=out is not None)
         ctx.ids = [i.expand(shape).contiguous() for i in ids]
         ctx.weights = weights
+        note_use(*weights)
         ctx.padding_idx0 = padding_idx0
         return out
 
@@ -314,11 +355,11 @@ class EmbeddingFn(torch.autograd.Function):
             else:
                 ops.embedding_bwd(i, dout, g, pad)
             grad_written(w)
-        return (None, None) + (None,) * (2 * len(ctx.ids))
+        return None, None, None, None
 
 
 def embedding_sum(ids_list, weight_list, padding_idx0=-1):
-    return EmbeddingFn.apply(len(ids_list), padding_idx0, *ids_list, *weight_list)
+    return EmbeddingFn.apply(tuple(ids_list), tuple(weight_list), padding_idx0, _anchor(weight_list))
 
 
 class LMLossFn(torch.autograd.Function):
@@ -357,13 +398,15 @@ class LMHeadLossFn(torch.autograd.Function):
     the node back-propagates the loss). Opt-in (CT_FUSED_LM_STATS=1): not yet run on a GPU."""
 
     @staticmethod
-    def forward(ctx, hidden, weight, labels, shift):
+    def forward(ctx, hidden, wb, labels, shift, anchor):
+        weight = wb[0]
         cd = compute_dtype()
         B, S, H = hidden.shape
         x2 = _low(_as2d(hidden.detach()), cd)
         w16 = shadow(weight, cd)
         logits, stats = ops.lm_head_logits_with_stats(x2, w16)
         need = hidden.requires_grad or weight.requires_grad
+        note_use(weight)
         loss, dl = ops.cross_entropy_fwd_stats(logits, labels.reshape(-1), stats, S=S, shift=shift, want_dlogits=need)
         ctx.save_for_backward(x2, dl)
         ctx.weight = weight
@@ -384,14 +427,14 @@ class LMHeadLossFn(torch.autograd.Function):
         dx = None
         if ctx.x_req:
             dx = ops.linear_dgrad(dl, shadow(weight, x2.dtype), out_dtype=ctx.x_dtype).view(ctx.x_shape)
-        return dx, None, None, None
+        return dx, None, None, None, None
 
 
 def lm_head_loss(hidden, weight, labels, shift=True):
     """(loss, logits) of the tied LM head; the fused-statistics node when it is enabled and the shape allows it."""
     B, S, H = hidden.shape
     if FUSED_LM_STATS and ops.lm_head_stats_ok(B * S, weight.shape[0], compute_dtype()):
-        return LMHeadLossFn.apply(hidden, weight, labels, shift)
+        return LMHeadLossFn.apply(hidden, (weight,), labels, shift, _anchor((weight,), hidden))
     logits = linear(hidden, weight)
     return lm_loss(logits, labels, shift=shift), logits
 
@@ -455,6 +498,8 @@ class PreLNBlockFn(torch.autograd.Function):
                               first_valid)
         ctx.spec = spec
         ctx.shape = (B, S, H)
+        for name in ("ln1", "qkv", "proj", "ln2", "fc1", "fc2"):
+            note_use(spec[name].weight, spec[name].bias)
         ctx.mark_non_differentiable(k, v)
         ctx.set_materialize_grads(False)  # no zero-filled [B,H,S,D] gradients for the k/v outputs
         return out.view(B, S, H), k, v

@@ -158,7 +158,7 @@ class TorchAdamW(torch.optim.Optimizer):
         for p in ps:
             st = self.state[p]
             if "step" not in st:
-                st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                st["step"] = torch.tensor(0.0, dtype=torch.float32, device="cpu")  # never on the GPU: step() reads it
                 if a is not None:
                     st["exp_avg"] = a.param_view(p, a.exp_avg)
                     st["exp_avg_sq"] = a.param_view(p, a.exp_avg_sq)
@@ -187,7 +187,7 @@ class TorchAdamW(torch.optim.Optimizer):
                     view.copy_(cur.to(device=view.device, dtype=view.dtype).reshape(view.shape))
                     st[key] = view
             if not torch.is_tensor(st.get("step")):
-                st["step"] = torch.tensor(float(st.get("step", 0)), dtype=torch.float32)
+                st["step"] = torch.tensor(float(st.get("step", 0)), dtype=torch.float32, device="cpu")
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)

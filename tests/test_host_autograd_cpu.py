@@ -527,3 +527,58 @@ def test_bloom_ddp_gradient_accumulation_with_no_sync():
     for n in g0:
         assert torch.allclose(g0[n], g1[n]), n
         assert rel_err(g0[n], (s0[n] + s1[n]) / 2) < 1e-5, n
+
+
+def _gpt_segment_ddp_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cleantransformer_b200.ddp import DistributedDataParallel
+    from cleantransformer_b200.models import modeling_gpt as mg
+    cfg = dict(vocab_size=80, n_embd=32, n_positions=16, n_layer=2, n_head=4, n_ctx=16, embd_pdrop=0.0,
+               attn_pdrop=0.0, resid_pdrop=0.0)
+    with mock_ops.patched():
+        torch.manual_seed(11)
+        m = mg.GPTLMHeadModel(mg.GPTConfig(**cfg), version="gpt2").eval()  # eval: Dropout(0.5) of the MLP (gpt:136)
+        ddp = DistributedDataParallel(m, bucket_cap_mb=0.005)
+        torch.manual_seed(90 + rank)
+        ids = torch.randint(1, 80, (2, 10))
+        seg = torch.randint(1, 80, (2, 10))       # modeling_gpt.py:186-188: segment ids index tokens_embed again
+        mask = torch.ones_like(ids)
+
+        def loss_of(model):
+            (logits, _), _ = model(ids, attention_mask=mask, segment_ids=seg)
+            return torch.nn.functional.cross_entropy(logits.float().view(-1, 80), ids.view(-1))
+
+        for _ in range(2):
+            for p in m.parameters():
+                p.grad = None
+            loss_of(ddp).backward()
+        table = m.gpt.tokens_embed.weight
+        assert table._ct_uses == 3                # lm_head + token lookup + segment lookup, counted in forward
+        reduced = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+        ref = mg.GPTLMHeadModel(mg.GPTConfig(**cfg), version="gpt2").eval()
+        ref.load_state_dict({k[len("module."):]: v for k, v in ddp.state_dict().items()})
+        ref._tie_weights()
+        loss_of(ref).backward()
+        local = {n: p.grad.detach().clone() for n, p in ref.named_parameters()}
+    out[rank] = (reduced, local)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gpt_segment_ids_ddp_world2_gloo_counts_three_writes_of_the_tied_table():
+    """with `segment_ids` GPTModel looks tokens_embed up twice, so the tied table receives three gradient
+    writes; the wrapper must reduce it after the third (a static `_ct_expected_writes = 2` reduced it one write
+    early and the last contribution stayed local)."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gpt_segment_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+    (r0, l0), (r1, l1) = out[0], out[1]
+    for n in r0:
+        assert torch.allclose(r0[n], r1[n]), n
+        assert rel_err(r0[n], (l0[n] + l1[n]) / 2) < 1e-5, n

@@ -227,22 +227,31 @@ def test_copy_engine_allreduce_plan_tiles_every_piece():
 
 
 def test_ddp_tied_table_state_machine():
-    """ddp._on_grad_written for a tied token table on the peer-memory path: the first gradient (dense LM-head wgrad)
-    launches the table's own bucket at once, the second must have gone through the sparse exchange — anything else
-    (a gradient that would silently stay local) is an error; ordinary parameters count down their bucket."""
+    """ddp._on_grad_written for a tied token table on the peer-memory path: a dense FIRST gradient (LM-head wgrad)
+    launches the table's own bucket at once; later token scatters exchanged by _sparse_embedding_bwd need no launch,
+    however many there are (GPT looks tokens_embed up twice with segment_ids, modeling_gpt.py:186-188: three writes);
+    a scatter that arrives first stays local and the table is reduced densely once the forward's use count is reached;
+    a dense gradient after the early launch, or any write after its bucket was reduced, is an error; ordinary
+    parameters count down their bucket against the use count announced by functional.note_use."""
     from cleantransformer_b200.ddp import DistributedDataParallel as D
     d = object.__new__(D)
     torch.nn.Module.__init__(d)
     tied, plain_a, plain_b = [torch.nn.Parameter(torch.zeros(4, 4)) for _ in range(3)]
-    tied._ct_expected_writes = 2
     launched = []
-    d._launch = lambda bi, final=False: launched.append(bi)
+
+    def launch(bi, final=False):
+        launched.append(bi)
+        d._launched[bi] = True
+
+    d._launch = launch
     d._bucket_of = {id(tied): 0, id(plain_a): 1, id(plain_b): 1}
     d._grad_off = {id(tied): 0}
     d.require_backward_grad_sync = True
 
-    def begin():
+    def begin(tied_uses=3, a_uses=1):
         d._pending, d._launched, d._writes, d._cb_queued, d._early = [1, 2], [False, False], {}, True, {}
+        d._scatter_how = {}
+        tied._ct_uses, plain_a._ct_uses, plain_b._ct_uses = tied_uses, a_uses, 0   # plain_b: torch-autograd gradient
         launched.clear()
 
     begin()
@@ -252,13 +261,27 @@ def test_ddp_tied_table_state_machine():
     assert launched == [0] and d._pending[1] == 1
     d._on_grad_written(plain_b)
     assert launched == [0, 1]
-    d._early[id(tied)] = "sparse"                  # what _sparse_embedding_bwd records after the exchange
-    d._on_grad_written(tied)                       # embedding scatter: nothing left to launch
+    for _ in range(2):                             # token scatter + segment scatter, both exchanged across ranks
+        d._scatter_how[id(tied)] = "exchanged"     # what _sparse_embedding_bwd records right before the notification
+        d._on_grad_written(tied)
     assert launched == [0, 1]
+    with pytest.raises(RuntimeError):              # a write after its bucket was all-reduced would be lost
+        d._on_grad_written(plain_a)
     begin()
     d._on_grad_written(tied)
-    with pytest.raises(RuntimeError):              # second contribution did not come through the sparse exchange
+    with pytest.raises(RuntimeError):              # second DENSE contribution after the early all-reduce
         d._on_grad_written(tied)
+    begin(tied_uses=2)
+    d._scatter_how[id(tied)] = "local"             # scatter first (no dense gradient yet): stays local ...
+    d._on_grad_written(tied)
+    assert launched == [] and d._early[id(tied)] == "local"
+    d._on_grad_written(tied)                       # ... and the table is reduced densely once both writes are in
+    assert launched == [0]
+    begin(a_uses=2)                                # a module used twice: reduce after the second write only
+    d._on_grad_written(plain_a)
+    assert d._pending[1] == 2
+    d._on_grad_written(plain_a); d._on_grad_written(plain_b)
+    assert launched == [1]
     begin()
     d.require_backward_grad_sync = False           # no_sync(): gradients stay local, nothing is launched
     d._on_grad_written(tied); d._on_grad_written(plain_a)
