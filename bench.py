@@ -43,9 +43,13 @@ def parse():
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true",
-                    help="replay forward+backward from one CUDA graph (cleantransformer_b200.graphs; single GPU, "
-                         "experimental: not yet run on a GPU)")
+    ap.add_argument("--no-eager-baseline", action="store_true",
+                    help="skip the in-run timing of the reference's eager-PyTorch path on the same GPUs")
+    ap.add_argument("--eager-steps", type=int, default=5)
+    ap.add_argument("--graph", action="store_true", help="(default on a single GPU) replay forward+backward from one "
+                    "CUDA graph (cleantransformer_b200.graphs)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel")
+    ap.add_argument("--no-kernel-table", action="store_true", help="skip the per-kernel roofline pass")
     ap.add_argument("--comm", default=None, help="p2p (default), nccl (baseline collective) or ce (copy-engine transport, experimental)")
     return ap.parse_args()
 
@@ -140,55 +144,49 @@ def cpu_reference_step_fn(layers, seq, seed=999):
     return step
 
 
+CPU_SAMPLE_SEQ = 256  # bounded CPU sample: B=1, S=256, all layers, full vocabulary (tokens/s on CPU is ~S-insensitive)
+
+
 def run_reference_arm(args):
+    """The reference's CPU path (oracle port: the reference is pure Python over PyTorch, there is nothing to compile
+    into oracle/_ref) with every host thread, on a bounded sample of the same workload: B=1, S=256 per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
-    step = cpu_reference_step_fn(args.layers, args.seq)
-    S = min(args.seq, 256)
-    t0 = time.time(); step(S); t1 = time.time() - t0
-    t1 = t1 * args.seq / S
-    # bound the whole run to ~3 minutes by shortening the per-step sample (tokens/s on CPU is ~S-insensitive)
-    budget = 170.0
-    while S > 64 and t1 * (S / args.seq) * (args.steps + max(args.warmup - 1, 0)) > budget:
-        S //= 2
-    for _ in range(max(args.warmup - 1, 0)):
+    S = min(args.seq, CPU_SAMPLE_SEQ)
+    step = cpu_reference_step_fn(args.layers, S)
+    for _ in range(max(args.warmup, 1)):
         step(S)
     t0 = time.time()
     for _ in range(args.steps):
         step(S)
     dt = time.time() - t0
     toks = S * args.steps / dt
-    sample = "B=1,S=%d,%d layers,fp32: fwd+bwd+AdamW per step (oracle port of the reference on host cores)" % (S, args.layers)
+    sample = "B=1,S=%d,%d layers,V=250880,fp32: fwd+bwd+AdamW per step (oracle port of the reference on host cores)" % (S, args.layers)
     line = {"impl": "reference", "metric": "Bloom-560M SFT tokens/sec", "value": toks, "unit": "tokens/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1000 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Bloom-560M SFT step (configs[1])", "global_batch": 1, "seq_len": S,
-                       "layers": args.layers, "parallelism": "cpu"},
+            "config": {"workload": "Bloom-560M SFT step (configs[1]), bounded CPU sample B=1 S=%d" % S, "global_batch": 1,
+                       "seq_len": S, "layers": args.layers, "parallelism": "cpu"},
             "cpu_baseline": {"value": toks, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": toks, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-
 # ------------------------------------------------------------------------------------------------
-# extra arm: the reference's own eager path on the same GPUs (what examples/ft_bloom*.py run)
+# the reference's own eager path on the same GPUs (what examples/ft_bloom*.py run): north_star's "number to beat"
 # ------------------------------------------------------------------------------------------------
-def run_eager_arm(args):
-    """oracle/ct_oracle.py is an op-for-op restatement of the reference modules in plain PyTorch, so
-    running it on the GPU under torch.autocast(bfloat16) with torch.optim.AdamW (and torch DDP for
-    N > 1) is the reference's eager path; /root/reference itself does not exist on the GPU box."""
+def eager_time(args, dev, world, rank, local, steps, warmup):
+    """oracle/ct_oracle.py is an op-for-op restatement of the reference modules in plain PyTorch (pinned to the real
+    reference by tests/test_oracle_golden.py), so running it on the GPU under torch.autocast(bfloat16) with
+    torch.optim.AdamW (ft_bloom.py:70) and torch DDP/NCCL for N > 1 (ft_bloom_DDP.py:99) IS the reference's eager
+    path; /root/reference itself does not exist on the GPU box. Same B, S, layers, vocabulary as our arm.
+    Returns {"value": tokens/s, "ms_per_step": ...}; the process group must already exist for world > 1."""
     import torch.distributed as dist
     from oracle import ct_oracle as O
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     H, V, nh, L = BLOOM_560M["hidden_size"], BLOOM_560M["vocab_size"], 16, args.layers
     torch.manual_seed(999)
 
@@ -232,14 +230,14 @@ def run_eager_arm(args):
         opt.step()
         return loss
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = step()
     e1.record()
     if world > 1:
@@ -248,16 +246,165 @@ def run_eager_arm(args):
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t)
+    out = {"value": B * S * world * steps / (ms * 1e-3), "unit": "tokens/s", "ms_per_step": ms / steps, "steps": steps,
+           "warmup": max(warmup, 3), "loss": float(loss),
+           "what": "the reference's eager-PyTorch arithmetic (oracle restatement) under torch.autocast(bfloat16), "
+                   "torch.optim.AdamW" + (", torch DDP over NCCL" if world > 1 else "") +
+                   ", same B=%d S=%d layers=%d V=%d, CUDA-event timed, max over ranks" % (B, S, L, V)}
+    del model, net, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_eager_arm(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    r = eager_time(args, dev, world, rank, local, args.steps, args.warmup)
     if rank == 0:
-        print(json.dumps({"impl": "eager", "metric": "Bloom-560M SFT tokens/sec", "value": B * S * world * args.steps / (ms * 1e-3),
+        print(json.dumps({"impl": "eager", "metric": "Bloom-560M SFT tokens/sec", "value": r["value"],
                           "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "dtype": "bf16 autocast",
-                          "data": "synthetic", "loss": float(loss),
-                          "config": {"workload": "Bloom-560M SFT step: reference eager-PyTorch path (oracle restatement), "
-                                                 "torch.optim.AdamW" + (", torch DDP/NCCL" if world > 1 else ""),
-                                     "global_batch": B * world, "seq_len": S, "layers": L}}), flush=True)
+                          "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "dtype": "bf16 autocast",
+                          "data": "synthetic", "loss": r["loss"],
+                          "config": {"workload": "Bloom-560M SFT step: " + r["what"],
+                                     "global_batch": args.batch * world, "seq_len": args.seq, "layers": args.layers}}), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# per-kernel roofline table: CUDA events around every C-ABI call of an instrumented (un-graphed) step
+# ------------------------------------------------------------------------------------------------
+class KernelProfiler:
+    """Wraps the tensor-level entry points of cleantransformer_b200.ops with CUDA events and attributes to each call its
+    ALGORITHMIC work (flop for the tensor-core kernels, bytes for the HBM-bound ones; DESIGN.md §5 states the formulas).
+    Events are recorded on the calling stream; backward runs on autograd's thread but on the same stream."""
+
+    def __init__(self, ops):
+        self.ops, self.rows, self.saved = ops, [], {}
+        self.lock = threading.Lock()
+
+    @staticmethod
+    def _nbytes(*ts):
+        return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+    def _wrap(self, name, work_fn):
+        orig = getattr(self.ops, name)
+        self.saved[name] = orig
+        prof = self
+
+        def wrapped(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig(*a, **kw)
+            e1.record()
+            try:
+                role, work, unit = work_fn(out, *a, **kw)
+            except Exception:  # noqa: BLE001 — attribution must never break the step
+                role, work, unit = name, 0.0, "B"
+            with prof.lock:
+                prof.rows.append((role, work, unit, e0, e1))
+            return out
+
+        setattr(self.ops, name, wrapped)
+
+    def start(self):
+        ops, nb = self.ops, self._nbytes
+
+        def gemm(out, A, B, M, N, K, a_mn=False, b_mn=False, **kw):
+            kind = "wgrad" if (a_mn and b_mn) else ("dgrad" if b_mn else "fwd")
+            epi = ("+gelu" if kw.get("act") else "") + ("+res" if kw.get("residual") is not None else "") + \
+                  ("*act'" if kw.get("actgrad_src") is not None else "") + ("+rowstats" if kw.get("row_stats") is not None else "")
+            return "gemm %s M=%d N=%d K=%d%s" % (kind, M, N, K, epi), 2.0 * M * N * K, "flop"
+
+        def attn_fwd(out, q, k, v, scale, causal=False, *a, **kw):
+            B, H, Sq, D = q.shape
+            return "attention forward", 4.0 * B * H * Sq * k.shape[2] * D * (0.5 if causal else 1.0), "flop"
+
+        def attn_bwd(out, dout, q, k, v, o, lse2, dq, dk, dv, scale, causal=False, *a, **kw):
+            B, H, Sq, D = q.shape
+            return ("attention backward (incl. delta, dQ convert)",
+                    10.0 * B * H * Sq * k.shape[2] * D * (0.5 if causal else 1.0), "flop")
+
+        def ln_fwd(out, x, gamma, beta, eps, out_dtype=None, out2_dtype=None, save_stats=True):
+            return "LayerNorm forward", nb(x, out[0], out[1]), "B"
+
+        def ln_bwd(out, dy, x, *a, **kw):
+            outs = out if isinstance(out, tuple) else (out,)
+            return "LayerNorm backward (+residual add, bf16 copy, bias column sums)", \
+                nb(dy, x, kw.get("dy2"), kw.get("dx_add"), *outs), "B"
+
+        def adamw(out, p, g, m, v, *a, **kw):
+            return "AdamW (flat arena, bf16 shadow)", nb(p, g, m, v) + nb(p, m, v) + nb(kw.get("shadow")), "B"
+
+        def ce(out, logits2d, *a, **kw):
+            return "cross entropy (loss + dlogits)", nb(logits2d, out[1]), "B"
+
+        def colsum(out, x2d, o, accumulate):
+            return "bias gradient column sums", nb(x2d), "B"
+
+        def cast(out, src, dtype, out_=None):
+            return "casts", nb(src, out), "B"
+
+        def emb_f(out, ids, weight, *a, **kw):
+            return "embedding gather / scatter", nb(out) * 2, "B"
+
+        def emb_b(out, ids, dout, dweight, *a, **kw):
+            return "embedding gather / scatter", nb(dout) * 2, "B"
+
+        for name, fn in (("gemm", gemm), ("attn_fwd", attn_fwd), ("attn_bwd", attn_bwd), ("layernorm_fwd", ln_fwd),
+                         ("layernorm_bwd", ln_bwd), ("adamw_step", adamw), ("cross_entropy_fwd", ce),
+                         ("cross_entropy_fwd_stats", ce), ("colsum", colsum), ("cast", cast),
+                         ("embedding_fwd", emb_f), ("embedding_bwd", emb_b)):
+            self._wrap(name, fn)
+
+    def stop(self):
+        for name, orig in self.saved.items():
+            setattr(self.ops, name, orig)
+        self.saved = {}
+
+    def table(self, steps, peaks):
+        tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        agg = {}
+        for role, work, unit, e0, e1 in self.rows:
+            r = agg.setdefault(role, {"launches": 0, "ms": 0.0, "work": 0.0, "unit": unit})
+            r["launches"] += 1; r["ms"] += e0.elapsed_time(e1); r["work"] += work
+        total = sum(r["ms"] for r in agg.values()) or 1.0
+        out = []
+        for role, r in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            row = {"role": role, "launches_per_step": r["launches"] / steps, "ms_per_step": r["ms"] / steps,
+                   "share": r["ms"] / total}
+            if r["work"] > 0 and r["ms"] > 0:
+                if r["unit"] == "flop":
+                    ach = r["work"] / (r["ms"] * 1e-3) / 1e12
+                    row.update(achieved=ach, unit="TFLOP/s", peak=tf_peak, frac=ach / tf_peak)
+                else:
+                    ach = r["work"] / (r["ms"] * 1e-3) / 1e9
+                    row.update(achieved=ach, unit="GB/s", peak=hbm_peak, frac=ach / hbm_peak)
+            out.append(row)
+        return out, total / steps
+
+
+def recorded_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's largest launch, from the committed ncu
+    capture of THIS build (profiles/r02_ncu_traffic.json holds the sha1 of the kernel's source next to the bytes): a
+    number from another build is not reported — null instead."""
+    import hashlib
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    try:
+        rec = json.load(open(path))[kernel]
+        src = os.path.join(ROOT, "cleantransformer_b200", "csrc", rec["source"])
+        if hashlib.sha1(open(src, "rb").read()).hexdigest() == rec["source_sha1"]:
+            return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"]), rec.get("capture")
+    except Exception:  # noqa: BLE001
+        pass
+    return None, None
+
 
 # ------------------------------------------------------------------------------------------------
 # our arm
@@ -300,6 +447,7 @@ def main():
     if world > 1:
         net = DistributedDataParallel(model, device_ids=[local], comm=args.comm)
     optimizer = TorchAdamW(net.parameters(), lr=1e-5)
+    use_graph = (world == 1 and not args.no_graph) or args.graph
 
     B, S = args.batch, args.seq
     g = torch.Generator().manual_seed(999 + rank)
@@ -347,8 +495,9 @@ def main():
         l_before = ops.LAUNCHES[0]
         loss = step_resident()
         launches_per_eager_step = ops.LAUNCHES[0] - l_before
+    del loss  # (a live loss tensor keeps its autograd graph, not a problem any more — see functional._anchor)
     step_eager = step_resident
-    if args.graph:
+    if use_graph:
         if world > 1:
             raise SystemExit("--graph: single GPU only (peer-memory collectives cannot be replayed)")
         from cleantransformer_b200.graphs import GraphedTrainStep
@@ -373,7 +522,7 @@ def main():
     l0 = ops.LAUNCHES[0]
     ms, loss = timed(step_resident, args.steps)
     launches = ops.LAUNCHES[0] - l0
-    if args.graph:  # the replayed graph launches the same kernels as the eager step it was captured from
+    if use_graph:  # the replayed graph launches the same kernels as the eager step it was captured from (+ AdamW, counted)
         launches = launches_per_eager_step * args.steps
     for _ in range(2):
         step_e2e()
@@ -381,23 +530,42 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # roofline pass: per-launch CUDA-event timing of the dominant kernel (tcgen05 GEMM) over 2 more steps
-    ops.GEMM_PROFILE = []
-    barrier()
-    for _ in range(2):
-        step_eager()  # (kernel by kernel also under --graph: the per-launch events need individual launches)
-    torch.cuda.synchronize()
-    prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
-    flop = sum(2.0 * m * n * k for (m, n, k, _, _) in prof)
-    gms = sum(a.elapsed_time(b) for (_, _, _, a, b) in prof)
+    # roofline pass: CUDA events around every kernel-launching call of 2 more (un-graphed) steps
     peaks, peak_kind = measured_peaks()
-    achieved = flop / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+    prof = KernelProfiler(ops)
+    per_kernel, kernel_ms = None, None
+    gemm_flop = gemm_ms = 0.0
+    n_gemm = 0
+    if not args.no_kernel_table:
+        prof.start()
+        barrier()
+        for _ in range(2):
+            step_eager()
+        torch.cuda.synchronize()
+        prof.stop()
+        per_kernel, kernel_ms = prof.table(2, peaks)
+        for role, work, unit, e0, e1 in prof.rows:
+            if role.startswith("gemm"):
+                gemm_flop += work; gemm_ms += e0.elapsed_time(e1); n_gemm += 1
+    achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    peak_burst = float(peaks.get("bf16_tflops", peak))
+    traffic, traffic_capture = recorded_traffic("gemm_tcgen05_2cta_kernel")
 
     tokens = B * S * world
     value = tokens * args.steps / (ms * 1e-3)
     e2e_value = tokens * args.steps / (ms_e2e * 1e-3)
     ms_step = ms / args.steps
+    loss_v, loss_e2e_v = float(loss.detach()), float(loss_e2e)
+
+    eager = None
+    if not args.no_eager_baseline:
+        # free our step's memory first: the eager path materialises [B,h,S,S] scores and fp32 logits
+        del net, model, optimizer
+        if use_graph:
+            del gstep
+        torch.cuda.empty_cache()
+        eager = eager_time(args, dev, world, rank, local, max(args.eager_steps, 5), 3)
 
     if rank == 0:
         line = {
@@ -409,36 +577,44 @@ def main():
                        "parallelism": "dp%d" % world, "precision": "fp32 master params/residual/LN/softmax/loss, bf16 tensor-core operands",
                        "l2": "inputs larger than L2 (1.1 GB bf16 weights + >3 GB activations per step vs 126 MB L2); no flush",
                        "ddp_comm": (args.comm or "p2p") if world > 1 else None,
-                       "cuda_graph": bool(args.graph)},
+                       "cuda_graph": bool(use_graph)},
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": 3 * B * S * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "loss": float(loss.detach()), "loss_e2e": float(loss_e2e),
+            "loss": loss_v, "loss_e2e": loss_e2e_v,
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_2cta_kernel", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of the LM-head forward GEMM
-                         # (the largest launch of this kernel: M=8192, N=250880, K=1024), ncu --set full,
-                         # profiles/r01c_ncu_full_2layer_step_summary.csv row 20 (3.06 GB read + 4.08 GB written;
-                         # algorithmic: 0.53 GB operands + 4.11 GB bf16 logits)
-                         "traffic": 7.14e9 if args.layers == 24 else None,
-                         "peak_source": peak_kind + " (bf16_tflops_sustained: kernel timed inside a long step)",
-                         "launches_timed": len(prof), "gemm_ms_per_step": gms / 2.0,
-                         "gemm_share_of_step": (gms / 2.0) / ms_step if ms_step else None},
+                         "frac_of_burst_peak": achieved / peak_burst if peak_burst else None,
+                         # measured by ncu --set full on this build's kernel (largest launch: the LM-head forward
+                         # GEMM, M=8192 N=250880 K=1024), null when no capture of this build is committed
+                         "traffic": traffic, "traffic_capture": traffic_capture,
+                         "peak_source": peak_kind + " (bf16_tflops_sustained: kernel timed inside a long step; "
+                                                    "burst %.1f)" % peak_burst,
+                         "launches_timed": n_gemm, "gemm_ms_per_step": gemm_ms / 2.0,
+                         "gemm_share_of_step": (gemm_ms / 2.0) / ms_step if ms_step else None,
+                         "kernel_ms_per_step_ungraphed": kernel_ms,
+                         "per_kernel": per_kernel},
             "step_roofline": {
                 "attn_ffn_tflops_per_gpu": ATTN_FFN_FLOP_PER_TOKEN * B * S / (ms_step * 1e-3) / 1e12,
                 "attn_ffn_frac_of_peak": ATTN_FFN_FLOP_PER_TOKEN * B * S / (ms_step * 1e-3) / 1e12 / peak,
-                "whole_model_tflops_per_gpu": MODEL_FLOP_PER_TOKEN * B * S / (ms_step * 1e-3) / 1e12},
+                "whole_model_tflops_per_gpu": MODEL_FLOP_PER_TOKEN * B * S / (ms_step * 1e-3) / 1e12,
+                "whole_model_frac_of_peak": MODEL_FLOP_PER_TOKEN * B * S / (ms_step * 1e-3) / 1e12 / peak},
         }
+        if eager is not None:
+            line["eager_baseline"] = dict(eager, speedup=value / eager["value"])
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
-            Sc = min(S, 128)  # bounded sample: ~10-30 s of host work (tokens/s on CPU is ~S-insensitive)
+            Sc = min(S, CPU_SAMPLE_SEQ)  # bounded sample: ~10-30 s of host work (tokens/s on CPU is ~S-insensitive)
             stepf = cpu_reference_step_fn(args.layers, Sc)
             stepf(Sc)  # warm-up
-            t0 = time.time(); stepf(Sc); dt = time.time() - t0
+            t0 = time.time()
+            for _ in range(3):
+                stepf(Sc)
+            dt = (time.time() - t0) / 3
             line["cpu_baseline"] = {"value": Sc / dt, "unit": "tokens/s", "cores": torch.get_num_threads(),
                                     "kind": "port",
-                                    "sample": "B=1,S=%d, all %d layers, full 250880 vocab, fp32, 1 warm-up + 1 timed step "
+                                    "sample": "B=1,S=%d, all %d layers, full 250880 vocab, fp32, 1 warm-up + 3 timed steps "
                                               "(oracle port + torch.optim.AdamW)" % (Sc, args.layers)}
         print(json.dumps(line), flush=True)
     if world > 1:

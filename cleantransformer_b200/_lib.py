@@ -69,7 +69,7 @@ class AttnBwdArgs(ctypes.Structure):
         ("dq", c_void_p), ("dq_sb", c_i64), ("dq_sh", c_i64), ("dq_ss", c_i64),
         ("dk", c_void_p), ("dk_sb", c_i64), ("dk_sh", c_i64), ("dk_ss", c_i64),
         ("dv", c_void_p), ("dv_sb", c_i64), ("dv_sh", c_i64), ("dv_ss", c_i64),
-        ("delta", c_void_p), ("dq_accum", c_void_p),
+        ("delta", c_void_p), ("dq_accum", c_void_p), ("dq_accum_armed", ctypes.c_int32),
     ]
 
 

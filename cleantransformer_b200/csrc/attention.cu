@@ -949,12 +949,401 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
 }
 
 // =================================================================================================
+// tcgen05 forward, generation 4 (default). r01z (ncu, profiles/r01z_ncu_full_attention_summary.csv) showed the
+// generation-2 kernel above at 3 % tensor-pipe / 37 % MUFU activity with 16 % of the warp slots occupied: one thread
+// owns a whole 128-key score row, four softmax warps per CTA, so each scheduler holds two warps that take turns
+// waiting for TMEM, for MUFU results and for each other. Here
+//   * a query row is shared by TWO threads (warps w and w+4 of the same TMEM lane quarter own key columns [0,64) and
+//     [64,128) of every tile): 8 softmax warps per CTA, 16 per SM, half the registers and half the dependent chain
+//     per thread. The only thing the two halves must agree on per tile is the row maximum: it crosses through a spare
+//     TMEM column (tcgen05.st / 64-thread named barrier / tcgen05.ld) — shared memory is full (2 CTAs x 113 KB);
+//     the row sums stay private and are added once in the epilogue;
+//   * the running maximum is a REFERENCE that only moves when a tile exceeds it by more than 2^8 (P stays inside
+//     bf16/f16 range, sums are fp32), so O is rescaled in TMEM — a warp-collective load/store — only in the first
+//     tiles of a row instead of whenever any of 32 rows moves;
+//   * one score path for regular tiles and one for tiles that need a per-element test (causal diagonal, ragged key
+//     edge) instead of five specialised ones: the instruction stream shrinks (r01z: 22 % of the forward samples were
+//     `no_instructions` — instruction-cache misses in a fully unrolled 168-register kernel);
+//   * the per-key bias of a tile is staged by an otherwise idle warp under an mbarrier pair, not by the softmax
+//     threads behind a CTA-wide barrier;
+//   * heavy (late) query tiles of ALL heads are scheduled first (longest-processing-time order over the whole grid).
+// Warp roles (384 threads): 0-3 / 4-7 softmax halves (setmaxnreg 104), 8 TMA producer, 9 MMA issuer, 10 bias staging,
+// 11 idle (setmaxnreg 32). TMEM (256 columns per CTA, 2 CTAs/SM): [0,128) S, [128,192) O, [192,196) row-maximum
+// mailbox.
+// =================================================================================================
+constexpr int F4_THREADS = 384;
+constexpr int F4_SMEM = 7 * FA_TILE + 128 + 512;
+
+template <uint32_t N>
+__device__ __forceinline__ void f4_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <uint32_t N>
+__device__ __forceinline__ void f4_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+
+// One 32-column chunk of a REGULAR tile: t = s * sl2 + kb clamped at -FLT_MAX (in place) when there is a per-key
+// bias, raw scores otherwise (scaled inside the exp2); returns the running maximum.
+template <bool HAS_KB>
+__device__ __forceinline__ float f4_scale_max(uint32_t (&r)[32], uint32_t kb_addr, float sl2, float mt) {
+  if constexpr (HAS_KB) {
+    const float2 s2 = make_float2(sl2, sl2);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 k4 = lds128f(kb_addr + 16 * g);
+      float2 a = __ffma2_rn(make_float2(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1])), s2,
+                            make_float2(k4.x, k4.y));
+      float2 c = __ffma2_rn(make_float2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])), s2,
+                            make_float2(k4.z, k4.w));
+      a.x = fmaxf(a.x, -FLT_MAX); a.y = fmaxf(a.y, -FLT_MAX);  // a masked key (bias -inf) scores finfo.min, not -inf
+      c.x = fmaxf(c.x, -FLT_MAX); c.y = fmaxf(c.y, -FLT_MAX);
+      r[4 * g] = __float_as_uint(a.x); r[4 * g + 1] = __float_as_uint(a.y);
+      r[4 * g + 2] = __float_as_uint(c.x); r[4 * g + 3] = __float_as_uint(c.y);
+      mt = fmaxf(mt, fmaxf(a.x, a.y));
+      mt = fmaxf(mt, fmaxf(c.x, c.y));
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < 16; ++g)
+      mt = fmaxf(mt, fmaxf(__uint_as_float(r[2 * g]), __uint_as_float(r[2 * g + 1])));
+  }
+  return mt;
+}
+
+// The same for a tile that needs a per-element test: causally masked entries REPLACED by the fill (+ bias), clamp,
+// keys beyond Sk excluded (-inf). `lim` = last visible column of this chunk for this thread's row (>= 32: all).
+template <bool HAS_KB>
+__device__ __forceinline__ float f4_mask_max(uint32_t (&r)[32], uint32_t kb_addr, float sl2, float cf2, int lim, int n_ok,
+                                            float mt) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (HAS_KB) k4 = lds128f(kb_addr + 16 * g);
+    const float kb[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = 4 * g + u;
+      float v = (t > lim) ? (cf2 + kb[u]) : fmaf(__uint_as_float(r[t]), sl2, kb[u]);
+      v = fmaxf(v, -FLT_MAX);
+      if (t >= n_ok) v = -INFINITY;
+      r[t] = __float_as_uint(v);
+      mt = fmaxf(mt, v);
+    }
+  }
+  return mt;
+}
+
+// p = 2^(t - m) (SCALED) or 2^(s * sl2 - m) for one 32-column chunk -> four 16-byte pieces of the swizzled P panel
+template <bool SCALED, bool BF16>
+__device__ __forceinline__ void f4_exp_store(const uint32_t (&r)[32], int c, float m, float sl2, uint32_t p_row, int sw,
+                                             float2& acc0, float2& acc1) {
+  const float2 nm = make_float2(-m, -m);
+  const float2 s2 = make_float2(sl2, sl2);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float2 a = make_float2(__uint_as_float(r[8 * g + 2 * u]), __uint_as_float(r[8 * g + 2 * u + 1]));
+      if constexpr (SCALED) a = __fadd2_rn(a, nm);
+      else a = __ffma2_rn(a, s2, nm);
+      v[u] = make_float2(ex2(a.x), ex2(a.y));
+    }
+    acc0 = __fadd2_rn(acc0, v[0]); acc1 = __fadd2_rn(acc1, v[1]);
+    acc0 = __fadd2_rn(acc0, v[2]); acc1 = __fadd2_rn(acc1, v[3]);
+    uint32_t w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if constexpr (BF16) {
+        w[u] = pack_bf16x2(v[u].x, v[u].y);
+      } else {
+        __half2 h = __floats2half2_rn(v[u].x, v[u].y);
+        w[u] = *reinterpret_cast<uint32_t*>(&h);
+      }
+    }
+    const uint32_t addr = p_row + (((4 * c + g) ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                 : "memory");
+  }
+}
+
+template <bool HAS_KB, bool BF16>
+__global__ void __launch_bounds__(F4_THREADS, 2)
+    attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const AttnP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t sQ = base;
+  const uint32_t sK = base + FA_TILE;
+  const uint32_t sV = base + 3 * FA_TILE;
+  const uint32_t sP = base + 5 * FA_TILE;  // two 64-key panels, one per softmax half
+  const uint32_t bars = base + 7 * FA_TILE;
+  const uint32_t q_full = bars, k_full = bars + 8, v_full = bars + 24, kv_empty = bars + 40, s_full = bars + 56,
+                 s_free = bars + 64, p_ready = bars + 72, o_full = bars + 80, tmem_slot = bars + 88,
+                 kb_full = bars + 96, kb_free = bars + 104, kb_s = bars + 128;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + 7 * FA_TILE + 88);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_q_tiles = (p.Sq + 127) / 128;
+  const int n_bh = p.B * p.H;
+  const int q_tile = n_q_tiles - 1 - (int)(blockIdx.x / n_bh);  // all heads' heavy (late) query tiles first
+  const int bh = blockIdx.x % n_bh;
+  const int h = bh % p.H, b = bh / p.H;
+  const int q0 = q_tile * 128;
+
+  int n_kv = (p.Sk + 127) / 128;
+  if (p.causal) {
+    // rows that are fully masked (left padding) weight every key uniformly in the reference: visit them all
+    const bool full_sweep = p.first_valid && (q0 + p.off < p.first_valid[b]);
+    if (!full_sweep) {
+      const int last_key = min(p.Sk - 1, q0 + 127 + p.off);
+      n_kv = last_key < 0 ? 0 : last_key / 128 + 1;
+    }
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full + 8 * s, 1); mbar_init(v_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 256);
+    mbar_init(p_ready, 256);
+    mbar_init(o_full, 1);
+    mbar_init(kb_full, 32);
+    mbar_init(kb_free, 256);
+    mbar_fence_init();
+  }
+  if (warp == 9) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp >= 8) {
+    f4_setmaxnreg_dec<32>();
+    if (warp == 8) {
+      // ------------------------------ TMA producer ------------------------------
+      if (lane == 0 && n_kv > 0) {
+        mbar_expect_tx(q_full, FA_TILE);
+        tma_load_4d(sQ, &tmQ, q_full, 0, q0, h, b);
+        for (int j = 0; j < n_kv; ++j) {
+          const int s = j & 1;
+          mbar_wait(kv_empty + 8 * s, ((j >> 1) & 1) ^ 1);
+          mbar_expect_tx(k_full + 8 * s, FA_TILE);
+          tma_load_4d(sK + s * FA_TILE, &tmK, k_full + 8 * s, 0, j * 128, h, b);
+          mbar_expect_tx(v_full + 8 * s, FA_TILE);
+          tma_load_4d(sV + s * FA_TILE, &tmV, v_full + 8 * s, 0, j * 128, h, b);
+        }
+      }
+    } else if (warp == 9) {
+      // ------------------------------ MMA issuer ------------------------------
+      if (lane == 0 && n_kv > 0) {
+        const uint32_t idesc_s = umma_idesc_f16(BF16 ? 1 : 0, 0, 0, 128, 128);
+        const uint32_t idesc_o = umma_idesc_f16(BF16 ? 1 : 0, 0, 1, 128, 64);
+        mbar_wait(q_full, 0);
+        for (int j = 0; j <= n_kv; ++j) {
+          if (j < n_kv) {  // S(j) = Q K(j)^T; for j > 0 it runs under the softmax of tile j-1
+            const int s = j & 1;
+            mbar_wait(k_full + 8 * s, (j >> 1) & 1);
+            if (j > 0) mbar_wait(s_free, (j - 1) & 1);  // every softmax thread holds S(j-1) in registers
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem, umma_smem_desc_sw128(sQ + k * 32, 0, 1024),
+                       umma_smem_desc_sw128(sK + s * FA_TILE + k * 32, 0, 1024), idesc_s, k > 0);
+            umma_commit(s_full);
+          }
+          if (j > 0) {  // O += P(j-1) V(j-1)
+            const int jj = j - 1, s = jj & 1;
+            mbar_wait(p_ready, jj & 1);
+            mbar_wait(v_full + 8 * s, (jj >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_f16(tmem + 128, umma_smem_desc_sw128(sP + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                       umma_smem_desc_sw128(sV + s * FA_TILE + k * 2048, 64 * 128, 1024), idesc_o, (jj > 0 || k > 0));
+            umma_commit(kv_empty + 8 * s);
+            umma_commit(o_full);
+          }
+        }
+      }
+    } else if (warp == 10) {
+      // ------------------------------ per-key bias staging ------------------------------
+      if constexpr (HAS_KB) {
+        const float* kb_row = p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh;
+        for (int j = 0; j < n_kv; ++j) {
+          float v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int col = j * 128 + lane * 4 + u;
+            v[u] = col < p.Sk ? __ldg(kb_row + col) : 0.f;
+          }
+          if (j > 0) mbar_wait(kb_free, (j - 1) & 1);  // every softmax thread is done with the previous tile's bias
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(kb_s + 16 * lane), "f"(v[0]), "f"(v[1]),
+                       "f"(v[2]), "f"(v[3])
+                       : "memory");
+          mbar_arrive(kb_full);
+        }
+      }
+    }
+  } else {
+    f4_setmaxnreg_inc<104>();
+    // ------------------------------ softmax: two threads per query row ------------------------------
+    const int half = warp >> 2;  // key columns [64 * half, 64 * half + 64) of every tile
+    const int wq = warp & 3;
+    const int qr = wq * 32 + lane;  // row inside the tile == TMEM lane
+    const int i = q0 + qr;
+    const uint32_t t_lane = tmem + ((uint32_t)(wq * 32) << 16);
+    const uint32_t t_s = t_lane + 64 * half;
+    const uint32_t t_o = t_lane + 128 + 32 * half;  // this thread's 32 of the 64 output columns
+    const uint32_t t_mail = t_lane + 192;
+    const uint32_t p_row = sP + half * FA_TILE + qr * 128;
+    const uint32_t kb_half = kb_s + 256 * half;
+    const int sw = qr & 7;
+    const int vis = i + p.off;  // last key this row may see under the causal mask
+    float m_ref = -INFINITY, l = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int col0 = j * 128 + 64 * half;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(t_s, ra);
+      tmem_ld_32x32(t_s + 32, rb);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);  // S(j) is in registers: S(j+1) may be issued
+      // CTA-uniform: does any element of this tile need a test (causal boundary inside the tile, ragged key edge)?
+      const bool masked_tile = (p.causal && (j * 128 + 127 > q0 + p.off)) || (j * 128 + 128 > p.Sk);
+      if constexpr (HAS_KB) mbar_wait(kb_full, j & 1);
+      float mt = -INFINITY;
+      bool scaled = HAS_KB;
+      if (!masked_tile) {
+        mt = f4_scale_max<HAS_KB>(ra, kb_half, p.sl2, mt);
+        mt = f4_scale_max<HAS_KB>(rb, kb_half + 128, p.sl2, mt);
+        if constexpr (!HAS_KB) mt *= p.sl2;  // sl2 > 0 (checked on the host)
+      } else {
+        const int lim = p.causal ? vis - col0 : 1 << 20;
+        const int n_ok = p.Sk - col0;
+        mt = f4_mask_max<HAS_KB>(ra, kb_half, p.sl2, p.causal_fill2, lim, n_ok, mt);
+        mt = f4_mask_max<HAS_KB>(rb, kb_half + 128, p.sl2, p.causal_fill2, lim - 32, n_ok - 32, mt);
+        scaled = true;
+      }
+      if constexpr (HAS_KB) mbar_arrive(kb_free);
+      // ---- row maximum of the tile: through the TMEM mailbox to the thread that owns the other 64 columns ----
+      tmem_st_32x1(t_mail + 2 * (j & 1) + half, __float_as_uint(mt));
+      tmem_st_wait();
+      tc_fence_before();
+      bar_sync_named(1 + wq, 64);
+      tc_fence_after();
+      uint32_t other;
+      tmem_ld_32x1(t_mail + 2 * (j & 1) + (half ^ 1), other);
+      tmem_ld_wait();
+      mt = fmaxf(fmaxf(mt, __uint_as_float(other)), -FLT_MAX);
+      // ---- reference maximum: moves only when this tile exceeds it by more than 2^8 ----
+      float alpha = 1.f;
+      const bool need = mt > m_ref + 8.f;  // (first tile: m_ref = -inf)
+      if (need) {
+        alpha = ex2(m_ref - mt);
+        l *= alpha;
+        m_ref = mt;
+      }
+      const bool rescale = j > 0 && __any_sync(0xffffffffu, need);
+      if (j > 0) {  // P(j-1) V(j-1) retired: the P panel may be overwritten, O may be rescaled
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
+      if (scaled) {
+        f4_exp_store<true, BF16>(ra, 0, m_ref, p.sl2, p_row, sw, acc0, acc1);
+        f4_exp_store<true, BF16>(rb, 1, m_ref, p.sl2, p_row, sw, acc0, acc1);
+      } else {
+        f4_exp_store<false, BF16>(ra, 0, m_ref, p.sl2, p_row, sw, acc0, acc1);
+        f4_exp_store<false, BF16>(rb, 1, m_ref, p.sl2, p_row, sw, acc0, acc1);
+      }
+      l += (acc0.x + acc0.y) + (acc1.x + acc1.y);
+      fence_proxy_async_smem();
+      if (rescale) {  // warp-uniform: the TMEM accesses are warp-collective
+        uint32_t o0[32];
+        tmem_ld_32x32(t_o, o0);
+        tmem_ld_wait();
+        const float2 a2 = make_float2(alpha, alpha);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const float2 x = __fmul2_rn(make_float2(__uint_as_float(o0[2 * t]), __uint_as_float(o0[2 * t + 1])), a2);
+          o0[2 * t] = __float_as_uint(x.x); o0[2 * t + 1] = __float_as_uint(x.y);
+        }
+        tmem_st_32x32(t_o, o0);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    // ---- epilogue: l = l(half 0) + l(half 1); O / l -> merged-head layout (32 of the 64 columns each), lse2 ----
+    if (n_kv > 0) {
+      tmem_st_32x1(t_mail + 2 * (n_kv & 1) + half, __float_as_uint(l));
+      tmem_st_wait();
+      tc_fence_before();
+      bar_sync_named(1 + wq, 64);
+      tc_fence_after();
+      uint32_t other;
+      tmem_ld_32x1(t_mail + 2 * (n_kv & 1) + (half ^ 1), other);
+      tmem_ld_wait();
+      l += __uint_as_float(other);
+      mbar_wait(o_full, (n_kv - 1) & 1);
+      tc_fence_after();
+    }
+    uint32_t o0[32];
+    if (n_kv > 0) {
+      tmem_ld_32x32(t_o, o0);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) o0[t] = 0u;
+    }
+    if (i < p.Sq) {
+      const float inv = (n_kv > 0) ? 1.f / l : 0.f;
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
+                      2 * ((int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)i * p.o_ss + 32 * half);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float f[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f[u] = __uint_as_float(o0[8 * g + u]) * inv;
+        uint4 w;
+        if constexpr (BF16) {
+          w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]);
+          w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
+        } else {
+          __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+          __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+          w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+          w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+        }
+        *reinterpret_cast<uint4*>(orow + 16 * g) = w;
+      }
+      if (half == 0 && p.lse2) p.lse2[((int64_t)b * p.H + h) * p.Sq + i] = (n_kv > 0) ? m_ref + log2f(l) : -INFINITY;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+// =================================================================================================
 // tcgen05 backward
 // =================================================================================================
 struct AttnBwdP {
   AttnP f;
   const float* delta;
   float* dq_accum;  // [B, Sq, H, 64] f32
+  int* dq_counters;  // [B*H] zero on entry / exit, or null: the dQ workspace is converted by a separate kernel
+  void* dq; int64_t dq_sb, dq_sh, dq_ss;
   void* dk; int64_t dk_sb, dk_sh, dk_ss;
   void* dv; int64_t dv_sb, dv_sh, dv_ss;
 };
@@ -1667,6 +2056,56 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
             x = __floats2half2_rn(f6, f7); w.w = *reinterpret_cast<uint32_t*>(&x);
           }
           *reinterpret_cast<uint4*>(row + 16 * g) = w;
+        }
+      }
+    }
+    // ---- the LAST key-tile CTA of this (b, h) turns the head's f32 dQ workspace into the bf16/f16 gradient and
+    // re-arms it (zeros) for the next call: no memset, no separate convert launch, the workspace never leaves L2 ----
+    if constexpr (DQT) {
+      if (bp.dq_counters != nullptr) {
+        uint32_t* last_flag = reinterpret_cast<uint32_t*>(smem + N_TILES * FA_TILE + 96);
+        __threadfence();  // this thread's red.global.adds are visible device-wide ...
+        bar_sync_named(2, 256);
+        if (threadIdx.x == 64) {  // ... before the CTA counts itself in
+          const int prev = atomicAdd(bp.dq_counters + bh, 1);
+          *last_flag = (prev == n_kv_tiles - 1) ? 1u : 0u;
+          if (prev == n_kv_tiles - 1) bp.dq_counters[bh] = 0;
+        }
+        bar_sync_named(2, 256);
+        if (*last_flag) {
+          __threadfence();
+          const int t = (int)threadIdx.x - 64;
+          const int row = t & 127, dh = t >> 7;  // 64 bytes (32 of the 64 head-dim columns) of one query row per thread
+          for (int qt = 0; qt < n_q_tiles; ++qt) {
+            float* tile = bp.dq_accum + ((int64_t)bh * n_q_tiles + qt) * FB_DQ_TILE;
+            const int qi = qt * 128 + row;
+            float4 v[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) v[g] = __ldcg(reinterpret_cast<const float4*>(tile + ((8 * dh + g) * 128 + row) * 4));
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              __stcg(reinterpret_cast<float4*>(tile + ((8 * dh + g) * 128 + row) * 4), make_float4(0.f, 0.f, 0.f, 0.f));
+            if (qi < p.Sq) {
+              uint8_t* orow = reinterpret_cast<uint8_t*>(bp.dq) +
+                              2 * ((int64_t)b * bp.dq_sb + (int64_t)h * bp.dq_sh + (int64_t)qi * bp.dq_ss + 32 * dh);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const float4 lo = v[2 * g], hi = v[2 * g + 1];
+                uint4 w;
+                if constexpr (BF16) {
+                  w.x = pack_bf16x2(lo.x, lo.y); w.y = pack_bf16x2(lo.z, lo.w);
+                  w.z = pack_bf16x2(hi.x, hi.y); w.w = pack_bf16x2(hi.z, hi.w);
+                } else {
+                  __half2 x;
+                  x = __floats2half2_rn(lo.x, lo.y); w.x = *reinterpret_cast<uint32_t*>(&x);
+                  x = __floats2half2_rn(lo.z, lo.w); w.y = *reinterpret_cast<uint32_t*>(&x);
+                  x = __floats2half2_rn(hi.x, hi.y); w.z = *reinterpret_cast<uint32_t*>(&x);
+                  x = __floats2half2_rn(hi.z, hi.w); w.w = *reinterpret_cast<uint32_t*>(&x);
+                }
+                *reinterpret_cast<uint4*>(orow + 16 * g) = w;
+              }
+            }
+          }
         }
       }
     }
@@ -3044,7 +3483,25 @@ extern "C" int ct_attn_fwd(const ct_attn_args* args, void* stream) {
       attr = true;
     }
     const int64_t grid = (int64_t)a.B * a.H * ((a.Sq + 127) / 128);
-    // ATTN_FWD_IMPL: 0 = auto (v2: register-resident score rows, O in TMEM), 1 = v1 (two TMEM passes),
+    // ATTN_FWD_IMPL: 0 = auto (generation 4: two threads per query row), 4 = the same, 3 = generation 2;
+    if ((option(OPT_ATTN_FWD_IMPL) == 0 || option(OPT_ATTN_FWD_IMPL) == 4) && a.scale > 0.f) {
+      static bool attr4 = false;
+      if (!attr4) {
+        CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
+        CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
+        CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
+        CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
+        attr4 = true;
+      }
+      const bool kb = a.kbias2 != nullptr, bf = p.fmt == 1;
+      if (kb && bf) attn_fwd_tc4_kernel<true, true><<<(unsigned)grid, F4_THREADS, F4_SMEM, st>>>(tmQ, tmK, tmV, p);
+      else if (kb) attn_fwd_tc4_kernel<true, false><<<(unsigned)grid, F4_THREADS, F4_SMEM, st>>>(tmQ, tmK, tmV, p);
+      else if (bf) attn_fwd_tc4_kernel<false, true><<<(unsigned)grid, F4_THREADS, F4_SMEM, st>>>(tmQ, tmK, tmV, p);
+      else attn_fwd_tc4_kernel<false, false><<<(unsigned)grid, F4_THREADS, F4_SMEM, st>>>(tmQ, tmK, tmV, p);
+      CT_LAUNCH_OK();
+      return 0;
+    }
+    // ATTN_FWD_IMPL (older generations): 3 = v2 (register-resident score rows, O in TMEM), 1 = v1 (two TMEM passes),
     //                2 = v3 (v2 + lazy reference maximum + P handed over per 64-key panel; bf16 only; compiled,
     //                    not yet run on a GPU)
     const bool v2 = option(OPT_ATTN_FWD_IMPL) != 1 && a.scale > 0.f;
@@ -3115,6 +3572,8 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     fill_common(bp.f, a);
     bp.delta = args->delta;
     bp.dq_accum = args->dq_accum;
+    bp.dq_counters = nullptr;
+    bp.dq = args->dq; bp.dq_sb = args->dq_sb; bp.dq_sh = args->dq_sh; bp.dq_ss = args->dq_ss;
     bp.dk = args->dk; bp.dk_sb = args->dk_sb; bp.dk_sh = args->dk_sh; bp.dk_ss = args->dk_ss;
     bp.dv = args->dv; bp.dv_sb = args->dv_sb; bp.dv_sh = args->dv_sh; bp.dv_ss = args->dv_ss;
     CUtensorMap tmQ, tmK, tmV, tmDO;
@@ -3133,8 +3592,15 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     const int nqt = (a.Sq + 127) / 128;
     // the workspace is sized for whole query tiles (include/ct_b200.h): B*H*ceil(Sq/128)*128*64 floats
     const size_t dq_elems = (size_t)a.B * a.H * nqt * FB_DQ_TILE;
-    CT_CUDA_OK(cudaMemsetAsync(args->dq_accum, 0,
-                               sizeof(float) * (dq_tiled ? dq_elems : (size_t)a.B * a.Sq * a.H * 64), st));
+    // dq_accum_armed: the caller keeps the workspace (+ B*H int32 counters right behind it) zeroed between calls and
+    // the default kernel converts and re-zeroes it itself (last CTA of every head)
+    const bool fused_dq = args->dq_accum_armed != 0 && variant == 4 && tma_ok4(args->dq, args->dq_sb, args->dq_sh, args->dq_ss);
+    if (fused_dq) bp.dq_counters = reinterpret_cast<int*>(args->dq_accum + dq_elems);
+    else if (args->dq_accum_armed != 0)
+      CT_REQUIRE(false, CT_ERR_UNSUPPORTED, "ct_attn_bwd: dq_accum_armed needs the default backward kernel and a 16-byte aligned dq");
+    if (!fused_dq)
+      CT_CUDA_OK(cudaMemsetAsync(args->dq_accum, 0,
+                                 sizeof(float) * (dq_tiled ? dq_elems : (size_t)a.B * a.Sq * a.H * 64), st));
     static bool attr = false;
     if (!attr) {
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
@@ -3185,6 +3651,7 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
         break;
     }
     CT_LAUNCH_OK();
+    if (fused_dq) return 0;
     const int64_t n = dq_tiled ? (int64_t)(dq_elems / 8) : (int64_t)a.B * a.Sq * a.H * 64 / 8;
     int64_t blocks = (n + 255) / 256;
     if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;

@@ -246,6 +246,11 @@ typedef struct {
   int64_t dv_sb, dv_sh, dv_ss;
   float* delta;
   float* dq_accum;
+  /* 0: dq_accum may hold anything; the library zeroes it, accumulates, and converts it with a second kernel.
+   * 1: the caller owns a PERSISTENT workspace of B*H*ceil(Sq/128)*128*D floats followed by B*H int32 counters, all
+   *    zero on entry; the backward kernel converts dQ itself (last CTA of each head) and leaves workspace and counters
+   *    zero again: no memset, no convert launch (tcgen05 path, D == 64; one call at a time per workspace). */
+  int32_t dq_accum_armed;
 } ct_attn_bwd_args;
 int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream);
 

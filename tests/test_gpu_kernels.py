@@ -288,17 +288,14 @@ ATT_CASES = [
     (2, 2, 256, 640, 64, True, 0, "none", -FLT_MAX, 1),     # Sq < Sk: diagonal offset by 384 (aligned)
     (2, 2, 200, 440, 64, True, 0, "right", -FLT_MAX, 1),    # diagonal offset (240) not a multiple of 128
 ]
-# kernel variants of the tcgen05 path (ATTN_FWD_IMPL, ATTN_BWD_IMPL): "v1" = first-generation softmax / backward
-# math, "v2" = register-resident rows, "v2t" = v2 backward with the tiled dQ workspace, "v3" = backward with
-# double-buffered P^T / dS^T (element math of tile it+1 under the MMAs of tile it), "v4" = v3 with the dQ drain on its
-# own warpgroup
-ATT_VARIANTS = {"v1": (1, 1), "v2": (0, 2), "v2t": (0, 3), "v3": (0, 4), "v4": (0, 5)}
-if os.environ.get("CT_TEST_EXPERIMENTAL"):
-    # variants written after the round's GPU budget was spent: compiled, never run — opt-in until a GPU visit
-    # has shown them green (run them under `timeout`: a protocol bug in a persistent kernel traps after 2 s)
-    ATT_VARIANTS["v5"] = (0, 6)  # persistent backward
-    ATT_VARIANTS["v6"] = (0, 7)  # backward with sixteen compute warps
-    ATT_VARIANTS["f3"] = (2, 4)  # forward with the lazy reference maximum and per-panel P hand-over
+# kernel variants of the tcgen05 path (ATTN_FWD_IMPL, ATTN_BWD_IMPL): "f4" = the defaults (forward generation 4: two
+# threads per query row, lazy reference maximum; backward v3 with the fused dQ convert); "v1" = first-generation softmax
+# / backward math, "v2" = forward generation 2 (one thread per row) + register-resident backward, "v2t" = v2 backward
+# with the tiled dQ workspace, "v3" = backward with double-buffered P^T / dS^T, "v4" = v3 with the dQ drain on its own
+# warpgroup, "v5" = persistent v3, "v6" = v3 with sixteen compute warps, "f3" = forward generation 2 with the lazy
+# maximum and per-panel P hand-over
+ATT_VARIANTS = {"f4": (0, 0), "v1": (1, 1), "v2": (3, 2), "v2t": (3, 3), "v3": (3, 4), "v4": (3, 5), "v5": (3, 6),
+                "v6": (3, 7), "f3": (2, 4)}
 ATT_PARAMS = [c + ("-",) for c in ATT_CASES if c[-1] == 2] + \
              [c + (v,) for c in ATT_CASES if c[-1] == 1 for v in ATT_VARIANTS]
 
@@ -385,7 +382,7 @@ def test_attention_matches_reference_bloom_layer(golden):
     assert rel_err(o, ref) < 8e-3
 
 
-@pytest.mark.parametrize("variant", ["v1", "v2"])
+@pytest.mark.parametrize("variant", ["f4", "v1", "v2"])
 def test_attention_rows_sum_to_one_at_full_size(variant):
     with _AttnVariant(variant):
         _rows_sum_to_one()

@@ -124,7 +124,9 @@ def attn_ab():
         ref = _attn_oracle(qr, kr, vr, scale, True, fill, kb2[:nb].expand(nb, H, S) if kb2 is not None else None)
         do = torch.randn(B, S, H * D, device=DEV).bfloat16()
         ref.backward(do[:nb].float())
-        for impl, (fi, bi) in (("v2", (0, 2)), ("v3", (0, 4)), ("v4", (0, 5))) + ((("v5", (0, 6)), ("v6", (0, 7)), ("f3", (2, 4))) if os.environ.get("CT_TEST_EXPERIMENTAL") else ()):
+        # (forward option, backward option): f4 = the defaults (forward generation 4, backward v3 + fused dQ convert);
+        # v3 = forward generation 2 + backward v3
+        for impl, (fi, bi) in (("f4", (0, 0)), ("v3", (3, 4)), ("v4", (3, 5))):
             pf, pb = ops.set_option("ATTN_FWD_IMPL", fi), ops.set_option("ATTN_BWD_IMPL", bi)
             try:
                 o, lse2 = ops.attn_fwd(q, k, v, scale, True, fill, kb2, fv)
