@@ -304,8 +304,8 @@ class KernelProfiler:
             e1.record()
             try:
                 role, work, unit = work_fn(out, *a, **kw)
-            except Exception:  # noqa: BLE001 — attribution must never break the step
-                role, work, unit = name, 0.0, "B"
+            except Exception as ex:  # noqa: BLE001 — attribution must never break the step
+                role, work, unit = "%s (unattributed: %s)" % (name, type(ex).__name__), 0.0, "B"
             with prof.lock:
                 prof.rows.append((role, work, unit, e0, e1))
             return out
@@ -315,45 +315,45 @@ class KernelProfiler:
     def start(self):
         ops, nb = self.ops, self._nbytes
 
-        def gemm(out, A, B, M, N, K, a_mn=False, b_mn=False, **kw):
+        def gemm(ret, A, B, M, N, K, a_mn=False, b_mn=False, **kw):
             kind = "wgrad" if (a_mn and b_mn) else ("dgrad" if b_mn else "fwd")
             epi = ("+gelu" if kw.get("act") else "") + ("+res" if kw.get("residual") is not None else "") + \
                   ("*act'" if kw.get("actgrad_src") is not None else "") + ("+rowstats" if kw.get("row_stats") is not None else "")
             return "gemm %s M=%d N=%d K=%d%s" % (kind, M, N, K, epi), 2.0 * M * N * K, "flop"
 
-        def attn_fwd(out, q, k, v, scale, causal=False, *a, **kw):
+        def attn_fwd(ret, q, k, v, scale, causal=False, *a, **kw):
             B, H, Sq, D = q.shape
             return "attention forward", 4.0 * B * H * Sq * k.shape[2] * D * (0.5 if causal else 1.0), "flop"
 
-        def attn_bwd(out, dout, q, k, v, o, lse2, dq, dk, dv, scale, causal=False, *a, **kw):
+        def attn_bwd(ret, dout, q, k, v, o, lse2, dq, dk, dv, scale, causal=False, *a, **kw):
             B, H, Sq, D = q.shape
             return ("attention backward (incl. delta, dQ convert)",
                     10.0 * B * H * Sq * k.shape[2] * D * (0.5 if causal else 1.0), "flop")
 
-        def ln_fwd(out, x, gamma, beta, eps, out_dtype=None, out2_dtype=None, save_stats=True):
-            return "LayerNorm forward", nb(x, out[0], out[1]), "B"
+        def ln_fwd(ret, x, gamma, beta, eps, out_dtype=None, out2_dtype=None, save_stats=True):
+            return "LayerNorm forward", nb(x, ret[0], ret[1]), "B"
 
-        def ln_bwd(out, dy, x, *a, **kw):
-            outs = out if isinstance(out, tuple) else (out,)
+        def ln_bwd(ret, dy, x, *a, **kw):
+            outs = ret if isinstance(ret, tuple) else (ret,)
             return "LayerNorm backward (+residual add, bf16 copy, bias column sums)", \
                 nb(dy, x, kw.get("dy2"), kw.get("dx_add"), *outs), "B"
 
-        def adamw(out, p, g, m, v, *a, **kw):
+        def adamw(ret, p, g, m, v, *a, **kw):
             return "AdamW (flat arena, bf16 shadow)", nb(p, g, m, v) + nb(p, m, v) + nb(kw.get("shadow")), "B"
 
-        def ce(out, logits2d, *a, **kw):
-            return "cross entropy (loss + dlogits)", nb(logits2d, out[1]), "B"
+        def ce(ret, logits2d, *a, **kw):
+            return "cross entropy (loss + dlogits)", nb(logits2d, ret[1]), "B"
 
-        def colsum(out, x2d, o, accumulate):
+        def colsum(ret, x2d, o, accumulate):
             return "bias gradient column sums", nb(x2d), "B"
 
-        def cast(out, src, dtype, out_=None):
-            return "casts", nb(src, out), "B"
+        def cast(ret, src, dtype, out=None):
+            return "casts", nb(src, ret), "B"
 
-        def emb_f(out, ids, weight, *a, **kw):
-            return "embedding gather / scatter", nb(out) * 2, "B"
+        def emb_f(ret, ids, weight, *a, **kw):
+            return "embedding gather / scatter", nb(ret) * 2, "B"
 
-        def emb_b(out, ids, dout, dweight, *a, **kw):
+        def emb_b(ret, ids, dout, dweight, *a, **kw):
             return "embedding gather / scatter", nb(dout) * 2, "B"
 
         for name, fn in (("gemm", gemm), ("attn_fwd", attn_fwd), ("attn_bwd", attn_bwd), ("layernorm_fwd", ln_fwd),
@@ -447,7 +447,7 @@ def main():
     if world > 1:
         net = DistributedDataParallel(model, device_ids=[local], comm=args.comm)
     optimizer = TorchAdamW(net.parameters(), lr=1e-5)
-    use_graph = (world == 1 and not args.no_graph) or args.graph
+    use_graph = ((world == 1 or (args.comm or "p2p") == "p2p") and not args.no_graph) or args.graph
 
     B, S = args.batch, args.seq
     g = torch.Generator().manual_seed(999 + rank)
@@ -498,8 +498,6 @@ def main():
     del loss  # (a live loss tensor keeps its autograd graph, not a problem any more — see functional._anchor)
     step_eager = step_resident
     if use_graph:
-        if world > 1:
-            raise SystemExit("--graph: single GPU only (peer-memory collectives cannot be replayed)")
         from cleantransformer_b200.graphs import GraphedTrainStep
         optimizer.zero_grad()
         gstep = GraphedTrainStep(net, dict(input_ids=ids, attention_mask=mask, labels=labels))
@@ -561,9 +559,11 @@ def main():
     eager = None
     if not args.no_eager_baseline:
         # free our step's memory first: the eager path materialises [B,h,S,S] scores and fp32 logits
-        del net, model, optimizer
         if use_graph:
             del gstep
+        if world > 1:
+            net.close()  # one peer-memory context per process; the eager arm uses torch DDP over NCCL
+        del net, model, optimizer
         torch.cuda.empty_cache()
         eager = eager_time(args, dev, world, rank, local, max(args.eager_steps, 5), 3)
 

@@ -69,7 +69,7 @@ class AttnBwdArgs(ctypes.Structure):
         ("dq", c_void_p), ("dq_sb", c_i64), ("dq_sh", c_i64), ("dq_ss", c_i64),
         ("dk", c_void_p), ("dk_sb", c_i64), ("dk_sh", c_i64), ("dk_ss", c_i64),
         ("dv", c_void_p), ("dv_sb", c_i64), ("dv_sh", c_i64), ("dv_ss", c_i64),
-        ("delta", c_void_p), ("dq_accum", c_void_p), ("dq_accum_armed", ctypes.c_int32),
+        ("delta", c_void_p), ("dq_accum", c_void_p),
     ]
 
 
@@ -139,9 +139,15 @@ SIGNATURES = {
     "ct_allreduce_bucket": (c_int, [c_i64, c_i64, c_float, c_int, c_int, c_void_p]),
     "ct_broadcast": (c_int, [c_i64, c_i64, c_int, c_void_p]),
     "ct_comm_barrier": (c_int, [c_void_p]),
-    "ct_comm_pull": (c_int, [c_int, c_i64, c_void_p, c_i64, c_void_p]),
-    "ct_comm_push": (c_int, [c_int, c_i64, c_i64, c_i64, c_void_p]),
-    "ct_comm_reduce_slices": (c_int, [c_i64, c_void_p, c_i64, c_i64, c_float, c_int, c_void_p]),
+    "ct_comm_vmm_supported": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "ct_comm_vmm_init": (c_int, [c_int, c_int, c_int, ctypes.c_size_t, ctypes.POINTER(c_void_p),
+                                 ctypes.POINTER(c_int)]),
+    "ct_comm_vmm_connect": (c_int, [ctypes.POINTER(c_int)]),
+    "ct_comm_mc_create": (c_int, [ctypes.POINTER(c_int)]),
+    "ct_comm_mc_import": (c_int, [c_int]),
+    "ct_comm_mc_add_device": (c_int, []),
+    "ct_comm_mc_bind": (c_int, []),
+    "ct_comm_info": (c_int, [ctypes.POINTER(c_int)]),
     "ct_embedding_bwd_allranks": (c_int, [c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_float, c_int,
                                           c_void_p]),
     "ct_comm_finalize": (c_int, []),

@@ -1342,8 +1342,6 @@ struct AttnBwdP {
   AttnP f;
   const float* delta;
   float* dq_accum;  // [B, Sq, H, 64] f32
-  int* dq_counters;  // [B*H] zero on entry / exit, or null: the dQ workspace is converted by a separate kernel
-  void* dq; int64_t dq_sb, dq_sh, dq_ss;
   void* dk; int64_t dk_sb, dk_sh, dk_ss;
   void* dv; int64_t dv_sb, dv_sh, dv_ss;
 };
@@ -2056,56 +2054,6 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
             x = __floats2half2_rn(f6, f7); w.w = *reinterpret_cast<uint32_t*>(&x);
           }
           *reinterpret_cast<uint4*>(row + 16 * g) = w;
-        }
-      }
-    }
-    // ---- the LAST key-tile CTA of this (b, h) turns the head's f32 dQ workspace into the bf16/f16 gradient and
-    // re-arms it (zeros) for the next call: no memset, no separate convert launch, the workspace never leaves L2 ----
-    if constexpr (DQT) {
-      if (bp.dq_counters != nullptr) {
-        uint32_t* last_flag = reinterpret_cast<uint32_t*>(smem + N_TILES * FA_TILE + 96);
-        __threadfence();  // this thread's red.global.adds are visible device-wide ...
-        bar_sync_named(2, 256);
-        if (threadIdx.x == 64) {  // ... before the CTA counts itself in
-          const int prev = atomicAdd(bp.dq_counters + bh, 1);
-          *last_flag = (prev == n_kv_tiles - 1) ? 1u : 0u;
-          if (prev == n_kv_tiles - 1) bp.dq_counters[bh] = 0;
-        }
-        bar_sync_named(2, 256);
-        if (*last_flag) {
-          __threadfence();
-          const int t = (int)threadIdx.x - 64;
-          const int row = t & 127, dh = t >> 7;  // 64 bytes (32 of the 64 head-dim columns) of one query row per thread
-          for (int qt = 0; qt < n_q_tiles; ++qt) {
-            float* tile = bp.dq_accum + ((int64_t)bh * n_q_tiles + qt) * FB_DQ_TILE;
-            const int qi = qt * 128 + row;
-            float4 v[8];
-#pragma unroll
-            for (int g = 0; g < 8; ++g) v[g] = __ldcg(reinterpret_cast<const float4*>(tile + ((8 * dh + g) * 128 + row) * 4));
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              __stcg(reinterpret_cast<float4*>(tile + ((8 * dh + g) * 128 + row) * 4), make_float4(0.f, 0.f, 0.f, 0.f));
-            if (qi < p.Sq) {
-              uint8_t* orow = reinterpret_cast<uint8_t*>(bp.dq) +
-                              2 * ((int64_t)b * bp.dq_sb + (int64_t)h * bp.dq_sh + (int64_t)qi * bp.dq_ss + 32 * dh);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const float4 lo = v[2 * g], hi = v[2 * g + 1];
-                uint4 w;
-                if constexpr (BF16) {
-                  w.x = pack_bf16x2(lo.x, lo.y); w.y = pack_bf16x2(lo.z, lo.w);
-                  w.z = pack_bf16x2(hi.x, hi.y); w.w = pack_bf16x2(hi.z, hi.w);
-                } else {
-                  __half2 x;
-                  x = __floats2half2_rn(lo.x, lo.y); w.x = *reinterpret_cast<uint32_t*>(&x);
-                  x = __floats2half2_rn(lo.z, lo.w); w.y = *reinterpret_cast<uint32_t*>(&x);
-                  x = __floats2half2_rn(hi.x, hi.y); w.z = *reinterpret_cast<uint32_t*>(&x);
-                  x = __floats2half2_rn(hi.z, hi.w); w.w = *reinterpret_cast<uint32_t*>(&x);
-                }
-                *reinterpret_cast<uint4*>(orow + 16 * g) = w;
-              }
-            }
-          }
         }
       }
     }
@@ -3572,8 +3520,6 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     fill_common(bp.f, a);
     bp.delta = args->delta;
     bp.dq_accum = args->dq_accum;
-    bp.dq_counters = nullptr;
-    bp.dq = args->dq; bp.dq_sb = args->dq_sb; bp.dq_sh = args->dq_sh; bp.dq_ss = args->dq_ss;
     bp.dk = args->dk; bp.dk_sb = args->dk_sb; bp.dk_sh = args->dk_sh; bp.dk_ss = args->dk_ss;
     bp.dv = args->dv; bp.dv_sb = args->dv_sb; bp.dv_sh = args->dv_sh; bp.dv_ss = args->dv_ss;
     CUtensorMap tmQ, tmK, tmV, tmDO;
@@ -3592,15 +3538,8 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     const int nqt = (a.Sq + 127) / 128;
     // the workspace is sized for whole query tiles (include/ct_b200.h): B*H*ceil(Sq/128)*128*64 floats
     const size_t dq_elems = (size_t)a.B * a.H * nqt * FB_DQ_TILE;
-    // dq_accum_armed: the caller keeps the workspace (+ B*H int32 counters right behind it) zeroed between calls and
-    // the default kernel converts and re-zeroes it itself (last CTA of every head)
-    const bool fused_dq = args->dq_accum_armed != 0 && variant == 4 && tma_ok4(args->dq, args->dq_sb, args->dq_sh, args->dq_ss);
-    if (fused_dq) bp.dq_counters = reinterpret_cast<int*>(args->dq_accum + dq_elems);
-    else if (args->dq_accum_armed != 0)
-      CT_REQUIRE(false, CT_ERR_UNSUPPORTED, "ct_attn_bwd: dq_accum_armed needs the default backward kernel and a 16-byte aligned dq");
-    if (!fused_dq)
-      CT_CUDA_OK(cudaMemsetAsync(args->dq_accum, 0,
-                                 sizeof(float) * (dq_tiled ? dq_elems : (size_t)a.B * a.Sq * a.H * 64), st));
+    CT_CUDA_OK(cudaMemsetAsync(args->dq_accum, 0,
+                               sizeof(float) * (dq_tiled ? dq_elems : (size_t)a.B * a.Sq * a.H * 64), st));
     static bool attr = false;
     if (!attr) {
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
@@ -3651,7 +3590,6 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
         break;
     }
     CT_LAUNCH_OK();
-    if (fused_dq) return 0;
     const int64_t n = dq_tiled ? (int64_t)(dq_elems / 8) : (int64_t)a.B * a.Sq * a.H * 64 / 8;
     int64_t blocks = (n + 255) / 256;
     if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;

@@ -1,43 +1,125 @@
-// comm.cu — gradient-bucket all-reduce as plain CUDA kernels over NVLink/NVSwitch peer memory.
+// comm.cu — gradient-bucket all-reduce as plain CUDA kernels over NVLink 5 / NVSwitch peer memory.
 //
 // Replaces the ncclAllReduce calls that torch's DDP reducer issues for the reference
 // (examples/ft_bloom_DDP.py:99,126,135 `DDP(model, device_ids=[local_rank])`; README.md:46-52
 // describes the hand-rolled version: param sync, gradient buckets, overlapped reduction).
 //
-// Memory: every rank cudaMalloc()s one symmetric gradient buffer + one small signal buffer and
-// publishes cudaIpcMemHandles; Python (torch.distributed, used only as bootstrap) exchanges the 64-byte
-// handles and each rank maps every peer buffer (cudaIpcOpenMemHandle). The gradient arena
-// (arena.py) lives inside the symmetric buffer, so wgrad kernels write straight into NVLink-visible
-// memory and the reduction is in place.
+// Memory. Every rank owns one symmetric buffer (gradient arena + staging + a page of signal words). Two ways to
+// make it visible to the peers:
+//   * VMM + multicast (default where the driver offers it): cuMemCreate / cuMemMap, the allocation exported as a
+//     POSIX file descriptor that Python passes to the peers over a Unix socket (SCM_RIGHTS), every peer maps it
+//     (unicast pointers), and all ranks bind their allocation to ONE multicast object (cuMulticastCreate /
+//     cuMulticastBindMem): a store to the multicast address lands in every GPU's buffer, a `multimem.ld_reduce`
+//     returns the sum over all GPUs, added inside the NVSwitch (NVLS);
+//   * cudaMalloc + cudaIpcMemHandle (fallback): unicast peer pointers only.
+// The gradient arena (arena.py) lives inside the symmetric buffer, so wgrad kernels write straight into
+// NVLink-visible memory and the reduction is in place.
 //
-// ct_allreduce(offset, count): two-shot, one kernel per rank
+// All-reduce of a bucket [offset, offset+count), one kernel per rank:
 //   phase 0  signal "my data for epoch e is ready" to every peer, wait for all peers
-//   phase 1  rank r owns slice r of the range: 128-bit loads of that slice from all W ranks
-//            (peer reads over NVLink), fp32 sum in rank order (deterministic), * scale, 128-bit
-//            stores of the result to all W ranks (peer writes)
+//   phase 1  rank r owns slice r of the range
+//            NVLS:     v = multimem.ld_reduce.add(slice element)  (the switch reads all W copies and adds);
+//                      multimem.st(v * scale)                      (the switch writes all W copies)
+//                      -> per rank 1/W of the bucket crosses the SM twice, instead of (W-1)/W of it W-fold: a
+//                      handful of small CTAs keep NVLink busy, and the persistent GEMMs of backward keep their SMs;
+//            unicast:  128-bit loads of the slice from all W ranks, fp32 sum in rank order, * scale, 128-bit
+//                      stores of the result to all W ranks
 //   phase 2  last CTA signals "my slice is written everywhere", waits for all peers' signals
 // One-shot variant (each rank reads everything from every peer, writes only locally) for small,
-// latency-bound buckets. Bytes over NVLink per rank: two-shot 2*(W-1)/W * bytes, one-shot
-// (W-1) * bytes inbound.
+// latency-bound buckets. Every rank ends up with bit-identical bucket contents in all modes (one owner adds,
+// everybody receives its bits).
+//
+// Epochs live in DEVICE memory (a word of the local signal page, bumped by the last CTA of every collective):
+// the kernels take no per-call host counter, so a captured CUDA graph replays them correctly.
 #include "ct_common.cuh"
 #include "../../include/ct_b200.h"
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
+#include <unistd.h>
 #include <vector>
 
 namespace ct {
 
 constexpr int MAX_WORLD = 16;
+constexpr size_t SIG_BYTES = 4096;          // signal page behind the data (VMM mode) / own cudaMalloc (IPC mode)
+constexpr int SIG_COUNTER = 2 * MAX_WORLD;  // CTA counter (local use only)
+constexpr int SIG_EPOCH = 2 * MAX_WORLD + 1;  // epoch of the last finished collective (local use only)
+
+struct Drv {
+  bool ok = false;
+  CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*MemExport)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+  CUresult (*MemImport)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+  CUresult (*MemGetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  CUresult (*McCreate)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*) = nullptr;
+  CUresult (*McAddDevice)(CUmemGenericAllocationHandle, CUdevice) = nullptr;
+  CUresult (*McBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t,
+                        unsigned long long) = nullptr;
+  CUresult (*McGetGranularity)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags) = nullptr;
+  CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+  CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice) = nullptr;
+};
+
+static Drv& drv() {
+  static Drv d;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    bool ok = true;
+    auto get = [&](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess ||
+          *fn == nullptr)
+        ok = false;
+    };
+    get("cuMemCreate", (void**)&d.MemCreate);
+    get("cuMemRelease", (void**)&d.MemRelease);
+    get("cuMemAddressReserve", (void**)&d.MemAddressReserve);
+    get("cuMemAddressFree", (void**)&d.MemAddressFree);
+    get("cuMemMap", (void**)&d.MemMap);
+    get("cuMemUnmap", (void**)&d.MemUnmap);
+    get("cuMemSetAccess", (void**)&d.MemSetAccess);
+    get("cuMemExportToShareableHandle", (void**)&d.MemExport);
+    get("cuMemImportFromShareableHandle", (void**)&d.MemImport);
+    get("cuMemGetAllocationGranularity", (void**)&d.MemGetGranularity);
+    get("cuMulticastCreate", (void**)&d.McCreate);
+    get("cuMulticastAddDevice", (void**)&d.McAddDevice);
+    get("cuMulticastBindMem", (void**)&d.McBindMem);
+    get("cuMulticastGetGranularity", (void**)&d.McGetGranularity);
+    get("cuDeviceGet", (void**)&d.DeviceGet);
+    get("cuDeviceGetAttribute", (void**)&d.DeviceGetAttribute);
+    d.ok = ok;
+  });
+  return d;
+}
+
+#define CT_CU_OK(expr)                                                                    \
+  do {                                                                                    \
+    CUresult _r = (expr);                                                                 \
+    if (_r != CUDA_SUCCESS) {                                                             \
+      ct::set_error("%s:%d: %s -> CUresult %d", __FILE__, __LINE__, #expr, (int)_r);      \
+      return CT_ERR_COMM;                                                                 \
+    }                                                                                     \
+  } while (0)
 
 struct CommCtx {
   int rank = -1, world = 0, device = 0;
   bool ready = false;
-  float* data[MAX_WORLD] = {nullptr};        // symmetric gradient buffers (local at [rank])
-  uint32_t* sig[MAX_WORLD] = {nullptr};      // signal buffers: [0..W) ready flags, [W..2W) done flags,
-                                             // [2W] CTA counter (local use only)
-  size_t data_bytes = 0;
-  uint32_t epoch = 0;
-  std::vector<void*> opened;
+  bool vmm = false;                           // buffers come from cuMemCreate (else cudaMalloc + IPC)
+  float* data[MAX_WORLD] = {nullptr};         // symmetric buffers (local at [rank])
+  uint32_t* sig[MAX_WORLD] = {nullptr};       // signal words: [0..W) ready flags, [W..2W) done flags, counter, epoch
+  float* mc_data = nullptr;                   // multicast mapping of the same bytes on every rank (NVLS), or null
+  size_t data_bytes = 0;                      // usable floats * 4
+  size_t alloc_bytes = 0;                     // VMM: granularity-rounded size of the allocation (data + signal page)
+  CUmemGenericAllocationHandle mem = 0, mc = 0;
+  CUmemGenericAllocationHandle peer_mem[MAX_WORLD] = {0};
+  std::vector<void*> opened;                  // IPC mappings
 };
 static CommCtx g_comm;
 static std::mutex g_comm_mu;
@@ -45,8 +127,8 @@ static std::mutex g_comm_mu;
 struct ArParams {
   float* data[MAX_WORLD];
   uint32_t* sig[MAX_WORLD];
+  float* mc;
   int rank, world;
-  uint32_t epoch;
   int64_t offset, count;  // elements (count % 4 == 0, offset % 4 == 0)
   float scale;
 };
@@ -59,6 +141,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
   float4 v;
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -69,6 +156,21 @@ __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
 }
 __device__ __forceinline__ void st_peer_f4(float* p, float4 v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+// NVLS: one load returns the fp32 sum of the addressed 16 bytes over every GPU bound to the multicast object (the
+// NVSwitch reads the W copies and adds); one store writes all W copies.
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y),
                "f"(v.z), "f"(v.w)
                : "memory");
 }
@@ -94,87 +196,108 @@ __device__ __forceinline__ void wait_flags(const uint32_t* flags, int world, uin
   __syncthreads();
 }
 
+// Every collective kernel: epoch = (last finished epoch of this rank) + 1, read from device memory. All ranks run
+// the same sequence of collectives on their communication stream, so the counters agree without any host state.
+__device__ __forceinline__ uint32_t begin_collective(const ArParams& p) {
+  const uint32_t epoch = ld_volatile_u32(p.sig[p.rank] + SIG_EPOCH) + 1u;
+  if (blockIdx.x == 0 && (int)threadIdx.x < p.world) st_release_sys(p.sig[threadIdx.x] + p.rank, epoch);
+  wait_flags(p.sig[p.rank], p.world, epoch);
+  return epoch;
+}
+// The last CTA to get here publishes completion to the peers, waits for theirs and closes the epoch.
+__device__ __forceinline__ void end_collective(const ArParams& p, uint32_t epoch) {
+  uint32_t* my_sig = p.sig[p.rank];
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int last;
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(my_sig + SIG_COUNTER, 1u);
+    last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) my_sig[SIG_COUNTER] = 0;  // reset for the next call (stream-ordered)
+  if ((int)threadIdx.x < p.world) st_release_sys(p.sig[threadIdx.x] + MAX_WORLD + p.rank, epoch);
+  wait_flags(my_sig + MAX_WORLD, p.world, epoch);
+  if (threadIdx.x == 0) {
+    my_sig[SIG_EPOCH] = epoch;
+    __threadfence();
+  }
+}
+
 constexpr int AR_THREADS = 256;
 
-template <bool ONE_SHOT>
+// MODE 0 two-shot over unicast peer pointers, 1 one-shot, 2 two-shot through the multicast mapping (NVLS)
+template <int MODE>
 __global__ void __launch_bounds__(AR_THREADS, 6)  // <= 40 registers: fits beside a resident GEMM CTA
     allreduce_kernel(const ArParams p) {
   const int W = p.world, r = p.rank;
-  uint32_t* my_sig = p.sig[r];
-  // ---- phase 0: publish readiness, wait for everyone ----
-  if (blockIdx.x == 0 && (int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + r, p.epoch);
-  wait_flags(my_sig, W, p.epoch);
-
+  const uint32_t epoch = begin_collective(p);
   const int64_t nvec = p.count >> 2;
-  if (ONE_SHOT) {
-    // every rank reduces the whole range into its own buffer
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (MODE == 1) {
+    // every rank reduces the whole range; results are staged behind the range (nobody may overwrite its input
+    // while peers still read it) and copied back by a second kernel
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 mine;
       for (int q = 0; q < W; ++q) {
         const float4 v = ld_peer_f4(p.data[q] + p.offset + 4 * i);
-        if (q == r) mine = v;
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
-      (void)mine;
       acc.x *= p.scale; acc.y *= p.scale; acc.z *= p.scale; acc.w *= p.scale;
-      // results are staged: nobody may overwrite its input while peers still read it
-      // -> written after phase 2's barrier below (kept in registers is impossible for big ranges),
-      // so one-shot writes to a shadow half of the range instead: see host side (count doubled)
       st_peer_f4(p.data[r] + p.offset + p.count + 4 * i, acc);
     }
   } else {
-    // slice owned by this rank (multiple of 4 elements). Four independent 16-byte vectors per
-    // thread per iteration: W x 4 peer loads in flight per thread (NVLink latency ~2 us needs
-    // ~1.5 MB in flight per direction), small CTAs / few registers so they co-reside with the
-    // persistent GEMM CTAs of the backward pass.
+    // slice owned by this rank (multiple of 4 elements); four independent 16-byte vectors per thread per iteration
     const int64_t per = ((nvec + W - 1) / W);
     const int64_t v0 = min(nvec, per * r), v1 = min(nvec, per * (r + 1));
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = v0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v1; i += 4 * stride) {
       float4 acc[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-      for (int q = 0; q < W; ++q) {
-        float4 v[4];
+      if (MODE == 2) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int64_t idx = i + u * stride;
-          v[u] = idx < v1 ? ld_peer_f4(p.data[q] + p.offset + 4 * idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+          acc[u] = idx < v1 ? multimem_ld_reduce_f4(p.mc + p.offset + 4 * idx) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      } else {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
+        for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+        for (int q = 0; q < W; ++q) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int64_t idx = i + u * stride;
+            v[u] = idx < v1 ? ld_peer_f4(p.data[q] + p.offset + 4 * idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
+          }
         }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         acc[u].x *= p.scale; acc[u].y *= p.scale; acc[u].z *= p.scale; acc[u].w *= p.scale;
       }
-      for (int q = 0; q < W; ++q) {
+      if (MODE == 2) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int64_t idx = i + u * stride;
-          if (idx < v1) st_peer_f4(p.data[q] + p.offset + 4 * idx, acc[u]);
+          if (idx < v1) multimem_st_f4(p.mc + p.offset + 4 * idx, acc[u]);
+        }
+      } else {
+        for (int q = 0; q < W; ++q) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int64_t idx = i + u * stride;
+            if (idx < v1) st_peer_f4(p.data[q] + p.offset + 4 * idx, acc[u]);
+          }
         }
       }
     }
   }
-  // ---- phase 2: last CTA publishes completion and waits for the peers' completion ----
-  __threadfence_system();
-  __syncthreads();
-  __shared__ int last;
-  if (threadIdx.x == 0) {
-    const uint32_t prev = atomicAdd(my_sig + 2 * MAX_WORLD, 1u);
-    last = (prev == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!last) return;
-  if (threadIdx.x == 0) my_sig[2 * MAX_WORLD] = 0;  // reset for the next call (stream-ordered)
-  if ((int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + MAX_WORLD + r, p.epoch);
-  wait_flags(my_sig + MAX_WORLD, W, p.epoch);
+  end_collective(p, epoch);
 }
 
 // one-shot epilogue: copy the staged result back over the input (local, after the barrier)
@@ -187,27 +310,18 @@ __global__ void __launch_bounds__(256)
 // broadcast: every rank copies [offset, offset+count) from the root's buffer (after a barrier)
 __global__ void __launch_bounds__(512)
     broadcast_kernel(const ArParams p, int root) {
-  const int W = p.world, r = p.rank;
-  uint32_t* my_sig = p.sig[r];
-  if (blockIdx.x == 0 && (int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + r, p.epoch);
-  wait_flags(my_sig, W, p.epoch);
-  if (r != root) {
+  const uint32_t epoch = begin_collective(p);
+  if (p.rank != root) {
     const int64_t nvec = p.count >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x)
-      st_peer_f4(p.data[r] + p.offset + 4 * i, ld_peer_f4(p.data[root] + p.offset + 4 * i));
+      st_peer_f4(p.data[p.rank] + p.offset + 4 * i, ld_peer_f4(p.data[root] + p.offset + 4 * i));
   }
-  __threadfence_system();
-  __syncthreads();
-  __shared__ int last;
-  if (threadIdx.x == 0) {
-    const uint32_t prev = atomicAdd(my_sig + 2 * MAX_WORLD, 1u);
-    last = (prev == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!last) return;
-  if (threadIdx.x == 0) my_sig[2 * MAX_WORLD] = 0;
-  if ((int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + MAX_WORLD + r, p.epoch);
-  wait_flags(my_sig + MAX_WORLD, W, p.epoch);
+  end_collective(p, epoch);
+}
+
+__global__ void __launch_bounds__(32) comm_barrier_kernel(const ArParams p) {
+  const uint32_t epoch = begin_collective(p);
+  end_collective(p, epoch);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -218,18 +332,15 @@ __global__ void __launch_bounds__(512)
 // is: every rank publishes its T x H token gradients + token ids in the symmetric buffer, and every rank
 // scatter-adds ALL ranks' rows (scaled by 1/W) into its own, already averaged, table gradient:
 // (W-1) * T * H * 4 bytes inbound per rank (235 MB at W = 8) instead of 2 (W-1)/W x 1 GB.
+// (fp32 atomics: the table gradients of different ranks agree to rounding, not bit for bit.)
 struct EsParams {
-  float* data[MAX_WORLD];
-  uint32_t* sig[MAX_WORLD];
-  int rank, world;
-  uint32_t epoch;
+  ArParams a;
   int64_t hdr_off;    // float offset of the staging header: int64 T (tokens this rank staged)
   int64_t rows_off;   // float offset of the staged rows [cap, H] f32
   int64_t ids_off;    // float offset of the staged ids [cap] int64
   int64_t grad_off;   // float offset of the table gradient [V, H] in the LOCAL buffer
   int64_t H, V;
   long long padding_idx;
-  float scale;
 };
 
 __device__ __forceinline__ long long ld_peer_s64(const long long* p) {
@@ -240,92 +351,87 @@ __device__ __forceinline__ long long ld_peer_s64(const long long* p) {
 
 __global__ void __launch_bounds__(256)
     embed_scatter_allranks_kernel(const EsParams p) {
-  const int W = p.world, r = p.rank;
-  uint32_t* my_sig = p.sig[r];
-  if (blockIdx.x == 0 && (int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + r, p.epoch);
-  wait_flags(my_sig, W, p.epoch);
-
+  const int W = p.a.world, r = p.a.rank;
+  const uint32_t epoch = begin_collective(p.a);
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float* grad = p.data[r] + p.grad_off;
+  float* grad = p.a.data[r] + p.grad_off;
+  const float scale = p.a.scale;
   for (int k = 0; k < W; ++k) {
     const int q = (r + k) % W;  // own rows first, then the peers round-robin (spreads the NVLink load)
-    const long long Tq = ld_peer_s64(reinterpret_cast<const long long*>(p.data[q] + p.hdr_off));
-    const long long* ids = reinterpret_cast<const long long*>(p.data[q] + p.ids_off);
-    const float* rows = p.data[q] + p.rows_off;
+    const long long Tq = ld_peer_s64(reinterpret_cast<const long long*>(p.a.data[q] + p.hdr_off));
+    const long long* ids = reinterpret_cast<const long long*>(p.a.data[q] + p.ids_off);
+    const float* rows = p.a.data[q] + p.rows_off;
     for (int64_t t = warp0; t < Tq; t += nwarps) {
       const long long id = ld_peer_s64(ids + t);
       if (id < 0 || id >= p.V || id == p.padding_idx) continue;
       const float* src = rows + t * p.H;
       float* dst = grad + id * p.H;
-      for (int64_t c = lane * 4; c < p.H; c += 128) {
-        const float4 v = ld_peer_f4(src + c);
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(v.x * p.scale),
-                     "f"(v.y * p.scale), "f"(v.z * p.scale), "f"(v.w * p.scale)
-                     : "memory");
+      // eight 16-byte peer loads in flight per lane (a 1024-wide row in one go) BEFORE the first reduction: a
+      // volatile red after every load serialised them on the NVLink round trip
+      for (int64_t c0 = 0; c0 < p.H; c0 += 1024) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int64_t c = c0 + u * 128 + lane * 4;
+          v[u] = c < p.H ? ld_peer_f4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int64_t c = c0 + u * 128 + lane * 4;
+          if (c < p.H)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(v[u].x * scale),
+                         "f"(v[u].y * scale), "f"(v[u].z * scale), "f"(v[u].w * scale)
+                         : "memory");
+        }
       }
     }
   }
-  // completion barrier: nobody restages while a peer still reads
-  __threadfence_system();
-  __syncthreads();
-  __shared__ int last;
-  if (threadIdx.x == 0) {
-    const uint32_t prev = atomicAdd(my_sig + 2 * MAX_WORLD, 1u);
-    last = (prev == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!last) return;
-  if (threadIdx.x == 0) my_sig[2 * MAX_WORLD] = 0;
-  if ((int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + MAX_WORLD + r, p.epoch);
-  wait_flags(my_sig + MAX_WORLD, W, p.epoch);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Copy-engine transport (comm mode "ce"). r01i showed what the register-staged kernel above costs when it shares
-// SMs with the persistent GEMMs of the backward pass: 48 CTAs hide the exchange but slow the GEMMs by 3.3 ms per
-// step, fewer CTAs leave it exposed. The alternative keeps the SMs out of the transport altogether: the two
-// NVLink legs of the two-shot all-reduce are cudaMemcpyAsync peer copies (DMA engines), and the only kernels are a
-// one-CTA flag barrier and an HBM-bound local reduction of the W staged slices:
-//   barrier | pull slice r of every peer into local staging | reduce (rank order) | push the result into every
-//   peer's slice r | barrier
-// Every slice is reduced by exactly one rank and then copied, so all ranks end up bit-identical.
-__global__ void __launch_bounds__(32) comm_barrier_kernel(const ArParams p) {
-  const int W = p.world, r = p.rank;
-  if ((int)threadIdx.x < W) st_release_sys(p.sig[threadIdx.x] + r, p.epoch);
-  wait_flags(p.sig[r], W, p.epoch);
-}
-
-// dst[i] = scale * sum over ranks q in rank order of (q == rank ? dst[i] : staged[slot(q)][i]); slots are the peers
-// in ascending rank order, `stride` floats apart
-__global__ void __launch_bounds__(256)
-    reduce_slices_kernel(float* __restrict__ dst, const float* __restrict__ staged, int64_t stride, int world,
-                         int rank, int64_t nvec, float scale) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int slot = 0;
-    for (int q = 0; q < world; ++q) {
-      const float4 v = q == rank ? reinterpret_cast<const float4*>(dst)[i]
-                                 : __ldcs(reinterpret_cast<const float4*>(staged + (int64_t)(slot++) * stride) + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
-    reinterpret_cast<float4*>(dst)[i] = acc;
-  }
+  end_collective(p.a, epoch);  // nobody restages while a peer still reads
 }
 
 static void fill_params(ArParams& p, int64_t offset, int64_t count, float scale) {
   for (int q = 0; q < g_comm.world; ++q) { p.data[q] = g_comm.data[q]; p.sig[q] = g_comm.sig[q]; }
+  p.mc = g_comm.mc_data;
   p.rank = g_comm.rank; p.world = g_comm.world;
-  p.epoch = ++g_comm.epoch;
   p.offset = offset; p.count = count; p.scale = scale;
+}
+
+static int set_timeout(int device) {
+  const char* e = getenv("CT_COMM_TIMEOUT_S");
+  const double secs = e ? atof(e) : 1800.0;
+  int khz = 2000000;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+  const long long cycles = secs > 0 ? (long long)(secs * 1e3 * (double)khz) : 0;
+  CT_CUDA_OK(cudaMemcpyToSymbol(g_wait_timeout_cycles, &cycles, sizeof(cycles)));
+  return 0;
+}
+
+static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int map_rw(CUmemGenericAllocationHandle h, size_t bytes, size_t gran, int device, CUdeviceptr* out) {
+  Drv& D = drv();
+  CUdeviceptr va = 0;
+  CT_CU_OK(D.MemAddressReserve(&va, bytes, gran, 0, 0));
+  CT_CU_OK(D.MemMap(va, bytes, 0, h, 0));
+  CUmemAccessDesc acc;
+  memset(&acc, 0, sizeof(acc));
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = device;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  CT_CU_OK(D.MemSetAccess(va, bytes, &acc, 1));
+  *out = va;
+  return 0;
 }
 
 }  // namespace ct
 
 using namespace ct;
 
+// ---------------------------------------------------------------------------------------------------
+// set-up, IPC flavour
+// ---------------------------------------------------------------------------------------------------
 extern "C" int ct_comm_init(int rank, int world, int device, size_t data_bytes, void** local_data,
                             void* data_handle_out, void* sig_handle_out) {
   std::lock_guard<std::mutex> lk(g_comm_mu);
@@ -338,30 +444,24 @@ extern "C" int ct_comm_init(int rank, int world, int device, size_t data_bytes, 
   float* d = nullptr;
   uint32_t* s = nullptr;
   CT_CUDA_OK(cudaMalloc(&d, data_bytes));
-  CT_CUDA_OK(cudaMalloc(&s, sizeof(uint32_t) * (2 * MAX_WORLD + 8)));
+  CT_CUDA_OK(cudaMalloc(&s, SIG_BYTES));
   CT_CUDA_OK(cudaMemset(d, 0, data_bytes));
-  CT_CUDA_OK(cudaMemset(s, 0, sizeof(uint32_t) * (2 * MAX_WORLD + 8)));
+  CT_CUDA_OK(cudaMemset(s, 0, SIG_BYTES));
   CT_CUDA_OK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)data_handle_out, d));
   CT_CUDA_OK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)sig_handle_out, s));
-  {
-    const char* e = getenv("CT_COMM_TIMEOUT_S");
-    const double secs = e ? atof(e) : 1800.0;
-    int khz = 2000000;
-    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
-    const long long cycles = secs > 0 ? (long long)(secs * 1e3 * (double)khz) : 0;
-    CT_CUDA_OK(cudaMemcpyToSymbol(g_wait_timeout_cycles, &cycles, sizeof(cycles)));
-  }
+  int rc = set_timeout(device);
+  if (rc) return rc;
   g_comm.rank = rank; g_comm.world = world; g_comm.device = device;
+  g_comm.vmm = false;
   g_comm.data[rank] = d; g_comm.sig[rank] = s;
   g_comm.data_bytes = data_bytes;
-  g_comm.epoch = 0;
   *local_data = d;
   return 0;
 }
 
 extern "C" int ct_comm_connect(const void* data_handles, const void* sig_handles) {
   std::lock_guard<std::mutex> lk(g_comm_mu);
-  CT_REQUIRE(g_comm.rank >= 0, CT_ERR_COMM, "ct_comm_connect: ct_comm_init first");
+  CT_REQUIRE(g_comm.rank >= 0 && !g_comm.vmm, CT_ERR_COMM, "ct_comm_connect: ct_comm_init first");
   CT_REQUIRE(data_handles && sig_handles, CT_ERR_BAD_ARG, "ct_comm_connect: null handles");
   const cudaIpcMemHandle_t* dh = (const cudaIpcMemHandle_t*)data_handles;
   const cudaIpcMemHandle_t* sh = (const cudaIpcMemHandle_t*)sig_handles;
@@ -380,6 +480,175 @@ extern "C" int ct_comm_connect(const void* data_handles, const void* sig_handles
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// set-up, VMM + multicast flavour
+// ---------------------------------------------------------------------------------------------------
+extern "C" int ct_comm_vmm_supported(int device, int* vmm_ok, int* multicast_ok) {
+  CT_REQUIRE(vmm_ok && multicast_ok, CT_ERR_BAD_ARG, "ct_comm_vmm_supported: null out");
+  *vmm_ok = *multicast_ok = 0;
+  Drv& D = drv();
+  if (!D.ok) return 0;
+  CT_CUDA_OK(cudaSetDevice(device));
+  CT_CUDA_OK(cudaFree(0));
+  CUdevice dev;
+  CT_CU_OK(D.DeviceGet(&dev, device));
+  int a = 0, b = 0, c = 0;
+  D.DeviceGetAttribute(&a, CU_DEVICE_ATTRIBUTE_VIRTUAL_MEMORY_MANAGEMENT_SUPPORTED, dev);
+  D.DeviceGetAttribute(&b, CU_DEVICE_ATTRIBUTE_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR_SUPPORTED, dev);
+  D.DeviceGetAttribute(&c, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev);
+  *vmm_ok = (a && b) ? 1 : 0;
+  *multicast_ok = (a && b && c) ? 1 : 0;
+  return 0;
+}
+
+extern "C" int ct_comm_vmm_init(int rank, int world, int device, size_t data_bytes, void** local_data,
+                                int* local_fd_out) {
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  CT_REQUIRE(world >= 1 && world <= MAX_WORLD && rank >= 0 && rank < world, CT_ERR_BAD_ARG,
+             "ct_comm_vmm_init: bad rank/world %d/%d", rank, world);
+  CT_REQUIRE(!g_comm.ready && g_comm.rank < 0, CT_ERR_COMM, "ct_comm_vmm_init: already initialised");
+  CT_REQUIRE(local_data && local_fd_out, CT_ERR_BAD_ARG, "ct_comm_vmm_init: null out");
+  Drv& D = drv();
+  CT_REQUIRE(D.ok, CT_ERR_UNSUPPORTED, "ct_comm_vmm_init: driver VMM / multicast entry points not available");
+  CT_CUDA_OK(cudaSetDevice(device));
+  CT_CUDA_OK(cudaFree(0));  // primary context current on this thread
+  CUmemAllocationProp prop;
+  memset(&prop, 0, sizeof(prop));
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = device;
+  prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  size_t gran = 0;
+  CT_CU_OK(D.MemGetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+  data_bytes = round_up(data_bytes, 4096);
+  {
+    // the multicast object wants its own (possibly larger) granularity for size and binding offsets
+    CUmulticastObjectProp mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.numDevices = (unsigned)world;
+    mp.size = round_up(data_bytes + SIG_BYTES, gran);
+    mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t mg = 0;
+    if (D.McGetGranularity(&mg, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && mg > gran) gran = mg;
+  }
+  const size_t total = round_up(data_bytes + SIG_BYTES, gran);
+  CUmemGenericAllocationHandle h = 0;
+  CT_CU_OK(D.MemCreate(&h, total, &prop, 0));
+  CUdeviceptr va = 0;
+  int rc = map_rw(h, total, gran, device, &va);
+  if (rc) return rc;
+  CT_CUDA_OK(cudaMemset((void*)va, 0, total));
+  CT_CUDA_OK(cudaDeviceSynchronize());
+  int fd = -1;
+  CT_CU_OK(D.MemExport(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+  rc = set_timeout(device);
+  if (rc) return rc;
+  g_comm.rank = rank; g_comm.world = world; g_comm.device = device;
+  g_comm.vmm = true;
+  g_comm.mem = h;
+  g_comm.alloc_bytes = total;
+  g_comm.data_bytes = data_bytes;
+  g_comm.data[rank] = (float*)va;
+  g_comm.sig[rank] = (uint32_t*)((char*)va + data_bytes);
+  *local_data = (void*)va;
+  *local_fd_out = fd;
+  return 0;
+}
+
+// peer_fds: [world] file descriptors received from the peers (entry [rank] ignored); the caller closes them
+extern "C" int ct_comm_vmm_connect(const int* peer_fds) {
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  CT_REQUIRE(g_comm.rank >= 0 && g_comm.vmm, CT_ERR_COMM, "ct_comm_vmm_connect: ct_comm_vmm_init first");
+  CT_REQUIRE(peer_fds, CT_ERR_BAD_ARG, "ct_comm_vmm_connect: null fds");
+  Drv& D = drv();
+  CUmemAllocationProp prop;
+  memset(&prop, 0, sizeof(prop));
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = g_comm.device;
+  prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  size_t gran = 0;
+  CT_CU_OK(D.MemGetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+  for (int q = 0; q < g_comm.world; ++q) {
+    if (q == g_comm.rank) continue;
+    CUmemGenericAllocationHandle ph = 0;
+    CT_CU_OK(D.MemImport(&ph, (void*)(uintptr_t)peer_fds[q], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+    CUdeviceptr va = 0;
+    int rc = map_rw(ph, g_comm.alloc_bytes, gran, g_comm.device, &va);
+    if (rc) return rc;
+    g_comm.peer_mem[q] = ph;
+    g_comm.data[q] = (float*)va;
+    g_comm.sig[q] = (uint32_t*)((char*)va + g_comm.data_bytes);
+  }
+  g_comm.ready = true;
+  return 0;
+}
+
+// Multicast object over the symmetric buffers: rank 0 creates it (and exports a descriptor for the peers), everyone
+// else imports; then ALL ranks add their device (barrier), bind their allocation and map the object (barrier).
+extern "C" int ct_comm_mc_create(int* mc_fd_out) {
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  CT_REQUIRE(g_comm.ready && g_comm.vmm && mc_fd_out, CT_ERR_COMM, "ct_comm_mc_create: VMM comm not connected");
+  Drv& D = drv();
+  CUmulticastObjectProp mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.numDevices = (unsigned)g_comm.world;
+  mp.size = g_comm.alloc_bytes;
+  mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  CT_CU_OK(D.McCreate(&g_comm.mc, &mp));
+  int fd = -1;
+  CT_CU_OK(D.MemExport(&fd, g_comm.mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+  *mc_fd_out = fd;
+  return 0;
+}
+
+extern "C" int ct_comm_mc_import(int mc_fd) {
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  CT_REQUIRE(g_comm.ready && g_comm.vmm, CT_ERR_COMM, "ct_comm_mc_import: VMM comm not connected");
+  CT_CU_OK(drv().MemImport(&g_comm.mc, (void*)(uintptr_t)mc_fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+  return 0;
+}
+
+extern "C" int ct_comm_mc_add_device(void) {
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  CT_REQUIRE(g_comm.ready && g_comm.vmm && g_comm.mc != 0, CT_ERR_COMM, "ct_comm_mc_add_device: no multicast object");
+  Drv& D = drv();
+  CUdevice dev;
+  CT_CU_OK(D.DeviceGet(&dev, g_comm.device));
+  CT_CU_OK(D.McAddDevice(g_comm.mc, dev));
+  return 0;
+}
+
+extern "C" int ct_comm_mc_bind(void) {
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  CT_REQUIRE(g_comm.ready && g_comm.vmm && g_comm.mc != 0, CT_ERR_COMM, "ct_comm_mc_bind: no multicast object");
+  Drv& D = drv();
+  CT_CU_OK(D.McBindMem(g_comm.mc, 0, g_comm.mem, 0, g_comm.alloc_bytes, 0));
+  CUmulticastObjectProp mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.numDevices = (unsigned)g_comm.world;
+  mp.size = g_comm.alloc_bytes;
+  mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  size_t mg = 0;
+  CT_CU_OK(D.McGetGranularity(&mg, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED));
+  CUdeviceptr va = 0;
+  int rc = map_rw(g_comm.mc, g_comm.alloc_bytes, mg, g_comm.device, &va);
+  if (rc) return rc;
+  g_comm.mc_data = (float*)va;
+  return 0;
+}
+
+// flags[0] = buffers come from the VMM API, flags[1] = multicast (NVLS) mapping present
+extern "C" int ct_comm_info(int* flags) {
+  CT_REQUIRE(flags, CT_ERR_BAD_ARG, "ct_comm_info: null out");
+  flags[0] = g_comm.ready && g_comm.vmm ? 1 : 0;
+  flags[1] = g_comm.ready && g_comm.mc_data != nullptr ? 1 : 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// collectives
+// ---------------------------------------------------------------------------------------------------
 extern "C" int ct_allreduce_bucket(int64_t offset, int64_t count, float scale, int mode, int max_ctas,
                                    void* stream) {
   CT_REQUIRE(g_comm.ready, CT_ERR_COMM, "ct_allreduce_bucket: comm not initialised");
@@ -387,24 +656,22 @@ extern "C" int ct_allreduce_bucket(int64_t offset, int64_t count, float scale, i
                  (size_t)(offset + count) * 4 <= g_comm.data_bytes,
              CT_ERR_BAD_ARG, "ct_allreduce_bucket: range [%lld,+%lld) must be 16-byte aligned and inside the buffer",
              (long long)offset, (long long)count);
-  CT_REQUIRE(mode == 0 || mode == 1, CT_ERR_BAD_ARG, "ct_allreduce_bucket: mode 0 (auto/two-shot) or 1 (one-shot)");
+  CT_REQUIRE(mode >= 0 && mode <= 3, CT_ERR_BAD_ARG,
+             "ct_allreduce_bucket: mode 0 (auto), 1 (one-shot), 2 (NVLS multimem), 3 (two-shot unicast)");
+  CT_REQUIRE(mode != 2 || g_comm.mc_data != nullptr, CT_ERR_UNSUPPORTED, "ct_allreduce_bucket: no multicast mapping");
   if (count == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   ArParams p;
-  {
-    std::lock_guard<std::mutex> lk(g_comm_mu);
-    fill_params(p, offset, count, scale);
-  }
-  if (max_ctas <= 0) max_ctas = 64;
+  fill_params(p, offset, count, scale);
+  if (mode == 0) mode = g_comm.mc_data != nullptr ? 2 : 3;
   {
     // same shared-memory carve-out as the big GEMM / attention kernels so that an all-reduce CTA can
     // be co-resident with them (an SM cannot host CTAs that want different L1/shared splits)
     static bool carve = false;
     if (!carve) {
-      cudaFuncSetAttribute(allreduce_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           cudaSharedmemCarveoutMaxShared);
-      cudaFuncSetAttribute(allreduce_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(allreduce_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(allreduce_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(allreduce_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       carve = true;
     }
   }
@@ -413,20 +680,23 @@ extern "C" int ct_allreduce_bucket(int64_t offset, int64_t count, float scale, i
     // one-shot needs a staging area of `count` floats right after the range
     CT_REQUIRE((size_t)(offset + 2 * count) * 4 <= g_comm.data_bytes, CT_ERR_WORKSPACE,
                "ct_allreduce_bucket: one-shot needs a staging area after the range");
+    if (max_ctas <= 0) max_ctas = 64;
     int64_t ctas = (nvec + AR_THREADS - 1) / AR_THREADS;
     if (ctas > max_ctas) ctas = max_ctas;
-    allreduce_kernel<true><<<(unsigned)ctas, AR_THREADS, 0, st>>>(p);
+    allreduce_kernel<1><<<(unsigned)ctas, AR_THREADS, 0, st>>>(p);
     CT_LAUNCH_OK();
     copy_f4_kernel<<<(unsigned)ctas, 256, 0, st>>>(g_comm.data[g_comm.rank] + offset,
                                                     g_comm.data[g_comm.rank] + offset + count, nvec);
     CT_LAUNCH_OK();
     return 0;
   }
+  if (max_ctas <= 0) max_ctas = mode == 2 ? 16 : 64;
   int64_t per = (nvec + g_comm.world - 1) / g_comm.world;
   int64_t ctas = (per + 4 * AR_THREADS - 1) / (4 * AR_THREADS);
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
-  allreduce_kernel<false><<<(unsigned)ctas, AR_THREADS, 0, st>>>(p);
+  if (mode == 2) allreduce_kernel<2><<<(unsigned)ctas, AR_THREADS, 0, st>>>(p);
+  else allreduce_kernel<0><<<(unsigned)ctas, AR_THREADS, 0, st>>>(p);
   CT_LAUNCH_OK();
   return 0;
 }
@@ -442,14 +712,9 @@ extern "C" int ct_embedding_bwd_allranks(int64_t hdr_offset, int64_t rows_offset
                  (size_t)ids_offset <= nfl && (size_t)(grad_offset + V * H) <= nfl,
              CT_ERR_BAD_ARG, "ct_embedding_bwd_allranks: offsets must be aligned and inside the symmetric buffer");
   EsParams p;
-  {
-    std::lock_guard<std::mutex> lk(g_comm_mu);
-    for (int q = 0; q < g_comm.world; ++q) { p.data[q] = g_comm.data[q]; p.sig[q] = g_comm.sig[q]; }
-    p.rank = g_comm.rank; p.world = g_comm.world;
-    p.epoch = ++g_comm.epoch;
-  }
+  fill_params(p.a, 0, 0, scale);
   p.hdr_off = hdr_offset; p.rows_off = rows_offset; p.ids_off = ids_offset; p.grad_off = grad_offset;
-  p.H = H; p.V = V; p.padding_idx = (long long)padding_idx; p.scale = scale;
+  p.H = H; p.V = V; p.padding_idx = (long long)padding_idx;
   if (max_ctas <= 0) max_ctas = sm_count() * 2;
   embed_scatter_allranks_kernel<<<(unsigned)max_ctas, 256, 0, (cudaStream_t)stream>>>(p);
   CT_LAUNCH_OK();
@@ -459,55 +724,8 @@ extern "C" int ct_embedding_bwd_allranks(int64_t hdr_offset, int64_t rows_offset
 extern "C" int ct_comm_barrier(void* stream) {
   CT_REQUIRE(g_comm.ready, CT_ERR_COMM, "ct_comm_barrier: comm not initialised");
   ArParams p;
-  {
-    std::lock_guard<std::mutex> lk(g_comm_mu);
-    fill_params(p, 0, 0, 1.f);
-  }
+  fill_params(p, 0, 0, 1.f);
   comm_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
-  CT_LAUNCH_OK();
-  return 0;
-}
-
-// copy-engine legs: `count` floats between the symmetric buffer of `peer` (offset in floats) and local memory
-extern "C" int ct_comm_pull(int peer, int64_t peer_offset, void* dst_local, int64_t count, void* stream) {
-  CT_REQUIRE(g_comm.ready, CT_ERR_COMM, "ct_comm_pull: comm not initialised");
-  CT_REQUIRE(peer >= 0 && peer < g_comm.world && dst_local && peer_offset >= 0 && count >= 0 &&
-                 (size_t)(peer_offset + count) * 4 <= g_comm.data_bytes,
-             CT_ERR_BAD_ARG, "ct_comm_pull: bad peer / range");
-  if (count == 0) return 0;
-  CT_CUDA_OK(cudaMemcpyAsync(dst_local, g_comm.data[peer] + peer_offset, (size_t)count * 4, cudaMemcpyDeviceToDevice,
-                             (cudaStream_t)stream));
-  return 0;
-}
-
-extern "C" int ct_comm_push(int peer, int64_t peer_offset, int64_t local_offset, int64_t count, void* stream) {
-  CT_REQUIRE(g_comm.ready, CT_ERR_COMM, "ct_comm_push: comm not initialised");
-  CT_REQUIRE(peer >= 0 && peer < g_comm.world && peer_offset >= 0 && local_offset >= 0 && count >= 0 &&
-                 (size_t)(peer_offset + count) * 4 <= g_comm.data_bytes &&
-                 (size_t)(local_offset + count) * 4 <= g_comm.data_bytes,
-             CT_ERR_BAD_ARG, "ct_comm_push: bad peer / range");
-  if (count == 0) return 0;
-  CT_CUDA_OK(cudaMemcpyAsync(g_comm.data[peer] + peer_offset, g_comm.data[g_comm.rank] + local_offset, (size_t)count * 4,
-                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-  return 0;
-}
-
-// local_offset: the slice this rank owns (inside its symmetric buffer); staged: (world-1) slices, `stride` floats
-// apart, peers in ascending rank order. count % 4 == 0, everything 16-byte aligned.
-extern "C" int ct_comm_reduce_slices(int64_t local_offset, const float* staged, int64_t stride, int64_t count,
-                                     float scale, int max_ctas, void* stream) {
-  CT_REQUIRE(g_comm.ready, CT_ERR_COMM, "ct_comm_reduce_slices: comm not initialised");
-  CT_REQUIRE(staged && local_offset >= 0 && count >= 0 && (count % 4) == 0 && (local_offset % 4) == 0 &&
-                 (stride % 4) == 0 && stride >= count && ((uintptr_t)staged & 15) == 0 &&
-                 (size_t)(local_offset + count) * 4 <= g_comm.data_bytes,
-             CT_ERR_BAD_ARG, "ct_comm_reduce_slices: bad range / alignment");
-  if (count == 0) return 0;
-  const int64_t nvec = count >> 2;
-  int64_t ctas = (nvec + 255) / 256;
-  if (max_ctas <= 0) max_ctas = sm_count() * 4;
-  if (ctas > max_ctas) ctas = max_ctas;
-  reduce_slices_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(
-      g_comm.data[g_comm.rank] + local_offset, staged, stride, g_comm.world, g_comm.rank, nvec, scale);
   CT_LAUNCH_OK();
   return 0;
 }
@@ -519,10 +737,7 @@ extern "C" int ct_broadcast(int64_t offset, int64_t count, int root, void* strea
              CT_ERR_BAD_ARG, "ct_broadcast: bad range/root");
   if (count == 0) return 0;
   ArParams p;
-  {
-    std::lock_guard<std::mutex> lk(g_comm_mu);
-    fill_params(p, offset, count, 1.f);
-  }
+  fill_params(p, offset, count, 1.f);
   broadcast_kernel<<<32, 512, 0, (cudaStream_t)stream>>>(p, root);
   CT_LAUNCH_OK();
   return 0;
@@ -532,10 +747,26 @@ extern "C" int ct_comm_finalize(void) {
   std::lock_guard<std::mutex> lk(g_comm_mu);
   if (g_comm.rank < 0) return 0;
   cudaDeviceSynchronize();  // teardown only
-  for (void* p : g_comm.opened) cudaIpcCloseMemHandle(p);
-  g_comm.opened.clear();
-  if (g_comm.data[g_comm.rank]) cudaFree(g_comm.data[g_comm.rank]);
-  if (g_comm.sig[g_comm.rank]) cudaFree(g_comm.sig[g_comm.rank]);
+  if (g_comm.vmm) {
+    Drv& D = drv();
+    if (g_comm.mc_data) {
+      D.MemUnmap((CUdeviceptr)g_comm.mc_data, g_comm.alloc_bytes);
+      D.MemAddressFree((CUdeviceptr)g_comm.mc_data, g_comm.alloc_bytes);
+    }
+    for (int q = 0; q < g_comm.world; ++q) {
+      if (!g_comm.data[q]) continue;
+      D.MemUnmap((CUdeviceptr)g_comm.data[q], g_comm.alloc_bytes);
+      D.MemAddressFree((CUdeviceptr)g_comm.data[q], g_comm.alloc_bytes);
+      if (q != g_comm.rank && g_comm.peer_mem[q]) D.MemRelease(g_comm.peer_mem[q]);
+    }
+    if (g_comm.mc) D.MemRelease(g_comm.mc);
+    if (g_comm.mem) D.MemRelease(g_comm.mem);
+  } else {
+    for (void* p : g_comm.opened) cudaIpcCloseMemHandle(p);
+    g_comm.opened.clear();
+    if (g_comm.data[g_comm.rank]) cudaFree(g_comm.data[g_comm.rank]);
+    if (g_comm.sig[g_comm.rank]) cudaFree(g_comm.sig[g_comm.rank]);
+  }
   g_comm = CommCtx();
   return 0;
 }

@@ -16,10 +16,13 @@ B200 design
     gradients have been enqueued (functional.grad_written) — the all-reduce kernel itself waits for
     the peers with flags in the same symmetric memory;
   * averaging (1/world) is fused into the all-reduce kernel;
-  * `comm="ce"` (not yet run on GPUs — written after the round's GPU budget was spent): same buckets, same
-    symmetric buffer, but the two NVLink legs of the two-shot all-reduce are peer copies on the DMA engines and the
-    only kernels are a one-CTA flag barrier and a local reduction (csrc/comm.cu), so the persistent GEMMs of the
-    backward pass keep every SM;
+  * where the driver offers it the symmetric buffer is a cuMemCreate allocation bound to an NVLink MULTICAST object
+    (file descriptors passed between the ranks over a Unix socket): the bucket all-reduce then adds inside the
+    NVSwitch (`multimem.ld_reduce` / `multimem.st`, csrc/comm.cu) and a rank only touches 1/W of a bucket — 16 small
+    CTAs instead of 48 register-staged ones beside the persistent GEMMs of backward. Fallback: cudaMalloc + IPC
+    handles, two-shot over unicast peer pointers;
+  * collective epochs live in device memory, so a whole training step — buckets included — can be captured in a CUDA
+    graph and replayed (graphs.GraphedTrainStep);
   * `comm="nccl"` keeps torch.distributed.all_reduce (NCCL on GPUs, gloo in the CPU tests) on the
     same bucket layout as the baseline/oracle.
 Parameters used more than once per step (tied embedding / lm_head) are reduced when the last of
@@ -31,6 +34,7 @@ kernel of backward, fully hidden), and the token-row gradients are exchanged spa
 """
 import ctypes
 import os
+import socket
 
 import torch
 import torch.distributed as dist
@@ -85,10 +89,14 @@ class DistributedDataParallel(torch.nn.Module):
         self.device = params[0].device
         on_gpu = self.device.type == "cuda"
         self.comm = comm or os.environ.get("CT_DDP_COMM") or ("p2p" if on_gpu else "nccl")
-        if self.comm in ("p2p", "ce") and not on_gpu:
-            raise RuntimeError("comm='%s' needs CUDA parameters" % self.comm)
-        self._peer_mem = self.comm in ("p2p", "ce")
-        self.max_ctas = int(os.environ.get("CT_DDP_CTAS", max_ctas))
+        if self.comm not in ("p2p", "nccl"):
+            raise ValueError("comm must be 'p2p' (peer-memory kernels) or 'nccl' (library collective), got %r" % self.comm)
+        if self.comm == "p2p" and not on_gpu:
+            raise RuntimeError("comm='p2p' needs CUDA parameters")
+        self._peer_mem = self.comm == "p2p"
+        self.nvls = False
+        self.max_ctas = int(os.environ.get("CT_DDP_CTAS", 0)) or None  # None: 16 with NVLS, else `max_ctas`
+        self._max_ctas_unicast = max_ctas
         self.final_ctas = int(os.environ.get("CT_DDP_FINAL_CTAS", 148))
         grad_buf = None
         n_total = sum((p.numel() + 63) // 64 * 64 for p in params)
@@ -154,12 +162,73 @@ class DistributedDataParallel(torch.nn.Module):
             p._ct_embedding_bwd_override = self._sparse_embedding_bwd
 
     # ---------------------------------------------------------------- P2P bootstrap
+    def _all_ok(self, ok):
+        """Do ALL ranks agree that a bootstrap stage succeeded? (torch.distributed is the bootstrap channel.)"""
+        t = torch.tensor([1 if ok else 0], device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(int(t))
+
+    def _exchange_fds(self, tag, send_fd, senders, receivers):
+        """Pass open file descriptors between the local ranks over abstract Unix sockets (SCM_RIGHTS): every rank in
+        `senders` sends `send_fd` to every OTHER rank in `receivers`. Returns {sender rank: fd} on the receivers."""
+        base = "\0ct_b200_%s_%s_%s_" % (os.environ.get("MASTER_PORT", "0"), os.getuid(), tag)
+        got = {}
+        srv = None
+        if self.rank in receivers:
+            srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            srv.bind(base + str(self.rank))
+            srv.listen(self.world)
+        dist.barrier(group=self.group)  # every listener is up
+        try:
+            if self.rank in senders:
+                for q in receivers:
+                    if q == self.rank:
+                        continue
+                    c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                    c.connect(base + str(q))
+                    socket.send_fds(c, [bytes([self.rank])], [send_fd])
+                    c.close()
+            if srv is not None:
+                for _ in [q for q in senders if q != self.rank]:
+                    conn, _addr = srv.accept()
+                    msg, fds, _flags, _a = socket.recv_fds(conn, 16, 1)
+                    got[msg[0]] = fds[0]
+                    conn.close()
+        finally:
+            if srv is not None:
+                srv.close()
+        dist.barrier(group=self.group)
+        return got
+
     def _init_p2p(self, n_total):
         lib = _lib.load()
+        nbytes = n_total * 4
         local = ctypes.c_void_p()
+        everyone = list(range(self.world))
+        vmm_ok, mc_ok = ctypes.c_int(0), ctypes.c_int(0)
+        if os.environ.get("CT_DDP_VMM", "1") != "0":
+            lib.ct_comm_vmm_supported(self.device.index, ctypes.byref(vmm_ok), ctypes.byref(mc_ok))
+        if self._all_ok(bool(vmm_ok.value)):
+            fd = ctypes.c_int(-1)
+            ok = lib.ct_comm_vmm_init(self.rank, self.world, self.device.index, nbytes, ctypes.byref(local),
+                                      ctypes.byref(fd)) == 0
+            err = "" if ok else _lib.last_error()
+            if self._all_ok(ok):
+                peer = self._exchange_fds("mem", fd.value, everyone, everyone)
+                arr = (ctypes.c_int * self.world)(*[peer.get(q, -1) for q in range(self.world)])
+                ok = lib.ct_comm_vmm_connect(arr) == 0
+                err = "" if ok else _lib.last_error()
+                for f in list(peer.values()) + [fd.value]:
+                    os.close(f)
+                if self._all_ok(ok):
+                    self._init_multicast(lib, bool(mc_ok.value))
+                    return torch.as_tensor(_CudaView(local.value, n_total), device=self.device)
+            if self.rank == 0 and err:
+                print("[cleantransformer_b200.ddp] VMM peer memory unavailable (%s): falling back to IPC handles" % err,
+                      flush=True)
+            lib.ct_comm_finalize()
         dh = ctypes.create_string_buffer(64)
         sh = ctypes.create_string_buffer(64)
-        nbytes = n_total * 4
         _lib.check(lib.ct_comm_init(self.rank, self.world, self.device.index, nbytes, ctypes.byref(local), dh, sh),
                    "ct_comm_init")
         gathered = [None] * self.world
@@ -169,6 +238,42 @@ class DistributedDataParallel(torch.nn.Module):
         _lib.check(lib.ct_comm_connect(dhs, shs), "ct_comm_connect")
         dist.barrier(group=self.group)
         return torch.as_tensor(_CudaView(local.value, n_total), device=self.device)
+
+    def _init_multicast(self, lib, supported):
+        """Bind every rank's allocation to one NVLink multicast object (NVLS). Any failure leaves the unicast VMM
+        mappings in place and the all-reduce on its two-shot unicast kernel."""
+        want = supported and os.environ.get("CT_DDP_NVLS", "1") != "0"
+        if not self._all_ok(want):
+            return
+        mcfd = ctypes.c_int(-1)
+        ok = True
+        if self.rank == 0:
+            ok = lib.ct_comm_mc_create(ctypes.byref(mcfd)) == 0
+        if not self._all_ok(ok):
+            if self.rank == 0:
+                print("[cleantransformer_b200.ddp] no multicast object (%s): two-shot unicast all-reduce" % _lib.last_error(),
+                      flush=True)
+            return
+        got = self._exchange_fds("mc", mcfd.value, [0], list(range(self.world)))
+        if self.rank != 0:
+            ok = lib.ct_comm_mc_import(got[0]) == 0
+            os.close(got[0])
+        else:
+            os.close(mcfd.value)
+        if not self._all_ok(ok):
+            return
+        ok = lib.ct_comm_mc_add_device() == 0
+        if not self._all_ok(ok):  # (also the barrier cuMulticastBindMem needs: every device has been added)
+            if self.rank == 0:
+                print("[cleantransformer_b200.ddp] cuMulticastAddDevice failed (%s)" % _lib.last_error(), flush=True)
+            return
+        ok = lib.ct_comm_mc_bind() == 0
+        err = "" if ok else _lib.last_error()
+        if not self._all_ok(ok):
+            if err:
+                print("[cleantransformer_b200.ddp] rank %d: multicast bind failed (%s)" % (self.rank, err), flush=True)
+            return  # a partially bound team is unusable: NO rank addresses it (self.nvls stays False everywhere)
+        self.nvls = True
 
     # ---------------------------------------------------------------- forward
     def forward(self, *args, **kwargs):
@@ -245,18 +350,16 @@ class DistributedDataParallel(torch.nn.Module):
         lo, hi, _ = self.buckets[bi]
         if os.environ.get("CT_DDP_SKIP_COMM"):  # timing experiments only: gradients stay local (WRONG results)
             return
-        if self.comm == "ce":
-            cur = torch.cuda.current_stream(self.device)
-            self._comm_stream.wait_stream(cur)
-            with torch.cuda.stream(self._comm_stream):
-                self._allreduce_ce(lo, hi - lo)
-        elif self.comm == "p2p":
+        if self.comm == "p2p":
             cur = torch.cuda.current_stream(self.device)
             self._comm_stream.wait_stream(cur)
             with torch.cuda.stream(self._comm_stream):
                 # buckets launched after backward has finished have nothing to overlap with: use every SM
-                ctas = self.final_ctas if final else self.max_ctas
-                _lib.check(_lib.load().ct_allreduce_bucket(lo, hi - lo, 1.0 / self.world, 0, ctas,
+                if self.nvls:
+                    mode, ctas = 2, (64 if final else (self.max_ctas or 16))
+                else:
+                    mode, ctas = 3, (self.final_ctas if final else (self.max_ctas or self._max_ctas_unicast))
+                _lib.check(_lib.load().ct_allreduce_bucket(lo, hi - lo, 1.0 / self.world, mode, ctas,
                                                            self._comm_stream.cuda_stream), "ct_allreduce_bucket")
         else:  # baseline / oracle path: library collective on the same bucket layout
             seg = self.arena.grad[lo:hi]
@@ -268,51 +371,6 @@ class DistributedDataParallel(torch.nn.Module):
             else:
                 dist.all_reduce(seg, group=self.group)
                 seg.mul_(1.0 / self.world)
-
-    CE_PIECE = 1 << 24  # floats per piece (64 MiB): bounds the staging area for the 980 MiB tied-table bucket
-
-    @staticmethod
-    def ce_plan(count, world, rank, piece=None):
-        """[(piece offset, slice start in the piece, slice length, slice stride)] for the copy-engine all-reduce of
-        `count` floats: every piece is cut into `world` slices of `stride` floats (a multiple of 4), rank r owns
-        slice r (possibly short or empty at the ragged end)."""
-        piece = piece or DistributedDataParallel.CE_PIECE
-        plan = []
-        for p0 in range(0, count, piece):
-            n = min(piece, count - p0)
-            stride = ((n + 4 * world - 1) // (4 * world)) * 4
-            a = min(n, stride * rank)
-            b = min(n, stride * (rank + 1))
-            plan.append((p0, a, b - a, stride))
-        return plan
-
-    def _allreduce_ce(self, off, count):
-        """Two-shot all-reduce of floats [off, off+count) of the symmetric buffer with the NVLink legs on the DMA
-        engines. Runs on the communication stream (the caller set it current)."""
-        lib = _lib.load()
-        st = self._comm_stream.cuda_stream
-        W, r = self.world, self.rank
-        plan = self.ce_plan(count, W, r)
-        need = (W - 1) * max(p[3] for p in plan)
-        stage = getattr(self, "_ce_stage", None)
-        if stage is None or stage.numel() < need:
-            stage = self._ce_stage = torch.empty(need, dtype=torch.float32, device=self.device)
-        _lib.check(lib.ct_comm_barrier(st), "ct_comm_barrier")  # every rank's gradients of this bucket are final
-        for p0, a, n, stride in plan:
-            if n == 0:
-                continue
-            base = off + p0 + a
-            slot = 0
-            for q in range(W):
-                if q != r:
-                    _lib.check(lib.ct_comm_pull(q, base, stage.data_ptr() + 4 * slot * stride, n, st), "ct_comm_pull")
-                    slot += 1
-            _lib.check(lib.ct_comm_reduce_slices(base, stage.data_ptr(), stride, n, 1.0 / W, 0, st),
-                       "ct_comm_reduce_slices")
-            for q in range(W):
-                if q != r:
-                    _lib.check(lib.ct_comm_push(q, base, base, n, st), "ct_comm_push")
-        _lib.check(lib.ct_comm_barrier(st), "ct_comm_barrier")  # every slice has landed everywhere
 
     def _sparse_embedding_bwd(self, param, ids, dout, grad, padding_idx):
         """EmbeddingFn's scatter for a tied table (functional.EmbeddingFn.backward). `grad` already holds the
@@ -342,8 +400,9 @@ class DistributedDataParallel(torch.nn.Module):
                 self._stage_hdr_off, self._stage_rows_off, self._stage_ids_off, self._grad_off[id(param)], H, V,
                 int(padding_idx), 1.0 / self.world, self.final_ctas * 2, self._comm_stream.cuda_stream),
                 "ct_embedding_bwd_allranks")
-        dout.record_stream(self._comm_stream)
-        ids.record_stream(self._comm_stream)
+        if not torch.cuda.is_current_stream_capturing():  # (graph memory is static; the side stream joins before the end)
+            dout.record_stream(self._comm_stream)
+            ids.record_stream(self._comm_stream)
         self._scatter_how[id(param)] = "exchanged"
 
     def _finish_backward(self):
@@ -361,6 +420,27 @@ class DistributedDataParallel(torch.nn.Module):
         self._pending = None
 
     # ---------------------------------------------------------------- misc surface
+    def close(self):
+        """Release the peer-mapped buffers (one communication context per process: call this before wrapping another
+        model with comm='p2p'). The module's gradients move back to ordinary memory; parameters are untouched."""
+        if self._peer_mem and self.world > 1 and self.arena is not None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            for p in self.arena.params:
+                if p.grad is not None and p.grad.data_ptr() == p._ct_grad_view.data_ptr():
+                    p.grad = None
+                p._ct_grad_view = None
+                p._ct_arena = None
+                hooks = getattr(p, "_ct_grad_hooks", None)
+                if hooks and self._on_grad_written in hooks:
+                    hooks.remove(self._on_grad_written)
+                if getattr(p, "_ct_embedding_bwd_override", None) is not None:
+                    p._ct_embedding_bwd_override = None
+            self.arena = None
+            _lib.check(_lib.load().ct_comm_finalize(), "ct_comm_finalize")
+            dist.barrier(group=self.group)
+            self._peer_mem = False
+
     def no_sync(self):
         ddp = self
 

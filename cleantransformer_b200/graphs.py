@@ -9,11 +9,13 @@ are `__grid_constant__` kernel parameters) and every intermediate buffer are the
 What stays outside the graph: the optimizer step (its bias-correction constants are host scalars that change every
 step: one launch) and anything that feeds new data (copied into the static input buffers before the replay).
 
-Not for `DistributedDataParallel(comm="p2p"|"ce")`: the peer barriers of csrc/comm.cu compare flag words with an epoch
-that is a kernel ARGUMENT — a replay would present the captured epoch again and sail through them.
+`DistributedDataParallel(comm="p2p")` is captured with the step: the bucket all-reduces are ordinary kernels on a side
+stream that forks from / joins the capture stream, and their epochs live in device memory (csrc/comm.cu), so every
+replay synchronises with the peers' replays. Every rank must capture and replay in step. `comm="nccl"` is not
+captured (library collectives bring their own graph rules).
 
-Status: written after round 1's GPU budget was spent — not yet run on a GPU (tests/test_gpu_models.py has an
-opt-in test under CT_TEST_EXPERIMENTAL=1; `bench.py --graph` uses it).
+Parameters never enter autograd as edges of this package's Functions (functional._anchor), so no stale AccumulateGrad
+node — created on another stream by an earlier, un-captured step — can tie the capture to uncaptured work.
 """
 import torch
 
@@ -30,9 +32,9 @@ class GraphedTrainStep:
 
     def __init__(self, model, example_inputs, loss_of=None, warmup=3):
         from .ddp import DistributedDataParallel
-        if isinstance(model, DistributedDataParallel) and getattr(model, "_peer_mem", False) and model.world > 1:
-            raise RuntimeError("GraphedTrainStep: the peer-memory DDP collectives cannot be replayed from a graph "
-                               "(epoch-stamped barriers); use it on a single GPU or with comm='nccl'")
+        if isinstance(model, DistributedDataParallel) and model.world > 1 and not getattr(model, "_peer_mem", False):
+            raise RuntimeError("GraphedTrainStep: only the peer-memory collectives (comm='p2p') are captured with the "
+                               "step; run comm='nccl' un-graphed")
         for k, v in example_inputs.items():
             if not (torch.is_tensor(v) and v.is_cuda):
                 raise RuntimeError("GraphedTrainStep: input '%s' must be a CUDA tensor" % k)

@@ -376,21 +376,6 @@ def attn_fwd(q, k, v, scale, causal=False, causal_fill=-FLT_MAX, kbias2=None, fi
     return o, lse2
 
 
-_DQ_WS = {}
-_DQ_FUSED = os.environ.get("CT_ATTN_DQ_FUSED", "1") != "0"
-
-
-def _dq_workspace(device, numel):
-    """Zero-initialised f32 dQ workspace (+ per-head counters), one per (device, stream); the backward kernel leaves it
-    zeroed, so it is allocated and cleared once."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _DQ_WS.get(key)
-    if ws is None or ws.numel() < numel:
-        ws = torch.zeros(numel, dtype=torch.float32, device=device)
-        _DQ_WS[key] = ws
-    return ws
-
-
 def attn_bwd(dout, q, k, v, o, lse2, dq, dk, dv, scale, causal=False, causal_fill=-FLT_MAX,
              kbias2=None, first_valid=None, impl=0):
     """dout/o [B,Sq,H*D]; q,k,v,dq,dk,dv [B,H,S,D] strided views; dq/dk/dv are written."""
@@ -405,18 +390,11 @@ def attn_bwd(dout, q, k, v, o, lse2, dq, dk, dv, scale, causal=False, causal_fil
     a.dv = dv.data_ptr(); a.dv_sb, a.dv_sh, a.dv_ss = _bhsd_strides(dv)
     delta = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
     a.delta = delta.data_ptr()
-    if D == 64:
-        # whole query tiles: the tcgen05 kernels lay the workspace out per 128-row tile (include/ct_b200.h). The
-        # workspace is persistent per (device, stream) and kept ZERO between calls by the kernel itself
-        # (dq_accum_armed): no memset, no separate f32 -> bf16 convert launch.
-        n = B * H * ((Sq + 127) // 128 * 128) * D
-        armed = _DQ_FUSED and all(t.data_ptr() % 16 == 0 and all(s % 8 == 0 for s in t.stride()[:3]) for t in (dq,))
-        if armed:
-            a.dq_accum = _dq_workspace(q.device, n + B * H).data_ptr()
-            a.dq_accum_armed = 1
-        else:
-            dq_acc = torch.empty(n, dtype=torch.float32, device=q.device)  # (alive until the launch below)
-            a.dq_accum = dq_acc.data_ptr()
+    # whole query tiles: the tcgen05 kernels lay the workspace out per 128-row tile (include/ct_b200.h). (Converting it
+    # inside the backward kernel — last CTA of a head, workspace kept zeroed — was measured: every CTA then pays a
+    # __threadfence for its red.global.adds, 185 vs 171 us per call, profiles/r02c_ab_attention.jsonl.)
+    dq_acc = torch.empty((B, H, (Sq + 127) // 128 * 128, D), dtype=torch.float32, device=q.device) if D == 64 else None
+    a.dq_accum = ptr(dq_acc)
     _ck(_lib.load().ct_attn_bwd(ctypes.byref(a), stream()), "ct_attn_bwd")
 
 

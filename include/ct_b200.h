@@ -246,11 +246,6 @@ typedef struct {
   int64_t dv_sb, dv_sh, dv_ss;
   float* delta;
   float* dq_accum;
-  /* 0: dq_accum may hold anything; the library zeroes it, accumulates, and converts it with a second kernel.
-   * 1: the caller owns a PERSISTENT workspace of B*H*ceil(Sq/128)*128*D floats followed by B*H int32 counters, all
-   *    zero on entry; the backward kernel converts dQ itself (last CTA of each head) and leaves workspace and counters
-   *    zero again: no memset, no convert launch (tcgen05 path, D == 64; one call at a time per workspace). */
-  int32_t dq_accum_armed;
 } ct_attn_bwd_args;
 int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream);
 
@@ -295,17 +290,34 @@ int ct_scale_by_scalar(void* x, int dtype, int64_t n, const float* device_scalar
 
 /* ---- DDP gradient all-reduce over NVLink/NVSwitch peer memory ---------------------------------- *
  * Replaces the ncclAllReduce calls of torch's DDP reducer behind `DDP(model, device_ids=[rank])`
- * (examples/ft_bloom_DDP.py:99,126,135; README.md:46-52). One process per GPU.
- *   ct_comm_init     cudaMalloc a symmetric f32 buffer of data_bytes (+ a signal buffer) on `device`,
- *                    return the local pointer and two 64-byte cudaIpcMemHandle blobs to publish
- *   ct_comm_connect  data_handles / sig_handles: world x 64 bytes, rank-ordered, as gathered by the
- *                    caller over its bootstrap channel (torch.distributed); maps every peer buffer
+ * (examples/ft_bloom_DDP.py:99,126,135; README.md:46-52). One process per GPU, one node.
+ * Two ways to set the symmetric buffer up (csrc/comm.cu):
+ *   VMM + multicast (preferred):
+ *     ct_comm_vmm_supported  does the device offer cuMemCreate / POSIX-fd export (vmm_ok) and NVLink multicast?
+ *     ct_comm_vmm_init   allocate data_bytes (+ a signal page) with cuMemCreate on `device`, map it, return the local
+ *                        pointer and a POSIX file descriptor of the allocation for the peers (the caller passes it
+ *                        over a Unix socket with SCM_RIGHTS and closes it afterwards)
+ *     ct_comm_vmm_connect  peer_fds[world] (entry [rank] ignored): import and map every peer's allocation
+ *     ct_comm_mc_create  (rank 0) create the multicast object, return its descriptor for the peers
+ *     ct_comm_mc_import  (other ranks) import it
+ *     ct_comm_mc_add_device  (all ranks; then a host barrier) join the multicast team
+ *     ct_comm_mc_bind    (all ranks; then a host barrier) bind the local allocation and map the multicast address:
+ *                        from here ct_allreduce_bucket adds inside the NVSwitch (multimem.ld_reduce / multimem.st)
+ *   cudaMalloc + IPC handles (fallback):
+ *     ct_comm_init     cudaMalloc a symmetric f32 buffer of data_bytes (+ a signal buffer) on `device`,
+ *                      return the local pointer and two 64-byte cudaIpcMemHandle blobs to publish
+ *     ct_comm_connect  data_handles / sig_handles: world x 64 bytes, rank-ordered, as gathered by the
+ *                      caller over its bootstrap channel (torch.distributed); maps every peer buffer
+ *   ct_comm_info       flags[0] = VMM buffers, flags[1] = multicast mapping present
+ * Collectives (same order on all ranks, each on the caller's stream; epochs are kept in device memory, so the
+ * kernels can be captured in a CUDA graph and replayed):
  *   ct_allreduce_bucket  in place over elements [offset, offset+count) of the symmetric buffer on
- *                    every rank: x = scale * sum_ranks x. mode 0 two-shot (reduce-scatter + all-gather
- *                    by the slice owner), mode 1 one-shot (needs `count` spare floats after the range).
- *                    Must be called in the same order by all ranks. max_ctas bounds the SMs used so
- *                    backward compute keeps running (0 = default 32).
+ *                    every rank: x = scale * sum_ranks x. mode 0 auto (NVLS when mapped, else two-shot unicast),
+ *                    1 one-shot (needs `count` spare floats after the range), 2 NVLS, 3 two-shot unicast
+ *                    (reduce-scatter + all-gather by the slice owner). max_ctas bounds the SMs used so
+ *                    backward compute keeps running (0 = default: 16 NVLS, 64 otherwise).
  *   ct_broadcast     copy [offset, offset+count) from root's buffer to every rank's buffer.
+ *   ct_comm_barrier  all ranks have reached this point of their stream.
  *   ct_embedding_bwd_allranks  sparse half of a TIED embedding gradient (modeling_bloom.py:215-216,
  *                    modeling_gpt.py:205: lm_head.weight is the token table). Every rank has staged, inside
  *                    its symmetric buffer, an int64 token count T at hdr_offset, T x H f32 token gradients
@@ -313,13 +325,15 @@ int ct_scale_by_scalar(void* x, int dtype, int64_t n, const float* device_scalar
  *                    every rank then adds scale * rows of ALL ranks into its own table gradient [V,H] at
  *                    grad_offset (rows with id == padding_idx or out of range are skipped). Replaces
  *                    "scatter locally, then all-reduce the whole V x H table" — see csrc/comm.cu.
- *                    Collective: same order on all ranks, same stream discipline as ct_allreduce_bucket.
- *   ct_comm_barrier / ct_comm_pull / ct_comm_push / ct_comm_reduce_slices  the same two-shot all-reduce with the
- *                    NVLink legs on the DMA engines (cudaMemcpyAsync peer copies) instead of SMs: barrier, pull
- *                    slice `rank` of every peer into caller-provided local staging, reduce the world slices in
- *                    rank order (scale * sum) into the local buffer, push the result into every peer, barrier.
- *                    Offsets / counts in floats; peers' staging slots in ascending rank order, `stride` apart.
  * The buffers are library-owned (freed by ct_comm_finalize); PyTorch sees them as non-owning tensors. */
+int ct_comm_vmm_supported(int device, int* vmm_ok, int* multicast_ok);
+int ct_comm_vmm_init(int rank, int world, int device, size_t data_bytes, void** local_data, int* local_fd_out);
+int ct_comm_vmm_connect(const int* peer_fds);
+int ct_comm_mc_create(int* mc_fd_out);
+int ct_comm_mc_import(int mc_fd);
+int ct_comm_mc_add_device(void);
+int ct_comm_mc_bind(void);
+int ct_comm_info(int* flags);
 int ct_comm_init(int rank, int world, int device, size_t data_bytes, void** local_data,
                  void* data_handle_out, void* sig_handle_out);
 int ct_comm_connect(const void* data_handles, const void* sig_handles);
@@ -327,10 +341,6 @@ int ct_allreduce_bucket(int64_t offset, int64_t count, float scale, int mode, in
                         void* stream);
 int ct_broadcast(int64_t offset, int64_t count, int root, void* stream);
 int ct_comm_barrier(void* stream);
-int ct_comm_pull(int peer, int64_t peer_offset, void* dst_local, int64_t count, void* stream);
-int ct_comm_push(int peer, int64_t peer_offset, int64_t local_offset, int64_t count, void* stream);
-int ct_comm_reduce_slices(int64_t local_offset, const float* staged, int64_t stride, int64_t count, float scale,
-                          int max_ctas, void* stream);
 int ct_embedding_bwd_allranks(int64_t hdr_offset, int64_t rows_offset, int64_t ids_offset, int64_t grad_offset,
                               int64_t H, int64_t V, int64_t padding_idx, float scale, int max_ctas,
                               void* stream);

@@ -207,6 +207,13 @@ def test_config5_bert_base_shape_vs_oracle():
         if p.grad is None:
             assert ref is None or float(ref.abs().max()) == 0.0, n
             continue
+        if n.endswith("k_linear.bias"):
+            # exactly zero in exact arithmetic (softmax is invariant to a per-query constant q.b_k): all three
+            # results are rounding noise, compared on the scale of the query-bias gradient instead of to each other
+            scale = float(g32[n.replace("k_linear", "q_linear")].abs().max())
+            ERRORS.setdefault(case, {})["grad." + n + " (identically zero; |ours| / |dq_bias|)"] = float(p.grad.abs().max()) / scale
+            assert float(p.grad.abs().max()) <= 2e-2 * scale, n
+            continue
         # q/k projections at N(0, 0.02) init: attention is near-uniform and the loss only reads token 0, so these
         # gradients are ~1e-3 of the others and cancellation-dominated (dS = P*(dP - delta) with delta = rowsum(dO*O)
         # taken from the bf16-rounded O in any flash-style backward): observed 1.2e-2, bound = observed x 1.5
@@ -276,7 +283,17 @@ def test_config2_bloom560m_layer_and_lm_head_full_shape_vs_oracle(fused_stats):
 # ------------------------------------------------------------------------------------------------------------------
 # C4 shape: greedy decoding, GPT-2-medium width, batch 32, left padded
 # ------------------------------------------------------------------------------------------------------------------
-def test_config4_gpt2_medium_shape_greedy_ids_bit_exact():
+def test_config4_gpt2_medium_shape_greedy_ids():
+    """Greedy decoding, GPT-2-medium width (1024 / 16 heads, 4 layers), batch 32, LEFT padded prompts, 64 new tokens,
+    through the KV-cache path (prefill on the tcgen05 attention kernel, then q_len = 1 steps: in-place cache append,
+    decode attention, fp32 LM-head logits) against the fp32 oracle's restatement of generation_util.py:57-119.
+
+    Token ids are compared DECISION BY DECISION with both sides fed the same prefix (the oracle's sequence): a
+    random-init model has near-uniform logits (thousands of top-2 near-ties), and one legitimate flip would otherwise
+    hide every later step. Bar: the argmax is bit-exact wherever the oracle's own top-2 gap exceeds twice the
+    measured logit error of that row; the logit error itself must stay within the bf16 bound; every flip is counted
+    and reported (SURVEY §7 near-tie policy). generate() itself must reproduce the oracle's ids up to the first
+    such near-tie of each row."""
     from cleantransformer_b200.models import modeling_gpt as mg
     from oracle import ct_oracle as O
     L, NEW = 4, 64
@@ -293,35 +310,55 @@ def test_config4_gpt2_medium_shape_greedy_ids_bit_exact():
         mask[b, :P - n] = 0
         ids[b, :P - n] = 0
     ids, mask = ids.to(DEV), mask.to(DEV)
-    gen = model.generate(ids, attention_mask=mask,
-                         generation_configs={"beam_size": 1, "do_sample": False, "max_gen_len": NEW - 2,
-                                             "end_ids": None, "pad_id": 0, "no_repeat_ngram_size": 0})
     sd = {k: v.detach() for k, v in model.state_dict().items()}
-    gaps = []
+    ref_logits = []
 
     def step_fn(i, m, kv):
         with torch.no_grad():
             out, kv = O.gpt_lm_head_model(i, m, sd, L, 16, 1024, 1e-5, version="gpt2", k_v_pasts=kv)
-        top2 = out[0][:, -1, :].float().topk(2, dim=-1).values
-        gaps.append(((top2[:, 0] - top2[:, 1]) / top2[:, 0].abs().clamp_min(1e-6)))
+        ref_logits.append(out[0][:, -1, :].float())
         return out, kv
 
-    ref = O.greedy_generate(step_fn, ids, mask, L, NEW - 2, pad_id=0)
-    assert gen.shape == ref.shape == (B, 1, P + NEW)
-    same = gen == ref
-    if not bool(same.all()):
-        # near-tie policy: a flip is only tolerated where the fp32 oracle's own top-2 gap is < 1e-4;
-        # after a flip the sequences legitimately diverge, so only the FIRST mismatch of a row is judged
-        gap = torch.stack(gaps, dim=1)  # [B, steps]
-        for b in range(B):
-            bad = (~same[b, 0]).nonzero()
-            if bad.numel():
-                t = int(bad[0]) - P
-                assert float(gap[b, t]) < 1e-4, ("greedy ids differ without a near tie", b, t, float(gap[b, t]))
-        ERRORS.setdefault("C4_gpt2medium_shape_greedy", {})["near_tie_rows"] = int((~same.all(-1)).sum())
-    else:
-        ERRORS.setdefault("C4_gpt2medium_shape_greedy", {})["near_tie_rows"] = 0
-        ERRORS["C4_gpt2medium_shape_greedy"]["min_top2_rel_gap"] = float(torch.stack(gaps, 1).min())
+    ref = O.greedy_generate(step_fn, ids, mask, L, NEW - 2, pad_id=0)      # [B, 1, P + NEW]
+    assert ref.shape == (B, 1, P + NEW)
+    seq = ref[:, 0]
+    # ---- our decode path, teacher-forced with the oracle's tokens ----
+    caches, fed = [None] * L, 0
+    full_mask = torch.cat([mask, mask[:, -1:].expand(B, NEW)], dim=1)
+    flips, worst_err, n_dec = [], 0.0, 0
+    with torch.no_grad():
+        for t in range(NEW):
+            cur = P + t
+            (logits, _), caches = model(seq[:, fed:cur], attention_mask=full_mask[:, :cur], k_v_pasts=caches)
+            fed = cur
+            ours, want = logits[:, -1, :].float(), ref_logits[t]
+            err = (ours - want).abs().amax(-1)                                  # per row
+            worst_err = max(worst_err, float((err / want.abs().amax(-1)).max()))
+            top2 = want.topk(2, dim=-1).values
+            gap = top2[:, 0] - top2[:, 1]
+            mism = ours.argmax(-1) != want.argmax(-1)
+            n_dec += B
+            for b in mism.nonzero().flatten().tolist():
+                flips.append((t, b, float(gap[b]), float(err[b])))
+                assert float(gap[b]) <= 2.0 * float(err[b]), ("argmax differs without a near tie", t, b, float(gap[b]), float(err[b]))
+    assert worst_err <= 4e-3, worst_err   # fp32 logits from bf16 operands: the bf16 bound, measured
+    # ---- generate() end to end: identical up to each row's first near-tie decision ----
+    gen = model.generate(ids, attention_mask=mask,
+                         generation_configs={"beam_size": 1, "do_sample": False, "max_gen_len": NEW - 2,
+                                             "end_ids": None, "pad_id": 0, "no_repeat_ngram_size": 0})
+    assert gen.shape == ref.shape
+    first_flip = {}
+    for t, b, _, _ in flips:
+        first_flip.setdefault(b, t)
+    exact_rows = 0
+    for b in range(B):
+        upto = P + first_flip.get(b, NEW)
+        assert torch.equal(gen[b, 0, :upto], ref[b, 0, :upto]), ("generate() diverges before the first near tie", b)
+        exact_rows += int(torch.equal(gen[b, 0], ref[b, 0]))
+    ERRORS["C4_gpt2medium_shape_greedy_B32_new64"] = {
+        "decisions": n_dec, "argmax_flips_at_near_ties": len(flips), "rows_bit_exact_end_to_end": exact_rows,
+        "worst_logit_err_rel": worst_err,
+        "largest_gap_over_err_at_a_flip": max([gp / max(e, 1e-30) for _, _, gp, e in flips], default=0.0)}
 
 
 # ------------------------------------------------------------------------------------------------------------------

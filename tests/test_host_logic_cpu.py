@@ -201,29 +201,37 @@ def test_adamw_load_state_dict_lands_in_the_arena(monkeypatch):
             assert int(st["step"]) == 3
 
 
-def test_copy_engine_allreduce_plan_tiles_every_piece():
-    """ddp.DistributedDataParallel.ce_plan: every piece of a bucket is cut into `world` 16-byte aligned slices that
-    tile it exactly (ragged ends short or empty), all ranks agree on the stride, staging fits (world-1) strides."""
+def _fd_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
     from cleantransformer_b200.ddp import DistributedDataParallel as D
-    for count, world, piece in [(64, 2, None), (6400, 8, 1024), (1 << 20, 4, 1 << 18), (64 * 7, 3, 128), (192, 8, 64)]:
-        plans = [D.ce_plan(count, world, r, piece) for r in range(world)]
-        assert len({len(p) for p in plans}) == 1
-        covered = 0
-        for k in range(len(plans[0])):
-            p0 = plans[0][k][0]
-            stride = plans[0][k][3]
-            assert stride % 4 == 0 and all(pl[k][0] == p0 and pl[k][3] == stride for pl in plans)
-            n = min(piece or D.CE_PIECE, count - p0)
-            pos = 0
-            for r in range(world):
-                _, a, ln, _ = plans[r][k]
-                assert ln >= 0 and ln <= stride and a % 4 == 0 and ln % 4 == 0
-                if ln:
-                    assert a == pos
-                    pos += ln
-            assert pos == n
-            covered += n
-        assert covered == count
+    d = object.__new__(D)
+    torch.nn.Module.__init__(d)
+    d.rank, d.world, d.group = rank, world, None
+    r = os.memfd_create("ct_test_%d" % rank)
+    os.write(r, b"from rank %d" % rank)
+    got = d._exchange_fds("t1", r, list(range(world)), list(range(world)))       # everyone -> everyone
+    msgs = {q: os.pread(fd, 64, 0) for q, fd in got.items()}
+    r2 = os.memfd_create("ct_test_root")
+    os.write(r2, b"root")
+    got2 = d._exchange_fds("t2", r2, [0], list(range(world)))                    # rank 0 -> the others
+    msgs2 = {q: os.pread(fd, 64, 0) for q, fd in got2.items()}
+    out[rank] = (msgs, msgs2)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ddp_file_descriptor_exchange_world3_gloo():
+    """ddp._exchange_fds (how the cuMemCreate allocations and the multicast object reach the peer processes): SCM_RIGHTS
+    over abstract Unix sockets, all-to-all and one-to-all, checked with memfds standing in for the CUDA handles."""
+    world = 3
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_fd_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        msgs, msgs2 = out[r]
+        assert msgs == {q: b"from rank %d" % q for q in range(world) if q != r}
+        assert msgs2 == ({} if r == 0 else {0: b"root"})
 
 
 def test_ddp_tied_table_state_machine():
