@@ -280,13 +280,19 @@ def run_eager_arm(args):
 # per-kernel roofline table: CUDA events around every C-ABI call of an instrumented (un-graphed) step
 # ------------------------------------------------------------------------------------------------
 class KernelProfiler:
-    """Wraps the tensor-level entry points of cleantransformer_b200.ops with CUDA events and attributes to each call its
-    ALGORITHMIC work (flop for the tensor-core kernels, bytes for the HBM-bound ones; DESIGN.md §5 states the formulas).
-    Events are recorded on the calling stream; backward runs on autograd's thread but on the same stream."""
+    """Per-kernel device times of an instrumented (un-graphed) step, attributed to roles with their ALGORITHMIC work
+    (flop for the tensor-core kernels, bytes for the HBM-bound ones; DESIGN.md §5 states the formulas).
+
+    Every tensor-level entry point of cleantransformer_b200.ops is wrapped in a uniquely named profiler range; the
+    kernels a call launches are timed by CUPTI (torch.profiler / kineto) — real execution time on the device, not
+    stream gaps, so a host that cannot keep the GPU fed during the un-graphed pass does not inflate anything — and
+    mapped back to the range that launched them. Fallback when CUPTI is unavailable: CUDA events around each call."""
 
     def __init__(self, ops):
-        self.ops, self.rows, self.saved = ops, [], {}
+        self.ops, self.calls, self.saved = ops, {}, {}
         self.lock = threading.Lock()
+        self.seq = 0
+        self.prof = None
 
     @staticmethod
     def _nbytes(*ts):
@@ -295,25 +301,29 @@ class KernelProfiler:
     def _wrap(self, name, work_fn):
         orig = getattr(self.ops, name)
         self.saved[name] = orig
-        prof = self
+        me = self
 
         def wrapped(*a, **kw):
+            with me.lock:
+                me.seq += 1
+                idx = me.seq
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = orig(*a, **kw)
+            with torch.profiler.record_function("ctop%d" % idx):
+                out = orig(*a, **kw)
             e1.record()
             try:
                 role, work, unit = work_fn(out, *a, **kw)
             except Exception as ex:  # noqa: BLE001 — attribution must never break the step
                 role, work, unit = "%s (unattributed: %s)" % (name, type(ex).__name__), 0.0, "B"
-            with prof.lock:
-                prof.rows.append((role, work, unit, e0, e1))
+            with me.lock:
+                me.calls[idx] = (role, work, unit, e0, e1)
             return out
 
         setattr(self.ops, name, wrapped)
 
     def start(self):
-        ops, nb = self.ops, self._nbytes
+        nb = self._nbytes
 
         def gemm(ret, A, B, M, N, K, a_mn=False, b_mn=False, **kw):
             kind = "wgrad" if (a_mn and b_mn) else ("dgrad" if b_mn else "fwd")
@@ -361,23 +371,45 @@ class KernelProfiler:
                          ("cross_entropy_fwd_stats", ce), ("colsum", colsum), ("cast", cast),
                          ("embedding_fwd", emb_f), ("embedding_bwd", emb_b)):
             self._wrap(name, fn)
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            if ProfilerActivity.CUDA in torch.profiler.supported_activities():
+                self.prof = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA])
+                self.prof.__enter__()
+        except Exception:  # noqa: BLE001
+            self.prof = None
 
     def stop(self):
         for name, orig in self.saved.items():
             setattr(self.ops, name, orig)
         self.saved = {}
+        self.device_us = {}
+        if self.prof is not None:
+            try:
+                self.prof.__exit__(None, None, None)
+                for ev in self.prof.events():
+                    if ev.name.startswith("ctop"):
+                        t = getattr(ev, "device_time_total", None)
+                        if t is None:
+                            t = getattr(ev, "cuda_time_total", 0.0)
+                        self.device_us[int(ev.name[4:])] = float(t)
+            except Exception:  # noqa: BLE001
+                self.device_us = {}
+            self.prof = None
 
     def table(self, steps, peaks):
         tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        use_cupti = sum(self.device_us.values()) > 0.0
         agg = {}
-        for role, work, unit, e0, e1 in self.rows:
+        for idx, (role, work, unit, e0, e1) in self.calls.items():
+            ms = self.device_us.get(idx, 0.0) * 1e-3 if use_cupti else e0.elapsed_time(e1)
             r = agg.setdefault(role, {"launches": 0, "ms": 0.0, "work": 0.0, "unit": unit})
-            r["launches"] += 1; r["ms"] += e0.elapsed_time(e1); r["work"] += work
+            r["launches"] += 1; r["ms"] += ms; r["work"] += work
         total = sum(r["ms"] for r in agg.values()) or 1.0
         out = []
         for role, r in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
-            row = {"role": role, "launches_per_step": r["launches"] / steps, "ms_per_step": r["ms"] / steps,
+            row = {"role": role, "calls_per_step": r["launches"] / steps, "ms_per_step": r["ms"] / steps,
                    "share": r["ms"] / total}
             if r["work"] > 0 and r["ms"] > 0:
                 if r["unit"] == "flop":
@@ -387,7 +419,18 @@ class KernelProfiler:
                     ach = r["work"] / (r["ms"] * 1e-3) / 1e9
                     row.update(achieved=ach, unit="GB/s", peak=hbm_peak, frac=ach / hbm_peak)
             out.append(row)
-        return out, total / steps
+        return out, total / steps, ("cupti kernel durations (torch.profiler)" if use_cupti else "cuda events around each call")
+
+    def gemm_totals(self):
+        use_cupti = sum(self.device_us.values()) > 0.0
+        flop = ms = 0.0
+        n = 0
+        for idx, (role, work, unit, e0, e1) in self.calls.items():
+            if role.startswith("gemm"):
+                flop += work
+                ms += self.device_us.get(idx, 0.0) * 1e-3 if use_cupti else e0.elapsed_time(e1)
+                n += 1
+        return flop, ms, n
 
 
 def recorded_traffic(kernel):
@@ -446,6 +489,7 @@ def main():
     net = model
     if world > 1:
         net = DistributedDataParallel(model, device_ids=[local], comm=args.comm)
+    nvls_used = bool(getattr(net, "nvls", False)) if world > 1 else None
     optimizer = TorchAdamW(net.parameters(), lr=1e-5)
     use_graph = ((world == 1 or (args.comm or "p2p") == "p2p") and not args.no_graph) or args.graph
 
@@ -534,17 +578,16 @@ def main():
     per_kernel, kernel_ms = None, None
     gemm_flop = gemm_ms = 0.0
     n_gemm = 0
+    timing_source = None
     if not args.no_kernel_table:
         prof.start()
         barrier()
         for _ in range(2):
-            step_eager()
+            step_eager()  # (kernel by kernel also under --graph: per-kernel attribution needs individual launches)
         torch.cuda.synchronize()
         prof.stop()
-        per_kernel, kernel_ms = prof.table(2, peaks)
-        for role, work, unit, e0, e1 in prof.rows:
-            if role.startswith("gemm"):
-                gemm_flop += work; gemm_ms += e0.elapsed_time(e1); n_gemm += 1
+        per_kernel, kernel_ms, timing_source = prof.table(2, peaks)
+        gemm_flop, gemm_ms, n_gemm = prof.gemm_totals()
     achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     peak_burst = float(peaks.get("bf16_tflops", peak))
@@ -577,6 +620,7 @@ def main():
                        "parallelism": "dp%d" % world, "precision": "fp32 master params/residual/LN/softmax/loss, bf16 tensor-core operands",
                        "l2": "inputs larger than L2 (1.1 GB bf16 weights + >3 GB activations per step vs 126 MB L2); no flush",
                        "ddp_comm": (args.comm or "p2p") if world > 1 else None,
+                       "ddp_nvls": nvls_used,
                        "cuda_graph": bool(use_graph)},
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": 3 * B * S * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
@@ -593,7 +637,7 @@ def main():
                                                     "burst %.1f)" % peak_burst,
                          "launches_timed": n_gemm, "gemm_ms_per_step": gemm_ms / 2.0,
                          "gemm_share_of_step": (gemm_ms / 2.0) / ms_step if ms_step else None,
-                         "kernel_ms_per_step_ungraphed": kernel_ms,
+                         "kernel_ms_per_step": kernel_ms, "kernel_timing": timing_source,
                          "per_kernel": per_kernel},
             "step_roofline": {
                 "attn_ffn_tflops_per_gpu": ATTN_FFN_FLOP_PER_TOKEN * B * S / (ms_step * 1e-3) / 1e12,

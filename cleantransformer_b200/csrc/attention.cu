@@ -978,6 +978,16 @@ template <uint32_t N>
 __device__ __forceinline__ void f4_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <uint32_t N>
 __device__ __forceinline__ void f4_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+// 64-thread barrier of the two warps that share TMEM lane quarter `wq`; the barrier ids are compile-time constants so
+// that ptxas reserves 5 named barriers for the kernel, not all 16 (the barrier file of an SM is shared by its CTAs)
+__device__ __forceinline__ void f4_pair_sync(int wq) {
+  switch (wq) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
 __device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
@@ -1239,7 +1249,7 @@ __global__ void __launch_bounds__(F4_THREADS, 2)
       tmem_st_32x1(t_mail + 2 * (j & 1) + half, __float_as_uint(mt));
       tmem_st_wait();
       tc_fence_before();
-      bar_sync_named(1 + wq, 64);
+      f4_pair_sync(wq);
       tc_fence_after();
       uint32_t other;
       tmem_ld_32x1(t_mail + 2 * (j & 1) + (half ^ 1), other);
@@ -1289,7 +1299,7 @@ __global__ void __launch_bounds__(F4_THREADS, 2)
       tmem_st_32x1(t_mail + 2 * (n_kv & 1) + half, __float_as_uint(l));
       tmem_st_wait();
       tc_fence_before();
-      bar_sync_named(1 + wq, 64);
+      f4_pair_sync(wq);
       tc_fence_after();
       uint32_t other;
       tmem_ld_32x1(t_mail + 2 * (n_kv & 1) + (half ^ 1), other);
@@ -3619,6 +3629,18 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
   CT_LAUNCH_OK();
   attn_bwd_dkv_simt_kernel<<<(unsigned)((wk + SIMT_WARPS - 1) / SIMT_WARPS), SIMT_WARPS * 32, 0, st>>>(bp);
   CT_LAUNCH_OK();
+  return 0;
+}
+
+// Diagnostic: resident CTAs per SM of the default tcgen05 forward / backward kernels (cudaOccupancy API, no launch).
+extern "C" int ct_attn_occupancy(int* fwd_ctas_per_sm, int* bwd_ctas_per_sm) {
+  CT_REQUIRE(fwd_ctas_per_sm && bwd_ctas_per_sm, CT_ERR_BAD_ARG, "ct_attn_occupancy: null out");
+  CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
+  CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
+  CT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(fwd_ctas_per_sm, attn_fwd_tc4_kernel<true, true>, F4_THREADS,
+                                                           F4_SMEM));
+  CT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bwd_ctas_per_sm, attn_bwd_tc2_kernel<true, 3>, FB_THREADS,
+                                                           FB_SMEM_PIPE));
   return 0;
 }
 

@@ -248,6 +248,8 @@ typedef struct {
   float* dq_accum;
 } ct_attn_bwd_args;
 int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream);
+/* diagnostic: resident CTAs per SM of the default tcgen05 forward / backward kernels (occupancy API, no launch) */
+int ct_attn_occupancy(int* fwd_ctas_per_sm, int* bwd_ctas_per_sm);
 
 /* Build kbias2 / first_valid from the caller's attention_mask [B,Sk] (1 = attend).
  * mask_dtype: CT_F32, 3 = int64, 4 = int32.

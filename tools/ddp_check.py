@@ -43,7 +43,7 @@ def check(cond, what):
 
 def same_on_all_ranks(t):
     """Is this tensor bit-identical on every rank?"""
-    bits = t.contiguous().view(torch.int32).to(torch.int64)
+    bits = t.detach().contiguous().view(-1).view(torch.int32).to(torch.int64)
     s = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=t.device) % 1000003).sum()])
     lo, hi = s.clone(), s.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)

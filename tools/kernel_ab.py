@@ -101,6 +101,11 @@ def _attn_oracle(q, k, v, scale, causal, causal_fill, kb2):
 
 
 def attn_ab():
+    import ctypes
+    from cleantransformer_b200 import _lib
+    f, b = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.check(_lib.load().ct_attn_occupancy(ctypes.byref(f), ctypes.byref(b)), "ct_attn_occupancy")
+    out(kernel="attention", occupancy_ctas_per_sm=dict(forward=f.value, backward=b.value))
     cases = [  # name, B, H, S, mask mode, padding, fill
         ("bloom_bench_8x16x1024", 8, 16, 1024, 0, False, -ops.FLT_MAX),
         ("bloom_rightpad_2x16x1024", 2, 16, 1024, 0, True, -ops.FLT_MAX),
