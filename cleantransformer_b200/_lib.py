@@ -125,7 +125,7 @@ SIGNATURES = {
                               c_i64, c_i64, c_int, c_void_p]),
     "ct_attn_fwd": (c_int, [ctypes.POINTER(AttnArgs), c_void_p]),
     "ct_attn_bwd": (c_int, [ctypes.POINTER(AttnBwdArgs), c_void_p]),
-    "ct_attn_occupancy": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "ct_attn_occupancy": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "ct_attn_mask_prep": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
     "ct_embedding_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_void_p]),

@@ -972,7 +972,11 @@ __global__ void __launch_bounds__(FA_THREADS, 2)
 // mailbox.
 // =================================================================================================
 constexpr int F4_THREADS = 384;
-constexpr int F4_SMEM = 7 * FA_TILE + 128 + 512;
+// Dynamic shared memory = the seven 16 KB tiles, nothing else: 2 x (114,688 + 1 KB static (barriers, bias staging; a
+// 1024-aligned dynamic window costs that much in any case) + 1 KB reserved by the system) = 233,472 bytes = exactly
+// what an SM has. One more byte and a second CTA no longer fits (r02e: the occupancy API reported 1 CTA/SM with the
+// barriers and the bias row appended to the dynamic window, 57 us; see profiles/r02_attention_notes.md).
+constexpr int F4_SMEM = 7 * FA_TILE;
 
 template <uint32_t N>
 __device__ __forceinline__ void f4_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -1090,11 +1094,12 @@ __global__ void __launch_bounds__(F4_THREADS, 2)
   const uint32_t sK = base + FA_TILE;
   const uint32_t sV = base + 3 * FA_TILE;
   const uint32_t sP = base + 5 * FA_TILE;  // two 64-key panels, one per softmax half
-  const uint32_t bars = base + 7 * FA_TILE;
+  __shared__ __align__(16) uint8_t f4_aux[640];  // mbarriers + TMEM slot (128 B), per-key bias of the current tile (512 B)
+  const uint32_t bars = smem_u32(f4_aux);
   const uint32_t q_full = bars, k_full = bars + 8, v_full = bars + 24, kv_empty = bars + 40, s_full = bars + 56,
                  s_free = bars + 64, p_ready = bars + 72, o_full = bars + 80, tmem_slot = bars + 88,
                  kb_full = bars + 96, kb_free = bars + 104, kb_s = bars + 128;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + 7 * FA_TILE + 88);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(f4_aux + 88);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_q_tiles = (p.Sq + 127) / 128;
@@ -3633,7 +3638,9 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
 }
 
 // Diagnostic: resident CTAs per SM of the default tcgen05 forward / backward kernels (cudaOccupancy API, no launch).
-extern "C" int ct_attn_occupancy(int* fwd_ctas_per_sm, int* bwd_ctas_per_sm) {
+// detail (optional, 8 ints): forward kernel numRegs, static shared bytes, dynamic shared bytes asked for, and its
+// occupancy with the dynamic shared memory reduced by 0 / 1 / 2 / 4 / 16 KB (what limits it: registers or smem?).
+extern "C" int ct_attn_occupancy(int* fwd_ctas_per_sm, int* bwd_ctas_per_sm, int* detail) {
   CT_REQUIRE(fwd_ctas_per_sm && bwd_ctas_per_sm, CT_ERR_BAD_ARG, "ct_attn_occupancy: null out");
   CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
   CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
@@ -3641,6 +3648,15 @@ extern "C" int ct_attn_occupancy(int* fwd_ctas_per_sm, int* bwd_ctas_per_sm) {
                                                            F4_SMEM));
   CT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bwd_ctas_per_sm, attn_bwd_tc2_kernel<true, 3>, FB_THREADS,
                                                            FB_SMEM_PIPE));
+  if (detail) {
+    cudaFuncAttributes fa;
+    CT_CUDA_OK(cudaFuncGetAttributes(&fa, attn_fwd_tc4_kernel<true, true>));
+    detail[0] = fa.numRegs; detail[1] = (int)fa.sharedSizeBytes; detail[2] = F4_SMEM;
+    const int cut[5] = {0, 1024, 2048, 4096, 16384};
+    for (int i = 0; i < 5; ++i)
+      CT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(detail + 3 + i, attn_fwd_tc4_kernel<true, true>,
+                                                               F4_THREADS, F4_SMEM - cut[i]));
+  }
   return 0;
 }
 

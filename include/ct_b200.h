@@ -248,8 +248,10 @@ typedef struct {
   float* dq_accum;
 } ct_attn_bwd_args;
 int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream);
-/* diagnostic: resident CTAs per SM of the default tcgen05 forward / backward kernels (occupancy API, no launch) */
-int ct_attn_occupancy(int* fwd_ctas_per_sm, int* bwd_ctas_per_sm);
+/* diagnostic: resident CTAs per SM of the default tcgen05 forward / backward kernels (occupancy API, no launch);
+ * detail: NULL or 8 ints (forward kernel: registers, static smem, dynamic smem, occupancy at dynamic smem
+ * - {0, 1, 2, 4, 16} KB) */
+int ct_attn_occupancy(int* fwd_ctas_per_sm, int* bwd_ctas_per_sm, int* detail);
 
 /* Build kbias2 / first_valid from the caller's attention_mask [B,Sk] (1 = attend).
  * mask_dtype: CT_F32, 3 = int64, 4 = int32.

@@ -104,8 +104,11 @@ def attn_ab():
     import ctypes
     from cleantransformer_b200 import _lib
     f, b = ctypes.c_int(0), ctypes.c_int(0)
-    _lib.check(_lib.load().ct_attn_occupancy(ctypes.byref(f), ctypes.byref(b)), "ct_attn_occupancy")
-    out(kernel="attention", occupancy_ctas_per_sm=dict(forward=f.value, backward=b.value))
+    det = (ctypes.c_int * 8)()
+    _lib.check(_lib.load().ct_attn_occupancy(ctypes.byref(f), ctypes.byref(b), det), "ct_attn_occupancy")
+    out(kernel="attention", occupancy_ctas_per_sm=dict(forward=f.value, backward=b.value),
+        forward_detail=dict(regs=det[0], static_smem=det[1], dynamic_smem=det[2],
+                            ctas_per_sm_at_smem_minus_0_1_2_4_16KB=[det[3 + i] for i in range(5)]))
     cases = [  # name, B, H, S, mask mode, padding, fill
         ("bloom_bench_8x16x1024", 8, 16, 1024, 0, False, -ops.FLT_MAX),
         ("bloom_rightpad_2x16x1024", 2, 16, 1024, 0, True, -ops.FLT_MAX),
