@@ -403,6 +403,11 @@ __device__ __forceinline__ bool bar_red_or(int id, int nthreads, bool pred) {
       : "memory");
   return out != 0;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -1001,7 +1006,7 @@ __device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t r) {
 
 // One 32-column chunk of a REGULAR tile: t = s * sl2 + kb clamped at -FLT_MAX (in place) when there is a per-key
 // bias, raw scores otherwise (scaled inside the exp2); returns the running maximum.
-template <bool HAS_KB>
+template <bool HAS_KB, bool CLAMP>
 __device__ __forceinline__ float f4_scale_max(uint32_t (&r)[32], uint32_t kb_addr, float sl2, float mt) {
   if constexpr (HAS_KB) {
     const float2 s2 = make_float2(sl2, sl2);
@@ -1012,8 +1017,10 @@ __device__ __forceinline__ float f4_scale_max(uint32_t (&r)[32], uint32_t kb_add
                             make_float2(k4.x, k4.y));
       float2 c = __ffma2_rn(make_float2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])), s2,
                             make_float2(k4.z, k4.w));
-      a.x = fmaxf(a.x, -FLT_MAX); a.y = fmaxf(a.y, -FLT_MAX);  // a masked key (bias -inf) scores finfo.min, not -inf
-      c.x = fmaxf(c.x, -FLT_MAX); c.y = fmaxf(c.y, -FLT_MAX);
+      if constexpr (CLAMP) {  // only tiles with a masked key (bias -inf): it scores finfo.min, not -inf
+        a.x = fmaxf(a.x, -FLT_MAX); a.y = fmaxf(a.y, -FLT_MAX);
+        c.x = fmaxf(c.x, -FLT_MAX); c.y = fmaxf(c.y, -FLT_MAX);
+      }
       r[4 * g] = __float_as_uint(a.x); r[4 * g + 1] = __float_as_uint(a.y);
       r[4 * g + 2] = __float_as_uint(c.x); r[4 * g + 3] = __float_as_uint(c.y);
       mt = fmaxf(mt, fmaxf(a.x, a.y));
@@ -1072,7 +1079,7 @@ __device__ __forceinline__ void f4_exp_store(const uint32_t (&r)[32], int c, flo
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if constexpr (BF16) {
-        w[u] = pack_bf16x2(v[u].x, v[u].y);
+        w[u] = pack_bf16x2_alu(v[u].x, v[u].y);  // not F2FP: see ct_common.cuh
       } else {
         __half2 h = __floats2half2_rn(v[u].x, v[u].y);
         w[u] = *reinterpret_cast<uint32_t*>(&h);
@@ -1094,7 +1101,7 @@ __global__ void __launch_bounds__(F4_THREADS, 2)
   const uint32_t sK = base + FA_TILE;
   const uint32_t sV = base + 3 * FA_TILE;
   const uint32_t sP = base + 5 * FA_TILE;  // two 64-key panels, one per softmax half
-  __shared__ __align__(16) uint8_t f4_aux[640];  // mbarriers + TMEM slot (128 B), per-key bias of the current tile (512 B)
+  __shared__ __align__(16) uint8_t f4_aux[656];  // mbarriers + TMEM slot (128 B), per-key bias of the tile (512 B), masked-key flag
   const uint32_t bars = smem_u32(f4_aux);
   const uint32_t q_full = bars, k_full = bars + 8, v_full = bars + 24, kv_empty = bars + 40, s_full = bars + 56,
                  s_free = bars + 64, p_ready = bars + 72, o_full = bars + 80, tmem_slot = bars + 88,
@@ -1198,10 +1205,12 @@ __global__ void __launch_bounds__(F4_THREADS, 2)
             const int col = j * 128 + lane * 4 + u;
             v[u] = col < p.Sk ? __ldg(kb_row + col) : 0.f;
           }
+          const bool any_masked = __any_sync(0xffffffffu, v[0] < -1e30f || v[1] < -1e30f || v[2] < -1e30f || v[3] < -1e30f);
           if (j > 0) mbar_wait(kb_free, (j - 1) & 1);  // every softmax thread is done with the previous tile's bias
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(kb_s + 16 * lane), "f"(v[0]), "f"(v[1]),
                        "f"(v[2]), "f"(v[3])
                        : "memory");
+          if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(kb_s + 512), "r"(any_masked ? 1u : 0u) : "memory");
           mbar_arrive(kb_full);
         }
       }
@@ -1238,10 +1247,15 @@ __global__ void __launch_bounds__(F4_THREADS, 2)
       if constexpr (HAS_KB) mbar_wait(kb_full, j & 1);
       float mt = -INFINITY;
       bool scaled = HAS_KB;
-      if (!masked_tile) {
-        mt = f4_scale_max<HAS_KB>(ra, kb_half, p.sl2, mt);
-        mt = f4_scale_max<HAS_KB>(rb, kb_half + 128, p.sl2, mt);
+      bool key_masked = false;  // CTA-uniform: does this tile hold a masked key (staged by the bias warp)?
+      if constexpr (HAS_KB) key_masked = lds32(kb_s + 512) != 0u;
+      if (!masked_tile && !key_masked) {
+        mt = f4_scale_max<HAS_KB, false>(ra, kb_half, p.sl2, mt);
+        mt = f4_scale_max<HAS_KB, false>(rb, kb_half + 128, p.sl2, mt);
         if constexpr (!HAS_KB) mt *= p.sl2;  // sl2 > 0 (checked on the host)
+      } else if (!masked_tile) {
+        mt = f4_scale_max<HAS_KB, true>(ra, kb_half, p.sl2, mt);
+        mt = f4_scale_max<HAS_KB, true>(rb, kb_half + 128, p.sl2, mt);
       } else {
         const int lim = p.causal ? vis - col0 : 1 << 20;
         const int n_ok = p.Sk - col0;
@@ -1775,6 +1789,86 @@ __device__ __forceinline__ void fb2_chunk(const FbCtx& cx, const uint32_t (&rs)[
   }
 }
 
+template <bool BF16>
+__device__ __forceinline__ void fb7_store_pair(const FbCtx& cx, int c, int g, const float (&pt)[8], const float (&ds)[8]) {
+  uint32_t a[4], d[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if constexpr (BF16) {
+      a[u] = pack_bf16x2_alu(pt[2 * u], pt[2 * u + 1]);
+      d[u] = pack_bf16x2_alu(ds[2 * u], ds[2 * u + 1]);
+    } else {
+      __half2 x = __floats2half2_rn(pt[2 * u], pt[2 * u + 1]);
+      a[u] = *reinterpret_cast<uint32_t*>(&x);
+      x = __floats2half2_rn(ds[2 * u], ds[2 * u + 1]);
+      d[u] = *reinterpret_cast<uint32_t*>(&x);
+    }
+  }
+  const int ch = (c & 1) * 4 + g;
+  const uint32_t off = cx.rr * 128 + (c >> 1) * FA_TILE + ((ch ^ cx.sw) << 4);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cx.sPT + off), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3])
+               : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cx.sDS + off), "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3])
+               : "memory");
+}
+
+// (v7) the same chunk with the bf16 packing on the ALU pipe instead of F2FP (XU). One 32-query chunk c of this thread's key row. KIND 0 = visible, 1 = entirely future, 2 = generic
+template <int KIND, bool BF16>
+__device__ __forceinline__ void fb7_chunk(const FbCtx& cx, const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c,
+                                          int q0) {
+  const float2 sl2v = make_float2(cx.sl2, cx.sl2), scv = make_float2(cx.scale, cx.scale), kbv = make_float2(cx.kb, cx.kb);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float pt[8], ds[8];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int col = c * 32 + g * 8 + hh * 4;
+      const float4 nl = lds128f(cx.lse_s + 4 * col);
+      const float nls[4] = {nl.x, nl.y, nl.z, nl.w};
+      if constexpr (KIND == 0) {
+        const float4 nd = lds128f(cx.del_s + 4 * col);
+        const float nds[4] = {nd.x, nd.y, nd.z, nd.w};
+#pragma unroll
+        for (int u2 = 0; u2 < 2; ++u2) {
+          const int e = g * 8 + hh * 4 + 2 * u2;
+          const float2 add = __fadd2_rn(kbv, make_float2(nls[2 * u2], nls[2 * u2 + 1]));
+          const float2 t = __ffma2_rn(make_float2(__uint_as_float(rs[e]), __uint_as_float(rs[e + 1])), sl2v, add);
+          const float2 pe = make_float2(ex2(t.x), ex2(t.y));
+          const float2 w = __ffma2_rn(make_float2(__uint_as_float(rd[e]), __uint_as_float(rd[e + 1])), scv,
+                                      make_float2(nds[2 * u2], nds[2 * u2 + 1]));
+          const float2 d2 = __fmul2_rn(pe, w);
+          pt[hh * 4 + 2 * u2] = pe.x; pt[hh * 4 + 2 * u2 + 1] = pe.y;
+          ds[hh * 4 + 2 * u2] = d2.x; ds[hh * 4 + 2 * u2 + 1] = d2.y;
+        }
+      } else if constexpr (KIND == 1) {
+        // causally masked for every key of this warp: the score is the (clamped) fill, a constant
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          pt[hh * 4 + u] = ex2(-FLT_MAX + nls[u]);
+          ds[hh * 4 + u] = 0.f;
+        }
+      } else {
+        const float4 nd = lds128f(cx.del_s + 4 * col);
+        const float nds[4] = {nd.x, nd.y, nd.z, nd.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = g * 8 + hh * 4 + u;
+          const int qg = q0 + col + u;
+          const bool fut = cx.causal && (cx.jg > qg + cx.off);
+          const float v = score2(__uint_as_float(rs[e]), cx.sl2, cx.kb, fut, cx.cf2, false);
+          float pe = ex2(v + nls[u]);
+          if (cx.key_oob) pe = 0.f;
+          pt[hh * 4 + u] = pe;
+          // a causally masked score is a constant in the reference (modeling_gpt.py:89 `w*b`,
+          // modeling_bloom.py:108 masked_fill): P still feeds dV, but no gradient reaches q.k
+          ds[hh * 4 + u] = fut ? 0.f : pe * fmaf(__uint_as_float(rd[e]), cx.scale, nds[u]);
+        }
+      }
+    }
+    fb7_store_pair<BF16>(cx, c, g, pt, ds);
+  }
+}
+
 // MODE bit 0: tiled dQ workspace; bit 1: P^T / dS^T (and the statistics) double-buffered, so the element math of
 // query tile it+1 runs under the dQ / dV / dK MMAs of tile it (v2 waits for them before touching the tiles).
 template <bool BF16, int MODE>
@@ -2071,6 +2165,317 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
           *reinterpret_cast<uint4*>(row + 16 * g) = w;
         }
       }
+    }
+  }
+  CT_DBG_CTA(4);
+  tc_fence_before();
+  __syncthreads();
+  CT_DBG_CTA(5);
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// v7 (default): v3 with the two global-memory tails of the compute warps handed to the TMA engine: the dQ tile of every
+// query tile leaves through shared memory as cp.reduce.async.bulk (fp32 add in the L2) instead of eight
+// red.global.add.v4 per thread (r01f stamps: 750-1500 of ~4700 cycles per tile sat in that drain), and dK / dV leave
+// as one TMA store per tile instead of 16-byte row-strided stores (3.5-4.9 k cycles of epilogue per CTA).
+template <bool BF16>
+__global__ void __launch_bounds__(FB_THREADS, 1)
+    attn_bwd_tc7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                        const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDK,
+                        const __grid_constant__ CUtensorMap tmDV, const AttnBwdP bp) {
+  const AttnP& p = bp.f;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t sK = base, sV = base + FA_TILE;
+  const uint32_t sQ = base + 2 * FA_TILE;   // 2 stages, each Q then dO
+  constexpr bool PIPE = true;
+  constexpr int N_TILES = PIPE ? 14 : 10;
+  constexpr uint32_t PDS_STRIDE = PIPE ? 4 * FA_TILE : 0;  // buffer (it & 1) of the P^T / dS^T pair
+  constexpr uint32_t STAT_STRIDE = PIPE ? 1024 : 0;
+  const uint32_t sPT = base + 6 * FA_TILE;  // 2 panels
+  const uint32_t sDS = base + 8 * FA_TILE;  // 2 panels
+  const uint32_t bars = base + N_TILES * FA_TILE;
+  const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 24, sdp_full = bars + 40,
+                 pds_ready = bars + 48, mma_done = bars + 56, dkv_full = bars + 64, tmem_slot = bars + 72,
+                 sdp_free = bars + 80, lse_s = bars + 128, del_s = bars + 640;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + N_TILES * FA_TILE + 72);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_kv_tiles = (p.Sk + 127) / 128;
+  const int kv_tile = blockIdx.x % n_kv_tiles;
+  const int bh = blockIdx.x / n_kv_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int kv0 = kv_tile * 128;
+  const int n_q_tiles = (p.Sq + 127) / 128;
+  int i_start = 0;
+  if (p.causal) {
+    const bool full_sweep = p.first_valid && (p.first_valid[b] > p.off);
+    if (!full_sweep) i_start = max(0, (kv0 - p.off) / 128);
+  }
+  const int n_it = max(0, n_q_tiles - i_start);
+  CT_DBG_CTA(0);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full + 8 * s, 1); mbar_init(qdo_empty + 8 * s, 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_free, 256);
+    mbar_init(pds_ready, 256);
+    mbar_init(mma_done, 1);
+    mbar_init(dkv_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t T_ST = tmem, T_DPT = tmem + 128, T_DV = tmem + 256, T_DK = tmem + 320, T_DQ = tmem + 384;
+
+  if (warp == 0) {
+    if (lane == 0 && n_it > 0) {
+      mbar_expect_tx(kv_full, 2 * FA_TILE);
+      tma_load_4d(sK, &tmK, kv_full, 0, kv0, h, b);
+      tma_load_4d(sV, &tmV, kv_full, 0, kv0, h, b);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1, q0 = (i_start + it) * 128;
+        mbar_wait(qdo_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(qdo_full + 8 * s, 2 * FA_TILE);
+        tma_load_4d(sQ + s * 2 * FA_TILE, &tmQ, qdo_full + 8 * s, 0, q0, h, b);
+        tma_load_4d(sQ + s * 2 * FA_TILE + FA_TILE, &tmDO, qdo_full + 8 * s, 0, q0, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_it > 0) {
+      const uint32_t idesc_kk = umma_idesc_f16(BF16 ? 1 : 0, 0, 0, 128, 128);  // S^T, dP^T
+      const uint32_t idesc_km = umma_idesc_f16(BF16 ? 1 : 0, 0, 1, 128, 64);   // dV, dK
+      const uint32_t idesc_mm = umma_idesc_f16(BF16 ? 1 : 0, 1, 1, 128, 64);   // dQ
+      auto issue_sdp = [&](int it) {
+        const int s = it & 1;
+        const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
+        mbar_wait(qdo_full + 8 * s, (it >> 1) & 1);
+        if (it > 0) mbar_wait(sdp_free, (it - 1) & 1);  // every compute thread holds S^T/dP^T(it-1) in registers
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // S^T[kv, q] = K[kv, d] . Q[q, d]
+          umma_f16(T_ST, umma_smem_desc_sw128(sK + k * 32, 0, 1024), umma_smem_desc_sw128(q + k * 32, 0, 1024),
+                   idesc_kk, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dP^T[kv, q] = V[kv, d] . dO[q, d]
+          umma_f16(T_DPT, umma_smem_desc_sw128(sV + k * 32, 0, 1024),
+                   umma_smem_desc_sw128(d_o + k * 32, 0, 1024), idesc_kk, k > 0);
+        umma_commit(sdp_full);
+      };
+      mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        const uint32_t q = sQ + s * 2 * FA_TILE, d_o = q + FA_TILE;
+        if (it + 1 < n_it) issue_sdp(it + 1);  // runs under the element math of tile it
+        mbar_wait(pds_ready, it & 1);
+        tc_fence_after();
+        const uint32_t pt = sPT + (it & 1) * PDS_STRIDE, dst = sDS + (it & 1) * PDS_STRIDE;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ[q, d] = dS[q, kv] . K[kv, d]  (A MN-major view of dS^T)
+          umma_f16(T_DQ, umma_smem_desc_sw128(dst + k * 2048, FA_TILE, 1024),
+                   umma_smem_desc_sw128(sK + k * 2048, 64 * 128, 1024), idesc_mm, k > 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV[kv, d] += P^T[kv, q] . dO[q, d]   (B MN-major: rows = q)
+          umma_f16(T_DV, umma_smem_desc_sw128(pt + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                   umma_smem_desc_sw128(d_o + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dK[kv, d] += dS^T[kv, q] . Q[q, d]
+          umma_f16(T_DK, umma_smem_desc_sw128(dst + (k >> 2) * FA_TILE + (k & 3) * 32, 0, 1024),
+                   umma_smem_desc_sw128(q + k * 2048, 64 * 128, 1024), idesc_km, (it > 0 || k > 0));
+        umma_commit(qdo_empty + 8 * s);
+        umma_commit(mma_done);  // dQ(it) readable; P^T / dS^T tiles free for tile it+1
+      }
+      umma_commit(dkv_full);
+    }
+  } else {
+    const int wq = warp & 3;
+    const int rr = wq * 32 + lane;   // key row inside the tile (S^T) / query row (dQ)
+    const int hf = (warp - 2) >> 2;  // which pair of 32-query chunks this warp owns
+    const int jg = kv0 + rr;
+    const uint32_t t_lane = (uint32_t)(wq * 32) << 16;
+    FbCtx cx;
+    cx.kb = (p.kbias2 && jg < p.Sk) ? __ldg(p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh + jg) : 0.f;
+    cx.sl2 = p.sl2; cx.scale = p.scale; cx.cf2 = p.causal_fill2;
+    cx.jg = jg; cx.off = p.off; cx.causal = p.causal; cx.key_oob = jg >= p.Sk;
+    cx.lse_s = lse_s; cx.del_s = del_s; cx.sPT = sPT; cx.sDS = sDS; cx.rr = rr; cx.sw = rr & 7;
+    // generic arithmetic for the whole warp when a key is masked (the reference's finite fill matters on
+    // fully masked query rows) or the key tile is ragged
+    const bool warp_generic = __any_sync(0xffffffffu, cx.kb < -1e30f) || (kv0 + 128 > p.Sk);
+    const bool fill_is_ninf = p.causal_fill2 == -INFINITY;
+    const float* lse_bh = p.lse2 + ((int64_t)b * p.H + h) * p.Sq;
+    const float* del_bh = bp.delta + ((int64_t)b * p.H + h) * p.Sq;
+    // per-query statistics of the current query tile, staged as -lse2 and -delta*scale
+    float nlse_next = -INFINITY, ndel_next = 0.f;
+    if (hf == 0 && n_it > 0 && i_start * 128 + rr < p.Sq) {
+      nlse_next = -__ldg(lse_bh + i_start * 128 + rr);
+      ndel_next = -__ldg(del_bh + i_start * 128 + rr) * p.scale;
+    }
+    const int c0 = 2 * hf, c1 = 2 * hf + 1;
+    CT_DBG_CTA(1);
+
+    // dQ rows of query tile `itp`: this thread owns query row rr, columns [32*hf, 32*hf + 32) of d. The 32 KB tile
+    // goes through the dS^T buffer of that tile (free: every MMA of tile itp has retired) and leaves as two TMA
+    // reduce-adds (cp.reduce.async.bulk: fp32 adds in the L2) into the [B,Sq,H,64] workspace — no per-thread
+    // red.global.add, the LSU and the issue slots stay with the element math.
+    auto red_dq = [&](const uint32_t (&r)[32], int itp) {
+      const uint32_t stg = sDS + (itp & 1) * PDS_STRIDE;
+      const uint32_t row = stg + hf * FA_TILE + rr * 128;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((g ^ cx.sw) << 4)), "r"(r[4 * g]),
+                     "r"(r[4 * g + 1]), "r"(r[4 * g + 2]), "r"(r[4 * g + 3])
+                     : "memory");
+      fence_proxy_async_smem();
+      bar_sync_named(2, 256);
+      if (threadIdx.x == 64) {
+        const int q0p = (i_start + itp) * 128;
+        tma_reduce_add_4d(&tmDQ, stg, 0, q0p, h, b);
+        tma_reduce_add_4d(&tmDQ, stg + FA_TILE, 32, q0p, h, b);
+        tma_commit_group();
+        tma_wait_group_read0();  // before this thread reaches the next tile's barrier: the buffer may then be rewritten
+      }
+    };
+
+    for (int it = 0; it < n_it; ++it) {
+      const int q0 = (i_start + it) * 128;
+      if constexpr (PIPE) {
+        cx.sPT = sPT + (it & 1) * PDS_STRIDE; cx.sDS = sDS + (it & 1) * PDS_STRIDE;
+        cx.lse_s = lse_s + (it & 1) * STAT_STRIDE; cx.del_s = del_s + (it & 1) * STAT_STRIDE;
+      }
+      CT_DBG_STAMP(16 * it + 0);
+      mbar_wait(sdp_full, it & 1);
+      CT_DBG_STAMP(16 * it + 1);
+      tc_fence_after();
+      // chunk kinds (warp-uniform)
+      const bool touches_diag = p.causal && (kv0 + 127 > q0 + p.off);
+      const bool aligned_diag = touches_diag && fill_is_ninf && (kv0 == q0 + p.off) && !warp_generic;
+      int kind0, kind1;
+      if (warp_generic || (touches_diag && !aligned_diag)) {
+        kind0 = kind1 = 2;
+      } else if (aligned_diag) {
+        // key row 32*wq+l vs queries 32*c..32*c+31: c < wq entirely future, c > wq entirely visible
+        kind0 = c0 < wq ? 1 : (c0 > wq ? 0 : 2);
+        kind1 = c1 < wq ? 1 : (c1 > wq ? 0 : 2);
+      } else {
+        kind0 = kind1 = 0;
+      }
+      uint32_t rs0[32], rd0[32], rs1[32], rd1[32];
+      if (kind0 != 1) { tmem_ld_32x32(T_ST + t_lane + c0 * 32, rs0); tmem_ld_32x32(T_DPT + t_lane + c0 * 32, rd0); }
+      if (kind1 != 1) { tmem_ld_32x32(T_ST + t_lane + c1 * 32, rs1); tmem_ld_32x32(T_DPT + t_lane + c1 * 32, rd1); }
+      if constexpr (!PIPE) {
+        if (it > 0) {
+          // all MMAs of tile it-1 retired: dQ(it-1) is complete and the P^T / dS^T tiles may be overwritten
+          mbar_wait(mma_done, (it - 1) & 1);
+          tc_fence_after();
+        }
+      }
+      CT_DBG_STAMP(16 * it + 2);
+      // v2: mma_done(it-1) implies pds_ready(it-1): every thread has finished the element math of tile it-1,
+      // nobody still reads its statistics. PIPE: buffer (it & 1) was last read by tile it-2, and every thread
+      // finished tile it-2 before it arrived at the named barrier of tile it-1, which this thread has passed.
+      if (hf == 0) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.lse_s + 4 * rr), "f"(nlse_next) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.del_s + 4 * rr), "f"(ndel_next) : "memory");
+      }
+      tmem_ld_wait();
+      CT_DBG_STAMP(16 * it + 3);
+      tc_fence_before();
+      mbar_arrive(sdp_free);        // S^T / dP^T are in registers: the next tile's MMAs may overwrite them
+      bar_sync_named(1, 256);       // statistics staged by the hf == 0 warps are visible
+      CT_DBG_STAMP(16 * it + 4);
+      if (hf == 0) {
+        const int nq = q0 + 128 + rr;
+        const bool ok = (it + 1 < n_it) && nq < p.Sq;
+        nlse_next = ok ? -__ldg(lse_bh + nq) : -INFINITY;
+        ndel_next = ok ? -__ldg(del_bh + nq) * p.scale : 0.f;
+      }
+      if (kind0 == 0) fb7_chunk<0, BF16>(cx, rs0, rd0, c0, q0);
+      else if (kind0 == 1) fb7_chunk<1, BF16>(cx, rs0, rd0, c0, q0);
+      else fb7_chunk<2, BF16>(cx, rs0, rd0, c0, q0);
+      CT_DBG_STAMP(16 * it + 5);
+      if (it > 0) {
+        // drain dQ(it-1) between the two chunks (T_DQ is only rewritten after pds_ready(it)): the
+        // red.global.add traffic overlaps the second chunk's math
+        if constexpr (PIPE) {
+          // MMAs of tile it-1 ran under chunk 0. Waiting for every phase in order also proves that buffer
+          // ((it+1) & 1) of P^T / dS^T — read by the MMAs of tile it-1 — is free when tile it+1 writes it.
+          mbar_wait(mma_done, (it - 1) & 1);
+          tc_fence_after();
+          CT_DBG_STAMP(16 * it + 9);
+        }
+        uint32_t rq[32];
+        tmem_ld_32x32(T_DQ + t_lane + hf * 32, rq);
+        tmem_ld_wait();
+        red_dq(rq, it - 1);
+      }
+      CT_DBG_STAMP(16 * it + 6);
+      if (kind1 == 0) fb7_chunk<0, BF16>(cx, rs1, rd1, c1, q0);
+      else if (kind1 == 1) fb7_chunk<1, BF16>(cx, rs1, rd1, c1, q0);
+      else fb7_chunk<2, BF16>(cx, rs1, rd1, c1, q0);
+      CT_DBG_STAMP(16 * it + 7);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_ready);
+      CT_DBG_STAMP(16 * it + 8);
+    }
+    CT_DBG_CTA(2);
+    // ---- last dQ tile, then dK / dV for this key row: 32 of the 64 head-dim columns per thread ----
+    if (n_it > 0) {
+      mbar_wait(mma_done, (n_it - 1) & 1);
+      tc_fence_after();
+      uint32_t rq[32];
+      tmem_ld_32x32(T_DQ + t_lane + hf * 32, rq);
+      tmem_ld_wait();
+      red_dq(rq, n_it - 1);
+      mbar_wait(dkv_full, 0);
+      tc_fence_after();
+    }
+    CT_DBG_CTA(3);
+    // ---- dK / dV: TMEM -> registers -> swizzled 16 KB tiles in the (now idle) K / V buffers -> one TMA store each
+    // (rows beyond Sk are clipped by the tensor map) instead of eight row-strided 16-byte stores per thread ----
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint32_t r[32];
+      if (n_it > 0) {
+        tmem_ld_32x32((which == 0 ? T_DV : T_DK) + t_lane + hf * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) r[t] = 0u;
+      }
+      const uint32_t row = (which == 0 ? sV : sK) + rr * 128;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float f0 = __uint_as_float(r[8 * g + 2 * u]), f1 = __uint_as_float(r[8 * g + 2 * u + 1]);
+          if constexpr (BF16) {
+            w[u] = pack_bf16x2(f0, f1);
+          } else {
+            __half2 x = __floats2half2_rn(f0, f1);
+            w[u] = *reinterpret_cast<uint32_t*>(&x);
+          }
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((4 * hf + g) ^ cx.sw) << 4)), "r"(w[0]),
+                     "r"(w[1]), "r"(w[2]), "r"(w[3])
+                     : "memory");
+      }
+    }
+    fence_proxy_async_smem();
+    bar_sync_named(2, 256);
+    if (threadIdx.x == 64) {
+      tma_store_4d(&tmDV, sV, 0, kv0, h, b);
+      tma_store_4d(&tmDK, sK, 0, kv0, h, b);
+      tma_commit_group();
+      tma_wait_group_read0();  // the CTA's shared memory must outlive the reads
     }
   }
   CT_DBG_CTA(4);
@@ -3548,8 +3953,8 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     //                    run on a GPU — written after the round's GPU budget was spent), 7 = v6 (v3 with sixteen
     //                    compute warps, one 32-query chunk each; same status)
     int variant = option(OPT_ATTN_BWD_IMPL);
-    if (variant < 1 || variant > 7) variant = 4;
-    const bool dq_tiled = variant >= 3;
+    if (variant < 1 || variant > 8) variant = 8;  // 8 = v7: v3 + TMA reduce-add dQ drain + TMA-stored dK / dV
+    const bool dq_tiled = variant >= 3 && variant != 8;
     const int nqt = (a.Sq + 127) / 128;
     // the workspace is sized for whole query tiles (include/ct_b200.h): B*H*ceil(Sq/128)*128*64 floats
     const size_t dq_elems = (size_t)a.B * a.H * nqt * FB_DQ_TILE;
@@ -3570,11 +3975,26 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc6_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       attr = true;
     }
     const int64_t grid = (int64_t)a.B * a.H * ((a.Sk + 127) / 128);
     const unsigned g = (unsigned)grid;
     switch (variant) {
+      case 8: {
+        CUtensorMap tmDQ, tmDK, tmDV;
+        // f32 workspace [B, Sq, H, 64] seen as (d, s, h, b); two 32-float (128-byte, swizzled) column panels per tile
+        const uint64_t dims[4] = {64, (uint64_t)a.Sq, (uint64_t)a.H, (uint64_t)a.B};
+        const uint64_t str[4] = {4, (uint64_t)a.H * 64 * 4, 64 * 4, (uint64_t)a.Sq * a.H * 64 * 4};
+        const uint32_t box[4] = {32, 128, 1, 1};
+        if ((rc = make_tmap(&tmDQ, args->dq_accum, 4, 4, dims, str, box, 1))) return rc;
+        if ((rc = make_qkv_tmap(&tmDK, args->dk, args->dk_sb, args->dk_sh, args->dk_ss, a.B, a.H, a.Sk, 64))) return rc;
+        if ((rc = make_qkv_tmap(&tmDV, args->dv, args->dv_sb, args->dv_sh, args->dv_ss, a.B, a.H, a.Sk, 64))) return rc;
+        if (fmt == 1) attn_bwd_tc7_kernel<true><<<g, FB_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, tmDQ, tmDK, tmDV, bp);
+        else attn_bwd_tc7_kernel<false><<<g, FB_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, tmDQ, tmDK, tmDV, bp);
+        break;
+      }
       case 1: attn_bwd_tc_kernel<<<g, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp); break;
       case 2:
         if (fmt == 1) attn_bwd_tc2_kernel<true, 0><<<g, FB_THREADS, FB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, bp);
@@ -3643,10 +4063,10 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
 extern "C" int ct_attn_occupancy(int* fwd_ctas_per_sm, int* bwd_ctas_per_sm, int* detail) {
   CT_REQUIRE(fwd_ctas_per_sm && bwd_ctas_per_sm, CT_ERR_BAD_ARG, "ct_attn_occupancy: null out");
   CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
-  CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
+  CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
   CT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(fwd_ctas_per_sm, attn_fwd_tc4_kernel<true, true>, F4_THREADS,
                                                            F4_SMEM));
-  CT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bwd_ctas_per_sm, attn_bwd_tc2_kernel<true, 3>, FB_THREADS,
+  CT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bwd_ctas_per_sm, attn_bwd_tc7_kernel<true>, FB_THREADS,
                                                            FB_SMEM_PIPE));
   if (detail) {
     cudaFuncAttributes fa;

@@ -90,6 +90,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// The same packing on the integer ALU pipe: add half an ulp of bf16 to the fp32 bit pattern, keep the upper halves
+// (round to nearest, ties away from zero; Inf stays Inf). F2FP.BF16.PACK_AB is issued to the XU pipe — the one MUFU.EX2
+// uses — and occupies it twice as long as an ex2 (two conversions per lane): in the attention kernels, where every
+// exponential is followed by a conversion, that made the CONVERSIONS the bottleneck (r02g ncu: XU 65 % busy in the
+// forward kernel with 2.4 M MUFU.EX2 + 1.3 M F2FP warp instructions). IADD + PRMT cost 1.5 ALU slots per element.
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
+  const uint32_t a = __float_as_uint(lo) + 0x8000u, b = __float_as_uint(hi) + 0x8000u;
+  return __byte_perm(a, b, 0x7632);
+}
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
@@ -212,6 +221,21 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint
       "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// TMA stores: shared tile -> global (plain, or element-wise fp32 add in the L2: cp.reduce). Bulk-group completion:
+// commit, then wait for the group's READS of shared memory before the tile is reused (or the CTA exits).
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   tmap),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA store)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -289,7 +289,8 @@ ATT_CASES = [
     (2, 2, 200, 440, 64, True, 0, "right", -FLT_MAX, 1),    # diagonal offset (240) not a multiple of 128
 ]
 # kernel variants of the tcgen05 path (ATTN_FWD_IMPL, ATTN_BWD_IMPL): "f4" = the defaults (forward generation 4: two
-# threads per query row, lazy reference maximum; backward v3 with the fused dQ convert); "v1" = first-generation softmax
+# threads per query row, lazy reference maximum, bf16 packing on the ALU pipe; backward v7 = v3 + TMA reduce-add dQ
+# drain + TMA-stored dK / dV + ALU packing); "v1" = first-generation softmax
 # / backward math, "v2" = forward generation 2 (one thread per row) + register-resident backward, "v2t" = v2 backward
 # with the tiled dQ workspace, "v3" = backward with double-buffered P^T / dS^T, "v4" = v3 with the dQ drain on its own
 # warpgroup, "v5" = persistent v3, "v6" = v3 with sixteen compute warps, "f3" = forward generation 2 with the lazy

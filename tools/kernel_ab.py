@@ -132,9 +132,9 @@ def attn_ab():
         ref = _attn_oracle(qr, kr, vr, scale, True, fill, kb2[:nb].expand(nb, H, S) if kb2 is not None else None)
         do = torch.randn(B, S, H * D, device=DEV).bfloat16()
         ref.backward(do[:nb].float())
-        # (forward option, backward option): f4 = the defaults (forward generation 4, backward v3 + fused dQ convert);
+        # (forward option, backward option): f4 = the defaults (forward generation 4, backward v7);
         # v3 = forward generation 2 + backward v3
-        for impl, (fi, bi) in (("f4", (0, 0)), ("v3", (3, 4)), ("v4", (3, 5))):
+        for impl, (fi, bi) in (("f4", (0, 0)), ("v3", (3, 4))):
             pf, pb = ops.set_option("ATTN_FWD_IMPL", fi), ops.set_option("ATTN_BWD_IMPL", bi)
             try:
                 o, lse2 = ops.attn_fwd(q, k, v, scale, True, fill, kb2, fv)
