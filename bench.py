@@ -39,6 +39,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"],
                     help="ours = this repo; reference = the reference's CPU path (oracle port) on host cores; "
                          "eager = the reference's eager-PyTorch path (oracle under bf16 autocast + torch AdamW/DDP) on the GPUs")
+    ap.add_argument("--workload", default="bloom_sft", choices=["bloom_sft", "gpt2_decode", "bert_cls"],
+                    help="bloom_sft = BASELINE.json's metric (configs[1], default); gpt2_decode = configs[3] (GPT-2-medium "
+                         "greedy decode with the KV cache, batch 32, 512 new tokens); bert_cls = configs[4] (bert-base "
+                         "sequence classification step, 64 x 512 per GPU)")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--layers", type=int, default=24)
@@ -450,6 +454,239 @@ def recorded_traffic(kernel):
 
 
 # ------------------------------------------------------------------------------------------------
+# extra workloads (BASELINE.json configs[3] and configs[4]); the default bench line is bloom_sft
+# ------------------------------------------------------------------------------------------------
+def _init_like_reference(model, seed=999):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() >= 2:
+                p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.device))
+            elif n.endswith("bias"):
+                p.zero_()
+            else:
+                p.fill_(1.0)
+
+
+def run_gpt2_decode(args):
+    """configs[3]: GPT-2-medium greedy decoding through GenerationMixin._greedy_search with the KV cache
+    (generation_util.py:57-119, modeling_gpt.py:76-80): batch 32, LEFT-padded prompts of 16..32 tokens, 512 new tokens.
+    A step = one whole generation. HBM roofline: every token-step streams the bf16 weights (709.6 MB) and the KV cache
+    (98,304 B per sequence per cached position), SURVEY §8 d6."""
+    from cleantransformer_b200 import ops
+    from cleantransformer_b200.models import modeling_gpt as mg
+    from oracle import ct_oracle as O
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ops.device_check(local)
+    L, NH, E, V, P, NEW = 24, 16, 1024, 50257, 32, 512
+    B = 32
+    cfg = dict(vocab_size=V, n_embd=E, n_positions=1024, n_layer=L, n_head=NH, n_ctx=1024, afn="gelu_new")
+    model = mg.GPTLMHeadModel(mg.GPTConfig(**cfg), version="gpt2").to(dev).eval()
+    _init_like_reference(model)
+    model._tie_weights()
+    g = torch.Generator().manual_seed(999)
+    ids_h = torch.randint(1, V, (B, P), generator=g)
+    lens = torch.randint(16, 33, (B,), generator=g).tolist()
+    mask_h = torch.ones(B, P, dtype=torch.long)
+    for b, n in enumerate(lens):
+        mask_h[b, :P - n] = 0
+        ids_h[b, :P - n] = 0
+    ids_h, mask_h = ids_h.pin_memory(), mask_h.pin_memory()
+    ids, mask = ids_h.to(dev), mask_h.to(dev)
+    gc = {"beam_size": 1, "do_sample": False, "max_gen_len": NEW - 2, "end_ids": None, "pad_id": 0,
+          "no_repeat_ngram_size": 0}
+
+    def step_resident():
+        return model.generate(ids, attention_mask=mask, generation_configs=gc)
+
+    def step_e2e():
+        return model.generate(ids_h.to(dev, non_blocking=True), attention_mask=mask_h.to(dev, non_blocking=True),
+                              generation_configs=gc).cpu()
+
+    def timed(fn, k):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), out
+
+    steps, warm = max(1, min(args.steps, 5)), max(args.warmup, 3)
+    for _ in range(warm):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.LAUNCHES[0]
+    ms, out = timed(step_resident, steps)
+    launches = ops.LAUNCHES[0] - l0
+    ms_e2e, out2 = timed(step_e2e, steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    assert out.shape == (B, 1, P + NEW) and torch.equal(out.cpu(), out2)
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    n_w = sum(p.numel() for p in model.parameters())
+    kv_bytes = sum(2 * L * E * 2 * B * (P + t) for t in range(NEW))       # K and V, bf16, read once per token-step
+    alg = NEW * n_w * 2 + kv_bytes                                       # bf16 weights streamed once per token-step
+    value = B * NEW * steps / (ms * 1e-3)
+    # the reference's own path on the same GPU: oracle restatement in fp32 (inference_gpt2.py runs the model as loaded)
+    eager = None
+    if not args.no_eager_baseline:
+        sd = {k: v.detach() for k, v in model.state_dict().items()}
+
+        def step_fn(i, m, kv):
+            with torch.no_grad():
+                return O.gpt_lm_head_model(i, m, sd, L, NH, 1024, 1e-5, version="gpt2", k_v_pasts=kv)
+
+        O.greedy_generate(step_fn, ids, mask, L, 30, pad_id=0)
+        ms_ref, _ = timed(lambda: O.greedy_generate(step_fn, ids, mask, L, NEW - 2, pad_id=0), 1)
+        eager = {"value": B * NEW / (ms_ref * 1e-3), "unit": "tokens/s", "ms_per_step": ms_ref,
+                 "what": "the reference's eager-PyTorch arithmetic (oracle restatement of modeling_gpt.py + "
+                         "generation_util.py:57-119), fp32, torch.concat KV cache, same prompts, 1 generation"}
+    line = {"metric": "GPT-2-medium greedy decode tokens/sec (KV cache)", "value": value, "unit": "tokens/s", "n_gpus": 1,
+            "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "GPT-2-medium greedy decode (configs[3]): batch 32, left-padded prompts 16..32, "
+                                   "512 new tokens, KV cache, random-init weights; a step = one whole generation",
+                       "global_batch": B, "prompt_len": P, "new_tokens": NEW, "layers": L,
+                       "l2": "709.6 MB of bf16 weights re-streamed every token-step (> 126 MB L2); no flush"},
+            "e2e": {"value": B * NEW * steps / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 2 * B * P * 8,
+                    "d2h_bytes_per_step": B * (P + NEW) * 8, "ms_per_step": ms_e2e / steps},
+            "gpu_launches": launches, "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": "decode token-step (weight-streaming GEMMs + cache attention)",
+                         "achieved": alg * steps / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg * steps / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                         "peak_source": peak_kind + " (hbm_gbs)",
+                         "algorithmic_bytes_per_generation": alg,
+                         "note": "launch-bound today: ~%d kernel launches per token-step from the Python loop; the "
+                                 "captured decode step of SURVEY §8 f N2 is not built yet" % (launches // (steps * NEW))}}
+    if eager is not None:
+        line["eager_baseline"] = dict(eager, speedup=value / eager["value"])
+    print(json.dumps(line), flush=True)
+
+
+def run_bert_cls(args):
+    """configs[4]: bert-base sequence classification training step (modeling_bert.py:232-333), 64 x 512 per GPU, DDP for
+    N > 1; loss = torch CrossEntropyLoss on the 28-way logits (the reference model has none, :332). Dropout is 0 (the fused
+    sites implement no dropout; the reference default is 0.1 — stated in `config`)."""
+    import torch.distributed as dist
+    from cleantransformer_b200 import ops
+    from cleantransformer_b200.models import modeling_bert as mbert
+    from cleantransformer_b200.optimizer import TorchAdamW
+    from cleantransformer_b200.ddp import DistributedDataParallel
+    from oracle import ct_oracle as O
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ops.device_check(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, S, NL = 64, 512, 28
+    cfg = mbert.BertConfig(num_labels=NL, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    model = mbert.BertForSequenceClassification(cfg).to(dev).train()
+    _init_like_reference(model)
+    net = DistributedDataParallel(model, device_ids=[local], comm=args.comm) if world > 1 else model
+    opt = TorchAdamW(net.parameters(), lr=1e-5)
+    g = torch.Generator().manual_seed(999 + rank)
+    ids_h = torch.randint(1, 30522, (B, S), generator=g).pin_memory()
+    lab_h = torch.randint(0, NL, (B,), generator=g).pin_memory()
+    ids, labels = ids_h.to(dev), lab_h.to(dev)
+    mask = torch.ones(B, S, device=dev)
+    seg = torch.zeros(B, S, dtype=torch.long, device=dev)
+    pos = torch.arange(S, device=dev)
+
+    def step(i, l):
+        opt.zero_grad()
+        logits = net(i, mask, seg, pos)
+        loss = torch.nn.functional.cross_entropy(logits.float(), l)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t)
+        return ms, out
+
+    for _ in range(max(args.warmup, 3)):
+        step(ids, labels)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.LAUNCHES[0]
+    ms, loss = timed(lambda: step(ids, labels), args.steps)
+    launches = ops.LAUNCHES[0] - l0
+    ms_e2e, loss2 = timed(lambda: step(ids_h.to(dev, non_blocking=True), lab_h.to(dev, non_blocking=True)).item(), args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    peaks, peak_kind = measured_peaks()
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    flop = 18.554e12 * (B * S / 32768.0)  # SURVEY §8 d5: bidirectional, dense, fwd+bwd
+    tokens = B * S * world
+    value = tokens * args.steps / (ms * 1e-3)
+    eager = None
+    if not args.no_eager_baseline:
+        sd = {k: torch.nn.Parameter(v.detach().clone()) for k, v in model.state_dict().items()}
+        eopt = torch.optim.AdamW(list(sd.values()), lr=1e-5)
+
+        def estep():
+            eopt.zero_grad()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                lg, _, _ = O.bert_classifier(ids, mask, seg, pos, sd, 12, 12, cfg.layer_norm_eps)
+            l = torch.nn.functional.cross_entropy(lg.float(), labels)
+            l.backward()
+            eopt.step()
+            return l
+
+        for _ in range(3):
+            estep()
+        ems, _ = timed(estep, 5)
+        eager = {"value": B * S * 5 / (ems * 1e-3) * world, "unit": "tokens/s", "ms_per_step": ems / 5,
+                 "what": "oracle restatement of modeling_bert.py under torch.autocast(bfloat16) + torch.optim.AdamW, "
+                         "per-GPU step without gradient exchange x world (upper bound for the reference under DDP)"}
+    if rank == 0:
+        line = {"metric": "BERT-base sequence-classification training tokens/sec", "value": value, "unit": "tokens/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "bert-base classification step (configs[4]): fwd + CE + bwd + AdamW, 64 x 512 per "
+                                       "GPU, 28 labels, random-init weights, dropout 0 (reference default 0.1: the fused "
+                                       "sites have no dropout yet)", "global_batch": B * world, "seq_len": S,
+                           "layers": 12, "parallelism": "dp%d" % world,
+                           "ddp_comm": (args.comm or "p2p") if world > 1 else None,
+                           "l2": "activations >> 126 MB L2; no flush"},
+                "e2e": {"value": tokens * args.steps / (ms_e2e * 1e-3), "unit": "tokens/s",
+                        "h2d_bytes_per_step": B * S * 8 + B * 8, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "loss": float(loss.detach()), "clocks": sampler.summary(),
+                "roofline": {"bound": "tensor", "kernel": "whole step (projection / FFN GEMMs + attention)",
+                             "achieved": flop / (ms / args.steps * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                             "frac": flop / (ms / args.steps * 1e-3) / 1e12 / peak, "traffic": None,
+                             "peak_source": peak_kind + " (bf16_tflops_sustained)"}}
+        if eager is not None:
+            line["eager_baseline"] = dict(eager, speedup=value / eager["value"])
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def main():
@@ -459,6 +696,12 @@ def main():
         return
     if args.impl == "eager":
         run_eager_arm(args)
+        return
+    if args.workload == "gpt2_decode":
+        run_gpt2_decode(args)
+        return
+    if args.workload == "bert_cls":
+        run_bert_cls(args)
         return
     import torch.distributed as dist
     from cleantransformer_b200 import ops

@@ -88,9 +88,9 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
 // Initial values come from the environment (CT_<NAME>), ct_set_option overrides at run time.
 static int g_opt[OPT_COUNT];
 static std::once_flag g_opt_once;
-static const char* const kOptNames[OPT_COUNT] = {"LN_BWD_IMPL", "ATTN_FWD_IMPL", "ATTN_BWD_IMPL", "GEMM_EPI_IMPL",
+static const char* const kOptNames[OPT_COUNT] = {"LN_BWD_IMPL", "GEMM_EPI_IMPL",
                                                  "GEMM_2CTA", "CE_IMPL", "GEMM_SPLITK"};
-static const int kOptDefaults[OPT_COUNT] = {0, 0, 0, 0, 1, 0, 0};
+static const int kOptDefaults[OPT_COUNT] = {0, 0, 1, 0, 0};
 static void opt_init() {
   std::call_once(g_opt_once, [] {
     for (int i = 0; i < OPT_COUNT; ++i) {

@@ -54,7 +54,7 @@ const char* get_error();
 int sm_count();  // cached multiprocessor count of the current device
 
 // Tuning knobs (ct_set_option / CT_<NAME> environment variables); 0 always means "default / auto".
-enum : int { OPT_LN_BWD_IMPL = 0, OPT_ATTN_FWD_IMPL, OPT_ATTN_BWD_IMPL, OPT_GEMM_EPI_IMPL, OPT_GEMM_2CTA, OPT_CE_IMPL,
+enum : int { OPT_LN_BWD_IMPL = 0, OPT_GEMM_EPI_IMPL, OPT_GEMM_2CTA, OPT_CE_IMPL,
              OPT_GEMM_SPLITK, OPT_COUNT };
 int option(int which);
 
@@ -221,21 +221,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint
       "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-// TMA stores: shared tile -> global (plain, or element-wise fp32 add in the L2: cp.reduce). Bulk-group completion:
-// commit, then wait for the group's READS of shared memory before the tile is reused (or the CTA exits).
-__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                   tmap),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA store)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -288,41 +288,15 @@ ATT_CASES = [
     (2, 2, 256, 640, 64, True, 0, "none", -FLT_MAX, 1),     # Sq < Sk: diagonal offset by 384 (aligned)
     (2, 2, 200, 440, 64, True, 0, "right", -FLT_MAX, 1),    # diagonal offset (240) not a multiple of 128
 ]
-# kernel variants of the tcgen05 path (ATTN_FWD_IMPL, ATTN_BWD_IMPL): "f4" = the defaults (forward generation 4: two
-# threads per query row, lazy reference maximum, bf16 packing on the ALU pipe; backward v7 = v3 + TMA reduce-add dQ
-# drain + TMA-stored dK / dV + ALU packing); "v1" = first-generation softmax
-# / backward math, "v2" = forward generation 2 (one thread per row) + register-resident backward, "v2t" = v2 backward
-# with the tiled dQ workspace, "v3" = backward with double-buffered P^T / dS^T, "v4" = v3 with the dQ drain on its own
-# warpgroup, "v5" = persistent v3, "v6" = v3 with sixteen compute warps, "f3" = forward generation 2 with the lazy
-# maximum and per-panel P hand-over
-ATT_VARIANTS = {"f4": (0, 0), "v1": (1, 1), "v2": (3, 2), "v2t": (3, 3), "v3": (3, 4), "v4": (3, 5), "v5": (3, 6),
-                "v6": (3, 7), "f3": (2, 4)}
-ATT_PARAMS = [c + ("-",) for c in ATT_CASES if c[-1] == 2] + \
-             [c + (v,) for c in ATT_CASES if c[-1] == 1 for v in ATT_VARIANTS]
-
-
-class _AttnVariant:
-    def __init__(self, variant):
-        self.v = ATT_VARIANTS.get(variant)
-
-    def __enter__(self):
-        if self.v is not None:
-            ops = _ops()
-            self.prev = (ops.set_option("ATTN_FWD_IMPL", self.v[0]), ops.set_option("ATTN_BWD_IMPL", self.v[1]))
-
-    def __exit__(self, *exc):
-        if self.v is not None:
-            ops = _ops()
-            ops.set_option("ATTN_FWD_IMPL", self.prev[0]); ops.set_option("ATTN_BWD_IMPL", self.prev[1])
+ATT_PARAMS = ATT_CASES
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
-@pytest.mark.parametrize("B,H,Sq,Sk,D,causal,mode,pad,cfill,impl,variant", ATT_PARAMS)
-def test_attention_fwd_bwd_vs_oracle(B, H, Sq, Sk, D, causal, mode, pad, cfill, impl, variant, dtype):
+@pytest.mark.parametrize("B,H,Sq,Sk,D,causal,mode,pad,cfill,impl", ATT_PARAMS)
+def test_attention_fwd_bwd_vs_oracle(B, H, Sq, Sk, D, causal, mode, pad, cfill, impl, dtype):
     if dtype == torch.float16 and (impl == 2 or Sq == 300):
         pytest.skip("f16 operands: tcgen05 path only, one shape per mask family")
-    with _AttnVariant(variant):
-        _attention_case(B, H, Sq, Sk, D, causal, mode, pad, cfill, impl, dtype)
+    _attention_case(B, H, Sq, Sk, D, causal, mode, pad, cfill, impl, dtype)
 
 
 def _attention_case(B, H, Sq, Sk, D, causal, mode, pad, cfill, impl, dtype):
@@ -383,13 +357,7 @@ def test_attention_matches_reference_bloom_layer(golden):
     assert rel_err(o, ref) < 8e-3
 
 
-@pytest.mark.parametrize("variant", ["f4", "v1", "v2"])
-def test_attention_rows_sum_to_one_at_full_size(variant):
-    with _AttnVariant(variant):
-        _rows_sum_to_one()
-
-
-def _rows_sum_to_one():
+def test_attention_rows_sum_to_one_at_full_size():
     """Property at BASELINE.json's size (B=8,H=16,S=1024,d=64): with V = 1 every output element is
     the softmax row sum, i.e. exactly 1 up to bf16 rounding of P; checks every tile incl. the diagonal."""
     ops = _ops()

@@ -1,8 +1,7 @@
 """A/B of kernel variants at the Bloom-560M bench shapes: parity error against a torch fp32 restatement
 and CUDA-event time per launch (inputs > L2 are rotated between launches), for
   LayerNorm backward  (LN_BWD_IMPL 1 = warp-per-row, 0 = row spread over cols/4 threads)
-  attention forward   (ATTN_FWD_IMPL 1 = v1, 0 = v2)
-  attention backward  (ATTN_BWD_IMPL 1 = v1, 2 = v2, 3 = v2 + tiled dQ workspace, 4 = v3 pipelined)
+  attention forward / backward (default kernels; occupancy diagnostic)
   GEMM epilogues      (GEMM_EPI_IMPL 1 = generic, 2 = specialised with row-per-thread residual loads, 0 = specialised)
 Prints one JSON line per measurement; never asserts (a failing variant shows up as a large error or an
 `error` field), so one GPU visit tells everything.   python tools/kernel_ab.py [ln] [attn] [gemm]
@@ -132,10 +131,7 @@ def attn_ab():
         ref = _attn_oracle(qr, kr, vr, scale, True, fill, kb2[:nb].expand(nb, H, S) if kb2 is not None else None)
         do = torch.randn(B, S, H * D, device=DEV).bfloat16()
         ref.backward(do[:nb].float())
-        # (forward option, backward option): f4 = the defaults (forward generation 4, backward v7);
-        # v3 = forward generation 2 + backward v3
-        for impl, (fi, bi) in (("f4", (0, 0)), ("v3", (3, 4))):
-            pf, pb = ops.set_option("ATTN_FWD_IMPL", fi), ops.set_option("ATTN_BWD_IMPL", bi)
+        for impl in ("default",):  # (older generations were removed; their numbers live in profiles/)
             try:
                 o, lse2 = ops.attn_fwd(q, k, v, scale, True, fill, kb2, fv)
                 dqkv = torch.zeros_like(qkv)
@@ -152,7 +148,7 @@ def attn_ab():
             except Exception as ex:  # noqa: BLE001
                 out(kernel="attention", case=name, impl=impl, error=repr(ex)[:300])
             finally:
-                ops.set_option("ATTN_FWD_IMPL", pf); ops.set_option("ATTN_BWD_IMPL", pb)
+                pass
 
 
 def gemm_ab():
