@@ -562,8 +562,11 @@ def run_gpt2_decode(args):
                          "frac": alg * steps / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                          "peak_source": peak_kind + " (hbm_gbs)",
                          "algorithmic_bytes_per_generation": alg,
-                         "note": "launch-bound today: ~%d kernel launches per token-step from the Python loop; the "
-                                 "captured decode step of SURVEY §8 f N2 is not built yet" % (launches // (steps * NEW))}}
+                         "kernel_launches_per_token_step": launches // (steps * NEW),
+                         "captured_step": bool(getattr(model, "_ct_decode_graph_launches", 0)),
+                         "note": "every q_len = 1 step after the first is one replay of a captured CUDA graph "
+                                 "(cleantransformer_b200/generation.py: _graphed_greedy; CT_DECODE_GRAPH=0 runs the "
+                                 "un-captured loop); M = 32 rows per GEMM, so the step is weight-streaming bound"}}
     if eager is not None:
         line["eager_baseline"] = dict(eager, speedup=value / eager["value"])
     print(json.dumps(line), flush=True)

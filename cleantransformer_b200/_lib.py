@@ -57,6 +57,7 @@ class AttnArgs(ctypes.Structure):
         ("kbias2", c_void_p), ("kb_sb", c_i64), ("kb_sh", c_i64),
         ("first_valid", c_void_p),
         ("impl", ctypes.c_int32),
+        ("seq_len_dev", c_void_p),
     ]
 
 
@@ -155,6 +156,10 @@ SIGNATURES = {
     "ct_kv_append": (c_int, [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int,
                              c_int, c_int, c_int, c_void_p]),
     "ct_attn_decode": (c_int, [ctypes.POINTER(AttnArgs), c_void_p]),
+    "ct_kv_append_dev": (c_int, [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int,
+                                 c_int, c_void_p, c_int, c_void_p]),
+    "ct_greedy_step": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_int, c_i64, c_void_p, c_i64,
+                               c_void_p, c_void_p, c_void_p, c_void_p]),
     "ct_gemm_wgrad_bias": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_i64,
                                    c_i64, c_i64, c_int, c_void_p]),
 }

@@ -74,6 +74,7 @@ struct AttnP {
   const int32_t* first_valid;
   void* o; int64_t o_sb, o_sh, o_ss;
   float* lse2;
+  const int32_t* sk_dev;  // decode from a CUDA graph: the number of cached keys lives in device memory (else null)
 };
 
 // score in the log2 domain for element (query i, key j) given the raw dot product
@@ -1113,6 +1114,129 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32)
   if (p.lse2 && lane == 0) p.lse2[((int64_t)b * p.H + h) * p.Sq + i] = m + log2f(l);
 }
 
+// q_len = 1 decode against a [b,h,t,d] cache (modeling_gpt.py:76-103 / modeling_bloom.py:88-116 with one new token),
+// head_dim D in {32, 64, 128}: one CTA of DEC_WARPS warps per (b, h), the keys dealt to the warps in groups of
+// 4 * KPI (KPI = keys per warp instruction). Keys and values are read as whole rows (D/8 lanes x 16 bytes per key); the
+// key count may live in device memory (sk_dev) so that one captured step serves every position of a generation.
+// Same score definition as every other path (score2); P is rounded to the activation dtype before P.V.
+constexpr int DEC_WARPS = 8;
+
+template <int D>
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+    attn_decode_kernel(const SimtP sp) {
+  constexpr int LPK = D / 8;     // lanes per key row
+  constexpr int KPI = 32 / LPK;  // keys per warp-wide load instruction
+  constexpr int G = 4;           // load groups in flight per iteration
+  const AttnP& p = sp.a;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = (int)(blockIdx.x % p.H), b = (int)(blockIdx.x / p.H);
+  const int Sk = p.sk_dev ? min(*p.sk_dev, p.Sk) : p.Sk;  // p.Sk is the capacity when the count is on the device
+  const int sub = lane / LPK, part = lane % LPK;  // key sub-slot inside a group, 16-byte piece of the row
+  auto unpack2 = [&](uint32_t w) {
+    return p.fmt == 1 ? unpack_bf16x2(w) : __half22float2(*reinterpret_cast<const __half2*>(&w));
+  };
+  float qf[8];  // the 8 query elements this lane multiplies
+  {
+    const uint4 qv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(sp.q) + (int64_t)b * sp.q_sb +
+                                                     (int64_t)h * sp.q_sh + part * 8);
+    const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 f = unpack2(qw[u]);
+      qf[2 * u] = f.x; qf[2 * u + 1] = f.y;
+    }
+  }
+  const float* kb_row = p.kbias2 ? p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh : nullptr;
+  const uint16_t* kbase = reinterpret_cast<const uint16_t*>(sp.k) + (int64_t)b * sp.k_sb + (int64_t)h * sp.k_sh + part * 8;
+  const uint16_t* vbase = reinterpret_cast<const uint16_t*>(sp.v) + (int64_t)b * sp.v_sb + (int64_t)h * sp.v_sh + part * 8;
+  float m = -INFINITY, l = 0.f;
+  float o_acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // this lane's 8 output columns, for its key sub-slot
+  for (int j0 = wib * (G * KPI); j0 < Sk; j0 += DEC_WARPS * G * KPI) {
+    float sc[G];
+    uint4 kv[G], vv[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {  // all loads of the iteration first: 2 * G 16-byte requests in flight per lane
+      const int j = j0 + KPI * g + sub;
+      kv[g] = make_uint4(0u, 0u, 0u, 0u);
+      vv[g] = make_uint4(0u, 0u, 0u, 0u);
+      if (j < Sk) {
+        kv[g] = *reinterpret_cast<const uint4*>(kbase + (int64_t)j * sp.k_ss);
+        vv[g] = *reinterpret_cast<const uint4*>(vbase + (int64_t)j * sp.v_ss);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int j = j0 + KPI * g + sub;
+      const uint32_t kw[4] = {kv[g].x, kv[g].y, kv[g].z, kv[g].w};
+      float acc = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 f = unpack2(kw[u]);
+        acc = fmaf(qf[2 * u], f.x, acc);
+        acc = fmaf(qf[2 * u + 1], f.y, acc);
+      }
+#pragma unroll
+      for (int o = LPK / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      // q_len == 1: the query is the last position, nothing lies in its future
+      sc[g] = j < Sk ? score2(acc, p.sl2, kb_row ? __ldg(kb_row + j) : 0.f, false, p.causal_fill2, false) : -INFINITY;
+    }
+    float mt = sc[0];
+#pragma unroll
+    for (int g = 1; g < G; ++g) mt = fmaxf(mt, sc[g]);
+#pragma unroll
+    for (int o = LPK; o < 32; o <<= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+    const float m_new = fmaxf(m, mt);
+    const float alpha = ex2(m - m_new);
+    l *= alpha;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) o_acc[u] *= alpha;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float e = ex2(sc[g] - m_new);
+      const float er = p.fmt == 1 ? __bfloat162float(__float2bfloat16_rn(e)) : __half2float(__float2half_rn(e));
+      if (part == 0) l += e;  // one lane per key sub-slot counts the key once
+      const uint32_t vw[4] = {vv[g].x, vv[g].y, vv[g].z, vv[g].w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 f = unpack2(vw[u]);
+        o_acc[2 * u] = fmaf(er, f.x, o_acc[2 * u]);
+        o_acc[2 * u + 1] = fmaf(er, f.y, o_acc[2 * u + 1]);
+      }
+    }
+    m = m_new;
+  }
+  // combine the key sub-slots of the warp (lanes with the same `part` share m already) ...
+#pragma unroll
+  for (int o = LPK; o < 32; o <<= 1) {
+    l += __shfl_xor_sync(0xffffffffu, l, o);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) o_acc[u] += __shfl_xor_sync(0xffffffffu, o_acc[u], o);
+  }
+  l = __shfl_sync(0xffffffffu, l, 0);  // lanes with part != 0 carried partial counts only
+  // ... then the warps of the CTA
+  __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
+  __shared__ float s_o[DEC_WARPS][D];
+  if (lane == 0) { s_m[wib] = m; s_l[wib] = l; }
+  if (sub == 0) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s_o[wib][part * 8 + u] = o_acc[u];
+  }
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float mm = s_m[0];
+#pragma unroll
+    for (int w = 1; w < DEC_WARPS; ++w) mm = fmaxf(mm, s_m[w]);
+    float lt = 0.f, ot = 0.f;
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) {
+      const float f = s_m[w] == -INFINITY ? 0.f : ex2(s_m[w] - mm);  // warps that saw no key contribute nothing
+      lt = fmaf(s_l[w], f, lt);
+      ot = fmaf(s_o[w][threadIdx.x], f, ot);
+    }
+    st16(p.o, p.fmt, (int64_t)b * p.o_sb + (int64_t)h * p.o_sh + threadIdx.x, ot / lt);
+  }
+}
+
 struct SimtBwdP {
   SimtP s;
   const void* dout;
@@ -1332,6 +1456,24 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// the same with the destination taken from device memory: rows [*len_dev - S, *len_dev) (captured decode step)
+__global__ void __launch_bounds__(256)
+    kv_append_dev_kernel(const uint16_t* __restrict__ src, int64_t s_sb, int64_t s_sh, int64_t s_ss,
+                         uint16_t* __restrict__ cache, int64_t c_sb, int64_t c_sh, int64_t c_ss, int B, int H,
+                         int S, int D, const int32_t* __restrict__ len_dev, int t_max) {
+  const int pos = *len_dev - S;
+  if (pos < 0 || pos + S > t_max) return;  // (a full cache: nothing is written; the host sized it for the generation)
+  const int64_t n = (int64_t)B * H * S * D;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(e % D);
+    const int sidx = (int)((e / D) % S);
+    const int h = (int)((e / ((int64_t)D * S)) % H);
+    const int b = (int)(e / ((int64_t)D * S * H));
+    cache[(int64_t)b * c_sb + (int64_t)h * c_sh + (int64_t)(pos + sidx) * c_ss + d] =
+        src[(int64_t)b * s_sb + (int64_t)h * s_sh + (int64_t)sidx * s_ss + d];
+  }
+}
+
 static int make_qkv_tmap(CUtensorMap* tm, const void* base, int64_t sb, int64_t sh, int64_t ss, int B,
                          int H, int S, int D) {
   uint64_t dims[4] = {(uint64_t)D, (uint64_t)S, (uint64_t)H, (uint64_t)B};
@@ -1356,6 +1498,7 @@ static void fill_common(AttnP& p, const ct_attn_args& a) {
   p.first_valid = a.first_valid;
   p.o = a.o; p.o_sb = a.o_sb; p.o_sh = a.o_sh; p.o_ss = a.o_ss;
   p.lse2 = a.lse2;
+  p.sk_dev = a.seq_len_dev;
 }
 
 static int check_args(const ct_attn_args& a, const char* who) {
@@ -1388,6 +1531,7 @@ extern "C" int ct_attn_fwd(const ct_attn_args* args, void* stream) {
   } else {
     use_tc = tc_ok && a.Sq >= 16 && a.scale > 0.f;
   }
+  if (a.seq_len_dev != nullptr) use_tc = false;
   if (use_tc) {
     AttnP p;
     fill_common(p, a);
@@ -1420,6 +1564,20 @@ extern "C" int ct_attn_fwd(const ct_attn_args* args, void* stream) {
   sp.q_sb = a.q_sb; sp.q_sh = a.q_sh; sp.q_ss = a.q_ss;
   sp.k_sb = a.k_sb; sp.k_sh = a.k_sh; sp.k_ss = a.k_ss;
   sp.v_sb = a.v_sb; sp.v_sh = a.v_sh; sp.v_ss = a.v_ss;
+  const bool decode = a.Sq == 1 && (a.D == 32 || a.D == 64 || a.D == 128) && a.lse2 == nullptr &&
+                      tma_ok4(a.q, a.q_sb, a.q_sh, 8) && tma_ok4(a.k, a.k_sb, a.k_sh, a.k_ss) &&
+                      tma_ok4(a.v, a.v_sb, a.v_sh, a.v_ss);
+  CT_REQUIRE(a.seq_len_dev == nullptr || decode, CT_ERR_UNSUPPORTED,
+             "ct_attn_fwd: a device-side key count needs the q_len = 1 decode kernel (head_dim 32 / 64 / 128, 16-byte "
+             "aligned rows, no lse output)");
+  if (decode) {
+    const unsigned grid = (unsigned)((int64_t)a.B * a.H);
+    if (a.D == 32) attn_decode_kernel<32><<<grid, DEC_WARPS * 32, 0, st>>>(sp);
+    else if (a.D == 64) attn_decode_kernel<64><<<grid, DEC_WARPS * 32, 0, st>>>(sp);
+    else attn_decode_kernel<128><<<grid, DEC_WARPS * 32, 0, st>>>(sp);
+    CT_LAUNCH_OK();
+    return 0;
+  }
   const int64_t warps = (int64_t)a.B * a.H * a.Sq;
   attn_fwd_simt_kernel<<<(unsigned)((warps + SIMT_WARPS - 1) / SIMT_WARPS), SIMT_WARPS * 32, 0, st>>>(sp);
   CT_LAUNCH_OK();
@@ -1564,6 +1722,20 @@ extern "C" int ct_kv_append(const void* src, int64_t s_sb, int64_t s_sh, int64_t
   if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
   kv_append_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       (const uint16_t*)src, s_sb, s_sh, s_ss, (uint16_t*)cache, c_sb, c_sh, c_ss, B, H, S_new, D, pos);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_kv_append_dev(const void* src, int64_t s_sb, int64_t s_sh, int64_t s_ss, void* cache,
+                                int64_t c_sb, int64_t c_sh, int64_t c_ss, int B, int H, int S_new, int D,
+                                const int32_t* len_dev, int t_max, void* stream) {
+  CT_REQUIRE(src && cache && len_dev, CT_ERR_BAD_ARG, "ct_kv_append_dev: null pointer");
+  CT_REQUIRE(B > 0 && H > 0 && S_new > 0 && D > 0 && t_max >= S_new, CT_ERR_BAD_ARG, "ct_kv_append_dev: bad shape");
+  const int64_t n = (int64_t)B * H * S_new * D;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  kv_append_dev_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const uint16_t*)src, s_sb, s_sh, s_ss, (uint16_t*)cache, c_sb, c_sh, c_ss, B, H, S_new, D, len_dev, t_max);
   CT_LAUNCH_OK();
   return 0;
 }

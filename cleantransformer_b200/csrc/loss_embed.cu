@@ -631,6 +631,72 @@ __global__ void __launch_bounds__(256)
     x[i] = (T)((float)x[i] * s);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// One step of GenerationMixin._greedy_search after the model call (generation_util.py:86-101, do_sample = False),
+// entirely on the device so that a whole decode step can be replayed from a CUDA graph:
+//   next = argmax(logits[b, :])  (first maximum, like torch.argmax);  next = next * alive + pad * (1 - alive);
+//   alive[b] &= next not in end_ids;  ids_out[b, out_pos] = next;  cur_ids[b] = next;  pos_ids[b] += 1;
+//   once per call (last block): out_pos += 1, seq_len += 1, done_at = out_pos when no row is alive any more.
+// state (int32): [0] seq_len (cache length the next model call sees, its own token included), [1] out_pos,
+//                [2] alive rows, [3] done_at (-1 until every row has finished), [4] block counter (0 between calls).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    greedy_step_kernel(const T* __restrict__ logits, int64_t ld, int64_t V, long long* __restrict__ alive,
+                       const long long* __restrict__ end_ids, int n_end, long long pad_id,
+                       long long* __restrict__ ids_out, int64_t out_stride, long long* __restrict__ cur_ids,
+                       long long* __restrict__ pos_ids, int* __restrict__ state) {
+  const int b = blockIdx.x;
+  const T* row = logits + (int64_t)b * ld;
+  float best = -INFINITY;
+  long long arg = 0x7fffffffffffffffLL;
+  for (int64_t j = threadIdx.x; j < V; j += blockDim.x) {
+    const float v = (float)row[j];
+    if (v > best || (v == best && j < arg) || (v != v && !(best != best))) { best = v; arg = j; }  // NaN wins like torch
+  }
+  auto better = [](float v, long long i, float bv, long long bi) {
+    const bool vn = v != v, bn = bv != bv;
+    if (vn != bn) return vn;
+    if (vn) return i < bi;
+    return v > bv || (v == bv && i < bi);
+  };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (better(ov, oi, best, arg)) { best = ov; arg = oi; }
+  }
+  __shared__ float sv[8];
+  __shared__ long long si[8];
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = arg; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (better(sv[w], si[w], best, arg)) { best = sv[w]; arg = si[w]; }
+    const long long was_alive = alive[b];
+    const long long next = arg * was_alive + pad_id * (1 - was_alive);
+    bool hit = false;
+    for (int e = 0; e < n_end; ++e) hit |= (next == end_ids[e]);
+    const int out_pos = state[1];
+    ids_out[(int64_t)b * out_stride + out_pos] = next;
+    cur_ids[b] = next;
+    if (pos_ids) pos_ids[b] += 1;
+    if (hit && was_alive) {
+      alive[b] = 0;
+      atomicSub(&state[2], 1);
+    }
+    __threadfence();
+    const int done = atomicAdd(&state[4], 1);
+    if (done == (int)gridDim.x - 1) {  // every row has read out_pos and updated the alive count
+      __threadfence();
+      state[4] = 0;
+      state[0] += 1;
+      state[1] = out_pos + 1;
+      if (atomicAdd(&state[2], 0) <= 0 && state[3] < 0) state[3] = out_pos + 1;
+    }
+  }
+}
+
 }  // namespace ct
 
 using namespace ct;
@@ -762,6 +828,34 @@ extern "C" int ct_scale_by_scalar(void* x, int dtype, int64_t n, const float* de
   else
     scale_by_device_scalar_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((float*)x, n,
                                                                                            device_scalar);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_greedy_step(const void* logits, int logits_dtype, int64_t ld, int64_t B, int64_t V, int64_t* alive,
+                              const int64_t* end_ids, int n_end, int64_t pad_id, int64_t* ids_out, int64_t out_stride,
+                              int64_t* cur_ids, int64_t* pos_ids, int32_t* state, void* stream) {
+  CT_REQUIRE(logits && alive && ids_out && cur_ids && state && (n_end == 0 || end_ids), CT_ERR_BAD_ARG,
+             "ct_greedy_step: null pointer");
+  CT_REQUIRE(B > 0 && V > 0 && ld >= V && n_end >= 0, CT_ERR_BAD_ARG, "ct_greedy_step: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (logits_dtype == DT_F32)
+    greedy_step_kernel<float><<<(unsigned)B, 256, 0, st>>>((const float*)logits, ld, V, (long long*)alive,
+                                                          (const long long*)end_ids, n_end, (long long)pad_id,
+                                                          (long long*)ids_out, out_stride, (long long*)cur_ids,
+                                                          (long long*)pos_ids, state);
+  else if (logits_dtype == DT_BF16)
+    greedy_step_kernel<__nv_bfloat16><<<(unsigned)B, 256, 0, st>>>((const __nv_bfloat16*)logits, ld, V, (long long*)alive,
+                                                                  (const long long*)end_ids, n_end, (long long)pad_id,
+                                                                  (long long*)ids_out, out_stride, (long long*)cur_ids,
+                                                                  (long long*)pos_ids, state);
+  else if (logits_dtype == DT_F16)
+    greedy_step_kernel<__half><<<(unsigned)B, 256, 0, st>>>((const __half*)logits, ld, V, (long long*)alive,
+                                                           (const long long*)end_ids, n_end, (long long)pad_id,
+                                                           (long long*)ids_out, out_stride, (long long*)cur_ids,
+                                                           (long long*)pos_ids, state);
+  else
+    CT_REQUIRE(false, CT_ERR_UNSUPPORTED, "ct_greedy_step: logits must be f32 / bf16 / f16");
   CT_LAUNCH_OK();
   return 0;
 }

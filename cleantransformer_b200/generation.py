@@ -8,8 +8,35 @@ only the new tokens are fed once a cache exists, finished rows emit pad_id, the 
 repeating its last column, and the loop ends when `step > max_gen_len + prompt_len` — i.e. it emits
 max_gen_len + 2 tokens, exactly like the reference. Beam search (generation_util.py:207-290) is out
 of scope for this tier.
+
+Greedy decoding (`do_sample=False`) on a CUDA model replays every q_len = 1 step from ONE captured CUDA graph
+(BASELINE.json configs[3]): `_graphed_greedy` below. The cache length, the write position and the
+alive flags live in device memory and are advanced by ct_greedy_step at the end of the step, so the graph's arguments
+never change; the host only replays and (when end ids are given) polls a done flag every few steps.
 """
+import os
+
 import torch
+
+from . import ops
+
+POLL_EVERY = 16  # graphed greedy decode: steps between two reads of the device-side "every row finished" flag
+
+
+def _on_device(t):
+    return t.is_cuda
+
+
+def _capture(step):
+    """Capture one call of `step` (it is NOT executed) and return (replay, kernel launches per replay)."""
+    graph = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    before = ops.LAUNCHES[0]
+    with torch.cuda.graph(graph):
+        step()
+    n = ops.LAUNCHES[0] - before
+    ops.LAUNCHES[0] = before
+    return graph.replay, n
 
 
 def _temperature(scores, temperature):
@@ -59,6 +86,11 @@ class GenerationMixin:
                        steamers=None):
         bsz, prompt_len = input_ids.shape
         limit = max_gen_len + prompt_len
+        if (not do_sample and steamers is None and _on_device(input_ids) and position_ids is None and segment_ids is None
+                and attention_mask is not None and getattr(self, "_ct_graph_decode", False) and self._decode_graph_ok()
+                and os.environ.get("CT_DECODE_GRAPH", "1") != "0" and max_gen_len >= 1
+                and bool((attention_mask[:, -1] != 0).all())):
+            return self._graphed_greedy(input_ids, attention_mask, end_ids_tensor, max_gen_len, pad_id)
         caches = [None] * self.config.n_layer
         alive = torch.ones(bsz, dtype=torch.long, device=input_ids.device)
         fed = 0  # number of tokens already inside the cache
@@ -102,3 +134,73 @@ class GenerationMixin:
             if alive.max() == 0 or fed > limit:
                 break
         return input_ids.view(bsz, 1, -1)
+
+    @torch.no_grad()
+    def _graphed_greedy(self, input_ids, attention_mask, end_ids_tensor, max_gen_len, pad_id):
+        """Same token ids as the loop above for do_sample=False (generation_util.py:57-119), with the q_len = 1 steps
+        replayed from a CUDA graph. The prompt's last mask column is 1 for every row (checked by the caller), so every
+        generated position is a valid key and its GPT position id is the previous one + 1.
+
+        Step k >= 1 of the reference feeds token P+k-1 and emits token P+k; it stops after the step that leaves
+        `fed > max_gen_len + P`, i.e. after max_gen_len + 2 emitted tokens, or right after the step in which the last
+        row hit an end id. Cache rows needed: P + max_gen_len + 1."""
+        dev = input_ids.device
+        bsz, P = input_ids.shape
+        n_emit = max_gen_len + 2
+        cap = P + max_gen_len + 1
+        full_mask = torch.cat([attention_mask, attention_mask[:, -1:].expand(bsz, cap - P)], dim=-1).contiguous()
+        ids_out = torch.empty(bsz, P + n_emit, dtype=torch.long, device=dev)
+        ids_out[:, :P] = input_ids
+        alive = torch.ones(bsz, dtype=torch.long, device=dev)
+        cur_ids = torch.empty(bsz, dtype=torch.long, device=dev)
+        pos_ids = None
+        if self._decode_needs_positions():  # position of the last prompt token; ct_greedy_step adds 1 per emitted token
+            pos_ids = (attention_mask.long().cumsum(-1)[:, -1] - 1).contiguous()
+        # state: cache length seen by the next step, write column, alive rows, done_at, block counter
+        state = torch.tensor([P, P, bsz, -1, 0], dtype=torch.int32, device=dev)
+        end_ids = None if end_ids_tensor is None else end_ids_tensor.to(device=dev, dtype=torch.long).contiguous()
+
+        def pick(logits):
+            ops.greedy_step(logits, alive, end_ids, pad_id, ids_out, cur_ids, pos_ids, state)
+
+        # prefill: the un-graphed full-sequence path, with the caches allocated once for the whole generation
+        old_cap = ops.KV_CACHE_MIN_CAP[0]
+        ops.KV_CACHE_MIN_CAP[0] = cap
+        try:
+            outputs, caches = self(input_ids, attention_mask=attention_mask, k_v_pasts=[None] * self.config.n_layer)
+        finally:
+            ops.KV_CACHE_MIN_CAP[0] = old_cap
+        pick(outputs[0][:, -1, :])
+        static_kv = [ops.StaticKV(k._ct_cache_base, v._ct_cache_base, state) for k, v in caches]
+        mask_obj = self._decode_static_mask(full_mask)
+
+        def step():
+            kw = dict(attention_mask=mask_obj, k_v_pasts=static_kv)
+            if pos_ids is not None:
+                kw["position_ids"] = pos_ids.view(bsz, 1)
+            out, _ = self(cur_ids.view(bsz, 1), **kw)
+            pick(out[0][:, -1, :])
+
+        def finished():
+            return end_ids is not None and int(state[3]) >= 0
+
+        n_steps = n_emit - 1  # q_len = 1 steps still to run
+        if n_steps > 0 and not finished():
+            step()  # first decode step outside the capture: lazy kernel attributes, and it is a real step
+            n_steps -= 1
+        self._ct_decode_graph_launches = 0
+        if n_steps > 0 and not finished():
+            replay, self._ct_decode_graph_launches = _capture(step)
+            done = 0
+            while done < n_steps:
+                burst = min(POLL_EVERY, n_steps - done) if end_ids is not None else n_steps - done
+                for _ in range(burst):
+                    replay()
+                done += burst
+                ops.LAUNCHES[0] += burst * self._ct_decode_graph_launches
+                if finished():
+                    break
+            del replay
+        st = state.tolist()
+        n_out = st[3] if (end_ids is not None and st[3] >= 0) else min(st[1], P + n_emit)
+        return ids_out[:, :n_out].reshape(bsz, 1, -1)

@@ -135,6 +135,15 @@ class BloomAttentionLayer(torch.nn.Module):
         bias = alibi if isinstance(alibi, AttnBias) else \
             AttnBias.from_reference_args(alibi, attention_mask, bsz, self.num_heads)
         qkv = F.linear(hidden_states, self.query_key_value.weight, self.query_key_value.bias)
+        if isinstance(k_v_past, ops.StaticKV):
+            # captured decode step (generation.py): device-side cache position / length
+            q, k, v = F.split_packed(qkv, self.num_heads, F.LAYOUT_BLOOM)
+            ops.kv_append_dev(k_v_past.k, k, k_v_past.len_dev)
+            ops.kv_append_dev(k_v_past.v, v, k_v_past.len_dev)
+            ctx, _ = ops.attn_fwd(q, k_v_past.k, k_v_past.v, self.inv_norm_factor, bias.causal, -ops.FLT_MAX,
+                                  bias.kbias2, bias.first_valid, need_lse=False, seq_len_dev=k_v_past.len_dev)
+            out = F.linear(ctx, self.dense.weight, self.dense.bias, residual=residual)
+            return out, k_v_past
         if k_v_past is None and torch.is_grad_enabled() and qkv.requires_grad:
             ctx = F.PackedAttentionFn.apply(qkv, self.num_heads, F.LAYOUT_BLOOM, self.inv_norm_factor,
                                             bias.causal, -ops.FLT_MAX, bias.kbias2, bias.first_valid)
@@ -240,7 +249,8 @@ class BloomModel(torch.nn.Module):
             k_v_pasts = [None] * self.config.n_layer
         emb = F.embedding_sum([input_ids], [self.word_embeddings.weight])
         hidden_states = self.word_embeddings_layernorm(emb)
-        bias = AttnBias.from_mask(attention_mask, self.num_heads, input_ids.shape[1])
+        bias = attention_mask if isinstance(attention_mask, AttnBias) else \
+            AttnBias.from_mask(attention_mask, self.num_heads, input_ids.shape[1])
         for i, block in enumerate(self.blocks):
             hidden_states, k_v_pasts[i] = block(hidden_states, attention_mask=None, alibi=bias,
                                                 head_mask=None, k_v_past=k_v_pasts[i])
@@ -262,6 +272,19 @@ class BloomForCausalLM(torch.nn.Module, GenerationMixin):
         # wrapper reduces this bucket only after both have been written
         self.lm_head.weight._ct_expected_writes = 2
         self.lm_head.weight._ct_sparse_second_write = True  # ... the second one being the token scatter
+
+    _ct_graph_decode = True  # generation.py may replay the q_len = 1 step from a CUDA graph
+
+    def _decode_static_mask(self, full_mask):
+        """ALiBi + padding bias over the whole cache capacity, built once per generation; q_len = 1: no causal part."""
+        b = AttnBias.from_mask(full_mask, self.bloom.num_heads, 1)
+        return b
+
+    def _decode_needs_positions(self):
+        return False
+
+    def _decode_graph_ok(self):
+        return (self.config.hidden_size // self.config.n_head) in (32, 64, 128)  # csrc/attention.cu: attn_decode_kernel<D>
 
     def forward(self, input_ids, attention_mask=None, head_mask=None, k_v_pasts=None, labels=None, **kwargs):
         hidden_states, k_v_pasts = self.bloom(input_ids, attention_mask, head_mask, k_v_pasts)

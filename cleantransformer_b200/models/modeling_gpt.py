@@ -125,6 +125,15 @@ class AttentionLayer(torch.nn.Module):
         kb = mask.kbias2 if mask is not None else None
         fv = mask.first_valid if mask is not None else None
         qkv = self.c_attn(hidden_states)
+        if isinstance(k_v_past, ops.StaticKV):
+            # captured decode step (generation.py): append at the device-side position, attend over the device-side length
+            q, k, v = F.split_packed(qkv, self.n_head, F.LAYOUT_GPT)
+            ops.kv_append_dev(k_v_past.k, k, k_v_past.len_dev)
+            ops.kv_append_dev(k_v_past.v, v, k_v_past.len_dev)
+            ctx, _ = ops.attn_fwd(q, k_v_past.k, k_v_past.v, sm_scale, True, -1e4, kb, fv, need_lse=False,
+                                  seq_len_dev=k_v_past.len_dev)
+            out = self.c_proj(ctx, residual=residual, out_dtype=None if residual is not None else torch.float32)
+            return out, k_v_past
         if k_v_past is None and torch.is_grad_enabled() and qkv.requires_grad:
             ctx = F.PackedAttentionFn.apply(qkv, self.n_head, F.LAYOUT_GPT, sm_scale, True, -1e4, kb, fv)
             _, k, v = F.split_packed(qkv.detach(), self.n_head, F.LAYOUT_GPT)
@@ -210,7 +219,9 @@ class GPTModel(torch.nn.Module):
             position_ids.masked_fill_(attention_mask == 0, 1)
             position_ids = position_ids[:, -q_len:]
         mask = None
-        if attention_mask is not None:
+        if isinstance(attention_mask, GptMask):
+            mask = attention_mask  # prepared once by the caller (captured decode step: position_ids are given too)
+        elif attention_mask is not None:
             kb, fv = ops.attn_mask_prep(attention_mask, self.config.n_head, ops.MASK_GPT)
             mask = GptMask(kb, fv)
         if k_v_pasts is None:
@@ -242,6 +253,19 @@ class GPTLMHeadModel(torch.nn.Module, GenerationMixin):
         self.lm_head.weight = self.gpt.tokens_embed.weight
         self.lm_head.weight._ct_expected_writes = 2  # lm_head wgrad + embedding scatter (see ddp.py)
         self.lm_head.weight._ct_sparse_second_write = True  # ... the second one being the token scatter
+
+    _ct_graph_decode = True  # generation.py may replay the q_len = 1 step from a CUDA graph
+
+    def _decode_static_mask(self, full_mask):
+        """Per-key bias over the whole cache capacity (generated positions are valid keys), built once per generation."""
+        kb, fv = ops.attn_mask_prep(full_mask, self.config.n_head, ops.MASK_GPT)
+        return GptMask(kb, fv)
+
+    def _decode_needs_positions(self):
+        return True
+
+    def _decode_graph_ok(self):
+        return (self.config.n_embd // self.config.n_head) in (32, 64, 128)  # csrc/attention.cu: attn_decode_kernel<D>
 
     def forward(self, input_ids, attention_mask=None, segment_ids=None, position_ids=None, k_v_pasts=None):
         hidden_states, k_v_pasts = self.gpt(input_ids, attention_mask, position_ids, segment_ids, k_v_pasts)

@@ -28,7 +28,7 @@ _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
 # (bench.py's roofline pass). Counts are the number of kernels each C-ABI call enqueues.
 LAUNCHES = [0]
 GEMM_PROFILE = None  # when a list: (M, N, K, start_event, end_event) appended per ct_gemm call
-_KERNELS_PER_CALL = {"ct_kv_append": 1, "ct_attn_decode": 1,
+_KERNELS_PER_CALL = {"ct_kv_append": 1, "ct_attn_decode": 1, "ct_kv_append_dev": 1, "ct_greedy_step": 1,
                      "ct_layernorm_fwd": 1, "ct_layernorm_bwd": 2, "ct_layernorm_bwd_ex": 2, "ct_adamw_step": 1, "ct_adamw_multi": 1,
                      "ct_sgd_step": 1, "ct_cast": 1, "ct_colsum": 1, "ct_act_fwd": 1, "ct_act_bwd": 1,
                      "ct_gemm": 1, "ct_attn_fwd": 1, "ct_attn_bwd": 3, "ct_attn_mask_prep": 1,
@@ -340,7 +340,7 @@ def _bhsd_strides(t):
     return t.stride(0), t.stride(1), t.stride(2)
 
 
-def _fill_attn(a, q, k, v, o, lse2, scale, causal, causal_fill, kbias2, first_valid, impl):
+def _fill_attn(a, q, k, v, o, lse2, scale, causal, causal_fill, kbias2, first_valid, impl, seq_len_dev=None):
     B, H, Sq, D = q.shape
     Sk = k.shape[2]
     a.B, a.H, a.Sq, a.Sk, a.D = B, H, Sq, Sk, D
@@ -360,18 +360,21 @@ def _fill_attn(a, q, k, v, o, lse2, scale, causal, causal_fill, kbias2, first_va
         a.kb_sh = kbias2.stride(1) if kbias2.shape[1] > 1 else 0
     a.first_valid = ptr(first_valid)
     a.impl = impl
+    a.seq_len_dev = ptr(seq_len_dev)
 
 
 def attn_fwd(q, k, v, scale, causal=False, causal_fill=-FLT_MAX, kbias2=None, first_valid=None,
-             need_lse=True, impl=0):
-    """q [B,H,Sq,D], k/v [B,H,Sk,D] as strided VIEWS (D contiguous). Returns (o [B,Sq,H*D], lse2)."""
+             need_lse=True, impl=0, seq_len_dev=None):
+    """q [B,H,Sq,D], k/v [B,H,Sk,D] as strided VIEWS (D contiguous). Returns (o [B,Sq,H*D], lse2).
+    seq_len_dev (int32 device scalar, q_len = 1 only): the number of valid cached keys is read on the device and Sk is
+    only the capacity — what a captured decode step needs."""
     _req_cuda(q, k, v)
     B, H, Sq, D = q.shape
     o = torch.empty((B, Sq, H * D), dtype=q.dtype, device=q.device)
     o4 = o.view(B, Sq, H, D).permute(0, 2, 1, 3)
     lse2 = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device) if need_lse else None
     a = AttnArgs()
-    _fill_attn(a, q, k, v, o4, lse2, scale, causal, causal_fill, kbias2, first_valid, impl)
+    _fill_attn(a, q, k, v, o4, lse2, scale, causal, causal_fill, kbias2, first_valid, impl, seq_len_dev)
     _ck(_lib.load().ct_attn_fwd(ctypes.byref(a), stream()), "ct_attn_fwd")
     return o, lse2
 
@@ -461,6 +464,37 @@ def scale_by_scalar(x, scalar_f32):
 # KV cache for generation
 # ------------------------------------------------------------------------------------------------
 KV_CACHE_CHUNK = 256  # capacity grows in steps of this many positions
+KV_CACHE_MIN_CAP = [0]  # generation.py raises it to prompt + max_gen_len so that one allocation serves a generation
+
+
+class StaticKV:
+    """K / V cache of one layer inside a CAPTURED decode step: the preallocated [B,H,T_cap,D] buffers plus a device
+    scalar with the cache length (the new token included), advanced by ct_greedy_step at the end of every step."""
+
+    def __init__(self, k_base, v_base, len_dev):
+        self.k, self.v, self.len_dev = k_base, v_base, len_dev
+
+
+def kv_append_dev(base, new, len_dev):
+    """base[b,h,*len_dev - s : *len_dev,:] = new[b,h,:s,:] — the destination is read on the device."""
+    _req_cuda(base, new, len_dev)
+    B, H, s, D = new.shape
+    assert new.stride(3) == 1 and base.stride(3) == 1 and len_dev.dtype == torch.int32
+    _ck(_lib.load().ct_kv_append_dev(ptr(new), new.stride(0), new.stride(1), new.stride(2), ptr(base), base.stride(0),
+                                     base.stride(1), base.stride(2), B, H, s, D, ptr(len_dev), base.shape[2], stream()),
+        "ct_kv_append_dev")
+
+
+def greedy_step(logits2d, alive, end_ids, pad_id, ids_out, cur_ids, pos_ids, state):
+    """generation_util.py:86-101 on the device (include/ct_b200.h: ct_greedy_step). logits2d [B,V] f32/bf16/f16;
+    alive, cur_ids, pos_ids (nullable) int64 [B]; end_ids int64 [n] or None; ids_out int64 [B,T]; state int32 [5]."""
+    _req_cuda(logits2d, alive, ids_out, cur_ids, state)
+    B, V = logits2d.shape
+    assert logits2d.stride(1) == 1 and ids_out.stride(1) == 1 and state.dtype == torch.int32 and state.numel() >= 5
+    n_end = 0 if end_ids is None else end_ids.numel()
+    _ck(_lib.load().ct_greedy_step(ptr(logits2d), dt(logits2d), logits2d.stride(0), B, V, ptr(alive), ptr(end_ids), n_end,
+                                   int(pad_id), ptr(ids_out), ids_out.stride(0), ptr(cur_ids), ptr(pos_ids), ptr(state),
+                                   stream()), "ct_greedy_step")
 
 
 def kv_cache_append(past, new):
@@ -472,7 +506,7 @@ def kv_cache_append(past, new):
     t = 0 if past is None else past.shape[2]
     base = getattr(past, "_ct_cache_base", None) if past is not None else None
     if base is None or base.shape[2] < t + s or base.dtype != new.dtype or past.data_ptr() != base.data_ptr():
-        cap = ((t + s + KV_CACHE_CHUNK - 1) // KV_CACHE_CHUNK + 1) * KV_CACHE_CHUNK
+        cap = max(((t + s + KV_CACHE_CHUNK - 1) // KV_CACHE_CHUNK + 1) * KV_CACHE_CHUNK, KV_CACHE_MIN_CAP[0])
         nbase = torch.empty((B, H, cap, D), dtype=new.dtype, device=new.device)
         if t:
             _ck(_lib.load().ct_kv_append(ptr(past), past.stride(0), past.stride(1), past.stride(2), ptr(nbase),

@@ -229,6 +229,8 @@ typedef struct {
   int64_t kb_sb, kb_sh;
   const int32_t* first_valid; /* [B] nullable: first key that is not hard-masked (left padding) */
   int32_t impl;               /* 0 auto, 1 force tcgen05 (D == 64), 2 force SIMT */
+  const int32_t* seq_len_dev; /* nullable; q_len = 1 decode only: the number of cached keys is read from device memory
+                                 (Sk is then just the capacity), so a captured decode step serves every position */
 } ct_attn_args;
 int ct_attn_fwd(const ct_attn_args* args, void* stream);
 
@@ -361,6 +363,19 @@ int ct_kv_append(const void* src, int64_t s_sb, int64_t s_sh, int64_t s_ss, void
                  int64_t c_sh, int64_t c_ss, int B, int H, int S_new, int D, int pos, int t_max,
                  void* stream);
 int ct_attn_decode(const ct_attn_args* args, void* stream);
+/* ct_kv_append with the destination read from device memory: rows [*len_dev - S_new, *len_dev) (a captured decode
+ * step: *len_dev = cache length after this append). Nothing is written when the rows do not fit t_max. */
+int ct_kv_append_dev(const void* src, int64_t s_sb, int64_t s_sh, int64_t s_ss, void* cache, int64_t c_sb,
+                     int64_t c_sh, int64_t c_ss, int B, int H, int S_new, int D, const int32_t* len_dev, int t_max,
+                     void* stream);
+/* One step of GenerationMixin._greedy_search after the model call (generation_util.py:86-101, do_sample = False) on
+ * the device: next = argmax(logits[b,:]) (first maximum); next = next*alive + pad*(1-alive); alive &= next not in
+ * end_ids; ids_out[b, out_pos] = next; cur_ids[b] = next; pos_ids[b] += 1 (nullable); then once: seq_len += 1,
+ * out_pos += 1, done_at = out_pos when no row is alive. state = int32[5] on the device: {seq_len, out_pos, alive rows,
+ * done_at (-1), 0}. logits [B, V] with row stride ld, dtype CT_F32 / CT_BF16 / CT_F16. */
+int ct_greedy_step(const void* logits, int logits_dtype, int64_t ld, int64_t B, int64_t V, int64_t* alive,
+                   const int64_t* end_ids, int n_end, int64_t pad_id, int64_t* ids_out, int64_t out_stride,
+                   int64_t* cur_ids, int64_t* pos_ids, int32_t* state, void* stream);
 
 #ifdef __cplusplus
 }

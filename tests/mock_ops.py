@@ -169,8 +169,14 @@ def _attn_core(q, k, v, scale, causal, causal_fill, kbias2):
     return o, (mx + torch.log2(l)).squeeze(-1)
 
 
-def attn_fwd(q, k, v, scale, causal=False, causal_fill=-FLT_MAX, kbias2=None, first_valid=None, need_lse=True, impl=0):
+def attn_fwd(q, k, v, scale, causal=False, causal_fill=-FLT_MAX, kbias2=None, first_valid=None, need_lse=True, impl=0,
+             seq_len_dev=None):
     B, H, Sq, D = q.shape
+    if seq_len_dev is not None:  # captured decode step: the key count is a device scalar, k / v are the whole capacity
+        n = int(seq_len_dev[0])
+        assert Sq == 1 and n <= k.shape[2]
+        k, v = k[:, :, :n], v[:, :, :n]
+        kbias2 = kbias2[:, :, :n] if kbias2 is not None else None
     o, lse2 = _attn_core(q, k, v, scale, causal, causal_fill, kbias2)
     return o.transpose(1, 2).reshape(B, Sq, H * D).to(q.dtype), (lse2 if need_lse else None)
 
@@ -277,8 +283,40 @@ def sgd_step(p, g, buf, lr, momentum, dampening, weight_decay, first_step):
 
 
 def kv_cache_append(past, new):
-    """ops.kv_cache_append grows a preallocated cache in place; the observable result is the concatenation."""
-    return new if past is None else torch.cat([past, new], 2)
+    """ops.kv_cache_append grows a preallocated cache in place; the observable result is the concatenation (a view of a
+    buffer with at least ops.KV_CACHE_MIN_CAP rows, reachable as `._ct_cache_base`)."""
+    from cleantransformer_b200 import ops
+    cat = new if past is None else torch.cat([past, new], 2)
+    B, H, t, D = cat.shape
+    base = torch.zeros(B, H, max(t, ops.KV_CACHE_MIN_CAP[0]), D, dtype=cat.dtype)
+    base[:, :, :t] = cat
+    view = base[:, :, :t]
+    view._ct_cache_base = base
+    return view
+
+
+def kv_append_dev(base, new, len_dev):
+    n, s = int(len_dev[0]), new.shape[2]
+    if n - s >= 0 and n <= base.shape[2]:
+        base[:, :, n - s:n] = new
+
+
+def greedy_step(logits2d, alive, end_ids, pad_id, ids_out, cur_ids, pos_ids, state):
+    """include/ct_b200.h: ct_greedy_step (generation_util.py:86-101 for do_sample=False)."""
+    nxt = torch.argmax(logits2d.float(), dim=-1) * alive + pad_id * (1 - alive)
+    if end_ids is not None and end_ids.numel():
+        hit = (nxt[None, :] == end_ids[:, None]).any(dim=0)
+        alive.mul_((~hit).long())
+    col = int(state[1])
+    ids_out[:, col] = nxt
+    cur_ids.copy_(nxt)
+    if pos_ids is not None:
+        pos_ids.add_(1)
+    state[0] += 1
+    state[1] += 1
+    state[2] = int(alive.sum())
+    if int(state[2]) == 0 and int(state[3]) < 0:
+        state[3] = col + 1
 
 
 def lm_head_stats_ok(M, V, dtype=None):
@@ -298,9 +336,11 @@ def patched(compute_dtype=torch.float32):
     from cleantransformer_b200 import functional, ops
     names = ["layernorm_fwd", "layernorm_bwd", "cast", "colsum", "act_fwd", "act_bwd", "gemm", "attn_mask_prep",
              "attn_fwd", "attn_bwd", "embedding_fwd", "embedding_bwd", "cross_entropy_fwd", "cross_entropy_fwd_stats",
-             "scale_by_scalar", "lm_head_stats_ok", "lm_head_logits_with_stats", "adamw_step", "adamw_multi", "sgd_step", "kv_cache_append"]
+             "scale_by_scalar", "lm_head_stats_ok", "lm_head_logits_with_stats", "adamw_step", "adamw_multi", "sgd_step", "kv_cache_append",
+             "kv_append_dev", "greedy_step"]
     saved = {n: getattr(ops, n) for n in names}
-    from cleantransformer_b200 import arena, optimizer
+    from cleantransformer_b200 import arena, generation, optimizer
+    saved_gen = generation._on_device, generation._capture
     saved_req, saved_cd, saved_oreq = ops._req_cuda, functional.COMPUTE_DTYPE, optimizer._require_cuda
     saved_sh = arena.SHADOW_ON_ANY_DEVICE
     try:
@@ -309,6 +349,8 @@ def patched(compute_dtype=torch.float32):
             setattr(ops, n, globals()[n])
         ops._req_cuda = lambda *ts: None
         optimizer._require_cuda = lambda ps: None
+        generation._on_device = lambda t: True          # the captured-decode host logic runs with ...
+        generation._capture = lambda step: (step, 1)    # ... the "replay" simply calling the step
         functional.COMPUTE_DTYPE = compute_dtype
         yield
     finally:
@@ -316,5 +358,6 @@ def patched(compute_dtype=torch.float32):
             setattr(ops, n, f)
         ops._req_cuda = saved_req
         optimizer._require_cuda = saved_oreq
+        generation._on_device, generation._capture = saved_gen
         functional.COMPUTE_DTYPE = saved_cd
         arena.SHADOW_ON_ANY_DEVICE = saved_sh

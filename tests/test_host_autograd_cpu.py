@@ -582,3 +582,69 @@ def test_gpt_segment_ids_ddp_world2_gloo_counts_three_writes_of_the_tied_table()
     for n in r0:
         assert torch.allclose(r0[n], r1[n]), n
         assert rel_err(r0[n], (l0[n] + l1[n]) / 2) < 1e-5, n
+
+
+@pytest.mark.parametrize("family", ["gpt2", "bloom"])
+def test_captured_decode_host_logic_matches_the_loop_and_the_oracle(family, monkeypatch):
+    """generation._graphed_greedy with the device pieces mocked: static KV buffers sized once, the
+    full-capacity mask, device-side cache length / write column / alive flags / position ids, polling and trimming.
+    Its ids must equal the un-captured loop's and the oracle's restatement of generation_util.py:57-119, with and
+    without end ids (rows finishing at different steps; every row finishing at once)."""
+    from cleantransformer_b200 import generation
+    from oracle import ct_oracle as O
+    torch.manual_seed(77)
+    V, L, NH = 97, 2, 2
+    B, P = 4, 7
+    ids = torch.randint(3, V, (B, P))
+    mask = torch.ones(B, P, dtype=torch.long)
+    for b, n in enumerate((0, 2, 4, 1)):  # LEFT padding (examples/inference_gpt2.py:55-59)
+        mask[b, :n] = 0
+        ids[b, :n] = 0
+    with mock_ops.patched():
+        if family == "gpt2":
+            from cleantransformer_b200.models import modeling_gpt as mg
+            m = mg.GPTLMHeadModel(mg.GPTConfig(vocab_size=V, n_embd=64, n_positions=64, n_layer=L, n_head=NH, n_ctx=64,
+                                               afn="gelu_new"), version="gpt2").eval()
+            sd = {k: v.detach() for k, v in m.state_dict().items()}
+
+            def step(x, am, caches):
+                return O.gpt_lm_head_model(x, am, sd, L, NH, 64, 1e-5, version="gpt2", k_v_pasts=caches)
+        else:
+            from cleantransformer_b200.models import modeling_bloom as mb
+            m = mb.BloomForCausalLM(mb.BloomConfig(vocab_size=V, hidden_size=64, n_layer=L, num_attention_heads=NH)).eval()
+            m._tie_weight()
+            with torch.no_grad():
+                for p in m.parameters():
+                    if p.dim() >= 2:
+                        p.normal_(0, 0.2)
+            sd = {k: v.detach() for k, v in m.state_dict().items() if k != "lm_head.weight"}
+
+            def step(x, am, caches):
+                return O.bloom_causal_lm(x, am, sd, L, NH, 1e-5, k_v_pasts=caches)
+
+        def gen(graph, **cfg):
+            monkeypatch.setenv("CT_DECODE_GRAPH", "1" if graph else "0")
+            m._ct_decode_graph_launches = -1
+            base = {"beam_size": 1, "do_sample": False, "max_gen_len": 9, "end_ids": None, "pad_id": 1}
+            base.update(cfg)
+            out = m.generate(ids, attention_mask=mask, generation_configs=base)
+            assert (m._ct_decode_graph_launches >= 0) == graph
+            return out
+
+        loop, cap = gen(False), gen(True)
+        assert cap.shape == (B, 1, P + 11) and torch.equal(loop, cap)
+        with torch.no_grad():
+            ref = O.greedy_generate(step, ids, mask, L, max_gen_len=9, pad_id=1)
+        assert torch.equal(cap.view(ref.shape), ref)
+        new = loop[:, 0, P:]
+        for ends in ([int(new[0, 2]), int(new[2, 6])], sorted(set(new[:, 1].tolist())), [int(new[1, 0])]):
+            a, b = gen(False, end_ids=ends), gen(True, end_ids=ends)
+            assert a.shape == b.shape and torch.equal(a, b), ends
+            with torch.no_grad():
+                r = O.greedy_generate(step, ids, mask, L, max_gen_len=9, pad_id=1, end_ids=ends)
+            assert torch.equal(b.view(r.shape), r), ends
+        assert torch.equal(gen(False, max_gen_len=1), gen(True, max_gen_len=1))
+        # POLL_EVERY smaller than the generation: the early stop is noticed at a poll, the result is trimmed at done_at
+        monkeypatch.setattr(generation, "POLL_EVERY", 2)
+        ends = sorted(set(new[:, 4].tolist()))
+        assert torch.equal(gen(False, end_ids=ends), gen(True, end_ids=ends))
