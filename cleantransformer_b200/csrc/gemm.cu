@@ -1099,6 +1099,110 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// =================================================================================================
+// Skinny GEMM (M <= 32 rows): the q_len = 1 decode step of GenerationMixin._greedy_search (generation_util.py:57-119)
+// multiplies 32 tokens by every weight matrix once per emitted token, so the weights are streamed from HBM and nothing
+// else matters. A 128-row tcgen05 tile wastes the launch on a handful of CTAs (N / 256 of them); here a
+// CTA owns 8*G output features, its 8 warps split K in interleaved 32-element chunks, every lane reads whole 16-byte
+// pieces of a weight row (and of the token rows), and the products run on mma.sync m16n8k16 with the TOKENS as the
+// 16-row operand. A lane's 16 bytes are 8 consecutive k; the fragment layout wants (2q, 2q+1) and (2q+8, 2q+9) per lane,
+// which is only a permutation of k applied to both operands alike, so no shuffle or shared-memory transpose is needed.
+// The 8 partial sums are added in warp order (deterministic), then the common scalar epilogue runs.
+// A [M,K] and B [N,K] both K-major, K % 32 == 0, 16-byte aligned rows.
+// =================================================================================================
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1, bool bf16) {
+  if (bf16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+constexpr int SK_WARPS = 8;
+
+template <int G>
+__global__ void __launch_bounds__(SK_WARPS * 32)
+    gemm_skinny_kernel(const uint16_t* __restrict__ A, int64_t lda, const uint16_t* __restrict__ B, int64_t ldb,
+                       int bf16, int K, const EpiParams e) {
+  constexpr int FT = 8 * G;  // output features per CTA
+  __shared__ float red[SK_WARPS][G * 8][32];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int n0 = blockIdx.x * FT;
+  const uint16_t* wrow[G];
+#pragma unroll
+  for (int j = 0; j < G; ++j) wrow[j] = B + (int64_t)min(n0 + 8 * j + g, e.N - 1) * ldb + q * 8;
+  const uint16_t* xrow[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xrow[i] = A + (int64_t)min(g + 8 * i, e.M - 1) * lda + q * 8;
+  float acc[G][2][4];
+#pragma unroll
+  for (int j = 0; j < G; ++j)
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[j][t][c] = 0.f;
+  const int chunks = K >> 5;
+  constexpr int U = G >= 4 ? 2 : 4;  // chunks in flight per warp: (G + 4) * U 16-byte loads per lane
+  for (int c0 = wib; c0 < chunks; c0 += SK_WARPS * U) {
+    uint4 w[U][G], x[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c = c0 + u * SK_WARPS;
+      if (c < chunks) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) w[u][j] = ld_stream16(wrow[j] + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[u][i] = __ldg(reinterpret_cast<const uint4*>(xrow[i] + c * 32));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (c0 + u * SK_WARPS < chunks) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mma16816(acc[j][t], x[u][2 * t].x, x[u][2 * t + 1].x, x[u][2 * t].y, x[u][2 * t + 1].y, w[u][j].x, w[u][j].y,
+                     bf16 != 0);
+            mma16816(acc[j][t], x[u][2 * t].z, x[u][2 * t + 1].z, x[u][2 * t].w, x[u][2 * t + 1].w, w[u][j].z, w[u][j].w,
+                     bf16 != 0);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < G; ++j)
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) red[wib][(j * 2 + t) * 4 + c][lane] = acc[j][t][c];
+  __syncthreads();
+  // element (token, feature) of the CTA tile lives in fragment slot (j, t, c) of lane (gg, qq)
+  for (int idx = threadIdx.x; idx < 32 * FT; idx += SK_WARPS * 32) {
+    const int tok = idx / FT, f = idx % FT;
+    if (tok >= e.M || n0 + f >= e.N) continue;
+    const int j = f >> 3, qq = (f & 7) >> 1, t = tok >> 4, gg = tok & 7;
+    const int c = (((tok >> 3) & 1) << 1) | (f & 1);
+    const int slot = (j * 2 + t) * 4 + c, ln = gg * 4 + qq;
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < SK_WARPS; ++wv) v += red[wv][slot][ln];
+    epi_scalar(e, tok, n0 + f, v, true);
+  }
+}
+
 static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 template <int BN>
@@ -1268,6 +1372,25 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
     use_tc = tma_ok && ((int64_t)a.M * a.N * a.K >= (1 << 18));
   }
 
+  // M <= 32 (one decode step): weight-streaming kernel on mma.sync; impl 4 forces it, impl 0 picks it when the layout fits
+  const bool skinny_ok = a.M <= 32 && !a.a_mn_major && !a.b_mn_major && tma_ok && (a.K % 32 == 0) && !a.row_stats;
+  CT_REQUIRE(a.impl != 4 || skinny_ok, CT_ERR_UNSUPPORTED,
+             "ct_gemm: the skinny kernel needs M <= 32, K-major A and B, K %% 32 == 0, 16-byte aligned rows");
+  if (skinny_ok && (a.impl == 4 || (a.impl == 0 && (int64_t)a.N * a.K >= (1 << 16)))) {
+    const uint16_t* A16 = (const uint16_t*)a.A;
+    const uint16_t* B16 = (const uint16_t*)a.B;
+    const int bf = a.ab_dtype == DT_BF16;
+    const int sms2 = sm_count();
+    // features per CTA: wide tiles amortise the token rows (read once per CTA) when there are CTAs to spare
+    if ((a.N + 31) / 32 >= 2 * sms2)
+      gemm_skinny_kernel<4><<<(unsigned)((a.N + 31) / 32), SK_WARPS * 32, 0, st>>>(A16, a.lda, B16, a.ldb, bf, a.K, e);
+    else if ((a.N + 15) / 16 >= sms2)
+      gemm_skinny_kernel<2><<<(unsigned)((a.N + 15) / 16), SK_WARPS * 32, 0, st>>>(A16, a.lda, B16, a.ldb, bf, a.K, e);
+    else
+      gemm_skinny_kernel<1><<<(unsigned)((a.N + 7) / 8), SK_WARPS * 32, 0, st>>>(A16, a.lda, B16, a.ldb, bf, a.K, e);
+    CT_LAUNCH_OK();
+    return 0;
+  }
   CT_REQUIRE(use_tc || !a.row_stats, CT_ERR_UNSUPPORTED, "ct_gemm: row_stats needs the tcgen05 2-CTA kernel");
   if (!use_tc) {
     if (a.K == 0) {

@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(256)
 // state (int32): [0] seq_len (cache length the next model call sees, its own token included), [1] out_pos,
 //                [2] alive rows, [3] done_at (-1 until every row has finished), [4] block counter (0 between calls).
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
     greedy_step_kernel(const T* __restrict__ logits, int64_t ld, int64_t V, long long* __restrict__ alive,
                        const long long* __restrict__ end_ids, int n_end, long long pad_id,
                        long long* __restrict__ ids_out, int64_t out_stride, long long* __restrict__ cur_ids,
@@ -666,8 +666,8 @@ __global__ void __launch_bounds__(256)
     const long long oi = __shfl_xor_sync(0xffffffffu, arg, o);
     if (better(ov, oi, best, arg)) { best = ov; arg = oi; }
   }
-  __shared__ float sv[8];
-  __shared__ long long si[8];
+  __shared__ float sv[32];
+  __shared__ long long si[32];
   if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = arg; }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -840,17 +840,17 @@ extern "C" int ct_greedy_step(const void* logits, int logits_dtype, int64_t ld, 
   CT_REQUIRE(B > 0 && V > 0 && ld >= V && n_end >= 0, CT_ERR_BAD_ARG, "ct_greedy_step: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   if (logits_dtype == DT_F32)
-    greedy_step_kernel<float><<<(unsigned)B, 256, 0, st>>>((const float*)logits, ld, V, (long long*)alive,
+    greedy_step_kernel<float><<<(unsigned)B, 1024, 0, st>>>((const float*)logits, ld, V, (long long*)alive,
                                                           (const long long*)end_ids, n_end, (long long)pad_id,
                                                           (long long*)ids_out, out_stride, (long long*)cur_ids,
                                                           (long long*)pos_ids, state);
   else if (logits_dtype == DT_BF16)
-    greedy_step_kernel<__nv_bfloat16><<<(unsigned)B, 256, 0, st>>>((const __nv_bfloat16*)logits, ld, V, (long long*)alive,
+    greedy_step_kernel<__nv_bfloat16><<<(unsigned)B, 1024, 0, st>>>((const __nv_bfloat16*)logits, ld, V, (long long*)alive,
                                                                   (const long long*)end_ids, n_end, (long long)pad_id,
                                                                   (long long*)ids_out, out_stride, (long long*)cur_ids,
                                                                   (long long*)pos_ids, state);
   else if (logits_dtype == DT_F16)
-    greedy_step_kernel<__half><<<(unsigned)B, 256, 0, st>>>((const __half*)logits, ld, V, (long long*)alive,
+    greedy_step_kernel<__half><<<(unsigned)B, 1024, 0, st>>>((const __half*)logits, ld, V, (long long*)alive,
                                                            (const long long*)end_ids, n_end, (long long)pad_id,
                                                            (long long*)ids_out, out_stride, (long long*)cur_ids,
                                                            (long long*)pos_ids, state);

@@ -51,6 +51,23 @@ def shadow(param, dtype=None):
     return sh
 
 
+SKINNY_ROWS = 32  # csrc/gemm.cu: gemm_skinny_kernel serves M <= 32 with K-major weights
+
+
+def shadow_kmajor(param, dtype=None):
+    """[out, in] low-precision copy of a Conv1D weight stored [in, out] (modeling_gpt.py:32-46), cached per parameter
+    version like `shadow`: the q_len = 1 decode step streams every weight once per token and the skinny kernel wants
+    each output feature's row contiguous. Costs one extra bf16 copy of the Conv1D weights, made at the first decode."""
+    dtype = dtype or compute_dtype()
+    sh = getattr(param, "_ct_shadow_t", None)
+    if sh is not None and sh.dtype == dtype and getattr(param, "_ct_shadow_t_ver", -1) == param._version \
+            and getattr(param, "_ct_shadow_t_ptr", 0) == param.data_ptr() and sh.device == param.device:
+        return sh
+    sh = shadow(param, dtype).t().contiguous()
+    param._ct_shadow_t, param._ct_shadow_t_ver, param._ct_shadow_t_ptr = sh, param._version, param.data_ptr()
+    return sh
+
+
 def invalidate_shadows(module_or_params):
     """Forget the cached low-precision copies. The cache is keyed on (`param._version`, `param.data_ptr()`): in-place
     updates through the parameter itself and `p.data = ...` re-pointing are noticed, but a write through `p.data`
@@ -173,18 +190,23 @@ class LinearFn(torch.autograd.Function):
     """y = act(x @ W^T + b) (+ residual). W: nn.Linear [out,in] or Conv1D [in,out] (w_in_out)."""
 
     @staticmethod
-    def forward(ctx, x, wb, act, residual, out_dtype, w_in_out, anchor):
+    def forward(ctx, x, wb, act, residual, out_dtype, w_in_out, anchor, infer=False):
+        """infer: linear() saw grad mode off (in here it always is): nothing is kept for a backward."""
         weight, bias = wb
         cd = compute_dtype()
         x2 = _low(_as2d(x.detach()), cd)
-        w16 = shadow(weight, cd)
         N = weight.shape[1] if w_in_out else weight.shape[0]
-        need = x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad) or \
-            (residual is not None and residual.requires_grad)
+        need = not infer and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad) or
+                              (residual is not None and residual.requires_grad))
+        if infer and w_in_out and x2.shape[0] <= SKINNY_ROWS and weight.shape[0] % 32 == 0:
+            # q_len = 1 decode step: stream a K-major copy of the Conv1D weight (feature rows contiguous)
+            w16, w_in_out_k = shadow_kmajor(weight, cd), False
+        else:
+            w16, w_in_out_k = shadow(weight, cd), w_in_out
         res2 = _as2d(residual.detach()).contiguous() if residual is not None else None
         note_use(weight, bias)
         y, pre = ops.linear_fwd(x2, w16, bias.detach() if bias is not None else None, act, res2, out_dtype,
-                                save_preact=(act != ops.ACT_NONE and need), w_in_out=w_in_out)
+                                save_preact=(act != ops.ACT_NONE and need), w_in_out=w_in_out_k)
         ctx.save_for_backward(x2, pre)
         ctx.weight, ctx.bias, ctx.act, ctx.w_in_out = weight, bias, act, w_in_out
         ctx.x_shape, ctx.x_dtype, ctx.x_req = x.shape, x.dtype, x.requires_grad
@@ -225,13 +247,14 @@ class LinearFn(torch.autograd.Function):
         if ctx.x_req:
             dx = ops.linear_dgrad(d2, shadow(weight, cd), out_dtype=ctx.x_dtype, w_in_out=ctx.w_in_out)
             dx = dx.view(ctx.x_shape)
-        return dx, None, None, dres, None, None, None
+        return dx, None, None, dres, None, None, None, None
 
 
 def linear(x, weight, bias=None, act=ops.ACT_NONE, residual=None, out_dtype=None, w_in_out=False):
     if out_dtype is None:
         out_dtype = residual.dtype if residual is not None else compute_dtype()
-    return LinearFn.apply(x, (weight, bias), act, residual, out_dtype, w_in_out, _anchor((weight, bias), x, residual))
+    return LinearFn.apply(x, (weight, bias), act, residual, out_dtype, w_in_out, _anchor((weight, bias), x, residual),
+                          not torch.is_grad_enabled())
 
 
 # ------------------------------------------------------------------------------------------------

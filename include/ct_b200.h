@@ -169,7 +169,9 @@ typedef struct {
   int32_t res_dtype;
   int64_t ldr;
   int32_t impl; /* 0 auto, 1 force 1-CTA tcgen05, 2 force the SIMT kernel (small/unaligned shapes),
-                   3 force the 2-CTA (cta_group::2, 256x256 tile) tcgen05 kernel */
+                   3 force the 2-CTA (cta_group::2, 256x256 tile) tcgen05 kernel,
+                   4 force the skinny weight-streaming kernel (M <= 32, K-major A and B, K % 32 == 0: the q_len = 1
+                   decode step, generation_util.py:57-119); auto picks it whenever that layout holds */
   float* row_stats; /* nullable. LM head (modeling_bloom.py:220-230): softmax statistics of every stored bf16 row,
                        [2*ceil(N/256)][M] float2 = (max * log2e, sum of 2^(v*log2e - max*log2e)) per (slot, row), a
                        slot being the four 32-column chunks of one parity of a 256-column tile; a slot without any

@@ -196,3 +196,66 @@ def test_right_padded_prompt_falls_back_to_the_loop():
     model._ct_decode_graph_launches = -1
     out = _gen(model, ids, mask, graph=True, max_gen_len=4)
     assert out.shape == (3, 1, 12 + 6) and model._ct_decode_graph_launches == -1
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 1024, 1024), (32, 3072, 1024), (32, 1024, 4096), (32, 50257, 1024),
+                                   (1, 4096, 1024), (7, 40, 96), (19, 1000, 32), (32, 250880, 64)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_skinny_gemm_vs_fp32_and_vs_the_tcgen05_kernel(M, N, K, dtype):
+    """csrc/gemm.cu: gemm_skinny_kernel (the decode step's weight-streaming GEMM, impl 4; auto for M <= 32) against an
+    fp32 product of the same rounded operands, with the full epilogue (bias, activation, residual, both output dtypes),
+    and against the 128-row tcgen05 kernel (impl 1) it replaces."""
+    from cleantransformer_b200 import ops
+    torch.manual_seed(M * 7 + N + K)
+    x = (torch.randn(M, K, device=DEV) * 0.5).to(dtype)
+    w = (torch.randn(N, K, device=DEV) * 0.05).to(dtype)
+    bias = torch.randn(N, device=DEV) * 0.1
+    res = torch.randn(M, N, device=DEV)
+    ref_lin = x.float() @ w.float().t()
+    # plain f32 output
+    y = ops.gemm(x, w, M, N, K, out_dtype=torch.float32, impl=4)
+    assert (y - ref_lin).abs().max() <= 2e-5 * K ** 0.5 * max(1.0, float(ref_lin.abs().max()))
+    y_auto = ops.gemm(x, w, M, N, K, out_dtype=torch.float32)
+    if K % 32 == 0 and N * K >= (1 << 16):
+        assert torch.equal(y, y_auto), "auto dispatch must pick the skinny kernel for M <= 32"
+    y_tc = ops.gemm(x, w, M, N, K, out_dtype=torch.float32, impl=1)
+    assert (y - y_tc).abs().max() <= 1e-4 * max(1.0, float(ref_lin.abs().max()))
+    # bias + tanh-GELU + residual, activation-dtype output
+    want = torch.nn.functional.gelu(ref_lin + bias, approximate="tanh") + res
+    got = ops.gemm(x, w, M, N, K, out_dtype=dtype, bias=bias, act=ops.ACT_GELU_TANH, residual=res, impl=4)
+    tol = (8e-3 if dtype == torch.bfloat16 else 2e-3) * max(1.0, float(want.abs().max()))
+    assert (got.float() - want).abs().max() <= tol
+    # deterministic: the K split is summed in a fixed order
+    assert torch.equal(got, ops.gemm(x, w, M, N, K, out_dtype=dtype, bias=bias, act=ops.ACT_GELU_TANH, residual=res, impl=4))
+
+
+def test_skinny_gemm_refuses_layouts_it_does_not_serve():
+    from cleantransformer_b200 import ops
+    x = torch.randn(33, 64, device=DEV).bfloat16()
+    w = torch.randn(128, 64, device=DEV).bfloat16()
+    with pytest.raises(RuntimeError):
+        ops.gemm(x, w, 33, 128, 64, out_dtype=torch.float32, impl=4)      # M > 32
+    x = torch.randn(8, 48, device=DEV).bfloat16()
+    w = torch.randn(128, 48, device=DEV).bfloat16()
+    with pytest.raises(RuntimeError):
+        ops.gemm(x, w, 8, 128, 48, out_dtype=torch.float32, impl=4)       # K % 32 != 0
+
+
+def test_conv1d_decode_step_uses_the_k_major_shadow_and_matches_the_full_path():
+    """modeling_gpt.py:32-46 Conv1D ([in,out] weight) with <= 32 rows under no_grad streams a cached [out,in] copy;
+    the result must equal the [in,out] tcgen05 path up to summation order, and follow weight updates."""
+    from cleantransformer_b200 import functional as F
+    from cleantransformer_b200.models.modeling_gpt import Conv1D
+    torch.manual_seed(3)
+    lin = Conv1D(3072, 1024).to(DEV)
+    x = torch.randn(32, 1, 1024, device=DEV)
+    with torch.no_grad():
+        y_dec = lin(x, out_dtype=torch.float32)
+    assert getattr(lin.weight, "_ct_shadow_t", None) is not None and lin.weight._ct_shadow_t.shape == (3072, 1024)
+    y_full = lin(x, out_dtype=torch.float32)  # grad mode on: the training path ([in,out] operand read in place)
+    assert (y_dec - y_full.detach()).abs().max() <= 1e-4 * float(y_full.abs().max())
+    with torch.no_grad():
+        lin.weight.mul_(2.0)
+        y2 = lin(x, out_dtype=torch.float32)
+        lin.bias.zero_()
+    assert (y2 - 2 * y_dec).abs().max() <= 2e-2 * float(y_dec.abs().max())  # refreshed shadow (bias was zero-initialised)
