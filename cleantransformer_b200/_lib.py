@@ -58,6 +58,7 @@ class AttnArgs(ctypes.Structure):
         ("first_valid", c_void_p),
         ("impl", ctypes.c_int32),
         ("seq_len_dev", c_void_p),
+        ("dropout_p", c_float), ("rng_stream", ctypes.c_uint32), ("rng_seed", ctypes.c_uint64),
     ]
 
 
@@ -160,6 +161,8 @@ SIGNATURES = {
                                  c_int, c_void_p, c_int, c_void_p]),
     "ct_greedy_step": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_int, c_i64, c_void_p, c_i64,
                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ct_dropout": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_i64, c_float, ctypes.c_uint64,
+                           ctypes.c_uint32, c_void_p]),
     "ct_gemm_wgrad_bias": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_i64,
                                    c_i64, c_i64, c_int, c_void_p]),
 }

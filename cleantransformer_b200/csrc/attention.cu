@@ -75,6 +75,7 @@ struct AttnP {
   void* o; int64_t o_sb, o_sh, o_ss;
   float* lse2;
   const int32_t* sk_dev;  // decode from a CUDA graph: the number of cached keys lives in device memory (else null)
+  DropKey drop;           // attention-probability dropout (thr == 0: off); element (b,h,i,j): hi = b*H + h, lo = i*Sk + j
 };
 
 // score in the log2 domain for element (query i, key j) given the raw dot product
@@ -218,9 +219,12 @@ __device__ __forceinline__ float f4_mask_max(uint32_t (&r)[32], uint32_t kb_addr
 }
 
 // p = 2^(t - m) (SCALED) or 2^(s * sl2 - m) for one 32-column chunk -> four 16-byte pieces of the swizzled P panel
-template <bool SCALED, bool BF16>
+// DROP: probabilities are zeroed AFTER they were added to the row sum (drop_keep_pre over lo_term0 + e * 0x9E3779B1 for
+// element e of the chunk); the 1 / (1 - p) factor is applied once, in the epilogue.
+template <bool SCALED, bool BF16, bool DROP = false>
 __device__ __forceinline__ void f4_exp_store(const uint32_t (&r)[32], int c, float m, float sl2, uint32_t p_row, int sw,
-                                             float2& acc0, float2& acc1) {
+                                             float2& acc0, float2& acc1, uint32_t lo_term0 = 0u, uint32_t drop_pre = 0u,
+                                             uint32_t drop_thr = 0u) {
   const float2 nm = make_float2(-m, -m);
   const float2 s2 = make_float2(sl2, sl2);
 #pragma unroll
@@ -235,6 +239,14 @@ __device__ __forceinline__ void f4_exp_store(const uint32_t (&r)[32], int c, flo
     }
     acc0 = __fadd2_rn(acc0, v[0]); acc1 = __fadd2_rn(acc1, v[1]);
     acc0 = __fadd2_rn(acc0, v[2]); acc1 = __fadd2_rn(acc1, v[3]);
+    if constexpr (DROP) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t lt = lo_term0 + (uint32_t)(8 * g + 2 * u) * 0x9E3779B1u;
+        if (!drop_keep_pre(lt, drop_pre, drop_thr)) v[u].x = 0.f;
+        if (!drop_keep_pre(lt + 0x9E3779B1u, drop_pre, drop_thr)) v[u].y = 0.f;
+      }
+    }
     uint32_t w[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -251,7 +263,7 @@ __device__ __forceinline__ void f4_exp_store(const uint32_t (&r)[32], int c, flo
   }
 }
 
-template <bool HAS_KB, bool BF16>
+template <bool HAS_KB, bool BF16, bool DROP>
 __global__ void __launch_bounds__(F4_THREADS, 2)
     attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const AttnP p) {
@@ -391,6 +403,7 @@ __global__ void __launch_bounds__(F4_THREADS, 2)
     const int sw = qr & 7;
     const int vis = i + p.off;  // last key this row may see under the causal mask
     float m_ref = -INFINITY, l = 0.f;
+    const uint32_t drop_pre = (uint32_t)bh * 0x85EBCA77u + p.drop.key1;
 
     for (int j = 0; j < n_kv; ++j) {
       const int col0 = j * 128 + 64 * half;
@@ -448,12 +461,16 @@ __global__ void __launch_bounds__(F4_THREADS, 2)
         tc_fence_after();
       }
       float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
+      uint32_t lt0 = 0u;  // dropout: lo = i * Sk + column, as lo * 0x9E3779B1 + key0 for this thread's first column
+      if constexpr (DROP) lt0 = ((uint32_t)i * (uint32_t)p.Sk + (uint32_t)col0) * 0x9E3779B1u + p.drop.key0;
       if (scaled) {
-        f4_exp_store<true, BF16>(ra, 0, m_ref, p.sl2, p_row, sw, acc0, acc1);
-        f4_exp_store<true, BF16>(rb, 1, m_ref, p.sl2, p_row, sw, acc0, acc1);
+        f4_exp_store<true, BF16, DROP>(ra, 0, m_ref, p.sl2, p_row, sw, acc0, acc1, lt0, drop_pre, p.drop.thr);
+        f4_exp_store<true, BF16, DROP>(rb, 1, m_ref, p.sl2, p_row, sw, acc0, acc1, lt0 + 32u * 0x9E3779B1u, drop_pre,
+                                       p.drop.thr);
       } else {
-        f4_exp_store<false, BF16>(ra, 0, m_ref, p.sl2, p_row, sw, acc0, acc1);
-        f4_exp_store<false, BF16>(rb, 1, m_ref, p.sl2, p_row, sw, acc0, acc1);
+        f4_exp_store<false, BF16, DROP>(ra, 0, m_ref, p.sl2, p_row, sw, acc0, acc1, lt0, drop_pre, p.drop.thr);
+        f4_exp_store<false, BF16, DROP>(rb, 1, m_ref, p.sl2, p_row, sw, acc0, acc1, lt0 + 32u * 0x9E3779B1u, drop_pre,
+                                        p.drop.thr);
       }
       l += (acc0.x + acc0.y) + (acc1.x + acc1.y);
       fence_proxy_async_smem();
@@ -496,7 +513,7 @@ __global__ void __launch_bounds__(F4_THREADS, 2)
       for (int t = 0; t < 32; ++t) o0[t] = 0u;
     }
     if (i < p.Sq) {
-      const float inv = (n_kv > 0) ? 1.f / l : 0.f;
+      const float inv = (n_kv > 0) ? (DROP ? p.drop.rscale : 1.f) / l : 0.f;
       uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
                       2 * ((int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)i * p.o_ss + 32 * half);
 #pragma unroll
@@ -563,6 +580,9 @@ struct FbCtx {
   int jg, off, causal, key_oob;
   uint32_t lse_s, del_s, sPT, sDS;
   int rr, sw;
+  // attention-probability dropout (d_thr == 0: off): lo * 0x9E3779B1 + key0 = query * d_istep + d_jterm
+  uint32_t d_jterm, d_istep, d_pre, d_thr;
+  float d_rs;
 };
 
 template <bool BF16>
@@ -588,7 +608,9 @@ __device__ __forceinline__ void fb2_store_pair(const FbCtx& cx, int c, int g, co
                : "memory");
 }
 
-// one 32-query chunk c of this thread's key row. KIND 0 = visible, 1 = entirely future, 2 = generic
+// one 32-query chunk c of this thread's key row. KIND 0 = visible, 1 = entirely future, 2 = generic,
+// 3 = generic with dropout: P^T (the dV operand) holds the surviving probabilities scaled by 1 / (1 - p), and dP reaches
+// dS only through them: dS = P * (keep * dP / (1 - p) - delta)
 template <int KIND, bool BF16>
 __device__ __forceinline__ void fb2_chunk(const FbCtx& cx, const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c,
                                           int q0) {
@@ -622,6 +644,21 @@ __device__ __forceinline__ void fb2_chunk(const FbCtx& cx, const uint32_t (&rs)[
         for (int u = 0; u < 4; ++u) {
           pt[hh * 4 + u] = ex2(-FLT_MAX + nls[u]);
           ds[hh * 4 + u] = 0.f;
+        }
+      } else if constexpr (KIND == 3) {
+        const float4 nd = lds128f(cx.del_s + 4 * col);
+        const float nds[4] = {nd.x, nd.y, nd.z, nd.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = g * 8 + hh * 4 + u;
+          const int qg = q0 + col + u;
+          const bool fut = cx.causal && (cx.jg > qg + cx.off);
+          const float v = score2(__uint_as_float(rs[e]), cx.sl2, cx.kb, fut, cx.cf2, false);
+          float pe = ex2(v + nls[u]);
+          if (cx.key_oob) pe = 0.f;
+          const float ks = drop_keep_pre((uint32_t)qg * cx.d_istep + cx.d_jterm, cx.d_pre, cx.d_thr) ? cx.d_rs : 0.f;
+          pt[hh * 4 + u] = pe * ks;
+          ds[hh * 4 + u] = fut ? 0.f : pe * fmaf(__uint_as_float(rd[e]) * ks, cx.scale, nds[u]);
         }
       } else {
         const float4 nd = lds128f(cx.del_s + 4 * col);
@@ -773,6 +810,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
     cx.sl2 = p.sl2; cx.scale = p.scale; cx.cf2 = p.causal_fill2;
     cx.jg = jg; cx.off = p.off; cx.causal = p.causal; cx.key_oob = jg >= p.Sk;
     cx.lse_s = lse_s; cx.del_s = del_s; cx.sPT = sPT; cx.sDS = sDS; cx.rr = rr; cx.sw = rr & 7;
+    cx.d_jterm = (uint32_t)jg * 0x9E3779B1u + p.drop.key0; cx.d_istep = (uint32_t)p.Sk * 0x9E3779B1u;
+    cx.d_pre = (uint32_t)bh * 0x85EBCA77u + p.drop.key1; cx.d_thr = p.drop.thr; cx.d_rs = p.drop.rscale;
     // generic arithmetic for the whole warp when a key is masked (the reference's finite fill matters on
     // fully masked query rows) or the key tile is ragged
     const bool warp_generic = __any_sync(0xffffffffu, cx.kb < -1e30f) || (kv0 + 128 > p.Sk);
@@ -864,7 +903,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         nlse_next = ok ? -__ldg(lse_bh + nq) : -INFINITY;
         ndel_next = ok ? -__ldg(del_bh + nq) * p.scale : 0.f;
       }
-      if (kind0 == 0) fb2_chunk<0, BF16>(cx, rs0, rd0, c0, q0);
+      if (cx.d_thr) fb2_chunk<3, BF16>(cx, rs0, rd0, c0, q0);
+      else if (kind0 == 0) fb2_chunk<0, BF16>(cx, rs0, rd0, c0, q0);
       else if (kind0 == 1) fb2_chunk<1, BF16>(cx, rs0, rd0, c0, q0);
       else fb2_chunk<2, BF16>(cx, rs0, rd0, c0, q0);
       CT_DBG_STAMP(16 * it + 5);
@@ -884,7 +924,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         red_dq(rq, it - 1);
       }
       CT_DBG_STAMP(16 * it + 6);
-      if (kind1 == 0) fb2_chunk<0, BF16>(cx, rs1, rd1, c1, q0);
+      if (cx.d_thr) fb2_chunk<3, BF16>(cx, rs1, rd1, c1, q0);
+      else if (kind1 == 0) fb2_chunk<0, BF16>(cx, rs1, rd1, c1, q0);
       else if (kind1 == 1) fb2_chunk<1, BF16>(cx, rs1, rd1, c1, q0);
       else fb2_chunk<2, BF16>(cx, rs1, rd1, c1, q0);
       CT_DBG_STAMP(16 * it + 7);
@@ -1088,7 +1129,9 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32)
     const float alpha = ex2(m - m_new);
     const float e = ex2(v - m_new);
     // P is rounded to the activation dtype before the PV product, like the tensor-core path
-    const float er = p.fmt == 1 ? __bfloat162float(__float2bfloat16_rn(e)) : __half2float(__float2half_rn(e));
+    float er = p.fmt == 1 ? __bfloat162float(__float2bfloat16_rn(e)) : __half2float(__float2half_rn(e));
+    if (p.drop.thr && !drop_keep(p.drop, (uint32_t)(b * p.H + h), (uint32_t)i * (uint32_t)p.Sk + (uint32_t)j))
+      er = 0.f;  // dropped after the softmax: the row sum below still counts the key
     l = l * alpha + warp_sum(e);
     m = m_new;
 #pragma unroll
@@ -1104,7 +1147,7 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32)
       }
     }
   }
-  const float inv = 1.f / l;
+  const float inv = p.drop.rscale / l;  // survivors of the dropout are scaled by 1 / (1 - p)
   const int64_t ooff = (int64_t)b * p.o_sb + (int64_t)h * p.o_sh + (int64_t)i * p.o_ss;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
@@ -1283,6 +1326,8 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32)
       }
       const bool fut = p.causal && (j > i + p.off);
       const float v = score2(s, p.sl2, kb_row ? kb_row[j] : 0.f, fut, p.causal_fill2, false);
+      if (p.drop.thr)  // dP reaches the scores only through the surviving probabilities, scaled by 1 / (1 - p)
+        dp = drop_keep(p.drop, (uint32_t)(b * p.H + h), (uint32_t)i * (uint32_t)p.Sk + (uint32_t)j) ? dp * p.drop.rscale : 0.f;
       ds = fut ? 0.f : ex2(v - lse) * (dp - dl) * p.scale;
     }
     const int lim = min(32, p.Sk - j0);
@@ -1341,7 +1386,11 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32)
       const bool fut = p.causal && (j > i + p.off);
       const float v = score2(s, p.sl2, kb, fut, p.causal_fill2, false);
       pe = ex2(v - p.lse2[((int64_t)b * p.H + h) * p.Sq + i]);
-      ds = fut ? 0.f : pe * (dp - bp.delta[((int64_t)b * p.H + h) * p.Sq + i]) * p.scale;
+      float keep_scale = 1.f;
+      if (p.drop.thr)
+        keep_scale = drop_keep(p.drop, (uint32_t)(b * p.H + h), (uint32_t)i * (uint32_t)p.Sk + (uint32_t)j) ? p.drop.rscale : 0.f;
+      ds = fut ? 0.f : pe * (dp * keep_scale - bp.delta[((int64_t)b * p.H + h) * p.Sq + i]) * p.scale;
+      pe *= keep_scale;  // dV sees the dropped probabilities
     }
     const int lim = min(32, p.Sq - i0);
     for (int t = 0; t < lim; ++t) {
@@ -1499,6 +1548,7 @@ static void fill_common(AttnP& p, const ct_attn_args& a) {
   p.o = a.o; p.o_sb = a.o_sb; p.o_sh = a.o_sh; p.o_ss = a.o_ss;
   p.lse2 = a.lse2;
   p.sk_dev = a.seq_len_dev;
+  p.drop = make_drop_key(a.dropout_p, a.rng_seed, a.rng_stream);
 }
 
 static int check_args(const ct_attn_args& a, const char* who) {
@@ -1506,6 +1556,8 @@ static int check_args(const ct_attn_args& a, const char* who) {
   CT_REQUIRE(a.B > 0 && a.H > 0 && a.Sq > 0 && a.Sk > 0 && a.D > 0 && a.D <= 128, CT_ERR_BAD_ARG,
              "%s: bad shape B=%d H=%d Sq=%d Sk=%d D=%d", who, a.B, a.H, a.Sq, a.Sk, a.D);
   CT_REQUIRE(a.dtype == DT_BF16 || a.dtype == DT_F16, CT_ERR_UNSUPPORTED, "%s: dtype must be bf16/f16", who);
+  CT_REQUIRE(a.dropout_p >= 0.f && a.dropout_p < 1.f, CT_ERR_BAD_ARG, "%s: dropout_p must be in [0, 1)", who);
+  CT_REQUIRE(a.dropout_p == 0.f || a.seq_len_dev == nullptr, CT_ERR_UNSUPPORTED, "%s: no dropout in the decode step", who);
   return 0;
 }
 
@@ -1542,18 +1594,28 @@ extern "C" int ct_attn_fwd(const ct_attn_args* args, void* stream) {
     CT_REQUIRE(a.scale > 0.f, CT_ERR_BAD_ARG, "ct_attn_fwd: the tcgen05 path needs scale > 0");
     static bool attr4 = false;
     if (!attr4) {
-      CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
-      CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
-      CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
-      CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
+#define CT_F4_ATTR(KB, BF, DR) \
+  CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<KB, BF, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM))
+      CT_F4_ATTR(true, true, false); CT_F4_ATTR(true, false, false); CT_F4_ATTR(false, true, false); CT_F4_ATTR(false, false, false);
+      CT_F4_ATTR(true, true, true); CT_F4_ATTR(true, false, true); CT_F4_ATTR(false, true, true); CT_F4_ATTR(false, false, true);
+#undef CT_F4_ATTR
       attr4 = true;
     }
     const int64_t grid = (int64_t)a.B * a.H * ((a.Sq + 127) / 128);
-    const bool kb = a.kbias2 != nullptr, bf = p.fmt == 1;
-    if (kb && bf) attn_fwd_tc4_kernel<true, true><<<(unsigned)grid, F4_THREADS, F4_SMEM, st>>>(tmQ, tmK, tmV, p);
-    else if (kb) attn_fwd_tc4_kernel<true, false><<<(unsigned)grid, F4_THREADS, F4_SMEM, st>>>(tmQ, tmK, tmV, p);
-    else if (bf) attn_fwd_tc4_kernel<false, true><<<(unsigned)grid, F4_THREADS, F4_SMEM, st>>>(tmQ, tmK, tmV, p);
-    else attn_fwd_tc4_kernel<false, false><<<(unsigned)grid, F4_THREADS, F4_SMEM, st>>>(tmQ, tmK, tmV, p);
+    const bool kb = a.kbias2 != nullptr, bf = p.fmt == 1, dr = p.drop.thr != 0u;
+#define CT_F4_GO(KB, BF, DR) attn_fwd_tc4_kernel<KB, BF, DR><<<(unsigned)grid, F4_THREADS, F4_SMEM, st>>>(tmQ, tmK, tmV, p)
+    if (dr) {
+      if (kb && bf) CT_F4_GO(true, true, true);
+      else if (kb) CT_F4_GO(true, false, true);
+      else if (bf) CT_F4_GO(false, true, true);
+      else CT_F4_GO(false, false, true);
+    } else {
+      if (kb && bf) CT_F4_GO(true, true, false);
+      else if (kb) CT_F4_GO(true, false, false);
+      else if (bf) CT_F4_GO(false, true, false);
+      else CT_F4_GO(false, false, false);
+    }
+#undef CT_F4_GO
     CT_LAUNCH_OK();
     return 0;
   }
@@ -1678,19 +1740,19 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
 // occupancy with the dynamic shared memory reduced by 0 / 1 / 2 / 4 / 16 KB (what limits it: registers or smem?).
 extern "C" int ct_attn_occupancy(int* fwd_ctas_per_sm, int* bwd_ctas_per_sm, int* detail) {
   CT_REQUIRE(fwd_ctas_per_sm && bwd_ctas_per_sm, CT_ERR_BAD_ARG, "ct_attn_occupancy: null out");
-  CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
+  CT_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc4_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
   CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
-  CT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(fwd_ctas_per_sm, attn_fwd_tc4_kernel<true, true>, F4_THREADS,
+  CT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(fwd_ctas_per_sm, attn_fwd_tc4_kernel<true, true, false>, F4_THREADS,
                                                            F4_SMEM));
   CT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bwd_ctas_per_sm, attn_bwd_tc2_kernel<true, 3>, FB_THREADS,
                                                            FB_SMEM_PIPE));
   if (detail) {
     cudaFuncAttributes fa;
-    CT_CUDA_OK(cudaFuncGetAttributes(&fa, attn_fwd_tc4_kernel<true, true>));
+    CT_CUDA_OK(cudaFuncGetAttributes(&fa, attn_fwd_tc4_kernel<true, true, false>));
     detail[0] = fa.numRegs; detail[1] = (int)fa.sharedSizeBytes; detail[2] = F4_SMEM;
     const int cut[5] = {0, 1024, 2048, 4096, 16384};
     for (int i = 0; i < 5; ++i)
-      CT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(detail + 3 + i, attn_fwd_tc4_kernel<true, true>,
+      CT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(detail + 3 + i, attn_fwd_tc4_kernel<true, true, false>,
                                                                F4_THREADS, F4_SMEM - cut[i]));
   }
   return 0;

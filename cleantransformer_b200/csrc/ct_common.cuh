@@ -112,6 +112,28 @@ __device__ __forceinline__ float tanh_approx(float x) {
 
 // Activations. gelu_tanh follows modeling_bloom.py:335-345 (constant 0.79788456) which equals
 // modeling_gpt.py:112-122 up to rounding of sqrt(2/pi).
+// ---- counter-based dropout mask (include/ct_b200.h: "dropout") ----
+struct DropKey { uint32_t key0, key1, thr; float rscale; };  // thr == 0: dropout off
+__host__ __device__ __forceinline__ DropKey make_drop_key(float p, uint64_t seed, uint32_t stream) {
+  DropKey k;
+  k.key0 = (uint32_t)seed + stream * 0x632BE5ABu;
+  k.key1 = (uint32_t)(seed >> 32) ^ (stream * 0x2545F491u);
+  k.thr = p > 0.f ? (uint32_t)(p * 16777216.f + 0.5f) : 0u;
+  k.rscale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  return k;
+}
+__device__ __forceinline__ uint32_t drop_mix(uint32_t h) {
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return h;
+}
+// `pre` = hi * 0x85EBCA77 + key1 (constant per (b, h) in attention); lo_term = lo * 0x9E3779B1 + key0
+__device__ __forceinline__ bool drop_keep_pre(uint32_t lo_term, uint32_t pre, uint32_t thr) {
+  return (drop_mix(lo_term ^ pre) >> 8) >= thr;
+}
+__device__ __forceinline__ bool drop_keep(const DropKey& k, uint32_t hi, uint32_t lo) {
+  return drop_keep_pre(lo * 0x9E3779B1u + k.key0, hi * 0x85EBCA77u + k.key1, k.thr);
+}
+
 __device__ __forceinline__ float act_apply(float x, int act) {
   switch (act) {
     case ACT_RELU: return fmaxf(x, 0.f);

@@ -155,6 +155,19 @@ static int ew_blocks(int64_t work) {
   if (b < 1) b = 1;
   return (int)b;
 }
+// torch.nn.Dropout on a hidden-state tensor, optionally fused with the residual add that follows it
+// (include/ct_b200.h: ct_dropout). 4 elements per thread and iteration: the streams are read as consecutive elements.
+__global__ void __launch_bounds__(256)
+    dropout_kernel(const void* __restrict__ x, int xdt, const void* __restrict__ res, int rdt, void* __restrict__ out,
+                   int odt, int64_t n, const DropKey k) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = drop_keep(k, (uint32_t)((uint64_t)i >> 32), (uint32_t)i) ? ld_any(x, xdt, i) * k.rscale : 0.f;
+    if (res) v += ld_any(res, rdt, i);
+    st_any(out, odt, i, v);
+  }
+}
+
 static bool dt_any_ok(int dt) { return dt == DT_F32 || dt == DT_BF16 || dt == DT_F16; }
 
 }  // namespace ct
@@ -235,6 +248,19 @@ extern "C" int ct_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dty
   else
     act_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, x, x_dtype, dx,
                                                                    dx_dtype, act, n);
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_dropout(const void* x, int x_dtype, const void* residual, int res_dtype, void* out, int out_dtype,
+                          int64_t n, float p, uint64_t seed, uint32_t rng_stream, void* stream) {
+  CT_REQUIRE(x && out, CT_ERR_BAD_ARG, "ct_dropout: null pointer");
+  CT_REQUIRE(dt_any_ok(x_dtype) && dt_any_ok(out_dtype) && (!residual || dt_any_ok(res_dtype)), CT_ERR_UNSUPPORTED,
+             "ct_dropout: dtype");
+  CT_REQUIRE(p >= 0.f && p < 1.f, CT_ERR_BAD_ARG, "ct_dropout: p must be in [0, 1)");
+  if (n <= 0) return 0;
+  dropout_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, residual, res_dtype, out, out_dtype, n,
+                                                                 make_drop_key(p, seed, rng_stream));
   CT_LAUNCH_OK();
   return 0;
 }

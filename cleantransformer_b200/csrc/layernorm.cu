@@ -42,25 +42,50 @@ struct Vec4<__nv_bfloat16> {
   }
 };
 
+template <>
+struct Vec4<__half> {
+  static __device__ __forceinline__ float4 load(const __half* p) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void store(__half* p, float4 v) {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+// run-time typed accessors: f32, bf16 (the default autocast dtype) or f16 (torch.cuda.amp.autocast(),
+// examples/ft_bloom_DDP.py:108-128)
 __device__ __forceinline__ float4 load4_dyn(const void* base, int dtype, int64_t idx) {
   if (dtype == DT_F32) return Vec4<float>::load(reinterpret_cast<const float*>(base) + idx);
-  return Vec4<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+  if (dtype == DT_BF16) return Vec4<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+  return Vec4<__half>::load(reinterpret_cast<const __half*>(base) + idx);
 }
 __device__ __forceinline__ void store4_dyn(void* base, int dtype, int64_t idx, float4 v) {
   if (dtype == DT_F32)
     Vec4<float>::store(reinterpret_cast<float*>(base) + idx, v);
-  else
+  else if (dtype == DT_BF16)
     Vec4<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(base) + idx, v);
+  else
+    Vec4<__half>::store(reinterpret_cast<__half*>(base) + idx, v);
 }
 __device__ __forceinline__ float load1_dyn(const void* base, int dtype, int64_t idx) {
   if (dtype == DT_F32) return reinterpret_cast<const float*>(base)[idx];
-  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+  if (dtype == DT_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+  return __half2float(reinterpret_cast<const __half*>(base)[idx]);
 }
 __device__ __forceinline__ void store1_dyn(void* base, int dtype, int64_t idx, float v) {
   if (dtype == DT_F32)
     reinterpret_cast<float*>(base)[idx] = v;
-  else
+  else if (dtype == DT_BF16)
     reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+  else
+    reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
 }
 
 constexpr int LN_WARPS = 8;
@@ -601,7 +626,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
   }
 }
 
-static bool dt_ok(int dt) { return dt == DT_F32 || dt == DT_BF16; }
+static bool dt_ok(int dt) { return dt == DT_F32 || dt == DT_BF16 || dt == DT_F16; }
 static bool aligned16(const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; }
 
 static int ln_grid(int64_t rows) {
@@ -624,7 +649,7 @@ extern "C" int ct_layernorm_fwd(const void* x, int x_dtype, const float* gamma, 
   if (rows == 0) return 0;  // empty input: nothing to do (pointers may legitimately be null)
   CT_REQUIRE(x && gamma && beta && (y || y2), CT_ERR_BAD_ARG, "ct_layernorm_fwd: null pointer");
   CT_REQUIRE(dt_ok(x_dtype) && (!y || dt_ok(y_dtype)) && (!y2 || dt_ok(y2_dtype)),
-             CT_ERR_UNSUPPORTED, "ct_layernorm_fwd: dtype must be f32 or bf16");
+             CT_ERR_UNSUPPORTED, "ct_layernorm_fwd: dtype must be f32, bf16 or f16");
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ln_grid(rows);
@@ -660,7 +685,7 @@ static int ln_bwd_v1(const void* dy, int dy_dtype, const void* dy2, int dy2_dtyp
   CT_REQUIRE(rows >= 0 && cols > 0, CT_ERR_BAD_ARG, "ct_layernorm_bwd: bad shape");
   CT_REQUIRE(dt_ok(x_dtype) && dt_ok(dx_dtype) && (!dy || dt_ok(dy_dtype)) &&
                  (!dy2 || dt_ok(dy2_dtype)) && (!dx_add || dt_ok(dx_add_dtype)),
-             CT_ERR_UNSUPPORTED, "ct_layernorm_bwd: dtype must be f32 or bf16");
+             CT_ERR_UNSUPPORTED, "ct_layernorm_bwd: dtype must be f32, bf16 or f16");
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec_shape = (cols % 128 == 0) && cols <= 1024;
   int grid_probe = ln_grid(rows);
@@ -722,7 +747,7 @@ extern "C" int ct_layernorm_bwd_ex(const ct_ln_bwd_args* args, void* stream) {
   CT_REQUIRE(dt_ok(a.x_dtype) && dt_ok(a.dx_dtype) && (!a.dy || dt_ok(a.dy_dtype)) &&
                  (!a.dy2 || dt_ok(a.dy2_dtype)) && (!a.dx_add || dt_ok(a.dx_add_dtype)) &&
                  (!a.dx2 || dt_ok(a.dx2_dtype)),
-             CT_ERR_UNSUPPORTED, "ct_layernorm_bwd: dtype must be f32 or bf16");
+             CT_ERR_UNSUPPORTED, "ct_layernorm_bwd: dtype must be f32, bf16 or f16");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = a.rows, cols = a.cols;
   const bool vec_shape = (cols % 128 == 0) && cols <= 1024;

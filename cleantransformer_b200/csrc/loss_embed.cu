@@ -106,6 +106,16 @@ template <>
 __device__ __forceinline__ float ce_ld<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) {
   return __bfloat162float(p[i]);
 }
+template <>
+__device__ __forceinline__ float ce_ld<__half>(const __half* p, int64_t i) { return __half2float(p[i]); }
+template <typename T>
+struct ce_is_bf16 { static constexpr bool value = false; };
+template <>
+struct ce_is_bf16<__nv_bfloat16> { static constexpr bool value = true; };
+template <typename T>
+struct ce_is_f16 { static constexpr bool value = false; };
+template <>
+struct ce_is_f16<__half> { static constexpr bool value = true; };
 
 // (max, sum of exp relative to max) pairs; a side that saw no element is (-inf, 0) and must not
 // produce exp(-inf - -inf) = NaN
@@ -152,7 +162,10 @@ __global__ void __launch_bounds__(CE_THREADS)
                   const float* __restrict__ stats, int64_t rows, int64_t V, int64_t S, int shift,
                   long long ignore_index) {
   __shared__ float red[2 * (CE_THREADS >> 5)];
-  const float inv_count = 1.f / fmaxf(stats[0], 1.f);
+  // f16 (torch.cuda.amp.autocast() + GradScaler, examples/ft_bloom_DDP.py:108-128): 1/count (~1e-4) times a small
+  // probability underflows the f16 range before the loss scale can be applied, so the f16 gradient is stored
+  // UN-normalised (softmax - onehot) and the caller multiplies by dloss / count in one step (ops.py).
+  const float inv_count = ce_is_f16<T>::value ? 1.f : 1.f / fmaxf(stats[0], 1.f);
   for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
     const T* x = logits + r * ld;
     const long long tgt = ce_target(labels, r, S, shift);
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(CE_THREADS)
       continue;
     }
     float m = -INFINITY, s = 0.f;
-    if (sizeof(T) == 2 && (V & 7) == 0 && (ld & 7) == 0) {
+    if (ce_is_bf16<T>::value && (V & 7) == 0 && (ld & 7) == 0) {
       const uint4* x8 = reinterpret_cast<const uint4*>(x);
       for (int64_t c = threadIdx.x; c < (V >> 3); c += CE_THREADS) {
         const uint4 u = x8[c];
@@ -199,7 +212,7 @@ __global__ void __launch_bounds__(CE_THREADS)
     if (row_loss && threadIdx.x == 0) row_loss[r] = lse - ce_ld<T>(x, tgt);
     if (dlogits) {
       T* d = dlogits + r * ldd;
-      if (sizeof(T) == 2 && (V & 7) == 0 && (ld & 7) == 0 && (ldd & 7) == 0) {
+      if (ce_is_bf16<T>::value && (V & 7) == 0 && (ld & 7) == 0 && (ldd & 7) == 0) {
         const uint4* x8 = reinterpret_cast<const uint4*>(x);
         uint4* d8 = reinterpret_cast<uint4*>(d);
         for (int64_t c = threadIdx.x; c < (V >> 3); c += CE_THREADS) {
@@ -726,7 +739,7 @@ extern "C" int ct_cross_entropy_fwd(const void* logits, int dtype, int64_t ld, c
                                     int64_t rows, int64_t V, int64_t S, int shift,
                                     int64_t ignore_index, void* stream) {
   CT_REQUIRE(logits && labels && loss && workspace, CT_ERR_BAD_ARG, "ct_cross_entropy_fwd: null pointer");
-  CT_REQUIRE(dtype == DT_F32 || dtype == DT_BF16, CT_ERR_UNSUPPORTED, "ct_cross_entropy_fwd: dtype");
+  CT_REQUIRE(dtype == DT_F32 || dtype == DT_BF16 || dtype == DT_F16, CT_ERR_UNSUPPORTED, "ct_cross_entropy_fwd: dtype");
   CT_REQUIRE(rows > 0 && V > 0 && (!shift || (S > 0 && rows % S == 0)), CT_ERR_BAD_ARG,
              "ct_cross_entropy_fwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
@@ -776,6 +789,10 @@ extern "C" int ct_cross_entropy_fwd(const void* logits, int dtype, int64_t ld, c
     ce_fwd_kernel<__nv_bfloat16><<<(unsigned)grid, CE_THREADS, 0, st>>>(
         (const __nv_bfloat16*)logits, ld, (const long long*)labels, (__nv_bfloat16*)dlogits, ldd, row_loss,
         stats, rows, V, S, shift, (long long)ignore_index);
+  else if (dtype == DT_F16)
+    ce_fwd_kernel<__half><<<(unsigned)grid, CE_THREADS, 0, st>>>(
+        (const __half*)logits, ld, (const long long*)labels, (__half*)dlogits, ldd, row_loss, stats, rows, V, S, shift,
+        (long long)ignore_index);
   else
     ce_fwd_kernel<float><<<(unsigned)grid, CE_THREADS, 0, st>>>(
         (const float*)logits, ld, (const long long*)labels, (float*)dlogits, ldd, row_loss, stats, rows, V, S,
@@ -818,13 +835,15 @@ extern "C" int ct_cross_entropy_fwd_stats(const void* logits, int64_t ld, const 
 
 extern "C" int ct_scale_by_scalar(void* x, int dtype, int64_t n, const float* device_scalar, void* stream) {
   CT_REQUIRE(x && device_scalar, CT_ERR_BAD_ARG, "ct_scale_by_scalar: null pointer");
-  CT_REQUIRE(dtype == DT_F32 || dtype == DT_BF16, CT_ERR_UNSUPPORTED, "ct_scale_by_scalar: dtype");
+  CT_REQUIRE(dtype == DT_F32 || dtype == DT_BF16 || dtype == DT_F16, CT_ERR_UNSUPPORTED, "ct_scale_by_scalar: dtype");
   if (n <= 0) return 0;
   int64_t blocks = (n + 255) / 256;
   if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
   if (dtype == DT_BF16)
     scale_by_device_scalar_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         (__nv_bfloat16*)x, n, device_scalar);
+  else if (dtype == DT_F16)
+    scale_by_device_scalar_kernel<__half><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((__half*)x, n, device_scalar);
   else
     scale_by_device_scalar_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((float*)x, n,
                                                                                            device_scalar);

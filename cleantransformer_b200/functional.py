@@ -260,6 +260,62 @@ def linear(x, weight, bias=None, act=ops.ACT_NONE, residual=None, out_dtype=None
 # ------------------------------------------------------------------------------------------------
 # Attention core
 # ------------------------------------------------------------------------------------------------
+# Dropout: one counter-based generator for every site (include/ct_b200.h: "dropout")
+# ------------------------------------------------------------------------------------------------
+class _DropoutState:
+    """seed: torch's CPU generator seed at first use (so `torch.manual_seed` governs the masks as it does for the
+    reference), or `manual_dropout_seed`. Every dropout call of a forward pass takes the next `stream` number; the
+    backward of that call reuses it, so no mask is ever stored."""
+    seed = None
+    stream = 0
+
+
+def manual_dropout_seed(seed):
+    _DropoutState.seed = int(seed)
+    _DropoutState.stream = 0
+
+
+def next_dropout(p):
+    """(p, seed, stream) for one dropout site call; refuses CUDA-graph capture (the stream number is a host counter that
+    a replay would not advance: every replay would drop the same elements)."""
+    if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("dropout > 0 cannot be captured in a CUDA graph (host-side mask counter); run the step un-graphed")
+    if _DropoutState.seed is None:
+        _DropoutState.seed = int(torch.initial_seed())
+    _DropoutState.stream = (_DropoutState.stream + 1) & 0xFFFFFFFF
+    return (float(p), _DropoutState.seed, _DropoutState.stream)
+
+
+class DropoutFn(torch.autograd.Function):
+    """torch.nn.Dropout on a hidden-state tensor, fused with the residual add that follows it where there is one
+    (transformer.py:109-116, modeling_gpt.py:136,150-153, modeling_bert.py:253-262, modeling_bloom.py dropout_add)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, drop, out_dtype):
+        ctx.drop = drop
+        ctx.x_dtype = x.dtype
+        ctx.has_res = residual is not None
+        ctx.res_dtype = residual.dtype if residual is not None else None
+        return ops.dropout(x.detach(), drop[0], drop[1], drop[2], residual.detach() if residual is not None else None,
+                           out_dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed, stream = ctx.drop
+        dx = ops.dropout(dy, p, seed, stream, None, ctx.x_dtype)
+        dres = None
+        if ctx.has_res:
+            dres = dy if dy.dtype == ctx.res_dtype else ops.cast(dy.contiguous(), ctx.res_dtype)
+        return dx, dres, None, None
+
+
+def dropout(x, p, training, residual=None, out_dtype=None):
+    """residual + dropout(x) (or dropout(x)); identity (+ residual) when not training or p == 0."""
+    if not training or p <= 0:
+        return x if residual is None else (x + residual if out_dtype is None else (x.to(out_dtype) + residual.to(out_dtype)))
+    return DropoutFn.apply(x, residual, next_dropout(p), out_dtype or (residual.dtype if residual is not None else x.dtype))
+
+
 LAYOUT_BLOOM = "bloom"        # fused [B,S,H,3,D]   (modeling_bloom.py:81-82)
 LAYOUT_GPT = "gpt"            # fused [B,S,3,H,D]   (modeling_gpt.py:72)
 
@@ -279,48 +335,49 @@ class PackedAttentionFn(torch.autograd.Function):
     """softmax(QK^T*scale + bias/masks) V on a packed QKV tensor (training / prefill, no cache)."""
 
     @staticmethod
-    def forward(ctx, qkv, n_head, layout, scale, causal, causal_fill, kbias2, first_valid):
+    def forward(ctx, qkv, n_head, layout, scale, causal, causal_fill, kbias2, first_valid, drop=None):
+        """drop: None or next_dropout(p) — attention-probability dropout inside the kernel."""
         qkv_d = qkv.detach().contiguous()
         q, k, v = split_packed(qkv_d, n_head, layout)
         o, lse2 = ops.attn_fwd(q, k, v, scale, causal, causal_fill, kbias2, first_valid,
-                               need_lse=qkv.requires_grad)
+                               need_lse=qkv.requires_grad, dropout=drop)
         ctx.save_for_backward(qkv_d, o, lse2, kbias2, first_valid)
-        ctx.cfg = (n_head, layout, scale, causal, causal_fill)
+        ctx.cfg = (n_head, layout, scale, causal, causal_fill, drop)
         return o
 
     @staticmethod
     def backward(ctx, do):
         qkv, o, lse2, kbias2, first_valid = ctx.saved_tensors
-        n_head, layout, scale, causal, causal_fill = ctx.cfg
+        n_head, layout, scale, causal, causal_fill, drop = ctx.cfg
         dqkv = torch.empty_like(qkv)
         q, k, v = split_packed(qkv, n_head, layout)
         dq, dk, dv = split_packed(dqkv, n_head, layout)
         do = do.contiguous()
         if do.dtype != qkv.dtype:
             do = ops.cast(do, qkv.dtype)
-        ops.attn_bwd(do, q, k, v, o, lse2, dq, dk, dv, scale, causal, causal_fill, kbias2, first_valid)
-        return dqkv, None, None, None, None, None, None, None
+        ops.attn_bwd(do, q, k, v, o, lse2, dq, dk, dv, scale, causal, causal_fill, kbias2, first_valid, dropout=drop)
+        return dqkv, None, None, None, None, None, None, None, None
 
 
 class SeparateAttentionFn(torch.autograd.Function):
     """Same, for three separate [B,S,H*D] projections (transformer.py:37-57)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, n_head, scale, causal, causal_fill, kbias2, first_valid):
+    def forward(ctx, q, k, v, n_head, scale, causal, causal_fill, kbias2, first_valid, drop=None):
         B, Sq, HD = q.shape
         D = HD // n_head
         qd, kd, vd = [t.detach().contiguous() for t in (q, k, v)]
         q4, k4, v4 = [t.view(B, t.shape[1], n_head, D).permute(0, 2, 1, 3) for t in (qd, kd, vd)]
         need = q.requires_grad or k.requires_grad or v.requires_grad
-        o, lse2 = ops.attn_fwd(q4, k4, v4, scale, causal, causal_fill, kbias2, first_valid, need_lse=need)
+        o, lse2 = ops.attn_fwd(q4, k4, v4, scale, causal, causal_fill, kbias2, first_valid, need_lse=need, dropout=drop)
         ctx.save_for_backward(qd, kd, vd, o, lse2, kbias2, first_valid)
-        ctx.cfg = (n_head, scale, causal, causal_fill)
+        ctx.cfg = (n_head, scale, causal, causal_fill, drop)
         return o
 
     @staticmethod
     def backward(ctx, do):
         qd, kd, vd, o, lse2, kbias2, first_valid = ctx.saved_tensors
-        n_head, scale, causal, causal_fill = ctx.cfg
+        n_head, scale, causal, causal_fill, drop = ctx.cfg
         B, Sq, HD = qd.shape
         D = HD // n_head
         v4 = lambda t: t.view(B, t.shape[1], n_head, D).permute(0, 2, 1, 3)
@@ -329,8 +386,8 @@ class SeparateAttentionFn(torch.autograd.Function):
         if do.dtype != qd.dtype:
             do = ops.cast(do, qd.dtype)
         ops.attn_bwd(do, v4(qd), v4(kd), v4(vd), o, lse2, v4(dq), v4(dk), v4(dv), scale, causal,
-                     causal_fill, kbias2, first_valid)
-        return dq, dk, dv, None, None, None, None, None, None
+                     causal_fill, kbias2, first_valid, dropout=drop)
+        return dq, dk, dv, None, None, None, None, None, None, None
 
 
 def attention_cached(q4, k4, v4, scale, causal, causal_fill, kbias2, first_valid):

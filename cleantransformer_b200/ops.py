@@ -28,7 +28,7 @@ _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
 # (bench.py's roofline pass). Counts are the number of kernels each C-ABI call enqueues.
 LAUNCHES = [0]
 GEMM_PROFILE = None  # when a list: (M, N, K, start_event, end_event) appended per ct_gemm call
-_KERNELS_PER_CALL = {"ct_kv_append": 1, "ct_attn_decode": 1, "ct_kv_append_dev": 1, "ct_greedy_step": 1,
+_KERNELS_PER_CALL = {"ct_dropout": 1, "ct_kv_append": 1, "ct_attn_decode": 1, "ct_kv_append_dev": 1, "ct_greedy_step": 1,
                      "ct_layernorm_fwd": 1, "ct_layernorm_bwd": 2, "ct_layernorm_bwd_ex": 2, "ct_adamw_step": 1, "ct_adamw_multi": 1,
                      "ct_sgd_step": 1, "ct_cast": 1, "ct_colsum": 1, "ct_act_fwd": 1, "ct_act_bwd": 1,
                      "ct_gemm": 1, "ct_attn_fwd": 1, "ct_attn_bwd": 3, "ct_attn_mask_prep": 1,
@@ -103,7 +103,8 @@ def _ln_workspace(device, cols):
     """Scratch for the two-stage dgamma/dbeta reduction (stream-ordered reuse on the current stream)."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _LN_WS.get(key)
-    need = 3 * 2 * 160 * 1024  # 3 * (2 * #SMs) * cols upper bound for cols <= 1024
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    need = 3 * 2 * sms * 1024  # three column sums x (2 * #SMs) partial rows x cols <= 1024 (csrc/layernorm.cu)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.float32, device=device)
         _LN_WS[key] = ws
@@ -340,7 +341,8 @@ def _bhsd_strides(t):
     return t.stride(0), t.stride(1), t.stride(2)
 
 
-def _fill_attn(a, q, k, v, o, lse2, scale, causal, causal_fill, kbias2, first_valid, impl, seq_len_dev=None):
+def _fill_attn(a, q, k, v, o, lse2, scale, causal, causal_fill, kbias2, first_valid, impl, seq_len_dev=None,
+               dropout=None):
     B, H, Sq, D = q.shape
     Sk = k.shape[2]
     a.B, a.H, a.Sq, a.Sk, a.D = B, H, Sq, Sk, D
@@ -361,32 +363,37 @@ def _fill_attn(a, q, k, v, o, lse2, scale, causal, causal_fill, kbias2, first_va
     a.first_valid = ptr(first_valid)
     a.impl = impl
     a.seq_len_dev = ptr(seq_len_dev)
+    if dropout is not None and dropout[0] > 0:  # (p, seed, stream): include/ct_b200.h "dropout"
+        a.dropout_p, a.rng_seed, a.rng_stream = float(dropout[0]), int(dropout[1]) & (2 ** 64 - 1), int(dropout[2]) & 0xFFFFFFFF
+    else:
+        a.dropout_p, a.rng_seed, a.rng_stream = 0.0, 0, 0
 
 
 def attn_fwd(q, k, v, scale, causal=False, causal_fill=-FLT_MAX, kbias2=None, first_valid=None,
-             need_lse=True, impl=0, seq_len_dev=None):
+             need_lse=True, impl=0, seq_len_dev=None, dropout=None):
     """q [B,H,Sq,D], k/v [B,H,Sk,D] as strided VIEWS (D contiguous). Returns (o [B,Sq,H*D], lse2).
     seq_len_dev (int32 device scalar, q_len = 1 only): the number of valid cached keys is read on the device and Sk is
-    only the capacity — what a captured decode step needs."""
+    only the capacity — what a captured decode step needs.
+    dropout = (p, seed, stream): attention-probability dropout after the softmax (include/ct_b200.h: "dropout")."""
     _req_cuda(q, k, v)
     B, H, Sq, D = q.shape
     o = torch.empty((B, Sq, H * D), dtype=q.dtype, device=q.device)
     o4 = o.view(B, Sq, H, D).permute(0, 2, 1, 3)
     lse2 = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device) if need_lse else None
     a = AttnArgs()
-    _fill_attn(a, q, k, v, o4, lse2, scale, causal, causal_fill, kbias2, first_valid, impl, seq_len_dev)
+    _fill_attn(a, q, k, v, o4, lse2, scale, causal, causal_fill, kbias2, first_valid, impl, seq_len_dev, dropout)
     _ck(_lib.load().ct_attn_fwd(ctypes.byref(a), stream()), "ct_attn_fwd")
     return o, lse2
 
 
 def attn_bwd(dout, q, k, v, o, lse2, dq, dk, dv, scale, causal=False, causal_fill=-FLT_MAX,
-             kbias2=None, first_valid=None, impl=0):
-    """dout/o [B,Sq,H*D]; q,k,v,dq,dk,dv [B,H,S,D] strided views; dq/dk/dv are written."""
+             kbias2=None, first_valid=None, impl=0, dropout=None):
+    """dout/o [B,Sq,H*D]; q,k,v,dq,dk,dv [B,H,S,D] strided views; dq/dk/dv are written. `dropout`: the forward's tuple."""
     B, H, Sq, D = q.shape
     o4 = o.view(B, Sq, H, D).permute(0, 2, 1, 3)
     dout = dout.contiguous()
     a = AttnBwdArgs()
-    _fill_attn(a.f, q, k, v, o4, lse2, scale, causal, causal_fill, kbias2, first_valid, impl)
+    _fill_attn(a.f, q, k, v, o4, lse2, scale, causal, causal_fill, kbias2, first_valid, impl, None, dropout)
     a.dout = dout.data_ptr()
     a.dq = dq.data_ptr(); a.dq_sb, a.dq_sh, a.dq_ss = _bhsd_strides(dq)
     a.dk = dk.data_ptr(); a.dk_sb, a.dk_sh, a.dk_ss = _bhsd_strides(dk)
@@ -399,6 +406,22 @@ def attn_bwd(dout, q, k, v, o, lse2, dq, dk, dv, scale, causal=False, causal_fil
     dq_acc = torch.empty((B, H, (Sq + 127) // 128 * 128, D), dtype=torch.float32, device=q.device) if D == 64 else None
     a.dq_accum = ptr(dq_acc)
     _ck(_lib.load().ct_attn_bwd(ctypes.byref(a), stream()), "ct_attn_bwd")
+
+
+def dropout(x, p, seed, rng_stream, residual=None, out_dtype=None):
+    """(residual +) x * keep / (1 - p) with the counter-based mask of include/ct_b200.h ("dropout"): element e of the
+    flattened tensor is kept iff ct_dropout_keep(seed, rng_stream, e >> 32, e & 0xffffffff). The site's backward is the
+    same call on the incoming gradient (no residual)."""
+    _req_cuda(x)
+    x = x.contiguous()
+    if residual is not None:
+        residual = residual.contiguous()
+        assert residual.shape == x.shape
+    out = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
+    _ck(_lib.load().ct_dropout(ptr(x), dt(x), ptr(residual), dt(residual) if residual is not None else 0, ptr(out),
+                               dt(out), x.numel(), float(p), int(seed) & (2 ** 64 - 1), int(rng_stream) & 0xFFFFFFFF,
+                               stream()), "ct_dropout")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -437,6 +460,10 @@ def cross_entropy_fwd(logits2d, labels, S=0, shift=False, ignore_index=-100, wan
                                            ptr(dl), dl.stride(0) if dl is not None else 0, ptr(loss),
                                            ptr(ws), rows, V, S, 1 if shift else 0, ignore_index,
                                            stream()), "ct_cross_entropy_fwd")
+    if dl is not None and dl.dtype == torch.float16:
+        # f16 gradients are stored as (softmax - onehot): dividing by the target count here would underflow before a
+        # GradScaler factor arrives (csrc/loss_embed.cu: ce_fwd_kernel). The backward multiplies by dloss / count.
+        dl._ct_pending_count = ws[0:1]
     return loss, dl
 
 
@@ -456,6 +483,12 @@ def cross_entropy_fwd_stats(logits2d, labels, row_stats, S=0, shift=False, ignor
 
 
 def scale_by_scalar(x, scalar_f32):
+    """x *= scalar (device f32 scalar: the upstream dloss). f16 cross-entropy gradients also carry their pending
+    1 / count (cross_entropy_fwd), applied here in the same f32 multiply."""
+    count = getattr(x, "_ct_pending_count", None)
+    if count is not None:
+        scalar_f32 = (scalar_f32.reshape(1) / count.clamp_min(1.0)).contiguous()
+        x._ct_pending_count = None
     _ck(_lib.load().ct_scale_by_scalar(ptr(x), dt(x), x.numel(), ptr(scalar_f32), stream()),
           "ct_scale_by_scalar")
 

@@ -151,7 +151,7 @@ def attn_mask_prep(attention_mask, n_head, mode, slopes=None):
     return kb.contiguous(), fv
 
 
-def _attn_core(q, k, v, scale, causal, causal_fill, kbias2):
+def _attn_core(q, k, v, scale, causal, causal_fill, kbias2, dropout=None):
     Sq, Sk = q.shape[2], k.shape[2]
     s2 = (q.float() @ k.float().transpose(2, 3)) * (scale * LOG2E)
     kb = kbias2[:, :, None, :] if kbias2 is not None else 0.0
@@ -165,30 +165,44 @@ def _attn_core(q, k, v, scale, causal, causal_fill, kbias2):
     mx = s2.max(-1, keepdim=True).values.detach()
     e = torch.exp2(s2 - mx)
     l = e.sum(-1, keepdim=True)
-    o = (e / l) @ v.float()
+    pr = e / l
+    if dropout is not None and dropout[0] > 0:  # after the softmax, survivors scaled (include/ct_b200.h: "dropout")
+        from oracle import ct_oracle as O
+        keep = O.dropout_mask_attention(q.shape[0], q.shape[1], Sq, Sk, *dropout)
+        pr = pr * keep / (1.0 - dropout[0])
+    o = pr @ v.float()
     return o, (mx + torch.log2(l)).squeeze(-1)
 
 
 def attn_fwd(q, k, v, scale, causal=False, causal_fill=-FLT_MAX, kbias2=None, first_valid=None, need_lse=True, impl=0,
-             seq_len_dev=None):
+             seq_len_dev=None, dropout=None):
     B, H, Sq, D = q.shape
     if seq_len_dev is not None:  # captured decode step: the key count is a device scalar, k / v are the whole capacity
         n = int(seq_len_dev[0])
         assert Sq == 1 and n <= k.shape[2]
         k, v = k[:, :, :n], v[:, :, :n]
         kbias2 = kbias2[:, :, :n] if kbias2 is not None else None
-    o, lse2 = _attn_core(q, k, v, scale, causal, causal_fill, kbias2)
+    o, lse2 = _attn_core(q, k, v, scale, causal, causal_fill, kbias2, dropout)
     return o.transpose(1, 2).reshape(B, Sq, H * D).to(q.dtype), (lse2 if need_lse else None)
 
 
 def attn_bwd(dout, q, k, v, o, lse2, dq, dk, dv, scale, causal=False, causal_fill=-FLT_MAX, kbias2=None,
-             first_valid=None, impl=0):
+             first_valid=None, impl=0, dropout=None):
     B, H, Sq, D = q.shape
     with torch.enable_grad():
         qr, kr, vr = [t.detach().float().clone().requires_grad_(True) for t in (q, k, v)]
-        out, _ = _attn_core(qr, kr, vr, scale, causal, causal_fill, kbias2)
+        out, _ = _attn_core(qr, kr, vr, scale, causal, causal_fill, kbias2, dropout)
         out.backward(dout.float().view(B, Sq, H, D).transpose(1, 2))
     dq.copy_(qr.grad); dk.copy_(kr.grad); dv.copy_(vr.grad)
+
+
+def dropout(x, p, seed, rng_stream, residual=None, out_dtype=None):
+    from oracle import ct_oracle as O
+    keep = O.dropout_mask_elementwise(x.shape, p, seed, rng_stream)
+    y = x.float() * keep / (1.0 - p)
+    if residual is not None:
+        y = y + residual.float()
+    return y.to(out_dtype or x.dtype)
 
 
 def embedding_fwd(ids, weight, out=None, accumulate=False):
@@ -337,7 +351,7 @@ def patched(compute_dtype=torch.float32):
     names = ["layernorm_fwd", "layernorm_bwd", "cast", "colsum", "act_fwd", "act_bwd", "gemm", "attn_mask_prep",
              "attn_fwd", "attn_bwd", "embedding_fwd", "embedding_bwd", "cross_entropy_fwd", "cross_entropy_fwd_stats",
              "scale_by_scalar", "lm_head_stats_ok", "lm_head_logits_with_stats", "adamw_step", "adamw_multi", "sgd_step", "kv_cache_append",
-             "kv_append_dev", "greedy_step"]
+             "kv_append_dev", "greedy_step", "dropout"]
     saved = {n: getattr(ops, n) for n in names}
     from cleantransformer_b200 import arena, generation, optimizer
     saved_gen = generation._on_device, generation._capture

@@ -1,0 +1,109 @@
+"""GPU parity for dropout inside the fused sites (transformer.py:47-50,108-116,
+modeling_gpt.py:93-96,136, modeling_bert.py attention / hidden dropout, modeling_bloom.py:111-113 + dropout_add).
+
+The reference draws its masks from torch's generator; which elements fall is not part of its contract. The product
+draws them from the counter-based generator of include/ct_b200.h, which oracle/ct_oracle.py restates (dropout_keep), so
+the tests hand the SAME masks to the reference arithmetic and compare values, not just statistics.
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+LOG2E = 1.4426950408889634
+FLT_MAX = 3.4028234663852886e38
+
+
+def _ops():
+    from cleantransformer_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("dtype,res_dtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32),
+                                             (torch.float16, None), (torch.bfloat16, torch.bfloat16)])
+def test_elementwise_dropout_kernel_matches_the_restated_generator(dtype, res_dtype):
+    from oracle import ct_oracle as O
+    ops = _ops()
+    torch.manual_seed(1)
+    x = torch.randn(7, 33, 129, device=DEV).to(dtype)
+    res = torch.randn(7, 33, 129, device=DEV).to(res_dtype) if res_dtype is not None else None
+    p, seed, stream = 0.1, 0x1234_5678_9ABC_DEF1, 77
+    y = ops.dropout(x, p, seed, stream, res, torch.float32)
+    keep = O.dropout_mask_elementwise(x.shape, p, seed, stream, device=DEV)
+    want = x.float() * keep / (1 - p) + (res.float() if res is not None else 0)
+    assert torch.allclose(y, want, rtol=1e-6, atol=1e-6)
+    frac = 1.0 - float(keep.float().mean())
+    assert abs(frac - p) < 0.01, frac
+    # another stream / seed gives another mask; p = 0 is the identity
+    assert not torch.equal(keep, O.dropout_mask_elementwise(x.shape, p, seed, stream + 1, device=DEV))
+    assert torch.equal(ops.dropout(x, 0.0, seed, stream, None, dtype), x)
+
+
+def _attn_ref(q, k, v, scale, causal, cfill, kb2, keep, p):
+    Sq, Sk = q.shape[2], k.shape[2]
+    s2 = (q.float() @ k.float().transpose(2, 3)) * (scale * LOG2E)
+    kb = kb2[:, :, None, :] if kb2 is not None else 0.0
+    s2 = s2 + kb
+    if causal:
+        i = torch.arange(Sq, device=q.device)[:, None]; j = torch.arange(Sk, device=q.device)[None, :]
+        fill = torch.full_like(s2, cfill * LOG2E if cfill > -1e30 else float("-inf")) + kb
+        s2 = torch.where(j > i + (Sk - Sq), fill, s2)
+    s2 = s2.clamp_min(-FLT_MAX)
+    pr = torch.softmax(s2 / LOG2E, dim=-1)
+    pr = pr * keep / (1 - p)          # torch.nn.Dropout on the probabilities (transformer.py:47-50)
+    o = pr @ v.float()
+    return o.transpose(1, 2).reshape(q.shape[0], Sq, -1)
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,D,causal,mode,cfill,impl", [
+    (2, 4, 12, 12, 8, True, 0, -FLT_MAX, 2),        # SIMT kernels (small head)
+    (2, 3, 40, 40, 32, False, 2, -FLT_MAX, 2),
+    (2, 4, 256, 256, 64, False, None, -FLT_MAX, 1),  # tcgen05 kernels
+    (3, 4, 300, 300, 64, True, 0, -FLT_MAX, 1),      # Bloom: ALiBi + causal + right padding, ragged
+    (3, 4, 300, 300, 64, True, 1, -1e4, 1),          # GPT: -1e4 replace + finfo.min, left padding
+    (2, 12, 512, 512, 64, False, 2, -FLT_MAX, 1),    # BERT-base head geometry, additive mask
+])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_attention_probability_dropout_fwd_bwd(B, H, Sq, Sk, D, causal, mode, cfill, impl, dtype):
+    from oracle import ct_oracle as O
+    ops = _ops()
+    if dtype == torch.float16 and impl == 2:
+        pytest.skip("f16 operands: tcgen05 path only")
+    torch.manual_seed(11)
+    qkv = torch.randn(B, Sk, H, 3, D, device=DEV).to(dtype)
+    q = qkv[:, Sk - Sq:, :, 0, :].permute(0, 2, 1, 3); k = qkv[..., 1, :].permute(0, 2, 1, 3); v = qkv[..., 2, :].permute(0, 2, 1, 3)
+    kb2 = fv = None
+    if mode is not None:
+        mask = torch.ones(B, Sk, dtype=torch.long, device=DEV)
+        for b in range(B):
+            n = Sk - (b * 37) % (Sk // 2 + 1)
+            if mode == 1:
+                mask[b, :Sk - n] = 0
+            else:
+                mask[b, n:] = 0
+        kb2, fv = ops.attn_mask_prep(mask, H, mode, O.alibi_slopes(H).to(DEV) if mode == 0 else None)
+    p, seed, stream = 0.1, 987654321012345, 5
+    drop = (p, seed, stream)
+    scale = 1.0 / math.sqrt(D)
+    o, lse2 = ops.attn_fwd(q, k, v, scale, causal, cfill, kb2, fv, impl=impl, dropout=drop)
+    o0, lse0 = ops.attn_fwd(q, k, v, scale, causal, cfill, kb2, fv, impl=impl)
+    assert torch.equal(lse2, lse0), "the softmax statistics do not see the dropout"
+    assert not torch.equal(o, o0)
+    keep = O.dropout_mask_attention(B, H, Sq, Sk, p, seed, stream, device=DEV)
+    kbe = kb2.expand(B, H, Sk) if kb2 is not None else None
+    qr, kr, vr = [t.float().detach().requires_grad_(True) for t in (q, k, v)]
+    ref = _attn_ref(qr, kr, vr, scale, causal, cfill, kbe, keep, p)
+    assert rel_err(o, ref) < 6e-3
+    do = torch.randn_like(ref).to(dtype)
+    dqkv = torch.zeros_like(qkv)
+    dq = dqkv[:, Sk - Sq:, :, 0, :].permute(0, 2, 1, 3); dk = dqkv[..., 1, :].permute(0, 2, 1, 3); dv = dqkv[..., 2, :].permute(0, 2, 1, 3)
+    ops.attn_bwd(do, q, k, v, o, lse2, dq, dk, dv, scale, causal, cfill, kb2, fv, impl=impl, dropout=drop)
+    ref.backward(do.float())
+    assert rel_err(dq, qr.grad) < 1e-2 and rel_err(dk, kr.grad) < 1e-2 and rel_err(dv, vr.grad) < 1e-2
+    # p = 0 through the same entry point is the plain kernel, bit for bit
+    o_p0, _ = ops.attn_fwd(q, k, v, scale, causal, cfill, kb2, fv, impl=impl, dropout=(0.0, seed, stream))
+    assert torch.equal(o_p0, o0)

@@ -339,3 +339,73 @@ def test_fused_lm_head_statistics_match_the_two_kernel_path():
     assert torch.equal(lg0, lg1)
     for n in g0:
         assert rel_err(g1[n], g0[n]) < 2e-3, n
+
+
+def test_fp16_autocast_gradscaler_recipe_vs_oracle():
+    """examples/ft_bloom_DDP.py:108-128 — the recipe scripts/ft_bloom_DDP.sh launches: torch.cuda.amp.autocast() (fp16)
+    + GradScaler around the model, `scaler.scale(loss).backward(); scaler.step(optimizer); scaler.update()`.
+    Three steps of a d=64 Bloom on our path (fp16 kernels, the scaled upstream gradient entering the fused
+    LM-head/CE node, GradScaler unscaling the arena gradients in place, TorchAdamW) against the oracle under the same
+    recipe with torch.optim.AdamW; then an overflowing scale: the step must be skipped (parameters bit-identical) and
+    the scale halved, exactly as with the reference's optimizer."""
+    from cleantransformer_b200.models import modeling_bloom as mb
+    from cleantransformer_b200 import optimizer as opt
+    from oracle import ct_oracle as O
+    torch.manual_seed(4242)
+    cfg = dict(vocab_size=1024, hidden_size=256, n_layer=2, num_attention_heads=4, layer_norm_epsilon=1e-5)
+    model = mb.BloomForCausalLM(mb.BloomConfig(**cfg)).to(DEV)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() >= 2:
+                p.normal_(0, 0.02)
+    model._tie_weight()
+    model.train()
+    B, S = 4, 192
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(3, 1024, (B, S), generator=g)
+    mask = torch.ones(B, S, dtype=torch.long)
+    for b, n in enumerate([192, 150, 97, 180]):
+        mask[b, n:] = 0
+        ids[b, n:] = 3
+    ids, mask = ids.to(DEV), mask.to(DEV)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items() if k != "lm_head.weight"}
+    init = {k: v.detach().clone() for k, v in sd.items()}
+    optim = opt.TorchAdamW(model.parameters(), lr=1e-3)
+    optim_o = torch.optim.AdamW(list(sd.values()), lr=1e-3)
+    scaler, scaler_o = torch.amp.GradScaler("cuda"), torch.amp.GradScaler("cuda")
+    for step in range(3):
+        optim.zero_grad()
+        with torch.autocast("cuda", dtype=torch.float16):
+            (loss, _, _), _ = model(input_ids=ids, attention_mask=mask, labels=ids)
+        scaler.scale(loss).backward()
+        scaler.step(optim)
+        scaler.update()
+        optim_o.zero_grad()
+        with torch.autocast("cuda", dtype=torch.float16):
+            (l_o, _, _), _ = O.bloom_causal_lm(ids, mask, sd, 2, 4, 1e-5, labels=ids, training=True)
+        scaler_o.scale(l_o).backward()
+        scaler_o.step(optim_o)
+        scaler_o.update()
+        assert torch.isfinite(loss) and abs(float(loss) - float(l_o)) / float(l_o) < 2e-3, (step, float(loss), float(l_o))
+        assert scaler.get_scale() == scaler_o.get_scale()
+    for name, p in model.named_parameters():
+        key = "bloom.word_embeddings.weight" if name == "lm_head.weight" else name
+        if p.dim() < 2:
+            continue
+        # three Adam steps: every element moved by about 3 * lr, in the direction of its gradient's sign; the two fp16
+        # paths must agree on the direction of the update as a whole
+        d_ours, d_ref = (p.detach() - init[key]).flatten(), (sd[key].detach() - init[key]).flatten()
+        cos = float(torch.dot(d_ours, d_ref) / (d_ours.norm() * d_ref.norm()))
+        assert cos > 0.95, (name, cos)
+    # overflow: inf gradients -> optimizer step skipped, scale halved
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    big = torch.amp.GradScaler("cuda", init_scale=2.0 ** 40)
+    optim.zero_grad()
+    with torch.autocast("cuda", dtype=torch.float16):
+        (loss, _, _), _ = model(input_ids=ids, attention_mask=mask, labels=ids)
+    big.scale(loss).backward()
+    big.step(optim)
+    big.update()
+    assert big.get_scale() == 2.0 ** 39
+    for n, p in model.named_parameters():
+        assert torch.equal(p.detach(), before[n]), n

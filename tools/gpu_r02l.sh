@@ -7,6 +7,8 @@ echo "== decode tests"; date
 timeout 900 python -m pytest tests/test_gpu_decode.py -m gpu -q -x > $OUT/${TAG}_decode_tests.log 2>&1; echo "decode rc=$?"; tail -25 $OUT/${TAG}_decode_tests.log
 echo "== whole GPU suite"; date
 timeout 1500 python -m pytest tests -m gpu -q > $OUT/${TAG}_tests.log 2>&1; echo "suite rc=$?"; tail -8 $OUT/${TAG}_tests.log
+echo "== opt-in tests"; date
+CT_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_models.py -m gpu -q -k "graphed_train_step or fused_lm_head" > $OUT/${TAG}_optin_tests.log 2>&1; echo "optin rc=$?"; tail -15 $OUT/${TAG}_optin_tests.log
 echo "== decode profile"; date
 timeout 600 python tools/decode_prof.py $OUT/${TAG}_decode_prof.json > $OUT/${TAG}_decode_prof.log 2>&1; echo "prof rc=$?"; head -60 $OUT/${TAG}_decode_prof.log | cut -c1-200
 echo "== bench arms"; date
