@@ -505,15 +505,18 @@ def run_gpt2_decode(args):
         return model.generate(ids_h.to(dev, non_blocking=True), attention_mask=mask_h.to(dev, non_blocking=True),
                               generation_configs=gc).cpu()
 
+    per_gen = []
+
     def timed(fn, k):
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(k):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
+        evs[0].record()
+        for i in range(k):
             out = fn()
-        e1.record()
+            evs[i + 1].record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1), out
+        per_gen.append([evs[i].elapsed_time(evs[i + 1]) for i in range(k)])
+        return evs[0].elapsed_time(evs[k]), out
 
     steps, warm = max(1, min(args.steps, 5)), max(args.warmup, 3)
     for _ in range(warm):
@@ -557,6 +560,7 @@ def run_gpt2_decode(args):
             "e2e": {"value": B * NEW * steps / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 2 * B * P * 8,
                     "d2h_bytes_per_step": B * (P + NEW) * 8, "ms_per_step": ms_e2e / steps},
             "gpu_launches": launches, "clocks": sampler.summary(),
+            "ms_per_generation": {"resident": per_gen[0], "e2e": per_gen[1]},
             "roofline": {"bound": "hbm", "kernel": "decode token-step (weight-streaming GEMMs + cache attention)",
                          "achieved": alg * steps / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": alg * steps / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,

@@ -59,6 +59,7 @@ class AttnArgs(ctypes.Structure):
         ("impl", ctypes.c_int32),
         ("seq_len_dev", c_void_p),
         ("dropout_p", c_float), ("rng_stream", ctypes.c_uint32), ("rng_seed", ctypes.c_uint64),
+        ("k_new", c_void_p), ("v_new", c_void_p), ("kn_sb", c_i64), ("kn_sh", c_i64), ("vn_sb", c_i64), ("vn_sh", c_i64),
     ]
 
 

@@ -76,6 +76,8 @@ struct AttnP {
   float* lse2;
   const int32_t* sk_dev;  // decode from a CUDA graph: the number of cached keys lives in device memory (else null)
   DropKey drop;           // attention-probability dropout (thr == 0: off); element (b,h,i,j): hi = b*H + h, lo = i*Sk + j
+  const uint16_t *k_new, *v_new;  // decode: the new token's rows, stored into cache row Sk - 1 by the kernel (else null)
+  int64_t kn_sb, kn_sh, vn_sb, vn_sh;
 };
 
 // score in the log2 domain for element (query i, key j) given the raw dot product
@@ -1175,6 +1177,20 @@ __global__ void __launch_bounds__(DEC_WARPS * 32)
   const int h = (int)(blockIdx.x % p.H), b = (int)(blockIdx.x / p.H);
   const int Sk = p.sk_dev ? min(*p.sk_dev, p.Sk) : p.Sk;  // p.Sk is the capacity when the count is on the device
   const int sub = lane / LPK, part = lane % LPK;  // key sub-slot inside a group, 16-byte piece of the row
+  if (p.k_new) {
+    // the reference's torch.concat((past, new)): this CTA owns cache rows (b, h, :), so it stores the new token's key and
+    // value at row Sk - 1 itself and reads them back after the barrier like any other cached row
+    if (Sk >= 1 && threadIdx.x < 2 * LPK) {
+      const int which = threadIdx.x / LPK, pc = threadIdx.x % LPK;
+      const uint16_t* src = which == 0 ? p.k_new + (int64_t)b * p.kn_sb + (int64_t)h * p.kn_sh
+                                       : p.v_new + (int64_t)b * p.vn_sb + (int64_t)h * p.vn_sh;
+      uint16_t* dst = which == 0
+          ? const_cast<uint16_t*>(reinterpret_cast<const uint16_t*>(sp.k)) + (int64_t)b * sp.k_sb + (int64_t)h * sp.k_sh + (int64_t)(Sk - 1) * sp.k_ss
+          : const_cast<uint16_t*>(reinterpret_cast<const uint16_t*>(sp.v)) + (int64_t)b * sp.v_sb + (int64_t)h * sp.v_sh + (int64_t)(Sk - 1) * sp.v_ss;
+      *reinterpret_cast<uint4*>(dst + pc * 8) = *reinterpret_cast<const uint4*>(src + pc * 8);
+    }
+    __syncthreads();
+  }
   auto unpack2 = [&](uint32_t w) {
     return p.fmt == 1 ? unpack_bf16x2(w) : __half22float2(*reinterpret_cast<const __half2*>(&w));
   };
@@ -1549,6 +1565,8 @@ static void fill_common(AttnP& p, const ct_attn_args& a) {
   p.lse2 = a.lse2;
   p.sk_dev = a.seq_len_dev;
   p.drop = make_drop_key(a.dropout_p, a.rng_seed, a.rng_stream);
+  p.k_new = (const uint16_t*)a.k_new; p.v_new = (const uint16_t*)a.v_new;
+  p.kn_sb = a.kn_sb; p.kn_sh = a.kn_sh; p.vn_sb = a.vn_sb; p.vn_sh = a.vn_sh;
 }
 
 static int check_args(const ct_attn_args& a, const char* who) {
@@ -1629,6 +1647,10 @@ extern "C" int ct_attn_fwd(const ct_attn_args* args, void* stream) {
   const bool decode = a.Sq == 1 && (a.D == 32 || a.D == 64 || a.D == 128) && a.lse2 == nullptr &&
                       tma_ok4(a.q, a.q_sb, a.q_sh, 8) && tma_ok4(a.k, a.k_sb, a.k_sh, a.k_ss) &&
                       tma_ok4(a.v, a.v_sb, a.v_sh, a.v_ss);
+  CT_REQUIRE((a.k_new == nullptr) == (a.v_new == nullptr), CT_ERR_BAD_ARG, "ct_attn_fwd: k_new and v_new come together");
+  CT_REQUIRE(a.k_new == nullptr || (decode && (((uintptr_t)a.k_new | (uintptr_t)a.v_new) & 15) == 0 &&
+                                    ((a.kn_sb | a.kn_sh | a.vn_sb | a.vn_sh) & 7) == 0),
+             CT_ERR_UNSUPPORTED, "ct_attn_fwd: k_new / v_new need the q_len = 1 decode kernel and 16-byte aligned rows");
   CT_REQUIRE(a.seq_len_dev == nullptr || decode, CT_ERR_UNSUPPORTED,
              "ct_attn_fwd: a device-side key count needs the q_len = 1 decode kernel (head_dim 32 / 64 / 128, 16-byte "
              "aligned rows, no lse output)");

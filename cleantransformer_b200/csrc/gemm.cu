@@ -1131,7 +1131,7 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
 constexpr int SK_WARPS = 8;
 
 template <int G>
-__global__ void __launch_bounds__(SK_WARPS * 32)
+__global__ void __launch_bounds__(SK_WARPS * 32, 2)
     gemm_skinny_kernel(const uint16_t* __restrict__ A, int64_t lda, const uint16_t* __restrict__ B, int64_t ldb,
                        int bf16, int K, const EpiParams e) {
   constexpr int FT = 8 * G;  // output features per CTA
@@ -1145,6 +1145,18 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
   const uint16_t* xrow[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) xrow[i] = A + (int64_t)min(g + 8 * i, e.M - 1) * lda + q * 8;
+  // the epilogue's operands are requested before the weight stream so that they do not add a second memory round trip
+  constexpr int EPT = (32 * FT) / (SK_WARPS * 32);  // output elements per thread
+  const bool lean = !e.preact && !e.actgrad_src && e.beta == 0.f && !e.atomic_out;
+  float ep_bias[EPT], ep_res[EPT];
+#pragma unroll
+  for (int it = 0; it < EPT; ++it) {
+    const int idx = threadIdx.x + it * SK_WARPS * 32;
+    const int tok = idx / FT, n = n0 + idx % FT;
+    const bool ok = tok < e.M && n < e.N;
+    ep_bias[it] = (lean && ok && e.bias) ? __ldg(e.bias + n) : 0.f;
+    ep_res[it] = (lean && ok && e.residual) ? ld_elem(e.residual, e.res_dtype, (int64_t)tok * e.ldr + n) : 0.f;
+  }
   float acc[G][2][4];
 #pragma unroll
   for (int j = 0; j < G; ++j)
@@ -1153,7 +1165,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[j][t][c] = 0.f;
   const int chunks = K >> 5;
-  constexpr int U = G >= 4 ? 2 : 4;  // chunks in flight per warp: (G + 4) * U 16-byte loads per lane
+  constexpr int U = G >= 2 ? 2 : 4;  // chunks in flight per warp: (G + 4) * U 16-byte loads per lane
   for (int c0 = wib; c0 < chunks; c0 += SK_WARPS * U) {
     uint4 w[U][G], x[U][4];
 #pragma unroll
@@ -1190,7 +1202,9 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
       for (int c = 0; c < 4; ++c) red[wib][(j * 2 + t) * 4 + c][lane] = acc[j][t][c];
   __syncthreads();
   // element (token, feature) of the CTA tile lives in fragment slot (j, t, c) of lane (gg, qq)
-  for (int idx = threadIdx.x; idx < 32 * FT; idx += SK_WARPS * 32) {
+#pragma unroll
+  for (int it = 0; it < EPT; ++it) {
+    const int idx = threadIdx.x + it * SK_WARPS * 32;
     const int tok = idx / FT, f = idx % FT;
     if (tok >= e.M || n0 + f >= e.N) continue;
     const int j = f >> 3, qq = (f & 7) >> 1, t = tok >> 4, gg = tok & 7;
@@ -1199,7 +1213,13 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
     float v = 0.f;
 #pragma unroll
     for (int wv = 0; wv < SK_WARPS; ++wv) v += red[wv][slot][ln];
-    epi_scalar(e, tok, n0 + f, v, true);
+    if (lean) {  // bias, activation, residual: the decode step's epilogues
+      v = fmaf(e.alpha, v, ep_bias[it]);
+      if (e.act != ACT_NONE) v = act_apply_call(v, e.act);
+      st_elem(e.C, e.c_dtype, (int64_t)tok * e.ldc + n0 + f, v + ep_res[it]);
+    } else {
+      epi_scalar(e, tok, n0 + f, v, true);
+    }
   }
 }
 

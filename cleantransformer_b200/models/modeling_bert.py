@@ -81,15 +81,16 @@ class BertTransformerBlock(torch.nn.Module):
         hidden_states = hidden_states if hidden_states.dtype == torch.float32 else hidden_states.float()
         ctx = self.attention(hidden_states, attention_mask)
         post = self.attention_post[0]
-        if _drop_on(self.attention_post[1]):
-            a = self.attention_post[1](F.linear(ctx, post.weight, post.bias, out_dtype=torch.float32))
-            s1 = a + hidden_states
+        if _drop_on(self.attention_post[1]):  # modeling_bert.py:253-256: dropout(linear) + hidden, then LayerNorm
+            a = F.linear(ctx, post.weight, post.bias, out_dtype=torch.float32)
+            s1 = F.dropout(a, self.attention_post[1].p, True, residual=hidden_states)
         else:
             s1 = F.linear(ctx, post.weight, post.bias, residual=hidden_states)
         n1, n1_low = self.norm1(s1, out_dtype=torch.float32, out2_dtype=cd)
         h = F.linear(n1_low, self.ffw[0].weight, self.ffw[0].bias, act=_ACT_ID[self.config.hidden_act])
-        if _drop_on(self.dropout):
-            s2 = self.dropout(F.linear(h, self.ffw[2].weight, self.ffw[2].bias, out_dtype=torch.float32)) + n1
+        if _drop_on(self.dropout):  # modeling_bert.py:259-262
+            f = F.linear(h, self.ffw[2].weight, self.ffw[2].bias, out_dtype=torch.float32)
+            s2 = F.dropout(f, self.dropout.p, True, residual=n1)
         else:
             s2 = F.linear(h, self.ffw[2].weight, self.ffw[2].bias, residual=n1)
         return self.norm2(s2)
@@ -122,7 +123,8 @@ class BertModel(torch.nn.Module):
         emb = F.embedding_sum([input_ids, segment_ids, position_ids[None, :] if position_ids.dim() == 1 else position_ids],
                               [self.word_embeddings.weight, self.segment_embeddings.weight,
                                self.position_embeddings.weight], padding_idx0=0)
-        hidden_states = self.embedding_post(emb)
+        hidden_states = self.embedding_post[0](emb)
+        hidden_states = F.dropout(hidden_states, self.embedding_post[1].p, _drop_on(self.embedding_post[1]))
         kb = None
         if attention_mask is not None:
             kb2, _ = ops.attn_mask_prep(attention_mask, self.config.num_attention_heads, ops.MASK_BERT)
@@ -154,7 +156,7 @@ class BertForSequenceClassification(torch.nn.Module):
 
     def forward(self, input_ids=None, attention_mask=None, segment_ids=None, position_ids=None):
         hidden_states, pooled_output = self.bert(input_ids, attention_mask, segment_ids, position_ids)
-        pooled_output = self.drop(pooled_output)
+        pooled_output = F.dropout(pooled_output, self.drop.p, _drop_on(self.drop))
         return F.linear(pooled_output, self.classifier.weight, self.classifier.bias, out_dtype=torch.float32)
 
 

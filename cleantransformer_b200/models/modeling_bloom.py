@@ -128,8 +128,9 @@ class BloomAttentionLayer(torch.nn.Module):
     def forward(self, hidden_states, residual, alibi, k_v_past=None, attention_mask=None, head_mask=None):
         if self.pretraining_tp > 1 and self.slow_but_exact:
             raise Exception("pretraining_tp and slow_but_exact not supported yet")
-        if self.training and (self.attention_dropout.p > 0 or self.hidden_dropout > 0):
-            raise NotImplementedError("Bloom dropout > 0 in training mode is not supported by the fused path")
+        # modeling_bloom.py:111 (probabilities, inside the kernel) and :121-123 (residual + dropout(dense))
+        a_drop = F.next_dropout(self.attention_dropout.p) if (self.training and self.attention_dropout.p > 0) else None
+        h_on = self.training and self.hidden_dropout > 0
         F.reject_head_mask(head_mask)
         bsz, q_len, _ = hidden_states.shape
         bias = alibi if isinstance(alibi, AttnBias) else \
@@ -138,15 +139,16 @@ class BloomAttentionLayer(torch.nn.Module):
         if isinstance(k_v_past, ops.StaticKV):
             # captured decode step (generation.py): device-side cache position / length
             q, k, v = F.split_packed(qkv, self.num_heads, F.LAYOUT_BLOOM)
-            ops.kv_append_dev(k_v_past.k, k, k_v_past.len_dev)
-            ops.kv_append_dev(k_v_past.v, v, k_v_past.len_dev)
             ctx, _ = ops.attn_fwd(q, k_v_past.k, k_v_past.v, self.inv_norm_factor, bias.causal, -ops.FLT_MAX,
-                                  bias.kbias2, bias.first_valid, need_lse=False, seq_len_dev=k_v_past.len_dev)
+                                  bias.kbias2, bias.first_valid, need_lse=False, seq_len_dev=k_v_past.len_dev,
+                                  kv_new=(k, v))  # the kernel appends k, v itself
             out = F.linear(ctx, self.dense.weight, self.dense.bias, residual=residual)
             return out, k_v_past
+        if a_drop is not None and not (k_v_past is None and torch.is_grad_enabled() and qkv.requires_grad):
+            raise NotImplementedError("attention dropout in training mode with a KV cache / without autograd")
         if k_v_past is None and torch.is_grad_enabled() and qkv.requires_grad:
             ctx = F.PackedAttentionFn.apply(qkv, self.num_heads, F.LAYOUT_BLOOM, self.inv_norm_factor,
-                                            bias.causal, -ops.FLT_MAX, bias.kbias2, bias.first_valid)
+                                            bias.causal, -ops.FLT_MAX, bias.kbias2, bias.first_valid, a_drop)
             _, k, v = F.split_packed(qkv.detach(), self.num_heads, F.LAYOUT_BLOOM)
         else:
             q, k, v = F.split_packed(qkv, self.num_heads, F.LAYOUT_BLOOM)
@@ -159,7 +161,11 @@ class BloomAttentionLayer(torch.nn.Module):
                 v = torch.cat((k_v_past[1], v), dim=-2)
             ctx = F.attention_cached(q, k, v, self.inv_norm_factor, bias.causal, -ops.FLT_MAX,
                                      bias.kbias2, bias.first_valid)
-        out = F.linear(ctx, self.dense.weight, self.dense.bias, residual=residual)
+        if h_on:
+            out = F.dropout(F.linear(ctx, self.dense.weight, self.dense.bias, out_dtype=torch.float32),
+                            self.hidden_dropout, True, residual=residual)
+        else:
+            out = F.linear(ctx, self.dense.weight, self.dense.bias, residual=residual)
         return out, (k, v)
 
 
@@ -177,9 +183,10 @@ class BloomMLP(torch.nn.Module):
         self.hidden_dropout = config.hidden_dropout
 
     def forward(self, hidden_states, residual):
-        if self.training and self.hidden_dropout > 0:
-            raise NotImplementedError("Bloom dropout > 0 in training mode is not supported by the fused path")
         h = F.linear(hidden_states, self.dense_h_to_4h.weight, self.dense_h_to_4h.bias, act=ops.ACT_GELU_TANH)
+        if self.training and self.hidden_dropout > 0:  # modeling_bloom.py:269: residual + dropout(dense_4h_to_h(...))
+            return F.dropout(F.linear(h, self.dense_4h_to_h.weight, self.dense_4h_to_h.bias, out_dtype=torch.float32),
+                             self.hidden_dropout, True, residual=residual)
         return F.linear(h, self.dense_4h_to_h.weight, self.dense_4h_to_h.bias, residual=residual)
 
 

@@ -114,9 +114,9 @@ class AttentionLayer(torch.nn.Module):
     def forward(self, hidden_states, k_v_past=None, attention_mask=None, head_mask=None, residual=None):
         """`residual` (extension): when given, `residual + c_proj(ctx)` is produced by the GEMM
         epilogue and returned instead of the bare projection."""
-        if self.training and (self.attn_dropout.p > 0 or self.resid_dropout.p > 0):
-            raise NotImplementedError("GPT dropout > 0 in training mode is not supported by the fused "
-                                      "path; call .eval() (the reference's own tests do, SURVEY §8 d2)")
+        # modeling_gpt.py:93-96,107: dropout on the attention probabilities (inside the kernel) and on the projection
+        a_drop = F.next_dropout(self.attn_dropout.p) if (self.training and self.attn_dropout.p > 0) else None
+        r_on = self.training and self.resid_dropout.p > 0
         F.reject_head_mask(head_mask)
         bsz, q_len, _ = hidden_states.shape
         head_dim = self.n_state // self.n_head
@@ -128,14 +128,14 @@ class AttentionLayer(torch.nn.Module):
         if isinstance(k_v_past, ops.StaticKV):
             # captured decode step (generation.py): append at the device-side position, attend over the device-side length
             q, k, v = F.split_packed(qkv, self.n_head, F.LAYOUT_GPT)
-            ops.kv_append_dev(k_v_past.k, k, k_v_past.len_dev)
-            ops.kv_append_dev(k_v_past.v, v, k_v_past.len_dev)
             ctx, _ = ops.attn_fwd(q, k_v_past.k, k_v_past.v, sm_scale, True, -1e4, kb, fv, need_lse=False,
-                                  seq_len_dev=k_v_past.len_dev)
+                                  seq_len_dev=k_v_past.len_dev, kv_new=(k, v))  # the kernel appends k, v itself
             out = self.c_proj(ctx, residual=residual, out_dtype=None if residual is not None else torch.float32)
             return out, k_v_past
+        if a_drop is not None and not (k_v_past is None and torch.is_grad_enabled() and qkv.requires_grad):
+            raise NotImplementedError("attention dropout in training mode with a KV cache / without autograd")
         if k_v_past is None and torch.is_grad_enabled() and qkv.requires_grad:
-            ctx = F.PackedAttentionFn.apply(qkv, self.n_head, F.LAYOUT_GPT, sm_scale, True, -1e4, kb, fv)
+            ctx = F.PackedAttentionFn.apply(qkv, self.n_head, F.LAYOUT_GPT, sm_scale, True, -1e4, kb, fv, a_drop)
             _, k, v = F.split_packed(qkv.detach(), self.n_head, F.LAYOUT_GPT)
         else:
             q, k, v = F.split_packed(qkv, self.n_head, F.LAYOUT_GPT)
@@ -147,7 +147,10 @@ class AttentionLayer(torch.nn.Module):
                 k = torch.cat((k_v_past[0], k), dim=-2)
                 v = torch.cat((k_v_past[1], v), dim=-2)
             ctx = F.attention_cached(q, k, v, sm_scale, True, -1e4, kb, fv)
-        out = self.c_proj(ctx, residual=residual, out_dtype=None if residual is not None else torch.float32)
+        if r_on:  # residual + dropout(c_proj(ctx)) (the caller's add, TransformerBlock.forward) as one kernel
+            out = F.dropout(self.c_proj(ctx, out_dtype=torch.float32), self.resid_dropout.p, True, residual=residual)
+        else:
+            out = self.c_proj(ctx, residual=residual, out_dtype=None if residual is not None else torch.float32)
         return out, (k, v)
 
 
@@ -170,10 +173,9 @@ class TransformerBlock(torch.nn.Module):
         self.norm2 = LayerNorm(n_embd, eps=config.layer_norm_epsilon)
 
     def _mlp(self, x, residual):
-        if self.training and self.mlp[3].p > 0:
-            raise NotImplementedError("GPT MLP Dropout(0.5) in training mode is not supported by the fused "
-                                      "path; call .eval()")
         h = self.mlp[0](x, act=_ACT_ID[self.afn])
+        if self.training and self.mlp[3].p > 0:  # modeling_gpt.py:136: torch.nn.Dropout() (p = 0.5) closes the MLP
+            return F.dropout(self.mlp[2](h, out_dtype=torch.float32), self.mlp[3].p, True, residual=residual)
         return self.mlp[2](h, residual=residual)
 
     def forward(self, x, attn_output=None, attention_mask=None, head_mask=None, k_v_past=None):
@@ -230,7 +232,7 @@ class GPTModel(torch.nn.Module):
         if segment_ids is not None:
             ids.append(segment_ids.view(-1, segment_ids.size(-1)))
             tables.append(self.tokens_embed.weight)
-        hidden_states = self.drop(F.embedding_sum(ids, tables))
+        hidden_states = F.dropout(F.embedding_sum(ids, tables), self.drop.p, self.training and self.drop.p > 0)
         for i, block in enumerate(self.blocks):
             hidden_states, k_v_pasts[i] = block(hidden_states, attention_mask=mask, k_v_past=k_v_pasts[i])
         if self.version == 'gpt':

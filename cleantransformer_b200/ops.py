@@ -342,7 +342,7 @@ def _bhsd_strides(t):
 
 
 def _fill_attn(a, q, k, v, o, lse2, scale, causal, causal_fill, kbias2, first_valid, impl, seq_len_dev=None,
-               dropout=None):
+               dropout=None, kv_new=None):
     B, H, Sq, D = q.shape
     Sk = k.shape[2]
     a.B, a.H, a.Sq, a.Sk, a.D = B, H, Sq, Sk, D
@@ -363,6 +363,14 @@ def _fill_attn(a, q, k, v, o, lse2, scale, causal, causal_fill, kbias2, first_va
     a.first_valid = ptr(first_valid)
     a.impl = impl
     a.seq_len_dev = ptr(seq_len_dev)
+    if kv_new is not None:  # decode: [B,H,1,D] views of the new token's key / value, appended by the kernel
+        kn, vn = kv_new
+        assert kn.shape[2] == 1 and vn.shape[2] == 1 and kn.stride(3) == 1 and vn.stride(3) == 1
+        a.k_new, a.v_new = kn.data_ptr(), vn.data_ptr()
+        a.kn_sb, a.kn_sh, a.vn_sb, a.vn_sh = kn.stride(0), kn.stride(1), vn.stride(0), vn.stride(1)
+    else:
+        a.k_new = a.v_new = None
+        a.kn_sb = a.kn_sh = a.vn_sb = a.vn_sh = 0
     if dropout is not None and dropout[0] > 0:  # (p, seed, stream): include/ct_b200.h "dropout"
         a.dropout_p, a.rng_seed, a.rng_stream = float(dropout[0]), int(dropout[1]) & (2 ** 64 - 1), int(dropout[2]) & 0xFFFFFFFF
     else:
@@ -370,18 +378,19 @@ def _fill_attn(a, q, k, v, o, lse2, scale, causal, causal_fill, kbias2, first_va
 
 
 def attn_fwd(q, k, v, scale, causal=False, causal_fill=-FLT_MAX, kbias2=None, first_valid=None,
-             need_lse=True, impl=0, seq_len_dev=None, dropout=None):
+             need_lse=True, impl=0, seq_len_dev=None, dropout=None, kv_new=None):
     """q [B,H,Sq,D], k/v [B,H,Sk,D] as strided VIEWS (D contiguous). Returns (o [B,Sq,H*D], lse2).
     seq_len_dev (int32 device scalar, q_len = 1 only): the number of valid cached keys is read on the device and Sk is
     only the capacity — what a captured decode step needs.
-    dropout = (p, seed, stream): attention-probability dropout after the softmax (include/ct_b200.h: "dropout")."""
+    dropout = (p, seed, stream): attention-probability dropout after the softmax (include/ct_b200.h: "dropout").
+    kv_new = (k_new, v_new) [B,H,1,D] (q_len = 1 only): stored into cache row (key count - 1) by the kernel itself."""
     _req_cuda(q, k, v)
     B, H, Sq, D = q.shape
     o = torch.empty((B, Sq, H * D), dtype=q.dtype, device=q.device)
     o4 = o.view(B, Sq, H, D).permute(0, 2, 1, 3)
     lse2 = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device) if need_lse else None
     a = AttnArgs()
-    _fill_attn(a, q, k, v, o4, lse2, scale, causal, causal_fill, kbias2, first_valid, impl, seq_len_dev, dropout)
+    _fill_attn(a, q, k, v, o4, lse2, scale, causal, causal_fill, kbias2, first_valid, impl, seq_len_dev, dropout, kv_new)
     _ck(_lib.load().ct_attn_fwd(ctypes.byref(a), stream()), "ct_attn_fwd")
     return o, lse2
 

@@ -8,9 +8,10 @@ with the reference) and forward signatures; the arithmetic is done by libct_b200
 `MultiHeadAttention` is exported as an alias of AttentionLayer (BASELINE.json's north_star uses
 that name; the reference only has it as a README heading).
 
-Dropout: the reference applies torch.nn.Dropout modules; they are kept as modules and are the
-identity in eval mode or with p = 0. With p > 0 in training mode the fused epilogues are bypassed
-for that site (the op is then LinearFn -> torch dropout -> add), see DESIGN.md.
+Dropout: the reference applies torch.nn.Dropout modules; they are kept as modules (p, train/eval state) and are the
+identity in eval mode or with p = 0. With p > 0 in training mode the attention kernel drops the probabilities itself
+(forward and backward regenerate the mask from a counter) and a hidden-state site runs ct_dropout, fused with the
+residual add that follows it, instead of the GEMM's residual epilogue (functional.dropout).
 """
 import math
 
@@ -72,9 +73,7 @@ class AttentionLayer(torch.nn.Module):
         return m.contiguous()
 
     def forward(self, hidden_states, attention_mask=None, head_mask=None):
-        if _dropout_active(self.dropout):
-            raise NotImplementedError("attention-probability dropout with p>0 in training mode is not "
-                                      "supported by the fused kernel; use eval() or p=0")
+        drop = F.next_dropout(self.dropout.p) if _dropout_active(self.dropout) else None  # transformer.py:47-50
         F.reject_head_mask(head_mask)
         b, s, _ = hidden_states.shape
         q = F.linear(hidden_states, self.q_linear.weight, self.q_linear.bias)
@@ -82,7 +81,7 @@ class AttentionLayer(torch.nn.Module):
         v = F.linear(hidden_states, self.v_linear.weight, self.v_linear.bias)
         kb = self.key_bias_from_additive(attention_mask, b, s)
         scale = 1.0 / math.sqrt(self.dim / self.m_head)
-        return F.SeparateAttentionFn.apply(q, k, v, self.m_head, scale, False, -ops.FLT_MAX, kb, None)
+        return F.SeparateAttentionFn.apply(q, k, v, self.m_head, scale, False, -ops.FLT_MAX, kb, None, drop)
 
 
 MultiHeadAttention = AttentionLayer
@@ -106,13 +105,13 @@ class TransformerBlock(torch.nn.Module):
 
     def forward(self, x):
         att_out = self.attention(x)
-        att_out = self.dropout(att_out)
-        # x + att: the residual add has no GEMM to ride on here (no out-projection): LayerNorm reads both
-        add_norm_out = self.norm1(x.float() + att_out.float())
+        on = _dropout_active(self.dropout)
+        # x + dropout(att): the residual add has no GEMM to ride on here (no out-projection)
+        add_norm_out = self.norm1(F.dropout(att_out, self.dropout.p, on, residual=x.float(), out_dtype=torch.float32))
         h = F.linear(add_norm_out, self.ffw[0].weight, self.ffw[0].bias, act=ops.ACT_RELU)
-        if _dropout_active(self.dropout):
-            ffw_out = self.dropout(F.linear(h, self.ffw[2].weight, self.ffw[2].bias, out_dtype=torch.float32))
-            return self.norm2(add_norm_out + ffw_out)
+        if on:
+            ffw_out = F.linear(h, self.ffw[2].weight, self.ffw[2].bias, out_dtype=torch.float32)
+            return self.norm2(F.dropout(ffw_out, self.dropout.p, True, residual=add_norm_out))
         summed = F.linear(h, self.ffw[2].weight, self.ffw[2].bias, residual=add_norm_out)
         return self.norm2(summed)
 

@@ -240,6 +240,12 @@ typedef struct {
   float dropout_p;     /* 0: none */
   uint32_t rng_stream; /* distinguishes the dropout sites / calls that share one seed */
   uint64_t rng_seed;
+  /* q_len = 1 decode only, nullable: the new token's key / value rows, element (b,h,d) at k_new + b*kn_sb + h*kn_sh + d.
+   * The kernel first stores them into cache row (key count - 1) of k / v (modeling_gpt.py:76-80, modeling_bloom.py:88-92:
+   * the torch.concat of the reference) and then attends — one launch instead of two appends and the attention. */
+  const void* k_new;
+  const void* v_new;
+  int64_t kn_sb, kn_sh, vn_sb, vn_sh;
 } ct_attn_args;
 int ct_attn_fwd(const ct_attn_args* args, void* stream);
 

@@ -175,11 +175,14 @@ def _attn_core(q, k, v, scale, causal, causal_fill, kbias2, dropout=None):
 
 
 def attn_fwd(q, k, v, scale, causal=False, causal_fill=-FLT_MAX, kbias2=None, first_valid=None, need_lse=True, impl=0,
-             seq_len_dev=None, dropout=None):
+             seq_len_dev=None, dropout=None, kv_new=None):
     B, H, Sq, D = q.shape
     if seq_len_dev is not None:  # captured decode step: the key count is a device scalar, k / v are the whole capacity
         n = int(seq_len_dev[0])
         assert Sq == 1 and n <= k.shape[2]
+        if kv_new is not None:  # the kernel stores the new token's rows at n - 1 before attending
+            k[:, :, n - 1:n] = kv_new[0]
+            v[:, :, n - 1:n] = kv_new[1]
         k, v = k[:, :, :n], v[:, :, :n]
         kbias2 = kbias2[:, :, :n] if kbias2 is not None else None
     o, lse2 = _attn_core(q, k, v, scale, causal, causal_fill, kbias2, dropout)

@@ -259,3 +259,28 @@ def test_conv1d_decode_step_uses_the_k_major_shadow_and_matches_the_full_path():
         y2 = lin(x, out_dtype=torch.float32)
         lin.bias.zero_()
     assert (y2 - 2 * y_dec).abs().max() <= 2e-2 * float(y_dec.abs().max())  # refreshed shadow (bias was zero-initialised)
+
+
+@pytest.mark.parametrize("D", [32, 64, 128])
+def test_decode_attention_appends_the_new_token_itself(D):
+    """ct_attn_args.k_new / v_new: the q_len = 1 kernel stores the new key / value at cache row (count - 1) and attends
+    in one launch — same output bits and same cache contents as ct_kv_append_dev followed by the attention."""
+    from cleantransformer_b200 import ops
+    torch.manual_seed(D)
+    B, H, CAP, n = 3, 5, 300, 131
+    q = torch.randn(B, H, 1, D, device=DEV).bfloat16()
+    qkv_new = torch.randn(B, 1, 2, H, D, device=DEV).bfloat16()          # strided views, like a packed projection
+    k_new, v_new = qkv_new[:, :, 0].permute(0, 2, 1, 3), qkv_new[:, :, 1].permute(0, 2, 1, 3)
+    k0 = torch.randn(B, H, CAP, D, device=DEV).bfloat16()
+    v0 = torch.randn(B, H, CAP, D, device=DEV).bfloat16()
+    kb = torch.randn(B, H, CAP, device=DEV)
+    n_dev = torch.tensor([n, 0, 0, 0, 0], dtype=torch.int32, device=DEV)
+    ka, va = k0.clone(), v0.clone()
+    ops.kv_append_dev(ka, k_new, n_dev)
+    ops.kv_append_dev(va, v_new, n_dev)
+    want, _ = ops.attn_fwd(q, ka, va, D ** -0.5, True, -1e4, kb, None, need_lse=False, seq_len_dev=n_dev)
+    kb_, vb_ = k0.clone(), v0.clone()
+    got, _ = ops.attn_fwd(q, kb_, vb_, D ** -0.5, True, -1e4, kb, None, need_lse=False, seq_len_dev=n_dev,
+                          kv_new=(k_new, v_new))
+    assert torch.equal(got, want) and torch.equal(kb_, ka) and torch.equal(vb_, va)
+    assert torch.equal(kb_[:, :, n - 1], k_new[:, :, 0]) and torch.equal(kb_[:, :, n:], k0[:, :, n:])

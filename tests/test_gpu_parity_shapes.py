@@ -281,6 +281,122 @@ def test_config2_bloom560m_layer_and_lm_head_full_shape_vs_oracle(fused_stats):
     _assert_case(case)
 
 
+def test_config5_bert_base_shape_train_mode_dropout_vs_oracle_with_the_same_masks():
+    """Config 5 as SURVEY d2 specifies it: hidden / attention dropout p = 0.1 in TRAIN mode (the reference's BertConfig
+    defaults). The product draws its masks from the counter-based generator of include/ct_b200.h; the oracle is handed
+    the same masks (oracle.DropoutFeeder), so logits, loss and every gradient are compared value for value, fp32 and
+    autocast, under the same bound as the dropout-free case."""
+    from cleantransformer_b200 import functional as F
+    from cleantransformer_b200.models import modeling_bert as mbert
+    from oracle import ct_oracle as O
+    cfg = mbert.BertConfig(num_hidden_layers=2, num_labels=28)   # hidden_dropout_prob = attention_probs_dropout_prob = 0.1
+    assert cfg.hidden_dropout_prob == 0.1 and cfg.attention_probs_dropout_prob == 0.1
+    model = mbert.BertForSequenceClassification(cfg).to(DEV).train()
+    _init(model)
+    B, S = 4, 512
+    g = torch.Generator().manual_seed(999)
+    ids = torch.randint(1, 30522, (B, S), generator=g)
+    mask = torch.ones(B, S)
+    for b, n in enumerate([512, 64, 300, 129]):
+        mask[b, n:] = 0
+        ids[b, n:] = 0
+    labels = torch.randint(0, 28, (B,), generator=g).to(DEV)
+    ids, mask = ids.to(DEV), mask.to(DEV)
+    seg = torch.zeros_like(ids)
+    pos = torch.arange(S, device=DEV)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    SEED = 20260
+
+    def oracle(autocast):
+        p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            lg, hid, pooled = O.bert_classifier(ids, mask, seg, pos, p, 2, 12, cfg.layer_norm_eps,
+                                                drop=O.DropoutFeeder(SEED), p_attn=0.1, p_hidden=0.1)
+        loss = torch.nn.functional.cross_entropy(lg.float(), labels)
+        loss.backward()
+        return lg.float(), loss, {k: t.grad for k, t in p.items()}
+
+    lg32, l32, g32 = oracle(False)
+    lg16, l16, g16 = oracle(True)
+    F.manual_dropout_seed(SEED)
+    logits = model(ids, mask, seg, pos)
+    loss = torch.nn.functional.cross_entropy(logits.float(), labels)
+    loss.backward()
+    case = "C5_bert_base_shape_2layer_dropout0.1_train"
+    _record(case, "logits", logits, lg32, lg16, 8e-3)
+    _record(case, "loss", loss, l32, l16, 1e-3)
+    for n, p in model.named_parameters():
+        ref = g32[n]
+        if p.grad is None:
+            assert ref is None or float(ref.abs().max()) == 0.0, n
+            continue
+        if n.endswith("k_linear.bias"):
+            scale = float(g32[n.replace("k_linear", "q_linear")].abs().max())
+            assert float(p.grad.abs().max()) <= 0.1 * scale, n
+            continue
+        floor = 1.8e-2 if (".q_linear." in n or ".k_linear." in n) else 1e-2
+        _record(case, "grad." + n, p.grad, ref, g16[n], floor)
+    _assert_case(case)
+    # the deterministic network is untouched by the dropout plumbing
+    with torch.no_grad():
+        lg_eval, _, _ = O.bert_classifier(ids, mask, seg, pos, sd, 2, 12, cfg.layer_norm_eps)
+        assert _err(model.eval()(ids, mask, seg, pos), lg_eval) < 8e-3
+    assert _err(logits, lg_eval) > 2e-2  # ... and the masks do change the training forward
+
+
+def test_gpt2_small_train_mode_dropout_vs_oracle_with_the_same_masks():
+    """GPT-2-small width (768 / 12 heads, 2 layers) in train mode as the reference builds it: embd / attn / resid dropout
+    0.1 (GPTConfig defaults) and the MLP's torch.nn.Dropout() at its default p = 0.5 (modeling_gpt.py:136)."""
+    from cleantransformer_b200 import functional as F
+    from cleantransformer_b200.models import modeling_gpt as mg
+    from oracle import ct_oracle as O
+    L = 2
+    cfgd = dict(vocab_size=5000, n_embd=768, n_positions=256, n_layer=L, n_head=12, n_ctx=256, afn="gelu_new")
+    model = mg.GPTLMHeadModel(mg.GPTConfig(**cfgd), version="gpt2").to(DEV)
+    _init(model)
+    model._tie_weights()
+    model.train()
+    assert model.gpt.drop.p == 0.1 and model.gpt.blocks[0].mlp[3].p == 0.5
+    B, S = 3, 200
+    g = torch.Generator().manual_seed(999)
+    ids = torch.randint(1, 5000, (B, S), generator=g)
+    mask = torch.ones(B, S, dtype=torch.long)
+    for b, n in enumerate([200, 150, 77]):     # LEFT padding
+        mask[b, :S - n] = 0
+        ids[b, :S - n] = 0
+    ids, mask = ids.to(DEV), mask.to(DEV)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items() if k != "lm_head.weight"}
+    SEED = 31337
+
+    def lm_loss(logits):
+        return torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]).float(), ids[:, 1:].reshape(-1))
+
+    def oracle(autocast):
+        p = {k: v.clone().requires_grad_(v.is_floating_point() and "attn.bias" not in k) for k, v in sd.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            (lg, _), _ = O.gpt_lm_head_model(ids, mask, p, L, 12, 256, 1e-5, version="gpt2", drop=O.DropoutFeeder(SEED),
+                                             p_embd=0.1, p_attn=0.1, p_resid=0.1, p_mlp=0.5)
+        loss = lm_loss(lg)
+        loss.backward()
+        return lg.float(), loss, {k: t.grad for k, t in p.items()}
+
+    lg32, l32, g32 = oracle(False)
+    lg16, l16, g16 = oracle(True)
+    F.manual_dropout_seed(SEED)
+    (logits, _), _ = model(ids, attention_mask=mask)
+    loss = lm_loss(logits)
+    loss.backward()
+    case = "GPT2_small_width_2layer_dropout_train"
+    _record(case, "logits", logits, lg32, lg16, 8e-3)
+    _record(case, "loss", loss, l32, l16, 1e-3)
+    for n, p in model.named_parameters():
+        key = "gpt.tokens_embed.weight" if n == "lm_head.weight" else n
+        if key not in g32 or g32[key] is None:
+            continue
+        _record(case, "grad." + n, p.grad, g32[key], g16[key], 1e-2)
+    _assert_case(case)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # C4 shape: greedy decoding, GPT-2-medium width, batch 32, left padded
 # ------------------------------------------------------------------------------------------------------------------

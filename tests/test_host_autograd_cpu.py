@@ -648,3 +648,130 @@ def test_captured_decode_host_logic_matches_the_loop_and_the_oracle(family, monk
         monkeypatch.setattr(generation, "POLL_EVERY", 2)
         ends = sorted(set(new[:, 4].tolist()))
         assert torch.equal(gen(False, end_ids=ends), gen(True, end_ids=ends))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Dropout in train mode: the host wiring — which site draws which stream of the counter-based
+# generator, the fused residual add, the backward regenerating the same mask — against the oracle given the SAME masks
+# (oracle.DropoutFeeder). The kernels themselves are checked on the GPU (tests/test_gpu_dropout.py).
+# ------------------------------------------------------------------------------------------------------------------
+def _grads_match(model, sd, rename=lambda n: n, tol=2e-3, at_least=10, floor=1e-9):
+    checked = 0
+    for name, p in model.named_parameters():
+        key = rename(name)
+        ref = sd[key].grad if key in sd else None
+        if ref is None:
+            continue
+        assert p.grad is not None, name
+        assert float((p.grad - ref).abs().max()) <= tol * float(ref.abs().max()) + floor, name
+        checked += 1
+    assert checked >= at_least
+
+
+def test_bert_train_mode_dropout_vs_oracle_with_the_same_masks(golden):
+    """BASELINE config 5 as SURVEY d2 specifies it: BERT with hidden / attention dropout p = 0.1 in train mode."""
+    from cleantransformer_b200 import functional as F
+    from cleantransformer_b200.models import modeling_bert as mbert
+    from oracle import ct_oracle as O
+    g = golden("bert_tiny")
+    cfg = dict(g["cfg"])
+    cfg["hidden_dropout_prob"], cfg["attention_probs_dropout_prob"] = 0.1, 0.2
+    ids, mask, seg, pos = g["ids"], g["mask"], g["seg"], g["pos"]
+    torch.manual_seed(5)
+    labels = torch.randint(0, cfg["num_labels"], (ids.shape[0],))
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["sd"].items()}
+    lg_ref, _, _ = O.bert_classifier(ids, mask, seg, pos, sd, cfg["num_hidden_layers"], cfg["num_attention_heads"],
+                                     cfg["layer_norm_eps"], drop=O.DropoutFeeder(777), p_attn=0.2, p_hidden=0.1)
+    torch.nn.functional.cross_entropy(lg_ref, labels).backward()
+    lg_eval, _, _ = O.bert_classifier(ids, mask, seg, pos, g["sd"], cfg["num_hidden_layers"],
+                                      cfg["num_attention_heads"], cfg["layer_norm_eps"])
+    assert rel_err(lg_ref.detach(), lg_eval) > 1e-2  # the masks do something
+    with mock_ops.patched():
+        model = mbert.BertForSequenceClassification(mbert.BertConfig(**cfg)).train()
+        model.load_state_dict(g["sd"], strict=True)
+        F.manual_dropout_seed(777)
+        logits = model(ids, mask, seg, pos)
+        torch.nn.functional.cross_entropy(logits.float(), labels).backward()
+        assert rel_err(logits, lg_ref) < 2e-4
+        _grads_match(model, sd, at_least=20)
+        # a second forward draws new masks (the stream counter moved on); eval() is the deterministic network again
+        assert rel_err(model(ids, mask, seg, pos), lg_ref) > 1e-3
+        assert rel_err(model.eval()(ids, mask, seg, pos), lg_eval) < 2e-4
+
+
+@pytest.mark.parametrize("version", ["gpt", "gpt2"])
+def test_gpt_train_mode_dropout_vs_oracle_with_the_same_masks(golden, version):
+    """GPT in train mode as the reference constructs it: embd / attn / resid dropout from the config and the MLP's
+    torch.nn.Dropout() with its default p = 0.5 (modeling_gpt.py:136)."""
+    from cleantransformer_b200 import functional as F
+    from cleantransformer_b200.models import modeling_gpt as mg
+    from oracle import ct_oracle as O
+    g = golden("gpt_tiny")
+    c, cfg = g[version], dict(g["cfg"])
+    cfg["embd_pdrop"], cfg["attn_pdrop"], cfg["resid_pdrop"] = 0.1, 0.15, 0.2
+    ids, mask = c["ids"], c["mask"]
+
+    def lm_loss(logits):
+        return torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]).float(), ids[:, 1:].reshape(-1))
+
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "attn.bias" not in k) for k, v in c["sd"].items()}
+    (lg_ref, _), _ = O.gpt_lm_head_model(ids, mask, sd, cfg["n_layer"], cfg["n_head"], cfg["n_ctx"],
+                                         cfg["layer_norm_epsilon"], version=version, drop=O.DropoutFeeder(4321),
+                                         p_embd=0.1, p_attn=0.15, p_resid=0.2, p_mlp=0.5)
+    lm_loss(lg_ref).backward()
+    with mock_ops.patched():
+        model = mg.GPTLMHeadModel(mg.GPTConfig(**cfg), version=version)
+        model.load_state_dict(c["sd"], strict=True)
+        model._tie_weights()
+        model.train()
+        F.manual_dropout_seed(4321)
+        (logits, _), _ = model(ids, attention_mask=mask)
+        lm_loss(logits).backward()
+    assert rel_err(logits, lg_ref) < 2e-4
+    _grads_match(model, sd, rename=lambda n: "gpt.tokens_embed.weight" if n == "lm_head.weight" else n, at_least=20)
+
+
+def test_bloom_and_generic_block_train_mode_dropout_vs_oracle_with_the_same_masks(golden):
+    """Bloom with hidden_dropout / attention_dropout > 0 (modeling_bloom.py:111-113, :121-123, :269: the un-fused
+    block path) and transformer.py's TransformerBlock (:47-50, :109, :115)."""
+    from cleantransformer_b200 import functional as F
+    from cleantransformer_b200 import transformer as T
+    from cleantransformer_b200.models import modeling_bloom as mb
+    from oracle import ct_oracle as O
+    g = golden("bloom_tiny")
+    cfg = dict(g["cfg"])
+    cfg["hidden_dropout"], cfg["attention_dropout"] = 0.1, 0.25
+    ids, mask, labels = g["ids"], g["mask"], g["labels"]
+    sd = {k: v.clone().requires_grad_(True) for k, v in g["sd"].items() if k != "lm_head.weight"}
+    (l_ref, lg_ref, _), _ = O.bloom_causal_lm(ids, mask, sd, cfg["n_layer"], cfg["num_attention_heads"],
+                                             cfg["layer_norm_epsilon"], labels=labels, training=True,
+                                             drop=O.DropoutFeeder(99), p_attn=0.25, p_hidden=0.1)
+    l_ref.backward()
+    with mock_ops.patched():
+        model = mb.BloomForCausalLM(mb.BloomConfig(**cfg))
+        model.load_state_dict(g["sd"], strict=True)
+        model._tie_weight()
+        model.train()
+        F.manual_dropout_seed(99)
+        (loss, logits, _), _ = model(input_ids=ids, attention_mask=mask, labels=labels)
+        loss.backward()
+        assert abs(float(loss) - float(l_ref)) / float(l_ref) < 1e-4 and rel_err(logits, lg_ref) < 2e-4
+        _grads_match(model, sd, rename=lambda n: "bloom.word_embeddings.weight" if n == "lm_head.weight" else n,
+                     at_least=20)
+        # transformer.py TransformerBlock (ExampleConfig: both probabilities 0.1)
+        gb = golden("generic_block")
+        cfg_b = T.ExampleConfig()
+        sdb = {k: v.clone().requires_grad_(True) for k, v in gb["sd"].items()}
+        xr = gb["x"].clone().requires_grad_(True)
+        y_ref = O.generic_block(xr, sdb, cfg_b.num_attention_heads, cfg_b.layer_norm_epsilong, drop=O.DropoutFeeder(5),
+                                p_attn=cfg_b.attention_probs_dropout_prob, p_hidden=cfg_b.hidden_dropout_prob)
+        dy = torch.randn_like(y_ref)
+        y_ref.backward(dy)
+        blk = T.TransformerBlock(cfg_b).train()
+        blk.load_state_dict(gb["sd"], strict=True)
+        x = gb["x"].clone().requires_grad_(True)
+        F.manual_dropout_seed(5)
+        y = blk(x)
+        y.backward(dy)
+        assert rel_err(y, y_ref) < 2e-4 and rel_err(x.grad, xr.grad) < 2e-3
+        _grads_match(blk, sdb, at_least=8, floor=1e-6)  # (the key bias gradient is analytically zero)
