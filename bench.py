@@ -578,8 +578,9 @@ def run_gpt2_decode(args):
 
 def run_bert_cls(args):
     """configs[4]: bert-base sequence classification training step (modeling_bert.py:232-333), 64 x 512 per GPU, DDP for
-    N > 1; loss = torch CrossEntropyLoss on the 28-way logits (the reference model has none, :332). Dropout is 0 (the fused
-    sites implement no dropout; the reference default is 0.1 — stated in `config`)."""
+    N > 1; loss = torch CrossEntropyLoss on the 28-way logits (the reference model has none, :332). Train mode with the
+    reference's default dropout (hidden and attention probabilities, p = 0.1; CT_BENCH_BERT_DROPOUT overrides): the
+    attention kernels drop the probabilities themselves, the hidden sites run ct_dropout fused with their residual add."""
     import torch.distributed as dist
     from cleantransformer_b200 import ops
     from cleantransformer_b200.models import modeling_bert as mbert
@@ -594,7 +595,8 @@ def run_bert_cls(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, S, NL = 64, 512, 28
-    cfg = mbert.BertConfig(num_labels=NL, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    p_drop = float(os.environ.get("CT_BENCH_BERT_DROPOUT", "0.1"))
+    cfg = mbert.BertConfig(num_labels=NL, hidden_dropout_prob=p_drop, attention_probs_dropout_prob=p_drop)
     model = mbert.BertForSequenceClassification(cfg).to(dev).train()
     _init_like_reference(model)
     net = DistributedDataParallel(model, device_ids=[local], comm=args.comm) if world > 1 else model
@@ -653,10 +655,18 @@ def run_bert_cls(args):
         sd = {k: torch.nn.Parameter(v.detach().clone()) for k, v in model.state_dict().items()}
         eopt = torch.optim.AdamW(list(sd.values()), lr=1e-5)
 
+        class _TorchDropout:  # the reference's torch.nn.Dropout modules (its own masks: same work, not the same bits)
+            def probs(self, w, p):
+                return torch.nn.functional.dropout(w, p, True)
+
+            def hidden(self, x, p):
+                return torch.nn.functional.dropout(x, p, True)
+
         def estep():
             eopt.zero_grad()
             with torch.autocast("cuda", dtype=torch.bfloat16):
-                lg, _, _ = O.bert_classifier(ids, mask, seg, pos, sd, 12, 12, cfg.layer_norm_eps)
+                lg, _, _ = O.bert_classifier(ids, mask, seg, pos, sd, 12, 12, cfg.layer_norm_eps,
+                                             drop=_TorchDropout() if p_drop > 0 else None, p_attn=p_drop, p_hidden=p_drop)
             l = torch.nn.functional.cross_entropy(lg.float(), labels)
             l.backward()
             eopt.step()
@@ -673,8 +683,9 @@ def run_bert_cls(args):
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "bert-base classification step (configs[4]): fwd + CE + bwd + AdamW, 64 x 512 per "
-                                       "GPU, 28 labels, random-init weights, dropout 0 (reference default 0.1: the fused "
-                                       "sites have no dropout yet)", "global_batch": B * world, "seq_len": S,
+                                       "GPU, 28 labels, random-init weights, train mode with hidden / attention "
+                                       "dropout p = %g (the reference default is 0.1)" % p_drop,
+                           "global_batch": B * world, "seq_len": S, "dropout": p_drop,
                            "layers": 12, "parallelism": "dp%d" % world,
                            "ddp_comm": (args.comm or "p2p") if world > 1 else None,
                            "l2": "activations >> 126 MB L2; no flush"},

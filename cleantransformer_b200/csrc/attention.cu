@@ -1167,7 +1167,7 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32)
 constexpr int DEC_WARPS = 8;
 
 template <int D>
-__global__ void __launch_bounds__(DEC_WARPS * 32)
+__global__ void __launch_bounds__(DEC_WARPS * 32, 4)  // 4 CTAs / SM: 592 (b, h) pairs in one wave
     attn_decode_kernel(const SimtP sp) {
   constexpr int LPK = D / 8;     // lanes per key row
   constexpr int KPI = 32 / LPK;  // keys per warp-wide load instruction

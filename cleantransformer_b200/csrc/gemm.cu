@@ -1128,10 +1128,9 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
   return v;
 }
 
-constexpr int SK_WARPS = 8;
-
-template <int G>
-__global__ void __launch_bounds__(SK_WARPS * 32, 2)
+// SK_WARPS warps split K: 8, or 16 for the narrowest tile (G = 1: few CTAs, so each one should keep more loads in flight)
+template <int G, int SK_WARPS>
+__global__ void __launch_bounds__(SK_WARPS * 32, SK_WARPS == 8 ? 2 : 1)
     gemm_skinny_kernel(const uint16_t* __restrict__ A, int64_t lda, const uint16_t* __restrict__ B, int64_t ldb,
                        int bf16, int K, const EpiParams e) {
   constexpr int FT = 8 * G;  // output features per CTA
@@ -1146,14 +1145,14 @@ __global__ void __launch_bounds__(SK_WARPS * 32, 2)
 #pragma unroll
   for (int i = 0; i < 4; ++i) xrow[i] = A + (int64_t)min(g + 8 * i, e.M - 1) * lda + q * 8;
   // the epilogue's operands are requested before the weight stream so that they do not add a second memory round trip
-  constexpr int EPT = (32 * FT) / (SK_WARPS * 32);  // output elements per thread
+  constexpr int EPT = (32 * FT + SK_WARPS * 32 - 1) / (SK_WARPS * 32);  // output elements per thread
   const bool lean = !e.preact && !e.actgrad_src && e.beta == 0.f && !e.atomic_out;
   float ep_bias[EPT], ep_res[EPT];
 #pragma unroll
   for (int it = 0; it < EPT; ++it) {
     const int idx = threadIdx.x + it * SK_WARPS * 32;
     const int tok = idx / FT, n = n0 + idx % FT;
-    const bool ok = tok < e.M && n < e.N;
+    const bool ok = idx < 32 * FT && tok < e.M && n < e.N;
     ep_bias[it] = (lean && ok && e.bias) ? __ldg(e.bias + n) : 0.f;
     ep_res[it] = (lean && ok && e.residual) ? ld_elem(e.residual, e.res_dtype, (int64_t)tok * e.ldr + n) : 0.f;
   }
@@ -1206,7 +1205,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32, 2)
   for (int it = 0; it < EPT; ++it) {
     const int idx = threadIdx.x + it * SK_WARPS * 32;
     const int tok = idx / FT, f = idx % FT;
-    if (tok >= e.M || n0 + f >= e.N) continue;
+    if (idx >= 32 * FT || tok >= e.M || n0 + f >= e.N) continue;
     const int j = f >> 3, qq = (f & 7) >> 1, t = tok >> 4, gg = tok & 7;
     const int c = (((tok >> 3) & 1) << 1) | (f & 1);
     const int slot = (j * 2 + t) * 4 + c, ln = gg * 4 + qq;
@@ -1403,11 +1402,11 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
     const int sms2 = sm_count();
     // features per CTA: wide tiles amortise the token rows (read once per CTA) when there are CTAs to spare
     if ((a.N + 31) / 32 >= 2 * sms2)
-      gemm_skinny_kernel<4><<<(unsigned)((a.N + 31) / 32), SK_WARPS * 32, 0, st>>>(A16, a.lda, B16, a.ldb, bf, a.K, e);
+      gemm_skinny_kernel<4, 8><<<(unsigned)((a.N + 31) / 32), 256, 0, st>>>(A16, a.lda, B16, a.ldb, bf, a.K, e);
     else if ((a.N + 15) / 16 >= sms2)
-      gemm_skinny_kernel<2><<<(unsigned)((a.N + 15) / 16), SK_WARPS * 32, 0, st>>>(A16, a.lda, B16, a.ldb, bf, a.K, e);
+      gemm_skinny_kernel<2, 8><<<(unsigned)((a.N + 15) / 16), 256, 0, st>>>(A16, a.lda, B16, a.ldb, bf, a.K, e);
     else
-      gemm_skinny_kernel<1><<<(unsigned)((a.N + 7) / 8), SK_WARPS * 32, 0, st>>>(A16, a.lda, B16, a.ldb, bf, a.K, e);
+      gemm_skinny_kernel<1, 16><<<(unsigned)((a.N + 7) / 8), 512, 0, st>>>(A16, a.lda, B16, a.ldb, bf, a.K, e);
     CT_LAUNCH_OK();
     return 0;
   }

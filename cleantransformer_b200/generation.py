@@ -163,6 +163,16 @@ class GenerationMixin:
         def pick(logits):
             ops.greedy_step(logits, alive, end_ids, pad_id, ids_out, cur_ids, pos_ids, state)
 
+        trace = getattr(self, "_ct_decode_trace", None)  # tools/decode_timing.py: a list that receives phase timings
+        marks = []
+
+        def mark(name):
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
         # prefill: the un-graphed full-sequence path, with the caches allocated once for the whole generation
         old_cap = ops.KV_CACHE_MIN_CAP[0]
         ops.KV_CACHE_MIN_CAP[0] = cap
@@ -185,12 +195,15 @@ class GenerationMixin:
             return end_ids is not None and int(state[3]) >= 0
 
         n_steps = n_emit - 1  # q_len = 1 steps still to run
+        mark("prefill")
         if n_steps > 0 and not finished():
             step()  # first decode step outside the capture: lazy kernel attributes, and it is a real step
             n_steps -= 1
         self._ct_decode_graph_launches = 0
+        mark("first_step")
         if n_steps > 0 and not finished():
             replay, self._ct_decode_graph_launches = _capture(step)
+            mark("capture")
             done = 0
             while done < n_steps:
                 burst = min(POLL_EVERY, n_steps - done) if end_ids is not None else n_steps - done
@@ -200,7 +213,11 @@ class GenerationMixin:
                 ops.LAUNCHES[0] += burst * self._ct_decode_graph_launches
                 if finished():
                     break
+            mark("replays")
             del replay
         st = state.tolist()
+        if trace is not None:
+            torch.cuda.synchronize()
+            trace.append({b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])})
         n_out = st[3] if (end_ids is not None and st[3] >= 0) else min(st[1], P + n_emit)
         return ids_out[:, :n_out].reshape(bsz, 1, -1)

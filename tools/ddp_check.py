@@ -275,6 +275,51 @@ def main():
     res["gpt_segment_ids_vs_mean"] = worst
     gddp.close()
 
+    # ---- BERT (config 5: separate q/k/v Linears, post-LN, dropout 0.1 in train mode) through the DDP wrapper ----
+    from cleantransformer_b200 import functional as F
+    from cleantransformer_b200.models import modeling_bert as mbert
+    bcfg = mbert.BertConfig(num_hidden_layers=2, num_labels=28)  # hidden / attention dropout 0.1 (reference default)
+
+    def bbuild():
+        torch.manual_seed(21)
+        with torch.device(dev):
+            mm = mbert.BertForSequenceClassification(bcfg)
+        with torch.no_grad():
+            for _, p in mm.named_parameters():
+                if p.dim() >= 2:
+                    p.normal_(0, 0.02)
+        return mm.train()
+
+    bg = torch.Generator().manual_seed(555 + rank)
+    bids = torch.randint(1, 30522, (4, 512), generator=bg).to(dev)
+    blab = torch.randint(0, 28, (4,), generator=bg).to(dev)
+    bmask = torch.ones(4, 512, device=dev)
+    bmask[1, 300:] = 0
+    bseg = torch.zeros(4, 512, dtype=torch.long, device=dev)
+    bpos = torch.arange(512, device=dev)
+
+    def bloss(model):
+        F.manual_dropout_seed(4000 + rank)  # every rank its own masks, the same ones for the local and the DDP run
+        return torch.nn.functional.cross_entropy(model(bids, bmask, bseg, bpos).float(), blab)
+
+    bb = bbuild(); bloss(bb).backward()
+    bmean = {}
+    for n, p in bb.named_parameters():
+        t = p.grad.detach().clone(); dist.all_reduce(t); bmean[n] = t / world
+    bm = bbuild()
+    bddp = DistributedDataParallel(bm, device_ids=[local], comm="p2p", bucket_cap_mb=1)
+    bloss(bddp).backward()
+    torch.cuda.synchronize()
+    worst = 0.0
+    for n, p in bm.named_parameters():
+        if n.endswith("k_linear.bias"):
+            continue  # analytically zero (softmax shift invariance): rounding noise on both sides
+        worst = max(worst, rel(p.grad, bmean[n]))
+        check(same_on_all_ranks(p.grad), "BERT p2p grad %s differs across ranks" % n)
+    check(worst <= 4e-3, "BERT (dropout 0.1, train) through DDP vs mean of local gradients: %g" % worst)
+    res["bert_dropout_ddp_vs_mean"] = worst
+    bddp.close()
+
     res["failures"] = FAILS
     allf = [None] * world
     dist.all_gather_object(allf, FAILS)
