@@ -80,14 +80,49 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
 
+    def _nvml(self):
+        """In-process NVML (nvidia_ml_py): the same counters as the nvidia-smi query without spawning a process every
+        200 ms (while the nvidia-smi sampler ran, single generations of the decode arm — 510 graph launches each —
+        took 1x to 4x their un-sampled time, r02n / r02o)."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:  # NVML enumerates physical devices, CUDA the visible ones: match by UUID
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                idx = self.index
+                if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                    idx = int(vis.split(",")[self.index])
+                h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            return pynvml, h
+        except Exception:
+            return None, None
+
     def run(self):
+        nv, h = self._nvml()
+        self.source = "nvml" if nv else "nvidia-smi"
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if nv:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    flag = lambda bit: "Active" if (r & bit) else "Not Active"
+                    self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                         str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)),
+                                         str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0),
+                                         flag(nv.nvmlClocksEventReasonHwSlowdown),
+                                         flag(nv.nvmlClocksEventReasonHwThermalSlowdown),
+                                         flag(nv.nvmlClocksEventReasonSwThermalSlowdown),
+                                         flag(nv.nvmlClocksEventReasonSwPowerCap)])
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                         timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
             time.sleep(0.2)
@@ -103,7 +138,7 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": getattr(self, "source", None)}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1129,10 +1129,13 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
 }
 
 // SK_WARPS warps split K: 8, or 16 for the narrowest tile (G = 1: few CTAs, so each one should keep more loads in flight)
-template <int G, int SK_WARPS>
+// BF16 / LEAN are compile-time so that a launch fetches only the code it runs (a decode step is ~100 of these kernels,
+// each a few microseconds long: instruction-cache misses at kernel start showed as stall_no_instruction ~ 1 per issue).
+// LEAN: epilogue = alpha, bias, activation, residual, store; otherwise the common scalar epilogue (epi_scalar).
+template <int G, int SK_WARPS, bool BF16, bool LEAN>
 __global__ void __launch_bounds__(SK_WARPS * 32, SK_WARPS == 8 ? 2 : 1)
     gemm_skinny_kernel(const uint16_t* __restrict__ A, int64_t lda, const uint16_t* __restrict__ B, int64_t ldb,
-                       int bf16, int K, const EpiParams e) {
+                       int K, const EpiParams e) {
   constexpr int FT = 8 * G;  // output features per CTA
   __shared__ float red[SK_WARPS][G * 8][32];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1146,7 +1149,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32, SK_WARPS == 8 ? 2 : 1)
   for (int i = 0; i < 4; ++i) xrow[i] = A + (int64_t)min(g + 8 * i, e.M - 1) * lda + q * 8;
   // the epilogue's operands are requested before the weight stream so that they do not add a second memory round trip
   constexpr int EPT = (32 * FT + SK_WARPS * 32 - 1) / (SK_WARPS * 32);  // output elements per thread
-  const bool lean = !e.preact && !e.actgrad_src && e.beta == 0.f && !e.atomic_out;
+  constexpr bool lean = LEAN;
   float ep_bias[EPT], ep_res[EPT];
 #pragma unroll
   for (int it = 0; it < EPT; ++it) {
@@ -1165,18 +1168,25 @@ __global__ void __launch_bounds__(SK_WARPS * 32, SK_WARPS == 8 ? 2 : 1)
       for (int c = 0; c < 4; ++c) acc[j][t][c] = 0.f;
   const int chunks = K >> 5;
   constexpr int U = G >= 2 ? 2 : 4;  // chunks in flight per warp: (G + 4) * U 16-byte loads per lane
+#pragma unroll
+  for (int j = 0; j < G; ++j) wrow[j] += wib * 32;  // pointers walk with the loop: constant offsets inside an iteration
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xrow[i] += wib * 32;
   for (int c0 = wib; c0 < chunks; c0 += SK_WARPS * U) {
     uint4 w[U][G], x[U][4];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int c = c0 + u * SK_WARPS;
-      if (c < chunks) {
+      if (c0 + u * SK_WARPS < chunks) {
 #pragma unroll
-        for (int j = 0; j < G; ++j) w[u][j] = ld_stream16(wrow[j] + c * 32);
+        for (int j = 0; j < G; ++j) w[u][j] = ld_stream16(wrow[j] + u * SK_WARPS * 32);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) x[u][i] = __ldg(reinterpret_cast<const uint4*>(xrow[i] + c * 32));
+        for (int i = 0; i < 4; ++i) x[u][i] = __ldg(reinterpret_cast<const uint4*>(xrow[i] + u * SK_WARPS * 32));
       }
     }
+#pragma unroll
+    for (int j = 0; j < G; ++j) wrow[j] += SK_WARPS * U * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xrow[i] += SK_WARPS * U * 32;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (c0 + u * SK_WARPS < chunks) {
@@ -1185,9 +1195,9 @@ __global__ void __launch_bounds__(SK_WARPS * 32, SK_WARPS == 8 ? 2 : 1)
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             mma16816(acc[j][t], x[u][2 * t].x, x[u][2 * t + 1].x, x[u][2 * t].y, x[u][2 * t + 1].y, w[u][j].x, w[u][j].y,
-                     bf16 != 0);
+                     BF16);
             mma16816(acc[j][t], x[u][2 * t].z, x[u][2 * t + 1].z, x[u][2 * t].w, x[u][2 * t + 1].w, w[u][j].z, w[u][j].w,
-                     bf16 != 0);
+                     BF16);
           }
         }
       }
@@ -1212,7 +1222,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32, SK_WARPS == 8 ? 2 : 1)
     float v = 0.f;
 #pragma unroll
     for (int wv = 0; wv < SK_WARPS; ++wv) v += red[wv][slot][ln];
-    if (lean) {  // bias, activation, residual: the decode step's epilogues
+    if constexpr (LEAN) {  // bias, activation, residual: the decode step's epilogues
       v = fmaf(e.alpha, v, ep_bias[it]);
       if (e.act != ACT_NONE) v = act_apply_call(v, e.act);
       st_elem(e.C, e.c_dtype, (int64_t)tok * e.ldc + n0 + f, v + ep_res[it]);
@@ -1398,15 +1408,25 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
   if (skinny_ok && (a.impl == 4 || (a.impl == 0 && (int64_t)a.N * a.K >= (1 << 16)))) {
     const uint16_t* A16 = (const uint16_t*)a.A;
     const uint16_t* B16 = (const uint16_t*)a.B;
-    const int bf = a.ab_dtype == DT_BF16;
+    const bool bf = a.ab_dtype == DT_BF16;
+    const bool lean = !a.preact && !a.actgrad_src && a.beta == 0.f;
     const int sms2 = sm_count();
     // features per CTA: wide tiles amortise the token rows (read once per CTA) when there are CTAs to spare
-    if ((a.N + 31) / 32 >= 2 * sms2)
-      gemm_skinny_kernel<4, 8><<<(unsigned)((a.N + 31) / 32), 256, 0, st>>>(A16, a.lda, B16, a.ldb, bf, a.K, e);
-    else if ((a.N + 15) / 16 >= sms2)
-      gemm_skinny_kernel<2, 8><<<(unsigned)((a.N + 15) / 16), 256, 0, st>>>(A16, a.lda, B16, a.ldb, bf, a.K, e);
-    else
-      gemm_skinny_kernel<1, 16><<<(unsigned)((a.N + 7) / 8), 512, 0, st>>>(A16, a.lda, B16, a.ldb, bf, a.K, e);
+    const int g = ((a.N + 31) / 32 >= 2 * sms2) ? 4 : ((a.N + 15) / 16 >= sms2) ? 2 : 1;
+#define CT_SK_GO(G, W, BF, LEAN) \
+  gemm_skinny_kernel<G, W, BF, LEAN><<<(unsigned)((a.N + 8 * G - 1) / (8 * G)), W * 32, 0, st>>>(A16, a.lda, B16, a.ldb, a.K, e)
+#define CT_SK_PICK(G, W)                                  \
+  do {                                                    \
+    if (bf && lean) CT_SK_GO(G, W, true, true);           \
+    else if (bf) CT_SK_GO(G, W, true, false);             \
+    else if (lean) CT_SK_GO(G, W, false, true);           \
+    else CT_SK_GO(G, W, false, false);                    \
+  } while (0)
+    if (g == 4) CT_SK_PICK(4, 8);
+    else if (g == 2) CT_SK_PICK(2, 8);
+    else CT_SK_PICK(1, 16);
+#undef CT_SK_PICK
+#undef CT_SK_GO
     CT_LAUNCH_OK();
     return 0;
   }
