@@ -386,20 +386,22 @@ class DistributedDataParallel(torch.nn.Module):
         T, H = ids.numel(), dout.shape[-1]
         if grad.data_ptr() != param._ct_grad_view.data_ptr():
             raise RuntimeError("DistributedDataParallel: the tied table's .grad is not its arena view")
-        if T > self._stage_cap:
-            raise RuntimeError("DistributedDataParallel: %d tokens per step exceed the sparse-exchange staging "
-                               "area (%d); raise CT_DDP_STAGE_TOKENS" % (T, self._stage_cap))
         V = param.shape[0]
         cur = torch.cuda.current_stream(self.device)
         self._comm_stream.wait_stream(cur)
+        rows, flat_ids = dout.reshape(-1, H), ids.reshape(-1)
         with torch.cuda.stream(self._comm_stream):
-            self._stage_hdr.fill_(T)
-            self._stage_rows[:T * H].copy_(dout.reshape(-1))
-            self._stage_ids[:T].copy_(ids.reshape(-1))
-            _lib.check(_lib.load().ct_embedding_bwd_allranks(
-                self._stage_hdr_off, self._stage_rows_off, self._stage_ids_off, self._grad_off[id(param)], H, V,
-                int(padding_idx), 1.0 / self.world, self.final_ctas * 2, self._comm_stream.cuda_stream),
-                "ct_embedding_bwd_allranks")
+            # more tokens than the staging area holds (CT_DDP_STAGE_TOKENS, sized at construction inside the symmetric
+            # buffer): several exchanges. Like the buckets, this assumes every rank runs the same batch shape.
+            for c0 in range(0, T, self._stage_cap):
+                n = min(self._stage_cap, T - c0)
+                self._stage_hdr.fill_(n)
+                self._stage_rows[:n * H].copy_(rows[c0:c0 + n].reshape(-1))
+                self._stage_ids[:n].copy_(flat_ids[c0:c0 + n])
+                _lib.check(_lib.load().ct_embedding_bwd_allranks(
+                    self._stage_hdr_off, self._stage_rows_off, self._stage_ids_off, self._grad_off[id(param)], H, V,
+                    int(padding_idx), 1.0 / self.world, self.final_ctas * 2, self._comm_stream.cuda_stream),
+                    "ct_embedding_bwd_allranks")
         if not torch.cuda.is_current_stream_capturing():  # (graph memory is static; the side stream joins before the end)
             dout.record_stream(self._comm_stream)
             ids.record_stream(self._comm_stream)

@@ -5,6 +5,7 @@ hand-written sm_100a kernel in libct_b200.so. Wrappers allocate outputs with tor
 raw data_ptr()s + the current stream. Nothing in this module computes with torch ops.
 """
 import ctypes
+import weakref
 import os
 
 import torch
@@ -546,7 +547,7 @@ def kv_cache_append(past, new):
     _req_cuda(new)
     B, H, s, D = new.shape
     t = 0 if past is None else past.shape[2]
-    base = getattr(past, "_ct_cache_base", None) if past is not None else None
+    base = _kv_base_of(past) if past is not None else None
     if base is None or base.shape[2] < t + s or base.dtype != new.dtype or past.data_ptr() != base.data_ptr():
         cap = max(((t + s + KV_CACHE_CHUNK - 1) // KV_CACHE_CHUNK + 1) * KV_CACHE_CHUNK, KV_CACHE_MIN_CAP[0])
         nbase = torch.empty((B, H, cap, D), dtype=new.dtype, device=new.device)
@@ -561,4 +562,26 @@ def kv_cache_append(past, new):
         "ct_kv_append")
     view = base[:, :, :t + s]
     view._ct_cache_base = base
+    _KV_BASES[base.untyped_storage().data_ptr()] = weakref.ref(base)
+    if len(_KV_BASES) > 4096:  # forget the buffers that are gone
+        for k in [k for k, r in _KV_BASES.items() if r() is None]:
+            del _KV_BASES[k]
     return view
+
+
+_KV_BASES = {}  # storage address -> weakref(preallocated buffer)
+
+
+def _kv_base_of(past):
+    """The preallocated buffer `past` is a prefix view of: the attribute kv_cache_append left on the tensor it returned,
+    or — when the caller re-sliced / re-wrapped that tensor, which drops Python attributes — the buffer registered for
+    its storage, provided `past` still starts at the buffer's first element with the buffer's strides."""
+    base = getattr(past, "_ct_cache_base", None)
+    if base is not None:
+        return base
+    ref = _KV_BASES.get(past.untyped_storage().data_ptr())
+    base = ref() if ref is not None else None
+    if (base is not None and past.dim() == 4 and past.data_ptr() == base.data_ptr() and past.stride() == base.stride()
+            and past.shape[:2] == base.shape[:2] and past.shape[3] == base.shape[3] and past.shape[2] <= base.shape[2]):
+        return base
+    return None

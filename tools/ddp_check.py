@@ -240,6 +240,21 @@ def main():
             del gstep
         ddp.close()
         dist.barrier()
+    # ---- the sparse tied-table exchange in several pieces (staging area smaller than the batch) ----
+    os.environ["CT_DDP_STAGE_TOKENS"] = "300"   # 1024 tokens per rank -> 4 exchanges
+    try:
+        m = build(5)
+        ddp = DistributedDataParallel(m, device_ids=[local], comm="p2p", bucket_cap_mb=1)
+        (l, _, _), _ = ddp(input_ids=ids, attention_mask=mask, labels=ids)
+        l.backward()
+        torch.cuda.synchronize()
+        worst = max(rel(p.grad, mean_grads[n]) for n, p in m.named_parameters())
+        check(worst <= 4e-3, "chunked sparse exchange vs mean of local gradients: %g" % worst)
+        out["chunked_sparse_exchange_vs_mean"] = worst
+        ddp.close()
+    finally:
+        del os.environ["CT_DDP_STAGE_TOKENS"]
+    dist.barrier()
     res["ddp"] = out
 
     # ---- GPT with segment_ids: the tied table receives three gradient writes ----
