@@ -554,6 +554,7 @@ struct AttnBwdP {
   void* dv; int64_t dv_sb, dv_sh, dv_ss;
 };
 constexpr int FB_THREADS = 320;  // TMA warp + MMA warp + 8 compute warps (2 per TMEM lane quarter)
+constexpr int FB_THREADS_WIDE = 640;  // control warpgroup (TMA, MMA, 2 idle) + 16 compute warps (4 per lane quarter)
 constexpr int FB_SMEM = 2 * FA_TILE /*K,V*/ + 4 * FA_TILE /*2 x (Q,dO)*/ + 2 * FA_TILE /*P^T*/ +
                         2 * FA_TILE /*dS^T*/ + 128 /*barriers*/ + 1024 /*lse2, delta of the query tile*/;
 // v3 (pipelined): second P^T / dS^T buffer pair and a second statistics buffer
@@ -613,16 +614,18 @@ __device__ __forceinline__ void fb2_store_pair(const FbCtx& cx, int c, int g, co
 // one 32-query chunk c of this thread's key row. KIND 0 = visible, 1 = entirely future, 2 = generic,
 // 3 = generic with dropout: P^T (the dV operand) holds the surviving probabilities scaled by 1 / (1 - p), and dP reaches
 // dS only through them: dS = P * (keep * dP / (1 - p) - delta)
-template <int KIND, bool BF16>
-__device__ __forceinline__ void fb2_chunk(const FbCtx& cx, const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c,
-                                          int q0) {
+// NG groups of 8 queries starting at group g0 of the chunk (NG = 4, g0 = 0: the whole chunk; the 16-warp kernel works
+// through a chunk in two halves to halve the registers that hold S^T / dP^T)
+template <int KIND, bool BF16, int NG = 4>
+__device__ __forceinline__ void fb2_chunk(const FbCtx& cx, const uint32_t (&rs)[8 * NG], const uint32_t (&rd)[8 * NG], int c,
+                                          int q0, int g0 = 0) {
   const float2 sl2v = make_float2(cx.sl2, cx.sl2), scv = make_float2(cx.scale, cx.scale), kbv = make_float2(cx.kb, cx.kb);
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < NG; ++g) {
     float pt[8], ds[8];
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
-      const int col = c * 32 + g * 8 + hh * 4;
+      const int col = c * 32 + (g0 + g) * 8 + hh * 4;
       const float4 nl = lds128f(cx.lse_s + 4 * col);
       const float nls[4] = {nl.x, nl.y, nl.z, nl.w};
       if constexpr (KIND == 0) {
@@ -680,14 +683,18 @@ __device__ __forceinline__ void fb2_chunk(const FbCtx& cx, const uint32_t (&rs)[
         }
       }
     }
-    fb2_store_pair<BF16>(cx, c, g, pt, ds);
+    fb2_store_pair<BF16>(cx, c, g0 + g, pt, ds);
   }
 }
 
 // MODE bit 0: tiled dQ workspace; bit 1: P^T / dS^T (and the statistics) double-buffered, so the element math of
 // query tile it+1 runs under the dQ / dV / dK MMAs of tile it (v2 waits for them before touching the tiles).
+// MODE bit 2 (WIDE): 16 compute warps instead of 8 — four per TMEM lane quarter, one 32-query chunk each — so that
+// every scheduler has four element-math warps to switch between instead of two (ncu on v3: warps active 15 %, issue
+// active 23 %, stalls on dependent MUFU / FFMA2 chains). Warps 0-3 are the control warpgroup (TMA, MMA, two idle);
+// a chunk is worked through in two halves of 16 queries, which keeps the kernel at 96 registers for 640 threads.
 template <bool BF16, int MODE>
-__global__ void __launch_bounds__(FB_THREADS, 1)
+__global__ void __launch_bounds__((MODE & 4) ? FB_THREADS_WIDE : FB_THREADS, 1)
     attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                         const AttnBwdP bp) {
@@ -696,7 +703,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   const uint32_t base = smem_u32(smem);
   const uint32_t sK = base, sV = base + FA_TILE;
   const uint32_t sQ = base + 2 * FA_TILE;   // 2 stages, each Q then dO
-  constexpr bool DQT = (MODE & 1) != 0, PIPE = (MODE & 2) != 0;
+  constexpr bool DQT = (MODE & 1) != 0, PIPE = (MODE & 2) != 0, WIDE = (MODE & 4) != 0;
+  static_assert(!WIDE || (DQT && PIPE), "the 16-warp variant builds on the tiled dQ workspace and the double buffers");
+  constexpr int N_COMPUTE = WIDE ? 512 : 256;  // compute threads
   constexpr int N_TILES = PIPE ? 14 : 10;
   constexpr uint32_t PDS_STRIDE = PIPE ? 4 * FA_TILE : 0;  // buffer (it & 1) of the P^T / dS^T pair
   constexpr uint32_t STAT_STRIDE = PIPE ? 1024 : 0;
@@ -728,8 +737,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(qdo_full + 8 * s, 1); mbar_init(qdo_empty + 8 * s, 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_free, 256);
-    mbar_init(pds_ready, 256);
+    mbar_init(sdp_free, N_COMPUTE);
+    mbar_init(pds_ready, N_COMPUTE);
     mbar_init(mma_done, 1);
     mbar_init(dkv_full, 1);
     mbar_fence_init();
@@ -800,6 +809,153 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         umma_commit(mma_done);  // dQ(it) readable; P^T / dS^T tiles free for tile it+1
       }
       umma_commit(dkv_full);
+    }
+  } else if (WIDE && warp < 4) {
+    // idle members of the control warpgroup
+  } else if constexpr (WIDE) {
+    const int wq = warp & 3;
+    const int rr = wq * 32 + lane;   // key row inside the tile (S^T) / query row (dQ)
+    const int c = (warp - 4) >> 2;   // the 32-query chunk this warp owns; also its 16 of the 64 dQ / dK / dV columns
+    const int jg = kv0 + rr;
+    const uint32_t t_lane = (uint32_t)(wq * 32) << 16;
+    FbCtx cx;
+    cx.kb = (p.kbias2 && jg < p.Sk) ? __ldg(p.kbias2 + (int64_t)b * p.kb_sb + (int64_t)h * p.kb_sh + jg) : 0.f;
+    cx.sl2 = p.sl2; cx.scale = p.scale; cx.cf2 = p.causal_fill2;
+    cx.jg = jg; cx.off = p.off; cx.causal = p.causal; cx.key_oob = jg >= p.Sk;
+    cx.lse_s = lse_s; cx.del_s = del_s; cx.sPT = sPT; cx.sDS = sDS; cx.rr = rr; cx.sw = rr & 7;
+    cx.d_jterm = (uint32_t)jg * 0x9E3779B1u + p.drop.key0; cx.d_istep = (uint32_t)p.Sk * 0x9E3779B1u;
+    cx.d_pre = (uint32_t)bh * 0x85EBCA77u + p.drop.key1; cx.d_thr = p.drop.thr; cx.d_rs = p.drop.rscale;
+    const bool warp_generic = __any_sync(0xffffffffu, cx.kb < -1e30f) || (kv0 + 128 > p.Sk);
+    const bool fill_is_ninf = p.causal_fill2 == -INFINITY;
+    const float* lse_bh = p.lse2 + ((int64_t)b * p.H + h) * p.Sq;
+    const float* del_bh = bp.delta + ((int64_t)b * p.H + h) * p.Sq;
+    float nlse_next = -INFINITY, ndel_next = 0.f;
+    if (c == 0 && n_it > 0 && i_start * 128 + rr < p.Sq) {
+      nlse_next = -__ldg(lse_bh + i_start * 128 + rr);
+      ndel_next = -__ldg(del_bh + i_start * 128 + rr) * p.scale;
+    }
+    // dQ of query tile `itp`: this thread owns query row (q0 + rr), columns [16*c, 16*c + 16) of d
+    auto red_dq16 = [&](const uint32_t (&r)[16], int itp) {
+      const int qi = (i_start + itp) * 128 + rr;
+      if (qi < p.Sq) {
+        float* dst = bp.dq_accum + (((int64_t)b * p.H + h) * n_q_tiles + (i_start + itp)) * FB_DQ_TILE +
+                     (c * 4 * 128 + rr) * 4;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 128 * 4 * g),
+                       "f"(__uint_as_float(r[4 * g])), "f"(__uint_as_float(r[4 * g + 1])),
+                       "f"(__uint_as_float(r[4 * g + 2])), "f"(__uint_as_float(r[4 * g + 3]))
+                       : "memory");
+      }
+    };
+    for (int it = 0; it < n_it; ++it) {
+      const int q0 = (i_start + it) * 128;
+      cx.sPT = sPT + (it & 1) * PDS_STRIDE; cx.sDS = sDS + (it & 1) * PDS_STRIDE;
+      cx.lse_s = lse_s + (it & 1) * STAT_STRIDE; cx.del_s = del_s + (it & 1) * STAT_STRIDE;
+      mbar_wait(sdp_full, it & 1);
+      tc_fence_after();
+      const bool touches_diag = p.causal && (kv0 + 127 > q0 + p.off);
+      const bool aligned_diag = touches_diag && fill_is_ninf && (kv0 == q0 + p.off) && !warp_generic;
+      int kind;
+      if (warp_generic || (touches_diag && !aligned_diag)) kind = 2;
+      else if (aligned_diag) kind = c < wq ? 1 : (c > wq ? 0 : 2);
+      else kind = 0;
+      // the chunk in two halves of 16 queries (32 live S^T / dP^T registers instead of 64)
+      uint32_t rs[16], rd[16];
+      if (kind != 1) { tmem_ld_32x16(T_ST + t_lane + c * 32, rs); tmem_ld_32x16(T_DPT + t_lane + c * 32, rd); }
+      // statistics buffer (it & 1) was last read by tile it-2; every thread finished tile it-2 before it arrived at the
+      // named barrier of tile it-1, which this thread has passed
+      if (c == 0) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.lse_s + 4 * rr), "f"(nlse_next) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.del_s + 4 * rr), "f"(ndel_next) : "memory");
+      }
+      tmem_ld_wait();
+      bar_sync_named(1, N_COMPUTE);       // statistics staged by the c == 0 warps are visible
+      if (c == 0) {
+        const int nq = q0 + 128 + rr;
+        const bool ok = (it + 1 < n_it) && nq < p.Sq;
+        nlse_next = ok ? -__ldg(lse_bh + nq) : -INFINITY;
+        ndel_next = ok ? -__ldg(del_bh + nq) * p.scale : 0.f;
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (half == 1) {
+          if (kind != 1) {
+            tmem_ld_32x16(T_ST + t_lane + c * 32 + 16, rs);
+            tmem_ld_32x16(T_DPT + t_lane + c * 32 + 16, rd);
+          }
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(sdp_free);          // S^T / dP^T are in registers: the next tile's MMAs may overwrite them
+        }
+        if (cx.d_thr) fb2_chunk<3, BF16, 2>(cx, rs, rd, c, q0, 2 * half);
+        else if (kind == 0) fb2_chunk<0, BF16, 2>(cx, rs, rd, c, q0, 2 * half);
+        else if (kind == 1) fb2_chunk<1, BF16, 2>(cx, rs, rd, c, q0, 2 * half);
+        else fb2_chunk<2, BF16, 2>(cx, rs, rd, c, q0, 2 * half);
+      }
+      fence_proxy_async_smem();
+      if (it > 0) {
+        // dQ(it-1) must leave TMEM before pds_ready(it) lets the MMA warp overwrite it; its MMAs ran under this tile's
+        // element math. Waiting for every mma_done phase in order also proves that buffer ((it+1) & 1) of P^T / dS^T —
+        // read by the MMAs of tile it-1 — is free when tile it+1 writes it.
+        mbar_wait(mma_done, (it - 1) & 1);
+        tc_fence_after();
+        uint32_t rq[16];
+        tmem_ld_32x16(T_DQ + t_lane + c * 16, rq);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(pds_ready);
+        red_dq16(rq, it - 1);             // the atomics drain while the next tile starts
+      } else {
+        tc_fence_before();
+        mbar_arrive(pds_ready);
+      }
+    }
+    if (n_it > 0) {
+      mbar_wait(mma_done, (n_it - 1) & 1);
+      tc_fence_after();
+      uint32_t rq[16];
+      tmem_ld_32x16(T_DQ + t_lane + c * 16, rq);
+      tmem_ld_wait();
+      red_dq16(rq, n_it - 1);
+      mbar_wait(dkv_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint32_t r[16];
+      if (n_it > 0) {
+        tmem_ld_32x16((which == 0 ? T_DV : T_DK) + t_lane + c * 16, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) r[t] = 0u;
+      }
+      if (!cx.key_oob) {
+        void* basep = which == 0 ? bp.dv : bp.dk;
+        const int64_t eo = which == 0
+            ? (int64_t)b * bp.dv_sb + (int64_t)h * bp.dv_sh + (int64_t)jg * bp.dv_ss
+            : (int64_t)b * bp.dk_sb + (int64_t)h * bp.dk_sh + (int64_t)jg * bp.dk_ss;
+        uint8_t* row = reinterpret_cast<uint8_t*>(basep) + 2 * (eo + c * 16);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 w;
+          const float f0 = __uint_as_float(r[8 * g]), f1 = __uint_as_float(r[8 * g + 1]),
+                      f2 = __uint_as_float(r[8 * g + 2]), f3 = __uint_as_float(r[8 * g + 3]),
+                      f4 = __uint_as_float(r[8 * g + 4]), f5 = __uint_as_float(r[8 * g + 5]),
+                      f6 = __uint_as_float(r[8 * g + 6]), f7 = __uint_as_float(r[8 * g + 7]);
+          if constexpr (BF16) {
+            w.x = pack_bf16x2(f0, f1); w.y = pack_bf16x2(f2, f3); w.z = pack_bf16x2(f4, f5); w.w = pack_bf16x2(f6, f7);
+          } else {
+            __half2 x;
+            x = __floats2half2_rn(f0, f1); w.x = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f2, f3); w.y = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f4, f5); w.z = *reinterpret_cast<uint32_t*>(&x);
+            x = __floats2half2_rn(f6, f7); w.w = *reinterpret_cast<uint32_t*>(&x);
+          }
+          *reinterpret_cast<uint4*>(row + 16 * g) = w;
+        }
+      }
     }
   } else {
     const int wq = warp & 3;
@@ -1723,11 +1879,19 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     if (!attr) {
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
+      CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
       attr = true;
     }
     const unsigned g = (unsigned)((int64_t)a.B * a.H * ((a.Sk + 127) / 128));
-    if (fmt == 1) attn_bwd_tc2_kernel<true, 3><<<g, FB_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
-    else attn_bwd_tc2_kernel<false, 3><<<g, FB_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
+    // ATTN_BWD_IMPL: 0 / 1 = 8 compute warps (two 32-query chunks each), 2 = 16 compute warps (one chunk each)
+    if (option(OPT_ATTN_BWD_IMPL) == 2) {
+      if (fmt == 1) attn_bwd_tc2_kernel<true, 7><<<g, FB_THREADS_WIDE, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
+      else attn_bwd_tc2_kernel<false, 7><<<g, FB_THREADS_WIDE, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
+    } else {
+      if (fmt == 1) attn_bwd_tc2_kernel<true, 3><<<g, FB_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
+      else attn_bwd_tc2_kernel<false, 3><<<g, FB_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
+    }
     CT_LAUNCH_OK();
     const int64_t n = (int64_t)(dq_elems / 8);
     int64_t blocks = (n + 255) / 256;

@@ -55,7 +55,7 @@ int sm_count();  // cached multiprocessor count of the current device
 
 // Tuning knobs (ct_set_option / CT_<NAME> environment variables); 0 always means "default / auto".
 enum : int { OPT_LN_BWD_IMPL = 0, OPT_GEMM_EPI_IMPL, OPT_GEMM_2CTA, OPT_CE_IMPL,
-             OPT_GEMM_SPLITK, OPT_COUNT };
+             OPT_GEMM_SPLITK, OPT_ATTN_BWD_IMPL, OPT_COUNT };
 int option(int which);
 
 // dtype enum shared with include/ct_b200.h

@@ -131,7 +131,8 @@ def attn_ab():
         ref = _attn_oracle(qr, kr, vr, scale, True, fill, kb2[:nb].expand(nb, H, S) if kb2 is not None else None)
         do = torch.randn(B, S, H * D, device=DEV).bfloat16()
         ref.backward(do[:nb].float())
-        for impl in ("default",):  # (older generations were removed; their numbers live in profiles/)
+        for impl in ("bwd_8_compute_warps", "bwd_16_compute_warps"):  # ATTN_BWD_IMPL 1 / 2 (same forward)
+            prev = ops.set_option("ATTN_BWD_IMPL", 2 if impl.startswith("bwd_16") else 1)
             try:
                 o, lse2 = ops.attn_fwd(q, k, v, scale, True, fill, kb2, fv)
                 dqkv = torch.zeros_like(qkv)
@@ -148,7 +149,7 @@ def attn_ab():
             except Exception as ex:  # noqa: BLE001
                 out(kernel="attention", case=name, impl=impl, error=repr(ex)[:300])
             finally:
-                pass
+                ops.set_option("ATTN_BWD_IMPL", prev)
 
 
 def gemm_ab():
