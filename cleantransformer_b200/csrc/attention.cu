@@ -719,8 +719,12 @@ __global__ void __launch_bounds__((MODE & 4) ? FB_THREADS_WIDE : FB_THREADS, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kv_tiles = (p.Sk + 127) / 128;
-  const int kv_tile = blockIdx.x % n_kv_tiles;
-  const int bh = blockIdx.x / n_kv_tiles;
+  // Under the causal mask key tile 0 meets every query tile and the last key tile only one: WIDE launches all heads'
+  // heaviest tiles first (longest-processing-time order) so that the last wave holds one-tile CTAs, and the CTAs that add
+  // into the same dQ tile are spread over the launch instead of running side by side.
+  const int n_bh_ = p.B * p.H;
+  const int kv_tile = WIDE ? (int)(blockIdx.x / n_bh_) : (int)(blockIdx.x % n_kv_tiles);
+  const int bh = WIDE ? (int)(blockIdx.x % n_bh_) : (int)(blockIdx.x / n_kv_tiles);
   const int h = bh % p.H, b = bh / p.H;
   const int kv0 = kv_tile * 128;
   const int n_q_tiles = (p.Sq + 127) / 128;
@@ -1884,8 +1888,9 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
       attr = true;
     }
     const unsigned g = (unsigned)((int64_t)a.B * a.H * ((a.Sk + 127) / 128));
-    // ATTN_BWD_IMPL: 0 / 1 = 8 compute warps (two 32-query chunks each), 2 = 16 compute warps (one chunk each)
-    if (option(OPT_ATTN_BWD_IMPL) == 2) {
+    // ATTN_BWD_IMPL: 0 (default) / 2 = 16 compute warps (one 32-query chunk each), heaviest key tiles first: 154 vs
+    // 179 us per call at the bench shape, identical bits (profiles/r02r_ab_attention.jsonl); 1 = 8 compute warps
+    if (option(OPT_ATTN_BWD_IMPL) != 1) {
       if (fmt == 1) attn_bwd_tc2_kernel<true, 7><<<g, FB_THREADS_WIDE, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
       else attn_bwd_tc2_kernel<false, 7><<<g, FB_THREADS_WIDE, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
     } else {
