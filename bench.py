@@ -426,12 +426,20 @@ class KernelProfiler:
         if self.prof is not None:
             try:
                 self.prof.__exit__(None, None, None)
+                self.all_device_us, self.other = 0.0, {}
                 for ev in self.prof.events():
                     if ev.name.startswith("ctop"):
                         t = getattr(ev, "device_time_total", None)
                         if t is None:
                             t = getattr(ev, "cuda_time_total", 0.0)
                         self.device_us[int(ev.name[4:])] = float(t)
+                    elif ev.device_type == torch.autograd.DeviceType.CUDA:
+                        # every device activity of the profiled steps (kernels, memsets, copies): what is not inside
+                        # one of the wrapped ops (ATen glue, allocator memsets, ...) shows up as the difference
+                        self.all_device_us += float(ev.device_time)
+                        if not ev.name.startswith(("void ct::", "ct::")):
+                            o = self.other.setdefault(ev.name[:80], [0, 0.0])
+                            o[0] += 1; o[1] += float(ev.device_time)
             except Exception:  # noqa: BLE001
                 self.device_us = {}
             self.prof = None
@@ -934,6 +942,12 @@ def main():
                          "launches_timed": n_gemm, "gemm_ms_per_step": gemm_ms / 2.0,
                          "gemm_share_of_step": (gemm_ms / 2.0) / ms_step if ms_step else None,
                          "kernel_ms_per_step": kernel_ms, "kernel_timing": timing_source,
+                         # every device activity of the instrumented steps (CUPTI), and what of it ran outside the
+                         # wrapped C-ABI calls (ATen glue, memsets, copies): the rest of ms_per_step is idle gaps
+                         "all_device_ms_per_step": (getattr(prof, "all_device_us", 0.0) or 0.0) / 2e3 or None,
+                         "device_activity_outside_the_c_abi": sorted(
+                             ({"name": k, "calls_per_step": v[0] / 2.0, "ms_per_step": v[1] / 2e3}
+                              for k, v in getattr(prof, "other", {}).items()), key=lambda r: -r["ms_per_step"])[:12],
                          "per_kernel": per_kernel},
             "step_roofline": {
                 "attn_ffn_tflops_per_gpu": ATTN_FFN_FLOP_PER_TOKEN * B * S / (ms_step * 1e-3) / 1e12,

@@ -492,3 +492,37 @@ def test_lm_head_row_stats_and_streaming_cross_entropy(M, V, K):
         ops.set_option("CE_IMPL", prev)
     assert abs(float(loss_s) - float(loss_r)) <= 2e-5 * abs(float(loss_r))
     assert rel_err(dl_s, dl_r) < 4e-3
+
+
+@pytest.mark.parametrize("B,H,S,causal,mode", [(2, 4, 384, True, 0), (1, 3, 300, False, 2), (2, 2, 1024, True, None)])
+def test_attention_backward_variants_agree_bit_for_bit(B, H, S, causal, mode):
+    """ATTN_BWD_IMPL: the default backward (16 compute warps, one 32-query chunk each, heaviest key tiles first) and the
+    8-warp kernel it replaced run the same arithmetic per element in the same order: dK / dV identical bits, dQ identical
+    up to the order of its fp32 atomics."""
+    from oracle import ct_oracle as O
+    ops = _ops()
+    torch.manual_seed(3)
+    D = 64
+    qkv = torch.randn(B, S, H, 3, D, device=DEV).bfloat16()
+    q, k, v = [qkv[..., i, :].permute(0, 2, 1, 3) for i in range(3)]
+    kb2 = fv = None
+    if mode is not None:
+        mask = torch.ones(B, S, dtype=torch.long, device=DEV)
+        mask[0, S - 70:] = 0
+        kb2, fv = ops.attn_mask_prep(mask, H, mode, O.alibi_slopes(H).to(DEV) if mode == 0 else None)
+    scale = 0.125
+    o, lse2 = ops.attn_fwd(q, k, v, scale, causal, -FLT_MAX, kb2, fv)
+    do = torch.randn_like(o)
+    outs = []
+    for impl in (1, 0):
+        prev = ops.set_option("ATTN_BWD_IMPL", impl)
+        try:
+            d = torch.zeros_like(qkv)
+            dq, dk, dv = [d[..., i, :].permute(0, 2, 1, 3) for i in range(3)]
+            ops.attn_bwd(do, q, k, v, o, lse2, dq, dk, dv, scale, causal, -FLT_MAX, kb2, fv)
+            torch.cuda.synchronize()
+            outs.append((dq.clone(), dk.clone(), dv.clone()))
+        finally:
+            ops.set_option("ATTN_BWD_IMPL", prev)
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert rel_err(outs[0][0], outs[1][0].float()) < 1e-2  # bf16 quantum after differently ordered fp32 atomics
