@@ -283,6 +283,8 @@ __global__ void __launch_bounds__(F4_THREADS, 2)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(f4_aux + 88);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();               // programmatic dependent launch: see ct_common.cuh (first_valid is read right below)
+  pdl_launch_dependents();
   const int n_q_tiles = (p.Sq + 127) / 128;
   const int n_bh = p.B * p.H;
   const int q_tile = n_q_tiles - 1 - (int)(blockIdx.x / n_bh);  // all heads' heavy (late) query tiles first
@@ -718,6 +720,8 @@ __global__ void __launch_bounds__((MODE & 4) ? FB_THREADS_WIDE : FB_THREADS, 1)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + N_TILES * FA_TILE + 72);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();               // programmatic dependent launch: see ct_common.cuh (first_valid is read right below)
+  pdl_launch_dependents();
   const int n_kv_tiles = (p.Sk + 127) / 128;
   // Under the causal mask key tile 0 meets every query tile and the last key tile only one: WIDE launches all heads'
   // heaviest tiles first (longest-processing-time order) so that the last wave holds one-tile CTAs, and the CTAs that add
@@ -1184,6 +1188,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     attn_delta64_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ o, int64_t sb,
                         int64_t sh, int64_t ss, float* __restrict__ delta, int B, int H, int Sq) {
+  pdl_wait();               // programmatic dependent launch: see ct_common.cuh
+  pdl_launch_dependents();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t row = t >> 3;  // (b, i, h) flattened with h fastest: coalesced along the merged head dim
   const int part = (int)(t & 7);
@@ -1211,6 +1217,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     attn_dq_convert_tiled_kernel(const float* __restrict__ acc, void* __restrict__ dq, int fmt, int64_t sb,
                                  int64_t sh, int64_t ss, int B, int H, int Sq) {
+  pdl_wait();               // programmatic dependent launch: see ct_common.cuh
+  pdl_launch_dependents();
   const int nqt = (Sq + 127) / 128;
   const int64_t n = (int64_t)B * H * nqt * 1024;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
@@ -1335,6 +1343,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4)  // 4 CTAs / SM: 592 (b, h)
   const AttnP& p = sp.a;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = (int)(blockIdx.x % p.H), b = (int)(blockIdx.x / p.H);
+  pdl_wait();               // programmatic dependent launch: see ct_common.cuh
+  pdl_launch_dependents();
   const int Sk = p.sk_dev ? min(*p.sk_dev, p.Sk) : p.Sk;  // p.Sk is the capacity when the count is on the device
   const int sub = lane / LPK, part = lane % LPK;  // key sub-slot inside a group, 16-byte piece of the row
   if (p.k_new) {
@@ -1781,7 +1791,8 @@ extern "C" int ct_attn_fwd(const ct_attn_args* args, void* stream) {
     }
     const int64_t grid = (int64_t)a.B * a.H * ((a.Sq + 127) / 128);
     const bool kb = a.kbias2 != nullptr, bf = p.fmt == 1, dr = p.drop.thr != 0u;
-#define CT_F4_GO(KB, BF, DR) attn_fwd_tc4_kernel<KB, BF, DR><<<(unsigned)grid, F4_THREADS, F4_SMEM, st>>>(tmQ, tmK, tmV, p)
+#define CT_F4_GO(KB, BF, DR) \
+  CT_CUDA_OK(launch_k(attn_fwd_tc4_kernel<KB, BF, DR>, dim3((unsigned)grid), dim3(F4_THREADS), F4_SMEM, st, tmQ, tmK, tmV, p))
     if (dr) {
       if (kb && bf) CT_F4_GO(true, true, true);
       else if (kb) CT_F4_GO(true, false, true);
@@ -1816,9 +1827,9 @@ extern "C" int ct_attn_fwd(const ct_attn_args* args, void* stream) {
              "aligned rows, no lse output)");
   if (decode) {
     const unsigned grid = (unsigned)((int64_t)a.B * a.H);
-    if (a.D == 32) attn_decode_kernel<32><<<grid, DEC_WARPS * 32, 0, st>>>(sp);
-    else if (a.D == 64) attn_decode_kernel<64><<<grid, DEC_WARPS * 32, 0, st>>>(sp);
-    else attn_decode_kernel<128><<<grid, DEC_WARPS * 32, 0, st>>>(sp);
+    if (a.D == 32) CT_CUDA_OK(launch_k(attn_decode_kernel<32>, dim3(grid), dim3(DEC_WARPS * 32), 0, st, sp));
+    else if (a.D == 64) CT_CUDA_OK(launch_k(attn_decode_kernel<64>, dim3(grid), dim3(DEC_WARPS * 32), 0, st, sp));
+    else CT_CUDA_OK(launch_k(attn_decode_kernel<128>, dim3(grid), dim3(DEC_WARPS * 32), 0, st, sp));
     CT_LAUNCH_OK();
     return 0;
   }
@@ -1837,17 +1848,20 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
              "ct_attn_bwd: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
   const int fmt = a.dtype == DT_BF16 ? 1 : 0;
-  {
+  // delta = rowsum(dO * O): launched right before its consumer (after the workspace memset on the tcgen05 path, so that
+  // delta -> backward -> convert is an unbroken kernel chain for programmatic dependent launch)
+  auto launch_delta = [&]() -> int {
     const int64_t warps = (int64_t)a.B * a.H * a.Sq;
     if (a.D == 64 && fmt == 1 && tma_ok4(args->dout, a.o_sb, a.o_sh, a.o_ss) && tma_ok4(a.o, a.o_sb, a.o_sh, a.o_ss))
-      attn_delta64_kernel<<<(unsigned)((warps * 8 + 255) / 256), 256, 0, st>>>(
-          (const __nv_bfloat16*)args->dout, (const __nv_bfloat16*)a.o, a.o_sb, a.o_sh, a.o_ss, args->delta, a.B,
-          a.H, a.Sq);
+      CT_CUDA_OK(launch_k(attn_delta64_kernel, dim3((unsigned)((warps * 8 + 255) / 256)), dim3(256), 0, st,
+                          (const __nv_bfloat16*)args->dout, (const __nv_bfloat16*)a.o, a.o_sb, a.o_sh, a.o_ss,
+                          args->delta, a.B, a.H, a.Sq));
     else
       attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
           args->dout, a.o, fmt, a.o_sb, a.o_sh, a.o_ss, args->delta, a.B, a.H, a.Sq, a.D);
     CT_LAUNCH_OK();
-  }
+    return 0;
+  };
   const bool tc_ok = a.D == 64 && tma_ok4(a.q, a.q_sb, a.q_sh, a.q_ss) &&
                      tma_ok4(a.k, a.k_sb, a.k_sh, a.k_ss) && tma_ok4(a.v, a.v_sb, a.v_sh, a.v_ss) &&
                      tma_ok4(args->dout, a.o_sb, a.o_sh, a.o_ss) &&
@@ -1879,6 +1893,7 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     // [b][h][query tile][d/4][row][4]
     const size_t dq_elems = (size_t)a.B * a.H * nqt * FB_DQ_TILE;
     CT_CUDA_OK(cudaMemsetAsync(args->dq_accum, 0, sizeof(float) * dq_elems, st));
+    if ((rc = launch_delta())) return rc;
     static bool attr = false;
     if (!attr) {
       CT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_PIPE));
@@ -1891,21 +1906,25 @@ extern "C" int ct_attn_bwd(const ct_attn_bwd_args* args, void* stream) {
     // ATTN_BWD_IMPL: 0 (default) / 2 = 16 compute warps (one 32-query chunk each), heaviest key tiles first: 154 vs
     // 179 us per call at the bench shape, identical bits (profiles/r02r_ab_attention.jsonl); 1 = 8 compute warps
     if (option(OPT_ATTN_BWD_IMPL) != 1) {
-      if (fmt == 1) attn_bwd_tc2_kernel<true, 7><<<g, FB_THREADS_WIDE, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
-      else attn_bwd_tc2_kernel<false, 7><<<g, FB_THREADS_WIDE, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
+      if (fmt == 1)
+        CT_CUDA_OK(launch_k(attn_bwd_tc2_kernel<true, 7>, dim3(g), dim3(FB_THREADS_WIDE), FB_SMEM_PIPE, st, tmQ, tmK, tmV, tmDO, bp));
+      else
+        CT_CUDA_OK(launch_k(attn_bwd_tc2_kernel<false, 7>, dim3(g), dim3(FB_THREADS_WIDE), FB_SMEM_PIPE, st, tmQ, tmK, tmV, tmDO, bp));
     } else {
-      if (fmt == 1) attn_bwd_tc2_kernel<true, 3><<<g, FB_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
-      else attn_bwd_tc2_kernel<false, 3><<<g, FB_THREADS, FB_SMEM_PIPE, st>>>(tmQ, tmK, tmV, tmDO, bp);
+      if (fmt == 1)
+        CT_CUDA_OK(launch_k(attn_bwd_tc2_kernel<true, 3>, dim3(g), dim3(FB_THREADS), FB_SMEM_PIPE, st, tmQ, tmK, tmV, tmDO, bp));
+      else
+        CT_CUDA_OK(launch_k(attn_bwd_tc2_kernel<false, 3>, dim3(g), dim3(FB_THREADS), FB_SMEM_PIPE, st, tmQ, tmK, tmV, tmDO, bp));
     }
     CT_LAUNCH_OK();
     const int64_t n = (int64_t)(dq_elems / 8);
     int64_t blocks = (n + 255) / 256;
     if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
-    attn_dq_convert_tiled_kernel<<<(unsigned)blocks, 256, 0, st>>>(args->dq_accum, args->dq, fmt, args->dq_sb,
-                                                                   args->dq_sh, args->dq_ss, a.B, a.H, a.Sq);
-    CT_LAUNCH_OK();
+    CT_CUDA_OK(launch_k(attn_dq_convert_tiled_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (const float*)args->dq_accum,
+                        args->dq, fmt, args->dq_sb, args->dq_sh, args->dq_ss, a.B, a.H, a.Sq));
     return 0;
   }
+  if ((rc = launch_delta())) return rc;
   SimtBwdP bp;
   fill_common(bp.s.a, a);
   bp.s.D = a.D;

@@ -89,8 +89,8 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
 static int g_opt[OPT_COUNT];
 static std::once_flag g_opt_once;
 static const char* const kOptNames[OPT_COUNT] = {"LN_BWD_IMPL", "GEMM_EPI_IMPL",
-                                                 "GEMM_2CTA", "CE_IMPL", "GEMM_SPLITK", "ATTN_BWD_IMPL"};
-static const int kOptDefaults[OPT_COUNT] = {0, 0, 1, 0, 0, 0};
+                                                 "GEMM_2CTA", "CE_IMPL", "GEMM_SPLITK", "ATTN_BWD_IMPL", "PDL"};
+static const int kOptDefaults[OPT_COUNT] = {0, 0, 1, 0, 0, 0, 0};
 static void opt_init() {
   std::call_once(g_opt_once, [] {
     for (int i = 0; i < OPT_COUNT; ++i) {

@@ -53,10 +53,35 @@ const char* get_error();
 
 int sm_count();  // cached multiprocessor count of the current device
 
+// ---- programmatic dependent launch -----------------------------------------------------------------------------------
+// A training step is ~620 kernels, a decode step ~170, each waiting for the previous grid to drain before its own launch
+// latency even starts: 3.0 - 3.5 ms of a 38 ms step were idle gaps between graph nodes (profiles/r02t_bench.json).
+// Kernels launched through launch_k() carry cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may become
+// resident while the previous kernel is still running (it allows that with pdl_launch_dependents() at its top) and run
+// their prologue — barrier init, TMEM allocation, descriptor prefetch — until pdl_wait(), which returns once the previous
+// grid has completed and its memory is visible. EVERY kernel launched this way calls pdl_wait() before its first access to
+// global memory; without the attribute both instructions are no-ops. PDL option: 0 = default (on), 2 = off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // Tuning knobs (ct_set_option / CT_<NAME> environment variables); 0 always means "default / auto".
 enum : int { OPT_LN_BWD_IMPL = 0, OPT_GEMM_EPI_IMPL, OPT_GEMM_2CTA, OPT_CE_IMPL,
-             OPT_GEMM_SPLITK, OPT_ATTN_BWD_IMPL, OPT_COUNT };
+             OPT_GEMM_SPLITK, OPT_ATTN_BWD_IMPL, OPT_PDL, OPT_COUNT };
 int option(int which);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = option(OPT_PDL) == 2 ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // dtype enum shared with include/ct_b200.h
 enum : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };

@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(256)
     colsum_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, float* __restrict__ out,
                          int64_t rows, int64_t cols, int64_t rows_per_block) {
   __shared__ float red[8][256 + 8];
+  pdl_wait();               // programmatic dependent launch: see ct_common.cuh
+  pdl_launch_dependents();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c0 = (int64_t)blockIdx.x * 256 + tx * 8;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
@@ -210,7 +212,7 @@ extern "C" int ct_colsum(const void* x, int x_dtype, int64_t ld, float* out, int
     if (rpb8 < 64) rpb8 = 64;
     slabs8 = (rows + rpb8 - 1) / rpb8;
     dim3 grid8((unsigned)strips8, (unsigned)slabs8);
-    colsum_bf16x8_kernel<<<grid8, 256, 0, st>>>((const __nv_bfloat16*)x, ld, out, rows, cols, rpb8);
+    CT_CUDA_OK(launch_k(colsum_bf16x8_kernel, grid8, dim3(256), 0, st, (const __nv_bfloat16*)x, ld, out, rows, cols, rpb8));
     CT_LAUNCH_OK();
     return 0;
   }

@@ -653,6 +653,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();               // programmatic dependent launch: see ct_common.cuh
+  pdl_launch_dependents();
 
   // work item -> (m_blk, n_blk, split): m fastest inside groups of `group_m` m-tiles so that the
   // CTAs resident at one time share a handful of A row-panels and B column-panels in L2.
@@ -878,6 +880,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
   cluster_sync_all();  // barrier inits + TMEM allocation visible to the peer before any remote access
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // everything above touched shared memory, TMEM and kernel parameters only: it may run under the previous kernel's tail
+  pdl_wait();               // programmatic dependent launch: see ct_common.cuh
+  pdl_launch_dependents();
 
   auto decode = [&](int w, int& m_blk, int& n_blk, int& split) {
     split = w % p.split_k;
@@ -1138,6 +1143,8 @@ __global__ void __launch_bounds__(SK_WARPS * 32, SK_WARPS == 8 ? 2 : 1)
                        int K, const EpiParams e) {
   constexpr int FT = 8 * G;  // output features per CTA
   __shared__ float red[SK_WARPS][G * 8][32];
+  pdl_wait();               // programmatic dependent launch: see ct_common.cuh
+  pdl_launch_dependents();
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   const int n0 = blockIdx.x * FT;
@@ -1268,7 +1275,7 @@ static int launch_tc(const ct_gemm_args& a, const EpiParams& e, int split_k, cud
   int64_t work = (int64_t)m_tiles * n_tiles * split_k;
   int grid = sm_count();
   if (work < grid) grid = (int)work;
-  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p, e);
+  CT_CUDA_OK(launch_k(gemm_tcgen05_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, p, e));
   CT_LAUNCH_OK();
   return 0;
 }
@@ -1283,7 +1290,7 @@ static int launch_2cta_kind(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
                                     SMEM2_BYTES));
     attr_set = true;
   }
-  gemm_tcgen05_2cta_kernel<EPIK><<<2 * pairs, GEMM_THREADS, SMEM2_BYTES, st>>>(tmA, tmB, p, e);
+  CT_CUDA_OK(launch_k(gemm_tcgen05_2cta_kernel<EPIK>, dim3(2 * pairs), dim3(GEMM_THREADS), SMEM2_BYTES, st, tmA, tmB, p, e));
   CT_LAUNCH_OK();
   return 0;
 }
@@ -1405,7 +1412,11 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
   const bool skinny_ok = a.M <= 32 && !a.a_mn_major && !a.b_mn_major && tma_ok && (a.K % 32 == 0) && !a.row_stats;
   CT_REQUIRE(a.impl != 4 || skinny_ok, CT_ERR_UNSUPPORTED,
              "ct_gemm: the skinny kernel needs M <= 32, K-major A and B, K %% 32 == 0, 16-byte aligned rows");
-  if (skinny_ok && (a.impl == 4 || (a.impl == 0 && (int64_t)a.N * a.K >= (1 << 16)))) {
+  // (a very wide, 16-byte addressable output — Bloom's 250 880-column LM head — is still served better by the 128-row
+  // tcgen05 kernel: 108 vs 229 us at M = 32, profiles/r02o_skinny.json; GPT-2's 50 257 columns are not addressable that
+  // way and take the skinny kernel: 57 vs 138 us)
+  const bool very_wide = a.N >= 131072 && (a.N % 8 == 0) && (a.ldc % 8 == 0) && al16(a.C);
+  if (skinny_ok && (a.impl == 4 || (a.impl == 0 && !very_wide && (int64_t)a.N * a.K >= (1 << 16)))) {
     const uint16_t* A16 = (const uint16_t*)a.A;
     const uint16_t* B16 = (const uint16_t*)a.B;
     const bool bf = a.ab_dtype == DT_BF16;
@@ -1414,7 +1425,8 @@ extern "C" int ct_gemm(const ct_gemm_args* args, void* stream) {
     // features per CTA: wide tiles amortise the token rows (read once per CTA) when there are CTAs to spare
     const int g = ((a.N + 31) / 32 >= 2 * sms2) ? 4 : ((a.N + 15) / 16 >= sms2) ? 2 : 1;
 #define CT_SK_GO(G, W, BF, LEAN) \
-  gemm_skinny_kernel<G, W, BF, LEAN><<<(unsigned)((a.N + 8 * G - 1) / (8 * G)), W * 32, 0, st>>>(A16, a.lda, B16, a.ldb, a.K, e)
+  CT_CUDA_OK(launch_k(gemm_skinny_kernel<G, W, BF, LEAN>, dim3((unsigned)((a.N + 8 * G - 1) / (8 * G))), dim3(W * 32), 0, st, \
+                      A16, a.lda, B16, a.ldb, a.K, e))
 #define CT_SK_PICK(G, W)                                  \
   do {                                                    \
     if (bf && lean) CT_SK_GO(G, W, true, true);           \

@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * LN_WARPS;
+  pdl_wait();               // programmatic dependent launch: see ct_common.cuh
+  pdl_launch_dependents();
 
   float4 g[VPL], b[VPL];
 #pragma unroll
@@ -449,6 +451,8 @@ __global__ void __launch_bounds__(NW * 64, 2)
   constexpr int COLS = NW * 128, TPR = NW * 32;
   __shared__ __align__(16) float red[2][2][4][8];  // [half][iteration parity][quantity][warp (zero padded)]
   __shared__ __align__(16) float comb[3 * COLS];
+  pdl_wait();               // programmatic dependent launch: see ct_common.cuh
+  pdl_launch_dependents();
   const int half = threadIdx.x >= TPR ? 1 : 0;
   const int t = threadIdx.x - half * TPR;
   const int lane = t & 31, wih = t >> 5;
@@ -540,20 +544,21 @@ __global__ void __launch_bounds__(NW * 64, 2)
 }
 
 template <int NW>
-static void launch_ln_bwd_fast(const ct_ln_bwd_args& a, int grid, cudaStream_t st) {
+static int launch_ln_bwd_fast(const ct_ln_bwd_args& a, int grid, cudaStream_t st) {
   const float* x = reinterpret_cast<const float*>(a.x);
   const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(a.dy);
   const float* add = reinterpret_cast<const float*>(a.dx_add);
   float* dx = reinterpret_cast<float*>(a.dx);
   __nv_bfloat16* dx2 = reinterpret_cast<__nv_bfloat16*>(a.dx2);
 #define CT_LNF(A, D)                                                                                         \
-  ln_bwd_fast_kernel<NW, A, D><<<grid, NW * 64, 0, st>>>(x, dy, a.gamma, a.mean, a.rstd, add, dx, dx2, a.dgamma, \
-                                                          a.dbeta, a.dxsum, a.workspace, a.rows)
+  CT_CUDA_OK(launch_k(ln_bwd_fast_kernel<NW, A, D>, dim3(grid), dim3(NW * 64), 0, st, x, dy, a.gamma, a.mean, a.rstd, add, \
+                      dx, dx2, a.dgamma, a.dbeta, a.dxsum, a.workspace, a.rows))
   if (add && dx2) CT_LNF(true, true);
   else if (add) CT_LNF(true, false);
   else if (dx2) CT_LNF(false, true);
   else CT_LNF(false, false);
 #undef CT_LNF
+  return 0;
 }
 
 // second stage of v2: out_which[c] (+)= sum_b partial[b][which][c]; CTA = 32 columns x 8 row groups
@@ -561,6 +566,8 @@ __global__ void __launch_bounds__(256)
     ln_bwd_reduce3_kernel(const float* __restrict__ partial, int nblocks, int cols, float* __restrict__ dgamma,
                           float* __restrict__ dbeta, float* __restrict__ dxsum, int acc_gb, int acc_sum) {
   __shared__ float sm[8][33];
+  pdl_wait();               // programmatic dependent launch: see ct_common.cuh
+  pdl_launch_dependents();
   const int which = blockIdx.y;
   float* out = which == 0 ? dgamma : (which == 1 ? dbeta : dxsum);
   if (out == nullptr) return;  // CTA-uniform
@@ -657,8 +664,8 @@ extern "C" int ct_layernorm_fwd(const void* x, int x_dtype, const float* gamma, 
                    aligned16(y2) && aligned16(gamma) && aligned16(beta);
 #define CT_LN_FWD(V)                                                                           \
   case V:                                                                                      \
-    ln_fwd_vec_kernel<V><<<grid, LN_WARPS * 32, 0, st>>>(x, x_dtype, gamma, beta, y, y_dtype,  \
-                                                         y2, y2_dtype, mean, rstd, rows, eps); \
+    CT_CUDA_OK(launch_k(ln_fwd_vec_kernel<V>, dim3(grid), dim3(LN_WARPS * 32), 0, st, x, x_dtype, gamma, beta, y, \
+                        y_dtype, y2, y2_dtype, mean, rstd, rows, eps));                                         \
     break;
   if (vec) {
     switch ((int)(cols / 128)) {
@@ -773,13 +780,13 @@ extern "C" int ct_layernorm_bwd_ex(const ct_ln_bwd_args* args, void* stream) {
                       a.dy_dtype == DT_BF16 && !a.dy2 && (!a.dx_add || a.dx_add_dtype == DT_F32) &&
                       a.dx_dtype == DT_F32 && (!a.dx2 || a.dx2_dtype == DT_BF16) && (!want_red || use_ws);
     if (fast) {
-      if (cols == 1024) launch_ln_bwd_fast<8>(a, grid, st);
-      else launch_ln_bwd_fast<6>(a, grid, st);
+      const int lrc = cols == 1024 ? launch_ln_bwd_fast<8>(a, grid, st) : launch_ln_bwd_fast<6>(a, grid, st);
+      if (lrc) return lrc;
       CT_LAUNCH_OK();
       if (use_ws) {
         dim3 g2((unsigned)((cols + 31) / 32), 3);
-        ln_bwd_reduce3_kernel<<<g2, 256, 0, st>>>(a.workspace, grid, (int)cols, a.dgamma, a.dbeta, a.dxsum,
-                                                  a.dgb_accumulate, a.dxsum_accumulate);
+        CT_CUDA_OK(launch_k(ln_bwd_reduce3_kernel, g2, dim3(256), 0, st, a.workspace, (int)grid, (int)cols, a.dgamma, a.dbeta,
+                            a.dxsum, a.dgb_accumulate, a.dxsum_accumulate));
         CT_LAUNCH_OK();
       }
       return 0;

@@ -216,7 +216,7 @@ def test_skinny_gemm_vs_fp32_and_vs_the_tcgen05_kernel(M, N, K, dtype):
     y = ops.gemm(x, w, M, N, K, out_dtype=torch.float32, impl=4)
     assert (y - ref_lin).abs().max() <= 2e-5 * K ** 0.5 * max(1.0, float(ref_lin.abs().max()))
     y_auto = ops.gemm(x, w, M, N, K, out_dtype=torch.float32)
-    if K % 32 == 0 and N * K >= (1 << 16):
+    if K % 32 == 0 and N * K >= (1 << 16) and N < 131072:  # (Bloom's 250 880-wide head stays on the tcgen05 kernel)
         assert torch.equal(y, y_auto), "auto dispatch must pick the skinny kernel for M <= 32"
     y_tc = ops.gemm(x, w, M, N, K, out_dtype=torch.float32, impl=1)
     assert (y - y_tc).abs().max() <= 1e-4 * max(1.0, float(ref_lin.abs().max()))
