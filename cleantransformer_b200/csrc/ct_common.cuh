@@ -60,7 +60,11 @@ int sm_count();  // cached multiprocessor count of the current device
 // resident while the previous kernel is still running (it allows that with pdl_launch_dependents() at its top) and run
 // their prologue — barrier init, TMEM allocation, descriptor prefetch — until pdl_wait(), which returns once the previous
 // grid has completed and its memory is visible. EVERY kernel launched this way calls pdl_wait() before its first access to
-// global memory; without the attribute both instructions are no-ops. PDL option: 0 = default (on), 2 = off.
+// global memory; without the attribute both instructions are no-ops.
+// PDL option: 1 = on, 2 = off, 0 = auto: off, except inside the captured decode step (generation.py switches it on
+// around the capture). Measured (profiles/r02u_*, r02v_*): decode +9 %; training step on one GPU +3 % / -4 % (inside the
+// noise of a power-capped box); under DistributedDataParallel -12 % at two GPUs — the pre-launched CTAs of the compute
+// chain take the SM slots that the bucket all-reduce kernels of the side stream used to slip into.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -79,7 +83,7 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = option(OPT_PDL) == 2 ? 0 : 1;
+  cfg.numAttrs = option(OPT_PDL) == 1 ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

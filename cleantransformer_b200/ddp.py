@@ -95,7 +95,7 @@ class DistributedDataParallel(torch.nn.Module):
             raise RuntimeError("comm='p2p' needs CUDA parameters")
         self._peer_mem = self.comm == "p2p"
         self.nvls = False
-        self.max_ctas = int(os.environ.get("CT_DDP_CTAS", 0)) or None  # None: 16 with NVLS, else `max_ctas`
+        self.max_ctas = int(os.environ.get("CT_DDP_CTAS", 0)) or None  # None: 16 / 32 with NVLS (see _launch), else `max_ctas`
         self._max_ctas_unicast = max_ctas
         self.final_ctas = int(os.environ.get("CT_DDP_FINAL_CTAS", 148))
         grad_buf = None
@@ -356,7 +356,9 @@ class DistributedDataParallel(torch.nn.Module):
             with torch.cuda.stream(self._comm_stream):
                 # buckets launched after backward has finished have nothing to overlap with: use every SM
                 if self.nvls:
-                    mode, ctas = 2, (64 if final else (self.max_ctas or 16))
+                    # per rank 1/W of a bucket crosses the SM: 16 CTAs at 8 ranks (8 / 16 / 32: 40.4 / 40.2 / 40.7 ms per
+                    # step, r02i), 32 below (2 ranks: 42.1 ms with 16, 40.6 with 32, r02e)
+                    mode, ctas = 2, (64 if final else (self.max_ctas or (16 if self.world >= 8 else 32)))
                 else:
                     mode, ctas = 3, (self.final_ctas if final else (self.max_ctas or self._max_ctas_unicast))
                 _lib.check(_lib.load().ct_allreduce_bucket(lo, hi - lo, 1.0 / self.world, mode, ctas,

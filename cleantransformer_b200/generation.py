@@ -196,6 +196,17 @@ class GenerationMixin:
 
         n_steps = n_emit - 1  # q_len = 1 steps still to run
         mark("prefill")
+        # programmatic dependent launch for the ~170 few-microsecond kernels of a decode step (csrc/ct_common.cuh): +9 %;
+        # the option is left alone when the user forced it on or off (CT_PDL = 1 / 2)
+        pdl_prev = ops.set_option("PDL", 1) if ops.get_option("PDL") == 0 else None
+        try:
+            return self._graphed_greedy_steps(step, finished, n_steps, mark, trace, marks, state, ids_out, end_ids,
+                                              bsz, P, n_emit)
+        finally:
+            if pdl_prev is not None:
+                ops.set_option("PDL", pdl_prev)
+
+    def _graphed_greedy_steps(self, step, finished, n_steps, mark, trace, marks, state, ids_out, end_ids, bsz, P, n_emit):
         if n_steps > 0 and not finished():
             step()  # first decode step outside the capture: lazy kernel attributes, and it is a real step
             n_steps -= 1

@@ -72,6 +72,12 @@ def set_option(name, value):
     return old.value
 
 
+def get_option(name):
+    old = ctypes.c_int(0)
+    check(_lib.load().ct_get_option(name.encode(), ctypes.byref(old)), "ct_get_option")
+    return old.value
+
+
 def device_check(device=None):
     dev = torch.cuda.current_device() if device is None else device
     check(_lib.load().ct_device_check(int(dev)), "ct_device_check")  # no launch
