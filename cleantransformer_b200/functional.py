@@ -310,10 +310,14 @@ class DropoutFn(torch.autograd.Function):
 
 
 def dropout(x, p, training, residual=None, out_dtype=None):
-    """residual + dropout(x) (or dropout(x)); identity (+ residual) when not training or p == 0."""
+    """residual + dropout(x) (or dropout(x)); identity (+ residual) when not training or p == 0 — the residual add then
+    runs through the same kernel with p = 0 (no ATen add on the path: transformer.py:109-111 has no GEMM to carry it)."""
+    od = out_dtype or (residual.dtype if residual is not None else x.dtype)
     if not training or p <= 0:
-        return x if residual is None else (x + residual if out_dtype is None else (x.to(out_dtype) + residual.to(out_dtype)))
-    return DropoutFn.apply(x, residual, next_dropout(p), out_dtype or (residual.dtype if residual is not None else x.dtype))
+        if residual is None:
+            return x if x.dtype == od else x.to(od)
+        return DropoutFn.apply(x, residual, (0.0, 0, 0), od)
+    return DropoutFn.apply(x, residual, next_dropout(p), od)
 
 
 LAYOUT_BLOOM = "bloom"        # fused [B,S,H,3,D]   (modeling_bloom.py:81-82)
