@@ -62,8 +62,8 @@ int sm_count();  // cached multiprocessor count of the current device
 // grid has completed and its memory is visible. EVERY kernel launched this way calls pdl_wait() before its first access to
 // global memory; without the attribute both instructions are no-ops.
 // PDL option: 1 = on, 2 = off, 0 = auto: off, except inside the captured decode step (generation.py switches it on
-// around the capture). Measured (profiles/r02u_*, r02v_*): decode +9 %; training step on one GPU +3 % / -4 % (inside the
-// noise of a power-capped box); under DistributedDataParallel -12 % at two GPUs — the pre-launched CTAs of the compute
+// around the capture). Measured (profiles/r02u_*, r02v_*, r02x_*): decode +9 %; training step on one GPU +0.6 % (three
+// alternating pairs of runs on a power-capped box); under DistributedDataParallel -12 % at two GPUs — the pre-launched CTAs of the compute
 // chain take the SM slots that the bucket all-reduce kernels of the side stream used to slip into.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
