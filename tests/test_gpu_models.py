@@ -9,6 +9,8 @@ the tensor maximum, so for tensors that pass through bf16 storage the test is
     err(ours) <= max(1.5 * err(reference bf16 autocast path), 4e-3)
 i.e. we must be at least as close to the fp32 reference as the reference's own bf16 path is (up to
 the bf16 quantum); fp32-resident quantities (loss) must meet 1e-3 directly. Token ids: bit-exact.
+Every error measured by this module is written to gpurun_out/r02_model_test_errors.json (committed copy:
+profiles/r02_model_test_errors.json); fixed bounds above one quantum are the observed value x 1.5.
 """
 import pytest
 import torch
@@ -24,8 +26,47 @@ def _cuda_sd(sd):
     return {k: v.to(DEV) for k, v in sd.items()}
 
 
+OBSERVED = {}   # every measured error of this module, dumped to gpurun_out/r02_model_test_errors.json (and committed under
+                # profiles/): the floors below are the observed values x 1.5, not round numbers
+
+
+def _note(err, bound, ref=None):
+    import inspect
+    fr = inspect.stack()[2]
+    OBSERVED.setdefault("%s:%d" % (fr.function, fr.lineno), []).append(
+        {"err": float(err), "bound": float(bound), "autocast_oracle_err": None if ref is None else float(ref)})
+
+
 def _bound(err_ours, err_ref, floor=4e-3):
+    _note(err_ours, max(1.5 * err_ref, floor), err_ref)
     assert err_ours <= max(1.5 * err_ref, floor), (err_ours, err_ref)
+
+
+def _below(err, bound):
+    _note(err, bound)
+    assert err < bound, (err, bound)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump_observed():
+    yield
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        def floor_bound(v):  # entries whose bound is the floor, not 1.5 x the autocast oracle's own error
+            return [x for x in v if x["autocast_oracle_err"] is None or 1.5 * x["autocast_oracle_err"] < x["bound"]]
+
+        worst = {k: {"max_err": max(x["err"] for x in v), "bound": max(x["bound"] for x in v), "n": len(v),
+                     "max_autocast_oracle_err": max([x["autocast_oracle_err"] or 0.0 for x in v]),
+                     "max_err_over_bound": max(x["err"] / x["bound"] for x in v),
+                     "max_err_where_the_floor_binds": max([x["err"] for x in floor_bound(v)] or [0.0]),
+                     "n_where_the_floor_binds": len(floor_bound(v))} for k, v in OBSERVED.items()}
+        with open(os.path.join(out, "r02_model_test_errors.json"), "w") as f:
+            json.dump(worst, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
 
 
 def test_bloom_tiny_forward_backward(golden):
@@ -75,12 +116,13 @@ def test_bloom_tiny_kv_cache(golden):
         (lp, _), kv = model(input_ids=ids[:, :8], attention_mask=ones[:, :8])
         (ld, _), kv2 = model(input_ids=ids[:, 8:9], attention_mask=ones, k_v_pasts=kv)
         (lf, _), _ = model(input_ids=ids[:, :9], attention_mask=ones)
-    assert rel_err(lp.cpu(), g["logits_prefill8"]) < 1e-2
-    assert rel_err(ld.cpu(), g["logits_decode"]) < 1e-2
-    assert rel_err(lf.cpu(), g["logits_full9"]) < 1e-2
+    # observed 2.7e-3 / 2.1e-3 / 2.7e-3 (profiles/r02_model_test_errors.json): x 1.5 = one bf16 output quantum
+    _below(rel_err(lp.cpu(), g["logits_prefill8"]), 4e-3)
+    _below(rel_err(ld.cpu(), g["logits_decode"]), 4e-3)
+    _below(rel_err(lf.cpu(), g["logits_full9"]), 4e-3)
     assert list(kv2[0][0].shape) == g["kv_shape"]
     # decode step == last position of the full forward (cache consistency inside our own path)
-    assert rel_err(ld[:, 0].float().cpu(), lf[:, 8].float().cpu()) < 1e-2
+    _below(rel_err(ld[:, 0].float().cpu(), lf[:, 8].float().cpu()), 4e-3)  # observed: identical
 
 
 @pytest.mark.parametrize("version", ["gpt2", "gpt"])
@@ -116,10 +158,10 @@ def test_gpt_tiny_logits_generation_and_block_grads(golden, version):
     model.zero_grad()
     y, (k_, v_) = blk(x)
     y.backward(c["blk_dy"].to(DEV))
-    assert rel_err(y.cpu(), c["blk_y"]) < 4e-3
-    assert rel_err(x.grad.cpu(), c["blk_dx"]) < 8e-3
+    _below(rel_err(y.cpu(), c["blk_y"]), 4e-3)
+    _below(rel_err(x.grad.cpu(), c["blk_dx"]), 4e-3)   # observed 1e-4 (fp32 residual stream)
     for name, p in blk.named_parameters():
-        assert rel_err(p.grad.cpu(), c["blk_grads"][name]) < 1e-2, name
+        _below(rel_err(p.grad.cpu(), c["blk_grads"][name]), 7e-3)   # observed 4.7e-3, x 1.5
 
 
 def test_bert_tiny(golden):
@@ -139,7 +181,7 @@ def test_bert_tiny(golden):
                                               cfg["num_attention_heads"], cfg["layer_norm_eps"])
     _bound(rel_err(hidden.cpu(), g["hidden"]), rel_err(h_ac.float().cpu(), g["hidden"]))
     _bound(rel_err(pooled.cpu(), g["pooled"]), rel_err(p_ac.float().cpu(), g["pooled"]))
-    _bound(rel_err(logits.cpu(), g["logits"]), rel_err(lg_ac.float().cpu(), g["logits"]), floor=8e-3)
+    _bound(rel_err(logits.cpu(), g["logits"]), rel_err(lg_ac.float().cpu(), g["logits"]))  # observed 6.7e-4
 
 
 def test_generic_block(golden):
@@ -151,8 +193,8 @@ def test_generic_block(golden):
         y = blk(g["x"].to(DEV))
         add = (1.0 - g["mask"][:, None, None, :]) * -10000.0
         a = blk.attention(g["x"].to(DEV), add.to(DEV))
-    assert rel_err(y.cpu(), g["y"]) < 1e-2
-    assert rel_err(a.cpu(), g["att_masked"]) < 1e-2
+    _below(rel_err(y.cpu(), g["y"]), 5.5e-3)            # observed 3.3e-3, x 1.5 (two bf16-rounded GEMM chains)
+    _below(rel_err(a.cpu(), g["att_masked"]), 5.5e-3)   # observed 3.5e-3
     assert T.MultiHeadAttention is T.AttentionLayer
 
 
@@ -245,7 +287,8 @@ def test_bloom_medium_training_step_vs_autocast_oracle():
     _bound(rel_err(logits, lg32), rel_err(lg16, lg32))
     for name, p in model.named_parameters():
         key = "bloom.word_embeddings.weight" if name == "lm_head.weight" else name
-        _bound(rel_err(p.grad, sd32[key].grad), rel_err(sd16[key].grad, sd32[key].grad), floor=8e-3)
+        # where the floor binds (the autocast oracle itself below 3.7e-3) the observed maximum is 3.5e-3: x 1.5
+        _bound(rel_err(p.grad, sd32[key].grad), rel_err(sd16[key].grad, sd32[key].grad), floor=5.5e-3)
     before = {n: p.detach().clone() for n, p in model.named_parameters()}
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
     optim.step()
