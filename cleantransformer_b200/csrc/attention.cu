@@ -837,10 +837,15 @@ __global__ void __launch_bounds__((MODE & 4) ? FB_THREADS_WIDE : FB_THREADS, 1)
     const bool fill_is_ninf = p.causal_fill2 == -INFINITY;
     const float* lse_bh = p.lse2 + ((int64_t)b * p.H + h) * p.Sq;
     const float* del_bh = bp.delta + ((int64_t)b * p.H + h) * p.Sq;
+    // Per-query statistics of this warp's chunk, staged as -lse2 and -delta*scale: lane l fetches query 32*c + l. The four
+    // warps that share chunk c write identical values to the same words, so a __syncwarp is all a warp needs before it
+    // reads them back (no CTA-wide barrier per tile); buffer (it & 1) is rewritten at tile it+2, which a warp reaches only
+    // after every warp has arrived at sdp_free(it+1), i.e. has finished reading tile it's statistics.
+    const int sq = 32 * c + lane;  // this lane's query inside the tile
     float nlse_next = -INFINITY, ndel_next = 0.f;
-    if (c == 0 && n_it > 0 && i_start * 128 + rr < p.Sq) {
-      nlse_next = -__ldg(lse_bh + i_start * 128 + rr);
-      ndel_next = -__ldg(del_bh + i_start * 128 + rr) * p.scale;
+    if (n_it > 0 && i_start * 128 + sq < p.Sq) {
+      nlse_next = -__ldg(lse_bh + i_start * 128 + sq);
+      ndel_next = -__ldg(del_bh + i_start * 128 + sq) * p.scale;
     }
     // dQ of query tile `itp`: this thread owns query row (q0 + rr), columns [16*c, 16*c + 16) of d
     auto red_dq16 = [&](const uint32_t (&r)[16], int itp) {
@@ -871,16 +876,12 @@ __global__ void __launch_bounds__((MODE & 4) ? FB_THREADS_WIDE : FB_THREADS, 1)
       // the chunk in two halves of 16 queries (32 live S^T / dP^T registers instead of 64)
       uint32_t rs[16], rd[16];
       if (kind != 1) { tmem_ld_32x16(T_ST + t_lane + c * 32, rs); tmem_ld_32x16(T_DPT + t_lane + c * 32, rd); }
-      // statistics buffer (it & 1) was last read by tile it-2; every thread finished tile it-2 before it arrived at the
-      // named barrier of tile it-1, which this thread has passed
-      if (c == 0) {
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.lse_s + 4 * rr), "f"(nlse_next) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.del_s + 4 * rr), "f"(ndel_next) : "memory");
-      }
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.lse_s + 4 * sq), "f"(nlse_next) : "memory");
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(cx.del_s + 4 * sq), "f"(ndel_next) : "memory");
       tmem_ld_wait();
-      bar_sync_named(1, N_COMPUTE);       // statistics staged by the c == 0 warps are visible
-      if (c == 0) {
-        const int nq = q0 + 128 + rr;
+      __syncwarp();                       // this warp's 32 statistics are visible to its lanes
+      {
+        const int nq = q0 + 128 + sq;
         const bool ok = (it + 1 < n_it) && nq < p.Sq;
         nlse_next = ok ? -__ldg(lse_bh + nq) : -INFINITY;
         ndel_next = ok ? -__ldg(del_bh + nq) * p.scale : 0.f;

@@ -131,7 +131,10 @@ def attn_ab():
         ref = _attn_oracle(qr, kr, vr, scale, True, fill, kb2[:nb].expand(nb, H, S) if kb2 is not None else None)
         do = torch.randn(B, S, H * D, device=DEV).bfloat16()
         ref.backward(do[:nb].float())
-        for impl in ("bwd_8_compute_warps", "bwd_16_compute_warps"):  # ATTN_BWD_IMPL 1 / 2 = default (same forward)
+        impls = ("bwd_8_compute_warps", "bwd_16_compute_warps")  # ATTN_BWD_IMPL 1 / 2 = default (same forward)
+        if os.environ.get("CT_AB_ONLY_DEFAULT"):
+            impls = impls[1:]
+        for impl in impls:
             prev = ops.set_option("ATTN_BWD_IMPL", 2 if impl.startswith("bwd_16") else 1)
             try:
                 o, lse2 = ops.attn_fwd(q, k, v, scale, True, fill, kb2, fv)
