@@ -1816,7 +1816,7 @@ extern "C" int ct_attn_fwd(const ct_attn_args* args, void* stream) {
   sp.q_sb = a.q_sb; sp.q_sh = a.q_sh; sp.q_ss = a.q_ss;
   sp.k_sb = a.k_sb; sp.k_sh = a.k_sh; sp.k_ss = a.k_ss;
   sp.v_sb = a.v_sb; sp.v_sh = a.v_sh; sp.v_ss = a.v_ss;
-  const bool decode = a.Sq == 1 && (a.D == 32 || a.D == 64 || a.D == 128) && a.lse2 == nullptr &&
+  const bool decode = a.Sq == 1 && a.dropout_p == 0.f && (a.D == 32 || a.D == 64 || a.D == 128) && a.lse2 == nullptr &&
                       tma_ok4(a.q, a.q_sb, a.q_sh, 8) && tma_ok4(a.k, a.k_sb, a.k_sh, a.k_ss) &&
                       tma_ok4(a.v, a.v_sb, a.v_sh, a.v_ss);
   CT_REQUIRE((a.k_new == nullptr) == (a.v_new == nullptr), CT_ERR_BAD_ARG, "ct_attn_fwd: k_new and v_new come together");

@@ -394,9 +394,10 @@ class SeparateAttentionFn(torch.autograd.Function):
         return dq, dk, dv, None, None, None, None, None, None, None
 
 
-def attention_cached(q4, k4, v4, scale, causal, causal_fill, kbias2, first_valid):
-    """Inference with a KV cache: q4 [B,H,Sq,D], k4/v4 [B,H,Sk,D] (any strides). No autograd."""
-    o, _ = ops.attn_fwd(q4, k4, v4, scale, causal, causal_fill, kbias2, first_valid, need_lse=False)
+def attention_cached(q4, k4, v4, scale, causal, causal_fill, kbias2, first_valid, drop=None):
+    """Inference with a KV cache: q4 [B,H,Sq,D], k4/v4 [B,H,Sk,D] (any strides). No autograd. `drop`: the reference's
+    generate() on a model left in train mode applies its attention dropout here as well."""
+    o, _ = ops.attn_fwd(q4, k4, v4, scale, causal, causal_fill, kbias2, first_valid, need_lse=False, dropout=drop)
     return o
 
 

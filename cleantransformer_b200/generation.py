@@ -89,6 +89,7 @@ class GenerationMixin:
         if (not do_sample and steamers is None and _on_device(input_ids) and position_ids is None and segment_ids is None
                 and attention_mask is not None and getattr(self, "_ct_graph_decode", False) and self._decode_graph_ok()
                 and os.environ.get("CT_DECODE_GRAPH", "1") != "0" and max_gen_len >= 1
+                and not self.training  # (train mode may have dropout active: its mask counter is host state)
                 and bool((attention_mask[:, -1] != 0).all())):
             return self._graphed_greedy(input_ids, attention_mask, end_ids_tensor, max_gen_len, pad_id)
         caches = [None] * self.config.n_layer

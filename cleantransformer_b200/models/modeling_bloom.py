@@ -144,8 +144,6 @@ class BloomAttentionLayer(torch.nn.Module):
                                   kv_new=(k, v))  # the kernel appends k, v itself
             out = F.linear(ctx, self.dense.weight, self.dense.bias, residual=residual)
             return out, k_v_past
-        if a_drop is not None and not (k_v_past is None and torch.is_grad_enabled() and qkv.requires_grad):
-            raise NotImplementedError("attention dropout in training mode with a KV cache / without autograd")
         if k_v_past is None and torch.is_grad_enabled() and qkv.requires_grad:
             ctx = F.PackedAttentionFn.apply(qkv, self.num_heads, F.LAYOUT_BLOOM, self.inv_norm_factor,
                                             bias.causal, -ops.FLT_MAX, bias.kbias2, bias.first_valid, a_drop)
@@ -160,7 +158,7 @@ class BloomAttentionLayer(torch.nn.Module):
                 k = torch.cat((k_v_past[0], k), dim=-2)
                 v = torch.cat((k_v_past[1], v), dim=-2)
             ctx = F.attention_cached(q, k, v, self.inv_norm_factor, bias.causal, -ops.FLT_MAX,
-                                     bias.kbias2, bias.first_valid)
+                                     bias.kbias2, bias.first_valid, a_drop)
         if h_on:
             out = F.dropout(F.linear(ctx, self.dense.weight, self.dense.bias, out_dtype=torch.float32),
                             self.hidden_dropout, True, residual=residual)

@@ -132,8 +132,6 @@ class AttentionLayer(torch.nn.Module):
                                   seq_len_dev=k_v_past.len_dev, kv_new=(k, v))  # the kernel appends k, v itself
             out = self.c_proj(ctx, residual=residual, out_dtype=None if residual is not None else torch.float32)
             return out, k_v_past
-        if a_drop is not None and not (k_v_past is None and torch.is_grad_enabled() and qkv.requires_grad):
-            raise NotImplementedError("attention dropout in training mode with a KV cache / without autograd")
         if k_v_past is None and torch.is_grad_enabled() and qkv.requires_grad:
             ctx = F.PackedAttentionFn.apply(qkv, self.n_head, F.LAYOUT_GPT, sm_scale, True, -1e4, kb, fv, a_drop)
             _, k, v = F.split_packed(qkv.detach(), self.n_head, F.LAYOUT_GPT)
@@ -146,7 +144,7 @@ class AttentionLayer(torch.nn.Module):
             elif k_v_past is not None:
                 k = torch.cat((k_v_past[0], k), dim=-2)
                 v = torch.cat((k_v_past[1], v), dim=-2)
-            ctx = F.attention_cached(q, k, v, sm_scale, True, -1e4, kb, fv)
+            ctx = F.attention_cached(q, k, v, sm_scale, True, -1e4, kb, fv, a_drop)
         if r_on:  # residual + dropout(c_proj(ctx)) (the caller's add, TransformerBlock.forward) as one kernel
             out = F.dropout(self.c_proj(ctx, out_dtype=torch.float32), self.resid_dropout.p, True, residual=residual)
         else:

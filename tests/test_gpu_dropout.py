@@ -107,3 +107,23 @@ def test_attention_probability_dropout_fwd_bwd(B, H, Sq, Sk, D, causal, mode, cf
     # p = 0 through the same entry point is the plain kernel, bit for bit
     o_p0, _ = ops.attn_fwd(q, k, v, scale, causal, cfill, kb2, fv, impl=impl, dropout=(0.0, seed, stream))
     assert torch.equal(o_p0, o0)
+
+
+def test_single_query_attention_with_dropout_takes_the_generic_kernel():
+    """q_len = 1 against a cache with attention dropout active (generate() on a model left in train mode, like the
+    reference): the decode kernel has no dropout, so the call must fall back to the kernel that has — and match the
+    restated masks."""
+    from oracle import ct_oracle as O
+    ops = _ops()
+    torch.manual_seed(21)
+    B, H, Sk, D = 2, 4, 37, 64
+    q = torch.randn(B, H, 1, D, device=DEV).bfloat16()
+    k = torch.randn(B, H, Sk, D, device=DEV).bfloat16()
+    v = torch.randn(B, H, Sk, D, device=DEV).bfloat16()
+    p, seed, stream = 0.3, 99, 7
+    o, _ = ops.attn_fwd(q, k, v, 0.125, True, -1e4, None, None, need_lse=False, dropout=(p, seed, stream))
+    keep = O.dropout_mask_attention(B, H, 1, Sk, p, seed, stream, device=DEV)
+    want = _attn_ref(q, k, v, 0.125, True, -1e4, None, keep, p)
+    assert rel_err(o, want) < 6e-3
+    o0, _ = ops.attn_fwd(q, k, v, 0.125, True, -1e4, None, None, need_lse=False)
+    assert not torch.equal(o, o0)

@@ -775,3 +775,36 @@ def test_bloom_and_generic_block_train_mode_dropout_vs_oracle_with_the_same_mask
         y.backward(dy)
         assert rel_err(y, y_ref) < 2e-4 and rel_err(x.grad, xr.grad) < 2e-3
         _grads_match(blk, sdb, at_least=8, floor=1e-6)  # (the key bias gradient is analytically zero)
+
+
+def test_generate_on_a_train_mode_model_takes_the_host_loop_with_dropout_active(golden, monkeypatch):
+    """generation_util.py:57-119 does not switch the model to eval(): called on a model in train mode the reference
+    decodes with its dropout active. The mirror then keeps the host loop (the captured step refuses dropout) and feeds
+    the attention dropout into the cached-attention calls; same masks -> same ids as the oracle."""
+    from cleantransformer_b200 import functional as F
+    from cleantransformer_b200.models import modeling_gpt as mg
+    from oracle import ct_oracle as O
+    torch.manual_seed(5)
+    V, L, NH = 61, 2, 2
+    cfg = dict(vocab_size=V, n_embd=64, n_positions=64, n_layer=L, n_head=NH, n_ctx=64, afn="gelu_new",
+               embd_pdrop=0.1, attn_pdrop=0.2, resid_pdrop=0.1)
+    ids = torch.randint(3, V, (2, 5))
+    mask = torch.ones(2, 5, dtype=torch.long)
+    mask[1, :2] = 0
+    with mock_ops.patched():
+        m = mg.GPTLMHeadModel(mg.GPTConfig(**cfg), version="gpt2").train()
+        sd = {k: v.detach() for k, v in m.state_dict().items()}
+        feeder = O.DropoutFeeder(2024)
+
+        def step(x, am, caches):
+            return O.gpt_lm_head_model(x, am, sd, L, NH, 64, 1e-5, version="gpt2", k_v_pasts=caches, drop=feeder,
+                                       p_embd=0.1, p_attn=0.2, p_resid=0.1, p_mlp=0.5)
+
+        with torch.no_grad():
+            ref = O.greedy_generate(step, ids, mask, L, max_gen_len=4, pad_id=0)
+        F.manual_dropout_seed(2024)
+        m._ct_decode_graph_launches = -1
+        out = m.generate(ids, attention_mask=mask, generation_configs={"beam_size": 1, "do_sample": False,
+                                                                      "max_gen_len": 4, "end_ids": None, "pad_id": 0})
+        assert m._ct_decode_graph_launches == -1, "train mode must not take the captured step"
+        assert torch.equal(out.view(ref.shape), ref)
