@@ -161,7 +161,7 @@ SIGNATURES = {
     "ct_kv_append_dev": (c_int, [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int,
                                  c_int, c_void_p, c_int, c_void_p]),
     "ct_greedy_step": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_int, c_i64, c_void_p, c_i64,
-                               c_void_p, c_void_p, c_void_p, c_void_p]),
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ct_dropout": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_i64, c_float, ctypes.c_uint64,
                            ctypes.c_uint32, c_void_p]),
     "ct_gemm_wgrad_bias": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_i64,

@@ -648,7 +648,8 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------
 // One step of GenerationMixin._greedy_search after the model call (generation_util.py:86-101, do_sample = False),
 // entirely on the device so that a whole decode step can be replayed from a CUDA graph:
-//   next = argmax(logits[b, :])  (first maximum, like torch.argmax);  next = next * alive + pad * (1 - alive);
+//   next = argmax(logits[b, :])  (first maximum, like torch.argmax) — or sampled[b] when the caller drew the token itself
+//   (do_sample = True: generation_util.py:78-84);  next = next * alive + pad * (1 - alive);
 //   alive[b] &= next not in end_ids;  ids_out[b, out_pos] = next;  cur_ids[b] = next;  pos_ids[b] += 1;
 //   once per call (last block): out_pos += 1, seq_len += 1, done_at = out_pos when no row is alive any more.
 // state (int32): [0] seq_len (cache length the next model call sees, its own token included), [1] out_pos,
@@ -658,12 +659,14 @@ __global__ void __launch_bounds__(1024)
     greedy_step_kernel(const T* __restrict__ logits, int64_t ld, int64_t V, long long* __restrict__ alive,
                        const long long* __restrict__ end_ids, int n_end, long long pad_id,
                        long long* __restrict__ ids_out, int64_t out_stride, long long* __restrict__ cur_ids,
-                       long long* __restrict__ pos_ids, int* __restrict__ state) {
+                       long long* __restrict__ pos_ids, int* __restrict__ state,
+                       const long long* __restrict__ sampled) {
   const int b = blockIdx.x;
   const T* row = logits + (int64_t)b * ld;
   float best = -INFINITY;
   long long arg = 0x7fffffffffffffffLL;
-  for (int64_t j = threadIdx.x; j < V; j += blockDim.x) {
+  const int64_t v_scan = sampled ? 0 : V;  // a token drawn by the caller: no scan
+  for (int64_t j = threadIdx.x; j < v_scan; j += blockDim.x) {
     const float v = (float)row[j];
     if (v > best || (v == best && j < arg) || (v != v && !(best != best))) { best = v; arg = j; }  // NaN wins like torch
   }
@@ -686,6 +689,7 @@ __global__ void __launch_bounds__(1024)
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
       if (better(sv[w], si[w], best, arg)) { best = sv[w]; arg = si[w]; }
+    if (sampled) arg = sampled[b];
     const long long was_alive = alive[b];
     const long long next = arg * was_alive + pad_id * (1 - was_alive);
     bool hit = false;
@@ -853,8 +857,8 @@ extern "C" int ct_scale_by_scalar(void* x, int dtype, int64_t n, const float* de
 
 extern "C" int ct_greedy_step(const void* logits, int logits_dtype, int64_t ld, int64_t B, int64_t V, int64_t* alive,
                               const int64_t* end_ids, int n_end, int64_t pad_id, int64_t* ids_out, int64_t out_stride,
-                              int64_t* cur_ids, int64_t* pos_ids, int32_t* state, void* stream) {
-  CT_REQUIRE(logits && alive && ids_out && cur_ids && state && (n_end == 0 || end_ids), CT_ERR_BAD_ARG,
+                              int64_t* cur_ids, int64_t* pos_ids, int32_t* state, const int64_t* sampled, void* stream) {
+  CT_REQUIRE((logits || sampled) && alive && ids_out && cur_ids && state && (n_end == 0 || end_ids), CT_ERR_BAD_ARG,
              "ct_greedy_step: null pointer");
   CT_REQUIRE(B > 0 && V > 0 && ld >= V && n_end >= 0, CT_ERR_BAD_ARG, "ct_greedy_step: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
@@ -862,17 +866,17 @@ extern "C" int ct_greedy_step(const void* logits, int logits_dtype, int64_t ld, 
     greedy_step_kernel<float><<<(unsigned)B, 1024, 0, st>>>((const float*)logits, ld, V, (long long*)alive,
                                                           (const long long*)end_ids, n_end, (long long)pad_id,
                                                           (long long*)ids_out, out_stride, (long long*)cur_ids,
-                                                          (long long*)pos_ids, state);
+                                                          (long long*)pos_ids, state, (const long long*)sampled);
   else if (logits_dtype == DT_BF16)
     greedy_step_kernel<__nv_bfloat16><<<(unsigned)B, 1024, 0, st>>>((const __nv_bfloat16*)logits, ld, V, (long long*)alive,
                                                                   (const long long*)end_ids, n_end, (long long)pad_id,
                                                                   (long long*)ids_out, out_stride, (long long*)cur_ids,
-                                                                  (long long*)pos_ids, state);
+                                                                  (long long*)pos_ids, state, (const long long*)sampled);
   else if (logits_dtype == DT_F16)
     greedy_step_kernel<__half><<<(unsigned)B, 1024, 0, st>>>((const __half*)logits, ld, V, (long long*)alive,
                                                            (const long long*)end_ids, n_end, (long long)pad_id,
                                                            (long long*)ids_out, out_stride, (long long*)cur_ids,
-                                                           (long long*)pos_ids, state);
+                                                           (long long*)pos_ids, state, (const long long*)sampled);
   else
     CT_REQUIRE(false, CT_ERR_UNSUPPORTED, "ct_greedy_step: logits must be f32 / bf16 / f16");
   CT_LAUNCH_OK();

@@ -9,8 +9,9 @@ repeating its last column, and the loop ends when `step > max_gen_len + prompt_l
 max_gen_len + 2 tokens, exactly like the reference. Beam search (generation_util.py:207-290) is out
 of scope for this tier.
 
-Greedy decoding (`do_sample=False`) on a CUDA model replays every q_len = 1 step from ONE captured CUDA graph
-(BASELINE.json configs[3]): `_graphed_greedy` below. The cache length, the write position and the
+Decoding on a CUDA model in eval mode — greedy (`do_sample=False`) or sampling (the reference's default: temperature,
+top-k, top-p, multinomial) — replays every q_len = 1 step from ONE captured CUDA graph (BASELINE.json
+configs[3]): `_graphed_greedy` below. The cache length, the write position and the
 alive flags live in device memory and are advanced by ct_greedy_step at the end of the step, so the graph's arguments
 never change; the host only replays and (when end ids are given) polls a done flag every few steps.
 """
@@ -63,6 +64,22 @@ def _filter_top_p(scores, top_p, min_keep=1):
     return scores.masked_fill(remove, float("-inf"))
 
 
+def _make_sampler(temperature, top_k, top_p):
+    """generation_util.py:74-84 for do_sample=True: logits wrappers (temperature, top-k, top-p) then one multinomial
+    draw per row. Plain torch ops: the same closure serves the host loop and — they are all capturable — the captured
+    decode step."""
+    def sample(scores):
+        scores = scores.float()
+        if temperature != 1.0:
+            scores = _temperature(scores, temperature)
+        if top_k > 0:
+            scores = _filter_top_k(scores, top_k)
+        if top_p < 1.0:
+            scores = _filter_top_p(scores, top_p)
+        return torch.multinomial(torch.softmax(scores, dim=-1), num_samples=1).squeeze(1)
+    return sample
+
+
 class GenerationMixin:
     def generate(self, input_ids, attention_mask=None, position_ids=None, segment_ids=None,
                  generation_configs={}, steamers=None):
@@ -86,12 +103,13 @@ class GenerationMixin:
                        steamers=None):
         bsz, prompt_len = input_ids.shape
         limit = max_gen_len + prompt_len
-        if (not do_sample and steamers is None and _on_device(input_ids) and position_ids is None and segment_ids is None
+        sampler = _make_sampler(temperature, top_k, top_p) if do_sample else None
+        if (steamers is None and _on_device(input_ids) and position_ids is None and segment_ids is None
                 and attention_mask is not None and getattr(self, "_ct_graph_decode", False) and self._decode_graph_ok()
                 and os.environ.get("CT_DECODE_GRAPH", "1") != "0" and max_gen_len >= 1
                 and not self.training  # (train mode may have dropout active: its mask counter is host state)
                 and bool((attention_mask[:, -1] != 0).all())):
-            return self._graphed_greedy(input_ids, attention_mask, end_ids_tensor, max_gen_len, pad_id)
+            return self._graphed_greedy(input_ids, attention_mask, end_ids_tensor, max_gen_len, pad_id, sampler)
         caches = [None] * self.config.n_layer
         alive = torch.ones(bsz, dtype=torch.long, device=input_ids.device)
         fed = 0  # number of tokens already inside the cache
@@ -105,14 +123,7 @@ class GenerationMixin:
             outputs, caches = self(input_ids[:, fed:], **kwargs)
             scores = outputs[0][:, -1, :]
             if do_sample:
-                scores = scores.float()
-                if temperature != 1.0:
-                    scores = _temperature(scores, temperature)
-                if top_k > 0:
-                    scores = _filter_top_k(scores, top_k)
-                if top_p < 1.0:
-                    scores = _filter_top_p(scores, top_p)
-                nxt = torch.multinomial(torch.softmax(scores, dim=-1), num_samples=1).squeeze(1)
+                nxt = sampler(scores)
             else:
                 nxt = torch.argmax(scores, dim=-1)
             nxt = nxt * alive + pad_id * (1 - alive)
@@ -137,9 +148,11 @@ class GenerationMixin:
         return input_ids.view(bsz, 1, -1)
 
     @torch.no_grad()
-    def _graphed_greedy(self, input_ids, attention_mask, end_ids_tensor, max_gen_len, pad_id):
+    def _graphed_greedy(self, input_ids, attention_mask, end_ids_tensor, max_gen_len, pad_id, sampler=None):
         """Same token ids as the loop above for do_sample=False (generation_util.py:57-119), with the q_len = 1 steps
-        replayed from a CUDA graph. The prompt's last mask column is 1 for every row (checked by the caller), so every
+        replayed from a CUDA graph. With a `sampler` (do_sample=True) the draw — torch's own processors and multinomial,
+        captured with the step; torch advances the generator's Philox offset per replay — replaces the argmax; the
+        bookkeeping stays in ct_greedy_step. The prompt's last mask column is 1 for every row (checked by the caller), so every
         generated position is a valid key and its GPT position id is the previous one + 1.
 
         Step k >= 1 of the reference feeds token P+k-1 and emits token P+k; it stops after the step that leaves
@@ -162,7 +175,8 @@ class GenerationMixin:
         end_ids = None if end_ids_tensor is None else end_ids_tensor.to(device=dev, dtype=torch.long).contiguous()
 
         def pick(logits):
-            ops.greedy_step(logits, alive, end_ids, pad_id, ids_out, cur_ids, pos_ids, state)
+            drawn = None if sampler is None else sampler(logits).contiguous()
+            ops.greedy_step(logits, alive, end_ids, pad_id, ids_out, cur_ids, pos_ids, state, sampled=drawn)
 
         trace = getattr(self, "_ct_decode_trace", None)  # tools/decode_timing.py: a list that receives phase timings
         marks = []

@@ -534,16 +534,19 @@ def kv_append_dev(base, new, len_dev):
         "ct_kv_append_dev")
 
 
-def greedy_step(logits2d, alive, end_ids, pad_id, ids_out, cur_ids, pos_ids, state):
+def greedy_step(logits2d, alive, end_ids, pad_id, ids_out, cur_ids, pos_ids, state, sampled=None):
     """generation_util.py:86-101 on the device (include/ct_b200.h: ct_greedy_step). logits2d [B,V] f32/bf16/f16;
-    alive, cur_ids, pos_ids (nullable) int64 [B]; end_ids int64 [n] or None; ids_out int64 [B,T]; state int32 [5]."""
+    alive, cur_ids, pos_ids (nullable) int64 [B]; end_ids int64 [n] or None; ids_out int64 [B,T]; state int32 [5];
+    sampled int64 [B] or None: tokens drawn by the caller (do_sample) that replace the argmax."""
     _req_cuda(logits2d, alive, ids_out, cur_ids, state)
     B, V = logits2d.shape
     assert logits2d.stride(1) == 1 and ids_out.stride(1) == 1 and state.dtype == torch.int32 and state.numel() >= 5
     n_end = 0 if end_ids is None else end_ids.numel()
+    if sampled is not None:
+        assert sampled.dtype == torch.int64 and sampled.is_contiguous() and sampled.numel() == B
     _ck(_lib.load().ct_greedy_step(ptr(logits2d), dt(logits2d), logits2d.stride(0), B, V, ptr(alive), ptr(end_ids), n_end,
                                    int(pad_id), ptr(ids_out), ids_out.stride(0), ptr(cur_ids), ptr(pos_ids), ptr(state),
-                                   stream()), "ct_greedy_step")
+                                   ptr(sampled), stream()), "ct_greedy_step")
 
 
 def kv_cache_append(past, new):

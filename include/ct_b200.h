@@ -401,10 +401,12 @@ int ct_kv_append_dev(const void* src, int64_t s_sb, int64_t s_sh, int64_t s_ss, 
  * the device: next = argmax(logits[b,:]) (first maximum); next = next*alive + pad*(1-alive); alive &= next not in
  * end_ids; ids_out[b, out_pos] = next; cur_ids[b] = next; pos_ids[b] += 1 (nullable); then once: seq_len += 1,
  * out_pos += 1, done_at = out_pos when no row is alive. state = int32[5] on the device: {seq_len, out_pos, alive rows,
- * done_at (-1), 0}. logits [B, V] with row stride ld, dtype CT_F32 / CT_BF16 / CT_F16. */
+ * done_at (-1), 0}. logits [B, V] with row stride ld, dtype CT_F32 / CT_BF16 / CT_F16.
+ * sampled (nullable, int64 [B]): the tokens the caller drew itself (do_sample = True, generation_util.py:78-84:
+ * temperature / top-k / top-p / multinomial) — they replace the argmax, the bookkeeping is the same. */
 int ct_greedy_step(const void* logits, int logits_dtype, int64_t ld, int64_t B, int64_t V, int64_t* alive,
                    const int64_t* end_ids, int n_end, int64_t pad_id, int64_t* ids_out, int64_t out_stride,
-                   int64_t* cur_ids, int64_t* pos_ids, int32_t* state, void* stream);
+                   int64_t* cur_ids, int64_t* pos_ids, int32_t* state, const int64_t* sampled, void* stream);
 
 #ifdef __cplusplus
 }

@@ -318,9 +318,10 @@ def kv_append_dev(base, new, len_dev):
         base[:, :, n - s:n] = new
 
 
-def greedy_step(logits2d, alive, end_ids, pad_id, ids_out, cur_ids, pos_ids, state):
-    """include/ct_b200.h: ct_greedy_step (generation_util.py:86-101 for do_sample=False)."""
-    nxt = torch.argmax(logits2d.float(), dim=-1) * alive + pad_id * (1 - alive)
+def greedy_step(logits2d, alive, end_ids, pad_id, ids_out, cur_ids, pos_ids, state, sampled=None):
+    """include/ct_b200.h: ct_greedy_step (generation_util.py:86-101; `sampled` replaces the argmax for do_sample)."""
+    tok = torch.argmax(logits2d.float(), dim=-1) if sampled is None else sampled
+    nxt = tok * alive + pad_id * (1 - alive)
     if end_ids is not None and end_ids.numel():
         hit = (nxt[None, :] == end_ids[:, None]).any(dim=0)
         alive.mul_((~hit).long())

@@ -284,3 +284,49 @@ def test_decode_attention_appends_the_new_token_itself(D):
                           kv_new=(k_new, v_new))
     assert torch.equal(got, want) and torch.equal(kb_, ka) and torch.equal(vb_, va)
     assert torch.equal(kb_[:, :, n - 1], k_new[:, :, 0]) and torch.equal(kb_[:, :, n:], k0[:, :, n:])
+
+
+def test_captured_decode_with_sampling():
+    """do_sample=True (the reference's default) through the captured step: torch's processors and multinomial are
+    captured with the step (their Philox offset advances per replay), ct_greedy_step takes the drawn tokens. The CUDA
+    generator is consumed differently by a replayed graph than by the host loop, so ids are not comparable draw by
+    draw; checked instead: top_k = 1 (a deterministic draw) reproduces the greedy ids of both paths, a flat
+    distribution gives different samples for different seeds and the same sample for the same seed, every drawn token
+    lies in the top-k set of its step (teacher-forced recomputation), finished rows emit pad."""
+    from cleantransformer_b200.models import modeling_gpt as mg
+    cfg = mg.GPTConfig(vocab_size=1000, n_embd=256, n_positions=256, n_layer=3, n_head=4, n_ctx=256, afn="gelu_new")
+    model = mg.GPTLMHeadModel(cfg, version="gpt2").to(DEV).eval()
+    _init(model, std=0.05)
+    model._tie_weights()
+    ids, mask = _left_padded(4, 16, 1000, 5)
+    greedy_loop = _gen(model, ids, mask, graph=False)
+    greedy_graph = _gen(model, ids, mask, graph=True)
+    assert torch.equal(greedy_loop, greedy_graph)
+    samp = dict(do_sample=True, temperature=1.5, top_k=1, top_p=1.0)
+    assert torch.equal(_gen(model, ids, mask, graph=True, **samp), greedy_graph)
+    assert model._ct_decode_graph_launches > 0, "sampling did not take the captured step"
+    assert torch.equal(_gen(model, ids, mask, graph=False, **samp), greedy_graph)
+    flat = dict(do_sample=True, temperature=30.0, top_k=50, top_p=1.0)
+    torch.manual_seed(11)
+    a = _gen(model, ids, mask, graph=True, **flat)
+    torch.manual_seed(11)
+    b = _gen(model, ids, mask, graph=True, **flat)
+    torch.manual_seed(12)
+    c = _gen(model, ids, mask, graph=True, **flat)
+    assert a.shape == (4, 1, 16 + 22) and torch.equal(a, b) and not torch.equal(a, c)
+    assert int(a.min()) >= 0 and int(a.max()) < 1000
+    # every sampled token is one of the 50 most likely of its step given the sampled prefix
+    seq = a[:, 0]
+    full_mask = torch.cat([mask, mask[:, -1:].expand(4, 22)], dim=1)
+    with torch.no_grad():
+        (logits, _), _ = model(seq[:, :-1], attention_mask=full_mask[:, :-1])
+    top = logits[:, 15:, :].float().topk(50, dim=-1).indices          # predictions for positions 16 ..
+    hit = (top == seq[:, 16:, None]).any(-1)
+    assert float(hit.float().mean()) > 0.97, float(hit.float().mean())  # (bf16 near-ties at the 50th place aside)
+    # end ids: rows that drew one emit pad afterwards
+    end = int(a[0, 0, 20])
+    torch.manual_seed(11)
+    e = _gen(model, ids, mask, graph=True, end_ids=[end], pad_id=7, **flat)
+    row = e[0, 0, 16:]
+    first = int((row == end).nonzero()[0])
+    assert bool((row[first + 1:] == 7).all())

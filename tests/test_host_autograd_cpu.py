@@ -808,3 +808,40 @@ def test_generate_on_a_train_mode_model_takes_the_host_loop_with_dropout_active(
                                                                       "max_gen_len": 4, "end_ids": None, "pad_id": 0})
         assert m._ct_decode_graph_launches == -1, "train mode must not take the captured step"
         assert torch.equal(out.view(ref.shape), ref)
+
+
+def test_captured_decode_with_sampling_host_logic(monkeypatch):
+    """do_sample=True (the reference's default, generation_util.py:74-84) through the captured step: the draw (torch's
+    processors + multinomial) happens inside the step and ct_greedy_step only does the bookkeeping. With the device
+    pieces mocked both paths consume the CPU generator identically, so the same seed must give the same ids; top_k = 1
+    makes the draw deterministic: the greedy ids."""
+    from cleantransformer_b200.models import modeling_gpt as mg
+    torch.manual_seed(123)
+    V, L, NH = 83, 2, 2
+    ids = torch.randint(3, V, (3, 6))
+    mask = torch.ones(3, 6, dtype=torch.long)
+    mask[2, :3] = 0
+    with mock_ops.patched():
+        m = mg.GPTLMHeadModel(mg.GPTConfig(vocab_size=V, n_embd=64, n_positions=64, n_layer=L, n_head=NH, n_ctx=64,
+                                           afn="gelu_new"), version="gpt2").eval()
+        with torch.no_grad():
+            m.gpt.tokens_embed.weight.mul_(0.1)  # (N(0,1) tied embeddings make the LM head all but deterministic)
+
+        def gen(graph, seed, **cfg):
+            monkeypatch.setenv("CT_DECODE_GRAPH", "1" if graph else "0")
+            m._ct_decode_graph_launches = -1
+            base = {"beam_size": 1, "do_sample": True, "max_gen_len": 8, "end_ids": None, "pad_id": 0,
+                    "temperature": 4.0, "top_k": 30, "top_p": 0.97}   # (flat enough for seeds to matter)
+            base.update(cfg)
+            torch.manual_seed(seed)
+            out = m.generate(ids, attention_mask=mask, generation_configs=base)
+            assert (m._ct_decode_graph_launches >= 0) == graph
+            return out
+
+        a, b = gen(False, 7), gen(True, 7)
+        assert a.shape == (3, 1, 6 + 10) and torch.equal(a, b)
+        assert not torch.equal(gen(True, 8), b)                     # another seed, another sample
+        greedy = gen(True, 1, do_sample=False)
+        assert torch.equal(gen(True, 5, top_k=1), greedy) and torch.equal(gen(False, 6, top_k=1), greedy)
+        ends = [int(b[0, 0, 8])]
+        assert torch.equal(gen(False, 7, end_ids=ends), gen(True, 7, end_ids=ends))
