@@ -122,8 +122,19 @@ class DistributedDataParallel(torch.nn.Module):
                 self._stage_rows = full[self._stage_rows_off:self._stage_ids_off]
                 self._stage_ids = full[self._stage_ids_off:self._stage_ids_off + 2 * self._stage_cap].view(torch.int64)
         self.arena = ParamArena(params, grad_buffer=grad_buf)
-        # (1) parameter / buffer sync from rank 0 (README.md:47; torch DDP's _sync_module_states)
-        dist.broadcast(self.arena.flat, 0, group=self.group)
+        # (1) parameter / buffer sync from rank 0 (README.md:47; torch DDP's _sync_module_states). With peer memory the flat
+        # parameter arena travels through the (still unused) symmetric gradient buffer: ct_broadcast, no library collective
+        if self._peer_mem and self.world > 1 and grad_buf is not None and self.arena.grad.numel() >= self.arena.flat.numel():
+            n = self.arena.flat.numel()
+            self.arena.grad[:n].copy_(self.arena.flat)
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.load().ct_comm_barrier(st), "ct_comm_barrier")      # every rank has staged (rank 0's counts)
+            _lib.check(_lib.load().ct_broadcast(0, n, 0, st), "ct_broadcast")
+            self.arena.flat.copy_(self.arena.grad[:n])
+            self.arena.grad.zero_()
+            torch.cuda.synchronize(self.device)
+        else:
+            dist.broadcast(self.arena.flat, 0, group=self.group)
         for b in module.buffers():
             if b.numel():
                 dist.broadcast(b, 0, group=self.group)
