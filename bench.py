@@ -573,6 +573,12 @@ def run_gpt2_decode(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
     assert out.shape == (B, 1, P + NEW) and torch.equal(out.cpu(), out2)
+    # the reference's default generation mode (do_sample=True: temperature / top-k / top-p / multinomial) through the same
+    # captured step, one timed generation after one warm-up
+    gs = dict(gc, do_sample=True, temperature=0.8, top_k=10, top_p=0.8)
+    model.generate(ids, attention_mask=mask, generation_configs=gs)
+    ms_samp, _ = timed(lambda: model.generate(ids, attention_mask=mask, generation_configs=gs), 1)
+    per_gen.pop()
     peaks, peak_kind = measured_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     n_w = sum(p.numel() for p in model.parameters())
@@ -604,6 +610,9 @@ def run_gpt2_decode(args):
                     "d2h_bytes_per_step": B * (P + NEW) * 8, "ms_per_step": ms_e2e / steps},
             "gpu_launches": launches, "clocks": sampler.summary(),
             "ms_per_generation": {"resident": per_gen[0], "e2e": per_gen[1]},
+            "sampling": {"value": B * NEW / (ms_samp * 1e-3), "unit": "tokens/s", "ms_per_generation": ms_samp,
+                         "what": "do_sample=True, temperature 0.8, top-k 10, top-p 0.8 (torch's processors + multinomial "
+                                 "captured with the decode step)"},
             "roofline": {"bound": "hbm", "kernel": "decode token-step (weight-streaming GEMMs + cache attention)",
                          "achieved": alg * steps / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": alg * steps / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
