@@ -230,6 +230,8 @@ class GenerationMixin:
         if n_steps > 0 and not finished():
             replay, self._ct_decode_graph_launches = _capture(step)
             mark("capture")
+            import time
+            t_issue = time.perf_counter()
             done = 0
             while done < n_steps:
                 burst = min(POLL_EVERY, n_steps - done) if end_ids is not None else n_steps - done
@@ -240,10 +242,13 @@ class GenerationMixin:
                 if finished():
                     break
             mark("replays")
+            if trace is not None:  # host time to ISSUE the replays (the queue may have throttled it): launch-bound?
+                self._ct_replay_issue_ms = (time.perf_counter() - t_issue) * 1e3
             del replay
         st = state.tolist()
         if trace is not None:
             torch.cuda.synchronize()
             trace.append({b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])})
+            trace[-1]["replay_issue_host_ms"] = getattr(self, "_ct_replay_issue_ms", None)
         n_out = st[3] if (end_ids is not None and st[3] >= 0) else min(st[1], P + n_emit)
         return ids_out[:, :n_out].reshape(bsz, 1, -1)

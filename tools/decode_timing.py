@@ -21,6 +21,8 @@ def main():
     mask = torch.ones(B, P, dtype=torch.long, device="cuda")
     gc = {"beam_size": 1, "do_sample": False, "max_gen_len": NEW - 2, "end_ids": None, "pad_id": 0}
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    # (replay_issue_host_ms: host wall clock to issue the 510 graph launches of a generation; close to `replays` = the
+    # device time means the launch queue throttled the host, i.e. the device is the bottleneck; far below = host is idle)
     model._ct_decode_trace = []
     rows = []
     for g in range(n):
