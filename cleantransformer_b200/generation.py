@@ -64,6 +64,21 @@ def _filter_top_p(scores, top_p, min_keep=1):
     return scores.masked_fill(remove, float("-inf"))
 
 
+DECODE_PLAN_CACHE = [os.environ.get("CT_DECODE_CACHE", "1") != "0"]  # keep the captured step between generate() calls
+
+
+class _DecodePlan:
+    """A captured decode step and everything it refers to by address."""
+    __slots__ = ("key", "fingerprint", "ids_out", "alive", "cur_ids", "pos_ids", "state", "end_ids", "mask_obj",
+                 "static_kv", "replay", "launches")
+
+
+def _fingerprint(model):
+    """The graph reads the parameters through cached low-precision copies: any update (version) or move (address) of a
+    parameter invalidates a cached plan."""
+    return tuple((p._version, p.data_ptr()) for p in model.parameters())
+
+
 def _make_sampler(temperature, top_k, top_p):
     """generation_util.py:74-84 for do_sample=True: logits wrappers (temperature, top-k, top-p) then one multinomial
     draw per row. Plain torch ops: the same closure serves the host loop and — they are all capturable — the captured
@@ -77,6 +92,7 @@ def _make_sampler(temperature, top_k, top_p):
         if top_p < 1.0:
             scores = _filter_top_p(scores, top_p)
         return torch.multinomial(torch.softmax(scores, dim=-1), num_samples=1).squeeze(1)
+    sample.key = (float(temperature), int(top_k), float(top_p))
     return sample
 
 
@@ -152,27 +168,56 @@ class GenerationMixin:
         """Same token ids as the loop above for do_sample=False (generation_util.py:57-119), with the q_len = 1 steps
         replayed from a CUDA graph. With a `sampler` (do_sample=True) the draw — torch's own processors and multinomial,
         captured with the step; torch advances the generator's Philox offset per replay — replaces the argmax; the
-        bookkeeping stays in ct_greedy_step. The prompt's last mask column is 1 for every row (checked by the caller), so every
-        generated position is a valid key and its GPT position id is the previous one + 1.
+        bookkeeping stays in ct_greedy_step. The prompt's last mask column is 1 for every row (checked by the caller), so
+        every generated position is a valid key and its GPT position id is the previous one + 1.
 
         Step k >= 1 of the reference feeds token P+k-1 and emits token P+k; it stops after the step that leaves
         `fed > max_gen_len + P`, i.e. after max_gen_len + 2 emitted tokens, or right after the step in which the last
-        row hit an end id. Cache rows needed: P + max_gen_len + 1."""
+        row hit an end id. Cache rows needed: P + max_gen_len + 1.
+
+        The captured step and every buffer it addresses (KV caches, mask bias, counters, output ids) form a `_DecodePlan`
+        kept on the model: the next generate() with the same shapes / options and unchanged parameters re-initialises the
+        buffers in place and replays — no second capture (10 - 200 ms of host time per generation, r03f)."""
         dev = input_ids.device
         bsz, P = input_ids.shape
         n_emit = max_gen_len + 2
         cap = P + max_gen_len + 1
+        n_end = 0 if end_ids_tensor is None else int(end_ids_tensor.numel())
+        key = (bsz, P, int(max_gen_len), int(pad_id), n_end, getattr(sampler, "key", None), str(dev))
+        plan = getattr(self, "_ct_decode_plan", None)
+        reuse = (plan is not None and plan.key == key and DECODE_PLAN_CACHE[0]
+                 and plan.fingerprint == _fingerprint(self))
+        self._ct_decode_plan_reused = bool(reuse)
         full_mask = torch.cat([attention_mask, attention_mask[:, -1:].expand(bsz, cap - P)], dim=-1).contiguous()
-        ids_out = torch.empty(bsz, P + n_emit, dtype=torch.long, device=dev)
-        ids_out[:, :P] = input_ids
-        alive = torch.ones(bsz, dtype=torch.long, device=dev)
-        cur_ids = torch.empty(bsz, dtype=torch.long, device=dev)
-        pos_ids = None
-        if self._decode_needs_positions():  # position of the last prompt token; ct_greedy_step adds 1 per emitted token
-            pos_ids = (attention_mask.long().cumsum(-1)[:, -1] - 1).contiguous()
-        # state: cache length seen by the next step, write column, alive rows, done_at, block counter
-        state = torch.tensor([P, P, bsz, -1, 0], dtype=torch.int32, device=dev)
-        end_ids = None if end_ids_tensor is None else end_ids_tensor.to(device=dev, dtype=torch.long).contiguous()
+        state0 = torch.tensor([P, P, bsz, -1, 0], dtype=torch.int32)
+        if not reuse:
+            self._ct_decode_plan = plan = None  # (frees the previous plan's caches and graph before allocating new ones)
+            plan = _DecodePlan()
+            plan.key = key
+            plan.ids_out = torch.empty(bsz, P + n_emit, dtype=torch.long, device=dev)
+            plan.alive = torch.ones(bsz, dtype=torch.long, device=dev)
+            plan.cur_ids = torch.empty(bsz, dtype=torch.long, device=dev)
+            # position of the last prompt token; ct_greedy_step adds 1 per emitted token
+            plan.pos_ids = torch.empty(bsz, dtype=torch.long, device=dev) if self._decode_needs_positions() else None
+            # state: cache length seen by the next step, write column, alive rows, done_at, block counter
+            plan.state = torch.empty(5, dtype=torch.int32, device=dev)
+            plan.end_ids = None if n_end == 0 else torch.empty(n_end, dtype=torch.long, device=dev)
+            plan.mask_obj = self._decode_static_mask(full_mask)
+        else:
+            fresh = self._decode_static_mask(full_mask)
+            for name in ("kbias2", "first_valid"):
+                dst, src = getattr(plan.mask_obj, name, None), getattr(fresh, name, None)
+                if dst is not None:
+                    dst.copy_(src)
+            plan.alive.fill_(1)
+        plan.ids_out[:, :P] = input_ids
+        plan.state.copy_(state0)
+        if plan.pos_ids is not None:
+            plan.pos_ids.copy_(attention_mask.long().cumsum(-1)[:, -1] - 1)
+        if plan.end_ids is not None:
+            plan.end_ids.copy_(end_ids_tensor.to(device=dev, dtype=torch.long).reshape(-1))
+        ids_out, alive, cur_ids, pos_ids, state, end_ids = (plan.ids_out, plan.alive, plan.cur_ids, plan.pos_ids,
+                                                            plan.state, plan.end_ids)
 
         def pick(logits):
             drawn = None if sampler is None else sampler(logits).contiguous()
@@ -188,16 +233,26 @@ class GenerationMixin:
                 marks.append((name, ev))
 
         mark("start")
-        # prefill: the un-graphed full-sequence path, with the caches allocated once for the whole generation
+        # prefill: the un-graphed full-sequence path; the caches are allocated once for the whole generation, or — with a
+        # cached plan — written into the plan's buffers (ops.KV_PREALLOC hands them to kv_cache_append in layer order)
         old_cap = ops.KV_CACHE_MIN_CAP[0]
         ops.KV_CACHE_MIN_CAP[0] = cap
+        ops.KV_PREALLOC.clear()
+        if reuse:
+            for kv in plan.static_kv:
+                ops.KV_PREALLOC.extend((kv.k, kv.v))
         try:
             outputs, caches = self(input_ids, attention_mask=attention_mask, k_v_pasts=[None] * self.config.n_layer)
         finally:
             ops.KV_CACHE_MIN_CAP[0] = old_cap
+            ops.KV_PREALLOC.clear()
+        if reuse and not all(k._ct_cache_base is kv.k and v._ct_cache_base is kv.v
+                             for (k, v), kv in zip(caches, plan.static_kv)):
+            raise RuntimeError("generate(): the prefill did not land in the cached decode plan's KV buffers")
         pick(outputs[0][:, -1, :])
-        static_kv = [ops.StaticKV(k._ct_cache_base, v._ct_cache_base, state) for k, v in caches]
-        mask_obj = self._decode_static_mask(full_mask)
+        if not reuse:
+            plan.static_kv = [ops.StaticKV(k._ct_cache_base, v._ct_cache_base, state) for k, v in caches]
+        static_kv, mask_obj = plan.static_kv, plan.mask_obj
 
         def step():
             kw = dict(attention_mask=mask_obj, k_v_pasts=static_kv)
@@ -215,40 +270,42 @@ class GenerationMixin:
         # the option is left alone when the user forced it on or off (CT_PDL = 1 / 2)
         pdl_prev = ops.set_option("PDL", 1) if ops.get_option("PDL") == 0 else None
         try:
-            return self._graphed_greedy_steps(step, finished, n_steps, mark, trace, marks, state, ids_out, end_ids,
-                                              bsz, P, n_emit)
+            if not reuse:
+                if n_steps > 0 and not finished():
+                    step()  # first decode step outside the capture: lazy kernel attributes, and it is a real step
+                    n_steps -= 1
+                mark("first_step")
+                plan.replay, plan.launches = None, 0
+                if n_steps > 0 and not finished():
+                    plan.replay, plan.launches = _capture(step)
+                    plan.fingerprint = _fingerprint(self)
+                    if DECODE_PLAN_CACHE[0]:
+                        self._ct_decode_plan = plan  # (one plan per model: its caches and graph stay alive)
+                mark("capture")
+            self._ct_decode_graph_launches = plan.launches
+            if plan.replay is not None and n_steps > 0 and not finished():
+                import time
+                t_issue = time.perf_counter()
+                done = 0
+                while done < n_steps:
+                    burst = min(POLL_EVERY, n_steps - done) if end_ids is not None else n_steps - done
+                    for _ in range(burst):
+                        plan.replay()
+                    done += burst
+                    ops.LAUNCHES[0] += burst * plan.launches
+                    if finished():
+                        break
+                mark("replays")
+                if trace is not None:  # host time to ISSUE the replays: far below the device time = the host is not the limit
+                    self._ct_replay_issue_ms = (time.perf_counter() - t_issue) * 1e3
         finally:
             if pdl_prev is not None:
                 ops.set_option("PDL", pdl_prev)
-
-    def _graphed_greedy_steps(self, step, finished, n_steps, mark, trace, marks, state, ids_out, end_ids, bsz, P, n_emit):
-        if n_steps > 0 and not finished():
-            step()  # first decode step outside the capture: lazy kernel attributes, and it is a real step
-            n_steps -= 1
-        self._ct_decode_graph_launches = 0
-        mark("first_step")
-        if n_steps > 0 and not finished():
-            replay, self._ct_decode_graph_launches = _capture(step)
-            mark("capture")
-            import time
-            t_issue = time.perf_counter()
-            done = 0
-            while done < n_steps:
-                burst = min(POLL_EVERY, n_steps - done) if end_ids is not None else n_steps - done
-                for _ in range(burst):
-                    replay()
-                done += burst
-                ops.LAUNCHES[0] += burst * self._ct_decode_graph_launches
-                if finished():
-                    break
-            mark("replays")
-            if trace is not None:  # host time to ISSUE the replays (the queue may have throttled it): launch-bound?
-                self._ct_replay_issue_ms = (time.perf_counter() - t_issue) * 1e3
-            del replay
         st = state.tolist()
         if trace is not None:
             torch.cuda.synchronize()
             trace.append({b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])})
             trace[-1]["replay_issue_host_ms"] = getattr(self, "_ct_replay_issue_ms", None)
+            trace[-1]["plan_reused"] = bool(reuse)
         n_out = st[3] if (end_ids is not None and st[3] >= 0) else min(st[1], P + n_emit)
-        return ids_out[:, :n_out].reshape(bsz, 1, -1)
+        return ids_out[:, :n_out].clone().reshape(bsz, 1, -1)  # (a copy: the buffer belongs to the plan)

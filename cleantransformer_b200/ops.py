@@ -4,6 +4,7 @@ PyTorch is plumbing here: it owns device memory and the current stream; every ar
 hand-written sm_100a kernel in libct_b200.so. Wrappers allocate outputs with torch.empty and pass
 raw data_ptr()s + the current stream. Nothing in this module computes with torch ops.
 """
+import collections
 import ctypes
 import weakref
 import os
@@ -514,6 +515,7 @@ def scale_by_scalar(x, scalar_f32):
 # ------------------------------------------------------------------------------------------------
 KV_CACHE_CHUNK = 256  # capacity grows in steps of this many positions
 KV_CACHE_MIN_CAP = [0]  # generation.py raises it to prompt + max_gen_len so that one allocation serves a generation
+KV_PREALLOC = collections.deque()  # generation.py: buffers of a cached decode plan, handed out in call order to the prefill
 
 
 class StaticKV:
@@ -557,7 +559,13 @@ def kv_cache_append(past, new):
     B, H, s, D = new.shape
     t = 0 if past is None else past.shape[2]
     base = _kv_base_of(past) if past is not None else None
-    if base is None or base.shape[2] < t + s or base.dtype != new.dtype or past.data_ptr() != base.data_ptr():
+    if past is None and KV_PREALLOC:
+        cand = KV_PREALLOC.popleft()
+        if (cand.shape[0] == B and cand.shape[1] == H and cand.shape[3] == D and cand.shape[2] >= s
+                and cand.dtype == new.dtype and cand.device == new.device):
+            base = cand
+    if base is None or base.shape[2] < t + s or base.dtype != new.dtype or \
+            (past is not None and past.data_ptr() != base.data_ptr()):
         cap = max(((t + s + KV_CACHE_CHUNK - 1) // KV_CACHE_CHUNK + 1) * KV_CACHE_CHUNK, KV_CACHE_MIN_CAP[0])
         nbase = torch.empty((B, H, cap, D), dtype=new.dtype, device=new.device)
         if t:

@@ -305,7 +305,13 @@ def kv_cache_append(past, new):
     from cleantransformer_b200 import ops
     cat = new if past is None else torch.cat([past, new], 2)
     B, H, t, D = cat.shape
-    base = torch.zeros(B, H, max(t, ops.KV_CACHE_MIN_CAP[0]), D, dtype=cat.dtype)
+    base = None
+    if past is None and ops.KV_PREALLOC:  # a cached decode plan's buffer (generation.py)
+        cand = ops.KV_PREALLOC.popleft()
+        if cand.shape[:2] == (B, H) and cand.shape[3] == D and cand.shape[2] >= t and cand.dtype == cat.dtype:
+            base = cand
+    if base is None:
+        base = torch.zeros(B, H, max(t, ops.KV_CACHE_MIN_CAP[0]), D, dtype=cat.dtype)
     base[:, :, :t] = cat
     view = base[:, :, :t]
     view._ct_cache_base = base

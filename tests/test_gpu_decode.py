@@ -330,3 +330,43 @@ def test_captured_decode_with_sampling():
     row = e[0, 0, 16:]
     first = int((row == end).nonzero()[0])
     assert bool((row[first + 1:] == 7).all())
+
+
+@pytest.mark.parametrize("family", ["gpt2", "bloom"])
+def test_decode_plan_reuse_on_the_device(family):
+    """The captured step is kept between generate() calls (generation._DecodePlan): a second generation with the same
+    shapes but other tokens / padding re-initialises the plan's buffers in place, prefills into its KV buffers and
+    replays the SAME graph — ids equal to the host loop's; a parameter update drops the plan."""
+    if family == "gpt2":
+        from cleantransformer_b200.models import modeling_gpt as mg
+        cfg = mg.GPTConfig(vocab_size=1000, n_embd=256, n_positions=256, n_layer=3, n_head=4, n_ctx=256, afn="gelu_new")
+        model = mg.GPTLMHeadModel(cfg, version="gpt2").to(DEV).eval()
+        _init(model)
+        model._tie_weights()
+    else:
+        from cleantransformer_b200.models import modeling_bloom as mb
+        cfg = mb.BloomConfig(vocab_size=1000, hidden_size=256, n_layer=3, num_attention_heads=4, hidden_dropout=0.0,
+                             attention_dropout=0.0)
+        model = mb.BloomForCausalLM(cfg).to(DEV).eval()
+        _init(model)
+        model._tie_weight()
+    outs = []
+    for seed in (11, 12, 13):
+        ids, mask = _left_padded(5, 24, 1000, seed)
+        want = _gen(model, ids, mask, graph=False)
+        got = _gen(model, ids, mask, graph=True)
+        assert torch.equal(want, got), seed
+        assert model._ct_decode_plan_reused == (seed != 11)
+        outs.append(got)
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
+    with torch.no_grad():
+        next(p for p in model.parameters() if p.dim() >= 2).mul_(1.01)
+    ids, mask = _left_padded(5, 24, 1000, 14)
+    assert torch.equal(_gen(model, ids, mask, graph=False), _gen(model, ids, mask, graph=True))
+    assert model._ct_decode_plan_reused is False
+    # sampling plans are cached too; the generator moves on between generations
+    flat = dict(do_sample=True, temperature=30.0, top_k=50, top_p=1.0)
+    torch.manual_seed(3)
+    a = _gen(model, ids, mask, graph=True, **flat)
+    b = _gen(model, ids, mask, graph=True, **flat)
+    assert model._ct_decode_plan_reused is True and a.shape == b.shape and not torch.equal(a, b)

@@ -845,3 +845,61 @@ def test_captured_decode_with_sampling_host_logic(monkeypatch):
         assert torch.equal(gen(True, 5, top_k=1), greedy) and torch.equal(gen(False, 6, top_k=1), greedy)
         ends = [int(b[0, 0, 8])]
         assert torch.equal(gen(False, 7, end_ids=ends), gen(True, 7, end_ids=ends))
+
+
+def test_decode_plan_is_reused_between_generations_and_dropped_when_parameters_change(monkeypatch):
+    """generation._DecodePlan: the captured step, its KV buffers, mask bias, counters and output buffer are kept on the
+    model; the next generate() with the same shapes / options re-initialises them in place (the prefill lands in the
+    plan's buffers through ops.KV_PREALLOC) and replays. Different prompts of the same shape must still give the loop's
+    ids; a parameter update, another shape or other options force a new plan; results never alias the plan's buffer."""
+    from cleantransformer_b200 import generation
+    from cleantransformer_b200.models import modeling_bloom as mb
+    torch.manual_seed(9)
+    V = 71
+    with mock_ops.patched():
+        m = mb.BloomForCausalLM(mb.BloomConfig(vocab_size=V, hidden_size=64, n_layer=2, num_attention_heads=2)).eval()
+        m._tie_weight()
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.dim() >= 2:
+                    p.normal_(0, 0.2)
+        cfg = {"beam_size": 1, "do_sample": False, "max_gen_len": 6, "end_ids": None, "pad_id": 1}
+
+        def prompts(seed, P=7):
+            g = torch.Generator().manual_seed(seed)
+            ids = torch.randint(3, V, (3, P), generator=g)
+            mask = torch.ones(3, P, dtype=torch.long)
+            n = int(torch.randint(0, P - 2, (1,), generator=g))
+            mask[1, :n] = 0
+            ids[1, :n] = 0
+            return ids, mask
+
+        def both(ids, mask, **extra):
+            c = dict(cfg, **extra)
+            monkeypatch.setenv("CT_DECODE_GRAPH", "0")
+            want = m.generate(ids, attention_mask=mask, generation_configs=c)
+            monkeypatch.setenv("CT_DECODE_GRAPH", "1")
+            got = m.generate(ids, attention_mask=mask, generation_configs=c)
+            assert torch.equal(want, got)
+            return got
+
+        first = both(*prompts(1))
+        assert m._ct_decode_plan_reused is False and m._ct_decode_plan is not None
+        keep = first.clone()
+        second = both(*prompts(2))                       # same shapes, other tokens and padding: the plan is reused
+        assert m._ct_decode_plan_reused is True and not torch.equal(second, first)
+        assert torch.equal(first, keep), "a returned result must not alias the plan's output buffer"
+        both(*prompts(3), end_ids=[int(second[0, 0, 9])])
+        assert m._ct_decode_plan_reused is False         # other options (an end id): new plan
+        both(*prompts(4, P=9))
+        assert m._ct_decode_plan_reused is False         # other prompt length
+        both(*prompts(5, P=9))
+        assert m._ct_decode_plan_reused is True
+        with torch.no_grad():
+            m.bloom.blocks[0].mlp.dense_h_to_4h.weight.mul_(1.5)   # a parameter update invalidates the cached step
+        both(*prompts(5, P=9))
+        assert m._ct_decode_plan_reused is False
+        monkeypatch.setattr(generation, "DECODE_PLAN_CACHE", [False])
+        both(*prompts(6, P=9))
+        both(*prompts(7, P=9))
+        assert m._ct_decode_plan_reused is False
