@@ -427,7 +427,7 @@ def attn_bwd(dout, q, k, v, o, lse2, dq, dk, dv, scale, causal=False, causal_fil
 
 def dropout(x, p, seed, rng_stream, residual=None, out_dtype=None):
     """(residual +) x * keep / (1 - p) with the counter-based mask of include/ct_b200.h ("dropout"): element e of the
-    flattened tensor is kept iff ct_dropout_keep(seed, rng_stream, e >> 32, e & 0xffffffff). The site's backward is the
+    flattened tensor is kept iff keep(seed, rng_stream, hi = e >> 32, lo = e & 0xffffffff). The site's backward is the
     same call on the incoming gradient (no residual)."""
     _req_cuda(x)
     x = x.contiguous()

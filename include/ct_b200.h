@@ -236,7 +236,8 @@ typedef struct {
   /* attention-probability dropout (transformer.py:47-50, modeling_gpt.py:93-96, modeling_bloom.py:111-113,
    * modeling_bert.py attention dropout): P(i,j) is zeroed with probability dropout_p AFTER the softmax (the row sum
    * keeps every key) and the survivors are scaled by 1/(1-p). The keep decision of element (b,h,i,j) is
-   * ct_dropout_keep(rng_seed, rng_stream, hi = b*H + h, lo = i*Sk + j) below; backward takes the same three values. */
+   * keep(rng_seed, rng_stream, hi = b*H + h, lo = i*Sk + j) as defined under "dropout" below; the backward takes the same
+   * three values. */
   float dropout_p;     /* 0: none */
   uint32_t rng_stream; /* distinguishes the dropout sites / calls that share one seed */
   uint64_t rng_seed;
@@ -255,7 +256,7 @@ int ct_attn_fwd(const ct_attn_args* args, void* stream);
  *   key0 = (uint32)seed + stream * 0x632BE5AB,  key1 = (uint32)(seed >> 32) ^ (stream * 0x2545F491)
  *   h = lo * 0x9E3779B1 + key0;  h ^= hi * 0x85EBCA77 + key1;
  *   h ^= h >> 16; h *= 0x7FEB352D; h ^= h >> 15; h *= 0x846CA68B; h ^= h >> 16;      (all mod 2^32)
- *   keep  <=>  (h >> 8) >= round(p * 2^24)
+ *   keep(seed, stream, hi, lo)  <=>  (h >> 8) >= round(p * 2^24)
  * Elementwise sites (torch.nn.Dropout on hidden states: transformer.py:109-116, modeling_gpt.py:136,
  * modeling_bert.py:253-262, modeling_bloom.py dropout_add): element e of the flattened tensor has hi = e >> 32,
  * lo = (uint32)e.   out = (residual ? residual : 0) + (keep ? x / (1-p) : 0); the backward of the site is the same call
