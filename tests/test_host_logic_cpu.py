@@ -356,3 +356,46 @@ def test_head_mask_is_refused_not_ignored():
     gpt = mg.AttentionLayer(mg.GPTConfig(vocab_size=32, n_embd=32, n_positions=8, n_layer=1, n_head=2, n_ctx=8)).eval()
     with pytest.raises(NotImplementedError):
         gpt(x, head_mask=hm)
+
+
+def test_kv_cache_base_is_found_again_after_the_caller_reslices_the_cache():
+    """ops._kv_base_of: kv_cache_append leaves the preallocated buffer as an attribute on the view
+    it returns; a caller that re-slices / re-wraps that view loses Python attributes, so the buffer is also registered
+    by storage address and recognised when the tensor still is a prefix view of it."""
+    import weakref
+    from cleantransformer_b200 import ops
+    base = torch.zeros(2, 3, 16, 8)
+    view = base[:, :, :5]
+    view._ct_cache_base = base
+    ops._KV_BASES[base.untyped_storage().data_ptr()] = weakref.ref(base)
+    assert ops._kv_base_of(view) is base
+    assert ops._kv_base_of(view[:, :, :5]) is base            # re-sliced: attribute gone, registry finds it
+    assert ops._kv_base_of(base[:, :, :7].detach()) is base
+    assert ops._kv_base_of(base[:, :, 2:7]) is None           # not a prefix
+    assert ops._kv_base_of(base[:, :2, :5]) is None           # other head count
+    assert ops._kv_base_of(torch.zeros(2, 3, 5, 8)) is None   # unrelated storage
+    del ops._KV_BASES[base.untyped_storage().data_ptr()]
+
+
+def test_dropout_stream_numbers_follow_the_call_order_and_the_seed_is_torchs():
+    """functional.next_dropout: every active dropout site of a forward takes the next stream number; the seed is the one
+    torch.manual_seed set unless manual_dropout_seed overrides it — what oracle.DropoutFeeder mirrors."""
+    from cleantransformer_b200 import functional as F
+    from oracle import ct_oracle as O
+    F.manual_dropout_seed(1234)
+    a, b = F.next_dropout(0.1), F.next_dropout(0.5)
+    assert a == (0.1, 1234, 1) and b == (0.5, 1234, 2)
+    F.manual_dropout_seed(99)
+    assert F.next_dropout(0.25) == (0.25, 99, 1)
+    F._DropoutState.seed = None
+    torch.manual_seed(4242)
+    assert F.next_dropout(0.1)[1] == 4242
+    # the restated generator: deterministic, seed- and stream-dependent, the right rate, p = 0 keeps everything
+    m1 = O.dropout_mask_elementwise((64, 1024), 0.3, 7, 1)
+    assert torch.equal(m1, O.dropout_mask_elementwise((64, 1024), 0.3, 7, 1))
+    assert not torch.equal(m1, O.dropout_mask_elementwise((64, 1024), 0.3, 7, 2))
+    assert not torch.equal(m1, O.dropout_mask_elementwise((64, 1024), 0.3, 8, 1))
+    assert abs(1 - float(m1.float().mean()) - 0.3) < 0.01
+    assert bool(O.dropout_mask_elementwise((8, 8), 0.0, 7, 1).all())
+    ma = O.dropout_mask_attention(2, 3, 5, 7, 0.5, 11, 4)
+    assert ma.shape == (2, 3, 5, 7) and not torch.equal(ma[0, 0], ma[0, 1]) and not torch.equal(ma[0, 0], ma[1, 0])
