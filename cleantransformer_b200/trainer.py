@@ -2,25 +2,54 @@
 HuggingFace Trainer that needs accelerate / peft / datasets and has no arithmetic of its own; SURVEY.md
 §0 D5). Only its hot-path lines are reproduced: `model(**inputs)` (trainer.py:560), backward (:555) and
 `optimizer.step()` (:501), driven by a plain loop over a DataLoader; everything they call runs on the
-sm_100a kernels (fused AdamW arena, bucketed P2P DDP). Checkpoint rotation, callbacks, hub upload and
-the accelerate plumbing are out of scope.
+sm_100a kernels (fused AdamW arena, bucketed P2P DDP). Checkpoints follow the reference's layout
+(`checkpoint-<step>/{pytorch_model.bin, optimizer.pt, scheduler.pt, trainer_state.json, rng_state.pth}`,
+trainer.py:1303-1342, rotation :1465-1486, resume :351-379, 448-453) but are written by `checkpoint.AsyncCheckpointer`:
+the step loop only enqueues three flat copies, the files are written behind it. Callbacks, hub upload and the
+accelerate plumbing are out of scope.
 
 Accepted `args`: any object with the TrainingArguments attribute names used below (missing ones take the
 HF defaults): per_device_train_batch_size, per_device_eval_batch_size, learning_rate, weight_decay,
-adam_beta1, adam_beta2, adam_epsilon, num_train_epochs, max_steps, logging_steps, output_dir, seed.
+adam_beta1, adam_beta2, adam_epsilon, num_train_epochs, max_steps, logging_steps, output_dir, seed,
+save_strategy ("steps" | "epoch" | "no"), save_steps, save_total_limit, save_only_model.
 """
+import json
 import math
 import os
+import random
+import re
+import shutil
 import time
 import types
 
 import torch
 
+from . import functional as F_
+from .checkpoint import AsyncCheckpointer, unwrap
 from .optimizer import TorchAdamW
+
+PREFIX_CHECKPOINT_DIR = "checkpoint"
+WEIGHTS_NAME, OPTIMIZER_NAME, SCHEDULER_NAME = "pytorch_model.bin", "optimizer.pt", "scheduler.pt"
+TRAINER_STATE_NAME, RNG_STATE_NAME = "trainer_state.json", "rng_state.pth"
 
 _DEFAULTS = dict(per_device_train_batch_size=8, per_device_eval_batch_size=8, learning_rate=5e-5,
                  weight_decay=0.0, adam_beta1=0.9, adam_beta2=0.999, adam_epsilon=1e-8, num_train_epochs=3.0,
-                 max_steps=-1, logging_steps=500, output_dir="./", seed=42, dataloader_drop_last=False)
+                 max_steps=-1, logging_steps=500, output_dir="./", seed=42, dataloader_drop_last=False,
+                 save_strategy="steps", save_steps=500, save_total_limit=None, save_only_model=False)
+
+
+def get_last_checkpoint(folder):
+    """Highest-numbered `checkpoint-<step>` directory of `folder` that holds a COMPLETE checkpoint (the trainer state
+    is the last file of a checkpoint to be written), or None."""
+    best, best_step = None, -1
+    if not os.path.isdir(folder):
+        return None
+    for name in os.listdir(folder):
+        m = re.fullmatch(PREFIX_CHECKPOINT_DIR + r"-(\d+)", name)
+        path = os.path.join(folder, name)
+        if m and os.path.isfile(os.path.join(path, TRAINER_STATE_NAME)) and int(m.group(1)) > best_step:
+            best, best_step = path, int(m.group(1))
+    return best
 
 
 class TrainOutput(types.SimpleNamespace):
@@ -46,6 +75,8 @@ class Trainer:
         self.optimizer, self.lr_scheduler = optimizers
         self.state = types.SimpleNamespace(global_step=0, epoch=0.0, log_history=[])
         self.device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        self._checkpointer = None
+        self._train_generator = None
 
     # ---- helpers -------------------------------------------------------------------------------
     def _arg(self, name):
@@ -57,6 +88,8 @@ class Trainer:
             sampler = torch.utils.data.distributed.DistributedSampler(dataset, seed=self._arg("seed"))
         g = torch.Generator()
         g.manual_seed(self._arg("seed"))
+        if shuffle:
+            self._train_generator = g if sampler is None else None
         return torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=shuffle and sampler is None,
                                            sampler=sampler, collate_fn=self.data_collator,
                                            drop_last=self._arg("dataloader_drop_last"),
@@ -108,10 +141,118 @@ class Trainer:
         loss.backward()
         return loss.detach()
 
+    # ---- checkpoints ---------------------------------------------------------------------------
+    def is_world_process_zero(self):
+        d = torch.distributed
+        return not (d.is_available() and d.is_initialized()) or d.get_rank() == 0
+
+    def _checkpointer_(self):
+        if self._checkpointer is None:
+            self._checkpointer = AsyncCheckpointer()
+        return self._checkpointer
+
+    def _rng_state(self):
+        st = {"python": random.getstate(), "cpu": torch.random.get_rng_state(),
+              "ct_dropout": (F_._DropoutState.seed, F_._DropoutState.stream)}
+        try:
+            import numpy as np
+            st["numpy"] = np.random.get_state()
+        except ImportError:
+            pass
+        if torch.cuda.is_available():
+            st["cuda"] = torch.cuda.random.get_rng_state()
+        return st
+
+    def _load_rng_state(self, checkpoint):
+        path = os.path.join(checkpoint, RNG_STATE_NAME)
+        if not os.path.isfile(path):
+            return
+        st = torch.load(path, weights_only=False)
+        random.setstate(st["python"])
+        torch.random.set_rng_state(st["cpu"])
+        if "numpy" in st:
+            import numpy as np
+            np.random.set_state(st["numpy"])
+        if "cuda" in st and torch.cuda.is_available():
+            torch.cuda.random.set_rng_state(st["cuda"])
+        F_._DropoutState.seed, F_._DropoutState.stream = st.get("ct_dropout", (None, 0))
+
+    def _save_checkpoint(self, model=None, metrics=None):
+        """trainer.py:1303-1342. Every rank may call it (like the reference); rank 0 writes. Returns the folder.
+        Nothing is on disk yet when it returns — `self.wait_for_checkpoints()` (called at the end of train()) or the
+        next save are the synchronisation points; `trainer_state.json` is written last and marks the folder complete."""
+        if not self.is_world_process_zero():
+            return None
+        run_dir = self._arg("output_dir")
+        out = os.path.join(run_dir, "%s-%d" % (PREFIX_CHECKPOINT_DIR, self.state.global_step))
+        os.makedirs(out, exist_ok=True)
+        files = {os.path.join(out, WEIGHTS_NAME): unwrap(model if model is not None else self.model).state_dict()}
+        if not self._arg("save_only_model"):
+            if self.optimizer is not None:
+                files[os.path.join(out, OPTIMIZER_NAME)] = self.optimizer.state_dict()
+            if self.lr_scheduler is not None:
+                files[os.path.join(out, SCHEDULER_NAME)] = self.lr_scheduler.state_dict()
+            files[os.path.join(out, RNG_STATE_NAME)] = self._rng_state()
+        state = {"global_step": self.state.global_step, "epoch": self.state.epoch,
+                 "log_history": list(self.state.log_history)}
+        if metrics is not None:
+            state["metrics"] = {k: float(v) for k, v in metrics.items()}
+        limit = self._arg("save_total_limit")
+        ck = self._checkpointer_()
+        ck.save(files, on_done=lambda: (self._write_state(out, state), self._rotate_checkpoints(run_dir, limit)))
+        return out
+
+    @staticmethod
+    def _write_state(out, state):
+        tmp = os.path.join(out, TRAINER_STATE_NAME + ".tmp")
+        with open(tmp, "w") as f:
+            json.dump(state, f, indent=2, sort_keys=True)
+        os.replace(tmp, os.path.join(out, TRAINER_STATE_NAME))
+
+    @staticmethod
+    def _sorted_checkpoints(run_dir):
+        found = []
+        for name in os.listdir(run_dir):
+            m = re.fullmatch(PREFIX_CHECKPOINT_DIR + r"-(\d+)", name)
+            if m and os.path.isdir(os.path.join(run_dir, name)):
+                found.append((int(m.group(1)), os.path.join(run_dir, name)))
+        return [p for _, p in sorted(found)]
+
+    @classmethod
+    def _rotate_checkpoints(cls, run_dir, limit):
+        """trainer.py:1465-1486: keep the `save_total_limit` newest folders. Runs in the writer thread AFTER the new
+        checkpoint is complete, so a crash never leaves fewer complete checkpoints than the limit."""
+        if limit is None or limit <= 0:
+            return
+        for old in cls._sorted_checkpoints(run_dir)[:-limit]:
+            shutil.rmtree(old, ignore_errors=True)
+
+    def wait_for_checkpoints(self):
+        if self._checkpointer is not None:
+            self._checkpointer.wait()
+
+    def _load_checkpoint(self, checkpoint):
+        """trainer.py:351-379, 1516-1597, 1619-1654: weights, optimizer / scheduler state, trainer state."""
+        weights = os.path.join(checkpoint, WEIGHTS_NAME)
+        if not os.path.isfile(weights):
+            raise ValueError("Can't find a valid checkpoint at %s" % checkpoint)
+        target = unwrap(self.model)
+        dev = next(target.parameters()).device
+        target.load_state_dict(torch.load(weights, map_location=dev), strict=True)
+        F_.invalidate_shadows(target)
+        opt = self.create_optimizer()
+        if os.path.isfile(os.path.join(checkpoint, OPTIMIZER_NAME)):
+            opt.load_state_dict(torch.load(os.path.join(checkpoint, OPTIMIZER_NAME), map_location="cpu"))
+        if self.lr_scheduler is not None and os.path.isfile(os.path.join(checkpoint, SCHEDULER_NAME)):
+            self.lr_scheduler.load_state_dict(torch.load(os.path.join(checkpoint, SCHEDULER_NAME), weights_only=False))
+        with open(os.path.join(checkpoint, TRAINER_STATE_NAME)) as f:
+            st = json.load(f)
+        self.state.global_step = int(st["global_step"])
+        self.state.epoch = float(st.get("epoch", 0.0))
+        self.state.log_history = list(st.get("log_history", []))
+
     # ---- public API ----------------------------------------------------------------------------
     def train(self, resume_from_checkpoint=None, **kwargs):
-        if resume_from_checkpoint:
-            raise NotImplementedError("checkpoint resume is outside the hot path this package covers")
         loader = self.get_train_dataloader()
         opt = self.create_optimizer()
         max_steps = self._arg("max_steps")
@@ -119,29 +260,61 @@ class Trainer:
         if max_steps is None or max_steps <= 0:
             max_steps = int(math.ceil(epochs * len(loader)))
         log_every = max(1, int(self._arg("logging_steps")))
-        t0, running, last = time.time(), None, float("nan")
-        epoch = 0
+        strategy = str(self._arg("save_strategy")).lower().replace("intervalstrategy.", "")
+        save_every = max(1, int(self._arg("save_steps")))
+        epoch, skip = 0, 0
+        if resume_from_checkpoint:
+            if isinstance(resume_from_checkpoint, bool):
+                resume_from_checkpoint = get_last_checkpoint(self._arg("output_dir"))
+                if resume_from_checkpoint is None:
+                    raise ValueError("No valid checkpoint found in output directory (%s)" % self._arg("output_dir"))
+            self._load_checkpoint(resume_from_checkpoint)
+            epoch, skip = divmod(self.state.global_step, max(1, len(loader)))
+        t0, running, last, n_running = time.time(), None, float("nan"), 0
+        ck = None
         while self.state.global_step < max_steps:
+            # the order of an epoch depends on (seed, epoch) only, so a resumed run replays nothing to find its place
             if hasattr(loader.sampler, "set_epoch"):
                 loader.sampler.set_epoch(epoch)
-            for inputs in loader:
+            if self._train_generator is not None:
+                self._train_generator.manual_seed(self._arg("seed") + epoch)
+            it = iter(loader)
+            in_epoch = skip
+            for _ in range(skip):   # trainer.py:448-451: batches of the interrupted epoch that were already trained on
+                next(it)
+            skip = 0
+            if resume_from_checkpoint:
+                self._load_rng_state(resume_from_checkpoint)   # trainer.py:453
+                resume_from_checkpoint = None
+            for inputs in it:
                 opt.zero_grad()
                 loss = self.training_step(self.model, inputs)
+                if ck is not None:
+                    ck.guard()   # a snapshot still reading the live parameters / moments finishes before they change
                 opt.step()
                 if self.lr_scheduler is not None:
                     self.lr_scheduler.step()
                 self.state.global_step += 1
+                in_epoch += 1
+                self.state.epoch = epoch + in_epoch / max(1, len(loader))
                 running = loss if running is None else running + loss
+                n_running += 1
                 if self.state.global_step % log_every == 0:
-                    last = float(running) / log_every
-                    running = None
+                    last = float(running) / n_running
+                    running, n_running = None, 0
                     self.state.log_history.append({"step": self.state.global_step, "loss": last})
+                if strategy == "steps" and self.state.global_step % save_every == 0:
+                    self._save_checkpoint(self.model)
+                    ck = self._checkpointer
                 if self.state.global_step >= max_steps:
                     break
             epoch += 1
-            self.state.epoch = float(epoch)
+            if strategy == "epoch" and in_epoch == len(loader):
+                self._save_checkpoint(self.model)
+                ck = self._checkpointer
         if running is not None:
-            last = float(running) / max(1, self.state.global_step % log_every)
+            last = float(running) / max(1, n_running)
+        self.wait_for_checkpoints()
         return TrainOutput(global_step=self.state.global_step, training_loss=last,
                            metrics={"train_runtime": time.time() - t0, "train_loss": last})
 
@@ -157,7 +330,11 @@ class Trainer:
         return {metric_key_prefix + "_loss": tot / max(n, 1), metric_key_prefix + "_batches": n}
 
     def save_model(self, output_dir=None, _internal_call=False):
+        """trainer.py:1347-1404 (plain-module branch: `torch.save(state_dict, pytorch_model.bin)`). On disk when it
+        returns."""
+        if not self.is_world_process_zero():
+            return
         out = output_dir or self._arg("output_dir")
-        os.makedirs(out, exist_ok=True)
-        model = self.model.module if hasattr(self.model, "module") else self.model
-        torch.save(model.state_dict(), os.path.join(out, "pytorch_model.bin"))
+        ck = self._checkpointer_()
+        ck.save({os.path.join(out, WEIGHTS_NAME): unwrap(self.model).state_dict()})
+        ck.wait()

@@ -903,3 +903,84 @@ def test_decode_plan_is_reused_between_generations_and_dropped_when_parameters_c
         both(*prompts(6, P=9))
         both(*prompts(7, P=9))
         assert m._ct_decode_plan_reused is False
+
+
+def _toy_trainer(tmp_path, max_steps, **extra):
+    import types
+    from cleantransformer_b200.models import modeling_bloom as mb
+    from cleantransformer_b200.trainer import Trainer
+    cfg = dict(vocab_size=64, hidden_size=32, n_layer=2, num_attention_heads=4)
+    g = torch.Generator().manual_seed(3)
+    data = [dict(input_ids=torch.randint(3, 64, (10,), generator=g), attention_mask=torch.ones(10, dtype=torch.long))
+            for _ in range(12)]
+    for d in data:
+        d["labels"] = d["input_ids"].clone()
+
+    def collate(items):
+        return {k: torch.stack([it[k] for it in items]) for k in items[0]}
+
+    torch.manual_seed(4)
+    m = mb.BloomForCausalLM(mb.BloomConfig(**cfg))
+    m._tie_weight()
+    a = dict(per_device_train_batch_size=4, learning_rate=5e-3, max_steps=max_steps, logging_steps=1,
+             output_dir=str(tmp_path), weight_decay=0.01, save_steps=5)
+    a.update(extra)
+    return Trainer(model=m, args=types.SimpleNamespace(**a), data_collator=collate, train_dataset=data), m
+
+
+def test_trainer_checkpoints_are_reference_shaped_and_a_resumed_run_is_bit_identical(golden, tmp_path):
+    """SURVEY §8 N4 (trainer/trainer.py:1303-1342 save, :351-379 + :448-453 resume, :1465-1486 rotation): the folders
+    hold what the reference's loaders expect (plain torch.save'd state_dicts that torch.optim.AdamW itself accepts),
+    are written behind the step loop, and a run resumed from the middle of an epoch ends with the SAME bits —
+    parameters, both AdamW moments, step counters, logged losses — as the uninterrupted one."""
+    import json, os
+    with mock_ops.patched():
+        straight, m_a = _toy_trainer(tmp_path / "a", 12)
+        out = straight.train()
+        assert out.global_step == 12
+        folders = sorted(os.listdir(tmp_path / "a"))
+        assert folders == ["checkpoint-10", "checkpoint-5"], folders
+        for f in folders:
+            assert sorted(os.listdir(tmp_path / "a" / f)) == ["optimizer.pt", "pytorch_model.bin", "rng_state.pth",
+                                                                "trainer_state.json"]
+        st = json.load(open(tmp_path / "a" / "checkpoint-5" / "trainer_state.json"))
+        assert st["global_step"] == 5 and len(st["log_history"]) == 5 and abs(st["epoch"] - 5 / 3) < 1e-9
+
+        # the files load into the reference's own stack: strict state_dict load, torch.optim.AdamW.load_state_dict
+        sd = torch.load(str(tmp_path / "a" / "checkpoint-5" / "pytorch_model.bin"))
+        assert set(sd) == set(m_a.state_dict())
+        assert sd["lm_head.weight"].data_ptr() == sd["bloom.word_embeddings.weight"].data_ptr()   # still tied
+        osd = torch.load(str(tmp_path / "a" / "checkpoint-5" / "optimizer.pt"))
+        ref_opt = torch.optim.AdamW([torch.nn.Parameter(p.detach().clone()) for p in m_a.parameters()], lr=1.0)
+        ref_opt.load_state_dict(osd)
+        assert all(float(s["step"]) == 5.0 for s in ref_opt.state.values())
+
+        # interrupted at step 7 (in the middle of epoch 2: its last checkpoint is step 5), then resumed to 12
+        first, _ = _toy_trainer(tmp_path / "b", 7)
+        first.train()
+        assert sorted(os.listdir(tmp_path / "b")) == ["checkpoint-5"]
+        second, m_b = _toy_trainer(tmp_path / "b", 12)
+        torch.manual_seed(12345)                 # whatever state the new process has must not matter
+        out_b = second.train(resume_from_checkpoint=True)
+        assert out_b.global_step == 12
+        assert [h["step"] for h in second.state.log_history] == list(range(1, 13))
+        for ha, hb in zip(straight.state.log_history, second.state.log_history):
+            assert ha == hb, (ha, hb)
+        for (n, pa), (_, pb) in zip(m_a.named_parameters(), m_b.named_parameters()):
+            assert torch.equal(pa, pb), n
+        for pa, pb in zip(m_a.parameters(), m_b.parameters()):
+            sa, sb = straight.optimizer.state[pa], second.optimizer.state[pb]
+            assert torch.equal(sa["exp_avg"], sb["exp_avg"]) and torch.equal(sa["exp_avg_sq"], sb["exp_avg_sq"])
+            assert float(sa["step"]) == float(sb["step"]) == 12.0
+            assert sb["exp_avg"].data_ptr() == second.optimizer._arena.param_view(pb, second.optimizer._arena.exp_avg).data_ptr()
+
+        # rotation keeps the newest `save_total_limit` complete folders; "epoch" strategy saves at epoch ends
+        rot, _ = _toy_trainer(tmp_path / "c", 9, save_steps=2, save_total_limit=2)
+        rot.train()
+        assert sorted(os.listdir(tmp_path / "c")) == ["checkpoint-6", "checkpoint-8"]
+        ep, _ = _toy_trainer(tmp_path / "d", 7, save_strategy="epoch", save_only_model=True)
+        ep.train()
+        assert sorted(os.listdir(tmp_path / "d")) == ["checkpoint-3", "checkpoint-6"]
+        assert sorted(os.listdir(tmp_path / "d" / "checkpoint-6")) == ["pytorch_model.bin", "trainer_state.json"]
+        with pytest.raises(ValueError):
+            _toy_trainer(tmp_path / "e", 3)[0].train(resume_from_checkpoint=True)

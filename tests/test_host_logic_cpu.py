@@ -399,3 +399,47 @@ def test_dropout_stream_numbers_follow_the_call_order_and_the_seed_is_torchs():
     assert bool(O.dropout_mask_elementwise((8, 8), 0.0, 7, 1).all())
     ma = O.dropout_mask_attention(2, 3, 5, 7, 0.5, 11, 4)
     assert ma.shape == (2, 3, 5, 7) and not torch.equal(ma[0, 0], ma[0, 1]) and not torch.equal(ma[0, 0], ma[1, 0])
+
+
+def test_async_checkpointer_snapshots_at_call_time_and_groups_by_storage(tmp_path):
+    """checkpoint.AsyncCheckpointer (examples/ft_bloom_DDP.py:155-156 is the blocking save it
+    replaces): the file holds the values AT THE CALL even when the live tensors change right after it, views of one
+    flat buffer are saved as ONE storage holding only the covering range, shared memory stays shared, strides and
+    nested containers survive, a failing write surfaces at the next synchronisation point, files appear atomically."""
+    import os
+    from cleantransformer_b200.checkpoint import AsyncCheckpointer
+    flat = torch.arange(1000, dtype=torch.float32)
+    w, b = flat[64:192].view(8, 16), flat[256:272]
+    tied = w
+    col = torch.arange(12.).view(3, 4).t()          # non-contiguous, its own storage
+    step = torch.tensor(7.0)
+    obj = {"model": {"w": w, "b": b, "tied": tied, "col": col, "empty": torch.empty(0, 3)},
+           "opt": {"state": {0: {"step": step, "m": flat[512:640].view(8, 16)}}, "groups": [{"lr": 1e-3, "params": [0]}]},
+           "tuple": (1, "x", torch.ones(2, dtype=torch.int64))}
+    expect_w, expect_m = w.clone(), flat[512:640].clone()
+    with AsyncCheckpointer() as ck:
+        path = str(tmp_path / "deep" / "x.pt")
+        ck.save({path: obj}, json_files={str(tmp_path / "s.json"): {"global_step": 7}},
+                on_done=lambda: open(tmp_path / "done", "w").close())
+        flat.zero_()            # the "next optimizer step"
+        step += 1
+        obj["opt"]["groups"][0]["lr"] = 5.0
+        ck.wait()
+        assert os.path.exists(tmp_path / "done") and not os.path.exists(path + ".tmp")
+        r = torch.load(path, weights_only=False)
+        assert torch.equal(r["model"]["w"], expect_w) and torch.equal(r["opt"]["state"][0]["m"].flatten(), expect_m)
+        assert float(r["opt"]["state"][0]["step"]) == 7.0 and r["opt"]["groups"][0]["lr"] == 1e-3
+        assert r["model"]["w"].data_ptr() == r["model"]["tied"].data_ptr()
+        assert r["model"]["w"].untyped_storage().data_ptr() == r["opt"]["state"][0]["m"].untyped_storage().data_ptr()
+        assert r["model"]["w"].untyped_storage().nbytes() == (640 - 64) * 4        # the covering range, not the arena
+        assert r["model"]["col"].stride() == (1, 4) and torch.equal(r["model"]["col"], col)
+        assert r["model"]["empty"].shape == (0, 3) and r["tuple"][:2] == (1, "x")
+        assert open(tmp_path / "s.json").read().strip().startswith("{")
+        # a failure in the writer thread is not lost
+        os.makedirs(tmp_path / "isdir.pt")
+        ck.save({str(tmp_path / "isdir.pt"): {"a": torch.ones(1)}})
+        with pytest.raises(RuntimeError, match="asynchronous checkpoint failed"):
+            ck.wait()
+        ck.save({str(tmp_path / "ok.pt"): {"a": torch.ones(1)}})
+        ck.wait()
+        assert torch.load(str(tmp_path / "ok.pt"))["a"].item() == 1.0
