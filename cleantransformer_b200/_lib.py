@@ -133,6 +133,9 @@ SIGNATURES = {
                                   c_void_p, c_void_p]),
     "ct_embedding_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_void_p]),
     "ct_embedding_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p]),
+    "ct_embedding_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_void_p, c_void_p,
+                                           c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                           c_void_p, c_void_p, c_i64, c_i64, c_float, c_void_p]),
     "ct_cross_entropy_fwd": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p, c_i64, c_void_p,
                                      c_void_p, c_i64, c_i64, c_i64, c_int, c_i64, c_void_p]),
     "ct_cross_entropy_fwd_stats": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,

@@ -27,13 +27,18 @@ The files are what the reference's loaders expect: plain `torch.save`d state_dic
 `optimizer.pt`, `scheduler.pt`) and json. On CPU tensors (the host-logic tests) the same code runs without
 streams: "copy" is a clone.
 """
+import atexit
 import copy
 import json
 import os
 import queue
 import threading
+import weakref
 
 import torch
+
+_torch_save = torch.save        # the launcher's --ct-async-save replaces torch.save; the writer thread needs the real one
+_LIVE = weakref.WeakSet()       # checkpointers that may hold a stage-"host" read of live tensors (guard_pending)
 
 
 def _extent(t):
@@ -86,6 +91,7 @@ class AsyncCheckpointer:
         self._thread = threading.Thread(target=self._writer, name="ct-checkpoint-writer", daemon=True)
         self._thread.start()
         self.saved = []                    # paths written so far (writer thread appends)
+        _LIVE.add(self)
 
     # ---- snapshot ------------------------------------------------------------------------------
     def _collect(self, obj, groups):
@@ -213,7 +219,7 @@ class AsyncCheckpointer:
                     event.synchronize()     # blocks this thread only
                 for path, obj in skeleton.items():
                     real = self._materialise(obj, host_of)
-                    self._atomic(path, lambda tmp, real=real: torch.save(real, tmp))
+                    self._atomic(path, lambda tmp, real=real: _torch_save(real, tmp))
                     self.saved.append(path)
                 for path, obj in json_files.items():
                     def w(tmp, obj=obj):
@@ -258,3 +264,39 @@ def unwrap(model):
     """The module whose state_dict the reference saves (`model.module` under DistributedDataParallel,
     examples/ft_bloom_DDP.py:147-150)."""
     return model.module if hasattr(model, "module") and isinstance(model.module, torch.nn.Module) else model
+
+
+def guard_pending():
+    """Called by this package's optimizers at the top of step(): no parameter or moment is overwritten while a
+    stage-"host" snapshot is still reading it, whoever drives the loop."""
+    for ck in list(_LIVE):
+        if ck._pending_read is not None:
+            ck.guard()
+
+
+_default = None
+
+
+def default_checkpointer():
+    """Process-wide checkpointer, flushed at interpreter exit."""
+    global _default
+    if _default is None:
+        _default = AsyncCheckpointer()
+        atexit.register(_default.close)
+    return _default
+
+
+def has_device_tensor(obj, _depth=0):
+    if torch.is_tensor(obj):
+        return obj.is_cuda
+    if isinstance(obj, dict):
+        return any(has_device_tensor(v, _depth + 1) for v in obj.values())
+    if isinstance(obj, (list, tuple)):
+        return any(has_device_tensor(v, _depth + 1) for v in obj)
+    return False
+
+
+def save_async(obj, path):
+    """`torch.save(obj, path)` that returns once the copies are enqueued (the launcher's `--ct-async-save` routes the
+    reference scripts' `torch.save(model.state_dict(), ...)`, examples/ft_bloom_DDP.py:155-156, through here)."""
+    default_checkpointer().save({os.fspath(path): obj})

@@ -145,6 +145,94 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
   }
 }
 
+// ---- embedding gather (up to three tables) + LayerNorm in one pass -------------------
+// modeling_bloom.py:190-191 (word_embeddings -> word_embeddings_layernorm), modeling_bert.py:297-301
+// (word + segment + position tables -> embedding_post LayerNorm). One warp per token: the table rows are
+// summed in registers, the sum is written once (fp32, only when a backward will need it as the LayerNorm
+// input) and normalised without ever being read back. An id outside its table poisons the row with NaN,
+// like embedding_fwd_kernel. Algorithmic bytes per token: H*4*(tables [+1 emb]) + H*(sizeof(y) [+ sizeof(y2)]).
+struct EmbedLnTables {
+  const long long* ids[3];
+  const float* w[3];
+  long long vocab[3];
+  int n;
+};
+
+template <int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+    embed_ln_fwd_kernel(EmbedLnTables tb, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        float* __restrict__ emb, void* __restrict__ y, int y_dtype, void* __restrict__ y2,
+                        int y2_dtype, float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows,
+                        float eps) {
+  constexpr int COLS = VPL * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * LN_WARPS;
+  float4 g[VPL], b[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    g[i] = Vec4<float>::load(gamma + i * 128 + lane * 4);
+    b[i] = Vec4<float>::load(beta + i * 128 + lane * 4);
+  }
+  for (int64_t row = warp; row < rows; row += nwarps) {
+    float4 v[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < tb.n) {
+        const long long id = tb.ids[k][row];
+        if (id < 0 || id >= tb.vocab[k]) {
+          bad = true;
+        } else {
+          const float* src = tb.w[k] + id * COLS + lane * 4;
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) {
+            const float4 t = Vec4<float>::load(src + i * 128);
+            v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+          }
+        }
+      }
+    }
+    if (bad) {
+      const float nan = __int_as_float(0x7fc00000);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) v[i] = make_float4(nan, nan, nan, nan);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (emb) Vec4<float>::store(emb + row * COLS + i * 128 + lane * 4, v[i]);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.f / COLS);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float var = warp_sum(q) * (1.f / COLS) + eps;
+    const float rstd = rsqrtf(var);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float4 o;
+      o.x = fmaf(v[i].x * rstd, g[i].x, b[i].x);
+      o.y = fmaf(v[i].y * rstd, g[i].y, b[i].y);
+      o.z = fmaf(v[i].z * rstd, g[i].z, b[i].z);
+      o.w = fmaf(v[i].w * rstd, g[i].w, b[i].w);
+      const int64_t idx = row * COLS + i * 128 + lane * 4;
+      if (y) store4_dyn(y, y_dtype, idx, o);
+      if (y2) store4_dyn(y2, y2_dtype, idx, o);
+    }
+  }
+}
+
 // ---- forward, arbitrary cols (row re-read from L1/L2) -------------------------------------------
 __global__ void __launch_bounds__(LN_WARPS * 32)
     ln_fwd_generic_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ gamma,
@@ -677,6 +765,48 @@ extern "C" int ct_layernorm_fwd(const void* x, int x_dtype, const float* gamma, 
                                                           y2_dtype, mean, rstd, rows, cols, eps);
   }
 #undef CT_LN_FWD
+  CT_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int ct_embedding_layernorm_fwd(const int64_t* ids0, const float* table0, int64_t vocab0,
+                                          const int64_t* ids1, const float* table1, int64_t vocab1,
+                                          const int64_t* ids2, const float* table2, int64_t vocab2,
+                                          const float* gamma, const float* beta, float* emb, void* y, int y_dtype,
+                                          void* y2, int y2_dtype, float* mean, float* rstd, int64_t rows,
+                                          int64_t cols, float eps, void* stream) {
+  CT_REQUIRE(rows >= 0 && cols > 0, CT_ERR_BAD_ARG, "ct_embedding_layernorm_fwd: bad shape %lld x %lld",
+             (long long)rows, (long long)cols);
+  if (rows == 0) return 0;
+  CT_REQUIRE(ids0 && table0 && gamma && beta && (y || y2), CT_ERR_BAD_ARG,
+             "ct_embedding_layernorm_fwd: null pointer");
+  CT_REQUIRE((ids1 == nullptr) == (table1 == nullptr) && (ids2 == nullptr) == (table2 == nullptr) &&
+                 (ids1 != nullptr || ids2 == nullptr),
+             CT_ERR_BAD_ARG, "ct_embedding_layernorm_fwd: tables are given in order, each with its ids");
+  CT_REQUIRE((!y || dt_ok(y_dtype)) && (!y2 || dt_ok(y2_dtype)), CT_ERR_UNSUPPORTED,
+             "ct_embedding_layernorm_fwd: dtype must be f32, bf16 or f16");
+  CT_REQUIRE((cols % 128 == 0) && cols <= 1024 && aligned16(table0) && aligned16(table1) && aligned16(table2) &&
+                 aligned16(emb) && aligned16(y) && aligned16(y2) && aligned16(gamma) && aligned16(beta),
+             CT_ERR_UNSUPPORTED,
+             "ct_embedding_layernorm_fwd: needs cols %% 128 == 0, cols <= 1024 and 16-byte aligned pointers "
+             "(use ct_embedding_fwd + ct_layernorm_fwd otherwise)");
+  EmbedLnTables tb;
+  tb.ids[0] = reinterpret_cast<const long long*>(ids0); tb.w[0] = table0; tb.vocab[0] = vocab0;
+  tb.ids[1] = reinterpret_cast<const long long*>(ids1); tb.w[1] = table1; tb.vocab[1] = vocab1;
+  tb.ids[2] = reinterpret_cast<const long long*>(ids2); tb.w[2] = table2; tb.vocab[2] = vocab2;
+  tb.n = 1 + (ids1 != nullptr) + (ids2 != nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(rows);
+#define CT_EMBED_LN(V)                                                                                   \
+  case V:                                                                                                \
+    embed_ln_fwd_kernel<V><<<grid, LN_WARPS * 32, 0, st>>>(tb, gamma, beta, emb, y, y_dtype, y2, y2_dtype, \
+                                                           mean, rstd, rows, eps);                       \
+    break;
+  switch ((int)(cols / 128)) {
+    CT_EMBED_LN(1) CT_EMBED_LN(2) CT_EMBED_LN(3) CT_EMBED_LN(4) CT_EMBED_LN(5) CT_EMBED_LN(6) CT_EMBED_LN(7)
+    CT_EMBED_LN(8)
+  }
+#undef CT_EMBED_LN
   CT_LAUNCH_OK();
   return 0;
 }

@@ -424,27 +424,85 @@ class EmbeddingFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        dout = dout.contiguous()
-        if dout.dtype != torch.float32:
-            dout = ops.cast(dout, torch.float32)
-        for k, (i, w) in enumerate(zip(ctx.ids, ctx.weights)):
-            if not w.requires_grad:
-                continue
-            g, acc = grad_buffer(w)
-            if not acc:
-                g.zero_()
-            pad = ctx.padding_idx0 if k == 0 else -1
-            override = getattr(w, "_ct_embedding_bwd_override", None)  # ddp.py: sparse exchange of a tied table
-            if override is not None:
-                override(w, i, dout, g, pad)
-            else:
-                ops.embedding_bwd(i, dout, g, pad)
-            grad_written(w)
+        _embedding_scatter(ctx.ids, ctx.weights, dout, ctx.padding_idx0)
         return None, None, None, None
+
+
+def _embedding_scatter(ids, weights, dout, padding_idx0):
+    """The autograd scatter of the gathers: every table's gradient += its token rows of `dout`."""
+    dout = dout.contiguous()
+    if dout.dtype != torch.float32:
+        dout = ops.cast(dout, torch.float32)
+    for k, (i, w) in enumerate(zip(ids, weights)):
+        if not w.requires_grad:
+            continue
+        g, acc = grad_buffer(w)
+        if not acc:
+            g.zero_()
+        pad = padding_idx0 if k == 0 else -1
+        override = getattr(w, "_ct_embedding_bwd_override", None)  # ddp.py: sparse exchange of a tied table
+        if override is not None:
+            override(w, i, dout, g, pad)
+        else:
+            ops.embedding_bwd(i, dout, g, pad)
+        grad_written(w)
 
 
 def embedding_sum(ids_list, weight_list, padding_idx0=-1):
     return EmbeddingFn.apply(tuple(ids_list), tuple(weight_list), padding_idx0, _anchor(weight_list))
+
+
+# SURVEY §8 f N3: the gather(s) and the LayerNorm that follows them as ONE kernel (Bloom's word_embeddings_layernorm,
+# BERT's embedding_post). Opt-in (CT_FUSED_EMBED_LN=1) — parity-tested on the GPU, never benchmarked at length.
+FUSED_EMBED_LN = os.environ.get("CT_FUSED_EMBED_LN", "0") == "1"
+
+
+class EmbeddingLNFn(torch.autograd.Function):
+    """LayerNorm(sum_k weight_k[ids_k]): modeling_bloom.py:190-191, modeling_bert.py:297-301. The backward is the
+    LayerNorm backward (transformer.py:79-89) on the saved sum followed by the scatter of EmbeddingFn."""
+
+    @staticmethod
+    def forward(ctx, ids, weights, padding_idx0, ln_wb, eps, out_dtype, anchor):
+        gamma, beta = ln_wb
+        shape = torch.broadcast_shapes(*[i.shape for i in ids])
+        ids = [i.expand(shape).contiguous() for i in ids]
+        need = any(w.requires_grad for w in weights) or gamma.requires_grad or beta.requires_grad
+        note_use(*weights)
+        note_use(gamma, beta)
+        emb, y, _, mean, rstd = ops.embedding_layernorm_fwd(ids, [w.detach() for w in weights], gamma.detach().reshape(-1),
+                                                            beta.detach().reshape(-1), eps, out_dtype, None, save=need)
+        if need:
+            ctx.save_for_backward(emb, mean, rstd)
+        ctx.ids, ctx.weights, ctx.padding_idx0 = ids, weights, padding_idx0
+        ctx.gamma, ctx.beta = gamma, beta
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        emb, mean, rstd = ctx.saved_tensors
+        gamma, beta = ctx.gamma, ctx.beta
+        gw, acc_w = grad_buffer(gamma) if gamma.requires_grad else (None, False)
+        gb, acc_b = grad_buffer(beta) if beta.requires_grad else (None, False)
+        if gw is not None and gb is not None and acc_w != acc_b:
+            (gw if not acc_w else gb).zero_()
+            acc_w = acc_b = True
+        demb = ops.layernorm_bwd(dy, emb, gamma.detach().reshape(-1), mean, rstd,
+                                 gw.view(-1) if gw is not None else None, gb.view(-1) if gb is not None else None,
+                                 acc_w if gw is not None else acc_b, dx_dtype=torch.float32)
+        if gw is not None:
+            grad_written(gamma)
+        if gb is not None:
+            grad_written(beta)
+        _embedding_scatter(ctx.ids, ctx.weights, demb, ctx.padding_idx0)
+        return None, None, None, None, None, None, None
+
+
+def embedding_layer_norm(ids_list, weight_list, ln_weight, ln_bias, eps, padding_idx0=-1, out_dtype=torch.float32):
+    """LayerNorm(embedding_sum(...)): one kernel when FUSED_EMBED_LN is on and the shape fits, else the two calls."""
+    if FUSED_EMBED_LN and ops.embedding_layernorm_ok(weight_list, ln_weight):
+        return EmbeddingLNFn.apply(tuple(ids_list), tuple(weight_list), padding_idx0, (ln_weight, ln_bias), eps,
+                                   out_dtype, _anchor(tuple(weight_list) + (ln_weight, ln_bias)))
+    return layer_norm(embedding_sum(ids_list, weight_list, padding_idx0), ln_weight, ln_bias, eps, out_dtype=out_dtype)
 
 
 class LMLossFn(torch.autograd.Function):

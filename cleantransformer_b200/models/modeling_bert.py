@@ -120,10 +120,11 @@ class BertModel(torch.nn.Module):
             # the reference builds this on the CPU (modeling_bert.py:294-295) and would then fail on a
             # GPU; build it on the input's device instead
             position_ids = torch.arange(input_ids.shape[1], dtype=torch.long, device=input_ids.device)
-        emb = F.embedding_sum([input_ids, segment_ids, position_ids[None, :] if position_ids.dim() == 1 else position_ids],
-                              [self.word_embeddings.weight, self.segment_embeddings.weight,
-                               self.position_embeddings.weight], padding_idx0=0)
-        hidden_states = self.embedding_post[0](emb)
+        ln = self.embedding_post[0]
+        hidden_states = F.embedding_layer_norm(
+            [input_ids, segment_ids, position_ids[None, :] if position_ids.dim() == 1 else position_ids],
+            [self.word_embeddings.weight, self.segment_embeddings.weight, self.position_embeddings.weight],
+            ln.weight, ln.bias, ln.eps, padding_idx0=0)
         hidden_states = F.dropout(hidden_states, self.embedding_post[1].p, _drop_on(self.embedding_post[1]))
         kb = None
         if attention_mask is not None:

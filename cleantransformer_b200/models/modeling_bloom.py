@@ -252,8 +252,8 @@ class BloomModel(torch.nn.Module):
         F.reject_head_mask(head_mask)
         if k_v_pasts is None:
             k_v_pasts = [None] * self.config.n_layer
-        emb = F.embedding_sum([input_ids], [self.word_embeddings.weight])
-        hidden_states = self.word_embeddings_layernorm(emb)
+        ln = self.word_embeddings_layernorm
+        hidden_states = F.embedding_layer_norm([input_ids], [self.word_embeddings.weight], ln.weight, ln.bias, ln.eps)
         bias = attention_mask if isinstance(attention_mask, AttnBias) else \
             AttnBias.from_mask(attention_mask, self.num_heads, input_ids.shape[1])
         for i, block in enumerate(self.blocks):

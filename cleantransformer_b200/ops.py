@@ -457,6 +457,44 @@ def embedding_fwd(ids, weight, out=None, accumulate=False):
     return out
 
 
+def embedding_layernorm_ok(weights, gamma):
+    """Shapes the fused gather + LayerNorm kernel takes (csrc/layernorm.cu: the row lives in registers)."""
+    H = gamma.numel()
+    return 1 <= len(weights) <= 3 and H % 128 == 0 and H <= 1024 and \
+        all(w.dtype == torch.float32 and w.dim() == 2 and w.shape[1] == H and w.is_contiguous() for w in weights)
+
+
+def embedding_layernorm_fwd(ids_list, weights, gamma, beta, eps, out_dtype=torch.float32, out2_dtype=None,
+                            save=True):
+    """LN(sum_k weights[k][ids_list[k]]) in one kernel (modeling_bloom.py:190-191, modeling_bert.py:297-301).
+    ids_list: int64 tensors of one common shape. Returns (emb or None, y, y2 or None, mean, rstd); emb / mean /
+    rstd only when `save` (what the LayerNorm backward needs)."""
+    _req_cuda(gamma, beta, *ids_list, *weights)
+    H = gamma.numel()
+    shape = tuple(ids_list[0].shape)
+    ids = [i.contiguous() for i in ids_list]
+    for i in ids:
+        if i.dtype != torch.int64 or tuple(i.shape) != shape:
+            raise TypeError("embedding_layernorm_fwd: ids must be int64 tensors of one shape")
+    rows = ids[0].numel()
+    dev = gamma.device
+    emb = torch.empty(shape + (H,), dtype=torch.float32, device=dev) if save else None
+    y = torch.empty(shape + (H,), dtype=out_dtype, device=dev)
+    y2 = torch.empty(shape + (H,), dtype=out2_dtype, device=dev) if out2_dtype is not None else None
+    mean = torch.empty(rows, dtype=torch.float32, device=dev) if save else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=dev) if save else None
+    tabs = []
+    for k in range(3):
+        if k < len(ids):
+            tabs += [ptr(ids[k]), ptr(weights[k]), weights[k].shape[0]]
+        else:
+            tabs += [0, 0, 0]
+    _ck(_lib.load().ct_embedding_layernorm_fwd(*tabs, ptr(gamma), ptr(beta), ptr(emb), ptr(y), dt(y), ptr(y2),
+                                                 dt(y2) if y2 is not None else 0, ptr(mean), ptr(rstd), rows, H,
+                                                 float(eps), stream()), "ct_embedding_layernorm_fwd")
+    return emb, y, y2, mean, rstd
+
+
 def embedding_bwd(ids, dout, dweight, padding_idx=-1):
     ids = ids.contiguous()
     dout = dout.contiguous()

@@ -15,6 +15,7 @@ There is no CPU path: parameters must live on a CUDA device.
 import torch
 
 from . import ops
+from .checkpoint import guard_pending
 from .arena import ParamArena, arena_of
 
 
@@ -44,6 +45,7 @@ class SGD:
     @torch.no_grad()
     def step(self):
         _require_cuda(self.params)
+        guard_pending()
         for i, param in enumerate(self.params):
             if param.grad is None:
                 continue
@@ -102,6 +104,7 @@ class AdamW:
     def step(self):
         if not self.params:
             return
+        guard_pending()
         self._ensure_state()
         a = self._arena
         wd = self.weight_decay or 0.0
@@ -201,6 +204,7 @@ class TorchAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         self._setup()
+        guard_pending()   # an asynchronous checkpoint still reading the live parameters / moments finishes first
         a = self._arena
         groups = self.param_groups
         uniform = all((g["lr"], g["betas"], g["eps"], g["weight_decay"]) ==

@@ -14,6 +14,10 @@ What `install()` does before the script is executed with runpy (SURVEY.md §0 D6
     DistributedDataParallel (bucketed P2P all-reduce over NVSwitch);
   * `transformers.BloomTokenizerFast` (removed from recent transformers releases) is aliased to
     PreTrainedTokenizerFast;
+  * with `--ct-async-save`, `torch.save(obj, path)` of anything that holds CUDA tensors (the periodic
+    `torch.save(model.state_dict(), ...)` of examples/ft_bloom_DDP.py:155-156) is snapshotted on the device and
+    written behind the step loop by `checkpoint.AsyncCheckpointer`; files are complete at interpreter exit at the
+    latest (opt-in: a script that reads its own checkpoint back right away must keep the blocking save);
   * the default device becomes the local GPU, because the inference examples build their inputs with
     bare `torch.tensor(...)` (examples/inference_bert.py:71-73) and there is no CPU fallback here.
 Nothing is copied from or written to the reference tree; the script's directory layout
@@ -39,7 +43,7 @@ _PACKAGES = ["CleanTransformer", "CleanTransformer.models", "CleanTransformer.ge
 _installed = {}
 
 
-def install(swap_optimizer=True, swap_ddp=True, default_device=True):
+def install(swap_optimizer=True, swap_ddp=True, default_device=True, async_save=False):
     """Idempotent. Returns a dict describing what was patched (used by the tests)."""
     if _installed:
         return _installed
@@ -77,6 +81,17 @@ def install(swap_optimizer=True, swap_ddp=True, default_device=True):
         from .ddp import DistributedDataParallel
         _installed["DistributedDataParallel"] = torch.nn.parallel.DistributedDataParallel
         torch.nn.parallel.DistributedDataParallel = DistributedDataParallel
+    if async_save:
+        from . import checkpoint
+        real_save = torch.save
+        _installed["torch.save"] = real_save
+
+        def save(obj, f, *args, **kwargs):
+            if isinstance(f, (str, os.PathLike)) and not args and not kwargs and checkpoint.has_device_tensor(obj):
+                return checkpoint.save_async(obj, f)
+            return real_save(obj, f, *args, **kwargs)
+
+        torch.save = save
     if default_device and torch.cuda.is_available():
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
@@ -87,11 +102,14 @@ def install(swap_optimizer=True, swap_ddp=True, default_device=True):
 
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
-    flags = {"swap_optimizer": True, "swap_ddp": True, "default_device": True}
+    flags = {"swap_optimizer": True, "swap_ddp": True, "default_device": True, "async_save": False}
     while argv and argv[0].startswith("--ct-"):
         flag = argv.pop(0)
         key = {"--ct-keep-torch-adamw": "swap_optimizer", "--ct-keep-torch-ddp": "swap_ddp",
                "--ct-keep-default-device": "default_device"}.get(flag)
+        if flag == "--ct-async-save":
+            flags["async_save"] = True
+            continue
         if key is None:
             raise SystemExit("unknown launcher flag %s" % flag)
         flags[key] = False

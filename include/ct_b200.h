@@ -305,6 +305,20 @@ int ct_embedding_fwd(const int64_t* ids, const float* weight, float* out, int64_
                      int64_t V, int accumulate, void* stream);
 int ct_embedding_bwd(const int64_t* ids, const float* dout, float* dweight, int64_t T, int64_t H,
                      int64_t V, int64_t padding_idx, void* stream);
+/* Gather + LayerNorm in one pass (SURVEY §8 f N3): y = LN(table0[ids0] (+ table1[ids1]) (+ table2[ids2])) —
+ * modeling_bloom.py:190-191 (word_embeddings -> word_embeddings_layernorm), modeling_bert.py:297-301 (word +
+ * segment + position tables -> embedding_post LayerNorm). ids* [rows] int64 (a broadcast position / segment row is
+ * expanded by the caller), tables f32 [vocab*, cols]; tables 1 and 2 optional (NULL, in order). `emb` (nullable,
+ * f32 [rows, cols]) receives the sum — the LayerNorm input that ct_layernorm_bwd needs; y / y2 / mean / rstd as
+ * ct_layernorm_fwd. The backward is ct_layernorm_bwd followed by ct_embedding_bwd per table. Needs
+ * cols % 128 == 0, cols <= 1024 and 16-byte aligned pointers (CT_ERR_UNSUPPORTED otherwise: call the two
+ * kernels). An id outside its table gives a NaN row, like ct_embedding_fwd. */
+int ct_embedding_layernorm_fwd(const int64_t* ids0, const float* table0, int64_t vocab0,
+                               const int64_t* ids1, const float* table1, int64_t vocab1,
+                               const int64_t* ids2, const float* table2, int64_t vocab2,
+                               const float* gamma, const float* beta, float* emb, void* y, int y_dtype,
+                               void* y2, int y2_dtype, float* mean, float* rstd, int64_t rows,
+                               int64_t cols, float eps, void* stream);
 
 /* ---- cross entropy: modeling_bloom.py:224-230 (shift + torch CrossEntropyLoss, mean) ---------- *
  * logits [rows, V] (bf16 or f32). shift != 0: row r = (b, s) is scored against labels[r + 1] and the

@@ -219,6 +219,14 @@ def embedding_fwd(ids, weight, out=None, accumulate=False):
     return out
 
 
+def embedding_layernorm_fwd(ids_list, weights, gamma, beta, eps, out_dtype=torch.float32, out2_dtype=None, save=True):
+    emb = None
+    for i, w in zip(ids_list, weights):
+        emb = w[i].float() if emb is None else emb + w[i]
+    y, y2, mean, rstd = layernorm_fwd(emb, gamma, beta, eps, out_dtype, out2_dtype, save_stats=save)
+    return (emb if save else None), y, y2, mean, rstd
+
+
 def embedding_bwd(ids, dout, dweight, padding_idx=-1):
     flat = ids.reshape(-1)
     d = dout.reshape(-1, dweight.shape[1]).float()
@@ -359,7 +367,7 @@ def patched(compute_dtype=torch.float32):
     """Route cleantransformer_b200.ops through the stand-ins above and run the host layer in `compute_dtype`."""
     from cleantransformer_b200 import functional, ops
     names = ["layernorm_fwd", "layernorm_bwd", "cast", "colsum", "act_fwd", "act_bwd", "gemm", "attn_mask_prep",
-             "attn_fwd", "attn_bwd", "embedding_fwd", "embedding_bwd", "cross_entropy_fwd", "cross_entropy_fwd_stats",
+             "attn_fwd", "attn_bwd", "embedding_fwd", "embedding_bwd", "embedding_layernorm_fwd", "cross_entropy_fwd", "cross_entropy_fwd_stats",
              "scale_by_scalar", "lm_head_stats_ok", "lm_head_logits_with_stats", "adamw_step", "adamw_multi", "sgd_step", "kv_cache_append",
              "kv_append_dev", "greedy_step", "dropout"]
     saved = {n: getattr(ops, n) for n in names}

@@ -984,3 +984,48 @@ def test_trainer_checkpoints_are_reference_shaped_and_a_resumed_run_is_bit_ident
         assert sorted(os.listdir(tmp_path / "d" / "checkpoint-6")) == ["pytorch_model.bin", "trainer_state.json"]
         with pytest.raises(ValueError):
             _toy_trainer(tmp_path / "e", 3)[0].train(resume_from_checkpoint=True)
+
+
+def test_fused_embedding_layernorm_node_host_logic(golden, monkeypatch):
+    """SURVEY §8 N3 (functional.EmbeddingLNFn, CT_FUSED_EMBED_LN): the gather(s) + LayerNorm as one node — Bloom's
+    word_embeddings -> word_embeddings_layernorm (modeling_bloom.py:190-191, tied table: the scatter is the SECOND
+    write of its gradient) and BERT's three tables -> embedding_post (modeling_bert.py:297-301, padding_idx 0 gets no
+    gradient) — against the reference's golden gradients / the oracle's autograd, with the fused call counted."""
+    from cleantransformer_b200 import functional as F, ops
+    from cleantransformer_b200.models import modeling_bert as mbert
+    from oracle import ct_oracle as O
+    g = golden("bloom_tiny")
+    with mock_ops.patched():
+        calls = []
+        inner = ops.embedding_layernorm_fwd
+        monkeypatch.setattr(ops, "embedding_layernorm_fwd", lambda *a, **k: (calls.append(1), inner(*a, **k))[1])
+        monkeypatch.setattr(ops, "embedding_layernorm_ok", lambda weights, gamma: True)
+        monkeypatch.setattr(F, "FUSED_EMBED_LN", True)
+        m = _bloom(g)
+        (loss, logits, hidden), kv = m(input_ids=g["ids"], attention_mask=g["mask"], labels=g["labels"])
+        loss.backward()
+        assert len(calls) == 1
+        _check_against_golden(m, g, loss, logits, hidden)
+        with torch.no_grad():                                   # nothing saved, nothing required: same values
+            (lg2, _), _ = m(input_ids=g["ids"], attention_mask=g["mask"])
+        assert torch.equal(lg2, logits.detach()) and len(calls) == 2
+
+        gb = golden("bert_tiny")
+        cfg = dict(gb["cfg"])
+        ids, mask, seg, pos = gb["ids"], gb["mask"], gb["seg"], gb["pos"]
+        torch.manual_seed(5)
+        labels = torch.randint(0, cfg["num_labels"], (ids.shape[0],))
+        sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in gb["sd"].items()}
+        lg_ref, _, _ = O.bert_classifier(ids, mask, seg, pos, sd, cfg["num_hidden_layers"], cfg["num_attention_heads"],
+                                         cfg["layer_norm_eps"])
+        torch.nn.functional.cross_entropy(lg_ref, labels).backward()
+        model = mbert.BertForSequenceClassification(mbert.BertConfig(**cfg)).eval()
+        model.load_state_dict(gb["sd"], strict=True)
+        out = model(ids, mask, seg, pos)
+        torch.nn.functional.cross_entropy(out.float(), labels).backward()
+        assert len(calls) == 3 and rel_err(out, lg_ref) < 2e-4
+        for name in ("bert.word_embeddings.weight", "bert.position_embeddings.weight", "bert.segment_embeddings.weight",
+                     "bert.embedding_post.0.weight", "bert.embedding_post.0.bias"):
+            p, ref = dict(model.named_parameters())[name], sd[name].grad
+            assert float((p.grad - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-9, name
+        assert float(model.bert.word_embeddings.weight.grad[0].abs().max()) == 0.0 or not bool((ids == 0).any())

@@ -97,3 +97,29 @@ def test_trainer_surface_cpu_side():
     assert float(Trainer._loss_of({"loss": torch.tensor(2.0)})) == 2.0
     for name in ("train", "evaluate", "save_model", "compute_loss", "training_step"):
         assert callable(getattr(t, name))
+
+
+def test_launcher_async_save_flag_routes_torch_save_and_flushes_at_exit(tmp_path):
+    """`--ct-async-save`: the reference scripts' `torch.save(model.state_dict(), path)`
+    (examples/ft_bloom_DDP.py:155-156) goes through checkpoint.save_async when the object holds device tensors and is
+    untouched otherwise; whatever is still queued is on disk when the interpreter exits."""
+    script = tmp_path / "saver.py"
+    script.write_text(textwrap.dedent('''
+        import sys, torch
+        from cleantransformer_b200 import checkpoint
+        sd = {"w": torch.arange(6.).view(2, 3), "nested": {"step": torch.tensor(2.0)}}
+        torch.save(sd, sys.argv[1] + "/plain.pt")                       # CPU tensors: the real torch.save, on disk now
+        assert torch.load(sys.argv[1] + "/plain.pt")["w"].sum() == 15
+        assert checkpoint._default is None
+        checkpoint.has_device_tensor = lambda obj: True                 # stand-in for "holds CUDA tensors"
+        torch.save(sd, sys.argv[1] + "/async.pt")
+        sd["w"].zero_()
+        assert checkpoint._default is not None
+        with open(sys.argv[1] + "/buffer.bin", "wb") as f:              # file objects keep the blocking path
+            torch.save(sd, f)
+        print("SAVER-OK")
+    '''))
+    out = _run(["-m", "cleantransformer_b200.run", "--ct-keep-default-device", "--ct-async-save", str(script), str(tmp_path)])
+    assert "SAVER-OK" in out
+    import torch
+    assert torch.load(str(tmp_path / "async.pt"))["w"].sum() == 15 and os.path.exists(tmp_path / "buffer.bin")
