@@ -132,7 +132,7 @@ class AsyncCheckpointer:
             free = self._pool.get(key)
             if free:
                 return free.pop()
-        return torch.empty(numel, dtype=dtype, pin_memory=pinned)
+        return torch.empty(numel, dtype=dtype, device="cpu", pin_memory=pinned)   # explicit: run.py makes cuda the default device
 
     def _release(self, bufs):
         with self._pool_lock:
@@ -159,7 +159,7 @@ class AsyncCheckpointer:
         host_of, held, event = {}, [], None
         if cuda_groups:
             dev = cuda_groups[0].device
-            nbytes = sum((g.hi - g.lo) * torch.empty(0, dtype=g.dtype).element_size() for g in cuda_groups)
+            nbytes = sum((g.hi - g.lo) * g.members[0].element_size() for g in cuda_groups)
             stage = self._stage_for(nbytes, dev)
             cur = torch.cuda.current_stream(dev)
             if self._copy_stream is None:
@@ -189,7 +189,7 @@ class AsyncCheckpointer:
             del srcs
         for g in groups.values():
             if id(g) not in host_of:    # host tensors (step counters, CPU models of the tests) and empty ones: cloned now
-                host_of[id(g)] = g.source().clone() if g.hi > g.lo else torch.empty(0, dtype=g.dtype)
+                host_of[id(g)] = g.source().clone() if g.hi > g.lo else torch.empty(0, dtype=g.dtype, device="cpu")
         self._jobs.put((event, skeleton, json_files, host_of, held, on_done))
 
     def guard(self):

@@ -95,6 +95,20 @@ class Trainer:
                                            drop_last=self._arg("dataloader_drop_last"),
                                            generator=g if sampler is None and shuffle else None)
 
+    @staticmethod
+    def _host_batches(loader):
+        """Batches are drawn with the CPU as the default device: the launcher (run.py) makes the GPU the default
+        device, under which the sampler's `randperm` would meet its CPU generator on the wrong device."""
+        with torch.device("cpu"):
+            it = iter(loader)
+        while True:
+            with torch.device("cpu"):
+                try:
+                    batch = next(it)
+                except StopIteration:
+                    return
+            yield batch
+
     def get_train_dataloader(self):
         if self.train_dataset is None:
             raise ValueError("Trainer: training requires a train_dataset.")
@@ -278,7 +292,7 @@ class Trainer:
                 loader.sampler.set_epoch(epoch)
             if self._train_generator is not None:
                 self._train_generator.manual_seed(self._arg("seed") + epoch)
-            it = iter(loader)
+            it = self._host_batches(loader)
             in_epoch = skip
             for _ in range(skip):   # trainer.py:448-451: batches of the interrupted epoch that were already trained on
                 next(it)
