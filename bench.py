@@ -54,7 +54,7 @@ def parse():
                     "CUDA graph (cleantransformer_b200.graphs)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel")
     ap.add_argument("--no-kernel-table", action="store_true", help="skip the per-kernel roofline pass")
-    ap.add_argument("--comm", default=None, help="p2p (default), nccl (baseline collective) or ce (copy-engine transport, experimental)")
+    ap.add_argument("--comm", default=None, help="p2p (default: peer-memory / NVLS kernels) or nccl (baseline collective)")
     return ap.parse_args()
 
 
