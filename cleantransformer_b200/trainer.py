@@ -11,7 +11,10 @@ accelerate plumbing are out of scope.
 Accepted `args`: any object with the TrainingArguments attribute names used below (missing ones take the
 HF defaults): per_device_train_batch_size, per_device_eval_batch_size, learning_rate, weight_decay,
 adam_beta1, adam_beta2, adam_epsilon, num_train_epochs, max_steps, logging_steps, output_dir, seed,
-save_strategy ("steps" | "epoch" | "no"), save_steps, save_total_limit, save_only_model.
+save_strategy ("steps" | "epoch" | "no"), save_steps, save_total_limit, save_only_model, gradient_accumulation_steps,
+max_grad_norm (applied only when the attribute is present and > 0: an HF `TrainingArguments` carries 1.0).
+`compute_metrics` / `preprocess_logits_for_metrics` are honoured by evaluate() (trainer.py:621-739); `callbacks` are
+accepted for signature compatibility and NOT dispatched (a warning says so).
 """
 import json
 import math
@@ -21,6 +24,7 @@ import re
 import shutil
 import time
 import types
+import warnings
 
 import torch
 
@@ -35,7 +39,8 @@ TRAINER_STATE_NAME, RNG_STATE_NAME = "trainer_state.json", "rng_state.pth"
 _DEFAULTS = dict(per_device_train_batch_size=8, per_device_eval_batch_size=8, learning_rate=5e-5,
                  weight_decay=0.0, adam_beta1=0.9, adam_beta2=0.999, adam_epsilon=1e-8, num_train_epochs=3.0,
                  max_steps=-1, logging_steps=500, output_dir="./", seed=42, dataloader_drop_last=False,
-                 save_strategy="steps", save_steps=500, save_total_limit=None, save_only_model=False)
+                 save_strategy="steps", save_steps=500, save_total_limit=None, save_only_model=False,
+                 gradient_accumulation_steps=1, max_grad_norm=None)
 
 
 def get_last_checkpoint(folder):
@@ -56,6 +61,13 @@ class TrainOutput(types.SimpleNamespace):
     pass
 
 
+class EvalPrediction(types.SimpleNamespace):
+    """transformers.EvalPrediction: `.predictions`, `.label_ids` (numpy arrays)."""
+
+    def __iter__(self):
+        return iter((self.predictions, self.label_ids))
+
+
 class Trainer:
     def __init__(self, model=None, args=None, data_collator=None, train_dataset=None, eval_dataset=None,
                  tokenizer=None, model_init=None, compute_metrics=None, callbacks=None, optimizers=(None, None),
@@ -72,11 +84,15 @@ class Trainer:
         self.compute_metrics = compute_metrics
         self.preprocess_logits_for_metrics = preprocess_logits_for_metrics
         self.callbacks = list(callbacks or [])
+        if self.callbacks:
+            warnings.warn("cleantransformer_b200.Trainer accepts `callbacks` for signature compatibility but does not "
+                          "dispatch them")
         self.optimizer, self.lr_scheduler = optimizers
         self.state = types.SimpleNamespace(global_step=0, epoch=0.0, log_history=[])
         self.device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
         self._checkpointer = None
         self._train_generator = None
+        self._loss_scale = 1.0
 
     # ---- helpers -------------------------------------------------------------------------------
     def _arg(self, name):
@@ -149,10 +165,12 @@ class Trainer:
         return (loss, outputs) if return_outputs else loss
 
     def training_step(self, model, inputs):
+        """trainer.py:543-556; the loss is scaled by 1 / gradient_accumulation_steps for the backward (the accumulated
+        gradient is the mean over the micro-batches, as accelerate's `backward` makes it); the returned loss is not."""
         model.train()
         inputs = self._prepare_inputs(inputs)
         loss = self.compute_loss(model, inputs)
-        loss.backward()
+        (loss * self._loss_scale if self._loss_scale != 1.0 else loss).backward()
         return loss.detach()
 
     # ---- checkpoints ---------------------------------------------------------------------------
@@ -271,8 +289,10 @@ class Trainer:
         opt = self.create_optimizer()
         max_steps = self._arg("max_steps")
         epochs = self._arg("num_train_epochs")
+        gas = max(1, int(self._arg("gradient_accumulation_steps")))
+        steps_per_epoch = max(1, -(-len(loader) // gas))    # optimizer steps; a short tail of micro-batches still steps
         if max_steps is None or max_steps <= 0:
-            max_steps = int(math.ceil(epochs * len(loader)))
+            max_steps = int(math.ceil(epochs * steps_per_epoch))
         log_every = max(1, int(self._arg("logging_steps")))
         strategy = str(self._arg("save_strategy")).lower().replace("intervalstrategy.", "")
         save_every = max(1, int(self._arg("save_steps")))
@@ -283,8 +303,9 @@ class Trainer:
                 if resume_from_checkpoint is None:
                     raise ValueError("No valid checkpoint found in output directory (%s)" % self._arg("output_dir"))
             self._load_checkpoint(resume_from_checkpoint)
-            epoch, skip = divmod(self.state.global_step, max(1, len(loader)))
-        t0, running, last, n_running = time.time(), None, float("nan"), 0
+            epoch, skip = divmod(self.state.global_step, steps_per_epoch)
+        t0, running, last, n_running, step_loss = time.time(), None, float("nan"), 0, None
+        self._loss_scale = 1.0 / gas
         ck = None
         while self.state.global_step < max_steps:
             # the order of an epoch depends on (seed, epoch) only, so a resumed run replays nothing to find its place
@@ -294,15 +315,30 @@ class Trainer:
                 self._train_generator.manual_seed(self._arg("seed") + epoch)
             it = self._host_batches(loader)
             in_epoch = skip
-            for _ in range(skip):   # trainer.py:448-451: batches of the interrupted epoch that were already trained on
+            for _ in range(skip * gas):   # trainer.py:448-451: batches of the interrupted epoch already trained on
                 next(it)
             skip = 0
             if resume_from_checkpoint:
                 self._load_rng_state(resume_from_checkpoint)   # trainer.py:453
                 resume_from_checkpoint = None
+            micro = 0
             for inputs in it:
-                opt.zero_grad()
-                loss = self.training_step(self.model, inputs)
+                if micro == 0:
+                    opt.zero_grad()
+                micro += 1
+                last_micro = micro == gas or (in_epoch * gas + micro) == len(loader)   # a short tail still steps
+                if not last_micro and hasattr(self.model, "no_sync"):
+                    with self.model.no_sync():      # DDP: reduce once per optimizer step
+                        loss = self.training_step(self.model, inputs)
+                else:
+                    loss = self.training_step(self.model, inputs)
+                step_loss = loss / gas if step_loss is None else step_loss + loss / gas
+                if not last_micro:
+                    continue
+                micro = 0
+                clip = getattr(self.args, "max_grad_norm", None)
+                if clip is not None and clip > 0:    # trainer.py:486-493
+                    torch.nn.utils.clip_grad_norm_(self.model.parameters(), clip)
                 if ck is not None:
                     ck.guard()   # a snapshot still reading the live parameters / moments finishes before they change
                 opt.step()
@@ -310,8 +346,9 @@ class Trainer:
                     self.lr_scheduler.step()
                 self.state.global_step += 1
                 in_epoch += 1
-                self.state.epoch = epoch + in_epoch / max(1, len(loader))
-                running = loss if running is None else running + loss
+                self.state.epoch = epoch + in_epoch / max(1, steps_per_epoch)
+                running = step_loss if running is None else running + step_loss
+                step_loss = None
                 n_running += 1
                 if self.state.global_step % log_every == 0:
                     last = float(running) / n_running
@@ -323,7 +360,7 @@ class Trainer:
                 if self.state.global_step >= max_steps:
                     break
             epoch += 1
-            if strategy == "epoch" and in_epoch == len(loader):
+            if strategy == "epoch" and in_epoch == steps_per_epoch:
                 self._save_checkpoint(self.model)
                 ck = self._checkpointer
         if running is not None:
@@ -334,14 +371,50 @@ class Trainer:
 
     @torch.no_grad()
     def evaluate(self, eval_dataset=None, ignore_keys=None, metric_key_prefix="eval"):
+        """trainer.py:591-739: mean loss over the batches; with `compute_metrics`, the logits (after
+        `preprocess_logits_for_metrics(logits, labels)`) and the labels of every batch are gathered on the host and
+        handed over as `EvalPrediction(predictions, label_ids)`; metric names get the prefix."""
+        if isinstance(eval_dataset, dict):
+            metrics = {}
+            for name, ds in eval_dataset.items():
+                metrics.update(self.evaluate(ds, ignore_keys, "%s_%s" % (metric_key_prefix, name)))
+            return metrics
         loader = self.get_eval_dataloader(eval_dataset)
         self.model.eval()
-        tot, n = 0.0, 0
-        for inputs in loader:
+        tot, n, preds, labels = 0.0, 0, [], []
+        for inputs in self._host_batches(loader):
             inputs = self._prepare_inputs(inputs)
-            tot += float(self.compute_loss(self.model, inputs))
+            loss, outputs = self.compute_loss(self.model, inputs, return_outputs=True)
+            tot += float(loss)
             n += 1
-        return {metric_key_prefix + "_loss": tot / max(n, 1), metric_key_prefix + "_batches": n}
+            if self.compute_metrics is not None:
+                logits = self._logits_of(outputs)
+                lab = inputs.get("labels")
+                if self.preprocess_logits_for_metrics is not None:
+                    logits = self.preprocess_logits_for_metrics(logits, lab)
+                preds.append(logits.detach().float().cpu())
+                if lab is not None:
+                    labels.append(lab.detach().cpu())
+        metrics = {}
+        if self.compute_metrics is not None and preds:
+            metrics = dict(self.compute_metrics(EvalPrediction(
+                predictions=torch.cat(preds).numpy(), label_ids=torch.cat(labels).numpy() if labels else None)))
+        metrics = {(k if k.startswith(metric_key_prefix + "_") else "%s_%s" % (metric_key_prefix, k)):
+                   (v.item() if hasattr(v, "item") else v) for k, v in metrics.items()}
+        metrics[metric_key_prefix + "_loss"] = tot / max(n, 1)
+        metrics[metric_key_prefix + "_batches"] = n
+        return metrics
+
+    @staticmethod
+    def _logits_of(outputs):
+        """What `prediction_step` keeps (trainer.py:741-787): everything but the loss; the reference models return
+        ((loss, logits, hidden), k_v_pasts) — the logits are the second element of the first tuple."""
+        if isinstance(outputs, dict):
+            return outputs["logits"]
+        first = outputs[0]
+        if isinstance(first, (tuple, list)):
+            return first[1]
+        return outputs[1]
 
     def save_model(self, output_dir=None, _internal_call=False):
         """trainer.py:1347-1404 (plain-module branch: `torch.save(state_dict, pytorch_model.bin)`). On disk when it

@@ -1029,3 +1029,58 @@ def test_fused_embedding_layernorm_node_host_logic(golden, monkeypatch):
             p, ref = dict(model.named_parameters())[name], sd[name].grad
             assert float((p.grad - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-9, name
         assert float(model.bert.word_embeddings.weight.grad[0].abs().max()) == 0.0 or not bool((ids == 0).any())
+
+
+def test_trainer_gradient_accumulation_clipping_and_metrics(golden, tmp_path):
+    """Trainer arguments that change the arithmetic are honoured, not ignored: `gradient_accumulation_steps` (two
+    half-batches per optimizer step = one full batch: same trajectory up to rounding; a resume lands on the right
+    micro-batch), `max_grad_norm` (trainer.py:486-493: the clipped run differs and its update is bounded),
+    `compute_metrics` + `preprocess_logits_for_metrics` in evaluate() (trainer.py:621-739)."""
+    import warnings
+    with mock_ops.patched():
+        full, m_full = _toy_trainer(tmp_path / "full", 6, save_strategy="no")
+        full.train()
+        acc, m_acc = _toy_trainer(tmp_path / "acc", 6, per_device_train_batch_size=2, gradient_accumulation_steps=2,
+                                  save_steps=4)
+        out = acc.train()
+        assert out.global_step == 6 and abs(acc.state.epoch - 2.0) < 1e-9        # 12 samples / (2 x 2) = 3 steps per epoch
+        for (n, a), (_, b) in zip(m_full.named_parameters(), m_acc.named_parameters()):
+            if n.endswith("query_key_value.bias"):
+                continue    # its key third has an analytically zero gradient: AdamW turns the rounding noise into +-lr
+            assert rel_err(b, a) < 1e-4, n   # AdamW normalises the update: fp32 rounding of the half-batch sums shows
+        for ha, hb in zip(full.state.log_history, acc.state.log_history):
+            assert abs(ha["loss"] - hb["loss"]) < 1e-5 * abs(ha["loss"])
+        res, m_res = _toy_trainer(tmp_path / "acc", 6, per_device_train_batch_size=2, gradient_accumulation_steps=2,
+                                  save_strategy="no")
+        res.train(resume_from_checkpoint=True)                                    # from step 4: epoch 1, one step in
+        for (n, a), (_, b) in zip(m_acc.named_parameters(), m_res.named_parameters()):
+            assert torch.equal(a, b), n
+
+        clipped, m_clip = _toy_trainer(tmp_path / "clip", 1, save_strategy="no", max_grad_norm=1e-3, learning_rate=1.0,
+                                       weight_decay=0.0)
+        free, m_free = _toy_trainer(tmp_path / "free", 1, save_strategy="no", learning_rate=1.0, weight_decay=0.0)
+        before = [p.detach().clone() for p in m_clip.parameters()]
+        clipped.train(); free.train()
+        gnorm = torch.sqrt(sum((p.grad.float() ** 2).sum() for p in m_clip.parameters()))
+        assert float(gnorm) <= 1e-3 * 1.001 and any(not torch.equal(a, b) for a, b in zip(m_clip.parameters(), m_free.parameters()))
+        assert all(torch.isfinite(p).all() for p in m_clip.parameters()) and len(before) > 0
+
+        seen = {}
+
+        def metrics(pred):
+            predictions, label_ids = pred
+            seen["shapes"] = (predictions.shape, label_ids.shape)
+            return {"top1": float((predictions[:, :-1] == label_ids[:, 1:]).mean()), "eval_already": 1.0}
+
+        ev, _ = _toy_trainer(tmp_path / "ev", 1, save_strategy="no")
+        ev.eval_dataset, ev.compute_metrics = ev.train_dataset, metrics
+        ev.preprocess_logits_for_metrics = lambda logits, labels: logits.argmax(-1)
+        m = ev.evaluate()
+        assert seen["shapes"] == ((12, 10), (12, 10)) and set(m) == {"eval_top1", "eval_already", "eval_loss", "eval_batches"}
+        assert 0.0 <= m["eval_top1"] <= 1.0 and m["eval_batches"] == 2           # eval batch size 8 (default)
+        m2 = ev.evaluate({"a": ev.train_dataset[:4], "b": ev.train_dataset[4:]})
+        assert {"eval_a_loss", "eval_b_top1"} <= set(m2)
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            _toy_trainer(tmp_path / "cb", 1)[0].__class__(model=m_full, callbacks=[object()])
+        assert any("callbacks" in str(x.message) for x in w)
