@@ -1084,3 +1084,69 @@ def test_trainer_gradient_accumulation_clipping_and_metrics(golden, tmp_path):
             warnings.simplefilter("always")
             _toy_trainer(tmp_path / "cb", 1)[0].__class__(model=m_full, callbacks=[object()])
         assert any("callbacks" in str(x.message) for x in w)
+
+
+def _trainer_ddp_worker(rank, world, port, out, root):
+    import os
+    import types
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cleantransformer_b200.ddp import DistributedDataParallel
+    from cleantransformer_b200.models import modeling_bloom as mb
+    from cleantransformer_b200.trainer import Trainer
+    cfg = dict(vocab_size=64, hidden_size=32, n_layer=2, num_attention_heads=4)
+    g = torch.Generator().manual_seed(3)
+    data = [dict(input_ids=torch.randint(3, 64, (10,), generator=g), attention_mask=torch.ones(10, dtype=torch.long))
+            for _ in range(16)]
+    for d in data:
+        d["labels"] = d["input_ids"].clone()
+
+    def collate(items):
+        return {k: torch.stack([it[k] for it in items]) for k in items[0]}
+
+    def make(max_steps):
+        torch.manual_seed(4 + rank)          # different initial weights per rank: the wrapper must broadcast rank 0's
+        m = mb.BloomForCausalLM(mb.BloomConfig(**cfg))
+        m._tie_weight()
+        ddp = DistributedDataParallel(m, bucket_cap_mb=0.005)
+        a = types.SimpleNamespace(per_device_train_batch_size=2, gradient_accumulation_steps=2, learning_rate=5e-3,
+                                  max_steps=max_steps, logging_steps=1, output_dir=root, save_steps=3, weight_decay=0.0)
+        return Trainer(model=ddp, args=a, data_collator=collate, train_dataset=data), m
+
+    with mock_ops.patched():
+        tr, m = make(5)
+        tr.train()                           # 16 samples / (2 ranks x 2 x 2) = 2 optimizer steps per epoch
+        dist.barrier()
+        first = [p.detach().clone() for p in m.parameters()]
+        files = sorted(os.listdir(root))
+        tr2, m2 = make(5)
+        tr2.train(resume_from_checkpoint=True)   # checkpoint-3 (written by rank 0 only), middle of epoch 1
+        second = [p.detach().clone() for p in m2.parameters()]
+    out[rank] = (first, second, files, tr.state.global_step, [h["loss"] for h in tr.state.log_history])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_trainer_drives_the_ddp_wrapper_world2_gloo(tmp_path):
+    """Trainer + DistributedDataParallel + TorchAdamW, two ranks (ft_bloom_DDP.py:99-156 through the Trainer surface):
+    DistributedSampler shards the data, micro-batches accumulate under no_sync(), only rank 0 writes checkpoints (with
+    un-prefixed keys: `model.module.state_dict()`), both ranks resume from them and end with the bits of the
+    uninterrupted run, and the replicas stay identical throughout."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_trainer_ddp_worker, args=(2, port, out, str(tmp_path)), nprocs=2, join=True)
+    (a0, b0, files0, steps0, loss0), (a1, b1, files1, steps1, loss1) = out[0], out[1]
+    assert steps0 == steps1 == 5 and files0 == files1 == ["checkpoint-3"]
+    assert loss0 != loss1                                   # each rank saw its own shard
+    for x, y in zip(a0, a1):
+        assert torch.equal(x, y)                            # replicas identical after training
+    for x, y in zip(a0, b0):
+        assert torch.equal(x, y)                            # resumed == uninterrupted, rank 0
+    for x, y in zip(a1, b1):
+        assert torch.equal(x, y)                            # ... and rank 1
+    sd = torch.load(str(tmp_path / "checkpoint-3" / "pytorch_model.bin"))
+    assert "lm_head.weight" in sd and not any(k.startswith("module.") for k in sd)
