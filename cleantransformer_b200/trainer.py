@@ -70,8 +70,8 @@ class EvalPrediction(types.SimpleNamespace):
 
 class Trainer:
     def __init__(self, model=None, args=None, data_collator=None, train_dataset=None, eval_dataset=None,
-                 tokenizer=None, model_init=None, compute_metrics=None, callbacks=None, optimizers=(None, None),
-                 preprocess_logits_for_metrics=None):
+                 tokenizer=None, model_init=None, compute_metrics=None, optimizers=(None, None), callbacks=None,
+                 preprocess_logits_for_metrics=None):   # trainer.py:140-153, same positional order
         if model is None:
             if model_init is None:
                 raise RuntimeError("`Trainer` requires either a `model` or `model_init` argument")

@@ -97,6 +97,12 @@ def test_trainer_surface_cpu_side():
     assert float(Trainer._loss_of({"loss": torch.tensor(2.0)})) == 2.0
     for name in ("train", "evaluate", "save_model", "compute_loss", "training_step"):
         assert callable(getattr(t, name))
+    import inspect
+    assert list(inspect.signature(Trainer.__init__).parameters)[1:] == [       # trainer/trainer.py:140-153
+        "model", "args", "data_collator", "train_dataset", "eval_dataset", "tokenizer", "model_init", "compute_metrics",
+        "optimizers", "callbacks", "preprocess_logits_for_metrics"]
+    assert list(inspect.signature(Trainer.train).parameters)[1:3] == ["resume_from_checkpoint", "kwargs"] or \
+        "resume_from_checkpoint" in inspect.signature(Trainer.train).parameters
 
 
 def test_launcher_async_save_flag_routes_torch_save_and_flushes_at_exit(tmp_path):
