@@ -107,7 +107,10 @@ class AsyncCheckpointer:
             g.add(t)
             return _Placeholder(g, t)
         if isinstance(obj, dict):
-            return type(obj)((k, self._collect(v, groups)) for k, v in obj.items())
+            new = copy.copy(obj)     # keeps the class and its attributes (a state_dict's `_metadata`)
+            for k, v in obj.items():
+                new[k] = self._collect(v, groups)
+            return new
         if isinstance(obj, (list, tuple)):
             seq = [self._collect(v, groups) for v in obj]
             return seq if isinstance(obj, list) else tuple(seq)
@@ -118,10 +121,13 @@ class AsyncCheckpointer:
         if isinstance(obj, _Placeholder):
             flat = host_of[id(obj.group)]
             return flat.as_strided(obj.shape, obj.stride, obj.offset - obj.group.lo)
-        if isinstance(obj, dict):
-            return type(obj)((k, AsyncCheckpointer._materialise(v, host_of)) for k, v in obj.items())
+        if isinstance(obj, dict):    # the skeleton is this snapshot's own copy: filled in place
+            for k in obj:
+                obj[k] = AsyncCheckpointer._materialise(obj[k], host_of)
+            return obj
         if isinstance(obj, list):
-            return [AsyncCheckpointer._materialise(v, host_of) for v in obj]
+            obj[:] = [AsyncCheckpointer._materialise(v, host_of) for v in obj]
+            return obj
         if isinstance(obj, tuple):
             return tuple(AsyncCheckpointer._materialise(v, host_of) for v in obj)
         return obj

@@ -435,6 +435,14 @@ def test_async_checkpointer_snapshots_at_call_time_and_groups_by_storage(tmp_pat
         assert r["model"]["col"].stride() == (1, 4) and torch.equal(r["model"]["col"], col)
         assert r["model"]["empty"].shape == (0, 3) and r["tuple"][:2] == (1, "x")
         assert open(tmp_path / "s.json").read().strip().startswith("{")
+        # a module's state_dict keeps its class and `_metadata` (load_state_dict reads the versions from it)
+        lin = torch.nn.Sequential(torch.nn.Linear(3, 2), torch.nn.BatchNorm1d(2))
+        live = lin.state_dict()
+        ck.save({str(tmp_path / "sd.pt"): live})
+        ck.wait()
+        back = torch.load(str(tmp_path / "sd.pt"), weights_only=False)
+        assert type(back) is type(live) and back._metadata == live._metadata and list(back) == list(live)
+        torch.nn.Sequential(torch.nn.Linear(3, 2), torch.nn.BatchNorm1d(2)).load_state_dict(back, strict=True)
         # a failure in the writer thread is not lost
         os.makedirs(tmp_path / "isdir.pt")
         ck.save({str(tmp_path / "isdir.pt"): {"a": torch.ones(1)}})
