@@ -129,3 +129,75 @@ def test_launcher_async_save_flag_routes_torch_save_and_flushes_at_exit(tmp_path
     assert "SAVER-OK" in out
     import torch
     assert torch.load(str(tmp_path / "async.pt"))["w"].sum() == 15 and os.path.exists(tmp_path / "buffer.bin")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "CleanTransformer")), reason="reference checkout not present")
+def test_checkpoints_load_into_the_reference_classes(tmp_path):
+    """what Trainer / AsyncCheckpointer write (plain state_dicts, examples/ft_bloom_DDP.py:155-156) is
+    read back by the REFERENCE's own classes: strict `load_state_dict` into CleanTransformer's BloomForCausalLM and
+    the same logits from its own forward; `optimizer.pt` continues a `torch.optim.AdamW` (what ft_bloom.py:70 builds)
+    with the same next step as this package's AdamW takes."""
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mock_ops
+    from cleantransformer_b200.models import modeling_bloom as mb
+    from cleantransformer_b200.trainer import Trainer
+    cfg = dict(vocab_size=64, hidden_size=32, n_layer=2, num_attention_heads=4, layer_norm_epsilon=1e-5,
+               hidden_dropout=0.0, attention_dropout=0.0)
+    g = torch.Generator().manual_seed(3)
+    data = [dict(input_ids=torch.randint(3, 64, (10,), generator=g), attention_mask=torch.ones(10, dtype=torch.long))
+            for _ in range(8)]
+    for d in data:
+        d["labels"] = d["input_ids"].clone()
+    collate = lambda items: {k: torch.stack([it[k] for it in items]) for k in items[0]}   # noqa: E731
+    with mock_ops.patched():
+        torch.manual_seed(4)
+        m = mb.BloomForCausalLM(mb.BloomConfig(**cfg))
+        m._tie_weight()
+        args = types.SimpleNamespace(per_device_train_batch_size=4, learning_rate=5e-3, max_steps=3, save_steps=3,
+                                     output_dir=str(tmp_path), weight_decay=0.01)
+        tr = Trainer(model=m, args=args, data_collator=collate, train_dataset=data)
+        tr.train()
+        ids, mask = data[0]["input_ids"][None], data[0]["attention_mask"][None]
+        m.eval()
+        with torch.no_grad():
+            (logits, _), _ = m(input_ids=ids, attention_mask=mask)
+        batch = collate(data[:4])
+        m.train()
+        tr.optimizer.zero_grad()
+        (loss, _, _), _ = m(**batch)
+        loss.backward()
+        grads = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+        tr.optimizer.step()
+        after = {n: p.detach().clone() for n, p in m.named_parameters()}
+    torch.save({"cfg": cfg, "ids": ids, "mask": mask, "logits": logits, "grads": grads, "after": after},
+               tmp_path / "expect.pt")
+    script = tmp_path / "load_in_reference.py"
+    script.write_text(textwrap.dedent('''
+        import sys, torch
+        sys.path.insert(0, %r)
+        from CleanTransformer.models.modeling_bloom import BloomForCausalLM, BloomConfig     # the reference itself
+        assert BloomForCausalLM.__module__ == "CleanTransformer.models.modeling_bloom"
+        e = torch.load(%r, weights_only=False)
+        ck = %r
+        model = BloomForCausalLM(BloomConfig(**e["cfg"]))
+        model.load_state_dict(torch.load(ck + "/pytorch_model.bin"), strict=True)
+        model._tie_weight()
+        model.eval()
+        with torch.no_grad():
+            (logits, _), _ = model(input_ids=e["ids"], attention_mask=e["mask"])
+        err = float((logits - e["logits"]).abs().max() / e["logits"].abs().max())
+        assert err < 1e-5, err
+        # continue the run with the reference's optimizer from optimizer.pt, fed this package's gradients
+        params = dict(model.named_parameters())
+        opt = torch.optim.AdamW(list(model.parameters()), lr=5e-3, weight_decay=0.01)
+        opt.load_state_dict(torch.load(ck + "/optimizer.pt"))
+        for n, p in params.items():
+            p.grad = e["grads"][n].clone()
+        opt.step()
+        worst = max(float((p - e["after"][n]).abs().max() / e["after"][n].abs().max()) for n, p in params.items())
+        assert worst < 1e-5, worst
+        print("REF-CHECKPOINT-OK %%.1e %%.1e" %% (err, worst))
+    ''' % (REF, str(tmp_path / "expect.pt"), str(tmp_path / "checkpoint-3"))))
+    out = _run([str(script)], cwd=str(tmp_path), env_extra={"PYTHONPATH": ""})
+    assert "REF-CHECKPOINT-OK" in out, out
