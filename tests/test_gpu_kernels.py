@@ -465,7 +465,8 @@ def test_kv_cache_append_matches_concat():
 
 
 @pytest.mark.skipif(not os.environ.get("CT_TEST_EXPERIMENTAL"),
-                    reason="row statistics in the logits GEMM were written after round 1's GPU budget was spent")
+                    reason="opt-in (CT_TEST_EXPERIMENTAL=1); the same path runs at the full 8192 x 250880 shape in "
+                           "test_gpu_parity_shapes.py::test_config2_...[fused_lm_stats]")
 @pytest.mark.parametrize("M,V,K", [(512, 1024, 256), (640, 2080, 320), (1024, 250880 // 8, 128)])
 def test_lm_head_row_stats_and_streaming_cross_entropy(M, V, K):
     """The logits GEMM's per-row softmax statistics reproduce logsumexp of the STORED bf16 logits, and the one-pass loss

@@ -305,7 +305,8 @@ def test_bloom_medium_training_step_vs_autocast_oracle():
 
 
 @pytest.mark.skipif(not __import__("os").environ.get("CT_TEST_EXPERIMENTAL"),
-                    reason="graphs.GraphedTrainStep was written after round 1's GPU budget was spent: opt-in until it has run")
+                    reason="opt-in (CT_TEST_EXPERIMENTAL=1): green on the GPU at visit r02l (profiles/r02l_optin_tests.log); the default "
+                           "bench replays this graph every step and tools/ddp_check.py compares graphed vs eager DDP steps")
 def test_graphed_train_step_matches_eager_step(golden):
     """Forward + loss + backward replayed from one CUDA graph == the same step launched kernel by kernel: loss,
     every gradient and the parameters after two AdamW steps (atomics in split-K / dQ / embedding scatter make the
@@ -349,7 +350,8 @@ def test_graphed_train_step_matches_eager_step(golden):
 
 
 @pytest.mark.skipif(not __import__("os").environ.get("CT_TEST_EXPERIMENTAL"),
-                    reason="LMHeadLossFn (fused LM-head statistics) was written after round 1's GPU budget was spent")
+                    reason="opt-in (CT_TEST_EXPERIMENTAL=1): green on the GPU at visit r02l (profiles/r02l_optin_tests.log); the "
+                           "full-shape case runs in test_gpu_parity_shapes.py[fused_lm_stats]")
 def test_fused_lm_head_statistics_match_the_two_kernel_path():
     """BloomForCausalLM with the fused LM-head loss node == the default Linear + cross-entropy nodes: loss, logits and
     every gradient (a shape the statistics epilogue accepts: 512 tokens, 1024-entry vocabulary)."""
