@@ -6,8 +6,11 @@ for beam_size == 1. The loop itself is host-side control flow (ke
 model call inside it runs on the sm_100a kernels. Loop semantics follow generation_util.py:57-119:
 only the new tokens are fed once a cache exists, finished rows emit pad_id, the mask grows by
 repeating its last column, and the loop ends when `step > max_gen_len + prompt_len` — i.e. it emits
-max_gen_len + 2 tokens, exactly like the reference. Beam search (generation_util.py:207-290) is out
-of scope for this tier.
+max_gen_len + 2 tokens, exactly like the reference. The no-repeat-ngram processor (logits_processor.py:11-32; what
+examples/inference_bloom.py:93 configures) is one vectorised mask per step, and beam search
+(generation_util.py:121-290; examples/inference_gpt2.py:64) is reproduced with its bookkeeping on the host — one small
+read-back per step instead of the reference's `.item()` per candidate; both run the host loop (their next step
+depends on the generated history), every model call inside it on the sm_100a kernels.
 
 Decoding on a CUDA model in eval mode — greedy (`do_sample=False`) or sampling (the reference's default: temperature,
 top-k, top-p, multinomial) — replays every q_len = 1 step from ONE captured CUDA graph (BASELINE.json
@@ -64,6 +67,21 @@ def _filter_top_p(scores, top_p, min_keep=1):
     return scores.masked_fill(remove, float("-inf"))
 
 
+def _ban_repeated_ngrams(input_ids, scores, n):
+    """logits_processor.py:11-32 (NoRepeatNGramLogitsProcessor): a token that would complete an n-gram already present
+    in the row (padding included, like the reference) gets -inf. No host loop: every window of the row is compared
+    with its last n-1 tokens at once."""
+    bsz, cur = input_ids.shape
+    if cur < n:
+        return scores
+    windows = input_ids.unfold(1, n, 1)                              # [bsz, cur-n+1, n]
+    tail = input_ids[:, cur - n + 1:]                                # the n-1 tokens the next one would follow
+    hit = (windows[:, :, :-1] == tail[:, None, :]).all(dim=-1)       # [bsz, cur-n+1]
+    banned = torch.zeros(scores.shape, dtype=torch.int32, device=scores.device)
+    banned.scatter_add_(1, windows[:, :, -1], hit.to(torch.int32))
+    return scores.masked_fill(banned > 0, float("-inf"))
+
+
 DECODE_PLAN_CACHE = [os.environ.get("CT_DECODE_CACHE", "1") != "0"]  # keep the captured step between generate() calls
 
 
@@ -100,23 +118,23 @@ class GenerationMixin:
     def generate(self, input_ids, attention_mask=None, position_ids=None, segment_ids=None,
                  generation_configs={}, steamers=None):
         cfg = generation_configs
-        if cfg.get("beam_size", 1) != 1:
-            raise NotImplementedError("beam search is outside the accelerated hot path (see DESIGN.md)")
-        if cfg.get("no_repeat_ngram_size", 0) > 1:
-            raise NotImplementedError("no_repeat_ngram processor is not part of the hot path")
         end_ids = cfg.get("end_ids", None)
         if isinstance(end_ids, int):
             end_ids = [end_ids]
         end_t = torch.tensor(list(end_ids), device=input_ids.device) if end_ids is not None else None
-        return self._greedy_search(input_ids, attention_mask, position_ids, segment_ids, end_t,
-                                   max_gen_len=cfg.get("max_gen_len", 100), pad_id=cfg.get("pad_id", 0),
-                                   do_sample=cfg.get("do_sample", True), temperature=cfg.get("temperature", 1.0),
-                                   top_k=cfg.get("top_k", 10), top_p=cfg.get("top_p", 0.8), steamers=steamers)
+        common = dict(max_gen_len=cfg.get("max_gen_len", 100), pad_id=cfg.get("pad_id", 0),
+                      do_sample=cfg.get("do_sample", True), temperature=cfg.get("temperature", 1.0),
+                      top_k=cfg.get("top_k", 10), top_p=cfg.get("top_p", 0.8), steamers=steamers,
+                      no_repeat_ngram_size=cfg.get("no_repeat_ngram_size", 0))
+        if cfg.get("beam_size", 1) == 1:
+            return self._greedy_search(input_ids, attention_mask, position_ids, segment_ids, end_t, **common)
+        return self._beam_search(input_ids, attention_mask, position_ids, segment_ids, end_t,
+                                 beam_size=cfg["beam_size"], early_stop=cfg.get("early_stop", True), **common)
 
     @torch.no_grad()
     def _greedy_search(self, input_ids, attention_mask, position_ids, segment_ids, end_ids_tensor,
                        max_gen_len, pad_id, do_sample=False, temperature=1.0, top_k=0, top_p=1.0,
-                       steamers=None):
+                       steamers=None, no_repeat_ngram_size=0):
         bsz, prompt_len = input_ids.shape
         limit = max_gen_len + prompt_len
         sampler = _make_sampler(temperature, top_k, top_p) if do_sample else None
@@ -124,6 +142,7 @@ class GenerationMixin:
                 and attention_mask is not None and getattr(self, "_ct_graph_decode", False) and self._decode_graph_ok()
                 and os.environ.get("CT_DECODE_GRAPH", "1") != "0" and max_gen_len >= 1
                 and not self.training  # (train mode may have dropout active: its mask counter is host state)
+                and no_repeat_ngram_size <= 1  # (the banned set depends on the generated history: host loop)
                 and bool((attention_mask[:, -1] != 0).all())):
             return self._graphed_greedy(input_ids, attention_mask, end_ids_tensor, max_gen_len, pad_id, sampler)
         caches = [None] * self.config.n_layer
@@ -138,6 +157,8 @@ class GenerationMixin:
                 kwargs["segment_ids"] = segment_ids[:, fed:]
             outputs, caches = self(input_ids[:, fed:], **kwargs)
             scores = outputs[0][:, -1, :]
+            if no_repeat_ngram_size > 1:
+                scores = _ban_repeated_ngrams(input_ids, scores, no_repeat_ngram_size)
             if do_sample:
                 nxt = sampler(scores)
             else:
@@ -162,6 +183,133 @@ class GenerationMixin:
             if alive.max() == 0 or fed > limit:
                 break
         return input_ids.view(bsz, 1, -1)
+
+    @torch.no_grad()
+    def _beam_search(self, input_ids, attention_mask, position_ids, segment_ids, end_ids_tensor, max_gen_len, pad_id,
+                     beam_size, early_stop=True, do_sample=False, temperature=1.0, top_k=0, top_p=1.0, steamers=None,
+                     no_repeat_ngram_size=0, length_penalty=1.0):
+        """generation_util.py:121-290, behaviour for behaviour: every row is expanded to `beam_size` beams (only beam 0
+        is live at the first step), 2 x beam_size continuations are drawn per row from the joint beam x vocabulary
+        scores (arg-top-k, or the logits wrappers + multinomial without replacement when sampling: the wrappers then act
+        on the JOINT distribution and the beam scores enter multiplied by the temperature), the first beam_size of
+        them are examined: an end id closes a candidate (score = log-probability / length ** length_penalty; the
+        beam_size best are kept), anything else fills the next live slot — slots that stay empty keep beam 0 / token 0
+        / score 0, as in the reference. A row is done after beam_size candidates (early_stop) or once its worst kept
+        candidate beats the best score still reachable; done rows emit pad_id. The loop runs until
+        `step > max_gen_len + prompt_len` (it does not stop early) and returns the LIVE beams
+        [bsz, beam_size, prompt + max_gen_len + 2]. Like the reference it needs end ids."""
+        if end_ids_tensor is None:
+            raise TypeError("beam search needs generation_configs['end_ids'] (the reference tests every candidate "
+                            "against them, generation_util.py:140)")
+        bsz, prompt_len = input_ids.shape
+        limit = max_gen_len + prompt_len
+        dev = input_ids.device
+        B = beam_size
+
+        def spread(t):
+            return None if t is None else t.repeat_interleave(B, dim=0)
+
+        input_ids, position_ids, attention_mask, segment_ids = (spread(input_ids), spread(position_ids),
+                                                                spread(attention_mask), spread(segment_ids))
+        beam_scores = torch.zeros(bsz, B, device=dev)
+        beam_scores[:, 1:] = -1e9
+        ends = set(int(e) for e in end_ids_tensor.reshape(-1).tolist())
+        rows = [dict(done=False, worst=torch.tensor(1e9), kept=[]) for _ in range(bsz)]   # kept: candidate scores
+        caches = [None] * self.config.n_layer
+        callbacks = [] if steamers is None else (steamers if isinstance(steamers, list) else [steamers])
+        fed = 0
+        while True:
+            kwargs = dict(attention_mask=attention_mask, k_v_pasts=caches)
+            if position_ids is not None:
+                kwargs["position_ids"] = position_ids[:, fed:]
+            if segment_ids is not None:
+                kwargs["segment_ids"] = segment_ids[:, fed:]
+            outputs, caches = self(input_ids[:, fed:], **kwargs)
+            scores = outputs[0][:, -1, :].float()
+            if no_repeat_ngram_size > 1:
+                scores = _ban_repeated_ngrams(input_ids, scores.view(bsz * B, -1), no_repeat_ngram_size)
+            # -- the 2B best continuations of every row (generation_util.py:183-205)
+            V = scores.shape[-1]
+            joint = torch.log_softmax(scores, dim=-1) + \
+                beam_scores.view(-1, 1) * (temperature if do_sample else 1.0)
+            joint = joint.view(bsz, B * V)
+            if do_sample:
+                if temperature != 1.0:
+                    joint = _temperature(joint, temperature)
+                if top_k > 0:
+                    joint = _filter_top_k(joint, top_k)
+                if top_p < 1.0:
+                    joint = _filter_top_p(joint, top_p)
+                drawn = torch.multinomial(torch.softmax(joint, dim=-1), num_samples=2 * B)
+                cand_scores, order = torch.sort(torch.gather(joint, -1, drawn), descending=True, dim=1)
+                drawn = torch.gather(drawn, -1, order)
+            else:
+                cand_scores, drawn = joint.topk(2 * B, dim=1, largest=True, sorted=True)
+            from_beam = torch.div(drawn, V, rounding_mode="floor")
+            tokens = drawn % V
+            # -- bookkeeping on the host (generation_util.py:121-181): one read-back per step
+            h_beam, h_tok, h_score = from_beam.cpu(), tokens.cpu(), cand_scores.float().cpu()
+            cur_len = input_ids.shape[-1]
+            new_beam = torch.zeros(bsz, B, dtype=from_beam.dtype)
+            new_tok = torch.zeros(bsz, B, dtype=tokens.dtype)
+            new_score = torch.zeros(bsz, B, dtype=cand_scores.dtype)
+            for r, row in enumerate(rows):
+                if row["done"]:
+                    new_tok[r, :] = pad_id
+                    continue
+                live = 0
+                for c in range(B):
+                    if int(h_tok[r, c]) in ends:
+                        sc = h_score[r, c] / (cur_len ** length_penalty)
+                        row["kept"].append(sc)
+                        if len(row["kept"]) > B:
+                            ranked = sorted((float(v), i) for i, v in enumerate(row["kept"]))
+                            del row["kept"][ranked[0][1]]
+                            row["worst"] = torch.tensor(ranked[1][0])
+                        else:
+                            row["worst"] = torch.minimum(sc, row["worst"])
+                    else:
+                        new_beam[r, live], new_tok[r, live], new_score[r, live] = h_beam[r, c], h_tok[r, c], h_score[r, c]
+                        live += 1
+                    if live >= B:
+                        break
+                if len(row["kept"]) >= B:
+                    if early_stop:
+                        row["done"] = True
+                        continue
+                    reachable = float(h_score[r].max()) / ((cur_len + 1) ** length_penalty)
+                    if float(row["worst"]) > reachable:
+                        row["done"] = True
+            from_beam, tokens, beam_scores = new_beam.to(dev), new_tok.to(dev), new_score.to(dev)
+
+            # -- the chosen beams become the next inputs; their caches follow them
+            def follow(value, how):
+                if value is None:
+                    return None
+                value = value.view(bsz, B, -1)
+                value = value.gather(1, from_beam[:, :, None].expand_as(value)).view(bsz * B, -1)
+                if how == "token":
+                    return torch.cat([value, tokens.view(-1)[:, None]], dim=-1)
+                if how == "position":
+                    return torch.cat([value, value[:, -1:] + 1], dim=-1)
+                return torch.cat([value, value[:, -1:]], dim=-1)
+
+            input_ids = follow(input_ids, "token")
+            position_ids = follow(position_ids, "position")
+            attention_mask = follow(attention_mask, "same")
+            segment_ids = follow(segment_ids, "same")
+            flat = (from_beam + torch.arange(bsz, device=dev)[:, None] * B).view(-1)
+            caches = [tuple(t.index_select(0, flat) for t in layer) for layer in caches]
+            stop = False
+            for cb in callbacks:
+                if callable(cb) and cb(input_ids.view(bsz, B, -1)):
+                    stop = True
+            if stop:
+                break
+            fed = input_ids.shape[1] - 1
+            if fed > limit:
+                break
+        return input_ids.view(bsz, B, -1)
 
     @torch.no_grad()
     def _graphed_greedy(self, input_ids, attention_mask, end_ids_tensor, max_gen_len, pad_id, sampler=None):

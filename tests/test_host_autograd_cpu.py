@@ -1150,3 +1150,24 @@ def test_trainer_drives_the_ddp_wrapper_world2_gloo(tmp_path):
         assert torch.equal(x, y)                            # ... and rank 1
     sd = torch.load(str(tmp_path / "checkpoint-3" / "pytorch_model.bin"))
     assert "lm_head.weight" in sd and not any(k.startswith("module.") for k in sd)
+
+
+def test_beam_search_and_no_repeat_ngram_through_the_gpt_and_bloom_mirrors(golden):
+    """examples/inference_gpt2.py:64-69 (beam_size 3, no_repeat_ngram_size 2) and inference_bloom.py:88-94 through the
+    model mirrors and their KV caches: the reference's REAL GPT / Bloom (same weights) produced the expected ids
+    (tests/golden/generation_beam.pt). Beam search re-orders the [b, h, t, d] caches by `index_select`; the next step
+    appends to the re-ordered caches."""
+    from cleantransformer_b200.models import modeling_bloom as mb, modeling_gpt as mg
+    g = golden("generation_beam")
+    with mock_ops.patched():
+        gt = golden("gpt_tiny")
+        cfg = dict(gt["cfg"])
+        gpt = mg.GPTLMHeadModel(mg.GPTConfig(**cfg), version="gpt2").eval()
+        gpt.load_state_dict(gt["gpt2"]["sd"], strict=True)
+        gpt._tie_weights()
+        bloom = _bloom(golden("bloom_tiny")).eval()
+        for name, model in (("gpt2", gpt), ("bloom", bloom)):
+            m = g["models"][name]
+            for case, ref in zip(g["real_cases"], m["outputs"]):
+                out = model.generate(m["ids"].clone(), attention_mask=m["mask"].clone(), generation_configs=dict(case))
+                assert out.shape == ref.shape and torch.equal(out, ref), (name, case)

@@ -85,7 +85,7 @@ def test_greedy_loop_matches_reference_semantics(golden):
     out2 = toy.generate(ids, attention_mask=mask, generation_configs={"beam_size": 1, "do_sample": False, "max_gen_len": 5,
                                                                      "end_ids": int(out[0, 0, 3]), "pad_id": 0})
     assert int(out2[0, 0, 3]) == int(out[0, 0, 3]) and int(out2[0, 0, 4]) == 0
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError):  # like the reference, beam search cannot run without end ids (generation_util.py:140)
         toy.generate(ids, attention_mask=mask, generation_configs={"beam_size": 4})
 
 
@@ -451,3 +451,54 @@ def test_async_checkpointer_snapshots_at_call_time_and_groups_by_storage(tmp_pat
         ck.save({str(tmp_path / "ok.pt"): {"a": torch.ones(1)}})
         ck.wait()
         assert torch.load(str(tmp_path / "ok.pt"))["a"].item() == 1.0
+
+
+def test_no_repeat_ngram_processor_and_beam_search_match_the_real_reference(golden):
+    """The rest of GenerationMixin.generate against outputs of the REFERENCE (tests/golden/generation_beam.pt,
+    tools/make_golden.py): NoRepeatNGramLogitsProcessor (logits_processor.py:11-32; examples/inference_bloom.py:93) on
+    its own and inside the greedy / sampling loop, and beam search (generation_util.py:121-290;
+    examples/inference_gpt2.py:64) — arg-top-k and seeded sampling over the joint beam x vocabulary scores, candidate
+    bookkeeping, early_stop on and off, pad ids for finished rows, beam re-ordering of ids / mask / positions /
+    segments / caches — token ids bit-exact, shapes included."""
+    from cleantransformer_b200.generation import GenerationMixin, _ban_repeated_ngrams
+    g = golden("generation_beam")
+    emb = g["emb"]
+    pr = g["processor"]
+    for n, want in pr["out"].items():
+        assert torch.equal(_ban_repeated_ngrams(pr["ids"], pr["scores"].clone(), n), want), n
+
+    class Cfg:
+        n_layer = 2
+
+    class Toy(GenerationMixin):
+        config = Cfg()
+        training = False
+
+        def __call__(self, ids, attention_mask=None, k_v_pasts=None, **kw):
+            new = []
+            for past in k_v_pasts:
+                run = ids.sum(-1, keepdim=True).float() if past is None else past[0] + ids.sum(-1, keepdim=True).float()
+                new.append((run, -run))
+            n = attention_mask.sum(-1, keepdim=True).float()
+            logits = emb[ids] + 0.01 * n[:, :, None] + 0.003 * torch.sin(new[0][0])[:, :, None] * emb[(ids + 1) % 40]
+            return (logits, logits), new
+
+    class ToyPos(Toy):
+        def __call__(self, ids, attention_mask=None, k_v_pasts=None, position_ids=None, segment_ids=None, **kw):
+            (logits, _), new = Toy.__call__(self, ids, attention_mask=attention_mask, k_v_pasts=k_v_pasts)
+            logits = logits + 0.02 * emb[(position_ids + 2 * segment_ids) % 40]
+            return (logits, logits), new
+
+    assert len(g["cases"]) == 9
+    for cfg, ref in zip(g["cases"], g["outputs"]):
+        torch.manual_seed(g["seed"])
+        out = Toy().generate(g["ids"].clone(), attention_mask=g["mask"].clone(), generation_configs=dict(cfg))
+        assert out.shape == ref.shape and torch.equal(out, ref), cfg
+    torch.manual_seed(g["seed"])
+    out = ToyPos().generate(g["ids"].clone(), attention_mask=g["mask"].clone(), position_ids=g["pos"].clone(),
+                            segment_ids=g["seg"].clone(), generation_configs=dict(g["cases"][g["with_pos_case"]]))
+    assert torch.equal(out, g["with_pos"])
+    seen = []
+    Toy().generate(g["ids"].clone(), attention_mask=g["mask"].clone(), generation_configs=dict(g["cases"][3]),
+                   steamers=lambda ids: seen.append(tuple(ids.shape)) or len(seen) == 2)
+    assert seen == [(3, 3, 5), (3, 3, 6)]            # streamers see [bsz, beam, len] and may stop the loop

@@ -296,6 +296,98 @@ def golden_generation_loop():
     save("generation_loop", {"emb": emb, "ids": ids, "mask": mask, "cases": cases, "outputs": outs, "seed": 123})
 
 
+def golden_generation_beam():
+    """The rest of the reference's GenerationMixin.generate (generation_util.py:16-55): the no-repeat-ngram processor
+    (logits_processor.py:11-32; what examples/inference_bloom.py:93 and inference_gpt2.py:68 configure) in the greedy /
+    sampling loop, and beam search (generation_util.py:121-290; inference_gpt2.py:64 runs beam_size 3) — around a toy
+    model whose logits depend on a per-row cache, so that the beam re-ordering of k_v_pasts matters."""
+    from CleanTransformer.generation.generation_util import GenerationMixin
+    from CleanTransformer.generation.logits_processor import NoRepeatNGramLogitsProcessor
+
+    class Cfg:
+        n_layer = 2
+
+    torch.manual_seed(1)
+    emb = torch.randn(40, 40)
+
+    class Toy(GenerationMixin):
+        config = Cfg()
+
+        def __call__(self, ids, attention_mask=None, k_v_pasts=None, **kw):
+            new = []
+            for past in k_v_pasts:
+                run = ids.sum(-1, keepdim=True).float() if past is None else past[0] + ids.sum(-1, keepdim=True).float()
+                new.append((run, -run))
+            n = attention_mask.sum(-1, keepdim=True).float()
+            logits = emb[ids] + 0.01 * n[:, :, None] + 0.003 * torch.sin(new[0][0])[:, :, None] * emb[(ids + 1) % 40]
+            return (logits, logits), new
+
+    torch.manual_seed(5)
+    proc = {"ids": torch.tensor([[3, 4, 3, 4, 3], [1, 1, 1, 1, 1], [5, 6, 7, 5, 6], [0, 0, 9, 8, 9]]),
+            "scores": torch.randn(4, 12), "out": {}}
+    for n in (2, 3, 6):
+        proc["out"][n] = NoRepeatNGramLogitsProcessor(n)(proc["ids"], proc["scores"].clone())
+    ids = torch.tensor([[0, 0, 5, 7], [0, 3, 4, 9], [1, 2, 3, 4]])
+    mask = torch.tensor([[0, 0, 1, 1], [0, 1, 1, 1], [1, 1, 1, 1]])
+    cases = [dict(beam_size=1, do_sample=False, max_gen_len=12, end_ids=None, pad_id=0, no_repeat_ngram_size=2),
+             dict(beam_size=1, do_sample=False, max_gen_len=12, end_ids=[13], pad_id=0, no_repeat_ngram_size=3),
+             dict(beam_size=1, do_sample=True, max_gen_len=8, end_ids=None, pad_id=0, no_repeat_ngram_size=2,
+                  temperature=0.7, top_k=5, top_p=0.9),
+             dict(beam_size=3, do_sample=False, max_gen_len=6, end_ids=[13, 22], pad_id=0),
+             dict(beam_size=3, do_sample=False, max_gen_len=8, end_ids=[7, 11, 30], pad_id=2, early_stop=False),
+             dict(beam_size=2, do_sample=False, max_gen_len=8, end_ids=[7, 11, 30, 31, 32, 33], pad_id=0,
+                  no_repeat_ngram_size=2),
+             dict(beam_size=4, do_sample=False, max_gen_len=10, end_ids=list(range(0, 40, 3)), pad_id=1),
+             dict(beam_size=3, do_sample=True, max_gen_len=6, end_ids=[13, 22], pad_id=0, temperature=0.7, top_k=5,
+                  top_p=0.9),
+             dict(beam_size=2, do_sample=True, max_gen_len=6, end_ids=[5], pad_id=0, temperature=1.3, top_k=0, top_p=1.0,
+                  no_repeat_ngram_size=2)]
+    outs = []
+    for cfg in cases:
+        torch.manual_seed(321)
+        outs.append(Toy().generate(ids.clone(), attention_mask=mask.clone(), generation_configs=dict(cfg)))
+    pos = torch.tensor([[0, 0, 0, 1], [0, 0, 1, 2], [0, 1, 2, 3]])
+    seg = torch.tensor([[0, 0, 1, 1], [0, 1, 1, 1], [1, 1, 1, 2]])
+
+    class ToyPos(Toy):
+        def __call__(self, ids, attention_mask=None, k_v_pasts=None, position_ids=None, segment_ids=None, **kw):
+            (logits, _), new = Toy.__call__(self, ids, attention_mask=attention_mask, k_v_pasts=k_v_pasts)
+            logits = logits + 0.02 * emb[(position_ids + 2 * segment_ids) % 40]
+            return (logits, logits), new
+
+    torch.manual_seed(321)
+    with_pos = ToyPos().generate(ids.clone(), attention_mask=mask.clone(), position_ids=pos.clone(),
+                                 segment_ids=seg.clone(), generation_configs=dict(cases[3]))
+    # the same callers around the reference's REAL models (the tiny GPT / Bloom of the other fixtures): beam search
+    # re-orders real [b, h, t, d] caches, the processor sees left-padded prompts
+    models = {}
+    gt = torch.load(os.path.join(OUT, "gpt_tiny.pt"), weights_only=False)
+    gcfg = dict(gt["cfg"])
+    gcfg.pop("layer_norm_epsilon", None)
+    gpt = rgpt.GPTLMHeadModel(rgpt.GPTConfig(**gcfg), version="gpt2").eval()
+    gpt.load_state_dict(gt["gpt2"]["sd"], strict=True)
+    gpt._tie_weights()
+    bt = torch.load(os.path.join(OUT, "bloom_tiny.pt"), weights_only=False)
+    bloom = rbloom.BloomForCausalLM(rbloom.BloomConfig(**bt["cfg"])).eval()
+    bloom.load_state_dict(bt["sd"], strict=True)
+    bloom._tie_weight()
+    real_cases = [dict(beam_size=3, do_sample=False, max_gen_len=8, end_ids=[5, 17, 40, 63, 88], pad_id=0,
+                       no_repeat_ngram_size=2),
+                  dict(beam_size=2, do_sample=False, max_gen_len=6, end_ids=list(range(0, 100, 4)), pad_id=0,
+                       early_stop=False),
+                  dict(beam_size=1, do_sample=False, max_gen_len=10, end_ids=None, pad_id=0, no_repeat_ngram_size=2)]
+    with torch.no_grad():
+        models["gpt2"] = {"ids": gt["gpt2"]["ids"], "mask": gt["gpt2"]["mask"], "outputs": [
+            gpt.generate(gt["gpt2"]["ids"].clone(), attention_mask=gt["gpt2"]["mask"].clone(),
+                         generation_configs=dict(c)) for c in real_cases]}
+        bids, bmask = bt["ids"][:, :8].clone(), torch.ones_like(bt["ids"][:, :8])
+        models["bloom"] = {"ids": bids, "mask": bmask, "outputs": [
+            bloom.generate(bids.clone(), attention_mask=bmask.clone(), generation_configs=dict(c)) for c in real_cases]}
+    save("generation_beam", {"emb": emb, "ids": ids, "mask": mask, "cases": cases, "outputs": outs, "seed": 321,
+                             "processor": proc, "pos": pos, "seg": seg, "with_pos_case": 3, "with_pos": with_pos,
+                             "real_cases": real_cases, "models": models})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     if len(sys.argv) > 1:  # regenerate only the named fixtures: python tools/make_golden.py sampling
@@ -311,3 +403,4 @@ if __name__ == "__main__":
     golden_optim()
     golden_sampling()
     golden_generation_loop()
+    golden_generation_beam()
