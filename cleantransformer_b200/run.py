@@ -19,7 +19,8 @@ What `install()` does before the script is executed with runpy (SURVEY.md §0 D6
     written behind the step loop by `checkpoint.AsyncCheckpointer`; files are complete at interpreter exit at the
     latest (opt-in: a script that reads its own checkpoint back right away must keep the blocking save);
   * the default device becomes the local GPU, because the inference examples build their inputs with
-    bare `torch.tensor(...)` (examples/inference_bert.py:71-73) and there is no CPU fallback here.
+    bare `torch.tensor(...)` (examples/inference_bert.py:71-73) and there is no CPU fallback here; `Tensor.numpy()`
+    of a CUDA tensor copies to the host first, because the same scripts print `generated.numpy().tolist()`.
 Nothing is copied from or written to the reference tree; the script's directory layout
 (`sys.path.append('.')`, `from examples.inference_bloom import ...`) works as it does upstream when the
 launcher is started from the reference root.
@@ -97,6 +98,16 @@ def install(swap_optimizer=True, swap_ddp=True, default_device=True, async_save=
         torch.cuda.set_device(local)
         torch.set_default_device("cuda:%d" % local)
         _installed["default_device"] = "cuda:%d" % local
+        # ... and the same scripts hand their results to numpy (`generated_sequence.numpy().tolist()`,
+        # examples/inference_bloom.py:100, inference_gpt2.py:76): tensors that became CUDA tensors only because of the
+        # line above are brought back first
+        _numpy = torch.Tensor.numpy
+        _installed["Tensor.numpy"] = _numpy
+
+        def numpy(self, *args, **kwargs):
+            return _numpy(self.cpu() if self.is_cuda else self, *args, **kwargs)
+
+        torch.Tensor.numpy = numpy
     return _installed
 
 

@@ -80,8 +80,29 @@ def test_reference_inference_bloom_loader_runs_unchanged(tmp_path):
         assert len(model.bloom.blocks) == 2 and model.bloom.blocks[0].self_attention.num_heads == 4
         sd = torch.load(%r)
         assert torch.equal(model.bloom.blocks[1].mlp.dense_4h_to_h.weight, sd["transformer.h.1.mlp.dense_4h_to_h.weight"])
+        # ... and generates with the example's OWN generation_configs (inference_bloom.py:87-98: sampling with
+        # temperature / top-k / top-p AND no_repeat_ngram_size 2) and gpt2's beam_size 3 (inference_gpt2.py:63-73);
+        # plain-torch stand-ins replace the CUDA kernels here (no GPU in this container)
+        sys.path.insert(0, %r)
+        import mock_ops
+        ids = torch.tensor([[3, 3, 11, 12, 13, 14], [21, 22, 23, 24, 25, 26]])
+        mask = torch.tensor([[0, 0, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1]])       # padding_side='left'
+        cfgs = {"beam_size": 1, "max_gen_len": 12, "end_ids": 2, "pad_id": 3, "early_stop": True,
+                "no_repeat_ngram_size": 2, "do_sample": True, "temperature": 0.8, "top_k": 10, "top_p": 0.8}
+        with mock_ops.patched():
+            torch.manual_seed(0)
+            out = model.generate(input_ids=ids, attention_mask=mask, generation_configs=cfgs)
+            rows = out.numpy().tolist()
+            assert out.shape[:2] == (2, 1) and 7 <= out.shape[2] <= 6 + 12 + 2
+            for row in rows:
+                seq = row[0][6:]
+                grams = [tuple(seq[i:i + 2]) for i in range(len(seq) - 1) if 3 not in seq[i:i + 2]]
+                assert len(grams) == len(set(grams)), seq          # no bigram repeats among the generated tokens
+            beams = model.generate(input_ids=ids, attention_mask=mask, generation_configs=dict(cfgs, beam_size=3))
+            assert beams.shape == (2, 3, 6 + 12 + 2)
         print("REF-LOADER-OK")
-    ''' % (REF, str(tmp_path / "config.json"), str(tmp_path / "pytorch_model.bin"), str(tmp_path / "pytorch_model.bin"))))
+    ''' % (REF, str(tmp_path / "config.json"), str(tmp_path / "pytorch_model.bin"), str(tmp_path / "pytorch_model.bin"),
+           os.path.join(ROOT, "tests"))))
     out = _run(["-m", "cleantransformer_b200.run", "--ct-keep-default-device", str(script)], cwd=str(tmp_path))
     assert "REF-LOADER-OK" in out
 
