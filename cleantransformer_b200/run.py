@@ -98,17 +98,38 @@ def install(swap_optimizer=True, swap_ddp=True, default_device=True, async_save=
         torch.cuda.set_device(local)
         torch.set_default_device("cuda:%d" % local)
         _installed["default_device"] = "cuda:%d" % local
-        # ... and the same scripts hand their results to numpy (`generated_sequence.numpy().tolist()`,
-        # examples/inference_bloom.py:100, inference_gpt2.py:76): tensors that became CUDA tensors only because of the
-        # line above are brought back first
-        _numpy = torch.Tensor.numpy
-        _installed["Tensor.numpy"] = _numpy
-
-        def numpy(self, *args, **kwargs):
-            return _numpy(self.cpu() if self.is_cuda else self, *args, **kwargs)
-
-        torch.Tensor.numpy = numpy
+        _patch_for_default_device(torch)
     return _installed
+
+
+def _patch_for_default_device(torch):
+    """What else has to give once a non-CPU default device is set behind a script written for the CPU:
+      * `generated_sequence.numpy().tolist()` (examples/inference_bloom.py:100, inference_gpt2.py:76): tensors that
+        became device tensors only because of the default device are brought back first;
+      * DataLoader shuffling (examples/ft_bloom.py:58 `shuffle=True`, ft_bloom_DDP.py:71 DistributedSampler): the
+        samplers call `torch.randperm(n, generator=<CPU generator>)`, which the default device would turn into a
+        device-side call with a CPU generator — an error. A factory call that is handed a CPU generator stays on
+        the CPU."""
+    _numpy = torch.Tensor.numpy
+    _installed["Tensor.numpy"] = _numpy
+
+    def numpy(self, *args, **kwargs):
+        return _numpy(self if self.device.type == "cpu" else self.cpu(), *args, **kwargs)
+
+    torch.Tensor.numpy = numpy
+
+    def keep_cpu_generators_on_the_cpu(fn):
+        def wrapper(*args, **kwargs):
+            g = kwargs.get("generator")
+            if g is not None and g.device.type == "cpu" and kwargs.get("device") is None:
+                kwargs["device"] = "cpu"
+            return fn(*args, **kwargs)
+        wrapper.__wrapped__ = fn
+        return wrapper
+
+    for name in ("randperm", "randint", "rand", "randn"):
+        _installed["torch." + name] = getattr(torch, name)
+        setattr(torch, name, keep_cpu_generators_on_the_cpu(getattr(torch, name)))
 
 
 def main(argv=None):

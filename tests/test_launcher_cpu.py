@@ -222,3 +222,39 @@ def test_checkpoints_load_into_the_reference_classes(tmp_path):
     ''' % (REF, str(tmp_path / "expect.pt"), str(tmp_path / "checkpoint-3"))))
     out = _run([str(script)], cwd=str(tmp_path), env_extra={"PYTHONPATH": ""})
     assert "REF-CHECKPOINT-OK" in out, out
+
+
+def test_launcher_default_device_patches_keep_cpu_scripts_working(tmp_path):
+    """With the GPU as default device (what install() does for the examples' bare `torch.tensor(...)` inputs) a script
+    written for the CPU still shuffles its DataLoader (examples/ft_bloom.py:58, ft_bloom_DDP.py:71: the samplers hand a
+    CPU generator to torch.randperm) and still calls `.numpy()` on its results (inference_bloom.py:100). Simulated
+    here with the `meta` device standing in for the GPU."""
+    script = tmp_path / "probe.py"
+    script.write_text(textwrap.dedent('''
+        import torch
+        from torch.utils.data import RandomSampler
+        from torch.utils.data.distributed import DistributedSampler
+        from cleantransformer_b200 import run
+        data = list(range(10))
+        torch.set_default_device("meta")
+        # (the samplers are driven directly with an explicit generator: DataLoader itself also draws a base seed with
+        # `.item()`, which the meta stand-in cannot do and a real GPU can)
+        try:
+            list(RandomSampler(data, generator=torch.Generator().manual_seed(0)))
+            broken = False
+        except Exception:
+            broken = True
+        assert broken, "torch handles CPU generators under a device default now: the patch can go"
+        run._patch_for_default_device(torch)
+        assert sorted(RandomSampler(data, generator=torch.Generator().manual_seed(0))) == data
+        ds = DistributedSampler(data, num_replicas=2, rank=1, shuffle=True, seed=3)
+        assert len(list(ds)) == 5
+        g = torch.Generator().manual_seed(1)
+        assert torch.randint(0, 5, (3,), generator=g).device.type == "cpu"
+        assert torch.randn(3).device.type == "meta"                  # everything else follows the default device
+        torch.set_default_device("cpu")
+        assert torch.arange(3.).numpy().tolist() == [0.0, 1.0, 2.0]
+        print("PATCH-OK")
+    '''))
+    out = _run([str(script)], cwd=str(tmp_path))
+    assert "PATCH-OK" in out
