@@ -306,3 +306,63 @@ def test_reference_ft_bloom_train_function_runs_unchanged(tmp_path):
     ''' % (REF, os.path.join(ROOT, "tests"), str(tmp_path / "ckpt"), str(tmp_path / "ckpt"))))
     out = _run(["-m", "cleantransformer_b200.run", "--ct-keep-default-device", "--ct-async-save", str(script)], cwd=REF)
     assert "REF-TRAIN-OK" in out, out
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "examples")), reason="reference checkout not present")
+def test_reference_ft_bloom_ddp_train_function_runs_unchanged_on_two_ranks(tmp_path):
+    """examples/ft_bloom_DDP.py `train()` (:77-156), unmodified, under torchrun with two gloo ranks: its
+    `DDP(model, device_ids=[local_rank])` is this package's wrapper (rank 0's parameters are broadcast, gradients are
+    averaged bucket by bucket), its AdamW the flat-arena one, its rank-0 `torch.save(model.state_dict())` keeps the
+    `module.` prefix. Replicas end identical although every rank saw its own batches."""
+    import socket
+    script = tmp_path / "use_ref_ddp_train.py"
+    script.write_text(textwrap.dedent('''
+        import io, contextlib, os, sys, torch
+        import torch.distributed as dist
+        sys.path.insert(0, %r)
+        sys.path.insert(0, %r)
+        import mock_ops
+        import examples.ft_bloom_DDP as ref                                 # the reference's own file
+        from CleanTransformer.models.modeling_bloom import BloomForCausalLM, BloomConfig
+        assert ref.DDP.__module__ == "cleantransformer_b200.ddp" and ref.AdamW.__module__ == "cleantransformer_b200.optimizer"
+        dist.init_process_group("gloo")
+        rank = dist.get_rank()
+        torch.manual_seed(100 + rank)                                       # replicas start DIFFERENT
+        model = BloomForCausalLM(BloomConfig(vocab_size=64, hidden_size=32, n_layer=2, num_attention_heads=4))
+        model._tie_weight()
+        g = torch.Generator().manual_seed(7 + rank)                         # ... and see different data
+        batches = []
+        for _ in range(2):
+            ids = torch.randint(3, 64, (2, 10), generator=g)
+            batches.append({"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": ids.clone()})
+
+        class Sampler:
+            epochs = []
+            def set_epoch(self, e):
+                self.epochs.append(e)
+
+        class Loader:
+            sampler = Sampler()
+            def __iter__(self):
+                return iter([dict(b) for b in batches])
+
+        with mock_ops.patched(), contextlib.redirect_stdout(io.StringIO()):
+            ref.train(model, Loader(), epoches=2, save_interval=4, print_interval=1, save_dir=%r)
+        assert Loader.sampler.epochs == [0, 1]
+        flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        both = [torch.empty_like(flat) for _ in range(2)]
+        dist.all_gather(both, flat)
+        assert torch.equal(both[0], both[1])                                # identical replicas after 4 steps
+        dist.barrier()
+        if rank == 0:
+            sd = torch.load(os.path.join(%r, "model_step_4.pt"))
+            assert all(k.startswith("module.") for k in sd) and "module.lm_head.weight" in sd
+            assert torch.equal(sd["module.bloom.ln_f.weight"], model.bloom.ln_f.weight.detach())
+            print("REF-DDP-TRAIN-OK")
+        dist.destroy_process_group()
+    ''' % (REF, os.path.join(ROOT, "tests"), str(tmp_path / "ckpt"), str(tmp_path / "ckpt"))))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = _run(["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                "--master-port", str(port), "-m", "cleantransformer_b200.run", "--ct-keep-default-device", str(script)],
+               cwd=REF)
+    assert "REF-DDP-TRAIN-OK" in out, out
