@@ -366,3 +366,66 @@ def test_reference_ft_bloom_ddp_train_function_runs_unchanged_on_two_ranks(tmp_p
                 "--master-port", str(port), "-m", "cleantransformer_b200.run", "--ct-keep-default-device", str(script)],
                cwd=REF)
     assert "REF-DDP-TRAIN-OK" in out, out
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "examples")), reason="reference checkout not present")
+def test_reference_gpt2_and_bert_loaders_run_unchanged_and_agree_with_huggingface(tmp_path):
+    """examples/inference_gpt2.py and inference_bert.py `load_config` / `load_model` (their HF -> reference key maps,
+    :14-44 / :14-52), unmodified, build THIS package's GPTLMHeadModel / BertForSequenceClassification from random-init
+    HuggingFace checkpoints (strict load); the logits then agree with the HuggingFace models' own (the independent
+    cross-oracle of SURVEY §8 c5; plain-torch stand-ins for the kernels, fp32)."""
+    transformers = pytest.importorskip("transformers")
+    torch.manual_seed(0)
+    gcfg = transformers.GPT2Config(vocab_size=101, n_embd=48, n_layer=2, n_head=4, n_positions=64, n_ctx=64,
+                                   resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    hf_gpt = transformers.GPT2LMHeadModel(gcfg).eval()
+    gsd = {k: v.clone() for k, v in hf_gpt.transformer.state_dict().items()}
+    for i in range(2):   # the causal buffer is part of the reference's state_dict (modeling_gpt.py:57-58)
+        gsd["h.%d.attn.bias" % i] = torch.tril(torch.ones(64, 64)).view(1, 1, 64, 64)
+    os.makedirs(tmp_path / "gpt2")
+    torch.save(gsd, tmp_path / "gpt2" / "pytorch_model.bin")
+    (tmp_path / "gpt2" / "config.json").write_text(json.dumps(
+        dict(vocab_size=101, n_embd=48, n_layer=2, n_head=4, n_positions=64, n_ctx=64, afn="gelu_new",
+             layer_norm_epsilon=1e-5)))
+    ids = torch.randint(1, 101, (2, 9))
+    with torch.no_grad():
+        g_logits = hf_gpt(input_ids=ids).logits
+    bcfg = transformers.BertConfig(vocab_size=120, hidden_size=32, num_hidden_layers=12, num_attention_heads=4,
+                                   intermediate_size=64, max_position_embeddings=40, num_labels=5,
+                                   hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    hf_bert = transformers.BertForSequenceClassification(bcfg).eval()
+    os.makedirs(tmp_path / "bert")
+    torch.save(hf_bert.state_dict(), tmp_path / "bert" / "pytorch_model.bin")
+    (tmp_path / "bert" / "config.json").write_text(json.dumps(
+        dict(vocab_size=120, hidden_size=32, num_hidden_layers=12, num_attention_heads=4, intermediate_size=64,
+             max_position_embeddings=40, num_labels=5, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)))
+    bids = torch.randint(1, 120, (3, 11))
+    bmask = torch.ones_like(bids)
+    bmask[1, 7:] = 0
+    with torch.no_grad():
+        b_logits = hf_bert(input_ids=bids, attention_mask=bmask, token_type_ids=torch.zeros_like(bids)).logits
+    torch.save({"ids": ids, "g_logits": g_logits, "bids": bids, "bmask": bmask, "b_logits": b_logits},
+               tmp_path / "expect.pt")
+    script = tmp_path / "use_ref_loaders.py"
+    script.write_text(textwrap.dedent('''
+        import sys, torch
+        sys.path.insert(0, %r)
+        sys.path.insert(0, %r)
+        import mock_ops
+        from examples import inference_gpt2, inference_bert                 # the reference's own files
+        e = torch.load(%r)
+        d = %r
+        gpt = inference_gpt2.load_model(inference_gpt2.load_config(d + "/gpt2/config.json"), d + "/gpt2/pytorch_model.bin")
+        bert = inference_bert.load_model(inference_bert.load_config(d + "/bert/config.json"), d + "/bert/pytorch_model.bin").eval()
+        assert type(gpt).__module__ == "cleantransformer_b200.models.modeling_gpt" and not gpt.training
+        assert type(bert).__module__ == "cleantransformer_b200.models.modeling_bert"
+        with mock_ops.patched(), torch.no_grad():
+            (logits, _), _ = gpt(e["ids"], attention_mask=torch.ones_like(e["ids"]))
+            b_logits = bert(e["bids"], e["bmask"], torch.zeros_like(e["bids"]), torch.arange(e["bids"].shape[1]))
+        ge = float((logits - e["g_logits"]).abs().max() / e["g_logits"].abs().max())
+        be = float((b_logits - e["b_logits"]).abs().max() / e["b_logits"].abs().max())
+        assert ge < 1e-5 and be < 1e-5, (ge, be)
+        print("REF-LOADERS-OK %%.1e %%.1e" %% (ge, be))
+    ''' % (REF, os.path.join(ROOT, "tests"), str(tmp_path / "expect.pt"), str(tmp_path))))
+    out = _run(["-m", "cleantransformer_b200.run", "--ct-keep-default-device", str(script)], cwd=REF)
+    assert "REF-LOADERS-OK" in out, out
