@@ -214,7 +214,7 @@ class GenerationMixin:
         beam_scores = torch.zeros(bsz, B, device=dev)
         beam_scores[:, 1:] = -1e9
         ends = set(int(e) for e in end_ids_tensor.reshape(-1).tolist())
-        rows = [dict(done=False, worst=torch.tensor(1e9), kept=[]) for _ in range(bsz)]   # kept: candidate scores
+        rows = [dict(done=False, worst=torch.tensor(1e9, device="cpu"), kept=[]) for _ in range(bsz)]   # kept: candidate scores
         caches = [None] * self.config.n_layer
         callbacks = [] if steamers is None else (steamers if isinstance(steamers, list) else [steamers])
         fed = 0
@@ -250,9 +250,9 @@ class GenerationMixin:
             # -- bookkeeping on the host (generation_util.py:121-181): one read-back per step
             h_beam, h_tok, h_score = from_beam.cpu(), tokens.cpu(), cand_scores.float().cpu()
             cur_len = input_ids.shape[-1]
-            new_beam = torch.zeros(bsz, B, dtype=from_beam.dtype)
-            new_tok = torch.zeros(bsz, B, dtype=tokens.dtype)
-            new_score = torch.zeros(bsz, B, dtype=cand_scores.dtype)
+            new_beam = torch.zeros(bsz, B, dtype=from_beam.dtype, device="cpu")   # (explicit: run.py makes the GPU the default)
+            new_tok = torch.zeros(bsz, B, dtype=tokens.dtype, device="cpu")
+            new_score = torch.zeros(bsz, B, dtype=cand_scores.dtype, device="cpu")
             for r, row in enumerate(rows):
                 if row["done"]:
                     new_tok[r, :] = pad_id
@@ -265,7 +265,7 @@ class GenerationMixin:
                         if len(row["kept"]) > B:
                             ranked = sorted((float(v), i) for i, v in enumerate(row["kept"]))
                             del row["kept"][ranked[0][1]]
-                            row["worst"] = torch.tensor(ranked[1][0])
+                            row["worst"] = torch.tensor(ranked[1][0], device="cpu")
                         else:
                             row["worst"] = torch.minimum(sc, row["worst"])
                     else:
