@@ -309,11 +309,15 @@ def test_reference_ft_bloom_train_function_runs_unchanged(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "examples")), reason="reference checkout not present")
-def test_reference_ft_bloom_ddp_train_function_runs_unchanged_on_two_ranks(tmp_path):
+@pytest.mark.parametrize("amp", [False, True], ids=["plain", "torch_amp_branch"])
+def test_reference_ft_bloom_ddp_train_function_runs_unchanged_on_two_ranks(tmp_path, amp):
     """examples/ft_bloom_DDP.py `train()` (:77-156), unmodified, under torchrun with two gloo ranks: its
     `DDP(model, device_ids=[local_rank])` is this package's wrapper (rank 0's parameters are broadcast, gradients are
     averaged bucket by bucket), its AdamW the flat-arena one, its rank-0 `torch.save(model.state_dict())` keeps the
-    `module.` prefix. Replicas end identical although every rank saw its own batches."""
+    `module.` prefix. Replicas end identical although every rank saw its own batches. `torch_amp_branch`: the
+    `--use_torch_amp` path (:108-128; GradScaler and autocast disable themselves without CUDA) — the branch that never
+    calls `optimizer.zero_grad()`, so every backward ACCUMULATES into the already averaged gradients and the wrapper
+    reduces the sum again, as torch's reducer does."""
     import socket
     script = tmp_path / "use_ref_ddp_train.py"
     script.write_text(textwrap.dedent('''
@@ -347,7 +351,10 @@ def test_reference_ft_bloom_ddp_train_function_runs_unchanged_on_two_ranks(tmp_p
                 return iter([dict(b) for b in batches])
 
         with mock_ops.patched(), contextlib.redirect_stdout(io.StringIO()):
-            ref.train(model, Loader(), epoches=2, save_interval=4, print_interval=1, save_dir=%r)
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref.train(model, Loader(), epoches=2, save_interval=4, print_interval=1, save_dir=%r, use_torch_amp=%r)
         assert Loader.sampler.epochs == [0, 1]
         flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
         both = [torch.empty_like(flat) for _ in range(2)]
@@ -360,7 +367,7 @@ def test_reference_ft_bloom_ddp_train_function_runs_unchanged_on_two_ranks(tmp_p
             assert torch.equal(sd["module.bloom.ln_f.weight"], model.bloom.ln_f.weight.detach())
             print("REF-DDP-TRAIN-OK")
         dist.destroy_process_group()
-    ''' % (REF, os.path.join(ROOT, "tests"), str(tmp_path / "ckpt"), str(tmp_path / "ckpt"))))
+    ''' % (REF, os.path.join(ROOT, "tests"), str(tmp_path / "ckpt"), amp, str(tmp_path / "ckpt"))))
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     out = _run(["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                 "--master-port", str(port), "-m", "cleantransformer_b200.run", "--ct-keep-default-device", str(script)],
