@@ -289,6 +289,8 @@ class Trainer:
         opt = self.create_optimizer()
         max_steps = self._arg("max_steps")
         epochs = self._arg("num_train_epochs")
+        if len(loader) == 0:
+            raise ValueError("Trainer.train: the training dataloader is empty")
         gas = max(1, int(self._arg("gradient_accumulation_steps")))
         steps_per_epoch = max(1, -(-len(loader) // gas))    # optimizer steps; a short tail of micro-batches still steps
         if max_steps is None or max_steps <= 0:
