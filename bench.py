@@ -483,14 +483,19 @@ class KernelProfiler:
 def recorded_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's largest launch, from the committed ncu
     capture of THIS build (profiles/r02_ncu_traffic.json holds the sha1 of the kernel's source next to the bytes): a
-    number from another build is not reported — null instead."""
+    number from another build is not reported — null instead. `equivalent_sources` lists later sources whose compiled
+    kernel was shown to be the captured one (SASS comparison committed under profiles/)."""
     import hashlib
     path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     try:
         rec = json.load(open(path))[kernel]
         src = os.path.join(ROOT, "cleantransformer_b200", "csrc", rec["source"])
-        if hashlib.sha1(open(src, "rb").read()).hexdigest() == rec["source_sha1"]:
+        sha = hashlib.sha1(open(src, "rb").read()).hexdigest()
+        if sha == rec["source_sha1"]:
             return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"]), rec.get("capture")
+        same = rec.get("equivalent_sources", {}).get(sha)
+        if same:
+            return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"]), "%s; %s" % (rec.get("capture"), same)
     except Exception:  # noqa: BLE001
         pass
     return None, None
