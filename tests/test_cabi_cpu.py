@@ -61,6 +61,18 @@ def test_error_convention_and_no_cpu_fallback():
     assert "null" in _lib.last_error()
     assert lib.ct_layernorm_fwd(None, 0, None, None, None, 0, None, 0, None, None, 1, 1, 1e-5, None) == -1
     assert lib.ct_allreduce_bucket(0, 16, 1.0, 0, 0, None) == -4  # comm not initialised
+    # the fused gather + LayerNorm entry point: shape / pointer / table-order / alignment checks precede any launch
+    f = lib.ct_embedding_layernorm_fwd
+    a = 1 << 12  # any non-null, 16-byte aligned address: it is never dereferenced on these paths
+    assert f(a, a, 10, None, None, 0, None, None, 0, a, a, None, a, 0, None, 0, None, None, -1, 128, 1e-5, None) == -1
+    assert f(None, None, 10, None, None, 0, None, None, 0, a, a, None, a, 0, None, 0, None, None, 4, 128, 1e-5, None) == -1
+    assert f(a, a, 10, None, None, 0, a, a, 5, a, a, None, a, 0, None, 0, None, None, 4, 128, 1e-5, None) == -1
+    assert "in order" in _lib.last_error()
+    assert f(a, a, 10, None, None, 0, None, None, 0, a, a, None, a, 0, None, 0, None, None, 4, 96, 1e-5, None) == -2
+    assert "ct_embedding_fwd + ct_layernorm_fwd" in _lib.last_error()
+    assert f(a, a + 4, 10, None, None, 0, None, None, 0, a, a, None, a, 0, None, 0, None, None, 4, 128, 1e-5, None) == -2
+    assert f(a, a, 10, None, None, 0, None, None, 0, a, a, None, a, 7, None, 0, None, None, 4, 128, 1e-5, None) == -2
+    assert f(a, a, 10, None, None, 0, None, None, 0, a, a, None, a, 0, None, 0, None, None, 0, 128, 1e-5, None) == 0  # empty
     x = torch.randn(4, 8)
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.layernorm_fwd(x, torch.ones(8), torch.zeros(8), 1e-5)
