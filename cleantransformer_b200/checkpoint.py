@@ -14,7 +14,7 @@ rank waiting in its next all-reduce — is idle.
      model + optimizer snapshot is three large copies, not 3 × 293 small ones; tensors that share memory
      (tied tables) stay shared in the file, exactly like `torch.save` of the live objects.
   2. stage "device" (default when HBM has room — 180 GB per GPU does): the ranges are copied device-to-device
-     on the caller's stream (≈ 2 ms for 6.7 GB) into a staging buffer; the training stream may overwrite the
+     on the caller's stream (6.7 GB: about 2 ms of HBM traffic, not timed) into a staging buffer; the training stream may overwrite the
      live tensors right away. A side stream drains the staging buffer into pinned host memory.
      stage "host": the side stream reads the live tensors; `guard()` makes the caller's stream wait for that
      read and must be called before anything overwrites them (the next `optimizer.step()`; forward and
