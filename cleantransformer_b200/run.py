@@ -53,7 +53,11 @@ def install(swap_optimizer=True, swap_ddp=True, default_device=True, async_save=
     for name in _PACKAGES:
         if name not in sys.modules:
             pkg = types.ModuleType(name)
-            pkg.__path__ = []  # a package: sub-module imports go through sys.modules
+            # a package: the mirrored sub-modules come from sys.modules (below); anything this package does not mirror
+            # (CleanTransformer/loss.py, tokenizers.py: outside the hot path) is imported from the reference checkout the
+            # launcher was started in, if there is one
+            here = os.path.join(os.getcwd(), *name.split("."))
+            pkg.__path__ = [here] if os.path.isdir(here) else []
             pkg.__doc__ = "alias package installed by cleantransformer_b200.run"
             sys.modules[name] = pkg
     for alias, target in _ALIASES.items():

@@ -46,6 +46,17 @@ def test_install_aliases_and_swaps(tmp_path):
     '''))
     out = _run(["-m", "cleantransformer_b200.run", "--ct-keep-default-device", str(script), "--flag", "7"])
     assert "PROBE-OK" in out
+    if os.path.isdir(os.path.join(REF, "CleanTransformer")):
+        # started from the reference root (as documented): what is NOT mirrored still imports — from the reference
+        script2 = tmp_path / "probe2.py"
+        script2.write_text(textwrap.dedent('''
+            from CleanTransformer.loss import CrossEntropyLoss                  # reference file (outside the hot path)
+            from CleanTransformer.models.modeling_bloom import BloomForCausalLM  # mirror
+            assert CrossEntropyLoss.__module__ == "CleanTransformer.loss"
+            assert BloomForCausalLM.__module__ == "cleantransformer_b200.models.modeling_bloom"
+            print("PROBE2-OK")
+        '''))
+        assert "PROBE2-OK" in _run(["-m", "cleantransformer_b200.run", "--ct-keep-default-device", str(script2)], cwd=REF)
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "examples")), reason="reference checkout not present")
